@@ -1,0 +1,488 @@
+"""HydPy objects  →  SoA bundles, and results  →  HydPy objects.
+
+This is the staging layer that replaces the reference's per-step `load_data`/`save_data`
+(ref: hydpy/cythons/modelutils.py:1080-1167) and the pointer exchange between nodes and models
+(ref: hydpy/core/modeltools.py:2550-2584, hydpy/cythons/pointerutils.pyx) for the covered models:
+
+* values are read from `model.parameters.<group>.<name>.value` after `update_parameters()` has run, i.e. the
+  reference's internal, simulation-step related values;
+* conditions come from `model.sequences.states.*` and `rconcmodel.sequences.logs.quh`;
+* forcing comes from `inputs.<name>.series` (must be in RAM — NetCDF just-in-time reading is refused exactly like
+  the reference's threaded mode does, ref: hydpy/core/hydpytools.py:3007-3015).
+
+Nothing here imports `hydpy`: all objects are duck-typed, so the module also works against look-alike objects.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Any, Iterable
+
+import numpy as np
+
+from . import layout
+from .abi import LandBundle, LandStates, RiverBundle
+
+LAND_MODELS = ("hland_96",)
+RIVER_MODELS = ("musk_classic",)
+
+_ZONE_CONTROL = (
+    "zonez", "pcorr", "pcalt", "rfcf", "sfcf", "tcorr", "tcalt", "icmax", "smax", "tt", "ttint", "cfmax", "cfvar",
+    "gmelt", "gvar", "cfr", "whc", "fc", "beta", "cflux",
+)
+_AET_CONTROL = ("temperaturethresholdice", "maxsoilwater", "soilmoisturelimit", "excessreduction")
+_PET_CONTROL = (
+    "hrualtitude", "evapotranspirationfactor", "altitudefactor", "precipitationfactor", "airtemperaturefactor",
+)
+
+
+class UnsupportedModelError(NotImplementedError):
+    """The project contains something the B200 engine does not cover (no silent fallback)."""
+
+
+def _f(par: Any, n: int | None = None) -> np.ndarray:
+    a = np.array(par.value, dtype=np.float64)
+    if n is not None:
+        a = np.broadcast_to(a, (n,)).copy() if a.ndim == 0 else a
+        if a.shape != (n,):
+            raise ValueError(f"parameter `{par.name}` has shape {a.shape}, expected ({n},)")
+    return a
+
+
+def _modelname(model: Any) -> str:
+    return getattr(model, "name", type(model).__module__.rsplit(".", 1)[-1])
+
+
+@dataclasses.dataclass
+class Problem:
+    """Everything one engine run needs, plus the objects the results go back to."""
+
+    land: LandBundle
+    states: LandStates
+    river: RiverBundle
+    discharge: np.ndarray                 # musk_classic states, concatenated
+    forcing: np.ndarray                   # [4, T, n_col]  (T = i1-i0)
+    doy: np.ndarray                       # [T] int64
+    ext: np.ndarray                       # [n_ext, T]
+    land_elements: list[Any] = dataclasses.field(default_factory=list)
+    river_elements: list[Any] = dataclasses.field(default_factory=list)
+    nodes: list[Any] = dataclasses.field(default_factory=list)
+    node_writeback: np.ndarray | None = None  # bool[n_node]: does the run overwrite sim.series of the node?
+    i0: int = 0
+    i1: int = 0
+
+    @property
+    def nt(self) -> int:
+        return int(self.forcing.shape[1])
+
+    def to_npz_dict(self) -> dict[str, np.ndarray]:
+        d = {**self.land.to_dict(), **self.river.to_dict()}
+        for n in LandStates.NAMES:
+            d["state_" + n] = getattr(self.states, n)
+        d["discharge"] = self.discharge
+        d["forcing"] = self.forcing
+        d["doy"] = self.doy
+        d["ext"] = self.ext
+        if self.node_writeback is not None:
+            d["node_writeback"] = self.node_writeback
+        return d
+
+    @classmethod
+    def from_npz_dict(cls, d: Any) -> "Problem":
+        from .abi import states_from_dict
+
+        return cls(
+            land=LandBundle.from_dict(d), states=states_from_dict(d), river=RiverBundle.from_dict(d),
+            discharge=np.array(d["discharge"], dtype=np.float64), forcing=np.array(d["forcing"], dtype=np.float64),
+            doy=np.array(d["doy"], dtype=np.int64), ext=np.array(d["ext"], dtype=np.float64),
+            node_writeback=np.array(d["node_writeback"], dtype=bool) if "node_writeback" in d else None,
+        )
+
+
+def _check_land_model(element: Any) -> None:
+    model = element.model
+    aet = getattr(model, "aetmodel", None)
+    if aet is None or _modelname(aet) != "evap_aet_hbv96":
+        raise UnsupportedModelError(
+            f"element `{element.name}`: hland_96 needs an `evap_aet_hbv96` AET submodel, found "
+            f"`{None if aet is None else _modelname(aet)}`"
+        )
+    pet = getattr(aet, "petmodel", None)
+    if pet is None or _modelname(pet) != "evap_pet_hbv96":
+        raise UnsupportedModelError(
+            f"element `{element.name}`: evap_aet_hbv96 needs an `evap_pet_hbv96` PET submodel, found "
+            f"`{None if pet is None else _modelname(pet)}`"
+        )
+    if getattr(aet, "snowycanopymodel", None) is not None:
+        raise UnsupportedModelError(f"element `{element.name}`: snowy-canopy submodels are not supported")
+    rconc = getattr(model, "rconcmodel", None)
+    if rconc is not None and _modelname(rconc) != "rconc_uh":
+        raise UnsupportedModelError(
+            f"element `{element.name}`: only `rconc_uh` (or no) runoff concentration submodel is supported, found "
+            f"`{_modelname(rconc)}`"
+        )
+    for seq in (model.sequences.inputs.p, model.sequences.inputs.t, pet.sequences.inputs.normalairtemperature,
+                pet.sequences.inputs.normalevapotranspiration):
+        if getattr(seq, "node2idx", None):
+            raise UnsupportedModelError(
+                f"element `{element.name}`: input sequence `{seq.name}` is fed by an input node, which the engine "
+                f"does not support yet"
+            )
+        if not seq.ramflag:
+            raise RuntimeError(
+                f"element `{element.name}`: the time series of input sequence `{seq.name}` is not available in "
+                f"RAM (just-in-time NetCDF reading is not possible with the B200 engine)"
+            )
+    if len(tuple(getattr(element, "outputs", ()))) or len(tuple(getattr(element, "inputs", ()))):
+        raise UnsupportedModelError(f"element `{element.name}`: input/output nodes are not supported")
+
+
+def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i1: int
+                 ) -> tuple[LandBundle, LandStates, np.ndarray, np.ndarray]:
+    """Gather all hland_96 elements into one `LandBundle` (+ conditions, forcing [4,T,E], doy[T])."""
+    elements = list(elements)
+    ne = len(elements)
+    zone_ptr = np.zeros(ne + 1, np.int64)
+    snow_ptr = np.zeros(ne + 1, np.int64)
+    sfdist_ptr = np.zeros(ne + 1, np.int64)
+    uh_ptr = np.zeros(ne + 1, np.int64)
+    sred_ptr = np.zeros(ne + 1, np.int64)
+    recstep = np.zeros(ne, np.int32)
+    eflags = np.zeros(ne, np.int32)
+    outlet_node = np.full(ne, -1, np.int32)
+    epar = np.zeros((len(layout.EPAR), ne))
+    zt_l, zf_l, zo_l, zp_l, sf_l, uh_l, sr_f, sr_t, sr_a = [], [], [], [], [], [], [], [], []
+    ic_l, sm_l, sp_l, wc_l, quh_l = [], [], [], [], []
+    uz = np.zeros(ne)
+    lz = np.zeros(ne)
+    nt = i1 - i0
+    forcing = np.zeros((4, nt, ne))
+    doy = None
+    for e, element in enumerate(elements):
+        _check_land_model(element)
+        model = element.model
+        con, der = model.parameters.control, model.parameters.derived
+        aet = model.aetmodel
+        pet = aet.petmodel
+        nz = int(con.nmbzones.value)
+        nc = int(con.sclass.value)
+        zone_ptr[e + 1] = zone_ptr[e] + nz
+        snow_ptr[e + 1] = snow_ptr[e] + nz * nc
+        sfdist_ptr[e + 1] = sfdist_ptr[e] + nc
+        recstep[e] = int(con.recstep.value)
+        eflags[e] = layout.EF_RESPAREA if bool(con.resparea.value) else 0
+        ep = layout.EP
+        epar[ep["z"], e] = der.z.value
+        epar[ep["relsoilarea"], e] = der.relsoilarea.value
+        epar[ep["rellandarea"], e] = der.rellandarea.value
+        epar[ep["relupperzonearea"], e] = der.relupperzonearea.value
+        epar[ep["rellowerzonearea"], e] = der.rellowerzonearea.value
+        epar[ep["percmax"], e] = con.percmax.value
+        epar[ep["dt"], e] = der.dt.value
+        epar[ep["alpha"], e] = con.alpha.value
+        epar[ep["k"], e] = con.k.value
+        epar[ep["k4"], e] = con.k4.value
+        epar[ep["gamma"], e] = con.gamma.value
+        epar[ep["qfactor"], e] = der.qfactor.value
+        epar[ep["petaltitude"], e] = pet.parameters.derived.altitude.value
+        zp = np.zeros((len(layout.ZPAR), nz))
+        for name in _ZONE_CONTROL:
+            zp[layout.ZP[name]] = _f(getattr(con, name), nz)
+        zp[layout.ZP["ttm"]] = _f(der.ttm, nz)
+        zp[layout.ZP["relzonearea"]] = _f(der.relzoneareas, nz)
+        for name in _AET_CONTROL:
+            zp[layout.ZP[name]] = _f(getattr(aet.parameters.control, name), nz)
+        for name in _PET_CONTROL:
+            zp[layout.ZP[name]] = _f(getattr(pet.parameters.control, name), nz)
+        zp[layout.ZP["hruareafraction"]] = _f(pet.parameters.derived.hruareafraction, nz)
+        zp_l.append(zp)
+        zt_l.append(np.array(con.zonetype.value, dtype=np.int32).reshape(nz))
+        acon = aet.parameters.control
+        flags = (
+            np.array(acon.water.value, dtype=bool).reshape(nz) * layout.ZF_WATER
+            + np.array(acon.interception.value, dtype=bool).reshape(nz) * layout.ZF_INTERCEPTION
+            + np.array(acon.soil.value, dtype=bool).reshape(nz) * layout.ZF_SOIL
+            + np.array(acon.tree.value, dtype=bool).reshape(nz) * layout.ZF_TREE
+            + np.array(der.sredend.value, dtype=bool).reshape(nz) * layout.ZF_SREDEND
+        )
+        zf_l.append(flags.astype(np.int32))
+        zo_l.append(np.array(der.indiceszonez.value, dtype=np.int32).reshape(nz))
+        sf_l.append(_f(con.sfdist, nc))
+        nsr = int(der.srednumber.value)
+        sred_ptr[e + 1] = sred_ptr[e] + nsr
+        if nsr:
+            order = np.array(der.sredorder.value, dtype=np.int64).reshape(-1, 2)[:nsr]
+            ratios = np.array(der.zonearearatios.value, dtype=np.float64)
+            sred = np.array(con.sred.value, dtype=np.float64)
+            sr_f.append(order[:, 0].astype(np.int32))
+            sr_t.append(order[:, 1].astype(np.int32))
+            sr_a.append(ratios[order[:, 0], order[:, 1]] * sred[order[:, 0], order[:, 1]])
+        rconc = getattr(model, "rconcmodel", None)
+        if rconc is not None:
+            uh = np.array(rconc.parameters.control.uh.value, dtype=np.float64).reshape(-1)
+            quh = np.array(rconc.sequences.logs.quh.value, dtype=np.float64).reshape(-1)
+            if quh.shape != uh.shape:
+                raise ValueError(f"element `{element.name}`: shapes of `uh` and `quh` differ")
+            uh_l.append(uh)
+            quh_l.append(quh)
+            uh_ptr[e + 1] = uh_ptr[e] + len(uh)
+        else:
+            uh_ptr[e + 1] = uh_ptr[e]
+        sta = model.sequences.states
+        ic_l.append(_f(sta.ic, nz))
+        sm_l.append(_f(sta.sm, nz))
+        sp_l.append(np.array(sta.sp.value, dtype=np.float64).reshape(nc * nz))
+        wc_l.append(np.array(sta.wc.value, dtype=np.float64).reshape(nc * nz))
+        uz[e] = sta.uz.value
+        lz[e] = sta.lz.value
+        inp = model.sequences.inputs
+        pinp = pet.sequences.inputs
+        forcing[0, :, e] = inp.p.series[i0:i1]
+        forcing[1, :, e] = inp.t.series[i0:i1]
+        forcing[2, :, e] = pinp.normalairtemperature.series[i0:i1]
+        forcing[3, :, e] = pinp.normalevapotranspiration.series[i0:i1]
+        this_doy = np.array(der.doy.value, dtype=np.int64)[i0:i1]
+        if doy is None:
+            doy = this_doy
+        elif not np.array_equal(doy, this_doy):
+            raise ValueError("all hland_96 elements must share one `doy` index")
+        out = model.sequences.outlets.q
+        for node in getattr(out, "node2idx", {}):
+            outlet_node[e] = node_index[node]
+
+    def cat(parts: list[np.ndarray], dtype: Any) -> np.ndarray:
+        return np.concatenate(parts).astype(dtype) if parts else np.zeros(0, dtype)
+
+    land = LandBundle(
+        zone_ptr=zone_ptr, snow_ptr=snow_ptr, sfdist_ptr=sfdist_ptr, uh_ptr=uh_ptr, sred_ptr=sred_ptr,
+        recstep=recstep, eflags=eflags, forcing_col=np.arange(ne, dtype=np.int32), outlet_node=outlet_node,
+        epar=epar, zonetype=cat(zt_l, np.int32), zflags=cat(zf_l, np.int32), zorder=cat(zo_l, np.int32),
+        zpar=np.concatenate(zp_l, axis=1) if zp_l else np.zeros((len(layout.ZPAR), 0)),
+        sfdist=cat(sf_l, np.float64), uh=cat(uh_l, np.float64), sred_from=cat(sr_f, np.int32),
+        sred_to=cat(sr_t, np.int32), sred_adjust=cat(sr_a, np.float64),
+    )
+    land.normalise()
+    states = LandStates(
+        ic=cat(ic_l, np.float64), sm=cat(sm_l, np.float64), sp=cat(sp_l, np.float64), wc=cat(wc_l, np.float64),
+        uz=uz, lz=lz, quh=cat(quh_l, np.float64),
+    )
+    if doy is None:
+        doy = np.zeros(nt, np.int64)
+    return land, states, forcing, doy
+
+
+def extract_river(elements: Iterable[Any], nodes: list[Any], node_index: dict[Any, int],
+                  land_index: dict[Any, int], i0: int, i1: int
+                  ) -> tuple[RiverBundle, np.ndarray, np.ndarray, np.ndarray]:
+    """Gather musk_classic elements + the node graph.  Returns (bundle, discharge, ext rows, node_writeback)."""
+    elements = list(elements)
+    reach_index = {el: i for i, el in enumerate(elements)}
+    nr, nn, nt = len(elements), len(nodes), i1 - i0
+    inlet_ptr = np.zeros(nr + 1, np.int64)
+    seg_ptr = np.zeros(nr + 1, np.int64)
+    reach_outlet = np.full(nr, -1, np.int32)
+    coef = np.zeros((3, nr))
+    inlet_node: list[int] = []
+    dis: list[np.ndarray] = []
+    for r, element in enumerate(elements):
+        model = element.model
+        con = model.parameters.control
+        ns = int(con.nmbsegments.value)
+        nmbruns = int(model.parameters.solver.nmbruns.value) if hasattr(model.parameters, "solver") else 1
+        if nmbruns != 1:
+            raise UnsupportedModelError(f"element `{element.name}`: musk_classic with nmbruns != 1 is not supported")
+        coef[:, r] = np.array(con.coefficients.value, dtype=np.float64).reshape(3)
+        d = np.array(model.sequences.states.discharge.value, dtype=np.float64).reshape(-1)
+        if len(d) != ns + 1:
+            raise ValueError(f"element `{element.name}`: `discharge` must have nmbsegments+1 entries")
+        dis.append(d)
+        seg_ptr[r + 1] = seg_ptr[r] + ns + 1
+        node2idx = model.sequences.inlets.q.node2idx
+        ordered = sorted(node2idx.items(), key=lambda kv: -1 if kv[1] is None else kv[1])
+        for node, _ in ordered:
+            inlet_node.append(node_index[node])
+        inlet_ptr[r + 1] = inlet_ptr[r] + len(ordered)
+        for node in model.sequences.outlets.q.node2idx:
+            reach_outlet[r] = node_index[node]
+    entry_ptr = np.zeros(nn + 1, np.int64)
+    entry_src: list[int] = []
+    node_mode = np.zeros(nn, np.int32)
+    node_ext = np.full(nn, -1, np.int32)
+    writeback = np.zeros(nn, bool)
+    ext_rows: list[np.ndarray] = []
+    for n, node in enumerate(nodes):
+        for element in node.entries:
+            if element in land_index:
+                entry_src.append(land_index[element])
+            elif element in reach_index:
+                entry_src.append(-1 - reach_index[element])
+            else:
+                raise UnsupportedModelError(
+                    f"node `{node.name}` is fed by element `{element.name}`, whose model is not covered by the "
+                    f"B200 engine"
+                )
+        entry_ptr[n + 1] = len(entry_src)
+        mode = str(node.deploymode)
+        seqs = node.sequences
+        if mode == "newsim":
+            writeback[n] = True
+        elif mode in ("oldsim", "oldsim_bi"):
+            node_mode[n] = layout.NODE_EXT
+            ext_rows.append(np.array(seqs.sim.series[i0:i1], dtype=np.float64))
+        elif mode in ("obs", "obs_bi"):
+            node_mode[n] = layout.NODE_EXT
+            ext_rows.append(np.array(seqs.obs.series[i0:i1], dtype=np.float64))
+            writeback[n] = True
+        elif mode == "obs_newsim":
+            node_mode[n] = layout.NODE_OBSNEWSIM
+            ext_rows.append(np.array(seqs.obs.series[i0:i1], dtype=np.float64))
+            writeback[n] = True
+        elif mode == "obs_oldsim":
+            node_mode[n] = layout.NODE_EXT
+            obs = np.array(seqs.obs.series[i0:i1], dtype=np.float64)
+            old = np.array(seqs.sim.series[i0:i1], dtype=np.float64)
+            ext_rows.append(np.where(np.isnan(obs), old, obs))
+        else:
+            raise UnsupportedModelError(f"node `{node.name}`: deploy mode `{mode}` is not supported")
+        if node_mode[n] != layout.NODE_NEWSIM:
+            node_ext[n] = len(ext_rows) - 1
+    river = RiverBundle(
+        entry_ptr=entry_ptr, entry_src=np.array(entry_src, np.int32), node_mode=node_mode, node_ext=node_ext,
+        inlet_ptr=inlet_ptr, inlet_node=np.array(inlet_node, np.int32), reach_outlet=reach_outlet, seg_ptr=seg_ptr,
+        coef=coef, n_ext=len(ext_rows),
+    )
+    river.normalise()
+    discharge = np.concatenate(dis) if dis else np.zeros(0)
+    ext = np.stack(ext_rows) if ext_rows else np.zeros((0, nt))
+    return river, discharge, ext, writeback
+
+
+def extract(hp: Any, i0: int, i1: int) -> Problem:
+    """Translate the complete `HydPy` project `hp` for the simulation window `[i0, i1)`.
+
+    Every element must handle `hland_96` or `musk_classic`; anything else raises `UnsupportedModelError`
+    (explicit error instead of a silent CPU fallback).
+    """
+    nodes = list(hp.nodes)
+    node_index = {node: i for i, node in enumerate(nodes)}
+    land_elements, river_elements = [], []
+    for element in hp.elements:
+        name = _modelname(element.model)
+        if name in LAND_MODELS:
+            land_elements.append(element)
+        elif name in RIVER_MODELS:
+            river_elements.append(element)
+        else:
+            raise UnsupportedModelError(
+                f"element `{element.name}` handles model `{name}`; the B200 engine covers "
+                f"{', '.join(LAND_MODELS + RIVER_MODELS)} only"
+            )
+        if len(tuple(getattr(element, "receivers", ()))) or len(tuple(getattr(element, "senders", ()))) or len(
+            tuple(getattr(element, "observers", ()))
+        ):
+            raise UnsupportedModelError(f"element `{element.name}`: receiver/sender/observer nodes are not supported")
+    land, states, forcing, doy = extract_land(land_elements, node_index, i0, i1)
+    land_index = {el: i for i, el in enumerate(land_elements)}
+    river, discharge, ext, writeback = extract_river(river_elements, nodes, node_index, land_index, i0, i1)
+    return Problem(
+        land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext,
+        land_elements=land_elements, river_elements=river_elements, nodes=nodes, node_writeback=writeback,
+        i0=i0, i1=i1,
+    )
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# results → HydPy objects   (contract: SURVEY.md §8b seam #1)
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def requested_series(problem: Problem) -> list[str]:
+    """Names of the land series at least one element keeps in RAM (`ramflag`)."""
+    wanted = []
+    for name in layout.SERIES:
+        group = layout.SERIES_GROUP[name]
+        for element in problem.land_elements:
+            seq = getattr(getattr(element.model.sequences, group), name)
+            if seq.ramflag:
+                wanted.append(name)
+                break
+    return wanted
+
+
+def _set_state(seq: Any, value: Any) -> None:
+    seq.new = value
+    seq.old = value
+
+
+def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, node_rows: np.ndarray,
+               land_rows: np.ndarray, reach_out: np.ndarray | None, reach_in: np.ndarray | None,
+               series: dict[str, np.ndarray]) -> None:
+    """Store the results of one run in the HydPy objects exactly where the reference leaves them."""
+    land, i0, i1 = problem.land, problem.i0, problem.i1
+    last = i1 - i0 - 1
+    for e, element in enumerate(problem.land_elements):
+        model = element.model
+        z0, z1 = int(land.zone_ptr[e]), int(land.zone_ptr[e + 1])
+        s0, s1 = int(land.snow_ptr[e]), int(land.snow_ptr[e + 1])
+        nz = z1 - z0
+        nc = (s1 - s0) // max(nz, 1)
+        sta = model.sequences.states
+        _set_state(sta.ic, states.ic[z0:z1])
+        _set_state(sta.sm, states.sm[z0:z1])
+        _set_state(sta.sp, states.sp[s0:s1].reshape(nc, nz))
+        _set_state(sta.wc, states.wc[s0:s1].reshape(nc, nz))
+        _set_state(sta.uz, float(states.uz[e]))
+        _set_state(sta.lz, float(states.lz[e]))
+        u0, u1 = int(land.uh_ptr[e]), int(land.uh_ptr[e + 1])
+        if u1 > u0:
+            model.rconcmodel.sequences.logs.quh.value = states.quh[u0:u1]
+        out = model.sequences.outlets.q
+        if getattr(out, "ramflag", False):
+            out.series[i0:i1] = land_rows[e]
+        if last >= 0:
+            out.value = float(land_rows[e, last])
+        for name, data in series.items():
+            group = layout.SERIES_GROUP[name]
+            seq = getattr(getattr(model.sequences, group), name)
+            if not seq.ramflag:
+                continue
+            if name in layout.SERIES_ZONE:
+                seq.series[i0:i1] = data[:, z0:z1]
+                if last >= 0 and group != "states":
+                    seq.value = data[last, z0:z1]
+            elif name in layout.SERIES_SNOW:
+                seq.series[i0:i1] = data[:, s0:s1].reshape(-1, nc, nz)
+                if last >= 0 and group != "states":
+                    seq.value = data[last, s0:s1].reshape(nc, nz)
+            else:
+                seq.series[i0:i1] = data[:, e]
+                if last >= 0 and group != "states":
+                    seq.value = float(data[last, e])
+    river = problem.river
+    for r, element in enumerate(problem.river_elements):
+        model = element.model
+        g0, g1 = int(river.seg_ptr[r]), int(river.seg_ptr[r + 1])
+        _set_state(model.sequences.states.discharge, discharge[g0:g1])
+        flu = model.sequences.fluxes
+        if reach_in is not None:
+            if flu.inflow.ramflag:
+                flu.inflow.series[i0:i1] = reach_in[r]
+            if last >= 0:
+                flu.inflow.value = float(reach_in[r, last])
+        if reach_out is not None:
+            if flu.outflow.ramflag:
+                flu.outflow.series[i0:i1] = reach_out[r]
+            out = model.sequences.outlets.q
+            if getattr(out, "ramflag", False):
+                out.series[i0:i1] = reach_out[r]
+            if last >= 0:
+                flu.outflow.value = float(reach_out[r, last])
+                out.value = float(reach_out[r, last])
+    for n, node in enumerate(problem.nodes):
+        if problem.node_writeback is not None and not problem.node_writeback[n]:
+            continue
+        sim = node.sequences.sim
+        if sim.ramflag:
+            sim.series[i0:i1] = node_rows[n]
+        if last >= 0:
+            # ref: hydpy/core/hydpytools.py:3094-3100 — sim.value = sim.series[last index]
+            sim.value = float(node_rows[n, last])

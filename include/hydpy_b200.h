@@ -1,0 +1,256 @@
+/* hydpy_b200.h — C-ABI of the B200-native engine for HydPy's data-parallel core.
+ *
+ * The reference (hydpy 6.5dev0, /root/reference) has NO C interface for this path: its native layer is one
+ * generated Cython extension type per model (`hydpy/cythons/modelutils.py:758-2999` writes
+ * `hydpy/cythons/autogen/c_<model>.pyx`), driven from Python by `HydPy.simulate`
+ * (`hydpy/core/hydpytools.py:2769-2963`) or `simulate_multithreaded` (`hydpytools.py:3055-3123`).  The entry
+ * points below are therefore what a binding of this path has to offer: every function names
+ * the reference interface it replaces.  Plain C: pointers + sizes only, caller owns all host buffers, the library
+ * owns device memory behind the opaque handle.  All floating point data is IEEE binary64, integers are int32/int64
+ * as declared.  Every function returns HB_OK (0) or a negative HB_E* code; `hb_last_error` gives the message.
+ *
+ * Units and time scaling: all values are the reference's *internal* values, i.e. what
+ * `model.parameters.<group>.fastaccess.<name>` holds after `model.update_parameters()` (time-dependent parameters
+ * already converted to the simulation step, `hydpy/core/parametertools.py:1464-1620`).
+ *
+ * Threading: one caller thread per handle (same as `HydPy.simulate`, which is synchronous and not re-entrant).
+ */
+#ifndef HYDPY_B200_H
+#define HYDPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------------------------------------------ */
+#define HB_OK 0
+#define HB_EINVAL (-1)   /* inconsistent or missing argument                                        */
+#define HB_ECUDA (-2)    /* CUDA runtime error (message holds cudaGetErrorString)                    */
+#define HB_ESTATE (-3)   /* call order violated (e.g. hb_run before hb_set_land/hb_set_forcing)      */
+#define HB_ENOMEM (-4)   /* host or device allocation failed                                         */
+#define HB_ENCCL (-5)    /* NCCL error / NCCL not loadable                                           */
+#define HB_ECYCLE (-6)   /* the node/reach network is not a DAG                                      */
+
+/* ---- zone types: `hydpy/models/hland/hland_constants.py` ------------------------------------------------- */
+#define HB_FIELD 1
+#define HB_FOREST 2
+#define HB_GLACIER 3
+#define HB_ILAKE 4
+#define HB_SEALED 5
+
+/* ---- per-zone flags (evap_aet_hbv96 control + hland derived), bit set of `zflags[]` ------------------------- */
+#define HB_ZF_WATER 1         /* evap_control.Water          (`hydpy/models/evap/evap_control.py`)             */
+#define HB_ZF_INTERCEPTION 2  /* evap_control.Interception                                                     */
+#define HB_ZF_SOIL 4          /* evap_control.Soil                                                             */
+#define HB_ZF_TREE 8          /* evap_control.Tree                                                             */
+#define HB_ZF_SREDEND 16      /* hland_derived.SRedEnd       (`hydpy/models/hland/hland_derived.py:403`)       */
+
+/* ---- per-element flags, bit set of `eflags[]` --------------------------------------------------------------- */
+#define HB_EF_RESPAREA 1      /* hland_control.RespArea                                                        */
+
+/* ---- per-zone double parameters: rows of `zpar[HB_ZP_COUNT][n_zone]` ---------------------------------------- *
+ * hland_96 control (`hydpy/models/hland/hland_control.py`), derived (`hland_derived.py`), evap_aet_hbv96 and
+ * evap_pet_hbv96 control/derived (`hydpy/models/evap/evap_control.py`, `evap_derived.py`).                      */
+enum hb_zpar {
+  HB_ZP_ZONEZ = 0, HB_ZP_PCORR, HB_ZP_PCALT, HB_ZP_RFCF, HB_ZP_SFCF, HB_ZP_TCORR, HB_ZP_TCALT, HB_ZP_ICMAX,
+  HB_ZP_SMAX, HB_ZP_TT, HB_ZP_TTINT, HB_ZP_TTM /* derived TTM = TT + DTTM */, HB_ZP_CFMAX, HB_ZP_CFVAR,
+  HB_ZP_GMELT, HB_ZP_GVAR, HB_ZP_CFR, HB_ZP_WHC, HB_ZP_FC, HB_ZP_BETA, HB_ZP_CFLUX,
+  HB_ZP_RELZONEAREA,                     /* hland_derived.RelZoneAreas                                         */
+  HB_ZP_TEMPERATURETHRESHOLDICE,         /* aet control                                                        */
+  HB_ZP_MAXSOILWATER, HB_ZP_SOILMOISTURELIMIT, HB_ZP_EXCESSREDUCTION,
+  HB_ZP_HRUALTITUDE,                     /* pet control                                                        */
+  HB_ZP_EVAPOTRANSPIRATIONFACTOR, HB_ZP_ALTITUDEFACTOR, HB_ZP_PRECIPITATIONFACTOR, HB_ZP_AIRTEMPERATUREFACTOR,
+  HB_ZP_HRUAREAFRACTION,                 /* pet derived                                                        */
+  HB_ZP_COUNT
+};
+
+/* ---- per-element double parameters: rows of `epar[HB_EP_COUNT][n_elem]` ------------------------------------- */
+enum hb_epar {
+  HB_EP_Z = 0 /* hland_derived.Z */, HB_EP_RELSOILAREA, HB_EP_RELLANDAREA, HB_EP_RELUPPERZONEAREA,
+  HB_EP_RELLOWERZONEAREA, HB_EP_PERCMAX, HB_EP_DT /* hland_derived.DT = 1/recstep */, HB_EP_ALPHA, HB_EP_K,
+  HB_EP_K4, HB_EP_GAMMA, HB_EP_QFACTOR /* hland_derived.QFactor */, HB_EP_PETALTITUDE /* evap_derived.Altitude */,
+  HB_EP_COUNT
+};
+
+/* ---- forcing fields: rows of `forcing[HB_FORCING_COUNT][nt][n_col]` ------------------------------------------ *
+ * hland_inputs.P, hland_inputs.T (`hydpy/models/hland/hland_inputs.py`), evap_inputs.NormalAirTemperature,
+ * evap_inputs.NormalEvapotranspiration (`hydpy/models/evap/evap_inputs.py`).                                     */
+enum hb_forcing { HB_F_P = 0, HB_F_T, HB_F_NORMALAIRTEMPERATURE, HB_F_NORMALEVAPOTRANSPIRATION, HB_FORCING_COUNT };
+
+/* ---- optional per-step output series of the land model (hland_96 factor/flux/state sequences) -------------- *
+ * Layouts on the host: zone sequences [nt][n_zone], snow sequences [nt][n_snow] (element-wise [class][zone]),
+ * element sequences [nt][n_elem].  (`hydpy/models/hland/hland_{factors,fluxes,states}.py`)                       */
+enum hb_series {
+  /* zone level */
+  HB_S_TC = 0, HB_S_FRACRAIN, HB_S_CFACT, HB_S_GACT, HB_S_PC, HB_S_EI, HB_S_TF, HB_S_SPL, HB_S_WCL, HB_S_SPG,
+  HB_S_WCG, HB_S_GLMELT, HB_S_IN, HB_S_R, HB_S_SR, HB_S_EA, HB_S_CF, HB_S_EL, HB_S_IC, HB_S_SM,
+  /* snow-class level */
+  HB_S_SWE, HB_S_MELT, HB_S_REFR, HB_S_SP, HB_S_WC,
+  /* element level */
+  HB_S_CONTRIAREA, HB_S_INUZ, HB_S_PERC, HB_S_Q0, HB_S_Q1, HB_S_INRC, HB_S_OUTRC, HB_S_RT, HB_S_QT, HB_S_UZ,
+  HB_S_LZ,
+  HB_S_COUNT
+};
+#define HB_S_FIRST_SNOW HB_S_SWE
+#define HB_S_FIRST_ELEM HB_S_CONTRIAREA
+
+/* ---- land description: all hland_96 elements (+ evap_aet_hbv96/evap_pet_hbv96, optional rconc_uh) ----------- *
+ * Replaces the per-element `Parameters`/`ControlParameters`/`DerivedParameters` extension types of
+ * `c_hland_96.pyx`, `c_evap_aet_hbv96.pyx`, `c_evap_pet_hbv96.pyx`, `c_rconc_uh.pyx`
+ * (generator: `hydpy/cythons/modelutils.py:1000-1050`).  Ragged dimensions are CSR-encoded.                      */
+typedef struct hb_land_desc {
+  int64_t n_elem;          /* number of hland_96 elements (ensemble members are additional elements)            */
+  int64_t n_zone;          /* sum of NmbZones                                                                   */
+  int64_t n_snow;          /* sum of SClass*NmbZones                                                            */
+  int64_t n_sfdist;        /* sum of SClass                                                                     */
+  int64_t n_uh;            /* sum of len(rconc_uh.UH) (0 for elements without rconc submodel)                   */
+  int64_t n_sred;          /* sum of hland_derived.SRedNumber                                                   */
+  const int64_t* zone_ptr;    /* [n_elem+1] zones of element e = zone_ptr[e]..zone_ptr[e+1]-1                   */
+  const int64_t* snow_ptr;    /* [n_elem+1] snow cells of e, index inside = c*NmbZones + k                      */
+  const int64_t* sfdist_ptr;  /* [n_elem+1] → sfdist[]; SClass = sfdist_ptr[e+1]-sfdist_ptr[e]                  */
+  const int64_t* uh_ptr;      /* [n_elem+1] → uh[] and quh[]; empty range ⇒ `model.rconcmodel is None`          */
+  const int64_t* sred_ptr;    /* [n_elem+1] → sred_from/to/adjust                                               */
+  const int32_t* recstep;     /* [n_elem]  hland_control.RecStep (already scaled to the simulation step)        */
+  const int32_t* eflags;      /* [n_elem]  HB_EF_*                                                              */
+  const int32_t* forcing_col; /* [n_elem]  column of the forcing arrays this element reads                      */
+  const int32_t* outlet_node; /* [n_elem]  node receiving `outlets.q` (−1: none)                                */
+  const double* epar;         /* [HB_EP_COUNT][n_elem]                                                          */
+  const int32_t* zonetype;    /* [n_zone]  HB_FIELD..HB_SEALED                                                  */
+  const int32_t* zflags;      /* [n_zone]  HB_ZF_*                                                              */
+  const int32_t* zorder;      /* [n_zone]  hland_derived.IndicesZoneZ (zone index local to its element)         */
+  const double* zpar;         /* [HB_ZP_COUNT][n_zone]                                                          */
+  const double* sfdist;       /* [n_sfdist] hland_control.SFDist                                                */
+  const double* uh;           /* [n_uh]    rconc_control.UH ordinates                                           */
+  const int32_t* sred_from;   /* [n_sred]  hland_derived.SRedOrder[:,0] (local zone index)                      */
+  const int32_t* sred_to;     /* [n_sred]  hland_derived.SRedOrder[:,1]                                         */
+  const double* sred_adjust;  /* [n_sred]  ZoneAreaRatios[f,t]*SRed[f,t]  (`hland_model.py:897`)                 */
+} hb_land_desc;
+
+/* ---- land conditions: hland_96 states + rconc_uh log (`Sequences.conditions`, `sequencetools.py:807-828`) ---- */
+typedef struct hb_land_states {
+  double* ic;   /* [n_zone] */
+  double* sm;   /* [n_zone] */
+  double* sp;   /* [n_snow] */
+  double* wc;   /* [n_snow] */
+  double* uz;   /* [n_elem] */
+  double* lz;   /* [n_elem] */
+  double* quh;  /* [n_uh]   */
+} hb_land_states;
+
+/* ---- river description: all musk_classic elements and the node graph --------------------------------------- *
+ * Replaces `c_musk_classic.pyx` objects plus the node⇄element pointer wiring of
+ * `hydpy/cythons/pointerutils.pyx` / `hydpy/core/threadingtools.py:396-446`.
+ * A node's simulated series is 0.0 + Σ of its entries in the listed order (`threadingtools.py:401-415`); a reach's
+ * inflow is 0.0 + Σ over its inlet nodes in the listed order (`musk_model.py:26-31`).                              */
+typedef struct hb_river_desc {
+  int64_t n_node;
+  int64_t n_reach;
+  int64_t n_entry;            /* total number of node entries                                                   */
+  int64_t n_inlet;            /* total number of reach inlet links                                              */
+  int64_t n_seg;              /* sum over reaches of (NmbSegments+1) = length of the discharge state            */
+  int64_t n_ext;              /* number of external (given) series rows                                         */
+  const int64_t* entry_ptr;   /* [n_node+1]                                                                     */
+  const int32_t* entry_src;   /* [n_entry] ≥0: land element index;  <0: reach index = -1-value                  */
+  const int32_t* node_mode;   /* [n_node]  HB_NODE_*                                                            */
+  const int32_t* node_ext;    /* [n_node]  row of the external series used by HB_NODE_EXT/OBSNEWSIM (−1: none)  */
+  const int64_t* inlet_ptr;   /* [n_reach+1]                                                                    */
+  const int32_t* inlet_node;  /* [n_inlet]                                                                      */
+  const int32_t* reach_outlet;/* [n_reach] node receiving the reach outflow (−1: none)                          */
+  const int64_t* seg_ptr;     /* [n_reach+1] → discharge[]; NmbSegments = seg_ptr[r+1]-seg_ptr[r]-1             */
+  const double* coef;         /* [3][n_reach] musk_control.Coefficients c0,c1,c2 (`musk_control.py:128-315`)    */
+} hb_river_desc;
+
+/* what a node hands to its downstream reaches (`devicetools.py:2205-2335`, `threadingtools.py:433-446`) */
+#define HB_NODE_NEWSIM 0     /* freshly simulated series                                                       */
+#define HB_NODE_EXT 1        /* the external row only (deploy modes oldsim / obs / oldsim_bi / obs_bi)          */
+#define HB_NODE_OBSNEWSIM 2  /* external row where it is not NaN, else the simulated series (obs_newsim)        */
+
+/* ---- life cycle -------------------------------------------------------------------------------------------- */
+typedef struct hb_engine hb_engine;
+
+/* ABI version of the loaded library (compare with HB_ABI_VERSION). */
+int hb_abi_version(void);
+/* Create an engine on CUDA device `device`.  Fails (HB_ECUDA) when no sm_100 device is usable: there is no CPU
+ * fallback.  Replaces: instantiating the Cython `Model` objects (`hydpy/core/importtools.py:83-108`). */
+int hb_create(int device, hb_engine** out);
+void hb_destroy(hb_engine* h);
+/* Message of the last failing call on `h` (or of the last failing hb_create when h is NULL). */
+const char* hb_last_error(const hb_engine* h);
+
+/* ---- setup --------------------------------------------------------------------------------------------------- */
+/* Upload structure + parameters of all land elements.  May be called again with the same structure to change
+ * parameter values (calibration loop: `hydpy/auxs/calibtools.py:2134-2150`). */
+int hb_set_land(hb_engine* h, const hb_land_desc* desc);
+/* Upload / download the conditions.  Replaces `Model.load_conditions`/`Sequences.conditions`
+ * (`hydpy/core/modeltools.py:2256`, `sequencetools.py:807-828`). */
+int hb_set_land_states(hb_engine* h, const hb_land_states* st);
+int hb_get_land_states(hb_engine* h, hb_land_states* st);
+/* Upload the river network.  Must follow hb_set_land (entries refer to land elements). */
+int hb_set_river(hb_engine* h, const hb_river_desc* desc);
+/* musk_classic `states.discharge` (old == new between steps), concatenated, length n_seg. */
+int hb_set_river_states(hb_engine* h, const double* discharge);
+int hb_get_river_states(hb_engine* h, double* discharge);
+/* Select which optional land series `hb_run` records (on ≠ 0).  Replaces the `ramflag` switches of
+ * `IOSequence.prepare_series` (`hydpy/core/sequencetools.py:1912`, save_data `modelutils.py:1127-1167`). */
+int hb_select_series(hb_engine* h, int series, int on);
+
+/* ---- one simulation window ------------------------------------------------------------------------------------ */
+/* Stage the forcing of the next window: `forcing` = [HB_FORCING_COUNT][nt][n_col] doubles, `doy` = [nt] values of
+ * hland_derived.DOY at the window's steps (`hland_model.py:1056`; 0-based day of a leap year).  Replaces
+ * `load_data` (`modelutils.py:1080-1125`) reading `inputs.<name>._<name>_array[idx]`. */
+int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy);
+/* External node rows of the window: [n_ext][nt].  (`oldsim`/`obs` deploy modes, multi-GPU boundary hand-over.) */
+int hb_set_external(hb_engine* h, int64_t nt, const double* rows);
+/* Advance all land elements by the staged `nt` steps (HB_RUN_LAND), then route (HB_RUN_RIVER).  States stay on
+ * the device, so consecutive windows continue seamlessly (`hydpytools.py:2817-2825`).  Replaces
+ * `Model.simulate_period(i0, i1)` for every element plus the node updates of `Worker.run`
+ * (`modelutils.py:1625-1634`, `threadingtools.py:358-446`).  Returns after results are complete on the device. */
+#define HB_RUN_LAND 1
+#define HB_RUN_RIVER 2
+int hb_run(hb_engine* h, int flags);
+
+/* ---- results of the last window -------------------------------------------------------------------------------- */
+/* `outlets.q` (= fluxes.qt) of every land element: host [n_elem][nt] (element-major rows). */
+int hb_get_land_outflow(hb_engine* h, double* rows);
+/* node.sequences.sim.series of the window: host [n_node][nt].  n_sel = 0 ⇒ all nodes in order, else rows of
+ * the listed nodes. */
+int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows);
+/* musk_classic fluxes.outflow / outlets.q of every reach: host [n_reach][nt]. */
+int hb_get_reach_outflow(hb_engine* h, double* rows);
+/* musk_classic fluxes.inflow of every reach: host [n_reach][nt]. */
+int hb_get_reach_inflow(hb_engine* h, double* rows);
+/* One selected land series (see enum hb_series for the layout). */
+int hb_get_series(hb_engine* h, int series, double* out);
+
+/* ---- multi-GPU boundary hand-over (NCCL over NVLink) ---------------------------------------------- */
+#define HB_NCCL_ID_BYTES 128
+/* Fill `id` (HB_NCCL_ID_BYTES) on rank 0; broadcast it out of band; then every rank calls hb_comm_init. */
+int hb_comm_unique_id(hb_engine* h, void* id);
+int hb_comm_init(hb_engine* h, int rank, int world, const void* id);
+/* Send the window's simulated rows of `n` local nodes to rank `peer` / receive `n` rows into the external rows
+ * `ext_rows[]` from rank `peer`.  Calls between matching ranks must pair up (grouped internally per call). */
+int hb_comm_send_nodes(hb_engine* h, int peer, int64_t n, const int32_t* nodes);
+int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows);
+int hb_comm_barrier(hb_engine* h);
+
+/* ---- measurement ------------------------------------------------------------------------------------------------ */
+typedef struct hb_timing {
+  double land_ms;        /* CUDA-event time of the runoff-generation kernel(s) of the last hb_run               */
+  double river_ms;       /* CUDA-event time of all routing kernels of the last hb_run                           */
+  double total_ms;       /* CUDA-event time of the whole hb_run on the engine stream                            */
+  int64_t land_launches;   /* kernels launched for the land part                                                */
+  int64_t river_launches;  /* kernels launched for the river part                                               */
+  int64_t n_levels;        /* topological levels of the river network                                           */
+} hb_timing;
+int hb_get_timing(hb_engine* h, hb_timing* out);
+/* Device properties the bench reports (SM count, clock in kHz, name into buf). */
+int hb_device_info(hb_engine* h, int* sm_count, int* clock_khz, char* name, int name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDPY_B200_H */

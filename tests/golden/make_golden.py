@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by RUNNING THE REFERENCE ITSELF (only possible where /root/reference
+exists, i.e. in the build container; the fixtures travel, the reference does not).
+
+What is produced (all under tests/golden/):
+
+* ``hland_96_integration.npz``  — the 11 integration tests of the reference's own ``hydpy/models/hland_96.py``
+  docstring (96 hourly steps each): the extracted problem (parameters, initial conditions, forcing) plus EVERY
+  factor/flux/state series, the outlet node series and the final conditions as raw float64.  While harvesting, the
+  docstring is executed by ``doctest``, so the reference build is at the same time checked against its own printed
+  6-digit tables.
+* ``musk_classic_integration.npz`` — the 3 integration tests of ``hydpy/models/musk_classic.py``.
+* ``lahn_daily.npz`` — the HydPy-H-Lahn example project, 1996-01-01…1998-01-01 daily (config 1 of BASELINE.json):
+  problem + all four gauge series + land outflows + final conditions + a few state series.
+* ``lahn_hourly_members.npz`` — config 2 in miniature: Lahn with ``simulationstep 1h`` (synthetic hourly
+  disaggregation of the daily forcing) for 14 days and 3 parameter-ensemble members.
+
+Usage:  python tests/golden/make_golden.py            (builds the scratch reference first if necessary)
+"""
+from __future__ import annotations
+
+import contextlib
+import doctest
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref  # noqa: E402
+
+SRC, STUBS = build_ref.scratch_paths()
+if not os.path.exists(os.path.join(os.path.dirname(SRC), ".built")):
+    build_ref.build()
+sys.path[:0] = [STUBS, SRC]
+
+import hydpy  # noqa: E402
+from hydpy import pub  # noqa: E402
+from hydpy.core import testtools  # noqa: E402
+
+from hydpy_b200 import layout  # noqa: E402
+from hydpy_b200.extract import extract  # noqa: E402
+
+
+def gather_expected(problem, hp) -> dict[str, np.ndarray]:
+    """Collect the reference's results in the ABI layouts."""
+    land, i0, i1 = problem.land, problem.i0, problem.i1
+    nt = i1 - i0
+    out: dict[str, np.ndarray] = {}
+    for name in layout.SERIES:
+        group = layout.SERIES_GROUP[name]
+        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_elem
+        arr = np.full((nt, width), np.nan)
+        have = False
+        for e, element in enumerate(problem.land_elements):
+            seq = getattr(getattr(element.model.sequences, group), name)
+            if not seq.ramflag:
+                continue
+            have = True
+            data = np.asarray(seq.series[i0:i1], dtype=np.float64)
+            if name in layout.SERIES_ZONE:
+                arr[:, land.zone_ptr[e]:land.zone_ptr[e + 1]] = data
+            elif name in layout.SERIES_SNOW:
+                arr[:, land.snow_ptr[e]:land.snow_ptr[e + 1]] = data.reshape(nt, -1)
+            else:
+                arr[:, e] = data
+        if have:
+            out["exp_" + name] = arr
+    out["exp_node_rows"] = np.stack(
+        [np.asarray(n.sequences.sim.series[i0:i1], dtype=np.float64) for n in problem.nodes]
+    ) if problem.nodes else np.zeros((0, nt))
+    after = extract(hp, i0, i1)
+    for n in after.states.NAMES:
+        out["exp_state_" + n] = getattr(after.states, n)
+    out["exp_discharge"] = after.discharge
+    rin, rout = [], []
+    for element in problem.river_elements:
+        flu = element.model.sequences.fluxes
+        if flu.inflow.ramflag and flu.outflow.ramflag:
+            rin.append(np.asarray(flu.inflow.series[i0:i1], dtype=np.float64))
+            rout.append(np.asarray(flu.outflow.series[i0:i1], dtype=np.float64))
+    if rin and len(rin) == len(problem.river_elements):
+        out["exp_reach_in"] = np.stack(rin)
+        out["exp_reach_out"] = np.stack(rout)
+    return out
+
+
+def harvest_module(modulename: str) -> dict[str, dict[str, np.ndarray]]:
+    """Execute the module docstring with doctest and snapshot every `test("name")` call."""
+    captured: dict[str, dict[str, np.ndarray]] = {}
+    orig_call = testtools.IntegrationTest.__call__
+
+    def hooked(self, filename=None, *, axis1=None, axis2=None, update_parameters=True, get_conditions=None,
+               use_conditions=None):
+        # same steps as the reference's IntegrationTest.__call__ (hydpy/core/testtools.py:626-645) minus plotting
+        self.prepare_model(update_parameters=update_parameters, use_conditions=use_conditions)
+        problem = None
+        if get_conditions is None and filename:
+            i0, i1 = pub.timegrids.simindices
+            problem = extract(self.hydpy, i0, i1)
+        seq2value = self._perform_simulation(get_conditions)
+        if problem is not None:
+            d = problem.to_npz_dict()
+            d.update(gather_expected(problem, self.hydpy))
+            captured[str(filename)] = d
+        self.print_table()
+        return seq2value
+
+    module = __import__(modulename, fromlist=["_"])
+    del pub.projectname
+    del pub.timegrids
+    pub.options.prepare_testing(usecython=True, threads=0)
+    testtools.IntegrationTest.plotting_options = testtools.PlottingOptions()
+    testtools.IntegrationTest.__call__ = hooked
+    try:
+        from hydpy.core import devicetools
+
+        tests = [t for t in doctest.DocTestFinder().find(module) if t.name == modulename]
+        assert len(tests) == 1, [t.name for t in tests]
+        runner = doctest.DocTestRunner(verbose=False)
+        buf = io.StringIO()
+        with devicetools.clear_registries_temporarily(), contextlib.redirect_stdout(buf):
+            runner.run(tests[0], out=buf.write)
+        res = runner.summarize(verbose=False)
+        if res.failed:
+            print(buf.getvalue()[-6000:])
+            raise SystemExit(f"{modulename}: {res.failed} of {res.attempted} reference doctest examples failed")
+        print(f"{modulename}: {res.attempted} reference doctest examples pass; {len(captured)} scenarios captured")
+    finally:
+        testtools.IntegrationTest.__call__ = orig_call
+    return captured
+
+
+def save_scenarios(path: str, scenarios: dict[str, dict[str, np.ndarray]]) -> None:
+    flat = {}
+    for sname, d in scenarios.items():
+        for k, v in d.items():
+            flat[f"{sname}/{k}"] = np.asarray(v)
+    flat["__scenarios__"] = np.array(sorted(scenarios))
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {os.path.getsize(path)/1024:.0f} KiB, scenarios: {', '.join(sorted(scenarios))}")
+
+
+def prepare_lahn(lastdate: str):
+    del pub.projectname
+    del pub.timegrids
+    pub.options.prepare_testing(usecython=True, threads=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hp, _, _ = testtools.prepare_full_example_2(lastdate=lastdate)
+    return hp
+
+
+def lahn_daily() -> dict[str, np.ndarray]:
+    hp = prepare_lahn("1998-01-01")
+    for element in hp.elements:
+        if element.model.name == "hland_96":
+            seqs = element.model.sequences
+            for seq in (seqs.states.sm, seqs.states.sp, seqs.states.uz, seqs.states.lz, seqs.fluxes.qt,
+                        seqs.fluxes.q0, seqs.fluxes.perc, seqs.factors.contriarea):
+                seq.prepare_series(allocate_ram=True)
+        else:
+            element.model.sequences.fluxes.inflow.prepare_series(allocate_ram=True)
+            element.model.sequences.fluxes.outflow.prepare_series(allocate_ram=True)
+    i0, i1 = pub.timegrids.simindices
+    problem = extract(hp, i0, i1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hp.simulate()
+    d = problem.to_npz_dict()
+    d.update(gather_expected(problem, hp))
+    d["node_names"] = np.array([n.name for n in problem.nodes])
+    d["land_names"] = np.array([e.name for e in problem.land_elements])
+    d["reach_names"] = np.array([e.name for e in problem.river_elements])
+    # the reference's own docstring goldens (hydpy/core/hydpytools.py:2791-2794) as a cross-check
+    kalk = d["exp_node_rows"][list(d["node_names"]).index("lahn_kalk")][:4]
+    assert np.allclose(kalk, [54.019332, 37.257552, 31.865302, 28.359538], rtol=0, atol=5e-7), kalk
+    return d
+
+
+def lahn_hourly_members(n_members: int = 3, days: int = 14) -> dict[str, dict[str, np.ndarray]]:
+    """Config 2 in miniature.  Hourly forcing = deterministic disaggregation of the daily Lahn series
+    (P/24 and NormalEvapotranspiration/24 per hour; T and NormalAirTemperature repeated), member 0 = shipped
+    parameter values, further members drawn with default_rng(20260101) inside plausible calibration bounds."""
+    import datetime
+
+    del pub.projectname
+    del pub.timegrids
+    pub.options.prepare_testing(usecython=True, threads=0)
+    first = datetime.datetime(1996, 1, 1)
+    last = first + datetime.timedelta(days=days)
+    with contextlib.redirect_stdout(io.StringIO()):
+        testtools.prepare_full_example_1()
+        with testtools.TestIO():
+            hp = hydpy.HydPy("HydPy-H-Lahn")
+            pub.timegrids = first.strftime("%Y-%m-%d"), last.strftime("%Y-%m-%d"), "1d"
+            hp.prepare_network()
+            hp.prepare_models()
+            hp.load_conditions()
+            hp.prepare_inputseries()
+            hp.load_inputseries()
+            daily = {}
+            for element in hp.elements:
+                m = element.model
+                if m.name != "hland_96":
+                    continue
+                pet = m.aetmodel.petmodel
+                daily[element.name] = (
+                    m.sequences.inputs.p.series.copy(), m.sequences.inputs.t.series.copy(),
+                    pet.sequences.inputs.normalairtemperature.series.copy(),
+                    pet.sequences.inputs.normalevapotranspiration.series.copy(),
+                )
+            # switch to hourly: re-create the project with simulationstep 1h
+            del pub.timegrids
+            hydpy.Node.clear_all()
+            hydpy.Element.clear_all()
+            hp = hydpy.HydPy("HydPy-H-Lahn")
+            pub.timegrids = first.strftime("%Y-%m-%d"), last.strftime("%Y-%m-%d"), "1h"
+            hp.prepare_network()
+            hp.prepare_models()
+            hp.load_conditions()
+            hp.prepare_nodeseries()
+            hp.prepare_inputseries()
+    for element in hp.elements:
+        m = element.model
+        if m.name != "hland_96":
+            continue
+        p, t, nat, net = daily[element.name]
+        pet = m.aetmodel.petmodel
+        m.sequences.inputs.p.series = np.repeat(p / 24.0, 24)
+        m.sequences.inputs.t.series = np.repeat(t, 24)
+        pet.sequences.inputs.normalairtemperature.series = np.repeat(nat, 24)
+        pet.sequences.inputs.normalevapotranspiration.series = np.repeat(net / 24.0, 24)
+    rng = np.random.default_rng(20260101)
+    conditions = hp.conditions
+    scenarios = {}
+    for member in range(n_members):
+        if member > 0:
+            for element in hp.elements:
+                m = element.model
+                if m.name == "hland_96":
+                    con = m.parameters.control
+                    con.fc(float(rng.uniform(100.0, 300.0)))
+                    con.beta(float(rng.uniform(1.0, 4.0)))
+                    con.percmax(float(rng.uniform(0.5, 2.0)))
+                    con.k(float(rng.uniform(0.001, 0.01)))
+                    con.k4(float(rng.uniform(0.005, 0.05)))
+                    con.alpha(float(rng.uniform(0.5, 1.5)))
+                    con.cfmax(float(rng.uniform(2.0, 5.0)))
+                    con.tt(float(rng.uniform(-1.0, 1.0)))
+                    con.whc(float(rng.uniform(0.05, 0.2)))
+                    con.cflux(float(rng.uniform(0.0, 1.0)))
+                    m.aetmodel.parameters.control.soilmoisturelimit(float(rng.uniform(0.6, 1.0)))
+                    m.aetmodel.parameters.control.maxsoilwater(con.fc)
+                else:
+                    con = m.parameters.control
+                    con.nmbsegments(lag=float(rng.uniform(0.0, 0.8)))
+                    con.coefficients(damp=float(rng.uniform(0.0, 1.0)))
+                m.update_parameters()
+            hp.conditions = conditions
+            for element in hp.elements:
+                m = element.model
+                if m.name == "musk_classic":
+                    m.sequences.states.discharge(0.0)
+        i0, i1 = pub.timegrids.simindices
+        problem = extract(hp, i0, i1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            hp.simulate()
+        d = problem.to_npz_dict()
+        d.update(gather_expected(problem, hp))
+        scenarios[f"member{member}"] = d
+    return scenarios
+
+
+def main() -> None:
+    save_scenarios(os.path.join(HERE, "hland_96_integration.npz"), harvest_module("hydpy.models.hland_96"))
+    save_scenarios(os.path.join(HERE, "musk_classic_integration.npz"), harvest_module("hydpy.models.musk_classic"))
+    save_scenarios(os.path.join(HERE, "lahn_daily.npz"), {"lahn_daily": lahn_daily()})
+    save_scenarios(os.path.join(HERE, "lahn_hourly_members.npz"), lahn_hourly_members())
+
+
+if __name__ == "__main__":
+    main()
