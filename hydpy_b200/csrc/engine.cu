@@ -1,0 +1,918 @@
+// engine.cu — host side of libhydpy_b200.so: the C-ABI of include/hydpy_b200.h over the sm_100a kernels.
+//
+// Replaces, for hland_96(+evap_aet_hbv96/evap_pet_hbv96/rconc_uh) and musk_classic, what the reference does in
+// `HydPy.simulate` → `simulate_multithreaded` (ref: hydpy/core/hydpytools.py:2769-3123) and
+// `Model.simulate_period` (ref: hydpy/cythons/modelutils.py:1625-1634).  There is deliberately NO CPU code path for
+// the model equations in this library: without a CUDA device `hb_create` fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "land_kernel.cuh"
+#include "river_kernel.cuh"
+
+using namespace hb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DBuf {  // device buffer that only grows
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
+    cudaError_t rc = cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T));
+    if (rc == cudaSuccess) cap = n ? n : 1;
+    else p = nullptr;
+    return rc;
+  }
+};
+
+// ---- minimal NCCL binding, resolved at run time (torch ships libnccl.so.2; the engine itself has no link-time
+// dependency on it, so single-GPU use never needs NCCL) ---------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (handle) return true;
+    const char* names[] = {getenv("HYDPY_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define HB_SYM(field, name) \
+  *(void**)(&field) = dlsym(handle, name); \
+  if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+    HB_SYM(GetUniqueId, "ncclGetUniqueId") HB_SYM(CommInitRank, "ncclCommInitRank")
+    HB_SYM(CommDestroy, "ncclCommDestroy") HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv")
+    HB_SYM(AllReduce, "ncclAllReduce") HB_SYM(GroupStart, "ncclGroupStart") HB_SYM(GroupEnd, "ncclGroupEnd")
+    HB_SYM(GetErrorString, "ncclGetErrorString")
+#undef HB_SYM
+    return true;
+  }
+};
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+}  // namespace
+
+struct hb_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string error;
+  cudaDeviceProp prop{};
+
+  // ---- land ----
+  bool have_land = false, have_states = false;
+  int64_t n_elem = 0, e_pad = 0, n_zone = 0, n_snow = 0, n_uh = 0;
+  int zmax = 0, cmax = 0, umax = 0;
+  bool any_snowlimit = false;
+  std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
+  std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
+  DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
+  DBuf<int64_t> d_zone0, d_snow0, d_sred_ptr;
+  DBuf<double> d_kz, d_ke, d_sfdist, d_uh, d_sred_adjust;
+  DBuf<double> d_ic, d_sm, d_sp, d_wc, d_uz, d_lz, d_quh, d_scr_a, d_scr_b, d_scr_sred;
+  bool series_on[HB_S_COUNT] = {};
+  DBuf<double> d_series[HB_S_COUNT];
+
+  // ---- window ----
+  int64_t nt = 0, n_col = 0;
+  bool have_forcing = false, have_results = false, have_routed = false;
+  DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows;
+
+  // ---- river ----
+  bool have_river = false;
+  int64_t n_node = 0, n_reach = 0, n_seg = 0, n_ext = 0, n_levels = 0;
+  std::vector<int32_t> level_node_ptr, level_reach_ptr;  // [n_levels+1]
+  DBuf<int64_t> d_entry_ptr, d_inlet_ptr, d_seg_ptr;
+  DBuf<int32_t> d_entry_src, d_node_mode, d_node_ext, d_inlet_node, d_node_order, d_reach_order, d_sel;
+  DBuf<double> d_coef, d_dis[2], d_ext_rows, d_node_rows, d_reach_in, d_reach_out, d_gather;
+  int dis_cur = 0;
+  bool have_ext = false;
+
+  // ---- comm ----
+  NcclApi nccl;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  DBuf<double> d_commbuf;
+
+  hb_timing timing{};
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    error = buf;
+    return code;
+  }
+};
+
+#define HB_CUDA(h, call)                                                                              \
+  do {                                                                                                \
+    cudaError_t rc__ = (call);                                                                        \
+    if (rc__ != cudaSuccess)                                                                          \
+      return (h)->fail(rc__ == cudaErrorMemoryAllocation ? HB_ENOMEM : HB_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                       cudaGetErrorString(rc__), __FILE__, __LINE__);                                 \
+  } while (0)
+
+#define HB_REQUIRE(h, cond, code, ...) \
+  do { if (!(cond)) return (h)->fail(code, __VA_ARGS__); } while (0)
+
+template <typename T>
+static int upload(hb_engine* h, DBuf<T>& buf, const T* src, size_t n) {
+  HB_CUDA(h, buf.reserve(n));
+  if (n) HB_CUDA(h, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return HB_OK;
+}
+template <typename T>
+static int upload(hb_engine* h, DBuf<T>& buf, const std::vector<T>& v) {
+  int rc = upload(h, buf, v.data(), v.size());
+  if (rc) return rc;
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));  // the vector may die right after the call
+  return HB_OK;
+}
+
+extern "C" {
+
+int hb_abi_version(void) { return HB_ABI_VERSION; }
+
+const char* hb_last_error(const hb_engine* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int hb_create(int device, hb_engine** out) {
+  if (!out) { g_create_error = "hb_create: out is NULL"; return HB_EINVAL; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t rc = cudaGetDeviceCount(&count);
+  if (rc != cudaSuccess || count == 0) {
+    g_create_error = std::string("hb_create: no CUDA device available (") + cudaGetErrorString(rc) +
+                     "); the B200 engine has no CPU fallback";
+    return HB_ECUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "hb_create: device index out of range";
+    return HB_EINVAL;
+  }
+  hb_engine* h = new hb_engine();
+  h->device = device;
+  if ((rc = cudaSetDevice(device)) != cudaSuccess || (rc = cudaGetDeviceProperties(&h->prop, device)) != cudaSuccess ||
+      (rc = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = std::string("hb_create: ") + cudaGetErrorString(rc);
+    delete h;
+    return HB_ECUDA;
+  }
+  if (h->prop.major < 10) {
+    g_create_error = std::string("hb_create: device '") + h->prop.name + "' is sm_" + std::to_string(h->prop.major) +
+                     std::to_string(h->prop.minor) + "; this library holds sm_100a code only";
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return HB_ECUDA;
+  }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return HB_OK;
+}
+
+void hb_destroy(hb_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+  cudaStreamSynchronize(h->stream);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hb_device_info(hb_engine* h, int* sm_count, int* clock_khz, char* name, int name_len) {
+  if (!h) return HB_EINVAL;
+  if (sm_count) *sm_count = h->prop.multiProcessorCount;
+  if (clock_khz) cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, h->device);
+  if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", h->prop.name);
+  return HB_OK;
+}
+
+int hb_host_alloc(hb_engine* h, int64_t bytes, void** out) {
+  if (!h || !out || bytes < 0) return HB_EINVAL;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, cudaHostAlloc(out, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+  return HB_OK;
+}
+
+int hb_host_free(hb_engine* h, void* p) {
+  if (!h) return HB_EINVAL;
+  if (p) HB_CUDA(h, cudaFreeHost(p));
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// land setup
+// ---------------------------------------------------------------------------------------------------------------------
+int hb_set_land(hb_engine* h, const hb_land_desc* d) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, d && d->n_elem >= 0, HB_EINVAL, "hb_set_land: invalid description");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t ne = d->n_elem;
+  HB_REQUIRE(h, ne == 0 || (d->zone_ptr && d->snow_ptr && d->sfdist_ptr && d->uh_ptr && d->sred_ptr && d->recstep &&
+                            d->eflags && d->forcing_col && d->epar && d->zpar && d->zonetype && d->zflags && d->zorder),
+             HB_EINVAL, "hb_set_land: NULL array in description");
+  const bool same_structure = h->have_land && h->n_elem == ne && h->n_zone == d->n_zone && h->n_snow == d->n_snow &&
+                              h->n_uh == d->n_uh;
+  int zmax = 1, cmax = 1, umax = 1;
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t nz = d->zone_ptr[e + 1] - d->zone_ptr[e], nc = d->sfdist_ptr[e + 1] - d->sfdist_ptr[e],
+                  nu = d->uh_ptr[e + 1] - d->uh_ptr[e];
+    HB_REQUIRE(h, nz >= 1 && nc >= 1 && nu >= 0, HB_EINVAL, "hb_set_land: element %lld has %lld zones, %lld snow classes",
+               (long long)e, (long long)nz, (long long)nc);
+    HB_REQUIRE(h, d->snow_ptr[e + 1] - d->snow_ptr[e] == nz * nc, HB_EINVAL,
+               "hb_set_land: snow_ptr of element %lld does not match SClass*NmbZones", (long long)e);
+    HB_REQUIRE(h, d->recstep[e] >= 0, HB_EINVAL, "hb_set_land: negative recstep");
+    if (nz > zmax) zmax = (int)nz;
+    if (nc > cmax) cmax = (int)nc;
+    if (nu > umax) umax = (int)nu;
+  }
+  HB_REQUIRE(h, (ne == 0 ? 0 : d->zone_ptr[ne]) == d->n_zone, HB_EINVAL, "hb_set_land: zone_ptr does not end at n_zone");
+  const int64_t ep = ((ne + 127) / 128) * 128 + (ne == 0 ? 128 : 0);
+  if (!same_structure) h->have_states = false;
+  h->n_elem = ne; h->e_pad = ep; h->n_zone = d->n_zone; h->n_snow = d->n_snow; h->n_uh = d->n_uh;
+  h->zmax = zmax; h->cmax = cmax; h->umax = umax;
+  h->zone_ptr.assign(d->zone_ptr, d->zone_ptr + ne + 1);
+  h->snow_ptr.assign(d->snow_ptr, d->snow_ptr + ne + 1);
+  h->uh_ptr.assign(d->uh_ptr, d->uh_ptr + ne + 1);
+  h->outlet_node.assign(ne, -1);
+  if (d->outlet_node) h->outlet_node.assign(d->outlet_node, d->outlet_node + ne);
+
+  std::vector<int32_t> nz(ep, 0), nc(ep, 1), nu(ep, 0), recstep(ep, 0), einfo(ep, 0), fcol(ep, 0);
+  std::vector<int32_t> zinfo((size_t)zmax * ep, 0), zorder((size_t)zmax * ep, 0);
+  std::vector<int64_t> zone0(ep, 0), snow0(ep, 0), sred_ptr(ep + 1, 0);
+  std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
+      sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
+  bool any_snowlimit = false;
+#define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
+#define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t z0 = d->zone_ptr[e];
+    const int n = (int)(d->zone_ptr[e + 1] - z0);
+    nz[e] = n;
+    nc[e] = (int)(d->sfdist_ptr[e + 1] - d->sfdist_ptr[e]);
+    nu[e] = (int)(d->uh_ptr[e + 1] - d->uh_ptr[e]);
+    recstep[e] = d->recstep[e];
+    fcol[e] = d->forcing_col[e];
+    zone0[e] = z0;
+    snow0[e] = d->snow_ptr[e];
+    sred_ptr[e] = d->sred_ptr[e];
+    const double z = EPAR(Z, e), relsoil = EPAR(RELSOILAREA, e), relupper = EPAR(RELUPPERZONEAREA, e),
+                 rellower = EPAR(RELLOWERZONEAREA, e), dt = EPAR(DT, e), petalt = EPAR(PETALTITUDE, e);
+    int info = 0;
+    if ((d->eflags[e] & HB_EF_RESPAREA) && relsoil > 0.0) info |= HB_EI_RESPAREA;
+    for (int k = 0; k < n; ++k) {
+      const int64_t zz = z0 + k;
+      const int zt = d->zonetype[zz];
+      HB_REQUIRE(h, zt >= HB_FIELD && zt <= HB_SEALED, HB_EINVAL, "hb_set_land: zone %lld has invalid type %d",
+                 (long long)zz, zt);
+      HB_REQUIRE(h, d->zorder[zz] >= 0 && d->zorder[zz] < n, HB_EINVAL, "hb_set_land: zorder out of range");
+      if (zt == HB_ILAKE) info |= HB_EI_LAKE;
+      if (zt == HB_SEALED) info |= HB_EI_SEALED;
+      if (zt != HB_ILAKE && !std::isinf(ZP(SMAX, zz))) info |= HB_EI_SNOWLIMIT;
+      zinfo[(size_t)k * ep + e] = zt | (d->zflags[zz] << 8);
+      zorder[(size_t)k * ep + e] = d->zorder[zz];
+      double* o = kz.data() + ((size_t)k * KZ_COUNT) * ep + e;
+      // folded exactly as the reference evaluates the sub-expressions (same operands, same order, IEEE binary64;
+      // this translation unit is compiled with -fmad=false and host code never contracts)
+      const double dz = ZP(ZONEZ, zz) - z;
+      const double half = ZP(TTINT, zz) / 2.0;
+      o[(size_t)KZ_TCORR * ep] = ZP(TCORR, zz);
+      o[(size_t)KZ_TCALT_DZ * ep] = ZP(TCALT, zz) * dz;
+      o[(size_t)KZ_TT_HI * ep] = ZP(TT, zz) + half;
+      o[(size_t)KZ_TT_LO * ep] = ZP(TT, zz) - half;
+      o[(size_t)KZ_TTINT * ep] = ZP(TTINT, zz);
+      o[(size_t)KZ_PCALT_F * ep] = 1.0 + ZP(PCALT, zz) * dz;
+      o[(size_t)KZ_PCORR * ep] = ZP(PCORR, zz);
+      o[(size_t)KZ_RFCF * ep] = ZP(RFCF, zz);
+      o[(size_t)KZ_SFCF * ep] = ZP(SFCF, zz);
+      o[(size_t)KZ_ICMAX * ep] = ZP(ICMAX, zz);
+      o[(size_t)KZ_CFMAX * ep] = ZP(CFMAX, zz);
+      o[(size_t)KZ_CFVAR * ep] = ZP(CFVAR, zz);
+      o[(size_t)KZ_TTM * ep] = ZP(TTM, zz);
+      o[(size_t)KZ_CFR_CFMAX * ep] = ZP(CFR, zz) * ZP(CFMAX, zz);
+      o[(size_t)KZ_WHC * ep] = ZP(WHC, zz);
+      o[(size_t)KZ_FC * ep] = ZP(FC, zz);
+      o[(size_t)KZ_BETA * ep] = ZP(BETA, zz);
+      o[(size_t)KZ_CFLUX * ep] = ZP(CFLUX, zz);
+      o[(size_t)KZ_W_UZ * ep] = ZP(RELZONEAREA, zz) / relupper;
+      o[(size_t)KZ_W_CONTRI * ep] = ZP(RELZONEAREA, zz) / relsoil;
+      o[(size_t)KZ_THRESH * ep] = ZP(SOILMOISTURELIMIT, zz) * ZP(MAXSOILWATER, zz);
+      o[(size_t)KZ_EXCESSRED * ep] = ZP(EXCESSREDUCTION, zz);
+      o[(size_t)KZ_ATF * ep] = ZP(AIRTEMPERATUREFACTOR, zz);
+      o[(size_t)KZ_ETF * ep] = ZP(EVAPOTRANSPIRATIONFACTOR, zz);
+      o[(size_t)KZ_ALT_F * ep] = 1.0 - ZP(ALTITUDEFACTOR, zz) / 100.0 * (ZP(HRUALTITUDE, zz) - petalt);
+      o[(size_t)KZ_NEG_PF * ep] = -ZP(PRECIPITATIONFACTOR, zz);
+      o[(size_t)KZ_SMAX * ep] = ZP(SMAX, zz);
+      o[(size_t)KZ_GMELT * ep] = ZP(GMELT, zz);
+      o[(size_t)KZ_GVAR * ep] = ZP(GVAR, zz);
+      o[(size_t)KZ_W_LZ * ep] = ZP(RELZONEAREA, zz) / rellower;
+      o[(size_t)KZ_RELZONEAREA * ep] = ZP(RELZONEAREA, zz);
+      o[(size_t)KZ_TTI * ep] = ZP(TEMPERATURETHRESHOLDICE, zz);
+    }
+    if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
+    einfo[e] = info;
+    ke[(size_t)KE_DT * ep + e] = dt;
+    ke[(size_t)KE_DT_PERCMAX * ep + e] = dt * EPAR(PERCMAX, e);
+    ke[(size_t)KE_DT_K * ep + e] = dt * EPAR(K, e);
+    ke[(size_t)KE_ALPHA1 * ep + e] = 1.0 + EPAR(ALPHA, e);
+    ke[(size_t)KE_K4 * ep + e] = EPAR(K4, e);
+    ke[(size_t)KE_GAMMA1 * ep + e] = 1.0 + EPAR(GAMMA, e);
+    ke[(size_t)KE_RELUPPER * ep + e] = relupper;
+    ke[(size_t)KE_RELLOWER * ep + e] = rellower;
+    ke[(size_t)KE_UP_LOW * ep + e] = relupper / rellower;
+    ke[(size_t)KE_QFACTOR * ep + e] = EPAR(QFACTOR, e);
+    ke[(size_t)KE_RELSOILAREA * ep + e] = relsoil;
+    ke[(size_t)KE_RELLANDAREA * ep + e] = EPAR(RELLANDAREA, e);
+    ke[(size_t)KE_BETA_LAST * ep + e] = ZP(BETA, z0 + n - 1);
+    for (int c = 0; c < nc[e]; ++c) sfdist[(size_t)c * ep + e] = d->sfdist[d->sfdist_ptr[e] + c];
+    for (int j = 0; j < nu[e]; ++j) uh[(size_t)j * ep + e] = d->uh[d->uh_ptr[e] + j];
+  }
+#undef ZP
+#undef EPAR
+  for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = ne ? d->sred_ptr[ne] : 0;
+  h->any_snowlimit = any_snowlimit;
+  h->h_nz = nz; h->h_nc = nc; h->h_nu = nu;
+  int rc;
+  if ((rc = upload(h, h->d_nz, nz)) || (rc = upload(h, h->d_nc, nc)) || (rc = upload(h, h->d_nu, nu)) ||
+      (rc = upload(h, h->d_recstep, recstep)) || (rc = upload(h, h->d_einfo, einfo)) ||
+      (rc = upload(h, h->d_fcol, fcol)) || (rc = upload(h, h->d_zinfo, zinfo)) || (rc = upload(h, h->d_zorder, zorder)) ||
+      (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) ||
+      (rc = upload(h, h->d_sred_ptr, sred_ptr)) || (rc = upload(h, h->d_kz, kz)) || (rc = upload(h, h->d_ke, ke)) ||
+      (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)))
+    return rc;
+  if ((rc = upload(h, h->d_sred_from, d->sred_from, (size_t)d->n_sred)) ||
+      (rc = upload(h, h->d_sred_to, d->sred_to, (size_t)d->n_sred)) ||
+      (rc = upload(h, h->d_sred_adjust, d->sred_adjust, (size_t)d->n_sred)))
+    return rc;
+  const size_t zs = (size_t)zmax * ep;
+  HB_CUDA(h, h->d_ic.reserve(zs)); HB_CUDA(h, h->d_sm.reserve(zs));
+  HB_CUDA(h, h->d_sp.reserve(zs * cmax)); HB_CUDA(h, h->d_wc.reserve(zs * cmax));
+  HB_CUDA(h, h->d_uz.reserve(ep)); HB_CUDA(h, h->d_lz.reserve(ep)); HB_CUDA(h, h->d_quh.reserve((size_t)umax * ep));
+  HB_CUDA(h, h->d_scr_a.reserve(zs)); HB_CUDA(h, h->d_scr_b.reserve(zs));
+  HB_CUDA(h, cudaMemsetAsync(h->d_scr_a.p, 0, zs * sizeof(double), h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->d_scr_b.p, 0, zs * sizeof(double), h->stream));
+  if (any_snowlimit) {
+    HB_CUDA(h, h->d_scr_sred.reserve(zs * 6));
+    HB_CUDA(h, cudaMemsetAsync(h->d_scr_sred.p, 0, zs * 6 * sizeof(double), h->stream));
+  }
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_land = true;
+  h->have_results = false;
+  return HB_OK;
+}
+
+int hb_set_land_states(hb_engine* h, const hb_land_states* st) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_land_states: call hb_set_land first");
+  HB_REQUIRE(h, st && (h->n_elem == 0 || (st->ic && st->sm && st->sp && st->wc && st->uz && st->lz)), HB_EINVAL,
+             "hb_set_land_states: NULL state array");
+  HB_REQUIRE(h, h->n_uh == 0 || st->quh, HB_EINVAL, "hb_set_land_states: quh is NULL");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t ep = h->e_pad, ne = h->n_elem;
+  const size_t zs = (size_t)h->zmax * ep;
+  std::vector<double> ic(zs, 0.0), sm(zs, 0.0), sp(zs * h->cmax, 0.0), wc(zs * h->cmax, 0.0), uz(ep, 0.0), lz(ep, 0.0),
+      quh((size_t)h->umax * ep, 0.0);
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t z0 = h->zone_ptr[e], s0 = h->snow_ptr[e], u0 = h->uh_ptr[e];
+    const int nz = h->h_nz[e], nc = h->h_nc[e], nu = h->h_nu[e];
+    for (int k = 0; k < nz; ++k) {
+      ic[(size_t)k * ep + e] = st->ic[z0 + k];
+      sm[(size_t)k * ep + e] = st->sm[z0 + k];
+      for (int c = 0; c < nc; ++c) {
+        sp[(size_t)c * zs + (size_t)k * ep + e] = st->sp[s0 + (int64_t)c * nz + k];
+        wc[(size_t)c * zs + (size_t)k * ep + e] = st->wc[s0 + (int64_t)c * nz + k];
+      }
+    }
+    uz[e] = st->uz[e];
+    lz[e] = st->lz[e];
+    for (int j = 0; j < nu; ++j) quh[(size_t)j * ep + e] = st->quh[u0 + j];
+  }
+  int rc;
+  if ((rc = upload(h, h->d_ic, ic)) || (rc = upload(h, h->d_sm, sm)) || (rc = upload(h, h->d_sp, sp)) ||
+      (rc = upload(h, h->d_wc, wc)) || (rc = upload(h, h->d_uz, uz)) || (rc = upload(h, h->d_lz, lz)) ||
+      (rc = upload(h, h->d_quh, quh)))
+    return rc;
+  h->have_states = true;
+  return HB_OK;
+}
+
+int hb_get_land_states(hb_engine* h, hb_land_states* st) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_land && h->have_states, HB_ESTATE, "hb_get_land_states: no states on the device");
+  HB_REQUIRE(h, st, HB_EINVAL, "hb_get_land_states: NULL argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t ep = h->e_pad, ne = h->n_elem;
+  const size_t zs = (size_t)h->zmax * ep;
+  std::vector<double> ic(zs), sm(zs), sp(zs * h->cmax), wc(zs * h->cmax), uz(ep), lz(ep), quh((size_t)h->umax * ep);
+#define HB_DL(vec, buf) HB_CUDA(h, cudaMemcpyAsync(vec.data(), buf.p, vec.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream))
+  HB_DL(ic, h->d_ic); HB_DL(sm, h->d_sm); HB_DL(sp, h->d_sp); HB_DL(wc, h->d_wc); HB_DL(uz, h->d_uz); HB_DL(lz, h->d_lz);
+  HB_DL(quh, h->d_quh);
+#undef HB_DL
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t z0 = h->zone_ptr[e], s0 = h->snow_ptr[e], u0 = h->uh_ptr[e];
+    const int nz = h->h_nz[e], nc = h->h_nc[e], nu = h->h_nu[e];
+    for (int k = 0; k < nz; ++k) {
+      if (st->ic) st->ic[z0 + k] = ic[(size_t)k * ep + e];
+      if (st->sm) st->sm[z0 + k] = sm[(size_t)k * ep + e];
+      for (int c = 0; c < nc; ++c) {
+        if (st->sp) st->sp[s0 + (int64_t)c * nz + k] = sp[(size_t)c * zs + (size_t)k * ep + e];
+        if (st->wc) st->wc[s0 + (int64_t)c * nz + k] = wc[(size_t)c * zs + (size_t)k * ep + e];
+      }
+    }
+    if (st->uz) st->uz[e] = uz[e];
+    if (st->lz) st->lz[e] = lz[e];
+    if (st->quh)
+      for (int j = 0; j < nu; ++j) st->quh[u0 + j] = quh[(size_t)j * ep + e];
+  }
+  return HB_OK;
+}
+
+int hb_select_series(hb_engine* h, int series, int on) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, series >= 0 && series < HB_S_COUNT, HB_EINVAL, "hb_select_series: unknown series %d", series);
+  h->series_on[series] = on != 0;
+  if (!on) h->d_series[series].release();
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// river setup
+// ---------------------------------------------------------------------------------------------------------------------
+int hb_set_river(hb_engine* h, const hb_river_desc* r) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_river: call hb_set_land first");
+  HB_REQUIRE(h, r && r->n_node >= 0 && r->n_reach >= 0, HB_EINVAL, "hb_set_river: invalid description");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t nn = r->n_node, nr = r->n_reach;
+  HB_REQUIRE(h, (nn == 0 || (r->entry_ptr && r->node_mode && r->node_ext)) &&
+                    (nr == 0 || (r->inlet_ptr && r->reach_outlet && r->seg_ptr && r->coef)),
+             HB_EINVAL, "hb_set_river: NULL array in description");
+  // validate + topological levels: node level = 0 without reach entries else 1 + max(level of entry reaches);
+  // reach level = max(level of its inlet nodes)
+  std::vector<int32_t> node_level(nn, -1), reach_level(nr, -1), node_pending(nn, 0), reach_pending(nr, 0);
+  std::vector<std::vector<int32_t>> node_exits(nn);
+  for (int64_t n = 0; n < nn; ++n) {
+    for (int64_t i = r->entry_ptr[n]; i < r->entry_ptr[n + 1]; ++i) {
+      const int32_t s = r->entry_src[i];
+      if (s >= 0) HB_REQUIRE(h, s < h->n_elem, HB_EINVAL, "hb_set_river: node %lld entry refers to land element %d of %lld",
+                             (long long)n, s, (long long)h->n_elem);
+      else {
+        HB_REQUIRE(h, -1 - s < nr, HB_EINVAL, "hb_set_river: node %lld entry refers to reach %d", (long long)n, -1 - s);
+        node_pending[n]++;
+      }
+    }
+    const int mode = r->node_mode[n];
+    HB_REQUIRE(h, mode >= HB_NODE_NEWSIM && mode <= HB_NODE_OBSNEWSIM, HB_EINVAL, "hb_set_river: invalid node mode");
+    if (mode != HB_NODE_NEWSIM)
+      HB_REQUIRE(h, r->node_ext[n] >= 0 && r->node_ext[n] < r->n_ext, HB_EINVAL,
+                 "hb_set_river: node %lld needs an external row", (long long)n);
+  }
+  for (int64_t q = 0; q < nr; ++q) {
+    HB_REQUIRE(h, r->seg_ptr[q + 1] - r->seg_ptr[q] >= 1, HB_EINVAL, "hb_set_river: reach %lld without discharge state",
+               (long long)q);
+    reach_pending[q] = (int32_t)(r->inlet_ptr[q + 1] - r->inlet_ptr[q]);
+    for (int64_t i = r->inlet_ptr[q]; i < r->inlet_ptr[q + 1]; ++i) {
+      const int32_t n = r->inlet_node[i];
+      HB_REQUIRE(h, n >= 0 && n < nn, HB_EINVAL, "hb_set_river: reach %lld inlet node out of range", (long long)q);
+      node_exits[n].push_back((int32_t)q);
+    }
+    HB_REQUIRE(h, r->reach_outlet[q] >= -1 && r->reach_outlet[q] < nn, HB_EINVAL, "hb_set_river: outlet out of range");
+  }
+  std::vector<int32_t> nq, rq;  // work lists
+  for (int64_t n = 0; n < nn; ++n)
+    if (node_pending[n] == 0) { node_level[n] = 0; nq.push_back((int32_t)n); }
+  for (int64_t q = 0; q < nr; ++q)
+    if (reach_pending[q] == 0) { reach_level[q] = 0; rq.push_back((int32_t)q); }
+  int64_t done = 0;
+  size_t ni = 0, ri = 0;
+  while (ni < nq.size() || ri < rq.size()) {
+    while (ni < nq.size()) {
+      const int32_t n = nq[ni++];
+      ++done;
+      for (int32_t q : node_exits[n]) {
+        if (reach_level[q] < node_level[n]) reach_level[q] = node_level[n];
+        if (--reach_pending[q] == 0) rq.push_back(q);
+      }
+    }
+    while (ri < rq.size()) {
+      const int32_t q = rq[ri++];
+      ++done;
+      const int32_t n = r->reach_outlet[q];
+      if (n >= 0) {
+        if (node_level[n] < reach_level[q] + 1) node_level[n] = reach_level[q] + 1;
+        if (--node_pending[n] == 0) nq.push_back(n);
+      }
+    }
+  }
+  HB_REQUIRE(h, done == nn + nr, HB_ECYCLE, "hb_set_river: the network contains a cycle (%lld of %lld devices ordered)",
+             (long long)done, (long long)(nn + nr));
+  int32_t nlev = 0;
+  for (auto l : node_level) if (l + 1 > nlev) nlev = l + 1;
+  for (auto l : reach_level) if (l + 1 > nlev) nlev = l + 1;
+  std::vector<int32_t> lnp(nlev + 1, 0), lrp(nlev + 1, 0), node_order(nn), reach_order(nr);
+  for (auto l : node_level) lnp[l + 1]++;
+  for (auto l : reach_level) lrp[l + 1]++;
+  for (int l = 0; l < nlev; ++l) { lnp[l + 1] += lnp[l]; lrp[l + 1] += lrp[l]; }
+  {
+    std::vector<int32_t> np(lnp.begin(), lnp.end() - 1), rp(lrp.begin(), lrp.end() - 1);
+    if (nlev == 0) { np.clear(); rp.clear(); }
+    for (int64_t n = 0; n < nn; ++n) node_order[np[node_level[n]]++] = (int32_t)n;
+    for (int64_t q = 0; q < nr; ++q) reach_order[rp[reach_level[q]]++] = (int32_t)q;
+  }
+  h->n_node = nn; h->n_reach = nr; h->n_seg = r->n_seg; h->n_ext = r->n_ext; h->n_levels = nlev;
+  h->level_node_ptr = lnp; h->level_reach_ptr = lrp;
+  int rc;
+  if ((rc = upload(h, h->d_entry_ptr, r->entry_ptr, (size_t)nn + 1)) ||
+      (rc = upload(h, h->d_entry_src, r->entry_src, (size_t)r->n_entry)) ||
+      (rc = upload(h, h->d_node_mode, r->node_mode, (size_t)nn)) || (rc = upload(h, h->d_node_ext, r->node_ext, (size_t)nn)) ||
+      (rc = upload(h, h->d_inlet_ptr, r->inlet_ptr, (size_t)nr + 1)) ||
+      (rc = upload(h, h->d_inlet_node, r->inlet_node, (size_t)r->n_inlet)) ||
+      (rc = upload(h, h->d_seg_ptr, r->seg_ptr, (size_t)nr + 1)) || (rc = upload(h, h->d_coef, r->coef, (size_t)3 * nr)) ||
+      (rc = upload(h, h->d_node_order, node_order)) || (rc = upload(h, h->d_reach_order, reach_order)))
+    return rc;
+  HB_CUDA(h, h->d_dis[0].reserve((size_t)r->n_seg));
+  HB_CUDA(h, h->d_dis[1].reserve((size_t)r->n_seg));
+  HB_CUDA(h, cudaMemsetAsync(h->d_dis[0].p, 0, (size_t)(r->n_seg ? r->n_seg : 1) * sizeof(double), h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->d_dis[1].p, 0, (size_t)(r->n_seg ? r->n_seg : 1) * sizeof(double), h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->dis_cur = 0;
+  h->have_river = true;
+  h->have_ext = false;
+  return HB_OK;
+}
+
+int hb_set_river_states(hb_engine* h, const double* discharge) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_set_river_states: call hb_set_river first");
+  HB_REQUIRE(h, discharge || h->n_seg == 0, HB_EINVAL, "hb_set_river_states: NULL argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  if (h->n_seg) {
+    HB_CUDA(h, cudaMemcpyAsync(h->d_dis[h->dis_cur].p, discharge, (size_t)h->n_seg * sizeof(double),
+                               cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+int hb_get_river_states(hb_engine* h, double* discharge) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_get_river_states: call hb_set_river first");
+  HB_REQUIRE(h, discharge || h->n_seg == 0, HB_EINVAL, "hb_get_river_states: NULL argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  if (h->n_seg) {
+    HB_CUDA(h, cudaMemcpyAsync(discharge, h->d_dis[h->dis_cur].p, (size_t)h->n_seg * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// window
+// ---------------------------------------------------------------------------------------------------------------------
+int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_forcing: call hb_set_land first");
+  HB_REQUIRE(h, nt >= 0 && n_col >= 1 && (nt == 0 || (forcing && doy)), HB_EINVAL, "hb_set_forcing: invalid argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)HB_FORCING_COUNT * nt * n_col;
+  HB_CUDA(h, h->d_forcing.reserve(n));
+  if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing.p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // 0.5*sin(2*pi*(doy+1)/366-1.39) with the HOST libm, evaluated exactly like the generated C of the reference
+  // (ref: hydpy/models/hland/hland_model.py:1056-1058) — the seasonal factor is therefore bit-identical to the CPU path
+  std::vector<double> sf((size_t)nt);
+  const double pi = 3.141592653589793;
+  for (int64_t t = 0; t < nt; ++t) sf[t] = 0.5 * sin((((2.0 * pi) * (double)(doy[t] + 1)) / 366.0) - 1.39);
+  int rc = upload(h, h->d_sinfactor, sf);
+  if (rc) return rc;
+  h->nt = nt;
+  h->n_col = n_col;
+  h->have_forcing = true;
+  h->have_results = false;
+  h->have_routed = false;
+  h->have_ext = false;
+  return HB_OK;
+}
+
+int hb_set_external(hb_engine* h, int64_t nt, const double* rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_set_external: call hb_set_river first");
+  HB_REQUIRE(h, h->have_forcing && nt == h->nt, HB_EINVAL, "hb_set_external: nt must equal the staged window length");
+  HB_REQUIRE(h, rows || h->n_ext == 0 || nt == 0, HB_EINVAL, "hb_set_external: NULL argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)h->n_ext * nt;
+  HB_CUDA(h, h->d_ext_rows.reserve(n));
+  if (n) {
+    HB_CUDA(h, cudaMemcpyAsync(h->d_ext_rows.p, rows, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->have_ext = true;
+  return HB_OK;
+}
+
+static int run_land(hb_engine* h) {
+  const int64_t nt = h->nt, ep = h->e_pad;
+  HB_CUDA(h, h->d_qt.reserve((size_t)nt * ep));
+  HB_CUDA(h, h->d_land_rows.reserve((size_t)h->n_elem * nt));
+  LandDev d{};
+  d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
+  d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
+  d.nz = h->d_nz.p; d.nc = h->d_nc.p; d.nu = h->d_nu.p; d.recstep = h->d_recstep.p; d.einfo = h->d_einfo.p;
+  d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p;
+  d.kz = h->d_kz.p; d.ke = h->d_ke.p; d.sfdist = h->d_sfdist.p; d.uh = h->d_uh.p;
+  d.sred_ptr = h->d_sred_ptr.p; d.sred_from = h->d_sred_from.p; d.sred_to = h->d_sred_to.p;
+  d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
+  d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
+  d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
+  d.nt = nt; d.n_col = h->n_col; d.forcing = h->d_forcing.p; d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
+  bool any_series = false;
+  for (int s = 0; s < HB_S_COUNT; ++s) {
+    d.series[s] = nullptr;
+    if (!h->series_on[s]) continue;
+    const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+    HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
+    d.series[s] = h->d_series[s].p;
+    any_series = true;
+  }
+  h->timing.land_launches = 0;
+  if (h->n_elem > 0 && nt > 0) {
+    const int block = 128;
+    const int grid = (int)((h->n_elem + block - 1) / block);
+    if (any_series) land_kernel<true><<<grid, block, 0, h->stream>>>(d);
+    else land_kernel<false><<<grid, block, 0, h->stream>>>(d);
+    HB_CUDA(h, cudaGetLastError());
+    dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
+    transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows.p, nt, h->n_elem, ep);
+    HB_CUDA(h, cudaGetLastError());
+    h->timing.land_launches = 2;
+  }
+  return HB_OK;
+}
+
+static int run_river(hb_engine* h) {
+  const int64_t nt = h->nt;
+  HB_CUDA(h, h->d_node_rows.reserve((size_t)h->n_node * nt));
+  HB_CUDA(h, h->d_reach_in.reserve((size_t)h->n_reach * nt));
+  HB_CUDA(h, h->d_reach_out.reserve((size_t)h->n_reach * nt));
+  RiverDev d{};
+  d.n_node = h->n_node; d.n_reach = h->n_reach; d.nt = nt;
+  d.entry_ptr = h->d_entry_ptr.p; d.entry_src = h->d_entry_src.p; d.node_mode = h->d_node_mode.p;
+  d.node_ext = h->d_node_ext.p; d.inlet_ptr = h->d_inlet_ptr.p; d.inlet_node = h->d_inlet_node.p;
+  d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows.p; d.ext_rows = h->d_ext_rows.p;
+  d.node_rows = h->d_node_rows.p; d.reach_in = h->d_reach_in.p; d.reach_out = h->d_reach_out.p;
+  d.dis_old = h->d_dis[h->dis_cur].p; d.dis_new = h->d_dis[1 - h->dis_cur].p;
+  int64_t launches = 0;
+  if (nt > 0) {
+    for (int64_t l = 0; l < h->n_levels; ++l) {
+      const int nn = h->level_node_ptr[l + 1] - h->level_node_ptr[l];
+      if (nn > 0) {
+        const int block = 256, grid = (int)(((int64_t)nn * 32 + block - 1) / block);
+        node_sum_kernel<<<grid, block, 0, h->stream>>>(d, h->d_node_order.p + h->level_node_ptr[l], nn);
+        ++launches;
+      }
+      const int nr = h->level_reach_ptr[l + 1] - h->level_reach_ptr[l];
+      if (nr > 0) {
+        const int block = 128, grid = (int)(((int64_t)nr * 32 + block - 1) / block);
+        reach_kernel<<<grid, block, 0, h->stream>>>(d, h->d_reach_order.p + h->level_reach_ptr[l], nr);
+        ++launches;
+      }
+    }
+    HB_CUDA(h, cudaGetLastError());
+    h->dis_cur = 1 - h->dis_cur;
+  }
+  h->timing.river_launches = launches;
+  return HB_OK;
+}
+
+int hb_run(hb_engine* h, int flags) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_run: call hb_set_land first");
+  HB_REQUIRE(h, h->have_forcing, HB_ESTATE, "hb_run: call hb_set_forcing first");
+  HB_REQUIRE(h, (flags & (HB_RUN_LAND | HB_RUN_RIVER)) != 0, HB_EINVAL, "hb_run: no work requested");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  if (flags & HB_RUN_LAND) HB_REQUIRE(h, h->have_states, HB_ESTATE, "hb_run: call hb_set_land_states first");
+  if (flags & HB_RUN_RIVER) {
+    HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_run: call hb_set_river first");
+    HB_REQUIRE(h, h->n_ext == 0 || h->have_ext, HB_ESTATE, "hb_run: call hb_set_external for this window first");
+    HB_REQUIRE(h, (flags & HB_RUN_LAND) || h->have_results, HB_ESTATE, "hb_run: routing needs the land results first");
+  }
+  int rc;
+  h->timing.land_ms = h->timing.river_ms = h->timing.total_ms = 0.0;
+  h->timing.n_levels = h->n_levels;
+  HB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  if (flags & HB_RUN_LAND) {
+    h->timing.river_launches = 0;
+    if ((rc = run_land(h))) return rc;
+    h->have_results = true;
+  }
+  HB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+  if (flags & HB_RUN_RIVER) {
+    if ((rc = run_river(h))) return rc;
+    h->have_routed = true;
+  }
+  HB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timing.land_ms = ms;
+  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->timing.river_ms = ms;
+  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->timing.total_ms = ms;
+  return HB_OK;
+}
+
+int hb_get_timing(hb_engine* h, hb_timing* out) {
+  if (!h || !out) return HB_EINVAL;
+  *out = h->timing;
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------------------------------
+static int download(hb_engine* h, double* dst, const double* src, size_t n) {
+  if (n) {
+    HB_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+int hb_get_land_outflow(hb_engine* h, double* rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_results, HB_ESTATE, "hb_get_land_outflow: no results (call hb_run)");
+  HB_REQUIRE(h, rows || h->n_elem * h->nt == 0, HB_EINVAL, "hb_get_land_outflow: NULL argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  return download(h, rows, h->d_land_rows.p, (size_t)h->n_elem * h->nt);
+}
+
+__global__ void gather_rows_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                   const int32_t* __restrict__ sel, int64_t n_sel, int64_t nt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sel * nt) return;
+  const int64_t r = i / nt, t = i - r * nt;
+  dst[i] = src[(int64_t)sel[r] * nt + t];
+}
+
+int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_node_series: no routing results (call hb_run)");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  if (n_sel == 0) {
+    HB_REQUIRE(h, rows || h->n_node * h->nt == 0, HB_EINVAL, "hb_get_node_series: NULL argument");
+    return download(h, rows, h->d_node_rows.p, (size_t)h->n_node * h->nt);
+  }
+  HB_REQUIRE(h, n_sel > 0 && nodes && rows, HB_EINVAL, "hb_get_node_series: invalid selection");
+  for (int64_t i = 0; i < n_sel; ++i)
+    HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node, HB_EINVAL, "hb_get_node_series: node %d out of range", nodes[i]);
+  int rc = upload(h, h->d_sel, nodes, (size_t)n_sel);
+  if (rc) return rc;
+  const size_t n = (size_t)n_sel * h->nt;
+  HB_CUDA(h, h->d_gather.reserve(n));
+  if (n) {
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_node_rows.p, h->d_gather.p, h->d_sel.p,
+                                                                           n_sel, h->nt);
+    HB_CUDA(h, cudaGetLastError());
+  }
+  return download(h, rows, h->d_gather.p, n);
+}
+
+int hb_get_reach_outflow(hb_engine* h, double* rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_reach_outflow: no routing results");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  return download(h, rows, h->d_reach_out.p, (size_t)h->n_reach * h->nt);
+}
+
+int hb_get_reach_inflow(hb_engine* h, double* rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_reach_inflow: no routing results");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  return download(h, rows, h->d_reach_in.p, (size_t)h->n_reach * h->nt);
+}
+
+int hb_get_series(hb_engine* h, int series, double* out) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, series >= 0 && series < HB_S_COUNT, HB_EINVAL, "hb_get_series: unknown series %d", series);
+  HB_REQUIRE(h, h->have_results && h->series_on[series] && h->d_series[series].p, HB_ESTATE,
+             "hb_get_series: series %d was not selected before hb_run", series);
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t width = series < HB_S_FIRST_SNOW ? h->n_zone : series < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+  return download(h, out, h->d_series[series].p, (size_t)h->nt * width);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// multi-GPU boundary hand-over
+// ---------------------------------------------------------------------------------------------------------------------
+#define HB_NCCL(h, call)                                                                                   \
+  do {                                                                                                     \
+    int rc__ = (call);                                                                                     \
+    if (rc__ != 0) return (h)->fail(HB_ENCCL, "%s failed: %s", #call, (h)->nccl.GetErrorString(rc__));     \
+  } while (0)
+
+int hb_comm_unique_id(hb_engine* h, void* id) {
+  if (!h || !id) return HB_EINVAL;
+  std::string err;
+  if (!h->nccl.load(err)) return h->fail(HB_ENCCL, "%s", err.c_str());
+  static_assert(sizeof(ncclUniqueId) == HB_NCCL_ID_BYTES, "ncclUniqueId size");
+  HB_NCCL(h, h->nccl.GetUniqueId((ncclUniqueId*)id));
+  return HB_OK;
+}
+
+int hb_comm_init(hb_engine* h, int rank, int world, const void* id) {
+  if (!h || !id) return HB_EINVAL;
+  HB_REQUIRE(h, world >= 1 && rank >= 0 && rank < world, HB_EINVAL, "hb_comm_init: invalid rank/world");
+  std::string err;
+  if (!h->nccl.load(err)) return h->fail(HB_ENCCL, "%s", err.c_str());
+  HB_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  HB_NCCL(h, h->nccl.CommInitRank(&h->comm, world, uid, rank));
+  h->rank = rank;
+  h->world = world;
+  return HB_OK;
+}
+
+int hb_comm_send_nodes(hb_engine* h, int peer, int64_t n, const int32_t* nodes) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_send_nodes: call hb_comm_init first");
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_comm_send_nodes: no routing results");
+  HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || nodes), HB_EINVAL,
+             "hb_comm_send_nodes: invalid argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_NCCL(h, h->nccl.GroupStart());
+  for (int64_t i = 0; i < n; ++i) {
+    HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node, HB_EINVAL, "hb_comm_send_nodes: node out of range");
+    // the routing kernels wrote the row in place: it is sent straight from the node-row buffer
+    HB_NCCL(h, h->nccl.Send(h->d_node_rows.p + (int64_t)nodes[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
+                            h->stream));
+  }
+  HB_NCCL(h, h->nccl.GroupEnd());
+  return HB_OK;
+}
+
+int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_recv_ext: call hb_comm_init first");
+  HB_REQUIRE(h, h->have_river && h->have_forcing, HB_ESTATE, "hb_comm_recv_ext: river/window not set");
+  HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || ext_rows), HB_EINVAL,
+             "hb_comm_recv_ext: invalid argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, h->d_ext_rows.reserve((size_t)h->n_ext * h->nt));
+  HB_NCCL(h, h->nccl.GroupStart());
+  for (int64_t i = 0; i < n; ++i) {
+    HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row out of range");
+    // received straight into the external-row buffer the reach kernels read
+    HB_NCCL(h, h->nccl.Recv(h->d_ext_rows.p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
+                            h->stream));
+  }
+  HB_NCCL(h, h->nccl.GroupEnd());
+  h->have_ext = true;
+  return HB_OK;
+}
+
+int hb_comm_barrier(hb_engine* h) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_barrier: call hb_comm_init first");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, h->d_commbuf.reserve(1));
+  HB_CUDA(h, cudaMemsetAsync(h->d_commbuf.p, 0, sizeof(double), h->stream));
+  HB_NCCL(h, h->nccl.AllReduce(h->d_commbuf.p, h->d_commbuf.p, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+"""ctypes binding of `libhydpy_b200.so` — the only compute path of this package.
+
+`Engine` mirrors the C-ABI of `include/hydpy_b200.h` one to one.  There is no CPU implementation behind it: if the
+shared library is missing or no sm_100 device is usable, every entry point raises (`EngineUnavailable`), it never
+falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import layout
+from .abi import (LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc, hb_timing, ptr)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libhydpy_b200.so")
+
+EXPORTS = (
+    "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
+    "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
+    "hb_select_series", "hb_set_forcing", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
+    "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
+    "hb_comm_send_nodes", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_device_info",
+)
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA engine cannot be used (library not built, or no B200-class device)."""
+
+
+class EngineError(RuntimeError):
+    """A call into libhydpy_b200.so failed; the message carries `hb_last_error`."""
+
+
+_lib: C.CDLL | None = None
+
+
+def load_library() -> C.CDLL:
+    """Load `libhydpy_b200.so` (built in-tree by `python -m hydpy_b200.build`) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise EngineUnavailable(
+            f"{LIBPATH} does not exist; build it with `python -m hydpy_b200.build` (needs nvcc). "
+            "hydpy_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIBPATH)
+    H = C.c_void_p
+    f64p, i32p, i64p = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    proto = {
+        "hb_abi_version": (C.c_int, []),
+        "hb_create": (C.c_int, [C.c_int, C.POINTER(H)]),
+        "hb_destroy": (None, [H]),
+        "hb_last_error": (C.c_char_p, [H]),
+        "hb_host_alloc": (C.c_int, [H, C.c_int64, C.POINTER(C.c_void_p)]),
+        "hb_host_free": (C.c_int, [H, C.c_void_p]),
+        "hb_set_land": (C.c_int, [H, C.POINTER(hb_land_desc)]),
+        "hb_set_land_states": (C.c_int, [H, C.POINTER(hb_land_states)]),
+        "hb_get_land_states": (C.c_int, [H, C.POINTER(hb_land_states)]),
+        "hb_set_river": (C.c_int, [H, C.POINTER(hb_river_desc)]),
+        "hb_set_river_states": (C.c_int, [H, f64p]),
+        "hb_get_river_states": (C.c_int, [H, f64p]),
+        "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
+        "hb_set_forcing": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
+        "hb_set_external": (C.c_int, [H, C.c_int64, f64p]),
+        "hb_run": (C.c_int, [H, C.c_int]),
+        "hb_get_land_outflow": (C.c_int, [H, f64p]),
+        "hb_get_node_series": (C.c_int, [H, C.c_int64, i32p, f64p]),
+        "hb_get_reach_outflow": (C.c_int, [H, f64p]),
+        "hb_get_reach_inflow": (C.c_int, [H, f64p]),
+        "hb_get_series": (C.c_int, [H, C.c_int, f64p]),
+        "hb_comm_unique_id": (C.c_int, [H, C.c_void_p]),
+        "hb_comm_init": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
+        "hb_comm_send_nodes": (C.c_int, [H, C.c_int, C.c_int64, i32p]),
+        "hb_comm_recv_ext": (C.c_int, [H, C.c_int, C.c_int64, i32p]),
+        "hb_comm_barrier": (C.c_int, [H]),
+        "hb_get_timing": (C.c_int, [H, C.POINTER(hb_timing)]),
+        "hb_device_info": (C.c_int, [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    }
+    assert set(proto) == set(EXPORTS)
+    for name, (res, args) in proto.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hb_abi_version() != layout.ABI_VERSION:
+        raise EngineUnavailable(
+            f"{LIBPATH} has ABI version {lib.hb_abi_version()}, the Python layer expects {layout.ABI_VERSION}; rebuild"
+        )
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    """Number of CUDA devices the driver offers (0 if the driver is absent)."""
+    try:
+        cudart = C.CDLL("libcudart.so")
+    except OSError:
+        try:
+            import glob
+
+            cands = sorted(glob.glob("/usr/local/cuda/lib64/libcudart.so*"))
+            cudart = C.CDLL(cands[-1]) if cands else None
+        except OSError:
+            cudart = None
+    if cudart is None:
+        return 0
+    n = C.c_int(0)
+    rc = cudart.cudaGetDeviceCount(C.byref(n))
+    return int(n.value) if rc == 0 else 0
+
+
+class PinnedArray:
+    """A float64/int64 NumPy array backed by page-locked host memory of the engine (`hb_host_alloc`)."""
+
+    def __init__(self, engine: "Engine", shape: Sequence[int], dtype=np.float64):
+        self._engine = engine
+        self.shape = tuple(int(s) for s in shape)
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * dtype.itemsize
+        p = C.c_void_p()
+        engine._check(engine._lib.hb_host_alloc(engine._h, nbytes, C.byref(p)), "hb_host_alloc")
+        self._p = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def free(self) -> None:
+        if self._p is not None and self._engine._h:
+            self.array = None  # type: ignore[assignment]
+            self._engine._lib.hb_host_free(self._engine._h, self._p)
+        self._p = None
+
+
+class Engine:
+    """One engine = one GPU (`hb_create`).  Methods map 1:1 to the C entry points."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.hb_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = (self._lib.hb_last_error(None) or b"").decode()
+            self._h = C.c_void_p()
+            raise EngineUnavailable(f"hb_create(device={device}) failed with code {rc}: {msg}")
+        self.device = int(device)
+        self.land: LandBundle | None = None
+        self.river: RiverBundle | None = None
+        self.nt = 0
+        self._keep: list[object] = []
+
+    # -- plumbing ---------------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = (self._lib.hb_last_error(self._h) or b"").decode()
+            raise EngineError(f"{what} failed with code {rc}: {msg}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.hb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "Engine":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    def pinned(self, shape: Sequence[int], dtype=np.float64) -> PinnedArray:
+        return PinnedArray(self, shape, dtype)
+
+    def device_info(self) -> dict[str, object]:
+        sm, khz = C.c_int(0), C.c_int(0)
+        name = C.create_string_buffer(256)
+        self._check(self._lib.hb_device_info(self._h, C.byref(sm), C.byref(khz), name, 256), "hb_device_info")
+        return {"name": name.value.decode(), "sm_count": sm.value, "clock_khz": khz.value}
+
+    # -- setup ------------------------------------------------------------------------------------------------------
+    def set_land(self, land: LandBundle) -> None:
+        d = land.as_struct()
+        self._check(self._lib.hb_set_land(self._h, C.byref(d)), "hb_set_land")
+        self.land = land
+
+    def set_land_states(self, states: LandStates) -> None:
+        s = states.as_struct()
+        self._check(self._lib.hb_set_land_states(self._h, C.byref(s)), "hb_set_land_states")
+
+    def get_land_states(self) -> LandStates:
+        land = self._need_land()
+        st = LandStates(
+            ic=np.zeros(land.n_zone), sm=np.zeros(land.n_zone), sp=np.zeros(land.n_snow), wc=np.zeros(land.n_snow),
+            uz=np.zeros(land.n_elem), lz=np.zeros(land.n_elem), quh=np.zeros(land.n_uh),
+        )
+        s = st.as_struct()
+        self._check(self._lib.hb_get_land_states(self._h, C.byref(s)), "hb_get_land_states")
+        return st
+
+    def set_river(self, river: RiverBundle) -> None:
+        d = river.as_struct()
+        self._check(self._lib.hb_set_river(self._h, C.byref(d)), "hb_set_river")
+        self.river = river
+
+    def set_river_states(self, discharge: np.ndarray) -> None:
+        river = self._need_river()
+        discharge = np.ascontiguousarray(discharge, dtype=np.float64)
+        if discharge.shape != (river.n_seg,):
+            raise ValueError(f"discharge must have shape ({river.n_seg},), not {discharge.shape}")
+        self._check(self._lib.hb_set_river_states(self._h, ptr(discharge, C.c_double)), "hb_set_river_states")
+
+    def get_river_states(self) -> np.ndarray:
+        river = self._need_river()
+        out = np.zeros(river.n_seg)
+        self._check(self._lib.hb_get_river_states(self._h, ptr(out, C.c_double)), "hb_get_river_states")
+        return out
+
+    def select_series(self, names: Iterable[str]) -> None:
+        names = set(names)
+        unknown = names - set(layout.SERIES)
+        if unknown:
+            raise ValueError(f"unknown series: {sorted(unknown)}")
+        for name in layout.SERIES:
+            self._check(self._lib.hb_select_series(self._h, layout.S[name], int(name in names)), "hb_select_series")
+
+    # -- window -----------------------------------------------------------------------------------------------------
+    def set_forcing(self, forcing: np.ndarray, doy: np.ndarray) -> None:
+        forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+        if forcing.ndim != 3 or forcing.shape[0] != len(layout.FORCING):
+            raise ValueError(f"forcing must have shape (4, nt, n_col), not {forcing.shape}")
+        doy = np.ascontiguousarray(doy, dtype=np.int64)
+        nt, ncol = forcing.shape[1], forcing.shape[2]
+        if doy.shape != (nt,):
+            raise ValueError(f"doy must have shape ({nt},), not {doy.shape}")
+        land = self._need_land()
+        if land.n_elem and int(land.forcing_col.max()) >= ncol:
+            raise ValueError("forcing has fewer columns than `forcing_col` refers to")
+        self._check(self._lib.hb_set_forcing(self._h, nt, ncol, ptr(forcing, C.c_double), ptr(doy, C.c_int64)),
+                    "hb_set_forcing")
+        self.nt = nt
+
+    def set_external(self, rows: np.ndarray) -> None:
+        river = self._need_river()
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(river.n_ext, self.nt)
+        self._check(self._lib.hb_set_external(self._h, self.nt, ptr(rows, C.c_double)), "hb_set_external")
+
+    def run(self, land: bool = True, river: bool = True) -> None:
+        flags = (layout.RUN_LAND if land else 0) | (layout.RUN_RIVER if river else 0)
+        self._check(self._lib.hb_run(self._h, flags), "hb_run")
+
+    # -- results ----------------------------------------------------------------------------------------------------
+    def get_land_outflow(self, out: np.ndarray | None = None) -> np.ndarray:
+        land = self._need_land()
+        out = self._out(out, (land.n_elem, self.nt))
+        self._check(self._lib.hb_get_land_outflow(self._h, ptr(out, C.c_double)), "hb_get_land_outflow")
+        return out
+
+    def get_node_series(self, nodes: Sequence[int] | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        river = self._need_river()
+        if nodes is None:
+            out = self._out(out, (river.n_node, self.nt))
+            self._check(self._lib.hb_get_node_series(self._h, 0, None, ptr(out, C.c_double)), "hb_get_node_series")
+            return out
+        sel = np.ascontiguousarray(nodes, dtype=np.int32)
+        out = self._out(out, (len(sel), self.nt))
+        if len(sel):
+            self._check(self._lib.hb_get_node_series(self._h, len(sel), ptr(sel, C.c_int32), ptr(out, C.c_double)),
+                        "hb_get_node_series")
+        return out
+
+    def get_reach_outflow(self) -> np.ndarray:
+        river = self._need_river()
+        out = np.zeros((river.n_reach, self.nt))
+        self._check(self._lib.hb_get_reach_outflow(self._h, ptr(out, C.c_double)), "hb_get_reach_outflow")
+        return out
+
+    def get_reach_inflow(self) -> np.ndarray:
+        river = self._need_river()
+        out = np.zeros((river.n_reach, self.nt))
+        self._check(self._lib.hb_get_reach_inflow(self._h, ptr(out, C.c_double)), "hb_get_reach_inflow")
+        return out
+
+    def get_series(self, name: str) -> np.ndarray:
+        land = self._need_land()
+        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_elem
+        out = np.zeros((self.nt, width))
+        self._check(self._lib.hb_get_series(self._h, layout.S[name], ptr(out, C.c_double)), "hb_get_series")
+        return out
+
+    def timing(self) -> dict[str, float]:
+        t = hb_timing()
+        self._check(self._lib.hb_get_timing(self._h, C.byref(t)), "hb_get_timing")
+        return {n: getattr(t, n) for n, _ in hb_timing._fields_}
+
+    # -- multi-GPU --------------------------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(layout.NCCL_ID_BYTES)
+        self._check(self._lib.hb_comm_unique_id(self._h, buf), "hb_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes) -> None:
+        if len(uid) != layout.NCCL_ID_BYTES:
+            raise ValueError("NCCL unique id must have 128 bytes")
+        buf = C.create_string_buffer(uid, layout.NCCL_ID_BYTES)
+        self._check(self._lib.hb_comm_init(self._h, rank, world, buf), "hb_comm_init")
+
+    def comm_send_nodes(self, peer: int, nodes: Sequence[int]) -> None:
+        sel = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._check(self._lib.hb_comm_send_nodes(self._h, peer, len(sel), ptr(sel, C.c_int32)), "hb_comm_send_nodes")
+
+    def comm_recv_ext(self, peer: int, rows: Sequence[int]) -> None:
+        sel = np.ascontiguousarray(rows, dtype=np.int32)
+        self._check(self._lib.hb_comm_recv_ext(self._h, peer, len(sel), ptr(sel, C.c_int32)), "hb_comm_recv_ext")
+
+    def comm_barrier(self) -> None:
+        self._check(self._lib.hb_comm_barrier(self._h), "hb_comm_barrier")
+
+    # -- helpers ----------------------------------------------------------------------------------------------------
+    def _need_land(self) -> LandBundle:
+        if self.land is None:
+            raise EngineError("no land description set (call set_land first)")
+        return self.land
+
+    def _need_river(self) -> RiverBundle:
+        if self.river is None:
+            raise EngineError("no river description set (call set_river first)")
+        return self.river
+
+    @staticmethod
+    def _out(out: np.ndarray | None, shape: tuple[int, ...]) -> np.ndarray:
+        if out is None:
+            return np.zeros(shape)
+        if out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"output array must be C-contiguous float64 of shape {shape}")
+        return out

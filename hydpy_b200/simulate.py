@@ -1,0 +1,114 @@
+"""The drop-in for `HydPy.simulate()` (ref: hydpy/core/hydpytools.py:2769-2952) on the B200 engine.
+
+    import hydpy_b200
+    hydpy_b200.simulate(hp)          # instead of hp.simulate()
+    hydpy_b200.install()             # or: make hp.simulate() itself use the engine
+
+Contract after return, for `[i0, i1) = pub.timegrids.simindices` (seam #1):
+  * `node.sequences.sim.series[i0:i1]` and `sim.value` of every node the run simulates;
+  * `series[i0:i1]` of every hland_96 factor/flux/state sequence and musk_classic inflow/outflow kept in RAM;
+  * final `states` (new and old) and `logs.quh`, so that a following window continues seamlessly.
+Projects containing anything but hland_96(+evap_aet_hbv96/evap_pet_hbv96, rconc_uh) and musk_classic raise
+`UnsupportedModelError` — there is no silent CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterable
+
+import numpy as np
+
+from .abi import LandStates
+from .engine import Engine
+from .extract import Problem, extract, requested_series, write_back
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """The process-wide engine of a device (created on first use)."""
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+def run_problem(problem: Problem, engine: Engine | None = None, *, series: Iterable[str] = (),
+                window: int | None = None, device: int = 0) -> dict[str, Any]:
+    """Run an extracted problem on the engine, optionally in time windows of `window` steps.
+
+    Returns the keyword arguments of `extract.write_back` (states, discharge, node_rows, land_rows, reach_out,
+    reach_in, series).
+    """
+    eng = engine if engine is not None else get_engine(device)
+    series = list(series)
+    nt = problem.nt
+    eng.set_land(problem.land)
+    eng.set_land_states(problem.states)
+    eng.set_river(problem.river)
+    eng.set_river_states(problem.discharge)
+    eng.select_series(series)
+    window = nt if not window or window <= 0 else min(int(window), nt)
+    node_rows = np.zeros((problem.river.n_node, nt))
+    land_rows = np.zeros((problem.land.n_elem, nt))
+    reach_out = np.zeros((problem.river.n_reach, nt))
+    reach_in = np.zeros((problem.river.n_reach, nt))
+    out_series = {name: [] for name in series}
+    t0 = 0
+    while t0 < nt or (nt == 0 and t0 == 0):
+        t1 = min(t0 + max(window, 1), nt)
+        eng.set_forcing(problem.forcing[:, t0:t1, :], problem.doy[t0:t1])
+        eng.set_external(problem.ext[:, t0:t1])
+        eng.run(land=True, river=True)
+        if t1 > t0:
+            land_rows[:, t0:t1] = eng.get_land_outflow()
+            node_rows[:, t0:t1] = eng.get_node_series()
+            reach_out[:, t0:t1] = eng.get_reach_outflow()
+            reach_in[:, t0:t1] = eng.get_reach_inflow()
+            for name in series:
+                out_series[name].append(eng.get_series(name))
+        t0 = t1
+        if nt == 0:
+            break
+    states: LandStates = eng.get_land_states()
+    discharge = eng.get_river_states()
+    return dict(
+        states=states, discharge=discharge, node_rows=node_rows, land_rows=land_rows, reach_out=reach_out,
+        reach_in=reach_in, series={n: np.concatenate(v, axis=0) for n, v in out_series.items() if v},
+    )
+
+
+def simulate(hp: Any, *, device: int = 0, window: int | None = None, engine: Engine | None = None) -> None:
+    """Perform the simulation run of `hp` over `pub.timegrids.sim` on the B200 engine."""
+    import hydpy  # the reference package owns objects, files and time grids
+
+    i0, i1 = hydpy.pub.timegrids.simindices
+    problem = extract(hp, i0, i1)
+    result = run_problem(problem, engine, series=requested_series(problem), window=window, device=device)
+    write_back(problem, **result)
+
+
+_original_simulate = None
+
+
+def install(device: int = 0, window: int | None = None) -> None:
+    """Monkey-patch `hydpy.HydPy.simulate` so that existing scripts use the engine unchanged."""
+    global _original_simulate
+    from hydpy.core import hydpytools
+
+    if _original_simulate is None:
+        _original_simulate = hydpytools.HydPy.simulate
+
+    def _simulate(self: Any) -> None:
+        simulate(self, device=device, window=window)
+
+    _simulate.__doc__ = simulate.__doc__
+    hydpytools.HydPy.simulate = _simulate  # type: ignore[method-assign]
+
+
+def uninstall() -> None:
+    """Undo `install`."""
+    global _original_simulate
+    if _original_simulate is not None:
+        from hydpy.core import hydpytools
+
+        hydpytools.HydPy.simulate = _original_simulate  # type: ignore[method-assign]
+        _original_simulate = None

