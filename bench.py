@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — zone-timesteps/s of the hland_96 + musk_classic hot path on N B200s (contract: see the task prompt).
+
+Workload (``config.workload``): BASELINE.json configs[3] — the synthetic 10^5-element hland_96 + 10^5-reach
+musk_classic river tree (≈200 topological levels), HOURLY, discharge-only output — the configuration the
+north_star's ≥100x target is quoted on.  One *step* = one simulation window of ``--window`` hours (default 240 = 10 days)
+for ALL elements followed by routing through the whole network; consecutive steps continue the same simulation
+(states stay on the device), so K steps simulate K*window hours of the 10-year period.
+
+* ``value``  — whole-job zone-timesteps/s with the forcing of all K windows already resident in HBM (device time, CUDA
+  events on the engine stream, max over ranks).
+* ``e2e``    — the same loop through the public API with HOST buffers: every step copies that window's forcing from
+  pinned host memory to the device and reads every node's discharge series back to pinned host memory.
+* N > 1     — weak scaling, element-sharded: every rank owns one 10^5-element sub-basin; the outlet reach of each
+  upstream shard hands its outflow series to the shard owning the downstream node with NCCL send/recv over NVLink
+  (the one real exchange step of the path).
+* ``--impl reference`` — the reference's own CPU implementation of the same window on a bounded element sample with all
+  host threads (oracle/_ref = unmodified reference binaries when present, else the C restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "zone-timesteps/sec (hland_96+musk)"
+UNIT = "zone-timesteps/s"
+
+
+def parse_args() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("engine", "reference"), default="engine")
+    ap.add_argument("--elements", type=int, default=100_000, help="hland_96 elements per GPU")
+    ap.add_argument("--window", type=int, default=240, help="simulation steps (hours) per bench step")
+    ap.add_argument("--levels", type=int, default=200)
+    ap.add_argument("--cpu-elements", type=int, default=0, help="element sample of the CPU baseline (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# distributed plumbing (torch.distributed only for rendezvous / barrier / reductions; the data path is the engine's NCCL)
+# ---------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self) -> None:
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group(backend="gloo", rank=self.rank, world_size=self.world)
+            self.pg = dist
+
+    def barrier(self) -> None:
+        if self.pg is not None:
+            self.pg.barrier()
+
+    def max(self, value: float) -> float:
+        if self.pg is None:
+            return value
+        import torch
+
+        t = torch.tensor([value], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, value: float) -> float:
+        if self.pg is None:
+            return value
+        import torch
+
+        t = torch.tensor([value], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.SUM)
+        return float(t[0])
+
+    def bcast_bytes(self, data: bytes | None, n: int) -> bytes:
+        if self.pg is None:
+            assert data is not None
+            return data
+        import torch
+
+        t = torch.zeros(n, dtype=torch.uint8)
+        if self.rank == 0:
+            t[:] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        self.pg.broadcast(t, src=0)
+        return bytes(t.numpy().tobytes())
+
+    def close(self) -> None:
+        if self.pg is not None:
+            self.pg.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int) -> None:
+        self.proc = None
+        self.path = None
+        exe = shutil.which("nvidia-smi")
+        if exe:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                [exe, f"--id={device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self) -> dict | None:
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------------
+def build_shard(args: argparse.Namespace, rank: int, world: int):
+    """Sub-basin of one rank: land elements, river tree and — for world > 1 — the cut edges."""
+    from hydpy_b200 import layout, synth
+
+    land, states = synth.make_land(args.elements, "1h", seed=1 + rank)
+    river, discharge = synth.make_tree_river(args.elements, "1h", seed=2 + rank, levels=args.levels)
+    if world > 1:
+        rng = np.random.default_rng(100 + rank)
+        if rank == 0:
+            # the root node additionally receives the outflow of every upstream shard as external rows
+            ext_entries = [layout.ENTRY_EXT - k for k in range(world - 1)]
+            src = river.entry_src.tolist()
+            end0 = int(river.entry_ptr[1])
+            src[end0:end0] = ext_entries
+            river.entry_src = np.array(src, np.int32)
+            river.entry_ptr = river.entry_ptr.copy()
+            river.entry_ptr[1:] += len(ext_entries)
+            river.n_ext = world - 1
+        else:
+            # one more reach routes this shard's root node towards the downstream shard (owner of the reach = upstream)
+            nseg = int(rng.integers(1, 24))
+            damp = float(rng.uniform(0, 1))
+            c0 = damp / (1.0 + damp)
+            river.inlet_ptr = np.append(river.inlet_ptr, river.inlet_ptr[-1] + 1)
+            river.inlet_node = np.append(river.inlet_node, 0).astype(np.int32)
+            river.reach_outlet = np.append(river.reach_outlet, -1).astype(np.int32)
+            river.seg_ptr = np.append(river.seg_ptr, river.seg_ptr[-1] + nseg + 1)
+            river.coef = np.concatenate([river.coef, np.array([[c0], [1 - 2 * c0], [c0]])], axis=1)
+            discharge = np.concatenate([discharge, np.zeros(nseg + 1)])
+        river.normalise()
+    return land, states, river, discharge
+
+
+def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
+    from hydpy_b200 import Engine, synth
+
+    K, W, win = args.steps, args.warmup, args.window
+    eng = Engine(dist.local_rank)
+    info = eng.device_info()
+    land, states, river, discharge = build_shard(args, dist.rank, dist.world)
+    eng.set_land(land)
+    eng.set_land_states(states)
+    eng.set_river(river)
+    eng.set_river_states(discharge)
+    if dist.world > 1:
+        uid = dist.bcast_bytes(eng.comm_unique_id() if dist.rank == 0 else None, 128)
+        eng.comm_init(dist.rank, dist.world, uid)
+    boundary_reach = river.n_reach - 1
+    no_ext = np.zeros((0, win))
+
+    def step_exchange_and_route() -> None:
+        """land → (NVLink hand-over of the boundary series) → routing, for the currently selected window."""
+        if dist.world == 1:
+            eng.set_external(no_ext)
+            eng.run(land=True, river=True)
+        elif dist.rank == 0:
+            eng.run(land=True, river=False)
+            for peer in range(1, dist.world):
+                eng.comm_recv_ext(peer, [peer - 1])
+            eng.run(land=False, river=True)
+        else:
+            eng.set_external(no_ext)
+            eng.run(land=True, river=True)
+            eng.comm_send_rows(0, [boundary_reach], kind="reach")
+
+    n_steps = W + K
+    # ---- forcing of all windows: generated up front (synthetic, seeded per window) in pinned host memory ----------------
+    pinned = eng.pinned((n_steps, 4, win, 1024))
+    doys = np.zeros((n_steps, win), np.int64)
+    for s in range(n_steps):
+        f, doys[s] = synth.make_forcing(win, "1h", seed=dist.rank, t0=s * win)
+        pinned.array[s] = f
+    zone_steps_per_step = land.n_zone * win
+    launches = 0
+
+    # ================= device-resident run (value) =====================================================================
+    block = np.ascontiguousarray(np.concatenate(list(pinned.array), axis=1))      # [4, n_steps*win, 1024]
+    eng.set_forcing(block, doys.reshape(-1))
+    del block
+    land_ms, river_ms = [], []
+    dist.barrier()
+    for s in range(W):
+        eng.select_window(s * win, win)
+        step_exchange_and_route()
+    dist.barrier()
+    sampler = ClockSampler(dist.local_rank)
+    eng.timer_start()
+    t_wall = time.perf_counter()
+    for s in range(W, W + K):
+        eng.select_window(s * win, win)
+        step_exchange_and_route()
+        tm = eng.timing()
+        land_ms.append(tm["land_ms"])
+        river_ms.append(tm["river_ms"])
+        launches += int(tm["land_launches"] + tm["river_launches"])
+    device_ms = eng.timer_stop()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks = sampler.stop()
+    dist.barrier()
+    device_ms_max = dist.max(device_ms)
+    total_zone_steps = dist.sum(float(zone_steps_per_step * K))
+    value = total_zone_steps / (device_ms_max * 1e-3)
+    n_levels = int(eng.timing()["n_levels"])
+    states_after_value = eng.get_land_states()
+
+    # ================= end-to-end run through the public API with host buffers (e2e) =====================================
+    eng.set_land_states(states)
+    eng.set_river_states(discharge)
+    out = eng.pinned((river.n_node, win))
+    h2d = 4 * win * 1024 * 8 + win * 8
+    d2h = river.n_node * win * 8
+    dist.barrier()
+    for s in range(W):
+        eng.set_forcing(pinned.array[s], doys[s])
+        step_exchange_and_route()
+        eng.get_node_series(out=out.array)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        eng.set_forcing(pinned.array[s], doys[s])
+        step_exchange_and_route()
+        eng.get_node_series(out=out.array)
+    e2e_s = time.perf_counter() - t0
+    dist.barrier()
+    e2e_s_max = dist.max(e2e_s)
+    e2e_value = total_zone_steps / e2e_s_max
+    checksum = float(out.array[0].sum())
+    states_after_e2e = eng.get_land_states()
+    same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
+
+    # ================= roofline of the dominant kernel (runoff generation) ===============================================
+    fp64_peak = eng.measure_fp64_peak()
+    R, U, Z = int(land.recstep[0]), int(land.uh_ptr[1] - land.uh_ptr[0]), land.n_zone / land.n_elem
+    ops_per_zone_step = 130.0 + (14.0 * R + 2.0 * U + 32.0) / Z          # SURVEY.md §8(d), div = pow = exp = 1 op
+    land_ms_avg = float(np.mean(land_ms))
+    achieved_tops = ops_per_zone_step * zone_steps_per_step / (land_ms_avg * 1e-3) / 1e12
+    bytes_per_launch = (4 * 8 + 8) * land.n_elem * win                     # 4 forcing doubles in + qt out per element-step
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
+        "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, hourly, discharge-only",
+            "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
+            "river_levels": n_levels, "window_steps": win, "recstep_per_step": R, "uh_ordinates": U,
+            "forcing_bank": 1024, "parallelism": f"element-sharded x{dist.world}" if dist.world > 1 else "single GPU",
+            "l2": "working set (zone constants 307 MB + states 38 MB + series) exceeds the 126 MB L2; no flush needed",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {"runoff_generation": land_ms_avg, "routing": float(np.mean(river_ms)),
+                               "wall": wall_ms / K},
+        "roofline": {
+            "bound": "fp64", "achieved": achieved_tops, "peak": fp64_peak / 2.0, "unit": "Top/s (FP64 ops, FMA = 1)",
+            "frac": achieved_tops / (fp64_peak / 2.0), "traffic": None,
+            "kernel": "land_kernel<false>", "ops_per_zone_step": ops_per_zone_step,
+            "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run)", "fp64_tflops_measured": fp64_peak,
+            "hbm": {"achieved": bytes_per_launch / (land_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_per_launch / (land_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+        },
+        "clocks": clocks, "device": info, "checksum": checksum,
+    }
+    pinned.free()
+    out.free()
+    eng.close()
+    return result
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_run(args: argparse.Namespace, steps: int, warmup: int, elements: int) -> dict:
+    """The reference's CPU implementation on a bounded sample of the same workload: `elements` land elements of shard 0
+    (+ their river sub-tree), `window` hours per step, all host threads."""
+    from hydpy_b200 import synth
+    from oracle import oracle, refdriver
+
+    cores = os.cpu_count() or 1
+    win = args.window
+    land, states = synth.make_land(elements, "1h", seed=1)
+    river, discharge = synth.make_tree_river(elements, "1h", seed=2, levels=max(2, args.levels * elements // args.elements))
+    kind = "reference" if refdriver.available() else "port"
+    zone_steps = land.n_zone * win
+    times = []
+    for s in range(warmup + steps):
+        forcing, doy = synth.make_forcing(win, "1h", seed=0, t0=s * win)
+        if kind == "reference":
+            els = refdriver.prepare_land(land, states, forcing, doy)       # object set-up is not timed
+            t0 = time.perf_counter()
+            qt = refdriver.run_land(els, threads=cores)
+            t_land = time.perf_counter() - t0
+            for el in els:
+                el.store_states(land, states)
+        else:
+            t0 = time.perf_counter()
+            qt, _ = oracle.land_run(land, states, forcing, doy, threads=cores)
+            t_land = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.river_run(river, discharge, qt, None)                       # routing: C restatement (≈1 % of the time)
+        t_river = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(t_land + t_river)
+    total = float(np.sum(times))
+    value = zone_steps * steps / total
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{elements} of {args.elements} elements ({land.n_zone} zones) x {win} hourly steps per step, "
+                      f"{steps} steps, runoff generation on {cores} threads"
+                      f" ({'unmodified reference binaries oracle/_ref' if kind == 'reference' else 'C restatement'})"
+                      f" + routing", "ms_per_step": 1e3 * total / steps}
+
+
+def auto_cpu_elements(args: argparse.Namespace) -> int:
+    if args.cpu_elements:
+        return args.cpu_elements
+    cores = os.cpu_count() or 1
+    # ≈3 µs per element-step and thread: aim at ≈2 s of wall time per step
+    n = int(2.0 * cores / (3e-6 * args.window))
+    return int(max(256, min(args.elements, n // 64 * 64)))
+
+
+def main() -> None:
+    args = parse_args()
+    dist = Dist()
+    if args.gpus != dist.world and dist.world > 1:
+        args.gpus = dist.world
+    try:
+        if args.impl == "reference":
+            if dist.rank == 0:
+                base = cpu_run(args, args.steps, args.warmup, auto_cpu_elements(args))
+                line = {
+                    "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic",
+                    "config": {"workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, "
+                                           "hourly, discharge-only (bounded element sample on the host CPU)",
+                               "window_steps": args.window},
+                    "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0,
+                }
+                print(json.dumps(line), flush=True)
+            return
+        result = run_engine(args, dist)
+        if dist.rank == 0:
+            if dist.world == 1 and not args.no_cpu_baseline:
+                base = cpu_run(args, steps=2, warmup=1, elements=auto_cpu_elements(args))
+                result["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            print(json.dumps(result), flush=True)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

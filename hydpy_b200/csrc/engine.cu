@@ -34,10 +34,11 @@ struct DBuf {  // device buffer that only grows
     cap = 0;
   }
   cudaError_t reserve(size_t n) {
+    if (n == 0) n = 1;  // never hand out NULL: empty arrays stay addressable
     if (n <= cap) return cudaSuccess;
     release();
-    cudaError_t rc = cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T));
-    if (rc == cudaSuccess) cap = n ? n : 1;
+    cudaError_t rc = cudaMalloc((void**)&p, n * sizeof(T));
+    if (rc == cudaSuccess) cap = n;
     else p = nullptr;
     return rc;
   }
@@ -86,6 +87,7 @@ struct hb_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_stop = nullptr;
   std::string error;
   cudaDeviceProp prop{};
 
@@ -104,7 +106,7 @@ struct hb_engine {
   DBuf<double> d_series[HB_S_COUNT];
 
   // ---- window ----
-  int64_t nt = 0, n_col = 0;
+  int64_t nt = 0, n_col = 0, nt_total = 0, t0 = 0;
   bool have_forcing = false, have_results = false, have_routed = false;
   DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows;
 
@@ -209,6 +211,7 @@ void hb_destroy(hb_engine* h) {
   cudaStreamSynchronize(h->stream);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -491,6 +494,9 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
       const int32_t s = r->entry_src[i];
       if (s >= 0) HB_REQUIRE(h, s < h->n_elem, HB_EINVAL, "hb_set_river: node %lld entry refers to land element %d of %lld",
                              (long long)n, s, (long long)h->n_elem);
+      else if (s <= HB_ENTRY_EXT)
+        HB_REQUIRE(h, HB_ENTRY_EXT - s < r->n_ext, HB_EINVAL, "hb_set_river: node %lld entry refers to external row %d",
+                   (long long)n, HB_ENTRY_EXT - s);
       else {
         HB_REQUIRE(h, -1 - s < nr, HB_EINVAL, "hb_set_river: node %lld entry refers to reach %d", (long long)n, -1 - s);
         node_pending[n]++;
@@ -608,7 +614,8 @@ int hb_get_river_states(hb_engine* h, double* discharge) {
 int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
   if (!h) return HB_EINVAL;
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_forcing: call hb_set_land first");
-  HB_REQUIRE(h, nt >= 0 && n_col >= 1 && (nt == 0 || (forcing && doy)), HB_EINVAL, "hb_set_forcing: invalid argument");
+  HB_REQUIRE(h, nt >= 0 && n_col >= (h->n_elem ? 1 : 0) && (nt == 0 || doy) && (nt * n_col == 0 || forcing), HB_EINVAL,
+             "hb_set_forcing: invalid argument (nt=%lld, n_col=%lld)", (long long)nt, (long long)n_col);
   HB_CUDA(h, cudaSetDevice(h->device));
   const size_t n = (size_t)HB_FORCING_COUNT * nt * n_col;
   HB_CUDA(h, h->d_forcing.reserve(n));
@@ -621,8 +628,24 @@ int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcin
   int rc = upload(h, h->d_sinfactor, sf);
   if (rc) return rc;
   h->nt = nt;
+  h->nt_total = nt;
+  h->t0 = 0;
   h->n_col = n_col;
   h->have_forcing = true;
+  h->have_results = false;
+  h->have_routed = false;
+  h->have_ext = false;
+  return HB_OK;
+}
+
+int hb_select_window(hb_engine* h, int64_t t0, int64_t nt) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_forcing, HB_ESTATE, "hb_select_window: call hb_set_forcing first");
+  HB_REQUIRE(h, t0 >= 0 && nt >= 0 && t0 + nt <= h->nt_total, HB_EINVAL,
+             "hb_select_window: [%lld, %lld) is outside the staged block of %lld steps", (long long)t0,
+             (long long)(t0 + nt), (long long)h->nt_total);
+  h->t0 = t0;
+  h->nt = nt;
   h->have_results = false;
   h->have_routed = false;
   h->have_ext = false;
@@ -659,7 +682,7 @@ static int run_land(hb_engine* h) {
   d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
   d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
   d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
-  d.nt = nt; d.n_col = h->n_col; d.forcing = h->d_forcing.p; d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
+  d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p; d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
   bool any_series = false;
   for (int s = 0; s < HB_S_COUNT; ++s) {
     d.series[s] = nullptr;
@@ -669,7 +692,6 @@ static int run_land(hb_engine* h) {
     d.series[s] = h->d_series[s].p;
     any_series = true;
   }
-  h->timing.land_launches = 0;
   if (h->n_elem > 0 && nt > 0) {
     const int block = 128;
     const int grid = (int)((h->n_elem + block - 1) / block);
@@ -732,11 +754,13 @@ int hb_run(hb_engine* h, int flags) {
     HB_REQUIRE(h, (flags & HB_RUN_LAND) || h->have_results, HB_ESTATE, "hb_run: routing needs the land results first");
   }
   int rc;
-  h->timing.land_ms = h->timing.river_ms = h->timing.total_ms = 0.0;
+  if (flags & HB_RUN_LAND) h->timing.land_ms = 0.0, h->timing.land_launches = 0;  // a routing-only call keeps them
+  h->timing.river_ms = 0.0;
   h->timing.n_levels = h->n_levels;
   HB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (flags & HB_RUN_LAND) {
     h->timing.river_launches = 0;
+    h->have_routed = false;
     if ((rc = run_land(h))) return rc;
     h->have_results = true;
   }
@@ -748,9 +772,61 @@ int hb_run(hb_engine* h, int flags) {
   HB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
-  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timing.land_ms = ms;
-  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->timing.river_ms = ms;
-  HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[2])); h->timing.total_ms = ms;
+  if (flags & HB_RUN_LAND) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timing.land_ms = ms; }
+  if (flags & HB_RUN_RIVER) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->timing.river_ms = ms; }
+  h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
+  return HB_OK;
+}
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;  // never true; keeps the chain alive
+}
+
+int hb_measure_fp64_peak(hb_engine* h, double* tflops) {
+  if (!h || !tflops) return HB_EINVAL;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, h->d_commbuf.reserve(1));
+  const int iters = 1 << 15, block = 256, grid = h->prop.multiProcessorCount * 16;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    HB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    fp64_peak_kernel<<<grid, block, 0, h->stream>>>(h->d_commbuf.p, iters);
+    HB_CUDA(h, cudaGetLastError());
+    HB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    const double tf = 2.0 * 8.0 * (double)iters * block * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
+  return HB_OK;
+}
+
+int hb_timer_start(hb_engine* h) {
+  if (!h) return HB_EINVAL;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+  return HB_OK;
+}
+
+int hb_timer_stop(hb_engine* h, double* ms) {
+  if (!h || !ms) return HB_EINVAL;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->ev_stop) HB_CUDA(h, cudaEventCreate(&h->ev_stop));
+  HB_CUDA(h, cudaEventRecord(h->ev_stop, h->stream));
+  HB_CUDA(h, cudaEventSynchronize(h->ev_stop));
+  float f = 0.f;
+  HB_CUDA(h, cudaEventElapsedTime(&f, h->ev[3], h->ev_stop));
+  *ms = f;
   return HB_OK;
 }
 
@@ -866,20 +942,22 @@ int hb_comm_init(hb_engine* h, int rank, int world, const void* id) {
   return HB_OK;
 }
 
-int hb_comm_send_nodes(hb_engine* h, int peer, int64_t n, const int32_t* nodes) {
+int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t* rows) {
   if (!h) return HB_EINVAL;
-  HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_send_nodes: call hb_comm_init first");
-  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_comm_send_nodes: no routing results");
-  HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || nodes), HB_EINVAL,
-             "hb_comm_send_nodes: invalid argument");
+  HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_send_rows: call hb_comm_init first");
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_comm_send_rows: no routing results");
+  HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || rows) &&
+                    (kind == HB_ROW_NODE || kind == HB_ROW_REACH),
+             HB_EINVAL, "hb_comm_send_rows: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
+  const int64_t limit = kind == HB_ROW_NODE ? h->n_node : h->n_reach;
+  const double* base = kind == HB_ROW_NODE ? h->d_node_rows.p : h->d_reach_out.p;
+  for (int64_t i = 0; i < n; ++i)
+    HB_REQUIRE(h, rows[i] >= 0 && rows[i] < limit, HB_EINVAL, "hb_comm_send_rows: row %d out of range", rows[i]);
   HB_NCCL(h, h->nccl.GroupStart());
-  for (int64_t i = 0; i < n; ++i) {
-    HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node, HB_EINVAL, "hb_comm_send_nodes: node out of range");
-    // the routing kernels wrote the row in place: it is sent straight from the node-row buffer
-    HB_NCCL(h, h->nccl.Send(h->d_node_rows.p + (int64_t)nodes[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
-                            h->stream));
-  }
+  // the routing kernels wrote the rows in place: they are sent straight from the result buffers over NVLink
+  for (int64_t i = 0; i < n; ++i)
+    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->stream));
   HB_NCCL(h, h->nccl.GroupEnd());
   return HB_OK;
 }

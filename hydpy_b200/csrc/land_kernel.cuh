@@ -115,9 +115,10 @@ struct LandDev {
   double* scr_b;           // [zmax][E_pad]  el of ILAKE zones
   double* scr_sred;        // [6][zmax][E_pad] spl, wcl, spg, wcg, spe, wce (only if any element has HB_EI_SNOWLIMIT)
   // window
-  int64_t nt, n_col;
-  const double* forcing;   // [4][nt][n_col]
-  const double* sinfactor; // [nt]
+  int64_t nt, n_col;       // steps of this window
+  int64_t nt_total, t0;    // staged forcing block and offset of the window inside it
+  const double* forcing;   // [4][nt_total][n_col]
+  const double* sinfactor; // [nt_total]
   double* qt;              // [nt][E_pad]
   double* series[HB_S_COUNT];  // optional, ABI layouts
 };
@@ -158,10 +159,10 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
   const int64_t zone0 = SERIES ? d.zone0[e] : 0, snow0 = SERIES ? d.snow0[e] : 0;
   double uz = d.uz[e], lz = d.lz[e];
   const int64_t zstride = (int64_t)d.zmax * ep;  // class stride of sp/wc
-  const double* fP = d.forcing + 0 * d.nt * d.n_col + col;
-  const double* fT = d.forcing + 1 * d.nt * d.n_col + col;
-  const double* fA = d.forcing + 2 * d.nt * d.n_col + col;
-  const double* fE = d.forcing + 3 * d.nt * d.n_col + col;
+  const double* fP = d.forcing + (0 * d.nt_total + d.t0) * d.n_col + col;
+  const double* fT = d.forcing + (1 * d.nt_total + d.t0) * d.n_col + col;
+  const double* fA = d.forcing + (2 * d.nt_total + d.t0) * d.n_col + col;
+  const double* fE = d.forcing + (3 * d.nt_total + d.t0) * d.n_col + col;
 
 #define SERZ(id, k, v) do { if (SERIES && d.series[id]) d.series[id][t * d.n_zone + zone0 + (k)] = (v); } while (0)
 #define SERS(id, c, k, v) \
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
   for (int64_t t = 0; t < d.nt; ++t) {
     const double in_p = ldg(fP + t * d.n_col), in_t = ldg(fT + t * d.n_col), in_nat = ldg(fA + t * d.n_col),
                  in_net = ldg(fE + t * d.n_col);
-    const double sinf = ldg(d.sinfactor + t);
+    const double sinf = ldg(d.sinfactor + d.t0 + t);
     const double d_t = in_t - in_nat;       // meanairtemperature - normalairtemperature
     const double ret_hi = 2.0 * in_net;
 

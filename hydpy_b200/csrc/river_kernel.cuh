@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const i
     double acc = 0.0;
     for (int64_t i = i0; i < i1; ++i) {
       const int32_t s = d.entry_src[i];
-      const double* src = (s >= 0) ? d.land_rows + (int64_t)s * d.nt : d.reach_out + (int64_t)(-1 - s) * d.nt;
+      const double* src = (s >= 0)             ? d.land_rows + (int64_t)s * d.nt
+                          : (s > HB_ENTRY_EXT) ? d.reach_out + (int64_t)(-1 - s) * d.nt
+                                               : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * d.nt;
       acc += src[t];
     }
     row[t] = acc;

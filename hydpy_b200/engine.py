@@ -21,9 +21,11 @@ LIBPATH = os.path.join(HERE, "libhydpy_b200.so")
 EXPORTS = (
     "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
-    "hb_select_series", "hb_set_forcing", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
+    "hb_select_series", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
     "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
-    "hb_comm_send_nodes", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_device_info",
+    "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
+    "hb_measure_fp64_peak",
+    "hb_device_info",
 )
 
 
@@ -66,6 +68,7 @@ def load_library() -> C.CDLL:
         "hb_get_river_states": (C.c_int, [H, f64p]),
         "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
         "hb_set_forcing": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
+        "hb_select_window": (C.c_int, [H, C.c_int64, C.c_int64]),
         "hb_set_external": (C.c_int, [H, C.c_int64, f64p]),
         "hb_run": (C.c_int, [H, C.c_int]),
         "hb_get_land_outflow": (C.c_int, [H, f64p]),
@@ -75,10 +78,13 @@ def load_library() -> C.CDLL:
         "hb_get_series": (C.c_int, [H, C.c_int, f64p]),
         "hb_comm_unique_id": (C.c_int, [H, C.c_void_p]),
         "hb_comm_init": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
-        "hb_comm_send_nodes": (C.c_int, [H, C.c_int, C.c_int64, i32p]),
+        "hb_comm_send_rows": (C.c_int, [H, C.c_int, C.c_int, C.c_int64, i32p]),
         "hb_comm_recv_ext": (C.c_int, [H, C.c_int, C.c_int64, i32p]),
         "hb_comm_barrier": (C.c_int, [H]),
         "hb_get_timing": (C.c_int, [H, C.POINTER(hb_timing)]),
+        "hb_timer_start": (C.c_int, [H]),
+        "hb_timer_stop": (C.c_int, [H, C.POINTER(C.c_double)]),
+        "hb_measure_fp64_peak": (C.c_int, [H, C.POINTER(C.c_double)]),
         "hb_device_info": (C.c_int, [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     }
     assert set(proto) == set(EXPORTS)
@@ -245,6 +251,11 @@ class Engine:
                     "hb_set_forcing")
         self.nt = nt
 
+    def select_window(self, t0: int, nt: int) -> None:
+        """Run the next `run()` over steps [t0, t0+nt) of the staged forcing block."""
+        self._check(self._lib.hb_select_window(self._h, int(t0), int(nt)), "hb_select_window")
+        self.nt = int(nt)
+
     def set_external(self, rows: np.ndarray) -> None:
         river = self._need_river()
         rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(river.n_ext, self.nt)
@@ -293,6 +304,21 @@ class Engine:
         self._check(self._lib.hb_get_series(self._h, layout.S[name], ptr(out, C.c_double)), "hb_get_series")
         return out
 
+    def timer_start(self) -> None:
+        self._check(self._lib.hb_timer_start(self._h), "hb_timer_start")
+
+    def timer_stop(self) -> float:
+        """Milliseconds of device time on the engine stream since `timer_start` (synchronises)."""
+        v = C.c_double(0.0)
+        self._check(self._lib.hb_timer_stop(self._h, C.byref(v)), "hb_timer_stop")
+        return float(v.value)
+
+    def measure_fp64_peak(self) -> float:
+        """Sustained DFMA throughput of the device in TFLOP/s (the FP64 roofline denominator)."""
+        v = C.c_double(0.0)
+        self._check(self._lib.hb_measure_fp64_peak(self._h, C.byref(v)), "hb_measure_fp64_peak")
+        return float(v.value)
+
     def timing(self) -> dict[str, float]:
         t = hb_timing()
         self._check(self._lib.hb_get_timing(self._h, C.byref(t)), "hb_get_timing")
@@ -310,9 +336,10 @@ class Engine:
         buf = C.create_string_buffer(uid, layout.NCCL_ID_BYTES)
         self._check(self._lib.hb_comm_init(self._h, rank, world, buf), "hb_comm_init")
 
-    def comm_send_nodes(self, peer: int, nodes: Sequence[int]) -> None:
-        sel = np.ascontiguousarray(nodes, dtype=np.int32)
-        self._check(self._lib.hb_comm_send_nodes(self._h, peer, len(sel), ptr(sel, C.c_int32)), "hb_comm_send_nodes")
+    def comm_send_rows(self, peer: int, rows: Sequence[int], kind: str = "node") -> None:
+        sel = np.ascontiguousarray(rows, dtype=np.int32)
+        k = {"node": layout.ROW_NODE, "reach": layout.ROW_REACH}[kind]
+        self._check(self._lib.hb_comm_send_rows(self._h, peer, k, len(sel), ptr(sel, C.c_int32)), "hb_comm_send_rows")
 
     def comm_recv_ext(self, peer: int, rows: Sequence[int]) -> None:
         sel = np.ascontiguousarray(rows, dtype=np.int32)

@@ -52,5 +52,7 @@ for _n in SERIES:
 NODE_NEWSIM, NODE_EXT, NODE_OBSNEWSIM = 0, 1, 2
 
 RUN_LAND, RUN_RIVER = 1, 2
+ROW_NODE, ROW_REACH = 0, 1
+ENTRY_EXT = -(1 << 30)
 
 NCCL_ID_BYTES = 128

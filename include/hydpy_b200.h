@@ -154,7 +154,8 @@ typedef struct hb_river_desc {
   int64_t n_seg;              /* sum over reaches of (NmbSegments+1) = length of the discharge state            */
   int64_t n_ext;              /* number of external (given) series rows                                         */
   const int64_t* entry_ptr;   /* [n_node+1]                                                                     */
-  const int32_t* entry_src;   /* [n_entry] ≥0: land element index;  <0: reach index = -1-value                  */
+  const int32_t* entry_src;   /* [n_entry] ≥0: land element index;  <0: reach index = -1-value;
+                                 ≤ HB_ENTRY_EXT: external row = HB_ENTRY_EXT-value (an upstream shard's outflow)  */
   const int32_t* node_mode;   /* [n_node]  HB_NODE_*                                                            */
   const int32_t* node_ext;    /* [n_node]  row of the external series used by HB_NODE_EXT/OBSNEWSIM (−1: none)  */
   const int64_t* inlet_ptr;   /* [n_reach+1]                                                                    */
@@ -163,6 +164,8 @@ typedef struct hb_river_desc {
   const int64_t* seg_ptr;     /* [n_reach+1] → discharge[]; NmbSegments = seg_ptr[r+1]-seg_ptr[r]-1             */
   const double* coef;         /* [3][n_reach] musk_control.Coefficients c0,c1,c2 (`musk_control.py:128-315`)    */
 } hb_river_desc;
+
+#define HB_ENTRY_EXT (-1073741824) /* -(1<<30) */
 
 /* what a node hands to its downstream reaches (`devicetools.py:2205-2335`, `threadingtools.py:433-446`) */
 #define HB_NODE_NEWSIM 0     /* freshly simulated series                                                       */
@@ -208,6 +211,10 @@ int hb_select_series(hb_engine* h, int series, int on);
  * hland_derived.DOY at the window's steps (`hland_model.py:1056`; 0-based day of a leap year).  Replaces
  * `load_data` (`modelutils.py:1080-1125`) reading `inputs.<name>._<name>_array[idx]`. */
 int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy);
+/* Select the sub-window [t0, t0+nt) of the staged forcing for the next hb_run (default after hb_set_forcing: the whole
+ * block).  Lets a caller stage a long forcing block once and advance in chunks — `pub.timegrids.sim` windows inside
+ * one `init` period, ref: hydpy/core/hydpytools.py:2804-2825. */
+int hb_select_window(hb_engine* h, int64_t t0, int64_t nt);
 /* External node rows of the window: [n_ext][nt].  (`oldsim`/`obs` deploy modes, multi-GPU boundary hand-over.) */
 int hb_set_external(hb_engine* h, int64_t nt, const double* rows);
 /* Advance all land elements by the staged `nt` steps (HB_RUN_LAND), then route (HB_RUN_RIVER).  States stay on
@@ -236,9 +243,12 @@ int hb_get_series(hb_engine* h, int series, double* out);
 /* Fill `id` (HB_NCCL_ID_BYTES) on rank 0; broadcast it out of band; then every rank calls hb_comm_init. */
 int hb_comm_unique_id(hb_engine* h, void* id);
 int hb_comm_init(hb_engine* h, int rank, int world, const void* id);
-/* Send the window's simulated rows of `n` local nodes to rank `peer` / receive `n` rows into the external rows
- * `ext_rows[]` from rank `peer`.  Calls between matching ranks must pair up (grouped internally per call). */
-int hb_comm_send_nodes(hb_engine* h, int peer, int64_t n, const int32_t* nodes);
+/* Send the window's simulated rows of `n` local nodes (kind HB_ROW_NODE) or the outflow rows of `n` local reaches
+ * (kind HB_ROW_REACH) to rank `peer` / receive `n` rows into the external rows `ext_rows[]` from rank `peer`.  Calls
+ * between matching ranks must pair up (grouped internally per call). */
+#define HB_ROW_NODE 0
+#define HB_ROW_REACH 1
+int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t* rows);
 int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows);
 int hb_comm_barrier(hb_engine* h);
 
@@ -252,6 +262,13 @@ typedef struct hb_timing {
   int64_t n_levels;        /* topological levels of the river network                                           */
 } hb_timing;
 int hb_get_timing(hb_engine* h, hb_timing* out);
+/* Generic device timer on the engine's stream (CUDA events): everything enqueued between start and stop — kernels,
+ * copies, NCCL sends/receives — is covered.  hb_timer_stop synchronises the stream and returns milliseconds. */
+int hb_timer_start(hb_engine* h);
+int hb_timer_stop(hb_engine* h, double* ms);
+/* FP64 roofline denominator: sustained DFMA throughput of the device in TFLOP/s (2 flops per FMA), measured with an
+ * independent-accumulator micro-benchmark on the engine's stream. */
+int hb_measure_fp64_peak(hb_engine* h, double* tflops);
 /* Device properties the bench reports (SM count, clock in kHz, name into buf). */
 int hb_device_info(hb_engine* h, int* sm_count, int* clock_khz, char* name, int name_len);
 

@@ -1,6 +1,10 @@
 """Ad-hoc device timing of the two kernel families (development aid; bench.py is the contract)."""
 import argparse
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
