@@ -109,6 +109,7 @@ struct hb_engine {
   int64_t nt = 0, n_col = 0, nt_total = 0, t0 = 0;
   bool have_forcing = false, have_results = false, have_routed = false;
   DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows;
+  DBuf<MathTables> d_tables;
 
   // ---- river ----
   bool have_river = false;
@@ -200,6 +201,17 @@ int hb_create(int device, hb_engine** out) {
     return HB_ECUDA;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  {
+    MathTables t;
+    make_math_tables(t);
+    if (h->d_tables.reserve(1) != cudaSuccess ||
+        cudaMemcpy(h->d_tables.p, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) {
+      g_create_error = "hb_create: cannot upload the math tables";
+      cudaStreamDestroy(h->stream);
+      delete h;
+      return HB_ECUDA;
+    }
+  }
   *out = h;
   return HB_OK;
 }
@@ -682,6 +694,7 @@ static int run_land(hb_engine* h) {
   d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
   d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
   d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
+  d.tables = h->d_tables.p;
   d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p; d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
   bool any_series = false;
   for (int s = 0; s < HB_S_COUNT; ++s) {

@@ -16,11 +16,13 @@
 //
 // Arithmetic: IEEE binary64, compiled with -fmad=false so that every a*b+c rounds twice exactly like the
 // reference's gcc -O2 x86-64 build; min/max follow Cython's lowering ((b<a)?b:a / (b>a)?b:a).  The only deviations
-// from the CPU path are libdevice pow/exp (≤2 ulp, glibc <1 ulp).  sin() is evaluated on the host with glibc.
+// from the CPU path are pow/exp (fastmath.cuh: relative error < 1e-14 for the model's arguments, glibc < 1 ulp) and
+// the reciprocal-multiply inside the UZ sub-step loop.  sin() is evaluated on the host with glibc.
 #pragma once
 #include <cstdint>
 
 #include "../../include/hydpy_b200.h"
+#include "fastmath.cuh"
 
 namespace hb {
 
@@ -119,6 +121,7 @@ struct LandDev {
   int64_t nt_total, t0;    // staged forcing block and offset of the window inside it
   const double* forcing;   // [4][nt_total][n_col]
   const double* sinfactor; // [nt_total]
+  const MathTables* tables;  // log/exp tables (fastmath.cuh), staged into shared memory by every block
   double* qt;              // [nt][E_pad]
   double* series[HB_S_COUNT];  // optional, ABI layouts
 };
@@ -144,6 +147,14 @@ __device__ __forceinline__ void zone_front(const double* __restrict__ kzk, int64
 
 template <bool SERIES>
 __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
+  __shared__ MathTables s_tables;
+  {
+    const double* src = reinterpret_cast<const double*>(d.tables);
+    double* dst = reinterpret_cast<double*>(&s_tables);
+    for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const MathTables* T = &s_tables;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.n_elem) return;
   const int64_t ep = d.e_pad;
@@ -416,7 +427,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         ret *= ldg(kzk + KZ_ETF * ep);
         pet = ret * ldg(kzk + KZ_ALT_F * ep);
         if (pet <= 0.0) pet = 0.0;
-        else pet *= exp(ldg(kzk + KZ_NEG_PF * ep) * pc);
+        else pet *= hb_exp(ldg(kzk + KZ_NEG_PF * ep) * pc, T);
       }
       // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1 (f = 1: no snow evaporation, hland_model.py:4425-4430)
       double aet_ie = 0.0;
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         const double fc = ldg(kzk + KZ_FC * ep);
         // ref: hland_model.py:1776-1790 Calc_R_SM_V1
         if (fc > 0.0) {
-          r = in_ * pow(sm / fc, ldg(kzk + KZ_BETA * ep));
+          r = in_ * hb_pow(sm / fc, ldg(kzk + KZ_BETA * ep), T);
           const double a = sm + in_ - fc;
           r = HB_PYMAX(r, a);
         } else r = in_;
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         // ref: hland_model.py:2092-2101 Calc_InUZ_V1
         inuz += ldg(kzk + KZ_W_UZ * ep) * (r - cf);
         // ref: hland_model.py:2224-2236 Calc_ContriArea_V1
-        if ((einfo & HB_EI_RESPAREA) && fc > 0.0) contriarea *= pow(sm / fc, ldg(kzk + KZ_W_CONTRI * ep));
+        if ((einfo & HB_EI_RESPAREA) && fc > 0.0) contriarea *= hb_pow(sm / fc, ldg(kzk + KZ_W_CONTRI * ep), T);
       } else {
         r = in_;
         d.sm[ik] = 0.0;
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
       SERZ(HB_S_R, k, r); SERZ(HB_S_CF, k, cf); SERZ(HB_S_EA, k, ea); SERZ(HB_S_SM, k, sm);
       SERZ(HB_S_EL, k, (zt == HB_ILAKE) ? d.scr_b[ik] : 0.0);
     }
-    if (einfo & HB_EI_RESPAREA) contriarea = pow(contriarea, beta_last);
+    if (einfo & HB_EI_RESPAREA) contriarea = hb_pow(contriarea, beta_last, T);
     SERE(HB_S_INUZ, inuz); SERE(HB_S_CONTRIAREA, contriarea);
 
     // ---- element level ------------------------------------------------------------------------------------------
@@ -502,6 +513,10 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
       const double uz_old = uz;
       const double dt_inuz = dt * inuz;
       const double perc_pot = dt_percmax * contriarea;
+      // uz/contriarea is evaluated as uz*(1/contriarea) with the reciprocal taken once per step (≤ 1 ulp from the
+      // reference's division, exact for contriarea == 1); alpha == 1 (the Lahn default) squares instead of pow()
+      const double inv_ca = 1.0 / contriarea;
+      const bool square = (alpha1 == 2.0);
       for (int i = 0; i < recstep; ++i) {
         const double a = uz + dt_inuz;
         uz = HB_PYMAX(a, 0.0);
@@ -511,7 +526,8 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         if (uz > 0.0) {
           double q0;
           if (contriarea > 0.0) {
-            const double q = dt_k * pow(uz / contriarea, alpha1);
+            const double x = uz * inv_ca;
+            const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
             q0 = HB_PYMIN(q, uz);
           } else q0 = uz;
           uz -= q0;
@@ -542,7 +558,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
       }
     // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1
     double q1 = 0.0;
-    if (lz > 0.0) q1 = k4 * pow(lz, gamma1);
+    if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
     lz -= q1;
     // ref: hland_model.py:3905-3912 Calc_InRC_V1
     double inrc = relupper * q0_sum + rellower * q1;

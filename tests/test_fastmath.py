@@ -1,0 +1,86 @@
+"""Accuracy of the engine's table-driven log/exp/pow (hydpy_b200/csrc/fastmath.cuh), host build of the SAME source,
+against x87 extended-precision libm.  The bounds asserted here are the ones DESIGN.md quotes."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_fastmath_host.so")
+
+
+@pytest.fixture(scope="module")
+def fm():
+    src = os.path.join(HERE, "fastmath_host.cpp")
+    hdr = os.path.join(HERE, "..", "hydpy_b200", "csrc", "fastmath.cuh")
+    if not os.path.exists(SO) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SO):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", SO], check=True)
+    lib = C.CDLL(SO)
+    return lib
+
+
+def p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_pow_relative_error(fm):
+    rng = np.random.default_rng(0)
+    n = 400_000
+    # the model's ranges: ratios in (0, ~1e3], exponents 0.05 … 5
+    x = np.concatenate([rng.uniform(1e-8, 2.0, n // 2), np.exp(rng.uniform(-30, 12, n // 2))])
+    y = rng.uniform(0.05, 5.0, n)
+    out, rel = np.zeros(n), np.zeros(n)
+    fm.fm_pow(p(x), p(y), p(out), n)
+    fm.fm_pow_relerr(p(x), p(y), p(out), p(rel), n)
+    # the exponent t = y*log(x) is held in one double: its two roundings (log, product) bound the relative error of
+    # the result by ≈ 2*|t|*2^-53, plus ≈ 2 ulp from the table/polynomial steps
+    t = np.abs(y * np.log(x))
+    bound = 5e-16 + 2.0 * t * 2.3e-16
+    assert np.all(rel <= bound), (rel.max(), x[np.argmax(rel / bound)], y[np.argmax(rel / bound)])
+    typical = t < 20.0                     # what the model produces (ratios 1e-4 … 1e3, exponents <= 5)
+    assert rel[typical].max() < 1e-14
+    print("pow: max rel err %.3e, median %.3e" % (rel.max(), np.median(rel)))
+
+
+def test_pow_special_cases_follow_libm(fm):
+    x = np.array([0.0, 1.0, 1.0, 2.0, 0.5, np.inf, np.nan, -1.0, 1e-310, 4.0, 1e300, 1e-300, 7.3])
+    y = np.array([2.0, 3.7, 0.0, 0.0, -1.0, 1.5, 1.0, 2.0, 0.5, 0.5, 2.0, 2.0, 1.0])
+    out = np.zeros(len(x))
+    fm.fm_pow(p(x), p(y), p(out), len(x))
+    with np.errstate(all="ignore"):
+        ref = np.power(x, y)
+    assert np.array_equal(out[:4], [0.0, 1.0, 1.0, 1.0])       # exact: pow(0,y)=0, pow(1,y)=1, pow(x,0)=1
+    np.testing.assert_allclose(out, ref, rtol=1e-15, equal_nan=True)
+    assert out[10] == np.inf and out[11] == 0.0
+
+
+def test_exp_relative_error(fm):
+    rng = np.random.default_rng(1)
+    n = 400_000
+    x = np.concatenate([rng.uniform(-40, 5, n // 2), rng.uniform(-700, 700, n // 2)])
+    out, rel = np.zeros(n), np.zeros(n)
+    fm.fm_exp(p(x), p(out), n)
+    fm.fm_exp_relerr(p(x), p(out), p(rel), n)
+    assert rel.max() < 4.5e-16, rel.max()
+    z = np.array([0.0, -0.0, 710.0, -750.0, np.nan])
+    o = np.zeros(5)
+    fm.fm_exp(p(z), p(o), 5)
+    assert o[0] == 1.0 and o[1] == 1.0 and o[2] == np.inf and o[3] == 0.0 and np.isnan(o[4])
+    print("exp: max rel err %.3e" % rel.max())
+
+
+def test_log_absolute_error(fm):
+    rng = np.random.default_rng(2)
+    n = 400_000
+    x = np.concatenate([rng.uniform(0.5, 2.0, n // 2), np.exp(rng.uniform(-700, 700, n // 2))])
+    out, err = np.zeros(n), np.zeros(n)
+    fm.fm_log(p(x), p(out), n)
+    fm.fm_log_abserr(p(x), p(out), p(err), n)
+    tol = 4e-16 + 2.3e-16 * np.abs(np.log(x))
+    assert np.all(err <= tol), (err.max(), x[np.argmax(err / tol)])
+    one = np.array([1.0])
+    o = np.zeros(1)
+    fm.fm_log(p(one), p(o), 1)
+    assert o[0] == 0.0
