@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "land_kernel.cuh"
+#include "land_kernel_v2.cuh"
 #include "river_kernel.cuh"
 
 using namespace hb;
@@ -96,6 +97,11 @@ struct hb_engine {
   int64_t n_elem = 0, e_pad = 0, n_zone = 0, n_snow = 0, n_uh = 0;
   int zmax = 0, cmax = 0, umax = 0;
   bool any_snowlimit = false;
+  int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
+  std::vector<int32_t> slow_list;     // the others
+  DBuf<int32_t> d_slow_list;
+  DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
+  int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
@@ -292,6 +298,11 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
+  int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
+  std::vector<int32_t> slow_list;     // the others
+  DBuf<int32_t> d_slow_list;
+  DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
+  int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
 #define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
 #define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
   for (int64_t e = 0; e < ne; ++e) {
@@ -308,6 +319,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
     const double z = EPAR(Z, e), relsoil = EPAR(RELSOILAREA, e), relupper = EPAR(RELUPPERZONEAREA, e),
                  rellower = EPAR(RELLOWERZONEAREA, e), dt = EPAR(DT, e), petalt = EPAR(PETALTITUDE, e);
     int info = 0;
+    bool soilonly = true, coupled = false;
     if ((d->eflags[e] & HB_EF_RESPAREA) && relsoil > 0.0) info |= HB_EI_RESPAREA;
     for (int k = 0; k < n; ++k) {
       const int64_t zz = z0 + k;
@@ -357,7 +369,17 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       o[(size_t)KZ_W_LZ * ep] = ZP(RELZONEAREA, zz) / rellower;
       o[(size_t)KZ_RELZONEAREA * ep] = ZP(RELZONEAREA, zz);
       o[(size_t)KZ_TTI * ep] = ZP(TEMPERATURETHRESHOLDICE, zz);
+      o[(size_t)KZ_INV_TTINT * ep] = 1.0 / ZP(TTINT, zz);
+      o[(size_t)KZ_INV_RFCF * ep] = 1.0 / ZP(RFCF, zz);
+      o[(size_t)KZ_INV_SFCF * ep] = 1.0 / ZP(SFCF, zz);
+      o[(size_t)KZ_INV_FC * ep] = 1.0 / ZP(FC, zz);
+      o[(size_t)KZ_INV_THRESH * ep] = 1.0 / (ZP(SOILMOISTURELIMIT, zz) * ZP(MAXSOILWATER, zz));
+      if (zt != HB_FIELD && zt != HB_FOREST) soilonly = false;
+      if ((zt == HB_FIELD || zt == HB_FOREST) && !(ZP(CFLUX, zz) == 0.0)) coupled = true;
     }
+    if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
+    else slow_list.push_back((int32_t)e);
+    if (soilonly) info |= HB_EI_SOILONLY;
     if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
     einfo[e] = info;
     ke[(size_t)KE_DT * ep + e] = dt;
@@ -380,6 +402,8 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
 #undef EPAR
   for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = ne ? d->sred_ptr[ne] : 0;
   h->any_snowlimit = any_snowlimit;
+  h->n_fast = n_fast;
+  h->slow_list = slow_list;
   h->h_nz = nz; h->h_nc = nc; h->h_nu = nu;
   int rc;
   if ((rc = upload(h, h->d_nz, nz)) || (rc = upload(h, h->d_nc, nc)) || (rc = upload(h, h->d_nu, nu)) ||
@@ -387,7 +411,8 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       (rc = upload(h, h->d_fcol, fcol)) || (rc = upload(h, h->d_zinfo, zinfo)) || (rc = upload(h, h->d_zorder, zorder)) ||
       (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) ||
       (rc = upload(h, h->d_sred_ptr, sred_ptr)) || (rc = upload(h, h->d_kz, kz)) || (rc = upload(h, h->d_ke, ke)) ||
-      (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)))
+      (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)) ||
+      (rc = upload(h, h->d_slow_list, slow_list)))
     return rc;
   if ((rc = upload(h, h->d_sred_from, d->sred_from, (size_t)d->n_sred)) ||
       (rc = upload(h, h->d_sred_to, d->sred_to, (size_t)d->n_sred)) ||
@@ -475,6 +500,18 @@ int hb_get_land_states(hb_engine* h, hb_land_states* st) {
       for (int j = 0; j < nu; ++j) st->quh[u0 + j] = quh[(size_t)j * ep + e];
   }
   return HB_OK;
+}
+
+int hb_set_option(hb_engine* h, int option, int64_t value) {
+  if (!h) return HB_EINVAL;
+  switch (option) {
+    case HB_OPT_LAND_PATH:
+      HB_REQUIRE(h, value == HB_LAND_AUTO || value == HB_LAND_GENERAL, HB_EINVAL, "hb_set_option: invalid land path");
+      h->land_path = (int)value;
+      return HB_OK;
+    default:
+      return h->fail(HB_EINVAL, "hb_set_option: unknown option %d", option);
+  }
 }
 
 int hb_select_series(hb_engine* h, int series, int on) {
@@ -684,38 +721,75 @@ static int run_land(hb_engine* h) {
   const int64_t nt = h->nt, ep = h->e_pad;
   HB_CUDA(h, h->d_qt.reserve((size_t)nt * ep));
   HB_CUDA(h, h->d_land_rows.reserve((size_t)h->n_elem * nt));
-  LandDev d{};
-  d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
-  d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
-  d.nz = h->d_nz.p; d.nc = h->d_nc.p; d.nu = h->d_nu.p; d.recstep = h->d_recstep.p; d.einfo = h->d_einfo.p;
-  d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p;
-  d.kz = h->d_kz.p; d.ke = h->d_ke.p; d.sfdist = h->d_sfdist.p; d.uh = h->d_uh.p;
-  d.sred_ptr = h->d_sred_ptr.p; d.sred_from = h->d_sred_from.p; d.sred_to = h->d_sred_to.p;
-  d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
-  d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
-  d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
-  d.tables = h->d_tables.p;
-  d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p; d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
   bool any_series = false;
-  for (int s = 0; s < HB_S_COUNT; ++s) {
-    d.series[s] = nullptr;
-    if (!h->series_on[s]) continue;
-    const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
-    HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
-    d.series[s] = h->d_series[s].p;
-    any_series = true;
+  for (int s = 0; s < HB_S_COUNT; ++s) any_series = any_series || h->series_on[s];
+  // fast path (land_kernel_v2.cuh) for the eligible elements unless series are requested or the caller forces the
+  // general kernel; everything else goes through the general kernel
+  const bool use_fast = h->n_fast > 0 && !any_series && h->land_path == HB_LAND_AUTO;
+  const int64_t n_general = use_fast ? (int64_t)h->slow_list.size() : h->n_elem;
+  h->timing.land_launches = 0;
+  if (h->n_elem == 0 || nt == 0) return HB_OK;
+
+  if (use_fast) {
+    LandV2Dev v{};
+    v.n_elem = h->n_elem; v.e_pad = ep; v.zmax = h->zmax;
+    v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
+    v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
+    v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
+    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing.p;
+    v.sinfactor = h->d_sinfactor.p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    // time chunks bound the two term buffers (3 GB each at most)
+    const int64_t per_step = (int64_t)h->zmax * ep;
+    int64_t chunk_max = (int64_t)(3.0e9 / 8.0) / per_step;
+    if (chunk_max < 8) chunk_max = 8;
+    const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
+    const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
+    HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
+    HB_CUDA(h, h->d_term_b.reserve((size_t)chunk * per_step));
+    v.term_a = h->d_term_a.p; v.term_b = h->d_term_b.p;
+    for (int64_t c0 = 0; c0 < nt; c0 += chunk) {
+      v.nt = (nt - c0 < chunk) ? (nt - c0) : chunk;
+      v.t_first = h->t0 + c0;
+      v.t_out = c0;
+      zone_kernel<<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+      element_kernel<<<(unsigned)((h->n_elem + 63) / 64), 64, 0, h->stream>>>(v);
+      h->timing.land_launches += 2;
+    }
+    HB_CUDA(h, cudaGetLastError());
   }
-  if (h->n_elem > 0 && nt > 0) {
+  if (n_general > 0) {
+    LandDev d{};
+    d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
+    d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
+    d.n_list = n_general; d.elist = use_fast ? h->d_slow_list.p : nullptr;
+    d.nz = h->d_nz.p; d.nc = h->d_nc.p; d.nu = h->d_nu.p; d.recstep = h->d_recstep.p; d.einfo = h->d_einfo.p;
+    d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p;
+    d.kz = h->d_kz.p; d.ke = h->d_ke.p; d.sfdist = h->d_sfdist.p; d.uh = h->d_uh.p;
+    d.sred_ptr = h->d_sred_ptr.p; d.sred_from = h->d_sred_from.p; d.sred_to = h->d_sred_to.p;
+    d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
+    d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
+    d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
+    d.tables = h->d_tables.p;
+    d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p;
+    d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
+    for (int s = 0; s < HB_S_COUNT; ++s) {
+      d.series[s] = nullptr;
+      if (!h->series_on[s]) continue;
+      const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+      HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
+      d.series[s] = h->d_series[s].p;
+    }
     const int block = 128;
-    const int grid = (int)((h->n_elem + block - 1) / block);
+    const int grid = (int)((n_general + block - 1) / block);
     if (any_series) land_kernel<true><<<grid, block, 0, h->stream>>>(d);
     else land_kernel<false><<<grid, block, 0, h->stream>>>(d);
     HB_CUDA(h, cudaGetLastError());
-    dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
-    transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows.p, nt, h->n_elem, ep);
-    HB_CUDA(h, cudaGetLastError());
-    h->timing.land_launches = 2;
+    h->timing.land_launches += 1;
   }
+  dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
+  transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows.p, nt, h->n_elem, ep);
+  HB_CUDA(h, cudaGetLastError());
+  h->timing.land_launches += 1;
   return HB_OK;
 }
 

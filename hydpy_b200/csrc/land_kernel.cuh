@@ -53,6 +53,8 @@ enum kz {
   KZ_SMAX, KZ_GMELT, KZ_GVAR,
   KZ_W_LZ,        // relzonearea/rellowerzonearea
   KZ_RELZONEAREA, KZ_TTI,
+  // reciprocals used by the fast path only (land_kernel_v2.cuh)
+  KZ_INV_TTINT, KZ_INV_RFCF, KZ_INV_SFCF, KZ_INV_FC, KZ_INV_THRESH,
   KZ_COUNT
 };
 
@@ -75,6 +77,8 @@ enum ke {
 #define HB_EI_LAKE 2       // has ILAKE zones
 #define HB_EI_SEALED 4     // has SEALED zones
 #define HB_EI_SNOWLIMIT 8  // some zone has finite SMax ⇒ Calc_SPL/Calc_SPG are live
+#define HB_EI_FAST 16      // eligible for the two-kernel fast path: one snow class, no snow limit, every CFlux == 0
+#define HB_EI_SOILONLY 32  // all zones are FIELD or FOREST
 
 // zone info: bits 0..2 zone type, bits 8.. zflags (HB_ZF_*)
 #define HB_ZI_TYPE(i) ((i) & 7)
@@ -83,6 +87,8 @@ enum ke {
 struct LandDev {
   int64_t n_elem, e_pad, n_zone, n_snow;
   int32_t zmax, cmax, umax;
+  int64_t n_list;          // number of elements this launch works on
+  const int32_t* elist;    // [n_list] their indices (NULL: elements 0..n_list-1)
   // structure
   const int32_t* nz;       // [E_pad]
   const int32_t* nc;       // [E_pad]
@@ -155,8 +161,9 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
   }
   __syncthreads();
   const MathTables* T = &s_tables;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.n_elem) return;
+  const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= d.n_list) return;
+  const int64_t e = d.elist ? (int64_t)d.elist[li] : li;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nc = d.nc[e], nu = d.nu[e], recstep = d.recstep[e], einfo = d.einfo[e];
   const int64_t col = d.fcol[e];

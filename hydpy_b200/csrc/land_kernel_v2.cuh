@@ -1,0 +1,354 @@
+// land_kernel_v2.cuh — runoff generation, fast path: two persistent kernels per time chunk.
+//
+// Why (profiles/r01_land_v1b_fastmath_details.csv): the one-thread-per-element kernel (land_kernel.cuh) re-reads its
+// 26 folded constants per zone and step from HBM (280 MB per simulated step for 10^5 elements, more than the L2), is
+// limited to 1.3 waves of 128-register threads and therefore spends 65 % of its stall cycles on the long scoreboard
+// with the FP64 pipe 12.8 % busy.  The decomposition below follows BASELINE.json's north_star instead:
+//
+//   zone_kernel    : ONE THREAD PER ZONE (x member), persistent over the chunk.  Every folded constant and the four
+//                    zone states (ic, sp, wc, sm) live in registers for all steps; the only memory traffic per step is
+//                    the element's forcing (4 doubles, prefetched one step ahead, shared by the element's zones through
+//                    L1/L2) and two result terms per zone.  Thread (k, e) sits at k*E_pad + e, so a warp holds zone k of
+//                    32 consecutive elements: all loads/stores are coalesced and ragged zone counts only retire warps.
+//   element_kernel : one thread per element, persistent over the chunk: adds the zone terms in ZONE ORDER (the
+//                    reference's summation order: Calc_InUZ_V1, Calc_ContriArea_V1, Calc_LZ_V1, Calc_EL_LZ_V1,
+//                    Calc_InRC_V1), then the sequential RecStep loop of Calc_Q0_Perc_UZ_V1, the lower zone and the unit
+//                    hydrograph.  It needs ≈56 registers, so all 10^5 chains are resident at once (5.3 warps per
+//                    scheduler), which is what hides the ≈15 k-cycle dependent chain of the 50 sub-steps.
+//
+// The split is legal exactly when the zone equations do not read the element state of the previous step, i.e. when
+// every CFlux of the element is zero (then Calc_CF_SM_V1 yields min(0*(1-sm/fc), uz+r, fc-sm) = the value without the
+// uz term, because uz >= 0 and r >= 0; ref: hydpy/models/hland/hland_model.py:1904-1919) — the Lahn default and the
+// synthetic configs.  Elements with CFlux > 0, several snow classes, a finite SMax (snow redistribution) or requested
+// series run through land_kernel.cuh, which covers everything.
+//
+// Numerics: same formulas and operand order as land_kernel.cuh; deliberate deviations (each <= 1 ulp per operation,
+// inside the 1e-9 parity bar, measured in tests/test_gpu_*): divisions by the step-invariant constants RfCF, SfCF,
+// TTInt, FC and SoilMoistureLimit*MaxSoilWater are multiplications by reciprocals folded on the host.
+#pragma once
+#include <cstdint>
+
+#include "land_kernel.cuh"
+
+namespace hb {
+
+struct LandV2Dev {
+  int64_t n_elem, e_pad;
+  int32_t zmax;
+  const int32_t* nz;       // [E_pad]
+  const int32_t* nu;       // [E_pad]
+  const int32_t* recstep;  // [E_pad]
+  const int32_t* einfo;    // [E_pad]  HB_EI_* incl. HB_EI_FAST / HB_EI_SOILONLY
+  const int32_t* fcol;     // [E_pad]
+  const int32_t* zinfo;    // [zmax][E_pad]
+  const double* kz;        // [zmax][KZ_COUNT][E_pad]
+  const double* ke;        // [KE_COUNT][E_pad]
+  const double* sfdist;    // [cmax][E_pad] (class 0 used)
+  const double* uh;        // [umax][E_pad]
+  double* ic;              // [zmax][E_pad]
+  double* sm;
+  double* sp;              // class 0
+  double* wc;
+  double* uz;              // [E_pad]
+  double* lz;
+  double* quh;             // [umax][E_pad]
+  int64_t nt;              // steps of this chunk
+  int64_t n_col, nt_total, t_first;  // forcing block [4][nt_total][n_col]; first step of the chunk inside it
+  const double* forcing;
+  const double* sinfactor;  // [nt_total]
+  const MathTables* tables;
+  double* term_a;          // [nt][zmax][E_pad]
+  double* term_b;          // [nt][zmax][E_pad]
+  double* qt;              // [nt_window][E_pad], chunk starts at row t_out
+  int64_t t_out;
+};
+
+__device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
+  const double* src = reinterpret_cast<const double*>(g);
+  double* dst = reinterpret_cast<double*>(s);
+  for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// zone kernel: everything of hland_96.run() that works on one zone (ref: hydpy/models/hland_96.py:1675-1705, the methods
+// Calc_TC_V1 … Calc_EA_SM_AETModel_V1 and the per-zone factors of Calc_InUZ_V1 / Calc_ContriArea_V1 / Calc_LZ_V1 /
+// Calc_EL_LZ_V1 / Calc_InRC_V1)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 4) zone_kernel(const LandV2Dev d) {
+  __shared__ MathTables s_tables;
+  stage_tables(&s_tables, d.tables);
+  const MathTables* T = &s_tables;
+  const int64_t ep = d.e_pad;
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // k*E_pad + e
+  const int k = (int)(slot / ep);
+  const int64_t e = slot - (int64_t)k * ep;
+  if (e >= d.n_elem) return;
+  const int einfo = d.einfo[e];
+  if (!(einfo & HB_EI_FAST) || k >= d.nz[e]) return;
+
+  const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
+#define KZ(name) kzk[(int64_t)(name) * ep]
+  const int zi = d.zinfo[slot];
+  const int zt = HB_ZI_TYPE(zi), zf = HB_ZI_FLAGS(zi);
+  const bool soil = (zt == HB_FIELD) || (zt == HB_FOREST);
+  const bool icept = soil || (zt == HB_SEALED);        // zone types with an interception storage
+  const bool resp = (einfo & HB_EI_RESPAREA) != 0;
+  // ---- constants → registers (coalesced: consecutive lanes = consecutive elements) ----
+  const double tcorr = KZ(KZ_TCORR), tcalt_dz = KZ(KZ_TCALT_DZ), tt_hi = KZ(KZ_TT_HI), tt_lo = KZ(KZ_TT_LO),
+               inv_ttint = KZ(KZ_INV_TTINT), pcalt_f = KZ(KZ_PCALT_F), pcorr = KZ(KZ_PCORR), inv_rfcf = KZ(KZ_INV_RFCF),
+               inv_sfcf = KZ(KZ_INV_SFCF), icmax = KZ(KZ_ICMAX), cfmax = KZ(KZ_CFMAX), cfvar = KZ(KZ_CFVAR),
+               ttm = KZ(KZ_TTM), cfr_cfmax = KZ(KZ_CFR_CFMAX), whc = KZ(KZ_WHC), fc = KZ(KZ_FC), inv_fc = KZ(KZ_INV_FC),
+               beta = KZ(KZ_BETA), thresh = KZ(KZ_THRESH), inv_thresh = KZ(KZ_INV_THRESH), excessred = KZ(KZ_EXCESSRED),
+               atf = KZ(KZ_ATF), etf = KZ(KZ_ETF), alt_f = KZ(KZ_ALT_F), neg_pf = KZ(KZ_NEG_PF);
+  // type-dependent constants share registers
+  const double w_a = soil || zt == HB_GLACIER ? KZ(KZ_W_UZ) : zt == HB_ILAKE ? KZ(KZ_W_LZ) : KZ(KZ_RELZONEAREA);
+  const double w_b = soil ? KZ(KZ_W_CONTRI) : KZ(KZ_W_LZ);
+  const double g_melt = zt == HB_GLACIER ? KZ(KZ_GMELT) : 0.0, g_var = zt == HB_GLACIER ? KZ(KZ_GVAR) : 0.0;
+  const double tti = zt == HB_ILAKE ? KZ(KZ_TTI) : 0.0;
+#undef KZ
+  const double sf = d.sfdist[e];
+  double ic = d.ic[slot], sm = d.sm[slot], sp = d.sp[slot], wc = d.wc[slot];
+
+  const int64_t col = d.fcol[e];
+  const double* fP = d.forcing + (0 * d.nt_total + d.t_first) * d.n_col + col;
+  const double* fT = d.forcing + (1 * d.nt_total + d.t_first) * d.n_col + col;
+  const double* fA = d.forcing + (2 * d.nt_total + d.t_first) * d.n_col + col;
+  const double* fE = d.forcing + (3 * d.nt_total + d.t_first) * d.n_col + col;
+  const double* sinp = d.sinfactor + d.t_first;
+  const int64_t tstride = (int64_t)d.zmax * ep;
+  double* out_a = d.term_a + slot;
+  double* out_b = d.term_b + slot;
+
+  double n_p = 0.0, n_t = 0.0, n_nat = 0.0, n_net = 0.0, n_sin = 0.0;
+  if (d.nt > 0) { n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp); }
+  for (int64_t t = 0; t < d.nt; ++t) {
+    const double in_p = n_p, in_t = n_t, in_nat = n_nat, in_net = n_net, sinf = n_sin;
+    if (t + 1 < d.nt) {  // prefetch the next step's forcing; consumed one iteration later
+      const int64_t o = (t + 1) * d.n_col;
+      n_p = ldg(fP + o); n_t = ldg(fT + o); n_nat = ldg(fA + o); n_net = ldg(fE + o); n_sin = ldg(sinp + t + 1);
+    }
+    // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
+    const double tc = in_t + tcorr - tcalt_dz;
+    double fracrain;
+    if (tc >= tt_hi) fracrain = 1.0;
+    else if (tc <= tt_lo) fracrain = 0.0;
+    else fracrain = (tc - tt_lo) * inv_ttint;
+    double pc = in_p * pcalt_f;
+    if (pc <= 0.0) pc = 0.0;
+    else pc *= pcorr / (fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf);
+    // ref: hland_model.py:299-309 Calc_TF_Ic_V1
+    double tf;
+    if (icept) {
+      const double a = pc - (icmax - ic);
+      tf = HB_PYMAX(a, 0.0);
+      ic += pc - tf;
+    } else { tf = pc; ic = 0.0; }
+    double in_ = tf, ncover = 0.0;
+    bool bare = true;
+    if (zt != HB_ILAKE) {
+      // ref: hland_model.py:484-499 Calc_SP_WC_V1
+      wc += sf * (tf * fracrain);
+      sp += sf * (tf * (1.0 - fracrain));
+      // ref: hland_model.py:1050-1062 Calc_CFAct_V1
+      const double cfa = cfmax + sinf * cfvar;
+      const double cfact = HB_PYMAX(cfa, 0.0);
+      // ref: hland_model.py:1166-1187 Calc_Melt_SP_WC_V1, 1318-1341 Calc_Refr_SP_WC_V1
+      if (tc > ttm) {
+        const double potmelt = cfact * (tc - ttm);
+        const double melt = HB_PYMIN(potmelt, sp);
+        sp -= melt; wc += melt;
+      } else if (tc < ttm) {
+        const double potrefr = cfr_cfmax * (ttm - tc);
+        const double refr = HB_PYMIN(potrefr, wc);
+        sp += refr; wc -= refr;
+      }
+      // ref: hland_model.py:1434-1448 Calc_In_WC_V1 (one snow class: the division by SClass is exact)
+      const double wc_old = wc, lim = whc * sp;
+      wc = HB_PYMIN(wc_old, lim);
+      in_ = wc_old - wc;
+      bare = sp <= 0.0;
+      ncover = (sp > 0.0) ? 1.0 : 0.0;
+      // ref: hland_model.py:1607-1619 Calc_GAct_V1, 1688-1701 Calc_GlMelt_In_V1
+      if (zt == HB_GLACIER && tc > ttm && bare) {
+        const double ga = g_melt + sinf * g_var;
+        const double gact = HB_PYMAX(ga, 0.0);
+        in_ += gact * (tc - ttm);
+      }
+    } else { sp = 0.0; wc = 0.0; }
+    // evap_pet_hbv96.run(): ref: evap_model.py:5111-5125, 5420-5424, 5312-5326
+    double pet;
+    {
+      double ret = in_net * (1.0 + atf * (in_t - in_nat));
+      const double lo = HB_PYMAX(ret, 0.0);
+      const double hi = 2.0 * in_net;
+      ret = HB_PYMIN(lo, hi);
+      ret *= etf;
+      pet = ret * alt_f;
+      if (pet <= 0.0) pet = 0.0;
+      else pet *= hb_exp(neg_pf * pc, T);
+    }
+    // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1; hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
+    double aet_ie = 0.0;
+    if (zf & HB_ZF_INTERCEPTION) aet_ie = HB_PYMIN(pet, ic);
+    if (icept) { const double ei = HB_PYMIN(aet_ie, ic); ic -= ei; }
+    else ic = 0.0;
+    double ta, tb = 1.0;
+    if (soil) {
+      // ref: hland_model.py:1776-1790 Calc_R_SM_V1
+      double r;
+      if (fc > 0.0) {
+        r = in_ * hb_pow(sm * inv_fc, beta, T);
+        const double a = sm + in_ - fc;
+        r = HB_PYMAX(r, a);
+      } else r = in_;
+      sm += in_ - r;
+      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0: cf = min(0*(1 - sm/fc), fc - sm)
+      double cf = 0.0;
+      if (fc > 0.0) {
+        cf = 0.0 * (1.0 - sm * inv_fc);
+        const double b = fc - sm;
+        cf = HB_PYMIN(cf, b);
+      }
+      sm += cf;
+      // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1 (6657-6672, 7001-7018, 7060-7069)
+      double set = 0.0;
+      if (zf & HB_ZF_SOIL) {
+        set = pet;
+        if (set > 0.0) {
+          if (sm < 0.0) set = 0.0;
+          else if (sm < thresh) set *= sm * inv_thresh;
+        }
+        const double petc = excessred * pet + (1.0 - excessred) * (pet + pet) / 2.0;
+        const double excess = set + aet_ie - petc;
+        if ((petc >= 0.0) && (excess > 0.0)) set -= excessred * excess;
+        else if ((petc < 0.0) && (excess < 0.0)) set -= excessred * excess;
+        set *= 1.0 - ncover;
+      }
+      // ref: hland_model.py:2002-2018 Calc_EA_SM_AETModel_V1
+      const double ea = HB_PYMIN(set, sm);
+      sm -= ea;
+      if (sm > fc) { r += sm - fc; sm = fc; }
+      // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
+      ta = w_a * (r - cf);
+      if (resp && fc > 0.0) tb = hb_pow(sm * inv_fc, w_b, T);
+    } else {
+      sm = 0.0;
+      if (zt == HB_ILAKE) {
+        // ref: hland_model.py:3113-3124 Calc_LZ_V1 (term), 3724-3737 Calc_EL_LZ_AETModel_V1 (term);
+        // evap_model.py:5673-5681 Calc_WaterEvaporation_V1
+        ta = w_a * pc;
+        const double el = ((zf & HB_ZF_WATER) && tc > tti) ? pet : 0.0;
+        tb = w_b * el;
+      } else ta = w_a * (in_ - 0.0);  // GLACIER: InUZ term; SEALED: InRC term (r = in_, ref: hland_model.py:1528-1535)
+    }
+    out_a[t * tstride] = ta;
+    out_b[t * tstride] = tb;
+  }
+  d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// element kernel: ordered zone sums + Calc_Q0_Perc_UZ_V1 … Calc_QT_V1
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64, 16) element_kernel(const LandV2Dev d) {
+  __shared__ MathTables s_tables;
+  stage_tables(&s_tables, d.tables);
+  const MathTables* T = &s_tables;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.n_elem) return;
+  const int einfo = d.einfo[e];
+  if (!(einfo & HB_EI_FAST)) return;
+  const int64_t ep = d.e_pad;
+  const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
+  const double dt = d.ke[KE_DT * ep + e], dt_percmax = d.ke[KE_DT_PERCMAX * ep + e], dt_k = d.ke[KE_DT_K * ep + e],
+               alpha1 = d.ke[KE_ALPHA1 * ep + e], k4 = d.ke[KE_K4 * ep + e], gamma1 = d.ke[KE_GAMMA1 * ep + e],
+               relupper = d.ke[KE_RELUPPER * ep + e], rellower = d.ke[KE_RELLOWER * ep + e],
+               up_low = d.ke[KE_UP_LOW * ep + e], qfactor = d.ke[KE_QFACTOR * ep + e],
+               beta_last = d.ke[KE_BETA_LAST * ep + e];
+  const bool resp = (einfo & HB_EI_RESPAREA) != 0, soilonly = (einfo & HB_EI_SOILONLY) != 0;
+  const bool square = (alpha1 == 2.0);
+  double uz = d.uz[e], lz = d.lz[e];
+  const int64_t tstride = (int64_t)d.zmax * ep;
+  for (int64_t t = 0; t < d.nt; ++t) {
+    const double* ta = d.term_a + t * tstride + e;
+    const double* tb = d.term_b + t * tstride + e;
+    double inuz = 0.0, contriarea = 1.0;
+    if (soilonly) {
+      for (int k = 0; k < nz; ++k) {
+        inuz += ta[(int64_t)k * ep];
+        contriarea *= tb[(int64_t)k * ep];
+      }
+    } else {
+      for (int k = 0; k < nz; ++k) {
+        const int zt = HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]);
+        if (zt == HB_FIELD || zt == HB_FOREST) { inuz += ta[(int64_t)k * ep]; contriarea *= tb[(int64_t)k * ep]; }
+        else if (zt == HB_GLACIER) inuz += ta[(int64_t)k * ep];
+      }
+    }
+    if (resp) contriarea = hb_pow(contriarea, beta_last, T);
+    // ref: hland_model.py:2456-2484 Calc_Q0_Perc_UZ_V1
+    double perc_sum = 0.0, q0_sum = 0.0;
+    {
+      const double uz_old = uz;
+      const double dt_inuz = dt * inuz;
+      const double perc_pot = dt_percmax * contriarea;
+      const double inv_ca = 1.0 / contriarea;
+      for (int i = 0; i < recstep; ++i) {
+        const double a = uz + dt_inuz;
+        uz = HB_PYMAX(a, 0.0);
+        const double perc = HB_PYMIN(perc_pot, uz);
+        uz -= perc;
+        perc_sum += perc;
+        if (uz > 0.0) {
+          double q0;
+          if (contriarea > 0.0) {
+            const double x = uz * inv_ca;
+            const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
+            q0 = HB_PYMIN(q, uz);
+          } else q0 = uz;
+          uz -= q0;
+          q0_sum += q0;
+        }
+      }
+      const double error = uz - (uz_old + inuz - perc_sum - q0_sum);
+      if (error > 0.0) {
+        const double factor = 1.0 - error / (perc_sum + q0_sum);
+        perc_sum *= factor;
+        q0_sum *= factor;
+      }
+    }
+    // ref: hland_model.py:3113-3124 Calc_LZ_V1, 3724-3737 Calc_EL_LZ_AETModel_V1
+    if (rellower > 0.0) {
+      lz += up_low * perc_sum;
+      if (einfo & HB_EI_LAKE)
+        for (int k = 0; k < nz; ++k)
+          if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) lz += ta[(int64_t)k * ep];
+    } else lz = 0.0;
+    if (einfo & HB_EI_LAKE)
+      for (int k = 0; k < nz; ++k)
+        if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) lz -= tb[(int64_t)k * ep];
+    // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1
+    double q1 = 0.0;
+    if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
+    lz -= q1;
+    // ref: hland_model.py:3905-3912 Calc_InRC_V1
+    double inrc = relupper * q0_sum + rellower * q1;
+    if (einfo & HB_EI_SEALED)
+      for (int k = 0; k < nz; ++k)
+        if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
+    // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
+    double outrc = inrc;
+    if (nu > 0) {
+      outrc = ldg(d.uh + e) * inrc + d.quh[e];
+      for (int j = 1; j < nu; ++j)
+        d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
+    }
+    // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
+    d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
+  }
+  d.uz[e] = uz;
+  d.lz[e] = lz;
+}
+
+}  // namespace hb

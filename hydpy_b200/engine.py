@@ -21,7 +21,7 @@ LIBPATH = os.path.join(HERE, "libhydpy_b200.so")
 EXPORTS = (
     "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
-    "hb_select_series", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
+    "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
     "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
         "hb_set_river_states": (C.c_int, [H, f64p]),
         "hb_get_river_states": (C.c_int, [H, f64p]),
         "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
+        "hb_set_option": (C.c_int, [H, C.c_int, C.c_int64]),
         "hb_set_forcing": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
         "hb_select_window": (C.c_int, [H, C.c_int64, C.c_int64]),
         "hb_set_external": (C.c_int, [H, C.c_int64, f64p]),
@@ -234,6 +235,11 @@ class Engine:
             raise ValueError(f"unknown series: {sorted(unknown)}")
         for name in layout.SERIES:
             self._check(self._lib.hb_select_series(self._h, layout.S[name], int(name in names)), "hb_select_series")
+
+    def set_land_path(self, path: str = "auto") -> None:
+        """'auto': fast two-kernel path where the parameters allow it; 'general': the general kernel for all elements."""
+        value = {"auto": layout.LAND_AUTO, "general": layout.LAND_GENERAL}[path]
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_PATH, value), "hb_set_option")
 
     # -- window -----------------------------------------------------------------------------------------------------
     def set_forcing(self, forcing: np.ndarray, doy: np.ndarray) -> None:

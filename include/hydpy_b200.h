@@ -205,6 +205,13 @@ int hb_get_river_states(hb_engine* h, double* discharge);
 /* Select which optional land series `hb_run` records (on ≠ 0).  Replaces the `ramflag` switches of
  * `IOSequence.prepare_series` (`hydpy/core/sequencetools.py:1912`, save_data `modelutils.py:1127-1167`). */
 int hb_select_series(hb_engine* h, int series, int on);
+/* Engine options.  HB_OPT_LAND_PATH: HB_LAND_AUTO (default) runs the elements that allow it (one snow class, SMax = inf,
+ * every CFlux == 0, no series requested) through the two-kernel fast path and the rest through the general kernel;
+ * HB_LAND_GENERAL forces the general kernel for all elements (results agree within the parity bar; used by tests). */
+#define HB_OPT_LAND_PATH 0
+#define HB_LAND_AUTO 0
+#define HB_LAND_GENERAL 1
+int hb_set_option(hb_engine* h, int option, int64_t value);
 
 /* ---- one simulation window ------------------------------------------------------------------------------------ */
 /* Stage the forcing of the next window: `forcing` = [HB_FORCING_COUNT][nt][n_col] doubles, `doy` = [nt] values of

@@ -10,11 +10,15 @@ from hydpy_b200.abi import LandBundle, LandStates, RiverBundle
 
 
 def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recstep: int = 20, bank: int | None = None,
-                snowlimit_fraction: float = 0.3) -> tuple[LandBundle, LandStates]:
+                snowlimit_fraction: float = 0.3, fast_fraction: float = 0.4) -> tuple[LandBundle, LandStates]:
+    """`fast_fraction` of the elements get one snow class, CFlux = 0 and SMax = inf, i.e. they qualify for the engine's
+    two-kernel fast path (all zone types still occur); the others exercise the general kernel."""
     rng = np.random.default_rng(seed)
     ne = n_elem
     nz = rng.integers(1, zmax + 1, size=ne)
     nc = rng.integers(1, cmax + 1, size=ne)
+    fast = np.random.default_rng(seed + 4242).uniform(size=ne) < fast_fraction
+    nc[fast] = 1
     nu = rng.integers(0, 6, size=ne)
     zone_ptr = np.concatenate([[0], np.cumsum(nz)]).astype(np.int64)
     snow_ptr = np.concatenate([[0], np.cumsum(nz * nc)]).astype(np.int64)
@@ -72,7 +76,9 @@ def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recst
         zorder[z0:z1] = order
         eflags[e] = layout.EF_RESPAREA if rng.uniform() < 0.5 else 0
         edges = 0
-        if rng.uniform() < snowlimit_fraction:
+        if fast[e]:
+            zpar[ZP["cflux"], z0:z1] = 0.0
+        if rng.uniform() < snowlimit_fraction and not fast[e]:
             zpar[ZP["smax"], z0:z1] = rng.uniform(5.0, 40.0, size=n)
             # redistribution edges from higher to lower non-lake zones (a DAG in descending altitude)
             desc = order[::-1]

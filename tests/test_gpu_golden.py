@@ -22,9 +22,11 @@ LAHN_H = load_scenarios("lahn_hourly_members.npz")
 EXACT_SERIES = ("tc", "fracrain", "cfact", "gact", "pc")
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["auto", "general"])
+def engine(request):
+    """Both land paths: 'auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only."""
     with Engine(0) as eng:
+        eng.set_land_path(request.param)
         yield eng
 
 
@@ -45,6 +47,12 @@ def run_and_check(engine, sc, window=None):
     for name in EXACT_SERIES:
         if name in res["series"]:
             assert np.array_equal(res["series"][name], sc.expected(name), equal_nan=True), f"{sc.name}:{name} not exact"
+    # discharge-only run (no series requested): the eligible elements take the fast path
+    res0 = run_problem(p, engine, window=window)
+    assert_close(res0["node_rows"][wb], sc.expected("node_rows")[wb], f"{sc.name}:node series (discharge-only run)")
+    for n in res0["states"].NAMES:
+        assert_close(getattr(res0["states"], n), sc.expected("state_" + n), f"{sc.name}:final state {n} (discharge-only)")
+    assert_close(res0["discharge"], sc.expected("discharge"), f"{sc.name}:final discharge (discharge-only run)")
     return res, worst
 
 

@@ -11,9 +11,11 @@ from tests.util import assert_close
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["auto", "general"])
+def engine(request):
+    """Both land paths: 'auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only."""
     with Engine(0) as eng:
+        eng.set_land_path(request.param)
         yield eng
 
 
@@ -50,10 +52,13 @@ def test_random_ragged_problem_all_series(engine, seed):
     ref = oracle_run(problem, series=layout.SERIES)
     res = run_problem(problem, engine, series=layout.SERIES)
     compare(res, ref, f"seed {seed}", series=layout.SERIES)
-    # routing is libm-free: given identical inflow it must be bit-identical; check through a land-free variant
+    # without series the eligible elements take the fast path: same bar against the oracle
+    res1 = run_problem(problem, engine)
+    compare(res1, ref, f"seed {seed} (no series)")
+    # splitting the period into windows must not change a single bit (states stay on the device)
     res2 = run_problem(problem, engine, window=17)
     for key in ("land_rows", "node_rows", "reach_out", "discharge"):
-        assert np.array_equal(res[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
 
 
 def test_long_reaches_more_than_32_segments(engine):
