@@ -123,6 +123,8 @@ struct hb_engine {
   std::vector<int32_t> level_node_ptr, level_reach_ptr;  // [n_levels+1]
   DBuf<int64_t> d_entry_ptr, d_inlet_ptr, d_seg_ptr;
   DBuf<int32_t> d_entry_src, d_node_mode, d_node_ext, d_inlet_node, d_node_order, d_reach_order, d_sel;
+  DBuf<int32_t> d_reach_level, d_node_owner, d_terminal_nodes;
+  int64_t n_terminal = 0;
   DBuf<double> d_coef, d_dis[2], d_ext_rows, d_node_rows, d_reach_in, d_reach_out, d_gather;
   int dis_cur = 0;
   bool have_ext = false;
@@ -609,6 +611,13 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     for (int64_t n = 0; n < nn; ++n) node_order[np[node_level[n]]++] = (int32_t)n;
     for (int64_t q = 0; q < nr; ++q) reach_order[rp[reach_level[q]]++] = (int32_t)q;
   }
+  // the reach that stores a node's row during the sweep = its first exit; nodes without exits are summed at the end
+  std::vector<int32_t> node_owner(nn, -1), terminal;
+  for (int64_t n = 0; n < nn; ++n) {
+    if (node_exits[n].empty()) terminal.push_back((int32_t)n);
+    else node_owner[n] = node_exits[n][0];
+  }
+  h->n_terminal = (int64_t)terminal.size();
   h->n_node = nn; h->n_reach = nr; h->n_seg = r->n_seg; h->n_ext = r->n_ext; h->n_levels = nlev;
   h->level_node_ptr = lnp; h->level_reach_ptr = lrp;
   int rc;
@@ -618,7 +627,9 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
       (rc = upload(h, h->d_inlet_ptr, r->inlet_ptr, (size_t)nr + 1)) ||
       (rc = upload(h, h->d_inlet_node, r->inlet_node, (size_t)r->n_inlet)) ||
       (rc = upload(h, h->d_seg_ptr, r->seg_ptr, (size_t)nr + 1)) || (rc = upload(h, h->d_coef, r->coef, (size_t)3 * nr)) ||
-      (rc = upload(h, h->d_node_order, node_order)) || (rc = upload(h, h->d_reach_order, reach_order)))
+      (rc = upload(h, h->d_node_order, node_order)) || (rc = upload(h, h->d_reach_order, reach_order)) ||
+      (rc = upload(h, h->d_reach_level, reach_level)) || (rc = upload(h, h->d_node_owner, node_owner)) ||
+      (rc = upload(h, h->d_terminal_nodes, terminal)))
     return rc;
   HB_CUDA(h, h->d_dis[0].reserve((size_t)r->n_seg));
   HB_CUDA(h, h->d_dis[1].reserve((size_t)r->n_seg));
@@ -804,25 +815,32 @@ static int run_river(hb_engine* h) {
   d.node_ext = h->d_node_ext.p; d.inlet_ptr = h->d_inlet_ptr.p; d.inlet_node = h->d_inlet_node.p;
   d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows.p; d.ext_rows = h->d_ext_rows.p;
   d.node_rows = h->d_node_rows.p; d.reach_in = h->d_reach_in.p; d.reach_out = h->d_reach_out.p;
-  d.dis_old = h->d_dis[h->dis_cur].p; d.dis_new = h->d_dis[1 - h->dis_cur].p;
+  d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur;
+  d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p;
   int64_t launches = 0;
   if (nt > 0) {
-    for (int64_t l = 0; l < h->n_levels; ++l) {
-      const int nn = h->level_node_ptr[l + 1] - h->level_node_ptr[l];
-      if (nn > 0) {
-        const int block = 256, grid = (int)(((int64_t)nn * 32 + block - 1) / block);
-        node_sum_kernel<<<grid, block, 0, h->stream>>>(d, h->d_node_order.p + h->level_node_ptr[l], nn);
+    // anti-diagonal sweep over (level, time chunk): launch `diag` works on the reaches of level l at chunk diag - l
+    const int n_chunks = (int)((nt + HB_RIVER_CHUNK - 1) / HB_RIVER_CHUNK);
+    const int nlev = (int)h->n_levels;
+    if (h->n_reach > 0) {
+      for (int diag = 0; diag < nlev + n_chunks - 1; ++diag) {
+        const int l_lo = diag - n_chunks + 1 > 0 ? diag - n_chunks + 1 : 0;
+        const int l_hi = diag < nlev - 1 ? diag : nlev - 1;
+        const int first = h->level_reach_ptr[l_lo];
+        const int n = h->level_reach_ptr[l_hi + 1] - first;
+        if (n <= 0) continue;
+        const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
+        reach_diag_kernel<<<grid, block, 0, h->stream>>>(d, h->d_reach_order.p + first, n, diag, n_chunks);
         ++launches;
       }
-      const int nr = h->level_reach_ptr[l + 1] - h->level_reach_ptr[l];
-      if (nr > 0) {
-        const int block = 128, grid = (int)(((int64_t)nr * 32 + block - 1) / block);
-        reach_kernel<<<grid, block, 0, h->stream>>>(d, h->d_reach_order.p + h->level_reach_ptr[l], nr);
-        ++launches;
-      }
+      h->dis_cur = (h->dis_cur + n_chunks) & 1;
+    }
+    if (h->n_terminal > 0) {
+      const int block = 256, grid = (int)((h->n_terminal * 32 + block - 1) / block);
+      node_sum_kernel<<<grid, block, 0, h->stream>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
+      ++launches;
     }
     HB_CUDA(h, cudaGetLastError());
-    h->dis_cur = 1 - h->dis_cur;
   }
   h->timing.river_launches = launches;
   return HB_OK;

@@ -6,12 +6,20 @@
 // (ref: hydpy/core/threadingtools.py:396-446).
 //
 // All series are device rows [row][nt] (time contiguous):  land rows (outlets.q of the land elements), node rows,
-// reach inflow/outflow rows, external rows.  Per level two launches:
-//   node_sum_kernel : one warp per node, lanes over time, entries added in the listed order (0.0 + a + b + …);
-//   reach_kernel    : one warp per reach; lane i owns segment i and the warp runs as a systolic pipeline over
-//                     "ticks": at tick τ lane i computes time τ-i, receiving new[i](t) from lane i-1 by shuffle.
-//                     The recurrence  new[i+1] = c0*new[i] + c1*old[i] + c2*old[i+1]  is evaluated with the
-//                     reference's operation order and no FMA contraction ⇒ bit-identical to the CPU path.
+// reach inflow/outflow rows, external rows.
+//
+//   reach_diag_kernel : one warp per (reach, time chunk).  The window is cut into chunks of HB_RIVER_CHUNK steps and
+//                     the (level, chunk) grid is swept along its anti-diagonals: launch d works on every reach of level l
+//                     at chunk d-l, which only needs chunk d-l of the levels below — finished by launch d-1.  The
+//                     sequential depth drops from levels x nt ticks to (levels + nt/chunk) short launches and every
+//                     launch has nt/chunk levels' worth of reaches in flight.
+//                     Inside a warp lane i owns segment i and the chunk runs as a systolic pipeline over "ticks": at
+//                     tick τ lane i computes time τ-i, receiving new[i](t) from lane i-1 by shuffle.  The recurrence
+//                     new[i+1] = c0*new[i] + c1*old[i] + c2*old[i+1]  is evaluated with the reference's operation order
+//                     and no FMA contraction ⇒ bit-identical to the CPU path.  The warp also forms the sums of its inlet
+//                     nodes (entries added in the listed order, 0.0 + a + b + …) and, as the owner of a node, stores
+//                     the node row.
+//   node_sum_kernel : one warp per node, lanes over time — for the nodes without a downstream reach (outlets).
 #pragma once
 #include <cstdint>
 
@@ -34,9 +42,13 @@ struct RiverDev {
   double* node_rows;        // [n_node][nt]
   double* reach_in;         // [n_reach][nt]
   double* reach_out;        // [n_reach][nt]
-  const double* dis_old;    // [n_seg] discharge at window start
-  double* dis_new;          // [n_seg] discharge at window end
+  double* dis[2];           // chunked sweep: chunk c reads dis[(par0 + c) & 1] and writes the other one
+  int par0;
+  const int32_t* reach_level;  // [n_reach]
+  const int32_t* node_owner;   // [n_node] reach that stores the node row (first exit), -1: terminal node
 };
+
+#define HB_RIVER_CHUNK 32
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
 __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restrict__ qt, double* __restrict__ rows,
@@ -75,24 +87,34 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const i
   }
 }
 
-// value a node hands to its downstream reach at time t (ref: threadingtools.py:433-446)
-__device__ __forceinline__ double delivered(const RiverDev& d, int32_t node, int64_t t) {
-  const int mode = d.node_mode[node];
-  double v;
-  if (mode == HB_NODE_NEWSIM) v = d.node_rows[(int64_t)node * d.nt + t];
-  else {
-    v = d.ext_rows[(int64_t)d.node_ext[node] * d.nt + t];
-    if (mode == HB_NODE_OBSNEWSIM && isnan(v)) v = d.node_rows[(int64_t)node * d.nt + t];
+// ref: threadingtools.py:396-415 node series = 0.0 + entries in order
+__device__ __forceinline__ double node_sum_at(const RiverDev& d, int64_t node, int64_t t) {
+  double acc = 0.0;
+  const int64_t i0 = d.entry_ptr[node], i1 = d.entry_ptr[node + 1];
+  for (int64_t i = i0; i < i1; ++i) {
+    const int32_t s = d.entry_src[i];
+    const double* src = (s >= 0)             ? d.land_rows + (int64_t)s * d.nt
+                        : (s > HB_ENTRY_EXT) ? d.reach_out + (int64_t)(-1 - s) * d.nt
+                                             : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * d.nt;
+    acc += src[t];
   }
-  return 0.0 + v;
+  return acc;
 }
 
-__global__ void __launch_bounds__(128) reach_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n) {
+__global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n,
+                                                         int diag, int n_chunks) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (warp >= n) return;
   const unsigned full = 0xffffffffu;
   const int64_t r = reaches[warp];
+  const int c = diag - d.reach_level[r];
+  if (c < 0 || c >= n_chunks) return;
   const int64_t nt = d.nt;
+  const int64_t ta = (int64_t)c * HB_RIVER_CHUNK;
+  const int64_t tb = (ta + HB_RIVER_CHUNK < nt) ? ta + HB_RIVER_CHUNK : nt;
+  const int len = (int)(tb - ta);
+  const double* dis_old = d.dis[(d.par0 + c) & 1];
+  double* dis_new = d.dis[(d.par0 + c + 1) & 1];
   const int64_t g0 = d.seg_ptr[r];
   const int S = (int)(d.seg_ptr[r + 1] - g0 - 1);
   const double c0 = d.coef[0 * d.n_reach + r], c1 = d.coef[1 * d.n_reach + r], c2 = d.coef[2 * d.n_reach + r];
@@ -100,60 +122,61 @@ __global__ void __launch_bounds__(128) reach_kernel(const RiverDev d, const int3
   double* rin = d.reach_in + r * nt;
   double* rout = d.reach_out + r * nt;
 
-  // ---- inflow row: ref musk_model.py:26-31 Pick_Inflow_V1 (0.0 + q[0] + q[1] + …) ----------------------------------
-  for (int64_t t = lane; t < nt; t += 32) {
+  // ---- inflow of the chunk (lane = time step): node sums, node rows of owned nodes, Pick_Inflow_V1 ----------------------
+  double x_own = 0.0;   // inflow at time ta+lane, kept in the register for the pipeline below
+  if (lane < len) {
+    const int64_t t = ta + lane;
     double inflow = 0.0;
-    for (int64_t j = j0; j < j1; ++j) inflow += delivered(d, d.inlet_node[j], t);
+    for (int64_t j = j0; j < j1; ++j) {
+      const int32_t node = d.inlet_node[j];
+      const double sim = node_sum_at(d, node, t);
+      if (d.node_owner[node] == (int32_t)r) d.node_rows[(int64_t)node * nt + t] = sim;
+      const int mode = d.node_mode[node];
+      double v = sim;
+      if (mode != HB_NODE_NEWSIM) {
+        v = d.ext_rows[(int64_t)d.node_ext[node] * nt + t];
+        if (mode == HB_NODE_OBSNEWSIM && isnan(v)) v = sim;
+      }
+      inflow += 0.0 + v;   // ref: musk_model.py:26-31 Pick_Inflow_V1
+    }
     rin[t] = inflow;
     if (S == 0) rout[t] = inflow;  // ref: musk_model.py:95-98, 831-835 — zero segments: outflow = discharge[0]
+    x_own = inflow;
   }
-  __syncwarp();
-  if (S == 0) {
-    if (lane == 0) d.dis_new[g0] = (nt > 0) ? rin[nt - 1] : d.dis_old[g0];
-    return;
-  }
-  if (lane == 0) d.dis_new[g0] = (nt > 0) ? rin[nt - 1] : d.dis_old[g0];
+  const double x_last = __shfl_sync(full, x_own, len - 1);
+  if (lane == 0) dis_new[g0] = x_last;
+  if (S == 0) return;
 
-  // ---- systolic pipeline over chunks of 32 segments ------------------------------------------------------------------
+  // ---- systolic pipeline over groups of 32 segments --------------------------------------------------------------------
   for (int cbase = 0; cbase < S; cbase += 32) {
     const int nseg = (S - cbase < 32) ? (S - cbase) : 32;
-    const double* X = (cbase == 0) ? rin : rout;   // later chunks continue in place on the outflow row
     double prev_in = 0.0, prev_out = 0.0, out = 0.0;
     if (lane < nseg) {
-      prev_in = d.dis_old[g0 + cbase + lane];
-      prev_out = d.dis_old[g0 + cbase + lane + 1];
+      prev_in = dis_old[g0 + cbase + lane];
+      prev_out = dis_old[g0 + cbase + lane + 1];
     }
-    const int64_t nticks = nt + nseg - 1;
-    double yb = 0.0;
-    for (int64_t tau0 = 0; tau0 < nticks; tau0 += 32) {
-      const double xb = (tau0 + lane < nt) ? X[tau0 + lane] : 0.0;
-      const int jn = (nticks - tau0 < 32) ? (int)(nticks - tau0) : 32;
-      for (int j = 0; j < jn; ++j) {
-        const int64_t tau = tau0 + j;
-        const double x0 = __shfl_sync(full, xb, j);
-        const double up = __shfl_up_sync(full, out, 1);
-        const double in = (lane == 0) ? x0 : up;
-        const int64_t tloc = tau - lane;
-        if (lane < nseg && tloc >= 0 && tloc < nt) {
-          // ref: musk_model.py:178-187 Calc_Discharge_V1 — (c0*new[i] + c1*old[i]) + c2*old[i+1]
-          const double nv = c0 * in + c1 * prev_in + c2 * prev_out;
-          prev_in = in;
-          prev_out = nv;
-          out = nv;
-        }
-        const double y = __shfl_sync(full, out, nseg - 1);
-        const int64_t p = tau - (nseg - 1);
-        if (p >= 0) {
-          if ((p & 31) == lane) yb = y;
-          if ((p & 31) == 31 || p == nt - 1) {
-            const int64_t pb = p - (p & 31);
-            if (lane <= (p & 31)) rout[pb + lane] = yb;
-          }
-        }
+    double xb = x_own;                               // input of this segment group at time ta+lane
+    double yb = 0.0;                                 // its output at time ta+lane (collected below)
+    const int nticks = len + nseg - 1;
+    for (int tau = 0; tau < nticks; ++tau) {
+      const double x0 = __shfl_sync(full, xb, tau & 31);   // only meaningful while tau < len
+      const double up = __shfl_up_sync(full, out, 1);
+      const double in = (lane == 0) ? x0 : up;
+      const int tloc = tau - lane;
+      if (lane < nseg && tloc >= 0 && tloc < len) {
+        // ref: musk_model.py:178-187 Calc_Discharge_V1 — (c0*new[i] + c1*old[i]) + c2*old[i+1]
+        const double nv = c0 * in + c1 * prev_in + c2 * prev_out;
+        prev_in = in;
+        prev_out = nv;
+        out = nv;
       }
+      const double y = __shfl_sync(full, out, nseg - 1);
+      const int p = tau - (nseg - 1);
+      if (p == lane) yb = y;
     }
-    __syncwarp();
-    if (lane < nseg) d.dis_new[g0 + cbase + lane + 1] = prev_out;
+    if (lane < nseg) dis_new[g0 + cbase + lane + 1] = prev_out;
+    x_own = yb;                                      // the next segment group continues on this output
+    if (cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
   }
 }
 
