@@ -40,7 +40,7 @@ UNIT = "zone-timesteps/s"
 def parse_args() -> argparse.Namespace:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("engine", "reference"), default="engine")
     ap.add_argument("--elements", type=int, default=100_000, help="hland_96 elements per GPU")
@@ -238,7 +238,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     block = np.ascontiguousarray(np.concatenate(list(pinned.array), axis=1))      # [4, n_steps*win, 1024]
     eng.set_forcing(block, doys.reshape(-1))
     del block
-    land_ms, river_ms = [], []
+    land_ms, river_ms, zone_ms, element_ms, general_ms = [], [], [], [], []
     dist.barrier()
     for s in range(W):
         eng.select_window(s * win, win)
@@ -253,6 +253,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         tm = eng.timing()
         land_ms.append(tm["land_ms"])
         river_ms.append(tm["river_ms"])
+        zone_ms.append(tm["zone_ms"])
+        element_ms.append(tm["element_ms"])
+        general_ms.append(tm["general_ms"])
         launches += int(tm["land_launches"] + tm["river_launches"])
     device_ms = eng.timer_stop()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
@@ -289,13 +292,40 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     states_after_e2e = eng.get_land_states()
     same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
 
-    # ================= roofline of the dominant kernel (runoff generation) ===============================================
+    # ================= roofline of the dominant kernel ====================================================================
+    # Discharge-only mode moves 40 B per element-step, so the bound is the FP64 pipe.
+    # Algorithmic work, SURVEY's convention (add/mul/cmp/div/pow/exp = 1 op each): 130 ops per zone-step in the
+    # thread-per-zone kernel, 14 R + 2 U + 32 ops per element-step in the thread-per-element kernel.
     fp64_peak = eng.measure_fp64_peak()
+    peak_ops = fp64_peak / 2.0                                             # T FP64 instructions/s (an FMA = 1 op)
     R, U, Z = int(land.recstep[0]), int(land.uh_ptr[1] - land.uh_ptr[0]), land.n_zone / land.n_elem
-    ops_per_zone_step = 130.0 + (14.0 * R + 2.0 * U + 32.0) / Z          # SURVEY.md §8(d), div = pow = exp = 1 op
-    land_ms_avg = float(np.mean(land_ms))
-    achieved_tops = ops_per_zone_step * zone_steps_per_step / (land_ms_avg * 1e-3) / 1e12
-    bytes_per_launch = (4 * 8 + 8) * land.n_elem * win                     # 4 forcing doubles in + qt out per element-step
+    n_fast = int(eng.timing()["n_fast"])
+    zone_ops = 130.0 * land.n_zone * win
+    element_ops = (14.0 * R + 2.0 * U + 32.0) * land.n_elem * win
+    land_ms_avg, zone_ms_avg, element_ms_avg = float(np.mean(land_ms)), float(np.mean(zone_ms)), float(np.mean(element_ms))
+    general_ms_avg = float(np.mean(general_ms))
+
+    def tops(ops: float, ms: float) -> float:
+        return ops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+
+    kernels = {
+        "zone_kernel": {"ms": zone_ms_avg, "ops_per_launch": zone_ops, "achieved": tops(zone_ops, zone_ms_avg),
+                        "frac": tops(zone_ops, zone_ms_avg) / peak_ops,
+                        "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 40 * land.n_elem * win},
+        "element_kernel": {"ms": element_ms_avg, "ops_per_launch": element_ops,
+                           "achieved": tops(element_ops, element_ms_avg),
+                           "frac": tops(element_ops, element_ms_avg) / peak_ops,
+                           "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win},
+        "land_kernel (general)": {"ms": general_ms_avg},
+        "routing (reach_diag_kernel x levels+chunks)": {
+            "ms": float(np.mean(river_ms)),
+            "algorithmic_bytes_per_step": 16 * river.n_reach * win + 8 * (river.n_node + land.n_elem) * win},
+    }
+    dominant = "zone_kernel" if n_fast else "land_kernel (general)"
+    dom_ms = zone_ms_avg if n_fast else general_ms_avg
+    dom_ops = zone_ops if n_fast else zone_ops + element_ops
+    achieved_tops = tops(dom_ops, dom_ms)
+    dom_bytes = kernels["zone_kernel"]["algorithmic_bytes_per_launch"] if n_fast else 40 * land.n_elem * win
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -303,6 +333,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dram__bytes_read.sum + dram__bytes_write.sum of one zone_kernel launch (240-step chunk, 10^5 x 12 zones) from the
+    # committed `ncu --set full` capture profiles/r01_v2_raw_selected.txt; only valid for the default workload
+    traffic = 5.08e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -312,7 +345,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
             "river_levels": n_levels, "window_steps": win, "recstep_per_step": R, "uh_ordinates": U,
             "forcing_bank": 1024, "parallelism": f"element-sharded x{dist.world}" if dist.world > 1 else "single GPU",
-            "l2": "working set (zone constants 307 MB + states 38 MB + series) exceeds the 126 MB L2; no flush needed",
+            "l2": "per step 4.6 GB of zone terms + 0.4 GB of rows stream through HBM (> 126 MB L2); no flush needed",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
@@ -320,13 +353,15 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         "kernel_ms_per_step": {"runoff_generation": land_ms_avg, "routing": float(np.mean(river_ms)),
                                "wall": wall_ms / K},
         "roofline": {
-            "bound": "fp64", "achieved": achieved_tops, "peak": fp64_peak / 2.0, "unit": "Top/s (FP64 ops, FMA = 1)",
-            "frac": achieved_tops / (fp64_peak / 2.0), "traffic": None,
-            "kernel": "land_kernel<false>", "ops_per_zone_step": ops_per_zone_step,
-            "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run)", "fp64_tflops_measured": fp64_peak,
-            "hbm": {"achieved": bytes_per_launch / (land_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_per_launch / (land_ms_avg * 1e-3) / 1e9 / hbm_peak,
-                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+            "bound": "fp64", "achieved": achieved_tops, "peak": peak_ops, "unit": "Top/s (FP64 ops, FMA = 1)",
+            "frac": achieved_tops / peak_ops, "traffic": traffic,
+            "kernel": dominant, "ops_per_launch": dom_ops,
+            "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
+            "fp64_tflops_measured": fp64_peak,
+            "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
+                    "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "kernels": kernels,
         },
         "clocks": clocks, "device": info, "checksum": checksum,
     }

@@ -20,6 +20,8 @@
 
 using namespace hb;
 
+enum { HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2 };
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -89,6 +91,20 @@ struct hb_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_stop = nullptr;
+  // per-kernel timing of the last hb_run: marks recorded between launches, resolved after the final synchronise
+  std::vector<cudaEvent_t> marks;
+  std::vector<int> mark_tag;          // kernel family that ran BEFORE the mark (HB_K_*), -1 for the opening mark
+  size_t n_marks = 0;
+  int mark(int tag) {
+    if (n_marks == marks.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return -1;
+      marks.push_back(e);
+      mark_tag.push_back(tag);
+    }
+    mark_tag[n_marks] = tag;
+    return cudaEventRecord(marks[n_marks++], stream) == cudaSuccess ? 0 : -1;
+  }
   std::string error;
   cudaDeviceProp prop{};
 
@@ -232,6 +248,7 @@ void hb_destroy(hb_engine* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  for (auto& e : h->marks) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -300,11 +317,8 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
-  int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
-  std::vector<int32_t> slow_list;     // the others
-  DBuf<int32_t> d_slow_list;
-  DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
-  int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
+  int64_t n_fast = 0;
+  std::vector<int32_t> slow_list;
 #define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
 #define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
   for (int64_t e = 0; e < ne; ++e) {
@@ -738,6 +752,7 @@ static int run_land(hb_engine* h) {
   // general kernel; everything else goes through the general kernel
   const bool use_fast = h->n_fast > 0 && !any_series && h->land_path == HB_LAND_AUTO;
   const int64_t n_general = use_fast ? (int64_t)h->slow_list.size() : h->n_elem;
+  h->timing.n_fast = use_fast ? h->n_fast : 0;
   h->timing.land_launches = 0;
   if (h->n_elem == 0 || nt == 0) return HB_OK;
 
@@ -762,8 +777,11 @@ static int run_land(hb_engine* h) {
       v.nt = (nt - c0 < chunk) ? (nt - c0) : chunk;
       v.t_first = h->t0 + c0;
       v.t_out = c0;
+      h->mark(-1);
       zone_kernel<<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+      h->mark(HB_K_ZONE);
       element_kernel<<<(unsigned)((h->n_elem + 63) / 64), 64, 0, h->stream>>>(v);
+      h->mark(HB_K_ELEMENT);
       h->timing.land_launches += 2;
     }
     HB_CUDA(h, cudaGetLastError());
@@ -792,8 +810,10 @@ static int run_land(hb_engine* h) {
     }
     const int block = 128;
     const int grid = (int)((n_general + block - 1) / block);
+    h->mark(-1);
     if (any_series) land_kernel<true><<<grid, block, 0, h->stream>>>(d);
     else land_kernel<false><<<grid, block, 0, h->stream>>>(d);
+    h->mark(HB_K_GENERAL);
     HB_CUDA(h, cudaGetLastError());
     h->timing.land_launches += 1;
   }
@@ -859,7 +879,9 @@ int hb_run(hb_engine* h, int flags) {
     HB_REQUIRE(h, (flags & HB_RUN_LAND) || h->have_results, HB_ESTATE, "hb_run: routing needs the land results first");
   }
   int rc;
-  if (flags & HB_RUN_LAND) h->timing.land_ms = 0.0, h->timing.land_launches = 0;  // a routing-only call keeps them
+  if (flags & HB_RUN_LAND)   // a routing-only call keeps the land figures
+    h->timing.land_ms = h->timing.zone_ms = h->timing.element_ms = h->timing.general_ms = 0.0, h->timing.land_launches = 0;
+  h->n_marks = 0;
   h->timing.river_ms = 0.0;
   h->timing.n_levels = h->n_levels;
   HB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
@@ -880,6 +902,13 @@ int hb_run(hb_engine* h, int flags) {
   if (flags & HB_RUN_LAND) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timing.land_ms = ms; }
   if (flags & HB_RUN_RIVER) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->timing.river_ms = ms; }
   h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
+  for (size_t i = 1; i < h->n_marks; ++i) {
+    if (h->mark_tag[i] < 0) continue;
+    HB_CUDA(h, cudaEventElapsedTime(&ms, h->marks[i - 1], h->marks[i]));
+    if (h->mark_tag[i] == HB_K_ZONE) h->timing.zone_ms += ms;
+    else if (h->mark_tag[i] == HB_K_ELEMENT) h->timing.element_ms += ms;
+    else if (h->mark_tag[i] == HB_K_GENERAL) h->timing.general_ms += ms;
+  }
   return HB_OK;
 }
 

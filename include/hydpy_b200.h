@@ -267,6 +267,10 @@ typedef struct hb_timing {
   int64_t land_launches;   /* kernels launched for the land part                                                */
   int64_t river_launches;  /* kernels launched for the river part                                               */
   int64_t n_levels;        /* topological levels of the river network                                           */
+  double zone_ms;          /* runoff generation, fast path: thread-per-zone kernel (all chunks of the window)       */
+  double element_ms;       /* runoff generation, fast path: thread-per-element kernel                               */
+  double general_ms;       /* runoff generation, general kernel (elements the fast path does not cover, or series)  */
+  int64_t n_fast;          /* land elements on the fast path in the last hb_run                                     */
 } hb_timing;
 int hb_get_timing(hb_engine* h, hb_timing* out);
 /* Generic device timer on the engine's stream (CUDA events): everything enqueued between start and stop — kernels,
