@@ -51,6 +51,7 @@ class hb_timing(C.Structure):
         ("land_ms", C.c_double), ("river_ms", C.c_double), ("total_ms", C.c_double),
         ("land_launches", C.c_int64), ("river_launches", C.c_int64), ("n_levels", C.c_int64),
         ("zone_ms", C.c_double), ("element_ms", C.c_double), ("general_ms", C.c_double), ("n_fast", C.c_int64),
+        ("n_runs", C.c_int64),
     ]
 
 

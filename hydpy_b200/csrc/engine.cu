@@ -20,7 +20,7 @@
 
 using namespace hb;
 
-enum { HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2 };
+enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
 
@@ -88,23 +88,34 @@ const int kNcclFloat64 = 8, kNcclSum = 0;
 
 struct hb_engine {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  // Three streams form the window pipeline: runoff generation of window w+1 (stream) overlaps routing of window w
+  // (s_river) and the device→host copy of its node series (s_copy).  All per-window buffers exist twice; `cur` is the
+  // set of the window staged last (it flips in hb_set_forcing / hb_select_window).
+  cudaStream_t stream = nullptr, s_river = nullptr, s_copy = nullptr;
+  int cur = 0;
+  cudaEvent_t ev_land_done[2] = {nullptr, nullptr}, ev_river_done[2] = {nullptr, nullptr},
+              ev_copy_done[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool pending = false;               // work enqueued by hb_run_async that hb_wait has not yet collected
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_stop = nullptr;
-  // per-kernel timing of the last hb_run: marks recorded between launches, resolved after the final synchronise
-  std::vector<cudaEvent_t> marks;
-  std::vector<int> mark_tag;          // kernel family that ran BEFORE the mark (HB_K_*), -1 for the opening mark
-  size_t n_marks = 0;
-  int mark(int tag) {
-    if (n_marks == marks.size()) {
-      cudaEvent_t e;
-      if (cudaEventCreate(&e) != cudaSuccess) return -1;
-      marks.push_back(e);
-      mark_tag.push_back(tag);
+  // per-kernel timing: marks recorded between launches, resolved by hb_wait and accumulated in `timing` until
+  // hb_get_timing reads (and resets) the sums
+  struct Marks {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;             // kernel family that ran BEFORE the mark (HB_K_*), HB_K_BEGIN for an opening mark
+    size_t n = 0;
+    int add(int t, cudaStream_t st) {
+      if (n == ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        ev.push_back(e);
+        tag.push_back(t);
+      }
+      tag[n] = t;
+      return cudaEventRecord(ev[n++], st) == cudaSuccess ? 0 : -1;
     }
-    mark_tag[n_marks] = tag;
-    return cudaEventRecord(marks[n_marks++], stream) == cudaSuccess ? 0 : -1;
-  }
+  } land_marks, river_marks;
+  int mark(int tag) { return land_marks.add(tag, stream); }
   std::string error;
   cudaDeviceProp prop{};
 
@@ -130,7 +141,7 @@ struct hb_engine {
   // ---- window ----
   int64_t nt = 0, n_col = 0, nt_total = 0, t0 = 0;
   bool have_forcing = false, have_results = false, have_routed = false;
-  DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows;
+  DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows[2];
   DBuf<MathTables> d_tables;
 
   // ---- river ----
@@ -141,7 +152,7 @@ struct hb_engine {
   DBuf<int32_t> d_entry_src, d_node_mode, d_node_ext, d_inlet_node, d_node_order, d_reach_order, d_sel;
   DBuf<int32_t> d_reach_level, d_node_owner, d_terminal_nodes;
   int64_t n_terminal = 0;
-  DBuf<double> d_coef, d_dis[2], d_ext_rows, d_node_rows, d_reach_in, d_reach_out, d_gather;
+  DBuf<double> d_coef, d_dis[2], d_ext_rows[2], d_node_rows[2], d_reach_in[2], d_reach_out[2], d_gather[2];
   int dis_cur = 0;
   bool have_ext = false;
 
@@ -226,6 +237,25 @@ int hb_create(int device, hb_engine** out) {
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
   {
+    // routing is a chain of ≈(levels + chunks) short dependent launches: at the highest priority its blocks take every
+    // slot the long-running land blocks free, so the chain is not starved while it overlaps the next window's land part
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&h->s_river, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&h->s_copy, cudaStreamNonBlocking, hi);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_land_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_river_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_copy_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
+  if (!h->s_river || !h->s_copy || !h->ev_join[1]) {
+    g_create_error = "hb_create: cannot create the pipeline streams/events";
+    hb_destroy(h);
+    return HB_ECUDA;
+  }
+  {
     MathTables t;
     make_math_tables(t);
     if (h->d_tables.reserve(1) != cudaSuccess ||
@@ -245,10 +275,18 @@ void hb_destroy(hb_engine* h) {
   cudaSetDevice(h->device);
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
   cudaStreamSynchronize(h->stream);
+  if (h->s_river) cudaStreamSynchronize(h->s_river);
+  if (h->s_copy) cudaStreamSynchronize(h->s_copy);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
-  for (auto& e : h->marks) cudaEventDestroy(e);
+  for (auto& e : h->land_marks.ev) cudaEventDestroy(e);
+  for (auto& e : h->river_marks.ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    for (cudaEvent_t e : {h->ev_land_done[i], h->ev_river_done[i], h->ev_copy_done[i], h->ev_join[i]})
+      if (e) cudaEventDestroy(e);
+  if (h->s_river) cudaStreamDestroy(h->s_river);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -279,6 +317,7 @@ int hb_host_free(hb_engine* h, void* p) {
 // ---------------------------------------------------------------------------------------------------------------------
 int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, d && d->n_elem >= 0, HB_EINVAL, "hb_set_land: invalid description");
   HB_CUDA(h, cudaSetDevice(h->device));
   const int64_t ne = d->n_elem;
@@ -453,6 +492,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
 
 int hb_set_land_states(hb_engine* h, const hb_land_states* st) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_land_states: call hb_set_land first");
   HB_REQUIRE(h, st && (h->n_elem == 0 || (st->ic && st->sm && st->sp && st->wc && st->uz && st->lz)), HB_EINVAL,
              "hb_set_land_states: NULL state array");
@@ -488,6 +528,7 @@ int hb_set_land_states(hb_engine* h, const hb_land_states* st) {
 
 int hb_get_land_states(hb_engine* h, hb_land_states* st) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, h->have_land && h->have_states, HB_ESTATE, "hb_get_land_states: no states on the device");
   HB_REQUIRE(h, st, HB_EINVAL, "hb_get_land_states: NULL argument");
   HB_CUDA(h, cudaSetDevice(h->device));
@@ -543,6 +584,7 @@ int hb_select_series(hb_engine* h, int series, int on) {
 // ---------------------------------------------------------------------------------------------------------------------
 int hb_set_river(hb_engine* h, const hb_river_desc* r) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_river: call hb_set_land first");
   HB_REQUIRE(h, r && r->n_node >= 0 && r->n_reach >= 0, HB_EINVAL, "hb_set_river: invalid description");
   HB_CUDA(h, cudaSetDevice(h->device));
@@ -658,6 +700,7 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
 
 int hb_set_river_states(hb_engine* h, const double* discharge) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_set_river_states: call hb_set_river first");
   HB_REQUIRE(h, discharge || h->n_seg == 0, HB_EINVAL, "hb_set_river_states: NULL argument");
   HB_CUDA(h, cudaSetDevice(h->device));
@@ -671,6 +714,7 @@ int hb_set_river_states(hb_engine* h, const double* discharge) {
 
 int hb_get_river_states(hb_engine* h, double* discharge) {
   if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
   HB_REQUIRE(h, h->have_river, HB_ESTATE, "hb_get_river_states: call hb_set_river first");
   HB_REQUIRE(h, discharge || h->n_seg == 0, HB_EINVAL, "hb_get_river_states: NULL argument");
   HB_CUDA(h, cudaSetDevice(h->device));
@@ -691,6 +735,7 @@ int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcin
   HB_REQUIRE(h, nt >= 0 && n_col >= (h->n_elem ? 1 : 0) && (nt == 0 || doy) && (nt * n_col == 0 || forcing), HB_EINVAL,
              "hb_set_forcing: invalid argument (nt=%lld, n_col=%lld)", (long long)nt, (long long)n_col);
   HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));  // runoff generation of the previous window still reads the old block
   const size_t n = (size_t)HB_FORCING_COUNT * nt * n_col;
   HB_CUDA(h, h->d_forcing.reserve(n));
   if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing.p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -705,6 +750,7 @@ int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcin
   h->nt_total = nt;
   h->t0 = 0;
   h->n_col = n_col;
+  h->cur ^= 1;
   h->have_forcing = true;
   h->have_results = false;
   h->have_routed = false;
@@ -720,6 +766,7 @@ int hb_select_window(hb_engine* h, int64_t t0, int64_t nt) {
              (long long)(t0 + nt), (long long)h->nt_total);
   h->t0 = t0;
   h->nt = nt;
+  h->cur ^= 1;
   h->have_results = false;
   h->have_routed = false;
   h->have_ext = false;
@@ -733,10 +780,10 @@ int hb_set_external(hb_engine* h, int64_t nt, const double* rows) {
   HB_REQUIRE(h, rows || h->n_ext == 0 || nt == 0, HB_EINVAL, "hb_set_external: NULL argument");
   HB_CUDA(h, cudaSetDevice(h->device));
   const size_t n = (size_t)h->n_ext * nt;
-  HB_CUDA(h, h->d_ext_rows.reserve(n));
-  if (n) {
-    HB_CUDA(h, cudaMemcpyAsync(h->d_ext_rows.p, rows, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  HB_CUDA(h, h->d_ext_rows[h->cur].reserve(n));
+  if (n) {  // in routing-stream order: the routing of two windows ago has finished reading this buffer set
+    HB_CUDA(h, cudaMemcpyAsync(h->d_ext_rows[h->cur].p, rows, n * sizeof(double), cudaMemcpyHostToDevice, h->s_river));
+    HB_CUDA(h, cudaStreamSynchronize(h->s_river));
   }
   h->have_ext = true;
   return HB_OK;
@@ -745,7 +792,7 @@ int hb_set_external(hb_engine* h, int64_t nt, const double* rows) {
 static int run_land(hb_engine* h) {
   const int64_t nt = h->nt, ep = h->e_pad;
   HB_CUDA(h, h->d_qt.reserve((size_t)nt * ep));
-  HB_CUDA(h, h->d_land_rows.reserve((size_t)h->n_elem * nt));
+  HB_CUDA(h, h->d_land_rows[h->cur].reserve((size_t)h->n_elem * nt));
   bool any_series = false;
   for (int s = 0; s < HB_S_COUNT; ++s) any_series = any_series || h->series_on[s];
   // fast path (land_kernel_v2.cuh) for the eligible elements unless series are requested or the caller forces the
@@ -753,7 +800,6 @@ static int run_land(hb_engine* h) {
   const bool use_fast = h->n_fast > 0 && !any_series && h->land_path == HB_LAND_AUTO;
   const int64_t n_general = use_fast ? (int64_t)h->slow_list.size() : h->n_elem;
   h->timing.n_fast = use_fast ? h->n_fast : 0;
-  h->timing.land_launches = 0;
   if (h->n_elem == 0 || nt == 0) return HB_OK;
 
   if (use_fast) {
@@ -818,7 +864,7 @@ static int run_land(hb_engine* h) {
     h->timing.land_launches += 1;
   }
   dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
-  transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows.p, nt, h->n_elem, ep);
+  transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, h->n_elem, ep);
   HB_CUDA(h, cudaGetLastError());
   h->timing.land_launches += 1;
   return HB_OK;
@@ -826,15 +872,15 @@ static int run_land(hb_engine* h) {
 
 static int run_river(hb_engine* h) {
   const int64_t nt = h->nt;
-  HB_CUDA(h, h->d_node_rows.reserve((size_t)h->n_node * nt));
-  HB_CUDA(h, h->d_reach_in.reserve((size_t)h->n_reach * nt));
-  HB_CUDA(h, h->d_reach_out.reserve((size_t)h->n_reach * nt));
+  HB_CUDA(h, h->d_node_rows[h->cur].reserve((size_t)h->n_node * nt));
+  HB_CUDA(h, h->d_reach_in[h->cur].reserve((size_t)h->n_reach * nt));
+  HB_CUDA(h, h->d_reach_out[h->cur].reserve((size_t)h->n_reach * nt));
   RiverDev d{};
   d.n_node = h->n_node; d.n_reach = h->n_reach; d.nt = nt;
   d.entry_ptr = h->d_entry_ptr.p; d.entry_src = h->d_entry_src.p; d.node_mode = h->d_node_mode.p;
   d.node_ext = h->d_node_ext.p; d.inlet_ptr = h->d_inlet_ptr.p; d.inlet_node = h->d_inlet_node.p;
-  d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows.p; d.ext_rows = h->d_ext_rows.p;
-  d.node_rows = h->d_node_rows.p; d.reach_in = h->d_reach_in.p; d.reach_out = h->d_reach_out.p;
+  d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows[h->cur].p; d.ext_rows = h->d_ext_rows[h->cur].p;
+  d.node_rows = h->d_node_rows[h->cur].p; d.reach_in = h->d_reach_in[h->cur].p; d.reach_out = h->d_reach_out[h->cur].p;
   d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur;
   d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p;
   int64_t launches = 0;
@@ -850,24 +896,23 @@ static int run_river(hb_engine* h) {
         const int n = h->level_reach_ptr[l_hi + 1] - first;
         if (n <= 0) continue;
         const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
-        reach_diag_kernel<<<grid, block, 0, h->stream>>>(d, h->d_reach_order.p + first, n, diag, n_chunks);
+        reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag, n_chunks);
         ++launches;
       }
       h->dis_cur = (h->dis_cur + n_chunks) & 1;
     }
     if (h->n_terminal > 0) {
       const int block = 256, grid = (int)((h->n_terminal * 32 + block - 1) / block);
-      node_sum_kernel<<<grid, block, 0, h->stream>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
+      node_sum_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
       ++launches;
     }
     HB_CUDA(h, cudaGetLastError());
   }
-  h->timing.river_launches = launches;
+  h->timing.river_launches += launches;
   return HB_OK;
 }
 
-int hb_run(hb_engine* h, int flags) {
-  if (!h) return HB_EINVAL;
+static int enqueue_run(hb_engine* h, int flags) {
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_run: call hb_set_land first");
   HB_REQUIRE(h, h->have_forcing, HB_ESTATE, "hb_run: call hb_set_forcing first");
   HB_REQUIRE(h, (flags & (HB_RUN_LAND | HB_RUN_RIVER)) != 0, HB_EINVAL, "hb_run: no work requested");
@@ -879,37 +924,76 @@ int hb_run(hb_engine* h, int flags) {
     HB_REQUIRE(h, (flags & HB_RUN_LAND) || h->have_results, HB_ESTATE, "hb_run: routing needs the land results first");
   }
   int rc;
-  if (flags & HB_RUN_LAND)   // a routing-only call keeps the land figures
-    h->timing.land_ms = h->timing.zone_ms = h->timing.element_ms = h->timing.general_ms = 0.0, h->timing.land_launches = 0;
-  h->n_marks = 0;
-  h->timing.river_ms = 0.0;
+  const int c = h->cur;
   h->timing.n_levels = h->n_levels;
-  HB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  h->pending = true;
   if (flags & HB_RUN_LAND) {
-    h->timing.river_launches = 0;
     h->have_routed = false;
+    // the routing that read this set's land rows two windows ago must be through before they are overwritten
+    HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_river_done[c], 0));
+    h->land_marks.add(HB_K_BEGIN, h->stream);
     if ((rc = run_land(h))) return rc;
+    h->land_marks.add(HB_K_END, h->stream);
+    HB_CUDA(h, cudaEventRecord(h->ev_land_done[c], h->stream));
     h->have_results = true;
   }
-  HB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
   if (flags & HB_RUN_RIVER) {
+    HB_CUDA(h, cudaStreamWaitEvent(h->s_river, h->ev_land_done[c], 0));
+    HB_CUDA(h, cudaStreamWaitEvent(h->s_river, h->ev_copy_done[c], 0));  // rows of two windows ago are on the host
+    h->river_marks.add(HB_K_BEGIN, h->s_river);
     if ((rc = run_river(h))) return rc;
+    h->river_marks.add(HB_K_END, h->s_river);
+    HB_CUDA(h, cudaEventRecord(h->ev_river_done[c], h->s_river));
     h->have_routed = true;
   }
-  HB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-  HB_CUDA(h, cudaStreamSynchronize(h->stream));
-  float ms = 0.f;
-  if (flags & HB_RUN_LAND) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timing.land_ms = ms; }
-  if (flags & HB_RUN_RIVER) { HB_CUDA(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->timing.river_ms = ms; }
-  h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
-  for (size_t i = 1; i < h->n_marks; ++i) {
-    if (h->mark_tag[i] < 0) continue;
-    HB_CUDA(h, cudaEventElapsedTime(&ms, h->marks[i - 1], h->marks[i]));
-    if (h->mark_tag[i] == HB_K_ZONE) h->timing.zone_ms += ms;
-    else if (h->mark_tag[i] == HB_K_ELEMENT) h->timing.element_ms += ms;
-    else if (h->mark_tag[i] == HB_K_GENERAL) h->timing.general_ms += ms;
-  }
+  ++h->timing.n_runs;
   return HB_OK;
+}
+
+static int resolve_marks(hb_engine* h, hb_engine::Marks& m, bool land) {
+  float ms = 0.f;
+  size_t begin = 0;
+  for (size_t i = 0; i < m.n; ++i) {
+    const int tag = m.tag[i];
+    if (tag == HB_K_BEGIN) { begin = i; continue; }
+    if (tag == HB_K_END) {
+      HB_CUDA(h, cudaEventElapsedTime(&ms, m.ev[begin], m.ev[i]));
+      (land ? h->timing.land_ms : h->timing.river_ms) += ms;
+      continue;
+    }
+    if (tag == HB_K_OTHER || i == 0) continue;
+    HB_CUDA(h, cudaEventElapsedTime(&ms, m.ev[i - 1], m.ev[i]));
+    if (tag == HB_K_ZONE) h->timing.zone_ms += ms;
+    else if (tag == HB_K_ELEMENT) h->timing.element_ms += ms;
+    else if (tag == HB_K_GENERAL) h->timing.general_ms += ms;
+  }
+  m.n = 0;
+  return HB_OK;
+}
+
+int hb_wait(hb_engine* h) {
+  if (!h) return HB_EINVAL;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_river));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_copy));
+  int rc;
+  if ((rc = resolve_marks(h, h->land_marks, true)) || (rc = resolve_marks(h, h->river_marks, false))) return rc;
+  h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
+  h->pending = false;
+  return HB_OK;
+}
+
+int hb_run_async(hb_engine* h, int flags) {
+  if (!h) return HB_EINVAL;
+  return enqueue_run(h, flags);
+}
+
+int hb_run(hb_engine* h, int flags) {
+  if (!h) return HB_EINVAL;
+  int rc = enqueue_run(h, flags);
+  if (rc) return rc;
+  return hb_wait(h);
 }
 
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
@@ -945,9 +1029,20 @@ int hb_measure_fp64_peak(hb_engine* h, double* tflops) {
   return HB_OK;
 }
 
+static int join_streams(hb_engine* h) {
+  // everything enqueued so far on the routing and copy streams becomes a dependency of the land stream
+  HB_CUDA(h, cudaEventRecord(h->ev_join[0], h->s_river));
+  HB_CUDA(h, cudaEventRecord(h->ev_join[1], h->s_copy));
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+  return HB_OK;
+}
+
 int hb_timer_start(hb_engine* h) {
   if (!h) return HB_EINVAL;
   HB_CUDA(h, cudaSetDevice(h->device));
+  int rc = join_streams(h);
+  if (rc) return rc;
   HB_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
   return HB_OK;
 }
@@ -956,6 +1051,8 @@ int hb_timer_stop(hb_engine* h, double* ms) {
   if (!h || !ms) return HB_EINVAL;
   HB_CUDA(h, cudaSetDevice(h->device));
   if (!h->ev_stop) HB_CUDA(h, cudaEventCreate(&h->ev_stop));
+  int rc = join_streams(h);
+  if (rc) return rc;
   HB_CUDA(h, cudaEventRecord(h->ev_stop, h->stream));
   HB_CUDA(h, cudaEventSynchronize(h->ev_stop));
   float f = 0.f;
@@ -966,7 +1063,13 @@ int hb_timer_stop(hb_engine* h, double* ms) {
 
 int hb_get_timing(hb_engine* h, hb_timing* out) {
   if (!h || !out) return HB_EINVAL;
+  if (h->pending) { int rc = hb_wait(h); if (rc) return rc; }
   *out = h->timing;
+  // sums restart with the next run
+  const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast;
+  h->timing = hb_timing{};
+  h->timing.n_levels = n_levels;
+  h->timing.n_fast = n_fast;
   return HB_OK;
 }
 
@@ -974,6 +1077,8 @@ int hb_get_timing(hb_engine* h, hb_timing* out) {
 // results
 // ---------------------------------------------------------------------------------------------------------------------
 static int download(hb_engine* h, double* dst, const double* src, size_t n) {
+  int rc = hb_wait(h);  // results of an asynchronous run must be complete
+  if (rc) return rc;
   if (n) {
     HB_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     HB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -986,7 +1091,7 @@ int hb_get_land_outflow(hb_engine* h, double* rows) {
   HB_REQUIRE(h, h->have_results, HB_ESTATE, "hb_get_land_outflow: no results (call hb_run)");
   HB_REQUIRE(h, rows || h->n_elem * h->nt == 0, HB_EINVAL, "hb_get_land_outflow: NULL argument");
   HB_CUDA(h, cudaSetDevice(h->device));
-  return download(h, rows, h->d_land_rows.p, (size_t)h->n_elem * h->nt);
+  return download(h, rows, h->d_land_rows[h->cur].p, (size_t)h->n_elem * h->nt);
 }
 
 __global__ void gather_rows_kernel(const double* __restrict__ src, double* __restrict__ dst,
@@ -997,41 +1102,60 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, double* __res
   dst[i] = src[(int64_t)sel[r] * nt + t];
 }
 
-int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows) {
-  if (!h) return HB_EINVAL;
+static int node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows, bool async) {
   HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_node_series: no routing results (call hb_run)");
   HB_CUDA(h, cudaSetDevice(h->device));
+  const int c = h->cur;
+  const double* src = h->d_node_rows[c].p;
+  size_t n = (size_t)h->n_node * h->nt;
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_river_done[c], 0));
   if (n_sel == 0) {
-    HB_REQUIRE(h, rows || h->n_node * h->nt == 0, HB_EINVAL, "hb_get_node_series: NULL argument");
-    return download(h, rows, h->d_node_rows.p, (size_t)h->n_node * h->nt);
+    HB_REQUIRE(h, rows || n == 0, HB_EINVAL, "hb_get_node_series: NULL argument");
+  } else {
+    HB_REQUIRE(h, n_sel > 0 && nodes && rows, HB_EINVAL, "hb_get_node_series: invalid selection");
+    for (int64_t i = 0; i < n_sel; ++i)
+      HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node, HB_EINVAL, "hb_get_node_series: node %d out of range", nodes[i]);
+    n = (size_t)n_sel * h->nt;
+    HB_CUDA(h, h->d_sel.reserve((size_t)n_sel));
+    HB_CUDA(h, h->d_gather[c].reserve(n));
+    // the selection is small: a synchronous copy keeps the caller's array free to go
+    HB_CUDA(h, cudaMemcpyAsync(h->d_sel.p, nodes, (size_t)n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_copy));
+    if (n) {
+      gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->s_copy>>>(src, h->d_gather[c].p, h->d_sel.p, n_sel,
+                                                                            h->nt);
+      HB_CUDA(h, cudaGetLastError());
+    }
+    src = h->d_gather[c].p;
   }
-  HB_REQUIRE(h, n_sel > 0 && nodes && rows, HB_EINVAL, "hb_get_node_series: invalid selection");
-  for (int64_t i = 0; i < n_sel; ++i)
-    HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node, HB_EINVAL, "hb_get_node_series: node %d out of range", nodes[i]);
-  int rc = upload(h, h->d_sel, nodes, (size_t)n_sel);
-  if (rc) return rc;
-  const size_t n = (size_t)n_sel * h->nt;
-  HB_CUDA(h, h->d_gather.reserve(n));
-  if (n) {
-    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_node_rows.p, h->d_gather.p, h->d_sel.p,
-                                                                           n_sel, h->nt);
-    HB_CUDA(h, cudaGetLastError());
-  }
-  return download(h, rows, h->d_gather.p, n);
+  if (n) HB_CUDA(h, cudaMemcpyAsync(rows, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->s_copy));
+  HB_CUDA(h, cudaEventRecord(h->ev_copy_done[c], h->s_copy));
+  if (!async) return hb_wait(h);
+  h->pending = true;
+  return HB_OK;
+}
+
+int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows) {
+  if (!h) return HB_EINVAL;
+  return node_series(h, n_sel, nodes, rows, false);
+}
+
+int hb_get_node_series_async(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows) {
+  if (!h) return HB_EINVAL;
+  return node_series(h, n_sel, nodes, rows, true);
 }
 
 int hb_get_reach_outflow(hb_engine* h, double* rows) {
   if (!h) return HB_EINVAL;
   HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_reach_outflow: no routing results");
   HB_CUDA(h, cudaSetDevice(h->device));
-  return download(h, rows, h->d_reach_out.p, (size_t)h->n_reach * h->nt);
+  return download(h, rows, h->d_reach_out[h->cur].p, (size_t)h->n_reach * h->nt);
 }
 
 int hb_get_reach_inflow(hb_engine* h, double* rows) {
   if (!h) return HB_EINVAL;
   HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_reach_inflow: no routing results");
   HB_CUDA(h, cudaSetDevice(h->device));
-  return download(h, rows, h->d_reach_in.p, (size_t)h->n_reach * h->nt);
+  return download(h, rows, h->d_reach_in[h->cur].p, (size_t)h->n_reach * h->nt);
 }
 
 int hb_get_series(hb_engine* h, int series, double* out) {
@@ -1085,13 +1209,13 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
              HB_EINVAL, "hb_comm_send_rows: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
   const int64_t limit = kind == HB_ROW_NODE ? h->n_node : h->n_reach;
-  const double* base = kind == HB_ROW_NODE ? h->d_node_rows.p : h->d_reach_out.p;
+  const double* base = kind == HB_ROW_NODE ? h->d_node_rows[h->cur].p : h->d_reach_out[h->cur].p;
   for (int64_t i = 0; i < n; ++i)
     HB_REQUIRE(h, rows[i] >= 0 && rows[i] < limit, HB_EINVAL, "hb_comm_send_rows: row %d out of range", rows[i]);
   HB_NCCL(h, h->nccl.GroupStart());
   // the routing kernels wrote the rows in place: they are sent straight from the result buffers over NVLink
   for (int64_t i = 0; i < n; ++i)
-    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->stream));
+    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->s_river));
   HB_NCCL(h, h->nccl.GroupEnd());
   return HB_OK;
 }
@@ -1103,13 +1227,13 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
   HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || ext_rows), HB_EINVAL,
              "hb_comm_recv_ext: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
-  HB_CUDA(h, h->d_ext_rows.reserve((size_t)h->n_ext * h->nt));
+  HB_CUDA(h, h->d_ext_rows[h->cur].reserve((size_t)h->n_ext * h->nt));
   HB_NCCL(h, h->nccl.GroupStart());
   for (int64_t i = 0; i < n; ++i) {
     HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row out of range");
     // received straight into the external-row buffer the reach kernels read
-    HB_NCCL(h, h->nccl.Recv(h->d_ext_rows.p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
-                            h->stream));
+    HB_NCCL(h, h->nccl.Recv(h->d_ext_rows[h->cur].p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
+                            h->s_river));
   }
   HB_NCCL(h, h->nccl.GroupEnd());
   h->have_ext = true;

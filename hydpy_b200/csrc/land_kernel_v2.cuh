@@ -75,7 +75,10 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 // Calc_TC_V1 … Calc_EA_SM_AETModel_V1 and the per-zone factors of Calc_InUZ_V1 / Calc_ContriArea_V1 / Calc_LZ_V1 /
 // Calc_EL_LZ_V1 / Calc_InRC_V1)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4) zone_kernel(const LandV2Dev d) {
+#ifndef HB_ZONE_BLOCKS
+#define HB_ZONE_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
   const MathTables* T = &s_tables;

@@ -16,12 +16,13 @@ from . import layout
 from .abi import (LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc, hb_timing, ptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libhydpy_b200.so")
+LIBPATH = os.environ.get("HYDPY_B200_LIB") or os.path.join(HERE, "libhydpy_b200.so")
 
 EXPORTS = (
     "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
-    "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run", "hb_get_land_outflow", "hb_get_node_series",
+    "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run",
+    "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
     "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
@@ -72,6 +73,9 @@ def load_library() -> C.CDLL:
         "hb_select_window": (C.c_int, [H, C.c_int64, C.c_int64]),
         "hb_set_external": (C.c_int, [H, C.c_int64, f64p]),
         "hb_run": (C.c_int, [H, C.c_int]),
+        "hb_run_async": (C.c_int, [H, C.c_int]),
+        "hb_wait": (C.c_int, [H]),
+        "hb_get_node_series_async": (C.c_int, [H, C.c_int64, i32p, f64p]),
         "hb_get_land_outflow": (C.c_int, [H, f64p]),
         "hb_get_node_series": (C.c_int, [H, C.c_int64, i32p, f64p]),
         "hb_get_reach_outflow": (C.c_int, [H, f64p]),
@@ -270,6 +274,28 @@ class Engine:
     def run(self, land: bool = True, river: bool = True) -> None:
         flags = (layout.RUN_LAND if land else 0) | (layout.RUN_RIVER if river else 0)
         self._check(self._lib.hb_run(self._h, flags), "hb_run")
+
+    def run_async(self, land: bool = True, river: bool = True) -> None:
+        """Enqueue the window and return: the next window's runoff generation overlaps this window's routing and
+        result copies (see `hb_run_async`).  `wait()` — or any synchronous call — collects the work."""
+        flags = (layout.RUN_LAND if land else 0) | (layout.RUN_RIVER if river else 0)
+        self._check(self._lib.hb_run_async(self._h, flags), "hb_run_async")
+
+    def wait(self) -> None:
+        self._check(self._lib.hb_wait(self._h), "hb_wait")
+
+    def get_node_series_async(self, out: np.ndarray) -> None:
+        """Copy all node series of the current window into the PINNED array `out` behind its routing; valid after
+        `wait()`."""
+        river = self._need_river()
+        if out.shape != (river.n_node, self.nt) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (n_node, nt)")
+        self._check(self._lib.hb_get_node_series_async(self._h, 0, None, ptr(out, C.c_double)),
+                    "hb_get_node_series_async")
+
+    @property
+    def window_steps(self) -> int:
+        return self.nt
 
     # -- results ----------------------------------------------------------------------------------------------------
     def get_land_outflow(self, out: np.ndarray | None = None) -> np.ndarray:

@@ -231,6 +231,12 @@ int hb_set_external(hb_engine* h, int64_t nt, const double* rows);
 #define HB_RUN_LAND 1
 #define HB_RUN_RIVER 2
 int hb_run(hb_engine* h, int flags);
+/* Pipelined variant for window loops: enqueues the same work and returns at once.  Runoff generation of the next window
+ * (after hb_set_forcing / hb_select_window) then overlaps routing and result copies of this one; the engine keeps two
+ * sets of per-window buffers, so results of a window stay readable until the window after the next is staged.
+ * hb_wait returns when everything enqueued so far is complete; every synchronous call waits implicitly. */
+int hb_run_async(hb_engine* h, int flags);
+int hb_wait(hb_engine* h);
 
 /* ---- results of the last window -------------------------------------------------------------------------------- */
 /* `outlets.q` (= fluxes.qt) of every land element: host [n_elem][nt] (element-major rows). */
@@ -238,6 +244,9 @@ int hb_get_land_outflow(hb_engine* h, double* rows);
 /* node.sequences.sim.series of the window: host [n_node][nt].  n_sel = 0 ⇒ all nodes in order, else rows of
  * the listed nodes. */
 int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows);
+/* Same, enqueued behind the routing of the current window on the copy stream; `rows` must be page-locked
+ * (hb_host_alloc) and stay untouched until hb_wait. */
+int hb_get_node_series_async(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows);
 /* musk_classic fluxes.outflow / outlets.q of every reach: host [n_reach][nt]. */
 int hb_get_reach_outflow(hb_engine* h, double* rows);
 /* musk_classic fluxes.inflow of every reach: host [n_reach][nt]. */
@@ -261,9 +270,9 @@ int hb_comm_barrier(hb_engine* h);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 typedef struct hb_timing {
-  double land_ms;        /* CUDA-event time of the runoff-generation kernel(s) of the last hb_run               */
-  double river_ms;       /* CUDA-event time of all routing kernels of the last hb_run                           */
-  double total_ms;       /* CUDA-event time of the whole hb_run on the engine stream                            */
+  double land_ms;        /* CUDA-event time of the runoff-generation kernel(s), on the land stream               */
+  double river_ms;       /* CUDA-event time of all routing kernels, on the routing stream                        */
+  double total_ms;       /* land_ms + river_ms                                                                   */
   int64_t land_launches;   /* kernels launched for the land part                                                */
   int64_t river_launches;  /* kernels launched for the river part                                               */
   int64_t n_levels;        /* topological levels of the river network                                           */
@@ -271,7 +280,10 @@ typedef struct hb_timing {
   double element_ms;       /* runoff generation, fast path: thread-per-element kernel                               */
   double general_ms;       /* runoff generation, general kernel (elements the fast path does not cover, or series)  */
   int64_t n_fast;          /* land elements on the fast path in the last hb_run                                     */
+  int64_t n_runs;          /* hb_run / hb_run_async calls the sums above cover                                      */
 } hb_timing;
+/* Times and launch counts are SUMS over all runs since the previous hb_get_timing call (which resets them); after a
+ * single hb_run they are that run's figures.  Waits for pending asynchronous work. */
 int hb_get_timing(hb_engine* h, hb_timing* out);
 /* Generic device timer on the engine's stream (CUDA events): everything enqueued between start and stop — kernels,
  * copies, NCCL sends/receives — is covered.  hb_timer_stop synchronises the stream and returns milliseconds. */

@@ -158,3 +158,55 @@ def test_ensemble_members_share_forcing_and_member0_equals_base(engine):
     ref = oracle_run(Problem(land=eland, states=estates, river=eriver, discharge=edis, forcing=forcing, doy=doy,
                              ext=np.zeros((0, nt))))
     assert_close(ens["node_rows"], ref["node_rows"], "ensemble: node series")
+
+
+def test_pipelined_windows_equal_synchronous_windows(engine):
+    """hb_run_async / hb_get_node_series_async (land of window w+1 overlapping routing and copies of window w) must give
+    exactly what the synchronous calls give, for host-staged forcing as well as for a resident forcing block."""
+    ne, win, nw = 3000, 24, 5
+    land, states = synth.make_land(ne, "1h", variants=True)
+    river, discharge = synth.make_tree_river(ne, "1h", levels=30)
+    forcing, doy = synth.make_forcing(win * nw, "1h")
+    no_ext = np.zeros((0, win))
+
+    def setup():
+        engine.set_land(land)
+        engine.set_land_states(states)
+        engine.set_river(river)
+        engine.set_river_states(discharge)
+        engine.select_series([])
+
+    setup()
+    sync_rows = []
+    for w in range(nw):
+        engine.set_forcing(forcing[:, w * win:(w + 1) * win], doy[w * win:(w + 1) * win])
+        engine.set_external(no_ext)
+        engine.run()
+        sync_rows.append(engine.get_node_series())
+    sync_states, sync_dis = engine.get_land_states(), engine.get_river_states()
+
+    for resident in (False, True):
+        setup()
+        bufs = [engine.pinned((river.n_node, win)) for _ in range(nw)]
+        if resident:
+            engine.set_forcing(forcing, doy)
+        engine.timing()                      # reset the sums
+        for w in range(nw):
+            if resident:
+                engine.select_window(w * win, win)
+            else:
+                engine.set_forcing(forcing[:, w * win:(w + 1) * win], doy[w * win:(w + 1) * win])
+            engine.set_external(no_ext)
+            engine.run_async()
+            engine.get_node_series_async(bufs[w].array)
+        engine.wait()
+        for w in range(nw):
+            assert np.array_equal(bufs[w].array, sync_rows[w]), f"window {w} (resident={resident})"
+        st, dis = engine.get_land_states(), engine.get_river_states()
+        for n in st.NAMES:
+            assert np.array_equal(getattr(st, n), getattr(sync_states, n)), n
+        assert np.array_equal(dis, sync_dis)
+        tm = engine.timing()
+        assert tm["n_runs"] == nw and tm["land_ms"] > 0 and tm["river_ms"] > 0
+        for b in bufs:
+            b.free()

@@ -37,7 +37,7 @@ for rep in range(args.reps):
     t2 = time.time()
     tm = eng.timing()
     zs = land.n_zone * args.nt
-    print(f"rep {rep}: h2d {1e3*(t1-t):.1f} ms  run wall {1e3*(t2-t1):.1f} ms  land {tm['land_ms']:.2f} ms  river {tm['river_ms']:.2f} ms "
+    print(f"rep {rep}: h2d {1e3*(t1-t):.1f} ms  run wall {1e3*(t2-t1):.1f} ms  land {tm['land_ms']:.2f} ms (zone {tm['zone_ms']:.2f} element {tm['element_ms']:.2f})  river {tm['river_ms']:.2f} ms "
           f"({tm['river_launches']} launches, {tm['n_levels']} levels)  -> {zs/tm['total_ms']*1e3:.3e} zone-steps/s (device)")
 t = time.time()
 rows = eng.get_node_series() if not args.no_river else eng.get_land_outflow()
