@@ -124,6 +124,7 @@ struct hb_engine {
   int64_t n_elem = 0, e_pad = 0, n_zone = 0, n_snow = 0, n_uh = 0;
   int zmax = 0, cmax = 0, umax = 0;
   bool any_snowlimit = false;
+  bool any_nonsoil_warp = false;      // some warp of the zone kernel holds a fast-path zone that is not FIELD/FOREST with FC > 0
   int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
   std::vector<int32_t> slow_list;     // the others
   DBuf<int32_t> d_slow_list;
@@ -457,6 +458,15 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
 #undef EPAR
   for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = ne ? d->sred_ptr[ne] : 0;
   h->any_snowlimit = any_snowlimit;
+  h->any_nonsoil_warp = false;
+  for (int64_t e = 0; e < ne && !h->any_nonsoil_warp; ++e) {
+    if (!(einfo[e] & HB_EI_FAST)) continue;
+    for (int k = 0; k < nz[e]; ++k) {
+      const int zt = zinfo[(size_t)k * ep + e] & 7;
+      const double fc = kz[((size_t)k * KZ_COUNT + KZ_FC) * ep + e];
+      if (!((zt == HB_FIELD || zt == HB_FOREST) && fc > 0.0)) { h->any_nonsoil_warp = true; break; }
+    }
+  }
   h->n_fast = n_fast;
   h->slow_list = slow_list;
   h->h_nz = nz; h->h_nc = nc; h->h_nu = nu;
@@ -824,7 +834,11 @@ static int run_land(hb_engine* h) {
       v.t_first = h->t0 + c0;
       v.t_out = c0;
       h->mark(-1);
-      zone_kernel<<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+      zone_kernel<true><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+      if (h->any_nonsoil_warp) {
+        zone_kernel<false><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+        h->timing.land_launches += 1;
+      }
       h->mark(HB_K_ZONE);
       element_kernel<<<(unsigned)((h->n_elem + 63) / 64), 64, 0, h->stream>>>(v);
       h->mark(HB_K_ELEMENT);

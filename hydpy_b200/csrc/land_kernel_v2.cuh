@@ -78,6 +78,8 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 #ifndef HB_ZONE_BLOCKS
 #define HB_ZONE_BLOCKS 4
 #endif
+// SOIL = true : the warps whose 32 zones are all FIELD/FOREST with FC > 0 (branch-free step); SOIL = false: all other warps
+template <bool SOIL>
 __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
@@ -125,12 +127,126 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 
   double n_p = 0.0, n_t = 0.0, n_nat = 0.0, n_net = 0.0, n_sin = 0.0;
   if (d.nt > 0) { n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp); }
-  for (int64_t t = 0; t < d.nt; ++t) {
-    const double in_p = n_p, in_t = n_t, in_nat = n_nat, in_net = n_net, sinf = n_sin;
-    if (t + 1 < d.nt) {  // prefetch the next step's forcing; consumed one iteration later
-      const int64_t o = (t + 1) * d.n_col;
-      n_p = ldg(fP + o); n_t = ldg(fT + o); n_nat = ldg(fA + o); n_net = ldg(fE + o); n_sin = ldg(sinp + t + 1);
+#define HB_ZONE_STEP_BEGIN                                                                                    \
+  const double in_p = n_p, in_t = n_t, in_nat = n_nat, in_net = n_net, sinf = n_sin;                             \
+  if (t + 1 < d.nt) { /* prefetch the next step's forcing; consumed one iteration later */                       \
+    const int64_t o = (t + 1) * d.n_col;                                                                         \
+    n_p = ldg(fP + o); n_t = ldg(fT + o); n_nat = ldg(fA + o); n_net = ldg(fE + o); n_sin = ldg(sinp + t + 1);   \
+  }
+
+  // ---- warps whose 32 zones are all FIELD/FOREST with FC > 0 (the bulk of any basin) run a BRANCH-FREE step: every
+  // data-dependent `if` of the reference becomes a select on values that are computed unconditionally.  Results are
+  // the same bit for bit (x - 0.0 == x, x * 1 == x …); the point is one large basic block in which the scheduler can
+  // interleave the independent chains (snow, exp of PET, pow of R, pow of ContriArea) — with 4 warps per scheduler the
+  // kernel is latency-bound otherwise (ncu: 62 % issue utilisation, half of the stall cycles are fixed-latency waits).
+  const unsigned amask = __activemask();
+  if (__all_sync(amask, soil && fc > 0.0) != SOIL) return;
+  if (SOIL) {
+    const bool f_icept = (zf & HB_ZF_INTERCEPTION) != 0, f_soil = (zf & HB_ZF_SOIL) != 0;
+    for (int64_t t = 0; t < d.nt; ++t) {
+      HB_ZONE_STEP_BEGIN
+      // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
+      const double tc = in_t + tcorr - tcalt_dz;
+      double fracrain = (tc - tt_lo) * inv_ttint;
+      fracrain = (tc <= tt_lo) ? 0.0 : fracrain;
+      fracrain = (tc >= tt_hi) ? 1.0 : fracrain;
+      const double pc0 = in_p * pcalt_f;
+      double pc = pc0 * (pcorr / (fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf));
+      pc = (pc0 <= 0.0) ? 0.0 : pc;
+      // ref: hland_model.py:299-309 Calc_TF_Ic_V1
+      const double a = pc - (icmax - ic);
+      const double tf = HB_PYMAX(a, 0.0);
+      ic += pc - tf;
+      // ref: hland_model.py:484-499 Calc_SP_WC_V1, 1050-1062 Calc_CFAct_V1
+      wc += sf * (tf * fracrain);
+      sp += sf * (tf * (1.0 - fracrain));
+      const double cfa = cfmax + sinf * cfvar;
+      const double cfact = HB_PYMAX(cfa, 0.0);
+      // ref: hland_model.py:1166-1187 Calc_Melt_SP_WC_V1, 1318-1341 Calc_Refr_SP_WC_V1
+      {
+        const double potmelt = cfact * (tc - ttm);
+        double melt = HB_PYMIN(potmelt, sp);
+        melt = (tc > ttm) ? melt : 0.0;
+        sp -= melt; wc += melt;
+        const double potrefr = cfr_cfmax * (ttm - tc);
+        double refr = HB_PYMIN(potrefr, wc);
+        refr = (tc < ttm) ? refr : 0.0;
+        sp += refr; wc -= refr;
+      }
+      // ref: hland_model.py:1434-1448 Calc_In_WC_V1
+      const double wc_old = wc, lim = whc * sp;
+      wc = HB_PYMIN(wc_old, lim);
+      const double in_ = wc_old - wc;
+      const double ncover = (sp > 0.0) ? 1.0 : 0.0;
+      // evap_pet_hbv96.run(): ref: evap_model.py:5111-5125, 5420-5424, 5312-5326
+      double pet;
+      {
+        double ret = in_net * (1.0 + atf * (in_t - in_nat));
+        const double lo = HB_PYMAX(ret, 0.0);
+        const double hi = 2.0 * in_net;
+        ret = HB_PYMIN(lo, hi);
+        ret *= etf;
+        pet = ret * alt_f;
+        const double damp = hb_exp(neg_pf * pc, T);
+        pet = (pet <= 0.0) ? 0.0 : pet * damp;
+      }
+      // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1; hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
+      double aet_ie = HB_PYMIN(pet, ic);
+      aet_ie = f_icept ? aet_ie : 0.0;
+      {
+        const double ei = HB_PYMIN(aet_ie, ic);
+        ic -= ei;
+      }
+      // ref: hland_model.py:1776-1790 Calc_R_SM_V1
+      double r = in_ * hb_pow(sm * inv_fc, beta, T);
+      {
+        const double a2 = sm + in_ - fc;
+        r = HB_PYMAX(r, a2);
+      }
+      sm += in_ - r;
+      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0
+      double cf = 0.0 * (1.0 - sm * inv_fc);
+      {
+        const double b = fc - sm;
+        cf = HB_PYMIN(cf, b);
+      }
+      sm += cf;
+      // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1 (6657-6672, 7001-7018, 7060-7069)
+      double set = pet;
+      {
+        double s1 = set * (sm * inv_thresh);
+        s1 = (sm < thresh) ? s1 : set;
+        s1 = (sm < 0.0) ? 0.0 : s1;
+        set = (set > 0.0) ? s1 : set;
+        const double petc = excessred * pet + (1.0 - excessred) * (pet + pet) / 2.0;
+        const double excess = set + aet_ie - petc;
+        const bool adjust = ((petc >= 0.0) && (excess > 0.0)) || ((petc < 0.0) && (excess < 0.0));
+        const double adjusted = set - excessred * excess;
+        set = adjust ? adjusted : set;
+        set *= 1.0 - ncover;
+        set = f_soil ? set : 0.0;
+      }
+      // ref: hland_model.py:2002-2018 Calc_EA_SM_AETModel_V1
+      const double ea = HB_PYMIN(set, sm);
+      sm -= ea;
+      {
+        const bool over = sm > fc;
+        const double r_over = r + (sm - fc);
+        r = over ? r_over : r;
+        sm = over ? fc : sm;
+      }
+      // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
+      const double contri = hb_pow(sm * inv_fc, w_b, T);
+      out_a[t * tstride] = w_a * (r - cf);
+      out_b[t * tstride] = resp ? contri : 1.0;
     }
+    d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
+    return;
+  }
+
+  // ---- general step (any zone type) ------------------------------------------------------------------------------------
+  for (int64_t t = 0; t < d.nt; ++t) {
+    HB_ZONE_STEP_BEGIN
     // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
     const double tc = in_t + tcorr - tcalt_dz;
     double fracrain;
@@ -248,13 +364,20 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
     out_a[t * tstride] = ta;
     out_b[t * tstride] = tb;
   }
+#undef HB_ZONE_STEP_BEGIN
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // element kernel: ordered zone sums + Calc_Q0_Perc_UZ_V1 … Calc_QT_V1
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64, 16) element_kernel(const LandV2Dev d) {
+#ifndef HB_ELEM_PREFETCH
+#define HB_ELEM_PREFETCH 1
+#endif
+#ifndef HB_ELEM_BLOCKS
+#define HB_ELEM_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
   const MathTables* T = &s_tables;
@@ -276,6 +399,20 @@ __global__ void __launch_bounds__(64, 16) element_kernel(const LandV2Dev d) {
   for (int64_t t = 0; t < d.nt; ++t) {
     const double* ta = d.term_a + t * tstride + e;
     const double* tb = d.term_b + t * tstride + e;
+#if HB_ELEM_PREFETCH
+    // the terms of the NEXT step are pulled towards the SM while the RecStep loop of this step runs (they were written
+    // by the zone kernel gigabytes ago, i.e. they come from HBM); costs no registers
+    if (t + 1 < d.nt)
+      for (int k = 0; k < nz; ++k) {
+#if HB_ELEM_PREFETCH == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ta + tstride + (int64_t)k * ep));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + tstride + (int64_t)k * ep));
+#else
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ta + tstride + (int64_t)k * ep));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + tstride + (int64_t)k * ep));
+#endif
+      }
+#endif
     double inuz = 0.0, contriarea = 1.0;
     if (soilonly) {
       for (int k = 0; k < nz; ++k) {
