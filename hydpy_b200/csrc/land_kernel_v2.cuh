@@ -116,12 +116,14 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
   double ic = d.ic[slot], sm = d.sm[slot], sp = d.sp[slot], wc = d.wc[slot];
 
   const int64_t col = d.fcol[e];
+  // all per-step addresses advance by pointer bumps (no 64-bit multiplies in the loop)
   const double* fP = d.forcing + (0 * d.nt_total + d.t_first) * d.n_col + col;
   const double* fT = d.forcing + (1 * d.nt_total + d.t_first) * d.n_col + col;
   const double* fA = d.forcing + (2 * d.nt_total + d.t_first) * d.n_col + col;
   const double* fE = d.forcing + (3 * d.nt_total + d.t_first) * d.n_col + col;
   const double* sinp = d.sinfactor + d.t_first;
   const int64_t tstride = (int64_t)d.zmax * ep;
+  const int64_t fstride = d.n_col;
   double* out_a = d.term_a + slot;
   double* out_b = d.term_b + slot;
 
@@ -129,10 +131,13 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
   if (d.nt > 0) { n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp); }
 #define HB_ZONE_STEP_BEGIN                                                                                    \
   const double in_p = n_p, in_t = n_t, in_nat = n_nat, in_net = n_net, sinf = n_sin;                             \
-  if (t + 1 < d.nt) { /* prefetch the next step's forcing; consumed one iteration later */                       \
-    const int64_t o = (t + 1) * d.n_col;                                                                         \
-    n_p = ldg(fP + o); n_t = ldg(fT + o); n_nat = ldg(fA + o); n_net = ldg(fE + o); n_sin = ldg(sinp + t + 1);   \
+  if (t + 1 < nt) { /* prefetch the next step's forcing; consumed one iteration later */                         \
+    fP += fstride; fT += fstride; fA += fstride; fE += fstride; ++sinp;                                          \
+    n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp);                           \
   }
+#define HB_ZONE_STEP_END(va, vb) \
+  *out_a = (va); *out_b = (vb); out_a += tstride; out_b += tstride;
+  const int nt = (int)d.nt;
 
   // ---- warps whose 32 zones are all FIELD/FOREST with FC > 0 (the bulk of any basin) run a BRANCH-FREE step: every
   // data-dependent `if` of the reference becomes a select on values that are computed unconditionally.  Results are
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
   if (__all_sync(amask, soil && fc > 0.0) != SOIL) return;
   if (SOIL) {
     const bool f_icept = (zf & HB_ZF_INTERCEPTION) != 0, f_soil = (zf & HB_ZF_SOIL) != 0;
-    for (int64_t t = 0; t < d.nt; ++t) {
+    for (int t = 0; t < nt; ++t) {
       HB_ZONE_STEP_BEGIN
       // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
       const double tc = in_t + tcorr - tcalt_dz;
@@ -237,15 +242,14 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       }
       // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
       const double contri = hb_pow(sm * inv_fc, w_b, T);
-      out_a[t * tstride] = w_a * (r - cf);
-      out_b[t * tstride] = resp ? contri : 1.0;
+      HB_ZONE_STEP_END(w_a * (r - cf), resp ? contri : 1.0)
     }
     d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
     return;
   }
 
   // ---- general step (any zone type) ------------------------------------------------------------------------------------
-  for (int64_t t = 0; t < d.nt; ++t) {
+  for (int t = 0; t < nt; ++t) {
     HB_ZONE_STEP_BEGIN
     // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
     const double tc = in_t + tcorr - tcalt_dz;
@@ -361,10 +365,10 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         tb = w_b * el;
       } else ta = w_a * (in_ - 0.0);  // GLACIER: InUZ term; SEALED: InRC term (r = in_, ref: hland_model.py:1528-1535)
     }
-    out_a[t * tstride] = ta;
-    out_b[t * tstride] = tb;
+    HB_ZONE_STEP_END(ta, tb)
   }
 #undef HB_ZONE_STEP_BEGIN
+#undef HB_ZONE_STEP_END
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
 }
 
