@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,8 @@
 #include "river_kernel.cuh"
 
 using namespace hb;
+
+#define HB_BULK_MIN 2048   // reaches in one routing launch from which the lane-per-reach kernel takes over
 
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
@@ -130,6 +133,7 @@ struct hb_engine {
   DBuf<int32_t> d_slow_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
+  int64_t river_bulk_min = HB_BULK_MIN;  // reaches per routing launch from which reach_bulk_kernel takes over
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
@@ -237,6 +241,7 @@ int hb_create(int device, hb_engine** out) {
     return HB_ECUDA;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  cudaFuncSetAttribute(reach_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_BULK_SMEM);
   {
     // routing is a chain of ≈(levels + chunks) short dependent launches: at the highest priority its blocks take every
     // slot the long-running land blocks free, so the chain is not starved while it overlaps the next window's land part
@@ -576,6 +581,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       HB_REQUIRE(h, value == HB_LAND_AUTO || value == HB_LAND_GENERAL, HB_EINVAL, "hb_set_option: invalid land path");
       h->land_path = (int)value;
       return HB_OK;
+    case HB_OPT_RIVER_BULK_MIN:
+      HB_REQUIRE(h, value >= 0, HB_EINVAL, "hb_set_option: invalid routing threshold");
+      h->river_bulk_min = value ? value : HB_BULK_MIN;
+      return HB_OK;
     default:
       return h->fail(HB_EINVAL, "hb_set_option: unknown option %d", option);
   }
@@ -676,6 +685,11 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     if (nlev == 0) { np.clear(); rp.clear(); }
     for (int64_t n = 0; n < nn; ++n) node_order[np[node_level[n]]++] = (int32_t)n;
     for (int64_t q = 0; q < nr; ++q) reach_order[rp[reach_level[q]]++] = (int32_t)q;
+    // within a level: by number of segments, so that the lanes of a lane-per-reach warp run loops of similar length
+    for (int l = 0; l < nlev; ++l)
+      std::stable_sort(reach_order.begin() + lrp[l], reach_order.begin() + lrp[l + 1], [&](int32_t a, int32_t b) {
+        return r->seg_ptr[a + 1] - r->seg_ptr[a] < r->seg_ptr[b + 1] - r->seg_ptr[b];
+      });
   }
   // the reach that stores a node's row during the sweep = its first exit; nodes without exits are summed at the end
   std::vector<int32_t> node_owner(nn, -1), terminal;
@@ -910,8 +924,16 @@ static int run_river(hb_engine* h) {
         const int n = h->level_reach_ptr[l_hi + 1] - first;
         if (n <= 0) continue;
         const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
-        reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag, n_chunks);
+        // wide diagonals are throughput-bound: lane-per-reach recurrence (reach_bulk_kernel) after the inflow pass
+        const int bulk = n >= h->river_bulk_min ? 1 : 0;
+        reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag, n_chunks, bulk);
         ++launches;
+        if (bulk) {
+          const int bgrid = (n + 32 * HB_BULK_WARPS - 1) / (32 * HB_BULK_WARPS);
+          reach_bulk_kernel<<<bgrid, 32 * HB_BULK_WARPS, HB_BULK_SMEM, h->s_river>>>(d, h->d_reach_order.p + first, n, diag,
+                                                                                  n_chunks);
+          ++launches;
+        }
       }
       h->dis_cur = (h->dis_cur + n_chunks) & 1;
     }

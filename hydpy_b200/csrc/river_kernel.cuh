@@ -49,6 +49,9 @@ struct RiverDev {
 };
 
 #define HB_RIVER_CHUNK 32
+#define HB_BULK_SMAX 32      // reaches with more segments always take the systolic path
+#define HB_BULK_WARPS 4      // warps per block of reach_bulk_kernel
+#define HB_BULK_SMEM (HB_BULK_WARPS * (32 * 33 + (HB_BULK_SMAX + 1) * 32) * 8)
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
 __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restrict__ qt, double* __restrict__ rows,
@@ -101,8 +104,9 @@ __device__ __forceinline__ double node_sum_at(const RiverDev& d, int64_t node, i
   return acc;
 }
 
+// bulk != 0: reaches with 1..HB_BULK_SMAX segments only get their inflow here; reach_bulk_kernel runs their recurrence
 __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n,
-                                                         int diag, int n_chunks) {
+                                                         int diag, int n_chunks, int bulk) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (warp >= n) return;
   const unsigned full = 0xffffffffu;
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
   }
   const double x_last = __shfl_sync(full, x_own, len - 1);
   if (lane == 0) dis_new[g0] = x_last;
-  if (S == 0) return;
+  if (S == 0 || (bulk && S <= HB_BULK_SMAX)) return;
 
   // ---- systolic pipeline over groups of 32 segments --------------------------------------------------------------------
   for (int cbase = 0; cbase < S; cbase += 32) {
@@ -177,6 +181,83 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
     if (lane < nseg) dis_new[g0 + cbase + lane + 1] = prev_out;
     x_own = yb;                                      // the next segment group continues on this output
     if (cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
+  }
+}
+
+// Wide anti-diagonals (thousands of reaches, e.g. all headwater reaches at once) are throughput-bound, and there the
+// systolic warp-per-reach mapping wastes lanes (12 segments on average) and ≈25 instructions per tick.  This kernel
+// maps LANE = REACH instead: a warp takes 32 reaches, stages their 32-step inflow tile in shared memory with coalesced
+// row loads (lanes over time), then every lane runs its own reach sequentially over time and segments — the same
+// operations in the same order ((c0*new[i] + c1*old[i]) + c2*old[i+1], ref: musk_model.py:178-187), ≈0.3 warp
+// instructions per reach-segment-step — and the outflow tile goes back with coalesced stores.  The inflow rows were
+// written by reach_diag_kernel(bulk = 1) in the launch before.
+__global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const RiverDev d, const int32_t* __restrict__ reaches,
+                                                                       int n, int diag, int n_chunks) {
+  extern __shared__ double smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* X = smem + (size_t)wib * (32 * 33 + (HB_BULK_SMAX + 1) * 32);   // [reach lane][33]: inflow, then outflow
+  double* Q = X + 32 * 33;                                              // [segment point][lane]
+  const unsigned full = 0xffffffffu;
+  const int task = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32 + lane;
+  int64_t r = -1, ta = 0, g0 = 0;
+  int len = 0, S = 0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  const int64_t nt = d.nt;
+  if (task < n) {
+    const int64_t rr = reaches[task];
+    const int c = diag - d.reach_level[rr];
+    g0 = d.seg_ptr[rr];
+    S = (int)(d.seg_ptr[rr + 1] - g0 - 1);
+    if (c >= 0 && c < n_chunks && S >= 1 && S <= HB_BULK_SMAX) {
+      r = rr;
+      ta = (int64_t)c * HB_RIVER_CHUNK;
+      const int64_t tb = (ta + HB_RIVER_CHUNK < nt) ? ta + HB_RIVER_CHUNK : nt;
+      len = (int)(tb - ta);
+      c0 = d.coef[0 * d.n_reach + r]; c1 = d.coef[1 * d.n_reach + r]; c2 = d.coef[2 * d.n_reach + r];
+    }
+  }
+  if (__all_sync(full, r < 0)) return;
+  const int c_own = (r >= 0) ? diag - d.reach_level[r] : 0;
+  // ---- inflow tile: row j of the tile = reach of lane j, lanes over time (coalesced) -----------------------------------
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+    const int64_t rj = __shfl_sync(full, r, j);
+    const int64_t taj = __shfl_sync(full, ta, j);
+    const int lenj = __shfl_sync(full, len, j);
+    if (rj >= 0 && lane < lenj) X[j * 33 + lane] = d.reach_in[rj * nt + taj + lane];
+  }
+  // ---- state of the own reach ----------------------------------------------------------------------------------------------
+  if (r >= 0) {
+    const double* dis_old = d.dis[(d.par0 + c_own) & 1];
+    for (int i = 0; i <= S; ++i) Q[i * 32 + lane] = dis_old[g0 + i];
+  }
+  __syncwarp();
+  // ---- lane = reach: sequential over time and segments ------------------------------------------------------------------
+  if (r >= 0) {
+    for (int tt = 0; tt < len; ++tt) {
+      double in = X[lane * 33 + tt];
+      double q_old = Q[lane];
+      Q[lane] = in;
+      for (int i = 0; i < S; ++i) {
+        const double q_next = Q[(i + 1) * 32 + lane];
+        const double nv = c0 * in + c1 * q_old + c2 * q_next;
+        Q[(i + 1) * 32 + lane] = nv;
+        q_old = q_next;
+        in = nv;
+      }
+      X[lane * 33 + tt] = in;
+    }
+    double* dis_new = d.dis[(d.par0 + c_own + 1) & 1];
+    for (int i = 0; i <= S; ++i) dis_new[g0 + i] = Q[i * 32 + lane];
+  }
+  __syncwarp();
+  // ---- outflow tile back to the rows (coalesced) --------------------------------------------------------------------------
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+    const int64_t rj = __shfl_sync(full, r, j);
+    const int64_t taj = __shfl_sync(full, ta, j);
+    const int lenj = __shfl_sync(full, len, j);
+    if (rj >= 0 && lane < lenj) d.reach_out[rj * nt + taj + lane] = X[j * 33 + lane];
   }
 }
 
