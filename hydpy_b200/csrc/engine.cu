@@ -21,8 +21,6 @@
 
 using namespace hb;
 
-#define HB_BULK_MIN 2048   // reaches in one routing launch from which the lane-per-reach kernel takes over
-
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
@@ -133,7 +131,7 @@ struct hb_engine {
   DBuf<int32_t> d_slow_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
-  int64_t river_bulk_min = HB_BULK_MIN;  // reaches per routing launch from which reach_bulk_kernel takes over
+  int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
@@ -157,6 +155,14 @@ struct hb_engine {
   DBuf<int32_t> d_entry_src, d_node_mode, d_node_ext, d_inlet_node, d_node_order, d_reach_order, d_sel;
   DBuf<int32_t> d_reach_level, d_node_owner, d_terminal_nodes;
   int64_t n_terminal = 0;
+  // persistent wavefront + headwater kernels (river_kernel.cuh)
+  DBuf<int32_t> d_head_all, d_head_bulk, d_wave_order, d_wave_lvl_ptr, d_dep_reach, d_diag_start;
+  DBuf<int64_t> d_dep_ptr;
+  DBuf<int> d_progress, d_wave_ctl;     // d_wave_ctl = {queue head, error flag}
+  std::vector<int32_t> wave_lvl_ptr;    // [n_levels+1]
+  int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
+  int diag_chunks = -1;                 // n_chunks the uploaded diag_start belongs to
+  int* h_wave_err = nullptr;            // pinned copy of the wavefront's error flag
   DBuf<double> d_coef, d_dis[2], d_ext_rows[2], d_node_rows[2], d_reach_in[2], d_reach_out[2], d_gather[2];
   int dis_cur = 0;
   bool have_ext = false;
@@ -291,6 +297,7 @@ void hb_destroy(hb_engine* h) {
   for (int i = 0; i < 2; ++i)
     for (cudaEvent_t e : {h->ev_land_done[i], h->ev_river_done[i], h->ev_copy_done[i], h->ev_join[i]})
       if (e) cudaEventDestroy(e);
+  if (h->h_wave_err) cudaFreeHost(h->h_wave_err);
   if (h->s_river) cudaStreamDestroy(h->s_river);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   cudaStreamDestroy(h->stream);
@@ -581,9 +588,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       HB_REQUIRE(h, value == HB_LAND_AUTO || value == HB_LAND_GENERAL, HB_EINVAL, "hb_set_option: invalid land path");
       h->land_path = (int)value;
       return HB_OK;
-    case HB_OPT_RIVER_BULK_MIN:
-      HB_REQUIRE(h, value >= 0, HB_EINVAL, "hb_set_option: invalid routing threshold");
-      h->river_bulk_min = value ? value : HB_BULK_MIN;
+    case HB_OPT_RIVER_SWEEP:
+      HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES, HB_EINVAL,
+                 "hb_set_option: invalid routing sweep");
+      h->river_sweep = (int)value;
       return HB_OK;
     default:
       return h->fail(HB_EINVAL, "hb_set_option: unknown option %d", option);
@@ -698,6 +706,34 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     else node_owner[n] = node_exits[n][0];
   }
   h->n_terminal = (int64_t)terminal.size();
+  // headwater reaches (level 0, at most HB_BULK_SMAX segments) are handled by two plain launches; the rest forms the
+  // wavefront: sorted by level (and by segments within a level), with the list of reaches each one waits for
+  std::vector<int32_t> head_all, head_bulk, wave_order, wave_lvl(nlev + 1, 0), dep_reach;
+  std::vector<int64_t> dep_ptr(nr + 1, 0);
+  for (int32_t q : reach_order) {
+    const int64_t nseg = r->seg_ptr[q + 1] - r->seg_ptr[q] - 1;
+    if (reach_level[q] == 0 && nseg <= HB_BULK_SMAX) {
+      head_all.push_back(q);
+      if (nseg >= 1) head_bulk.push_back(q);
+    } else {
+      wave_order.push_back(q);
+      wave_lvl[reach_level[q] + 1]++;
+    }
+  }
+  for (int l = 0; l < nlev; ++l) wave_lvl[l + 1] += wave_lvl[l];
+  for (int64_t q = 0; q < nr; ++q) {
+    for (int64_t i = r->inlet_ptr[q]; i < r->inlet_ptr[q + 1]; ++i) {
+      const int32_t n = r->inlet_node[i];
+      for (int64_t k = r->entry_ptr[n]; k < r->entry_ptr[n + 1]; ++k) {
+        const int32_t s = r->entry_src[k];
+        if (s < 0 && s > HB_ENTRY_EXT) dep_reach.push_back(-1 - s);
+      }
+    }
+    dep_ptr[q + 1] = (int64_t)dep_reach.size();
+  }
+  h->n_head_all = (int64_t)head_all.size(); h->n_head_bulk = (int64_t)head_bulk.size(); h->n_wave = (int64_t)wave_order.size();
+  h->wave_lvl_ptr = wave_lvl;
+  h->diag_chunks = -1;
   h->n_node = nn; h->n_reach = nr; h->n_seg = r->n_seg; h->n_ext = r->n_ext; h->n_levels = nlev;
   h->level_node_ptr = lnp; h->level_reach_ptr = lrp;
   int rc;
@@ -709,8 +745,15 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
       (rc = upload(h, h->d_seg_ptr, r->seg_ptr, (size_t)nr + 1)) || (rc = upload(h, h->d_coef, r->coef, (size_t)3 * nr)) ||
       (rc = upload(h, h->d_node_order, node_order)) || (rc = upload(h, h->d_reach_order, reach_order)) ||
       (rc = upload(h, h->d_reach_level, reach_level)) || (rc = upload(h, h->d_node_owner, node_owner)) ||
-      (rc = upload(h, h->d_terminal_nodes, terminal)))
+      (rc = upload(h, h->d_terminal_nodes, terminal)) || (rc = upload(h, h->d_head_all, head_all)) ||
+      (rc = upload(h, h->d_head_bulk, head_bulk)) || (rc = upload(h, h->d_wave_order, wave_order)) ||
+      (rc = upload(h, h->d_wave_lvl_ptr, wave_lvl)) || (rc = upload(h, h->d_dep_ptr, dep_ptr)) ||
+      (rc = upload(h, h->d_dep_reach, dep_reach)))
     return rc;
+  HB_CUDA(h, h->d_progress.reserve((size_t)nr));
+  HB_CUDA(h, h->d_wave_ctl.reserve(2));
+  if (!h->h_wave_err) HB_CUDA(h, cudaHostAlloc((void**)&h->h_wave_err, sizeof(int), cudaHostAllocDefault));
+  *h->h_wave_err = 0;
   HB_CUDA(h, h->d_dis[0].reserve((size_t)r->n_seg));
   HB_CUDA(h, h->d_dis[1].reserve((size_t)r->n_seg));
   HB_CUDA(h, cudaMemsetAsync(h->d_dis[0].p, 0, (size_t)(r->n_seg ? r->n_seg : 1) * sizeof(double), h->stream));
@@ -903,47 +946,85 @@ static int run_river(hb_engine* h) {
   HB_CUDA(h, h->d_node_rows[h->cur].reserve((size_t)h->n_node * nt));
   HB_CUDA(h, h->d_reach_in[h->cur].reserve((size_t)h->n_reach * nt));
   HB_CUDA(h, h->d_reach_out[h->cur].reserve((size_t)h->n_reach * nt));
+  const int n_chunks = (int)((nt + HB_RIVER_CHUNK - 1) / HB_RIVER_CHUNK);
+  const int nlev = (int)h->n_levels;
   RiverDev d{};
   d.n_node = h->n_node; d.n_reach = h->n_reach; d.nt = nt;
   d.entry_ptr = h->d_entry_ptr.p; d.entry_src = h->d_entry_src.p; d.node_mode = h->d_node_mode.p;
   d.node_ext = h->d_node_ext.p; d.inlet_ptr = h->d_inlet_ptr.p; d.inlet_node = h->d_inlet_node.p;
   d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows[h->cur].p; d.ext_rows = h->d_ext_rows[h->cur].p;
   d.node_rows = h->d_node_rows[h->cur].p; d.reach_in = h->d_reach_in[h->cur].p; d.reach_out = h->d_reach_out[h->cur].p;
-  d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur;
+  d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur; d.n_chunks = n_chunks;
   d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p;
+  d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
+  d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
+  d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
   int64_t launches = 0;
-  if (nt > 0) {
-    // anti-diagonal sweep over (level, time chunk): launch `diag` works on the reaches of level l at chunk diag - l
-    const int n_chunks = (int)((nt + HB_RIVER_CHUNK - 1) / HB_RIVER_CHUNK);
-    const int nlev = (int)h->n_levels;
-    if (h->n_reach > 0) {
-      for (int diag = 0; diag < nlev + n_chunks - 1; ++diag) {
-        const int l_lo = diag - n_chunks + 1 > 0 ? diag - n_chunks + 1 : 0;
-        const int l_hi = diag < nlev - 1 ? diag : nlev - 1;
-        const int first = h->level_reach_ptr[l_lo];
-        const int n = h->level_reach_ptr[l_hi + 1] - first;
-        if (n <= 0) continue;
-        const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
-        // wide diagonals are throughput-bound: lane-per-reach recurrence (reach_bulk_kernel) after the inflow pass
-        const int bulk = n >= h->river_bulk_min ? 1 : 0;
-        reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag, n_chunks, bulk);
-        ++launches;
-        if (bulk) {
-          const int bgrid = (n + 32 * HB_BULK_WARPS - 1) / (32 * HB_BULK_WARPS);
-          reach_bulk_kernel<<<bgrid, 32 * HB_BULK_WARPS, HB_BULK_SMEM, h->s_river>>>(d, h->d_reach_order.p + first, n, diag,
-                                                                                  n_chunks);
-          ++launches;
-        }
-      }
-      h->dis_cur = (h->dis_cur + n_chunks) & 1;
-    }
-    if (h->n_terminal > 0) {
-      const int block = 256, grid = (int)((h->n_terminal * 32 + block - 1) / block);
-      node_sum_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
+  if (nt > 0 && h->n_reach > 0 && h->river_sweep == HB_RIVER_LAUNCHES) {
+    // one launch per anti-diagonal of the (level, chunk) grid: launch `diag` works on the reaches of level l at chunk diag - l
+    for (int diag = 0; diag < nlev + n_chunks - 1; ++diag) {
+      const int l_lo = diag - n_chunks + 1 > 0 ? diag - n_chunks + 1 : 0;
+      const int l_hi = diag < nlev - 1 ? diag : nlev - 1;
+      const int first = h->level_reach_ptr[l_lo];
+      const int n = h->level_reach_ptr[l_hi + 1] - first;
+      if (n <= 0) continue;
+      const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
+      reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag);
       ++launches;
     }
-    HB_CUDA(h, cudaGetLastError());
+  } else if (nt > 0 && h->n_reach > 0) {
+    // headwater reaches in two plain launches, everything else in one persistent wavefront launch
+    if (h->n_wave > 0) {
+      if (h->diag_chunks != n_chunks) {
+        std::vector<int32_t> ds(d.n_diag + 1, 0);
+        for (int dg = 0; dg < d.n_diag; ++dg) {
+          const int l_lo = dg - n_chunks + 1 > 0 ? dg - n_chunks + 1 : 0;
+          const int l_hi = dg < nlev - 1 ? dg : nlev - 1;
+          ds[dg + 1] = ds[dg] + (h->wave_lvl_ptr[l_hi + 1] - h->wave_lvl_ptr[l_lo]);
+        }
+        HB_CUDA(h, cudaStreamSynchronize(h->s_river));   // a running wavefront still reads the old table
+        HB_CUDA(h, h->d_diag_start.reserve(ds.size()));
+        HB_CUDA(h, cudaMemcpy(h->d_diag_start.p, ds.data(), ds.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        h->diag_chunks = n_chunks;
+      }
+      d.diag_start = h->d_diag_start.p;
+      wave_init_kernel<<<(unsigned)((h->n_reach + 255) / 256), 256, 0, h->s_river>>>(d);
+      ++launches;
+    }
+    if (h->n_head_all > 0) {
+      const int64_t warps = h->n_head_all * n_chunks;
+      reach_head_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, h->s_river>>>(d, h->d_head_all.p, (int)h->n_head_all);
+      ++launches;
+      if (h->n_head_bulk > 0) {
+        const int per_block = 32 * HB_BULK_WARPS;
+        reach_bulk_kernel<<<(unsigned)((h->n_head_bulk + per_block - 1) / per_block), per_block, HB_BULK_SMEM, h->s_river>>>(
+            d, h->d_head_bulk.p, (int)h->n_head_bulk);
+        ++launches;
+      }
+      if (h->n_wave > 0) {
+        wave_head_done_kernel<<<(unsigned)((h->n_head_all + 255) / 256), 256, 0, h->s_river>>>(d, h->d_head_all.p,
+                                                                                            (int)h->n_head_all);
+        ++launches;
+      }
+    }
+    if (h->n_wave > 0) {
+      const int64_t n_tasks = h->n_wave * n_chunks;
+      HB_REQUIRE(h, n_tasks < (int64_t)1 << 31, HB_EINVAL, "hb_run: too many routing tasks for one window; use shorter windows");
+      int64_t blocks = (n_tasks + 3) / 4;
+      const int64_t cap = (int64_t)h->prop.multiProcessorCount * 8;
+      if (blocks > cap) blocks = cap;
+      reach_wave_kernel<<<(unsigned)blocks, 128, 0, h->s_river>>>(d, (int)n_tasks);
+      HB_CUDA(h, cudaMemcpyAsync(h->h_wave_err, d.error, sizeof(int), cudaMemcpyDeviceToHost, h->s_river));
+      ++launches;
+    }
   }
+  if (nt > 0 && h->n_reach > 0) h->dis_cur = (h->dis_cur + n_chunks) & 1;
+  if (nt > 0 && h->n_terminal > 0) {
+    const int block = 256, grid = (int)((h->n_terminal * 32 + block - 1) / block);
+    node_sum_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
+    ++launches;
+  }
+  HB_CUDA(h, cudaGetLastError());
   h->timing.river_launches += launches;
   return HB_OK;
 }
@@ -1017,6 +1098,12 @@ int hb_wait(hb_engine* h) {
   if ((rc = resolve_marks(h, h->land_marks, true)) || (rc = resolve_marks(h, h->river_marks, false))) return rc;
   h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
   h->pending = false;
+  if (h->h_wave_err && *h->h_wave_err) {
+    *h->h_wave_err = 0;
+    return h->fail(HB_ECUDA, "routing wavefront: a task waited beyond the spin limit for its upstream reaches "
+                             "(results of this window are invalid; HB_OPT_RIVER_SWEEP = HB_RIVER_LAUNCHES avoids the "
+                             "persistent kernel)");
+  }
   return HB_OK;
 }
 

@@ -1,25 +1,36 @@
-// river_kernel.cuh — musk_classic routing over the node/reach DAG as a topological-level wavefront.
+// river_kernel.cuh — musk_classic routing over the node/reach DAG.
 //
 // Replaces `c_musk_classic.pyx` (`Pick_Inflow_V1`, `Update_Discharge_V1`, `Calc_Discharge_V1`, `Calc_Outflow_V1`,
 // `Pass_Outflow_V1`; ref: hydpy/models/musk/musk_model.py:19-187, 809-848; SegmentModel.run
 // hydpy/core/modeltools.py:3449-3461) and the node summation of the reference's whole-period mode
 // (ref: hydpy/core/threadingtools.py:396-446).
 //
-// All series are device rows [row][nt] (time contiguous):  land rows (outlets.q of the land elements), node rows,
-// reach inflow/outflow rows, external rows.
+// All series are device rows [row][nt] (time contiguous): land rows (outlets.q of the land elements), node rows, reach
+// inflow/outflow rows, external rows.  The unit of work is a TASK = (reach, chunk of HB_RIVER_CHUNK = 32 time steps):
+// it needs the same chunk of the reaches that feed its inlet nodes and the previous chunk of its own reach (the
+// Muskingum state), i.e. tasks on anti-diagonal d = level + chunk only depend on diagonals < d.
 //
-//   reach_diag_kernel : one warp per (reach, time chunk).  The window is cut into chunks of HB_RIVER_CHUNK steps and
-//                     the (level, chunk) grid is swept along its anti-diagonals: launch d works on every reach of level l
-//                     at chunk d-l, which only needs chunk d-l of the levels below — finished by launch d-1.  The
-//                     sequential depth drops from levels x nt ticks to (levels + nt/chunk) short launches and every
-//                     launch has nt/chunk levels' worth of reaches in flight.
-//                     Inside a warp lane i owns segment i and the chunk runs as a systolic pipeline over "ticks": at
-//                     tick τ lane i computes time τ-i, receiving new[i](t) from lane i-1 by shuffle.  The recurrence
-//                     new[i+1] = c0*new[i] + c1*old[i] + c2*old[i+1]  is evaluated with the reference's operation order
-//                     and no FMA contraction ⇒ bit-identical to the CPU path.  The warp also forms the sums of its inlet
-//                     nodes (entries added in the listed order, 0.0 + a + b + …) and, as the owner of a node, stores
-//                     the node row.
-//   node_sum_kernel : one warp per node, lanes over time — for the nodes without a downstream reach (outlets).
+//   reach_chunk()      one warp, one task.  Lanes over time form the sums of the inlet nodes (entries added in the
+//                      listed order, 0.0 + a + b + …) and store the rows of the nodes this reach owns; then lane i owns
+//                      segment i and the chunk runs as a systolic pipeline over "ticks": at tick τ lane i computes time
+//                      τ-i, receiving new[i](t) from lane i-1 by shuffle.  The recurrence
+//                      new[i+1] = c0*new[i] + c1*old[i] + c2*old[i+1] is evaluated with the reference's operation order
+//                      and no FMA contraction ⇒ bit-identical to the CPU path.
+//   reach_head_kernel  level-0 reaches (headwaters: nothing upstream but land elements — half of a river tree): all
+//                      their tasks are independent, one launch covers every (reach, chunk); reaches with 1..32 segments
+//                      only get their inflow here and
+//   reach_bulk_kernel  runs their recurrences with LANE = REACH: the 32 reaches of a warp keep their segment states in
+//                      registers, inflow/outflow tiles move through shared memory with coalesced row accesses, ≈0.3 warp
+//                      instructions per reach-segment-step instead of ≈25 per tick of the systolic mapping.
+//   reach_wave_kernel  everything else in ONE persistent launch: warps draw tasks from an ordered queue (diagonal-major,
+//                      a valid topological order), wait on per-reach progress counters for the tasks they depend on and
+//                      publish their own.  Because a task only waits for tasks drawn EARLIER — by warps that are resident
+//                      and running — the scheme cannot deadlock whatever share of the GPU the kernel gets; a bounded spin
+//                      turns any violation of that invariant into an error flag instead of a hang.  Sequential depth:
+//                      (levels + chunks) task latencies instead of as many kernel launches.
+//   reach_diag_kernel  the same sweep as one launch per anti-diagonal (HB_RIVER_LAUNCHES): reference implementation of the
+//                      wavefront for tests and fallback.
+//   node_sum_kernel    one warp per node, lanes over time — for the nodes without a downstream reach (outlets).
 #pragma once
 #include <cstdint>
 
@@ -42,16 +53,28 @@ struct RiverDev {
   double* node_rows;        // [n_node][nt]
   double* reach_in;         // [n_reach][nt]
   double* reach_out;        // [n_reach][nt]
-  double* dis[2];           // chunked sweep: chunk c reads dis[(par0 + c) & 1] and writes the other one
+  double* dis[2];           // chunk c reads dis[(par0 + c) & 1] and writes the other one
   int par0;
+  int n_chunks;
   const int32_t* reach_level;  // [n_reach]
   const int32_t* node_owner;   // [n_node] reach that stores the node row (first exit), -1: terminal node
+  // persistent wavefront
+  const int32_t* wave_order;   // reaches of the wavefront sorted by level
+  const int32_t* wave_lvl_ptr; // [n_levels+1] into wave_order
+  const int32_t* diag_start;   // [n_diag+1] prefix sums of the tasks per anti-diagonal
+  const int64_t* dep_ptr;      // [n_reach+1] → dep_reach: the reaches feeding the inlet nodes of a reach
+  const int32_t* dep_reach;
+  int n_levels, n_diag;
+  int* counter;                // task queue head
+  int* progress;               // [n_reach] chunks completed in this run
+  int* error;                  // set when a wait ran into the spin limit
 };
 
 #define HB_RIVER_CHUNK 32
 #define HB_BULK_SMAX 32      // reaches with more segments always take the systolic path
 #define HB_BULK_WARPS 4      // warps per block of reach_bulk_kernel
-#define HB_BULK_SMEM (HB_BULK_WARPS * (32 * 33 + (HB_BULK_SMAX + 1) * 32) * 8)
+#define HB_BULK_SMEM (HB_BULK_WARPS * 32 * 33 * 8)
+#define HB_SPIN_LIMIT (1 << 24)
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
 __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restrict__ qt, double* __restrict__ rows,
@@ -70,49 +93,33 @@ __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restr
   }
 }
 
-// ref: hydpy/core/threadingtools.py:396-415 `_update_node_series`: series = 0.0; series += entry series (in order)
-__global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const int32_t* __restrict__ nodes, int n) {
-  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const int64_t node = nodes[warp];
-  const int64_t i0 = d.entry_ptr[node], i1 = d.entry_ptr[node + 1];
-  double* row = d.node_rows + node * d.nt;
-  for (int64_t t = lane; t < d.nt; t += 32) {
-    double acc = 0.0;
-    for (int64_t i = i0; i < i1; ++i) {
-      const int32_t s = d.entry_src[i];
-      const double* src = (s >= 0)             ? d.land_rows + (int64_t)s * d.nt
-                          : (s > HB_ENTRY_EXT) ? d.reach_out + (int64_t)(-1 - s) * d.nt
-                                               : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * d.nt;
-      acc += src[t];
-    }
-    row[t] = acc;
-  }
-}
-
-// ref: threadingtools.py:396-415 node series = 0.0 + entries in order
+// ref: threadingtools.py:396-415 node series = 0.0 + entries in order.  Reach outflow rows may have been written by
+// another SM moments ago (persistent wavefront): they are read through L2 (ld.global.cg), never from a stale L1 line.
 __device__ __forceinline__ double node_sum_at(const RiverDev& d, int64_t node, int64_t t) {
   double acc = 0.0;
   const int64_t i0 = d.entry_ptr[node], i1 = d.entry_ptr[node + 1];
   for (int64_t i = i0; i < i1; ++i) {
     const int32_t s = d.entry_src[i];
-    const double* src = (s >= 0)             ? d.land_rows + (int64_t)s * d.nt
-                        : (s > HB_ENTRY_EXT) ? d.reach_out + (int64_t)(-1 - s) * d.nt
-                                             : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * d.nt;
-    acc += src[t];
+    if (s >= 0) acc += d.land_rows[(int64_t)s * d.nt + t];
+    else if (s > HB_ENTRY_EXT) acc += __ldcg(d.reach_out + (int64_t)(-1 - s) * d.nt + t);
+    else acc += d.ext_rows[(int64_t)(HB_ENTRY_EXT - s) * d.nt + t];
   }
   return acc;
 }
 
-// bulk != 0: reaches with 1..HB_BULK_SMAX segments only get their inflow here; reach_bulk_kernel runs their recurrence
-__global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n,
-                                                         int diag, int n_chunks, int bulk) {
+__global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const int32_t* __restrict__ nodes, int n) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (warp >= n) return;
+  const int64_t node = nodes[warp];
+  double* row = d.node_rows + node * d.nt;
+  for (int64_t t = lane; t < d.nt; t += 32) row[t] = node_sum_at(d, node, t);
+}
+
+// One task by one warp.  bulk: reaches with 1..HB_BULK_SMAX segments stop after the inflow (reach_bulk_kernel continues);
+// concurrent: several chunks of this reach run at the same time (head kernel) — only the last one stores the state of
+// a segment-free reach, straight into the final buffer.
+__device__ __forceinline__ void reach_chunk(const RiverDev& d, int64_t r, int c, int lane, bool bulk, bool concurrent) {
   const unsigned full = 0xffffffffu;
-  const int64_t r = reaches[warp];
-  const int c = diag - d.reach_level[r];
-  if (c < 0 || c >= n_chunks) return;
   const int64_t nt = d.nt;
   const int64_t ta = (int64_t)c * HB_RIVER_CHUNK;
   const int64_t tb = (ta + HB_RIVER_CHUNK < nt) ? ta + HB_RIVER_CHUNK : nt;
@@ -147,17 +154,21 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
     if (S == 0) rout[t] = inflow;  // ref: musk_model.py:95-98, 831-835 — zero segments: outflow = discharge[0]
     x_own = inflow;
   }
+  if (bulk && S >= 1 && S <= HB_BULK_SMAX) return;
   const double x_last = __shfl_sync(full, x_own, len - 1);
-  if (lane == 0) dis_new[g0] = x_last;
-  if (S == 0 || (bulk && S <= HB_BULK_SMAX)) return;
+  if (lane == 0) {
+    if (!concurrent) dis_new[g0] = x_last;
+    else if (c == d.n_chunks - 1) d.dis[(d.par0 + d.n_chunks) & 1][g0] = x_last;
+  }
+  if (S == 0) return;
 
   // ---- systolic pipeline over groups of 32 segments --------------------------------------------------------------------
   for (int cbase = 0; cbase < S; cbase += 32) {
     const int nseg = (S - cbase < 32) ? (S - cbase) : 32;
     double prev_in = 0.0, prev_out = 0.0, out = 0.0;
-    if (lane < nseg) {
-      prev_in = dis_old[g0 + cbase + lane];
-      prev_out = dis_old[g0 + cbase + lane + 1];
+    if (lane < nseg) {   // through L2: the previous chunk may have been written by another SM (persistent wavefront)
+      prev_in = __ldcg(dis_old + g0 + cbase + lane);
+      prev_out = __ldcg(dis_old + g0 + cbase + lane + 1);
     }
     double xb = x_own;                               // input of this segment group at time ta+lane
     double yb = 0.0;                                 // its output at time ta+lane (collected below)
@@ -184,80 +195,156 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
   }
 }
 
-// Wide anti-diagonals (thousands of reaches, e.g. all headwater reaches at once) are throughput-bound, and there the
-// systolic warp-per-reach mapping wastes lanes (12 segments on average) and ≈25 instructions per tick.  This kernel
-// maps LANE = REACH instead: a warp takes 32 reaches, stages their 32-step inflow tile in shared memory with coalesced
-// row loads (lanes over time), then every lane runs its own reach sequentially over time and segments — the same
-// operations in the same order ((c0*new[i] + c1*old[i]) + c2*old[i+1], ref: musk_model.py:178-187), ≈0.3 warp
-// instructions per reach-segment-step — and the outflow tile goes back with coalesced stores.  The inflow rows were
-// written by reach_diag_kernel(bulk = 1) in the launch before.
+// ---- one launch per anti-diagonal ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n,
+                                                         int diag) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int64_t r = reaches[warp];
+  const int c = diag - d.reach_level[r];
+  if (c < 0 || c >= d.n_chunks) return;
+  reach_chunk(d, r, c, lane, false, false);
+}
+
+// ---- headwater reaches: every (reach, chunk) at once ------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) reach_head_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n) {
+  const int64_t task = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (task >= (int64_t)n * d.n_chunks) return;
+  const int c = (int)(task / n);
+  reach_chunk(d, reaches[task - (int64_t)c * n], c, lane, true, true);
+}
+
+// lane = reach; `reaches` = the head reaches with 1..HB_BULK_SMAX segments (their inflow rows are complete)
 __global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const RiverDev d, const int32_t* __restrict__ reaches,
-                                                                       int n, int diag, int n_chunks) {
+                                                                       int n) {
   extern __shared__ double smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* X = smem + (size_t)wib * (32 * 33 + (HB_BULK_SMAX + 1) * 32);   // [reach lane][33]: inflow, then outflow
-  double* Q = X + 32 * 33;                                              // [segment point][lane]
+  double* X = smem + (size_t)wib * (32 * 33);        // [reach lane][33]: inflow, then outflow of the chunk
   const unsigned full = 0xffffffffu;
   const int task = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32 + lane;
-  int64_t r = -1, ta = 0, g0 = 0;
-  int len = 0, S = 0;
-  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
   const int64_t nt = d.nt;
+  int64_t r = -1, g0 = 0;
+  int S = 0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  double q[HB_BULK_SMAX + 1];                        // discharge at the segment points: registers (static indexing only)
   if (task < n) {
-    const int64_t rr = reaches[task];
-    const int c = diag - d.reach_level[rr];
-    g0 = d.seg_ptr[rr];
-    S = (int)(d.seg_ptr[rr + 1] - g0 - 1);
-    if (c >= 0 && c < n_chunks && S >= 1 && S <= HB_BULK_SMAX) {
-      r = rr;
-      ta = (int64_t)c * HB_RIVER_CHUNK;
-      const int64_t tb = (ta + HB_RIVER_CHUNK < nt) ? ta + HB_RIVER_CHUNK : nt;
-      len = (int)(tb - ta);
-      c0 = d.coef[0 * d.n_reach + r]; c1 = d.coef[1 * d.n_reach + r]; c2 = d.coef[2 * d.n_reach + r];
+    r = reaches[task];
+    g0 = d.seg_ptr[r];
+    S = (int)(d.seg_ptr[r + 1] - g0 - 1);
+    c0 = d.coef[0 * d.n_reach + r]; c1 = d.coef[1 * d.n_reach + r]; c2 = d.coef[2 * d.n_reach + r];
+  }
+  const double* dis_old = d.dis[d.par0 & 1];
+#pragma unroll
+  for (int i = 0; i <= HB_BULK_SMAX; ++i) q[i] = (r >= 0 && i <= S) ? dis_old[g0 + i] : 0.0;
+  int smax = S;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(full, smax, o); smax = v > smax ? v : smax; }
+  for (int c = 0; c < d.n_chunks; ++c) {
+    const int64_t ta = (int64_t)c * HB_RIVER_CHUNK;
+    const int len = (int)((ta + HB_RIVER_CHUNK < nt ? ta + HB_RIVER_CHUNK : nt) - ta);
+    // inflow tile: row j = reach of lane j, lanes over time (coalesced)
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int64_t rj = __shfl_sync(full, r, j);
+      if (rj >= 0 && lane < len) X[j * 33 + lane] = d.reach_in[rj * nt + ta + lane];
     }
-  }
-  if (__all_sync(full, r < 0)) return;
-  const int c_own = (r >= 0) ? diag - d.reach_level[r] : 0;
-  // ---- inflow tile: row j of the tile = reach of lane j, lanes over time (coalesced) -----------------------------------
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int64_t rj = __shfl_sync(full, r, j);
-    const int64_t taj = __shfl_sync(full, ta, j);
-    const int lenj = __shfl_sync(full, len, j);
-    if (rj >= 0 && lane < lenj) X[j * 33 + lane] = d.reach_in[rj * nt + taj + lane];
-  }
-  // ---- state of the own reach ----------------------------------------------------------------------------------------------
-  if (r >= 0) {
-    const double* dis_old = d.dis[(d.par0 + c_own) & 1];
-    for (int i = 0; i <= S; ++i) Q[i * 32 + lane] = dis_old[g0 + i];
-  }
-  __syncwarp();
-  // ---- lane = reach: sequential over time and segments ------------------------------------------------------------------
-  if (r >= 0) {
-    for (int tt = 0; tt < len; ++tt) {
-      double in = X[lane * 33 + tt];
-      double q_old = Q[lane];
-      Q[lane] = in;
-      for (int i = 0; i < S; ++i) {
-        const double q_next = Q[(i + 1) * 32 + lane];
-        const double nv = c0 * in + c1 * q_old + c2 * q_next;
-        Q[(i + 1) * 32 + lane] = nv;
-        q_old = q_next;
-        in = nv;
+    __syncwarp();
+    if (r >= 0) {
+      for (int tt = 0; tt < len; ++tt) {
+        double in = X[lane * 33 + tt];
+        double q_old = q[0];
+        q[0] = in;
+#pragma unroll
+        for (int i = 0; i < HB_BULK_SMAX; ++i) {
+          if (i >= smax) break;                       // warp-uniform
+          if (i < S) {
+            // ref: musk_model.py:178-187 Calc_Discharge_V1 — (c0*new[i] + c1*old[i]) + c2*old[i+1]
+            const double q_next = q[i + 1];
+            const double nv = c0 * in + c1 * q_old + c2 * q_next;
+            q[i + 1] = nv;
+            q_old = q_next;
+            in = nv;
+          }
+        }
+        X[lane * 33 + tt] = in;
       }
-      X[lane * 33 + tt] = in;
     }
-    double* dis_new = d.dis[(d.par0 + c_own + 1) & 1];
-    for (int i = 0; i <= S; ++i) dis_new[g0 + i] = Q[i * 32 + lane];
+    __syncwarp();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int64_t rj = __shfl_sync(full, r, j);
+      if (rj >= 0 && lane < len) d.reach_out[rj * nt + ta + lane] = X[j * 33 + lane];
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  // ---- outflow tile back to the rows (coalesced) --------------------------------------------------------------------------
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int64_t rj = __shfl_sync(full, r, j);
-    const int64_t taj = __shfl_sync(full, ta, j);
-    const int lenj = __shfl_sync(full, len, j);
-    if (rj >= 0 && lane < lenj) d.reach_out[rj * nt + taj + lane] = X[j * 33 + lane];
+  double* dis_fin = d.dis[(d.par0 + d.n_chunks) & 1];
+#pragma unroll
+  for (int i = 0; i <= HB_BULK_SMAX; ++i)
+    if (r >= 0 && i <= S) dis_fin[g0 + i] = q[i];
+}
+
+// ---- persistent wavefront ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// queue head and error flag = 0; progress = 0 everywhere, then = n_chunks for the reaches the head kernels complete
+__global__ void wave_init_kernel(const RiverDev d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { *d.counter = 0; *d.error = 0; }
+  if (i < d.n_reach) d.progress[i] = 0;
+}
+__global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restrict__ head, int n_head) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_head) d.progress[head[i]] = d.n_chunks;
+}
+
+__global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n_tasks) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = atomicAdd(d.counter, 1);
+    task = __shfl_sync(full, task, 0);
+    if (task >= n_tasks) return;
+    // anti-diagonal of the task: largest dg with diag_start[dg] <= task
+    int lo = 0, hi = d.n_diag;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (d.diag_start[mid] <= task) lo = mid; else hi = mid;
+    }
+    const int dg = lo;
+    const int l_lo = dg - d.n_chunks + 1 > 0 ? dg - d.n_chunks + 1 : 0;
+    const int64_t r = d.wave_order[d.wave_lvl_ptr[l_lo] + (task - d.diag_start[dg])];
+    const int c = dg - d.reach_level[r];
+    // ---- wait: same chunk of every feeding reach, previous chunk of this reach (lanes over dependencies) -------------
+    bool ok = true;
+    {
+      const int64_t p0 = d.dep_ptr[r], p1 = d.dep_ptr[r + 1];
+      for (int64_t p = p0 + lane - 1; p < p1; p += 32) {     // p0-1 stands for the reach itself
+        const int* flag = d.progress + (p < p0 ? r : (int64_t)d.dep_reach[p]);
+        const int need = p < p0 ? c : c + 1;
+        int spins = 0;
+        while (ld_acquire(flag) < need) {
+          __nanosleep(100);
+          if (++spins > HB_SPIN_LIMIT || ld_acquire(d.error) != 0) { ok = false; break; }
+        }
+      }
+    }
+    if (!__all_sync(full, ok)) {
+      if (lane == 0) atomicExch(d.error, 1);
+      return;
+    }
+    reach_chunk(d, r, c, lane, false, false);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(d.progress + r, c + 1);
   }
 }
 

@@ -245,9 +245,10 @@ class Engine:
         value = {"auto": layout.LAND_AUTO, "general": layout.LAND_GENERAL}[path]
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_PATH, value), "hb_set_option")
 
-    def set_river_bulk_min(self, n: int = 0) -> None:
-        """Reaches per routing launch from which the lane-per-reach kernel is used (0 = default, 1 = always)."""
-        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_BULK_MIN, int(n)), "hb_set_option")
+    def set_river_sweep(self, mode: str = "persistent") -> None:
+        """'persistent': one persistent wavefront launch (default); 'launches': one launch per anti-diagonal."""
+        value = {"persistent": layout.RIVER_PERSISTENT, "launches": layout.RIVER_LAUNCHES}[mode]
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_SWEEP, value), "hb_set_option")
 
     # -- window -----------------------------------------------------------------------------------------------------
     def set_forcing(self, forcing: np.ndarray, doy: np.ndarray) -> None:

@@ -211,9 +211,13 @@ int hb_select_series(hb_engine* h, int series, int on);
 #define HB_OPT_LAND_PATH 0
 #define HB_LAND_AUTO 0
 #define HB_LAND_GENERAL 1
-/* HB_OPT_RIVER_BULK_MIN: number of reaches in one routing launch from which the lane-per-reach kernel replaces the
- * systolic warp-per-reach kernel (both bit-identical; 0 restores the default, 1 forces the lane-per-reach kernel). */
-#define HB_OPT_RIVER_BULK_MIN 1
+/* HB_OPT_RIVER_SWEEP: how the (topological level x 32-step chunk) wavefront of the routing runs.  HB_RIVER_PERSISTENT
+ * (default): headwater reaches in two plain launches, all other reaches in ONE persistent launch whose warps draw tasks
+ * from an ordered queue and wait on per-reach progress counters.  HB_RIVER_LAUNCHES: one launch per anti-diagonal.
+ * Both are bit-identical to the reference. */
+#define HB_OPT_RIVER_SWEEP 1
+#define HB_RIVER_PERSISTENT 0
+#define HB_RIVER_LAUNCHES 1
 int hb_set_option(hb_engine* h, int option, int64_t value);
 
 /* ---- one simulation window ------------------------------------------------------------------------------------ */

@@ -25,10 +25,10 @@ EXACT_SERIES = ("tc", "fracrain", "cfact", "gact", "pc")
 @pytest.fixture(scope="module", params=["auto", "general"])
 def engine(request):
     """Both land paths ('auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only) and
-    both routing kernels ('auto' keeps the systolic kernel at these sizes, 'general' forces the lane-per-reach one)."""
+    both routing sweeps ('auto': headwater kernels + persistent wavefront, 'general': one launch per anti-diagonal)."""
     with Engine(0) as eng:
         eng.set_land_path(request.param)
-        eng.set_river_bulk_min(1 if request.param == "general" else 0)
+        eng.set_river_sweep("launches" if request.param == "general" else "persistent")
         yield eng
 
 
