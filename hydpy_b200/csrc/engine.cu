@@ -21,6 +21,9 @@
 
 using namespace hb;
 
+#ifndef HB_WAVE_BLOCKS_PER_SM
+#define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
+#endif
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
@@ -158,6 +161,8 @@ struct hb_engine {
   // persistent wavefront + headwater kernels (river_kernel.cuh)
   DBuf<int32_t> d_head_all, d_head_bulk, d_wave_order, d_wave_lvl_ptr, d_dep_reach, d_diag_start;
   DBuf<int64_t> d_dep_ptr;
+  DBuf<ReachMeta> d_reach_meta;
+  DBuf<int32_t> d_wave_rec;
   DBuf<int> d_progress, d_wave_ctl;     // d_wave_ctl = {queue head, error flag}
   std::vector<int32_t> wave_lvl_ptr;    // [n_levels+1]
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
@@ -731,6 +736,46 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     }
     dep_ptr[q + 1] = (int64_t)dep_reach.size();
   }
+  HB_REQUIRE(h, r->n_seg < ((int64_t)1 << 31) && (int64_t)dep_reach.size() < ((int64_t)1 << 31) &&
+                    r->n_entry < ((int64_t)1 << 31),
+             HB_EINVAL, "hb_set_river: network too large for 32-bit offsets");
+  std::vector<ReachMeta> meta((size_t)nr);
+  for (int64_t q = 0; q < nr; ++q) {
+    ReachMeta& m = meta[q];
+    m.c0 = r->coef[0 * nr + q]; m.c1 = r->coef[1 * nr + q]; m.c2 = r->coef[2 * nr + q];
+    m.g0 = (int32_t)r->seg_ptr[q];
+    m.nseg = (int32_t)(r->seg_ptr[q + 1] - r->seg_ptr[q] - 1);
+    m.level = reach_level[q];
+    m.dep0 = (int32_t)dep_ptr[q];
+    m.n_dep = (int32_t)(dep_ptr[q + 1] - dep_ptr[q]);
+    m.simple_node = -1; m.entry0 = 0; m.n_entry = 0; m.owns_node = 0; m.pad = 0;
+    if (r->inlet_ptr[q + 1] - r->inlet_ptr[q] == 1) {
+      const int32_t n = r->inlet_node[r->inlet_ptr[q]];
+      const int64_t ne_ = r->entry_ptr[n + 1] - r->entry_ptr[n];
+      if (r->node_mode[n] == HB_NODE_NEWSIM && ne_ <= 32) {
+        m.simple_node = n;
+        m.entry0 = (int32_t)r->entry_ptr[n];
+        m.n_entry = (int32_t)ne_;
+        m.owns_node = node_owner[n] == (int32_t)q ? 1 : 0;
+      }
+    }
+  }
+  // 128-byte wavefront records in wave order (layout: HB_WR_* in river_kernel.cuh)
+  std::vector<int32_t> wave_rec(wave_order.size() * HB_WR_WORDS, 0);
+  for (size_t pos = 0; pos < wave_order.size(); ++pos) {
+    const int32_t q = wave_order[pos];
+    const ReachMeta& m = meta[q];
+    int32_t* w = wave_rec.data() + pos * HB_WR_WORDS;
+    memcpy(w + HB_WR_C0, &m.c0, 8); memcpy(w + HB_WR_C1, &m.c1, 8); memcpy(w + HB_WR_C2, &m.c2, 8);
+    w[HB_WR_REACH] = q; w[HB_WR_G0] = m.g0; w[HB_WR_NSEG] = m.nseg; w[HB_WR_LEVEL] = m.level;
+    w[HB_WR_NDEP] = m.n_dep; w[HB_WR_NENTRY] = m.n_entry; w[HB_WR_NODE] = m.simple_node; w[HB_WR_OWNS] = m.owns_node;
+    const bool inl = m.simple_node >= 0 && m.n_entry <= HB_WR_MAXLIST && m.n_dep <= HB_WR_MAXLIST;
+    w[HB_WR_INLINE] = inl ? 1 : 0;
+    if (inl) {
+      for (int i = 0; i < m.n_entry; ++i) w[HB_WR_ENTRY + i] = r->entry_src[m.entry0 + i];
+      for (int i = 0; i < m.n_dep; ++i) w[HB_WR_DEP + i] = dep_reach[m.dep0 + i];
+    }
+  }
   h->n_head_all = (int64_t)head_all.size(); h->n_head_bulk = (int64_t)head_bulk.size(); h->n_wave = (int64_t)wave_order.size();
   h->wave_lvl_ptr = wave_lvl;
   h->diag_chunks = -1;
@@ -748,7 +793,8 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
       (rc = upload(h, h->d_terminal_nodes, terminal)) || (rc = upload(h, h->d_head_all, head_all)) ||
       (rc = upload(h, h->d_head_bulk, head_bulk)) || (rc = upload(h, h->d_wave_order, wave_order)) ||
       (rc = upload(h, h->d_wave_lvl_ptr, wave_lvl)) || (rc = upload(h, h->d_dep_ptr, dep_ptr)) ||
-      (rc = upload(h, h->d_dep_reach, dep_reach)))
+      (rc = upload(h, h->d_dep_reach, dep_reach)) || (rc = upload(h, h->d_reach_meta, meta)) ||
+      (rc = upload(h, h->d_wave_rec, wave_rec)))
     return rc;
   HB_CUDA(h, h->d_progress.reserve((size_t)nr));
   HB_CUDA(h, h->d_wave_ctl.reserve(2));
@@ -890,7 +936,7 @@ static int run_land(hb_engine* h) {
       v.nt = (nt - c0 < chunk) ? (nt - c0) : chunk;
       v.t_first = h->t0 + c0;
       v.t_out = c0;
-      h->mark(-1);
+      h->mark(HB_K_OTHER);
       zone_kernel<true><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
       if (h->any_nonsoil_warp) {
         zone_kernel<false><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
@@ -927,7 +973,7 @@ static int run_land(hb_engine* h) {
     }
     const int block = 128;
     const int grid = (int)((n_general + block - 1) / block);
-    h->mark(-1);
+    h->mark(HB_K_OTHER);
     if (any_series) land_kernel<true><<<grid, block, 0, h->stream>>>(d);
     else land_kernel<false><<<grid, block, 0, h->stream>>>(d);
     h->mark(HB_K_GENERAL);
@@ -955,8 +1001,8 @@ static int run_river(hb_engine* h) {
   d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows[h->cur].p; d.ext_rows = h->d_ext_rows[h->cur].p;
   d.node_rows = h->d_node_rows[h->cur].p; d.reach_in = h->d_reach_in[h->cur].p; d.reach_out = h->d_reach_out[h->cur].p;
   d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur; d.n_chunks = n_chunks;
-  d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p;
-  d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
+  d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p; d.meta = h->d_reach_meta.p;
+  d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
   d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
   int64_t launches = 0;
@@ -1011,9 +1057,11 @@ static int run_river(hb_engine* h) {
       const int64_t n_tasks = h->n_wave * n_chunks;
       HB_REQUIRE(h, n_tasks < (int64_t)1 << 31, HB_EINVAL, "hb_run: too many routing tasks for one window; use shorter windows");
       int64_t blocks = (n_tasks + 3) / 4;
-      const int64_t cap = (int64_t)h->prop.multiProcessorCount * 8;
+      const int64_t cap = (int64_t)h->prop.multiProcessorCount * HB_WAVE_BLOCKS_PER_SM;
       if (blocks > cap) blocks = cap;
-      reach_wave_kernel<<<(unsigned)blocks, 128, 0, h->s_river>>>(d, (int)n_tasks);
+      const size_t tab = (size_t)(d.n_diag + 1 + nlev + 1) * sizeof(int32_t);
+      const int use_smem = tab <= 40 * 1024 ? 1 : 0;
+      reach_wave_kernel<<<(unsigned)blocks, 128, use_smem ? tab : 0, h->s_river>>>(d, (int)n_tasks, use_smem);
       HB_CUDA(h, cudaMemcpyAsync(h->h_wave_err, d.error, sizeof(int), cudaMemcpyDeviceToHost, h->s_river));
       ++launches;
     }

@@ -38,8 +38,23 @@
 
 namespace hb {
 
+// Everything a task needs to know about its reach in one 64-byte record (one cache line, one load latency)
+struct ReachMeta {
+  double c0, c1, c2;     // musk_control.Coefficients
+  int32_t g0;            // first point of the reach in the discharge state
+  int32_t nseg;          // NmbSegments
+  int32_t level;
+  int32_t dep0, n_dep;   // → dep_reach: the reaches feeding the inlet nodes
+  int32_t simple_node;   // >= 0: the reach has ONE inlet node, in deploy mode newsim, with <= 32 entries (fast inflow)
+  int32_t entry0, n_entry;
+  int32_t owns_node;     // 1: this reach stores the row of simple_node
+  int32_t pad;
+};
+static_assert(sizeof(ReachMeta) == 64, "ReachMeta must stay one 64-byte record");
+
 struct RiverDev {
   int64_t n_node, n_reach, nt;
+  const ReachMeta* meta;    // [n_reach]
   const int64_t* entry_ptr;
   const int32_t* entry_src;
   const int32_t* node_mode;
@@ -59,6 +74,7 @@ struct RiverDev {
   const int32_t* reach_level;  // [n_reach]
   const int32_t* node_owner;   // [n_node] reach that stores the node row (first exit), -1: terminal node
   // persistent wavefront
+  const int32_t* wave_rec;     // [n_wave][32] one 128-byte record per wavefront reach, in wave order (see HB_WR_*)
   const int32_t* wave_order;   // reaches of the wavefront sorted by level
   const int32_t* wave_lvl_ptr; // [n_levels+1] into wave_order
   const int32_t* diag_start;   // [n_diag+1] prefix sums of the tasks per anti-diagonal
@@ -75,6 +91,12 @@ struct RiverDev {
 #define HB_BULK_WARPS 4      // warps per block of reach_bulk_kernel
 #define HB_BULK_SMEM (HB_BULK_WARPS * 32 * 33 * 8)
 #define HB_SPIN_LIMIT (1 << 24)
+#ifndef HB_SPIN_FAST
+#define HB_SPIN_FAST 4
+#endif
+#ifndef HB_SPIN_SLEEP
+#define HB_SPIN_SLEEP 256
+#endif
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
 __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restrict__ qt, double* __restrict__ rows,
@@ -115,27 +137,121 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const i
   for (int64_t t = lane; t < d.nt; t += 32) row[t] = node_sum_at(d, node, t);
 }
 
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // One task by one warp.  bulk: reaches with 1..HB_BULK_SMAX segments stop after the inflow (reach_bulk_kernel continues);
 // concurrent: several chunks of this reach run at the same time (head kernel) — only the last one stores the state of
-// a segment-free reach, straight into the final buffer.
-__device__ __forceinline__ void reach_chunk(const RiverDev& d, int64_t r, int c, int lane, bool bulk, bool concurrent) {
+// a segment-free reach, straight into the final buffer.  WAVE: wait for the tasks this one depends on (persistent
+// wavefront) — AFTER all metadata is in registers, so that only the row loads and the ticks sit on the critical path.
+// Returns false when the wait ran into the spin limit.
+// words of a wavefront record (int32 each; doubles occupy two words)
+enum { HB_WR_C0 = 0, HB_WR_C1 = 2, HB_WR_C2 = 4, HB_WR_REACH = 6, HB_WR_G0, HB_WR_NSEG, HB_WR_LEVEL, HB_WR_NDEP,
+       HB_WR_NENTRY, HB_WR_NODE, HB_WR_OWNS, HB_WR_INLINE, HB_WR_PAD, HB_WR_ENTRY = 16, HB_WR_DEP = 24, HB_WR_WORDS = 32 };
+#define HB_WR_MAXLIST 8
+#define HB_NO_ENTRY 0x7fffffff
+
+// what a task knows about its reach before it touches any series
+struct TaskPrep {
+  ReachMeta m;
+  int64_t r;
+  int32_t esrc;    // entry_src of lane e of the simple inlet node (HB_NO_ENTRY otherwise)
+  int32_t dep;     // reach lane e waits for (wavefront, inline list), -1: none
+  bool inline_deps;
+};
+
+__device__ __forceinline__ TaskPrep prep_from_meta(const RiverDev& d, int64_t r, int lane) {
+  TaskPrep p;
+  p.m = d.meta[r];
+  p.r = r;
+  p.esrc = (p.m.simple_node >= 0 && lane < p.m.n_entry) ? d.entry_src[p.m.entry0 + lane] : HB_NO_ENTRY;
+  p.dep = -1;
+  p.inline_deps = false;
+  return p;
+}
+
+template <bool WAVE>
+__device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& tp, int c, int lane, bool bulk,
+                                            bool concurrent) {
   const unsigned full = 0xffffffffu;
   const int64_t nt = d.nt;
+  const ReachMeta& m = tp.m;
+  const int64_t r = tp.r;
   const int64_t ta = (int64_t)c * HB_RIVER_CHUNK;
   const int64_t tb = (ta + HB_RIVER_CHUNK < nt) ? ta + HB_RIVER_CHUNK : nt;
   const int len = (int)(tb - ta);
   const double* dis_old = d.dis[(d.par0 + c) & 1];
   double* dis_new = d.dis[(d.par0 + c + 1) & 1];
-  const int64_t g0 = d.seg_ptr[r];
-  const int S = (int)(d.seg_ptr[r + 1] - g0 - 1);
-  const double c0 = d.coef[0 * d.n_reach + r], c1 = d.coef[1 * d.n_reach + r], c2 = d.coef[2 * d.n_reach + r];
-  const int64_t j0 = d.inlet_ptr[r], j1 = d.inlet_ptr[r + 1];
+  const int64_t g0 = m.g0;
+  const int S = m.nseg;
+  const double c0 = m.c0, c1 = m.c1, c2 = m.c2;
   double* rin = d.reach_in + r * nt;
   double* rout = d.reach_out + r * nt;
+  // fast inflow: lane e holds the row of entry e of the single inlet node
+  const double* erow = nullptr;
+  bool ereach = false;
+  if (tp.esrc != HB_NO_ENTRY) {
+    const int32_t s = tp.esrc;
+    ereach = s < 0 && s > HB_ENTRY_EXT;
+    erow = (s >= 0 ? d.land_rows + (int64_t)s * nt
+                   : ereach ? d.reach_out + (int64_t)(-1 - s) * nt : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * nt) + ta;
+  }
+  // state of the first segment group; in the wavefront it is loaded as soon as the previous chunk of THIS reach is
+  // done — that happened a whole diagonal ago — so that the load overlaps the wait for the upstream reaches
+  double st_in = 0.0, st_out = 0.0;
+  if (WAVE) {
+    bool ok = true;
+    int spins = 0;
+    if (lane == 0)
+      while (ld_acquire(d.progress + r) < c) {
+        if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+        if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
+      }
+    if (!__all_sync(full, ok)) return false;
+    if (lane < S) {   // through L2: the previous chunk may have been written by another SM
+      st_in = __ldcg(dis_old + g0 + lane);
+      st_out = __ldcg(dis_old + g0 + lane + 1);
+    }
+    // same chunk of every feeding reach (lanes over dependencies)
+    for (int p = lane; p < m.n_dep; p += 32) {
+      const int* flag = d.progress + (tp.inline_deps ? tp.dep : d.dep_reach[m.dep0 + p]);
+      spins = 0;
+      while (ld_acquire(flag) < c + 1) {
+        if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+        if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
+      }
+    }
+    if (!__all_sync(full, ok)) return false;
+  } else if (lane < S) {
+    st_in = dis_old[g0 + lane];
+    st_out = dis_old[g0 + lane + 1];
+  }
 
   // ---- inflow of the chunk (lane = time step): node sums, node rows of owned nodes, Pick_Inflow_V1 ----------------------
   double x_own = 0.0;   // inflow at time ta+lane, kept in the register for the pipeline below
-  if (lane < len) {
+  if (m.simple_node >= 0) {
+    double sim = 0.0;   // ref: threadingtools.py:396-415 node series = 0.0 + entries in order
+    for (int e = 0; e < m.n_entry; ++e) {
+      const double* row = (const double*)__shfl_sync(full, (unsigned long long)erow, e);
+      const bool isr = __shfl_sync(full, (int)ereach, e) != 0;
+      if (lane < len) sim += isr ? __ldcg(row + lane) : row[lane];
+    }
+    if (lane < len) {
+      const int64_t t = ta + lane;
+      if (m.owns_node) d.node_rows[(int64_t)m.simple_node * nt + t] = sim;
+      const double inflow = 0.0 + (0.0 + sim);   // ref: musk_model.py:26-31 Pick_Inflow_V1
+      rin[t] = inflow;
+      if (S == 0) rout[t] = inflow;
+      x_own = inflow;
+    }
+  } else if (lane < len) {
+    const int64_t j0 = d.inlet_ptr[r], j1 = d.inlet_ptr[r + 1];
     const int64_t t = ta + lane;
     double inflow = 0.0;
     for (int64_t j = j0; j < j1; ++j) {
@@ -154,21 +270,24 @@ __device__ __forceinline__ void reach_chunk(const RiverDev& d, int64_t r, int c,
     if (S == 0) rout[t] = inflow;  // ref: musk_model.py:95-98, 831-835 — zero segments: outflow = discharge[0]
     x_own = inflow;
   }
-  if (bulk && S >= 1 && S <= HB_BULK_SMAX) return;
+  if (bulk && S >= 1 && S <= HB_BULK_SMAX) return true;
   const double x_last = __shfl_sync(full, x_own, len - 1);
   if (lane == 0) {
     if (!concurrent) dis_new[g0] = x_last;
     else if (c == d.n_chunks - 1) d.dis[(d.par0 + d.n_chunks) & 1][g0] = x_last;
   }
-  if (S == 0) return;
+  if (S == 0) return true;
 
   // ---- systolic pipeline over groups of 32 segments --------------------------------------------------------------------
   for (int cbase = 0; cbase < S; cbase += 32) {
     const int nseg = (S - cbase < 32) ? (S - cbase) : 32;
-    double prev_in = 0.0, prev_out = 0.0, out = 0.0;
-    if (lane < nseg) {   // through L2: the previous chunk may have been written by another SM (persistent wavefront)
-      prev_in = __ldcg(dis_old + g0 + cbase + lane);
-      prev_out = __ldcg(dis_old + g0 + cbase + lane + 1);
+    double prev_in = st_in, prev_out = st_out, out = 0.0;
+    if (cbase > 0) {
+      prev_in = prev_out = 0.0;
+      if (lane < nseg) {
+        prev_in = __ldcg(dis_old + g0 + cbase + lane);
+        prev_out = __ldcg(dis_old + g0 + cbase + lane + 1);
+      }
     }
     double xb = x_own;                               // input of this segment group at time ta+lane
     double yb = 0.0;                                 // its output at time ta+lane (collected below)
@@ -193,6 +312,7 @@ __device__ __forceinline__ void reach_chunk(const RiverDev& d, int64_t r, int c,
     x_own = yb;                                      // the next segment group continues on this output
     if (cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
   }
+  return true;
 }
 
 // ---- one launch per anti-diagonal ----------------------------------------------------------------------------------------
@@ -203,7 +323,7 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
   const int64_t r = reaches[warp];
   const int c = diag - d.reach_level[r];
   if (c < 0 || c >= d.n_chunks) return;
-  reach_chunk(d, r, c, lane, false, false);
+  reach_chunk<false>(d, prep_from_meta(d, r, lane), c, lane, false, false);
 }
 
 // ---- headwater reaches: every (reach, chunk) at once ------------------------------------------------------------------------
@@ -212,7 +332,7 @@ __global__ void __launch_bounds__(128) reach_head_kernel(const RiverDev d, const
   const int lane = threadIdx.x & 31;
   if (task >= (int64_t)n * d.n_chunks) return;
   const int c = (int)(task / n);
-  reach_chunk(d, reaches[task - (int64_t)c * n], c, lane, true, true);
+  reach_chunk<false>(d, prep_from_meta(d, reaches[task - (int64_t)c * n], lane), c, lane, true, true);
 }
 
 // lane = reach; `reaches` = the head reaches with 1..HB_BULK_SMAX segments (their inflow rows are complete)
@@ -230,9 +350,8 @@ __global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const Ri
   double q[HB_BULK_SMAX + 1];                        // discharge at the segment points: registers (static indexing only)
   if (task < n) {
     r = reaches[task];
-    g0 = d.seg_ptr[r];
-    S = (int)(d.seg_ptr[r + 1] - g0 - 1);
-    c0 = d.coef[0 * d.n_reach + r]; c1 = d.coef[1 * d.n_reach + r]; c2 = d.coef[2 * d.n_reach + r];
+    const ReachMeta m = d.meta[r];
+    g0 = m.g0; S = m.nseg; c0 = m.c0; c1 = m.c1; c2 = m.c2;
   }
   const double* dis_old = d.dis[d.par0 & 1];
 #pragma unroll
@@ -285,15 +404,6 @@ __global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const Ri
 }
 
 // ---- persistent wavefront ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // queue head and error flag = 0; progress = 0 everywhere, then = n_chunks for the reaches the head kernels complete
 __global__ void wave_init_kernel(const RiverDev d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,46 +415,94 @@ __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restric
   if (i < n_head) d.progress[head[i]] = d.n_chunks;
 }
 
-__global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n_tasks) {
+// dynamic shared memory: copies of diag_start [n_diag+1] and wave_lvl_ptr [n_levels+1] when they fit (use_smem).
+// Per-task latency is a chain of L2 round trips (≈0.7 µs each on B200): queue draw → record → progress flags → rows.
+// The first two are taken off the critical path by working two tasks ahead: the draw for task i+2 and the record load
+// for task i+1 are in flight while task i runs.  A warp therefore owns up to three tasks, always processed in
+// increasing order, which keeps the no-deadlock argument intact (the smallest unfinished task is always some warp's
+// current task or becomes it as soon as that warp's smaller tasks — already finished — are retired).
+__global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
+  extern __shared__ int32_t wave_tab[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  for (;;) {
-    int task = 0;
-    if (lane == 0) task = atomicAdd(d.counter, 1);
-    task = __shfl_sync(full, task, 0);
-    if (task >= n_tasks) return;
-    // anti-diagonal of the task: largest dg with diag_start[dg] <= task
+  const int32_t* diag_start = d.diag_start;
+  const int32_t* lvl_ptr = d.wave_lvl_ptr;
+  if (use_smem) {
+    for (int i = threadIdx.x; i <= d.n_diag; i += blockDim.x) wave_tab[i] = d.diag_start[i];
+    for (int i = threadIdx.x; i <= d.n_levels; i += blockDim.x) wave_tab[d.n_diag + 1 + i] = d.wave_lvl_ptr[i];
+    __syncthreads();
+    diag_start = wave_tab;
+    lvl_ptr = wave_tab + d.n_diag + 1;
+  }
+  // task index → (anti-diagonal, position in wave order)
+  auto locate = [&](int task, int& dg, int& pos) {
     int lo = 0, hi = d.n_diag;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (d.diag_start[mid] <= task) lo = mid; else hi = mid;
+      if (diag_start[mid] <= task) lo = mid; else hi = mid;
     }
-    const int dg = lo;
+    dg = lo;
     const int l_lo = dg - d.n_chunks + 1 > 0 ? dg - d.n_chunks + 1 : 0;
-    const int64_t r = d.wave_order[d.wave_lvl_ptr[l_lo] + (task - d.diag_start[dg])];
-    const int c = dg - d.reach_level[r];
-    // ---- wait: same chunk of every feeding reach, previous chunk of this reach (lanes over dependencies) -------------
-    bool ok = true;
-    {
-      const int64_t p0 = d.dep_ptr[r], p1 = d.dep_ptr[r + 1];
-      for (int64_t p = p0 + lane - 1; p < p1; p += 32) {     // p0-1 stands for the reach itself
-        const int* flag = d.progress + (p < p0 ? r : (int64_t)d.dep_reach[p]);
-        const int need = p < p0 ? c : c + 1;
-        int spins = 0;
-        while (ld_acquire(flag) < need) {
-          __nanosleep(100);
-          if (++spins > HB_SPIN_LIMIT || ld_acquire(d.error) != 0) { ok = false; break; }
-        }
-      }
+    pos = lvl_ptr[l_lo] + (task - diag_start[dg]);
+  };
+  auto load_record = [&](int task, int& dg) -> int {   // one coalesced 128-byte load: lane i holds word i
+    if (task >= n_tasks) { dg = 0; return 0; }
+    int pos;
+    locate(task, dg, pos);
+    return d.wave_rec[(int64_t)pos * HB_WR_WORDS + lane];
+  };
+  auto draw = [&]() -> int {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(d.counter, 1);
+    return t;                                           // valid in lane 0; broadcast when it is needed
+  };
+  int t_cur = __shfl_sync(full, draw(), 0);
+  int t_nxt = __shfl_sync(full, draw(), 0);
+  int dg_cur, dg_nxt;
+  int w_cur = load_record(t_cur, dg_cur);
+  int w_nxt = load_record(t_nxt, dg_nxt);
+  while (t_cur < n_tasks) {
+    const int a_nn = draw();                            // in flight while the current task runs
+    // ---- unpack the record of the current task -----------------------------------------------------------------------
+    TaskPrep tp;
+#define HB_W(i) __shfl_sync(full, w_cur, (i))
+    tp.m.c0 = __hiloint2double(HB_W(HB_WR_C0 + 1), HB_W(HB_WR_C0));
+    tp.m.c1 = __hiloint2double(HB_W(HB_WR_C1 + 1), HB_W(HB_WR_C1));
+    tp.m.c2 = __hiloint2double(HB_W(HB_WR_C2 + 1), HB_W(HB_WR_C2));
+    tp.r = HB_W(HB_WR_REACH);
+    tp.m.g0 = HB_W(HB_WR_G0);
+    tp.m.nseg = HB_W(HB_WR_NSEG);
+    tp.m.level = HB_W(HB_WR_LEVEL);
+    const int inline_ok = HB_W(HB_WR_INLINE);
+    const int e_word = __shfl_sync(full, w_cur, HB_WR_ENTRY + (lane & (HB_WR_MAXLIST - 1)));
+    const int d_word = __shfl_sync(full, w_cur, HB_WR_DEP + (lane & (HB_WR_MAXLIST - 1)));
+    if (inline_ok) {
+      tp.m.n_dep = HB_W(HB_WR_NDEP);
+      tp.m.n_entry = HB_W(HB_WR_NENTRY);
+      tp.m.simple_node = HB_W(HB_WR_NODE);
+      tp.m.owns_node = HB_W(HB_WR_OWNS);
+      tp.m.dep0 = 0; tp.m.entry0 = 0; tp.m.pad = 0;
+      tp.esrc = lane < tp.m.n_entry ? e_word : HB_NO_ENTRY;
+      tp.dep = lane < tp.m.n_dep ? d_word : -1;
+      tp.inline_deps = true;
+    } else {
+      tp = prep_from_meta(d, tp.r, lane);               // long lists / several inlet nodes / deploy modes: global arrays
     }
-    if (!__all_sync(full, ok)) {
+#undef HB_W
+    const int c = dg_cur - tp.m.level;
+    if (!reach_chunk<true>(d, tp, c, lane, false, false)) {
       if (lane == 0) atomicExch(d.error, 1);
       return;
     }
-    reach_chunk(d, r, c, lane, false, false);
-    __threadfence();
+    // bar.warp.sync orders the lanes' stores before lane 0's release, which is cumulative at gpu scope
     __syncwarp();
-    if (lane == 0) st_release(d.progress + r, c + 1);
+    if (lane == 0) st_release(d.progress + tp.r, c + 1);
+    // ---- rotate the pipeline ------------------------------------------------------------------------------------------------
+    const int t_nn = __shfl_sync(full, a_nn, 0);
+    int dg_nn;
+    const int w_nn = load_record(t_nn, dg_nn);
+    t_cur = t_nxt; w_cur = w_nxt; dg_cur = dg_nxt;
+    t_nxt = t_nn; w_nxt = w_nn; dg_nxt = dg_nn;
   }
 }
 
