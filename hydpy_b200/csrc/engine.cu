@@ -133,6 +133,9 @@ struct hb_engine {
   std::vector<int32_t> slow_list;     // the others
   DBuf<int32_t> d_slow_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
+  DBuf<double> d_series_stage[HB_S_FIRST_ELEM];   // chunk-local staging of the zone/snow series (fast path)
+  DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
+  DBuf<int64_t> d_zone_cell0, d_snow_cell0;       // [E_pad+1] first ABI cell of every element
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
   int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
@@ -486,6 +489,24 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   }
   h->n_fast = n_fast;
   h->slow_list = slow_list;
+  {
+    HB_REQUIRE(h, (int64_t)zmax * ep < ((int64_t)1 << 31), HB_EINVAL, "hb_set_land: too many zone slots for 32-bit indices");
+    std::vector<int32_t> zone_slot((size_t)d->n_zone, -1), snow_slot((size_t)d->n_snow, -1);
+    std::vector<int64_t> zone_cell0(ep + 1, d->n_zone), snow_cell0(ep + 1, d->n_snow);
+    for (int64_t e = 0; e < ne; ++e) {
+      zone_cell0[e] = d->zone_ptr[e];
+      snow_cell0[e] = d->snow_ptr[e];
+      if (!(einfo[e] & HB_EI_FAST)) continue;
+      for (int k = 0; k < nz[e]; ++k) {
+        zone_slot[(size_t)d->zone_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);
+        snow_slot[(size_t)d->snow_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);   // fast path: one snow class
+      }
+    }
+    int rc2;
+    if ((rc2 = upload(h, h->d_zone_slot, zone_slot)) || (rc2 = upload(h, h->d_snow_slot, snow_slot)) ||
+        (rc2 = upload(h, h->d_zone_cell0, zone_cell0)) || (rc2 = upload(h, h->d_snow_cell0, snow_cell0)))
+      return rc2;
+  }
   h->h_nz = nz; h->h_nc = nc; h->h_nu = nu;
   int rc;
   if ((rc = upload(h, h->d_nz, nz)) || (rc = upload(h, h->d_nc, nc)) || (rc = upload(h, h->d_nu, nu)) ||
@@ -910,10 +931,16 @@ static int run_land(hb_engine* h) {
   for (int s = 0; s < HB_S_COUNT; ++s) any_series = any_series || h->series_on[s];
   // fast path (land_kernel_v2.cuh) for the eligible elements unless series are requested or the caller forces the
   // general kernel; everything else goes through the general kernel
-  const bool use_fast = h->n_fast > 0 && !any_series && h->land_path == HB_LAND_AUTO;
+  // (zone/snow series of the fast path are staged through a [zmax][33] shared-memory tile: zmax <= 128)
+  const bool use_fast = h->n_fast > 0 && h->land_path == HB_LAND_AUTO && !(any_series && h->zmax > 128);
   const int64_t n_general = use_fast ? (int64_t)h->slow_list.size() : h->n_elem;
   h->timing.n_fast = use_fast ? h->n_fast : 0;
   if (h->n_elem == 0 || nt == 0) return HB_OK;
+  for (int s = 0; s < HB_S_COUNT; ++s) {
+    if (!h->series_on[s]) continue;
+    const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+    HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
+  }
 
   if (use_fast) {
     LandV2Dev v{};
@@ -923,27 +950,55 @@ static int run_land(hb_engine* h) {
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing.p;
     v.sinfactor = h->d_sinfactor.p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.n_zone = h->n_zone; v.n_snow = h->n_snow;
+    int n_staged = 0;
+    for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
     // time chunks bound the two term buffers (3 GB each at most)
     const int64_t per_step = (int64_t)h->zmax * ep;
-    int64_t chunk_max = (int64_t)(3.0e9 / 8.0) / per_step;
+    // scratch per simulated step: two term buffers + one staging buffer per recorded zone/snow series; 6 GB in total
+    int64_t chunk_max = (int64_t)(6.0e9 / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
     const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
     HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
     HB_CUDA(h, h->d_term_b.reserve((size_t)chunk * per_step));
     v.term_a = h->d_term_a.p; v.term_b = h->d_term_b.p;
+    for (int s = 0; s < HB_S_COUNT; ++s) {
+      v.series[s] = nullptr;
+      if (!h->series_on[s]) continue;
+      if (s < HB_S_FIRST_ELEM) {
+        HB_CUDA(h, h->d_series_stage[s].reserve((size_t)chunk * per_step));
+        v.series[s] = h->d_series_stage[s].p;
+      } else v.series[s] = h->d_series[s].p;
+    }
     for (int64_t c0 = 0; c0 < nt; c0 += chunk) {
       v.nt = (nt - c0 < chunk) ? (nt - c0) : chunk;
       v.t_first = h->t0 + c0;
       v.t_out = c0;
       h->mark(HB_K_OTHER);
-      zone_kernel<true><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+      const unsigned zgrid = (unsigned)(per_step / 128), egrid = (unsigned)((h->n_elem + 63) / 64);
+      if (any_series) zone_kernel<true, true><<<zgrid, 128, 0, h->stream>>>(v);
+      else zone_kernel<true, false><<<zgrid, 128, 0, h->stream>>>(v);
       if (h->any_nonsoil_warp) {
-        zone_kernel<false><<<(unsigned)(per_step / 128), 128, 0, h->stream>>>(v);
+        if (any_series) zone_kernel<false, true><<<zgrid, 128, 0, h->stream>>>(v);
+        else zone_kernel<false, false><<<zgrid, 128, 0, h->stream>>>(v);
         h->timing.land_launches += 1;
       }
+      if (n_staged) {
+        dim3 sg((unsigned)((h->n_elem + 31) / 32), (unsigned)(v.nt < 64 ? v.nt : 64));
+        const size_t sm_bytes = (size_t)h->zmax * 33 * sizeof(double);
+        for (int s = 0; s < HB_S_FIRST_ELEM; ++s) {
+          if (!h->series_on[s]) continue;
+          const bool snow = s >= HB_S_FIRST_SNOW;
+          series_scatter_kernel<<<sg, 256, sm_bytes, h->stream>>>(
+              h->d_series_stage[s].p, h->d_series[s].p, snow ? h->d_snow_cell0.p : h->d_zone_cell0.p,
+              snow ? h->d_snow_slot.p : h->d_zone_slot.p, h->n_elem, ep, h->zmax, snow ? h->n_snow : h->n_zone, (int)v.nt, c0);
+          h->timing.land_launches += 1;
+        }
+      }
       h->mark(HB_K_ZONE);
-      element_kernel<<<(unsigned)((h->n_elem + 63) / 64), 64, 0, h->stream>>>(v);
+      if (any_series) element_kernel<true><<<egrid, 64, 0, h->stream>>>(v);
+      else element_kernel<false><<<egrid, 64, 0, h->stream>>>(v);
       h->mark(HB_K_ELEMENT);
       h->timing.land_launches += 2;
     }
@@ -964,13 +1019,7 @@ static int run_land(hb_engine* h) {
     d.tables = h->d_tables.p;
     d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p;
     d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
-    for (int s = 0; s < HB_S_COUNT; ++s) {
-      d.series[s] = nullptr;
-      if (!h->series_on[s]) continue;
-      const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
-      HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
-      d.series[s] = h->d_series[s].p;
-    }
+    for (int s = 0; s < HB_S_COUNT; ++s) d.series[s] = h->series_on[s] ? h->d_series[s].p : nullptr;
     const int block = 128;
     const int grid = (int)((n_general + block - 1) / block);
     h->mark(HB_K_OTHER);

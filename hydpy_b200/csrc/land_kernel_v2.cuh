@@ -61,6 +61,11 @@ struct LandV2Dev {
   double* term_b;          // [nt][zmax][E_pad]
   double* qt;              // [nt_window][E_pad], chunk starts at row t_out
   int64_t t_out;
+  // optional series (SERIES kernels).  Element level: ABI layout [nt_window][n_elem], written in place.  Zone and
+  // snow level: the zone kernel writes a chunk-local staging buffer in ITS layout [nt][zmax][E_pad] (coalesced);
+  // series_scatter_kernel then moves the chunk into the ABI layout [nt_window][n_zone] with coalesced stores.
+  int64_t n_zone, n_snow;
+  double* series[HB_S_COUNT];
 };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
@@ -79,7 +84,8 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 #define HB_ZONE_BLOCKS 4
 #endif
 // SOIL = true : the warps whose 32 zones are all FIELD/FOREST with FC > 0 (branch-free step); SOIL = false: all other warps
-template <bool SOIL>
+// SERIES = true additionally records the requested hland_96 zone sequences (the HBM-bound regime of SURVEY.md §8d-ii)
+template <bool SOIL, bool SERIES>
 __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
@@ -138,6 +144,8 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 #define HB_ZONE_STEP_END(va, vb) \
   *out_a = (va); *out_b = (vb); out_a += tstride; out_b += tstride;
   const int nt = (int)d.nt;
+#define SERZ(id, v) do { if (SERIES && d.series[id]) d.series[id][(int64_t)t * tstride + slot] = (v); } while (0)
+#define SERS(id, v) SERZ(id, v)
 
   // ---- warps whose 32 zones are all FIELD/FOREST with FC > 0 (the bulk of any basin) run a BRANCH-FREE step: every
   // data-dependent `if` of the reference becomes a select on values that are computed unconditionally.  Results are
@@ -177,12 +185,19 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         double refr = HB_PYMIN(potrefr, wc);
         refr = (tc < ttm) ? refr : 0.0;
         sp += refr; wc -= refr;
+        SERS(HB_S_MELT, melt); SERS(HB_S_REFR, refr);
       }
       // ref: hland_model.py:1434-1448 Calc_In_WC_V1
       const double wc_old = wc, lim = whc * sp;
       wc = HB_PYMIN(wc_old, lim);
       const double in_ = wc_old - wc;
       const double ncover = (sp > 0.0) ? 1.0 : 0.0;
+      if (SERIES) {
+        SERZ(HB_S_TC, tc); SERZ(HB_S_FRACRAIN, fracrain); SERZ(HB_S_PC, pc); SERZ(HB_S_TF, tf); SERZ(HB_S_CFACT, cfact);
+        SERZ(HB_S_GACT, 0.0); SERZ(HB_S_SPL, 0.0); SERZ(HB_S_WCL, 0.0); SERZ(HB_S_SPG, 0.0); SERZ(HB_S_WCG, 0.0);
+        SERZ(HB_S_GLMELT, 0.0); SERZ(HB_S_SR, 0.0); SERZ(HB_S_EL, 0.0); SERZ(HB_S_IN, in_);
+        SERS(HB_S_SWE, sp + wc); SERS(HB_S_SP, sp); SERS(HB_S_WC, wc);   // ref: hland_model.py:1485-1495 Calc_SWE_V1
+      }
       // evap_pet_hbv96.run(): ref: evap_model.py:5111-5125, 5420-5424, 5312-5326
       double pet;
       {
@@ -201,6 +216,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       {
         const double ei = HB_PYMIN(aet_ie, ic);
         ic -= ei;
+        SERZ(HB_S_EI, ei); SERZ(HB_S_IC, ic);
       }
       // ref: hland_model.py:1776-1790 Calc_R_SM_V1
       double r = in_ * hb_pow(sm * inv_fc, beta, T);
@@ -240,6 +256,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         r = over ? r_over : r;
         sm = over ? fc : sm;
       }
+      SERZ(HB_S_R, r); SERZ(HB_S_CF, cf); SERZ(HB_S_EA, ea); SERZ(HB_S_SM, sm);
       // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
       const double contri = hb_pow(sm * inv_fc, w_b, T);
       HB_ZONE_STEP_END(w_a * (r - cf), resp ? contri : 1.0)
@@ -269,6 +286,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
     } else { tf = pc; ic = 0.0; }
     double in_ = tf, ncover = 0.0;
     bool bare = true;
+    double s_cfact = 0.0, s_gact = 0.0, s_melt = 0.0, s_refr = 0.0, s_glmelt = 0.0;   // recorded only
     if (zt != HB_ILAKE) {
       // ref: hland_model.py:484-499 Calc_SP_WC_V1
       wc += sf * (tf * fracrain);
@@ -276,15 +294,18 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       // ref: hland_model.py:1050-1062 Calc_CFAct_V1
       const double cfa = cfmax + sinf * cfvar;
       const double cfact = HB_PYMAX(cfa, 0.0);
+      s_cfact = cfact;
       // ref: hland_model.py:1166-1187 Calc_Melt_SP_WC_V1, 1318-1341 Calc_Refr_SP_WC_V1
       if (tc > ttm) {
         const double potmelt = cfact * (tc - ttm);
         const double melt = HB_PYMIN(potmelt, sp);
         sp -= melt; wc += melt;
+        s_melt = melt;
       } else if (tc < ttm) {
         const double potrefr = cfr_cfmax * (ttm - tc);
         const double refr = HB_PYMIN(potrefr, wc);
         sp += refr; wc -= refr;
+        s_refr = refr;
       }
       // ref: hland_model.py:1434-1448 Calc_In_WC_V1 (one snow class: the division by SClass is exact)
       const double wc_old = wc, lim = whc * sp;
@@ -293,12 +314,22 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       bare = sp <= 0.0;
       ncover = (sp > 0.0) ? 1.0 : 0.0;
       // ref: hland_model.py:1607-1619 Calc_GAct_V1, 1688-1701 Calc_GlMelt_In_V1
-      if (zt == HB_GLACIER && tc > ttm && bare) {
+      if (zt == HB_GLACIER) {
         const double ga = g_melt + sinf * g_var;
         const double gact = HB_PYMAX(ga, 0.0);
-        in_ += gact * (tc - ttm);
+        s_gact = gact;
+        if (tc > ttm && bare) {
+          s_glmelt = gact * (tc - ttm);
+          in_ += s_glmelt;
+        }
       }
     } else { sp = 0.0; wc = 0.0; }
+    if (SERIES) {
+      SERZ(HB_S_TC, tc); SERZ(HB_S_FRACRAIN, fracrain); SERZ(HB_S_PC, pc); SERZ(HB_S_TF, tf); SERZ(HB_S_CFACT, s_cfact);
+      SERZ(HB_S_GACT, s_gact); SERZ(HB_S_SPL, 0.0); SERZ(HB_S_WCL, 0.0); SERZ(HB_S_SPG, 0.0); SERZ(HB_S_WCG, 0.0);
+      SERZ(HB_S_GLMELT, s_glmelt); SERZ(HB_S_SR, zt == HB_SEALED ? in_ : 0.0); SERZ(HB_S_IN, in_);
+      SERS(HB_S_MELT, s_melt); SERS(HB_S_REFR, s_refr); SERS(HB_S_SWE, sp + wc); SERS(HB_S_SP, sp); SERS(HB_S_WC, wc);
+    }
     // evap_pet_hbv96.run(): ref: evap_model.py:5111-5125, 5420-5424, 5312-5326
     double pet;
     {
@@ -314,8 +345,10 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
     // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1; hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
     double aet_ie = 0.0;
     if (zf & HB_ZF_INTERCEPTION) aet_ie = HB_PYMIN(pet, ic);
-    if (icept) { const double ei = HB_PYMIN(aet_ie, ic); ic -= ei; }
+    double s_ei = 0.0;
+    if (icept) { s_ei = HB_PYMIN(aet_ie, ic); ic -= s_ei; }
     else ic = 0.0;
+    SERZ(HB_S_EI, s_ei); SERZ(HB_S_IC, ic);
     double ta, tb = 1.0;
     if (soil) {
       // ref: hland_model.py:1776-1790 Calc_R_SM_V1
@@ -355,21 +388,52 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
       ta = w_a * (r - cf);
       if (resp && fc > 0.0) tb = hb_pow(sm * inv_fc, w_b, T);
+      SERZ(HB_S_R, r); SERZ(HB_S_CF, cf); SERZ(HB_S_EA, ea); SERZ(HB_S_SM, sm); SERZ(HB_S_EL, 0.0);
     } else {
       sm = 0.0;
+      double el = 0.0;
       if (zt == HB_ILAKE) {
         // ref: hland_model.py:3113-3124 Calc_LZ_V1 (term), 3724-3737 Calc_EL_LZ_AETModel_V1 (term);
         // evap_model.py:5673-5681 Calc_WaterEvaporation_V1
         ta = w_a * pc;
-        const double el = ((zf & HB_ZF_WATER) && tc > tti) ? pet : 0.0;
+        el = ((zf & HB_ZF_WATER) && tc > tti) ? pet : 0.0;
         tb = w_b * el;
       } else ta = w_a * (in_ - 0.0);  // GLACIER: InUZ term; SEALED: InRC term (r = in_, ref: hland_model.py:1528-1535)
+      SERZ(HB_S_R, in_); SERZ(HB_S_CF, 0.0); SERZ(HB_S_EA, 0.0); SERZ(HB_S_SM, 0.0); SERZ(HB_S_EL, el);
     }
     HB_ZONE_STEP_END(ta, tb)
   }
 #undef HB_ZONE_STEP_BEGIN
 #undef HB_ZONE_STEP_END
+#undef SERZ
+#undef SERS
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
+}
+
+// staging layout [nt][zmax][E_pad]  →  ABI layout [nt_window][width] for the zones (or snow cells) of the fast-path
+// elements.  A block takes 32 consecutive elements: their staging rows are read coalesced into a shared-memory tile,
+// their ABI cells form ONE contiguous range (zones of consecutive elements follow each other), written coalesced.
+// slot_of[cell] = k*E_pad + e of the ABI cell, or -1 when the cell belongs to an element of the general kernel.
+__global__ void __launch_bounds__(256) series_scatter_kernel(const double* __restrict__ staged, double* __restrict__ abi,
+                                                             const int64_t* __restrict__ cell0,   // [E_pad+1] first cell
+                                                             const int32_t* __restrict__ slot_of, int64_t n_elem,
+                                                             int64_t e_pad, int zmax, int64_t width, int nt, int64_t t_out) {
+  extern __shared__ double tile[];                      // [zmax][33]
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int64_t e1 = e0 + 32 < n_elem ? e0 + 32 : n_elem;
+  const int64_t z_begin = cell0[e0], z_end = cell0[e1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int t = blockIdx.y; t < nt; t += gridDim.y) {
+    const double* src = staged + (int64_t)t * zmax * e_pad + e0;
+    for (int k = wib; k < zmax; k += 8) tile[k * 33 + lane] = src[(int64_t)k * e_pad + lane];
+    __syncthreads();
+    double* dst = abi + (t_out + t) * width;
+    for (int64_t z = z_begin + threadIdx.x; z < z_end; z += 256) {
+      const int32_t sl = slot_of[z];
+      if (sl >= 0) dst[z] = tile[(sl / e_pad) * 33 + (sl % e_pad - e0)];
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -381,6 +445,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 #ifndef HB_ELEM_BLOCKS
 #define HB_ELEM_BLOCKS 12
 #endif
+template <bool SERIES>
 __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
@@ -489,7 +554,15 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
     }
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
-    d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
+    const double qt = qfactor * outrc;
+    d.qt[(d.t_out + t) * ep + e] = qt;
+    if (SERIES) {
+#define SERE(id, v) do { if (d.series[id]) d.series[id][(d.t_out + t) * d.n_elem + e] = (v); } while (0)
+      SERE(HB_S_INUZ, inuz); SERE(HB_S_CONTRIAREA, contriarea); SERE(HB_S_PERC, perc_sum); SERE(HB_S_Q0, q0_sum);
+      SERE(HB_S_Q1, q1); SERE(HB_S_INRC, inrc); SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, outrc); SERE(HB_S_QT, qt);
+      SERE(HB_S_UZ, uz); SERE(HB_S_LZ, lz);
+#undef SERE
+    }
   }
   d.uz[e] = uz;
   d.lz[e] = lz;

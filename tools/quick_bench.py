@@ -17,6 +17,8 @@ ap.add_argument("--nt", type=int, default=168)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-river", action="store_true")
 ap.add_argument("--levels", type=int, default=200)
+ap.add_argument("--series", default="", help="comma-separated land series to record ('all' = every hland_96 sequence)")
+ap.add_argument("--path", default="auto")
 args = ap.parse_args()
 
 t = time.time()
@@ -27,6 +29,11 @@ eng = Engine(0)
 print(eng.device_info())
 t = time.time()
 eng.set_land(land); eng.set_land_states(states); eng.set_river(river); eng.set_river_states(dis)
+from hydpy_b200 import layout
+series = list(layout.SERIES) if args.series == "all" else [x for x in args.series.split(",") if x]
+eng.select_series(series)
+eng.set_land_path(args.path)
+nbytes = 8 * args.nt * sum(land.n_zone if x in layout.SERIES_ZONE else land.n_snow if x in layout.SERIES_SNOW else land.n_elem for x in series)
 print(f"uploaded in {time.time()-t:.2f}s")
 for rep in range(args.reps):
     forcing, doy = synth.make_forcing(args.nt, args.step, t0=rep * args.nt)
@@ -38,7 +45,8 @@ for rep in range(args.reps):
     tm = eng.timing()
     zs = land.n_zone * args.nt
     print(f"rep {rep}: h2d {1e3*(t1-t):.1f} ms  run wall {1e3*(t2-t1):.1f} ms  land {tm['land_ms']:.2f} ms (zone {tm['zone_ms']:.2f} element {tm['element_ms']:.2f})  river {tm['river_ms']:.2f} ms "
-          f"({tm['river_launches']} launches, {tm['n_levels']} levels)  -> {zs/tm['total_ms']*1e3:.3e} zone-steps/s (device)")
+          f"({tm['river_launches']} launches, {tm['n_levels']} levels)  -> {zs/tm['total_ms']*1e3:.3e} zone-steps/s (device)"
+          + (f"  series {nbytes/1e9:.2f} GB -> {nbytes/1e6/tm['land_ms']:.0f} GB/s of land time" if series else ""))
 t = time.time()
 rows = eng.get_node_series() if not args.no_river else eng.get_land_outflow()
 print(f"d2h {rows.nbytes/1e6:.0f} MB in {1e3*(time.time()-t):.1f} ms; finite={np.isfinite(rows).all()} mean={rows.mean():.4f}")
