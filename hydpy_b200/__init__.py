@@ -9,7 +9,7 @@ Public API:
 """
 from .abi import LandBundle, LandStates, RiverBundle
 from .engine import Engine, EngineError, EngineUnavailable, device_count
-from .extract import Problem, UnsupportedModelError, extract, requested_series, write_back
+from .extract import Problem, UnsupportedModelError, extract, requested_reach_states, requested_series, write_back
 from .simulate import get_engine, install, run_problem, simulate, uninstall
 
 __all__ = [

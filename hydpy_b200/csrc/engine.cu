@@ -138,6 +138,8 @@ struct hb_engine {
   DBuf<int64_t> d_zone_cell0, d_snow_cell0;       // [E_pad+1] first ABI cell of every element
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
   int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
+  bool river_state_series = false;        // record musk_classic states.discharge per step
+  DBuf<double> d_dis_series[2];
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
@@ -614,6 +616,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       HB_REQUIRE(h, value == HB_LAND_AUTO || value == HB_LAND_GENERAL, HB_EINVAL, "hb_set_option: invalid land path");
       h->land_path = (int)value;
       return HB_OK;
+    case HB_OPT_RIVER_STATE_SERIES:
+      h->river_state_series = value != 0;
+      if (!value) { h->d_dis_series[0].release(); h->d_dis_series[1].release(); }
+      return HB_OK;
     case HB_OPT_RIVER_SWEEP:
       HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES, HB_EINVAL,
                  "hb_set_option: invalid routing sweep");
@@ -1050,6 +1056,11 @@ static int run_river(hb_engine* h) {
   d.seg_ptr = h->d_seg_ptr.p; d.coef = h->d_coef.p; d.land_rows = h->d_land_rows[h->cur].p; d.ext_rows = h->d_ext_rows[h->cur].p;
   d.node_rows = h->d_node_rows[h->cur].p; d.reach_in = h->d_reach_in[h->cur].p; d.reach_out = h->d_reach_out[h->cur].p;
   d.dis[0] = h->d_dis[0].p; d.dis[1] = h->d_dis[1].p; d.par0 = h->dis_cur; d.n_chunks = n_chunks;
+  d.n_seg = h->n_seg; d.dis_series = nullptr;
+  if (h->river_state_series) {
+    HB_CUDA(h, h->d_dis_series[h->cur].reserve((size_t)nt * h->n_seg));
+    d.dis_series = h->d_dis_series[h->cur].p;
+  }
   d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p; d.meta = h->d_reach_meta.p;
   d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
@@ -1369,6 +1380,14 @@ int hb_get_reach_outflow(hb_engine* h, double* rows) {
   HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_reach_outflow: no routing results");
   HB_CUDA(h, cudaSetDevice(h->device));
   return download(h, rows, h->d_reach_out[h->cur].p, (size_t)h->n_reach * h->nt);
+}
+
+int hb_get_reach_state_series(hb_engine* h, double* out) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river && h->have_routed && h->river_state_series && h->d_dis_series[h->cur].p, HB_ESTATE,
+             "hb_get_reach_state_series: not recorded (set HB_OPT_RIVER_STATE_SERIES before hb_run)");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  return download(h, out, h->d_dis_series[h->cur].p, (size_t)h->nt * h->n_seg);
 }
 
 int hb_get_reach_inflow(hb_engine* h, double* rows) {

@@ -68,6 +68,8 @@ struct RiverDev {
   double* node_rows;        // [n_node][nt]
   double* reach_in;         // [n_reach][nt]
   double* reach_out;        // [n_reach][nt]
+  double* dis_series;       // optional [nt][n_seg]: musk_classic states.discharge at every step (NULL: not recorded)
+  int64_t n_seg;
   double* dis[2];           // chunk c reads dis[(par0 + c) & 1] and writes the other one
   int par0;
   int n_chunks;
@@ -248,6 +250,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       const double inflow = 0.0 + (0.0 + sim);   // ref: musk_model.py:26-31 Pick_Inflow_V1
       rin[t] = inflow;
       if (S == 0) rout[t] = inflow;
+      if (d.dis_series) d.dis_series[t * d.n_seg + g0] = inflow;
       x_own = inflow;
     }
   } else if (lane < len) {
@@ -268,6 +271,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     }
     rin[t] = inflow;
     if (S == 0) rout[t] = inflow;  // ref: musk_model.py:95-98, 831-835 — zero segments: outflow = discharge[0]
+    if (d.dis_series) d.dis_series[t * d.n_seg + g0] = inflow;
     x_own = inflow;
   }
   if (bulk && S >= 1 && S <= HB_BULK_SMAX) return true;
@@ -303,6 +307,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
         prev_in = in;
         prev_out = nv;
         out = nv;
+        if (d.dis_series) d.dis_series[(ta + tloc) * d.n_seg + g0 + cbase + lane + 1] = nv;
       }
       const double y = __shfl_sync(full, out, nseg - 1);
       const int p = tau - (nseg - 1);
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const Ri
             q[i + 1] = nv;
             q_old = q_next;
             in = nv;
+            if (d.dis_series) d.dis_series[(ta + tt) * d.n_seg + g0 + i + 1] = nv;
           }
         }
         X[lane * 33 + tt] = in;

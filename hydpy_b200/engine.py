@@ -23,7 +23,7 @@ EXPORTS = (
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
     "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run",
     "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
-    "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
+    "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
     "hb_device_info",
@@ -80,6 +80,7 @@ def load_library() -> C.CDLL:
         "hb_get_node_series": (C.c_int, [H, C.c_int64, i32p, f64p]),
         "hb_get_reach_outflow": (C.c_int, [H, f64p]),
         "hb_get_reach_inflow": (C.c_int, [H, f64p]),
+        "hb_get_reach_state_series": (C.c_int, [H, f64p]),
         "hb_get_series": (C.c_int, [H, C.c_int, f64p]),
         "hb_comm_unique_id": (C.c_int, [H, C.c_void_p]),
         "hb_comm_init": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
@@ -326,6 +327,16 @@ class Engine:
         river = self._need_river()
         out = np.zeros((river.n_reach, self.nt))
         self._check(self._lib.hb_get_reach_outflow(self._h, ptr(out, C.c_double)), "hb_get_reach_outflow")
+        return out
+
+    def record_reach_states(self, on: bool = True) -> None:
+        """Record musk_classic `states.discharge` of every step (read with `get_reach_state_series`)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_STATE_SERIES, int(bool(on))), "hb_set_option")
+
+    def get_reach_state_series(self) -> np.ndarray:
+        river = self._need_river()
+        out = np.zeros((self.nt, river.n_seg))
+        self._check(self._lib.hb_get_reach_state_series(self._h, ptr(out, C.c_double)), "hb_get_reach_state_series")
         return out
 
     def get_reach_inflow(self) -> np.ndarray:

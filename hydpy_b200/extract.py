@@ -408,6 +408,11 @@ def requested_series(problem: Problem) -> list[str]:
     return wanted
 
 
+def requested_reach_states(problem: Problem) -> bool:
+    """True when at least one musk_classic element keeps `states.discharge` in RAM."""
+    return any(getattr(el.model.sequences.states.discharge, "ramflag", False) for el in problem.river_elements)
+
+
 def _set_state(seq: Any, value: Any) -> None:
     seq.new = value
     seq.old = value
@@ -415,7 +420,7 @@ def _set_state(seq: Any, value: Any) -> None:
 
 def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, node_rows: np.ndarray,
                land_rows: np.ndarray, reach_out: np.ndarray | None, reach_in: np.ndarray | None,
-               series: dict[str, np.ndarray]) -> None:
+               series: dict[str, np.ndarray], reach_state_series: np.ndarray | None = None) -> None:
     """Store the results of one run in the HydPy objects exactly where the reference leaves them."""
     land, i0, i1 = problem.land, problem.i0, problem.i1
     last = i1 - i0 - 1
@@ -462,6 +467,8 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
         model = element.model
         g0, g1 = int(river.seg_ptr[r]), int(river.seg_ptr[r + 1])
         _set_state(model.sequences.states.discharge, discharge[g0:g1])
+        if reach_state_series is not None and getattr(model.sequences.states.discharge, "ramflag", False):
+            model.sequences.states.discharge.series[i0:i1] = reach_state_series[:, g0:g1]
         flu = model.sequences.fluxes
         if reach_in is not None:
             if flu.inflow.ramflag:

@@ -19,7 +19,7 @@ import numpy as np
 
 from .abi import LandStates
 from .engine import Engine
-from .extract import Problem, extract, requested_series, write_back
+from .extract import Problem, extract, requested_reach_states, requested_series, write_back
 
 _engines: dict[int, Engine] = {}
 
@@ -32,11 +32,11 @@ def get_engine(device: int = 0) -> Engine:
 
 
 def run_problem(problem: Problem, engine: Engine | None = None, *, series: Iterable[str] = (),
-                window: int | None = None, device: int = 0) -> dict[str, Any]:
+                window: int | None = None, device: int = 0, reach_states: bool = False) -> dict[str, Any]:
     """Run an extracted problem on the engine, optionally in time windows of `window` steps.
 
     Returns the keyword arguments of `extract.write_back` (states, discharge, node_rows, land_rows, reach_out,
-    reach_in, series).
+    reach_in, series and — with `reach_states` — reach_state_series = musk_classic `states.discharge` per step).
     """
     eng = engine if engine is not None else get_engine(device)
     series = list(series)
@@ -46,6 +46,8 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
     eng.set_river(problem.river)
     eng.set_river_states(problem.discharge)
     eng.select_series(series)
+    eng.record_reach_states(reach_states)
+    state_parts: list[np.ndarray] = []
     window = nt if not window or window <= 0 else min(int(window), nt)
     node_rows = np.zeros((problem.river.n_node, nt))
     land_rows = np.zeros((problem.land.n_elem, nt))
@@ -65,15 +67,21 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
             reach_in[:, t0:t1] = eng.get_reach_inflow()
             for name in series:
                 out_series[name].append(eng.get_series(name))
+            if reach_states:
+                state_parts.append(eng.get_reach_state_series())
         t0 = t1
         if nt == 0:
             break
     states: LandStates = eng.get_land_states()
     discharge = eng.get_river_states()
-    return dict(
+    result = dict(
         states=states, discharge=discharge, node_rows=node_rows, land_rows=land_rows, reach_out=reach_out,
         reach_in=reach_in, series={n: np.concatenate(v, axis=0) for n, v in out_series.items() if v},
     )
+    if reach_states:
+        result["reach_state_series"] = (np.concatenate(state_parts, axis=0) if state_parts
+                                        else np.zeros((0, problem.river.n_seg)))
+    return result
 
 
 def simulate(hp: Any, *, device: int = 0, window: int | None = None, engine: Engine | None = None) -> None:
@@ -82,7 +90,8 @@ def simulate(hp: Any, *, device: int = 0, window: int | None = None, engine: Eng
 
     i0, i1 = hydpy.pub.timegrids.simindices
     problem = extract(hp, i0, i1)
-    result = run_problem(problem, engine, series=requested_series(problem), window=window, device=device)
+    result = run_problem(problem, engine, series=requested_series(problem), window=window, device=device,
+                         reach_states=requested_reach_states(problem))
     write_back(problem, **result)
 
 

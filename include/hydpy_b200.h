@@ -218,6 +218,9 @@ int hb_select_series(hb_engine* h, int series, int on);
 #define HB_OPT_RIVER_SWEEP 1
 #define HB_RIVER_PERSISTENT 0
 #define HB_RIVER_LAUNCHES 1
+/* HB_OPT_RIVER_STATE_SERIES (0/1): record musk_classic `states.discharge` of every step for hb_get_reach_state_series
+ * (the `ramflag` of that sequence, `hydpy/models/musk/musk_states.py`). */
+#define HB_OPT_RIVER_STATE_SERIES 2
 int hb_set_option(hb_engine* h, int option, int64_t value);
 
 /* ---- one simulation window ------------------------------------------------------------------------------------ */
@@ -256,6 +259,9 @@ int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double
 int hb_get_node_series_async(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows);
 /* musk_classic fluxes.outflow / outlets.q of every reach: host [n_reach][nt]. */
 int hb_get_reach_outflow(hb_engine* h, double* rows);
+/* musk_classic states.discharge per step: host [nt][n_seg] (points of all reaches concatenated like the state itself);
+ * needs HB_OPT_RIVER_STATE_SERIES. */
+int hb_get_reach_state_series(hb_engine* h, double* out);
 /* musk_classic fluxes.inflow of every reach: host [n_reach][nt]. */
 int hb_get_reach_inflow(hb_engine* h, double* rows);
 /* One selected land series (see enum hb_series for the layout). */

@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         ]
         _lib.oracle_river_run.restype = C.c_int
         _lib.oracle_river_run.argtypes = [C.POINTER(hb_river_desc), f64p, C.c_int64, f64p, f64p, f64p, f64p, f64p]
+        _lib.oracle_river_run2.restype = C.c_int
+        _lib.oracle_river_run2.argtypes = [C.POINTER(hb_river_desc), f64p, C.c_int64, f64p, f64p, f64p, f64p, f64p, f64p]
         _lib.oracle_sinfactor.restype = C.c_double
         _lib.oracle_sinfactor.argtypes = [C.c_int64]
     return _lib
@@ -104,9 +106,10 @@ def land_run(land: LandBundle, states: LandStates, forcing: np.ndarray, doy: np.
     return qt, out
 
 
-def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, ext: np.ndarray | None = None
-              ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Route the window; `discharge` is updated in place.  Returns (node rows, reach outflow, reach inflow)."""
+def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, ext: np.ndarray | None = None,
+              dis_series: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Route the window; `discharge` is updated in place.  Returns (node rows, reach outflow, reach inflow).
+    `dis_series` (optional, [nt, n_seg]) receives musk_classic `states.discharge` after every step."""
     L = lib()
     land_rows = np.ascontiguousarray(land_rows, dtype=np.float64)
     nt = land_rows.shape[1] if land_rows.ndim == 2 and land_rows.shape[0] else (ext.shape[1] if ext is not None else 0)
@@ -118,9 +121,11 @@ def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, 
     rout = np.zeros((river.n_reach, nt))
     rin = np.zeros((river.n_reach, nt))
     assert discharge.dtype == np.float64 and discharge.flags.c_contiguous
-    rc = L.oracle_river_run(C.byref(d), ptr(discharge, C.c_double), nt, ptr(land_rows, C.c_double),
-                            ptr(ext, C.c_double), ptr(node_rows, C.c_double), ptr(rout, C.c_double),
-                            ptr(rin, C.c_double))
+    if dis_series is not None:
+        assert dis_series.shape == (nt, river.n_seg) and dis_series.dtype == np.float64 and dis_series.flags.c_contiguous
+    rc = L.oracle_river_run2(C.byref(d), ptr(discharge, C.c_double), nt, ptr(land_rows, C.c_double),
+                             ptr(ext, C.c_double), ptr(node_rows, C.c_double), ptr(rout, C.c_double),
+                             ptr(rin, C.c_double), ptr(dis_series, C.c_double) if dis_series is not None else None)
     if rc != 0:
         raise RuntimeError(f"oracle_river_run failed with code {rc}")
     return node_rows, rout, rin

@@ -1,0 +1,21 @@
+"""The drop-in boundary on real reference objects (CPU, only where the reference build of oracle/build_ref.py exists —
+i.e. in the build container; skipped on the GPU box, which has no /root/reference)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import build_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC, _ = build_ref.scratch_paths()
+BUILT = os.path.exists(os.path.join(os.path.dirname(SRC), ".built"))
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+def test_simulate_leaves_hydpy_objects_like_the_reference_does():
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_worker.py")], capture_output=True,
+                          text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "DROPIN_OK" in proc.stdout
