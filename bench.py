@@ -318,7 +318,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
                            "frac": tops(element_ops, element_ms_avg) / peak_ops,
                            "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win},
         "land_kernel (general)": {"ms": general_ms_avg},
-        "routing (reach_diag_kernel x levels+chunks)": {
+        "routing (reach_head + reach_bulk + reach_wave kernels)": {
             "ms": float(np.mean(river_ms)),
             "algorithmic_bytes_per_step": 16 * river.n_reach * win + 8 * (river.n_node + land.n_elem) * win},
     }
@@ -335,8 +335,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of one zone_kernel launch (240-step chunk, 10^5 x 12 zones) from the
-    # committed `ncu --set full` capture profiles/r01_v2_raw_selected.txt; only valid for the default workload
-    traffic = 5.08e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
+    # committed `ncu --set full` capture profiles/r01_final_summary.txt; only valid for the default workload
+    traffic = 5.09e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
