@@ -17,10 +17,14 @@
 
 #include "land_kernel.cuh"
 #include "land_kernel_v2.cuh"
+#include "land_kernel_coupled.cuh"
 #include "river_kernel.cuh"
 
 using namespace hb;
 
+#ifndef HB_COUPLED_B448
+#define HB_COUPLED_B448 2   // blocks per SM the fused capillary-flux kernel is compiled for at <= 13 warps per block
+#endif
 #ifndef HB_WAVE_BLOCKS_PER_SM
 #define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
@@ -130,8 +134,11 @@ struct hb_engine {
   bool any_snowlimit = false;
   bool any_nonsoil_warp = false;      // some warp of the zone kernel holds a fast-path zone that is not FIELD/FOREST with FC > 0
   int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
-  std::vector<int32_t> slow_list;     // the others
-  DBuf<int32_t> d_slow_list;
+  std::vector<int32_t> coupled_list;  // elements of the fused kernel (HB_EI_COUPLED)
+  std::vector<int32_t> general_list;  // elements of the general kernel in the current combination of paths
+  std::vector<int32_t> h_einfo;
+  int general_key = -1;
+  DBuf<int32_t> d_coupled_list, d_general_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
   DBuf<double> d_series_stage[HB_S_FIRST_ELEM];   // chunk-local staging of the zone/snow series (fast path)
   DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
@@ -259,6 +266,13 @@ int hb_create(int device, hb_engine** out) {
   for (auto& e : h->ev) cudaEventCreate(&e);
   cudaFuncSetAttribute(reach_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_BULK_SMEM);
   {
+    const int cs = (int)HB_COUPLED_SMEM(HB_COUPLED_ZMAX);
+    cudaFuncSetAttribute(coupled_kernel<288, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs);
+    cudaFuncSetAttribute(coupled_kernel<448, HB_COUPLED_B448>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs);
+    cudaFuncSetAttribute(coupled_kernel<640, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs);
+    cudaFuncSetAttribute(coupled_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs);
+  }
+  {
     // routing is a chain of ≈(levels + chunks) short dependent launches: at the highest priority its blocks take every
     // slot the long-running land blocks free, so the chain is not starved while it overlaps the next window's land part
     int lo = 0, hi = 0;
@@ -380,7 +394,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
   int64_t n_fast = 0;
-  std::vector<int32_t> slow_list;
+  std::vector<int32_t> coupled_list;
 #define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
 #define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
   for (int64_t e = 0; e < ne; ++e) {
@@ -456,7 +470,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       if ((zt == HB_FIELD || zt == HB_FOREST) && !(ZP(CFLUX, zz) == 0.0)) coupled = true;
     }
     if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
-    else slow_list.push_back((int32_t)e);
+    else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX) { info |= HB_EI_COUPLED; coupled_list.push_back((int32_t)e); }
     if (soilonly) info |= HB_EI_SOILONLY;
     if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
     einfo[e] = info;
@@ -490,7 +504,9 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
     }
   }
   h->n_fast = n_fast;
-  h->slow_list = slow_list;
+  h->coupled_list = coupled_list;
+  h->h_einfo.assign(einfo.begin(), einfo.begin() + ne);
+  h->general_key = -1;
   {
     HB_REQUIRE(h, (int64_t)zmax * ep < ((int64_t)1 << 31), HB_EINVAL, "hb_set_land: too many zone slots for 32-bit indices");
     std::vector<int32_t> zone_slot((size_t)d->n_zone, -1), snow_slot((size_t)d->n_snow, -1);
@@ -517,7 +533,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) ||
       (rc = upload(h, h->d_sred_ptr, sred_ptr)) || (rc = upload(h, h->d_kz, kz)) || (rc = upload(h, h->d_ke, ke)) ||
       (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)) ||
-      (rc = upload(h, h->d_slow_list, slow_list)))
+      (rc = upload(h, h->d_coupled_list, coupled_list)))
     return rc;
   if ((rc = upload(h, h->d_sred_from, d->sred_from, (size_t)d->n_sred)) ||
       (rc = upload(h, h->d_sred_to, d->sred_to, (size_t)d->n_sred)) ||
@@ -939,7 +955,22 @@ static int run_land(hb_engine* h) {
   // general kernel; everything else goes through the general kernel
   // (zone/snow series of the fast path are staged through a [zmax][33] shared-memory tile: zmax <= 128)
   const bool use_fast = h->n_fast > 0 && h->land_path == HB_LAND_AUTO && !(any_series && h->zmax > 128);
-  const int64_t n_general = use_fast ? (int64_t)h->slow_list.size() : h->n_elem;
+  // elements with capillary flux: fused kernel (no series recording there)
+  const bool use_coupled = !h->coupled_list.empty() && h->land_path == HB_LAND_AUTO && !any_series;
+  // the general kernel takes every element the two special paths do not take in this run
+  const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0);
+  if (general_key != h->general_key) {
+    h->general_list.clear();
+    for (int64_t e = 0; e < h->n_elem; ++e) {
+      const int info = h->h_einfo[e];
+      if ((use_fast && (info & HB_EI_FAST)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
+      h->general_list.push_back((int32_t)e);
+    }
+    int rc = upload(h, h->d_general_list, h->general_list);
+    if (rc) return rc;
+    h->general_key = general_key;
+  }
+  const int64_t n_general = (int64_t)h->general_list.size();
   h->timing.n_fast = use_fast ? h->n_fast : 0;
   if (h->n_elem == 0 || nt == 0) return HB_OK;
   for (int s = 0; s < HB_S_COUNT; ++s) {
@@ -1010,11 +1041,33 @@ static int run_land(hb_engine* h) {
     }
     HB_CUDA(h, cudaGetLastError());
   }
+  if (use_coupled) {
+    LandV2Dev v{};
+    v.n_elem = h->n_elem; v.e_pad = ep; v.zmax = h->zmax;
+    v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
+    v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
+    v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
+    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing.p;
+    v.sinfactor = h->d_sinfactor.p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.nt = nt; v.t_first = h->t0; v.t_out = 0;
+    v.clist = h->d_coupled_list.p; v.n_clist = (int64_t)h->coupled_list.size();
+    const int zw = h->zmax;
+    const unsigned threads = (unsigned)(zw + 1) * 32, grid = (unsigned)((v.n_clist + 31) / 32);
+    const size_t smem = HB_COUPLED_SMEM(zw);
+    h->mark(HB_K_OTHER);
+    if (threads <= 288) coupled_kernel<288, 4><<<grid, threads, smem, h->stream>>>(v);
+    else if (threads <= 448) coupled_kernel<448, HB_COUPLED_B448><<<grid, threads, smem, h->stream>>>(v);
+    else if (threads <= 640) coupled_kernel<640, 1><<<grid, threads, smem, h->stream>>>(v);
+    else coupled_kernel<1024, 1><<<grid, threads, smem, h->stream>>>(v);
+    h->mark(HB_K_GENERAL);
+    HB_CUDA(h, cudaGetLastError());
+    h->timing.land_launches += 1;
+  }
   if (n_general > 0) {
     LandDev d{};
     d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
     d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
-    d.n_list = n_general; d.elist = use_fast ? h->d_slow_list.p : nullptr;
+    d.n_list = n_general; d.elist = n_general == h->n_elem ? nullptr : h->d_general_list.p;
     d.nz = h->d_nz.p; d.nc = h->d_nc.p; d.nu = h->d_nu.p; d.recstep = h->d_recstep.p; d.einfo = h->d_einfo.p;
     d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p;
     d.kz = h->d_kz.p; d.ke = h->d_ke.p; d.sfdist = h->d_sfdist.p; d.uh = h->d_uh.p;

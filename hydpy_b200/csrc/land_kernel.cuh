@@ -79,6 +79,7 @@ enum ke {
 #define HB_EI_SNOWLIMIT 8  // some zone has finite SMax ⇒ Calc_SPL/Calc_SPG are live
 #define HB_EI_FAST 16      // eligible for the two-kernel fast path: one snow class, no snow limit, every CFlux == 0
 #define HB_EI_SOILONLY 32  // all zones are FIELD or FOREST
+#define HB_EI_COUPLED 64   // like HB_EI_FAST but with CFlux > 0 somewhere: fused kernel (land_kernel_coupled.cuh)
 
 // zone info: bits 0..2 zone type, bits 8.. zflags (HB_ZF_*)
 #define HB_ZI_TYPE(i) ((i) & 7)

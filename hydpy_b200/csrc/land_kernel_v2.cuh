@@ -66,6 +66,9 @@ struct LandV2Dev {
   // series_scatter_kernel then moves the chunk into the ABI layout [nt_window][n_zone] with coalesced stores.
   int64_t n_zone, n_snow;
   double* series[HB_S_COUNT];
+  // fused kernel for elements with capillary flux (land_kernel_coupled.cuh)
+  const int32_t* clist;    // their indices
+  int64_t n_clist;
 };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {

@@ -40,8 +40,9 @@ def load_template(step: str) -> dict[str, np.ndarray]:
 
 def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, bank: int = 1024,
               variants: bool = False, jitter: float = 0.1, area: float = 100.0,
-              own_nodes: bool = True) -> tuple[LandBundle, LandStates]:
-    """`n_elem` synthetic hland_96 elements (configs 3-5)."""
+              own_nodes: bool = True, cflux: float = 0.0) -> tuple[LandBundle, LandStates]:
+    """`n_elem` synthetic hland_96 elements (configs 3-5).  `cflux` > 0 (mm per simulation step, jittered like the other
+    parameters) switches the capillary flux on, i.e. couples the zones to the element's upper zone storage."""
     tpl = load_template(step)
     tz = tpl["zpar"].shape[1]
     rng = np.random.default_rng(seed)
@@ -58,7 +59,7 @@ def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, 
     zpar[ZP["ttm"]] = zpar[ZP["tt"]]                                      # dttm = 0 as in the Lahn project
     zpar[ZP["maxsoilwater"]] = zpar[ZP["fc"]]
     zpar[ZP["smax"]] = np.inf
-    zpar[ZP["cflux"]] = 0.0 * zpar[ZP["cflux"]]
+    zpar[ZP["cflux"]] = 0.0 * zpar[ZP["cflux"]] + cflux * (1.0 + jitter * rng.uniform(-1.0, 1.0, size=(ne, 1)))
     zonez = np.linspace(2.0, 7.0, nz)
     zpar[ZP["zonez"]] = zonez[None, :]
     zpar[ZP["hrualtitude"]] = 100.0 * zonez[None, :]

@@ -97,6 +97,25 @@ def test_synthetic_config4_slice_vs_oracle(engine):
     compare(res, ref, "config-4 slice")
 
 
+def test_synthetic_capillary_flux_vs_oracle(engine):
+    """CFlux > 0 couples the zones to the element's UZ of the previous step: fused kernel on the 'auto' path."""
+    ne, nt = 1500, 96
+    land, states = synth.make_land(ne, "1h", variants=True, cflux=0.02)
+    forcing, doy = synth.make_forcing(nt, "1h")
+    river, discharge = synth.make_tree_river(ne, "1h", levels=30)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    ref = oracle_run(problem)
+    assert np.any(ref["states"].sm != oracle_run(Problem(
+        land=synth.make_land(ne, "1h", variants=True)[0], states=states, river=river, discharge=discharge,
+        forcing=forcing, doy=doy, ext=np.zeros((0, nt))))["states"].sm), "the capillary flux has no effect in this test"
+    res = run_problem(problem, engine)
+    compare(res, ref, "capillary flux")
+    res2 = run_problem(problem, engine, window=29)
+    for key in ("land_rows", "node_rows", "discharge"):
+        assert np.array_equal(res[key], res2[key]), f"window splitting changes {key}"
+
+
 def test_synthetic_config3_daily_slice_vs_oracle(engine):
     ne, nt = 512, 40
     land, states = synth.make_land(ne, "1d")

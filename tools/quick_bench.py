@@ -19,10 +19,11 @@ ap.add_argument("--no-river", action="store_true")
 ap.add_argument("--levels", type=int, default=200)
 ap.add_argument("--series", default="", help="comma-separated land series to record ('all' = every hland_96 sequence)")
 ap.add_argument("--path", default="auto")
+ap.add_argument("--cflux", type=float, default=0.0)
 args = ap.parse_args()
 
 t = time.time()
-land, states = synth.make_land(args.elements, args.step)
+land, states = synth.make_land(args.elements, args.step, cflux=args.cflux)
 river, dis = synth.make_tree_river(args.elements, args.step, levels=args.levels)
 print(f"generated in {time.time()-t:.1f}s: zones={land.n_zone} reaches={river.n_reach} segs={river.n_seg}")
 eng = Engine(0)
