@@ -120,6 +120,87 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
   if (active && nt > 0) { n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp); }
   __syncthreads();
 
+  // Both roles run their own loop with the same sequence of block barriers (bar.sync on a named barrier, every warp takes
+  // exactly one of the two paths); separate loops let the compiler allocate registers per role instead of for the union.
+#define HB_BLOCK_BAR() asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory")
+  if (!zone_role) {
+    for (int t = 0; t < nt; ++t) {
+      HB_BLOCK_BAR();    // the terms of this step are complete
+      if (elem_role) {
+        double inuz = 0.0, contriarea = 1.0;
+        for (int kk = 0; kk < nz; ++kk) {
+          const int ztk = s_zt[kk * 32 + lane];
+          if (ztk == HB_FIELD || ztk == HB_FOREST) { inuz += s_a[kk * 32 + lane]; contriarea *= s_b[kk * 32 + lane]; }
+          else if (ztk == HB_GLACIER) inuz += s_a[kk * 32 + lane];
+        }
+        if (resp) contriarea = hb_pow(contriarea, beta_last, T);
+        // ref: hland_model.py:2456-2484 Calc_Q0_Perc_UZ_V1
+        double perc_sum = 0.0, q0_sum = 0.0;
+        {
+          const double uz_old = uz;
+          const double dt_inuz = dt * inuz;
+          const double perc_pot = dt_percmax * contriarea;
+          const double inv_ca = 1.0 / contriarea;
+          for (int i = 0; i < recstep; ++i) {
+            const double a = uz + dt_inuz;
+            uz = HB_PYMAX(a, 0.0);
+            const double perc = HB_PYMIN(perc_pot, uz);
+            uz -= perc;
+            perc_sum += perc;
+            if (uz > 0.0) {
+              double q0;
+              if (contriarea > 0.0) {
+                const double x = uz * inv_ca;
+                const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
+                q0 = HB_PYMIN(q, uz);
+              } else q0 = uz;
+              uz -= q0;
+              q0_sum += q0;
+            }
+          }
+          const double error = uz - (uz_old + inuz - perc_sum - q0_sum);
+          if (error > 0.0) {
+            const double factor = 1.0 - error / (perc_sum + q0_sum);
+            perc_sum *= factor;
+            q0_sum *= factor;
+          }
+        }
+        s_uz[lane] = uz;
+        // ref: hland_model.py:3113-3124 Calc_LZ_V1, 3724-3737 Calc_EL_LZ_AETModel_V1
+        if (rellower > 0.0) {
+          lz += up_low * perc_sum;
+          if (einfo & HB_EI_LAKE)
+            for (int kk = 0; kk < nz; ++kk)
+              if (s_zt[kk * 32 + lane] == HB_ILAKE) lz += s_a[kk * 32 + lane];
+        } else lz = 0.0;
+        if (einfo & HB_EI_LAKE)
+          for (int kk = 0; kk < nz; ++kk)
+            if (s_zt[kk * 32 + lane] == HB_ILAKE) lz -= s_b[kk * 32 + lane];
+        // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1
+        double q1 = 0.0;
+        if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
+        lz -= q1;
+        // ref: hland_model.py:3905-3912 Calc_InRC_V1
+        double inrc = relupper * q0_sum + rellower * q1;
+        if (einfo & HB_EI_SEALED)
+          for (int kk = 0; kk < nz; ++kk)
+            if (s_zt[kk * 32 + lane] == HB_SEALED) inrc += s_a[kk * 32 + lane];
+        // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
+        double outrc = inrc;
+        if (nu > 0) {
+          outrc = ldg(d.uh + e) * inrc + d.quh[e];
+          for (int j = 1; j < nu; ++j)
+            d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
+        }
+        // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
+        d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
+      }
+      HB_BLOCK_BAR();    // UZ of this step is published
+    }
+    if (elem_role) { d.uz[e] = uz; d.lz[e] = lz; }
+    return;
+  }
+
 #define tcorr CS(C_TCORR)
 #define tcalt_dz CS(C_TCALT_DZ)
 #define tt_hi CS(C_TT_HI)
@@ -152,14 +233,16 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
 #define g_var CS(C_G_VAR)
 #define tti CS(C_TTI)
 #define sf CS(C_SF)
-  for (int t = 0; t < nt; ++t) {
-    if (active) {
+  // A zone step is cut where it first reads UZ: `pre` (meteorology, snow, evaporation demand, R) of step t+1 runs while the
+  // element warp is busy with the RecStep chain of step t; `post` (capillary flux, soil evaporation, contributing area)
+  // follows once that UZ is published.
+  double c_tc = 0.0, c_pc = 0.0, c_in = 0.0, c_ncover = 0.0, c_pet = 0.0, c_aet = 0.0, c_r = 0.0;
+  auto pre = [&](int s_) {
       const double in_p = n_p, in_t = n_t, in_nat = n_nat, in_net = n_net, sinf = n_sin;
-      if (t + 1 < nt) {
+      if (s_ + 1 < nt) {
         fP += fstride; fT += fstride; fA += fstride; fE += fstride; ++sinp;
         n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp);
       }
-      const double uz_prev = s_uz[lane];
       // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
       const double tc = in_t + tcorr - tcalt_dz;
       double fracrain;
@@ -234,15 +317,25 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
       double s_ei = 0.0;
       if (icept) { s_ei = HB_PYMIN(aet_ie, ic); ic -= s_ei; }
       else ic = 0.0;
+      // ref: hland_model.py:1776-1790 Calc_R_SM_V1 (needs the soil moisture the previous step left behind — and that step's
+      // zone part is complete when this runs)
+      double r_ = in_;
+      if (soil && fc > 0.0) {
+        r_ = in_ * hb_pow(sm * inv_fc, beta, T);
+        const double a = sm + in_ - fc;
+        r_ = HB_PYMAX(r_, a);
+      }
+      c_tc = tc; c_pc = pc; c_in = in_; c_ncover = ncover; c_pet = pet; c_aet = aet_ie; c_r = r_;
+  };
+  if (active && nt > 0) pre(0);
+  for (int t = 0; t < nt; ++t) {
+    if (active) {
+      const double tc = c_tc, pc = c_pc, in_ = c_in, ncover = c_ncover, pet = c_pet, aet_ie = c_aet;
+      const double uz_prev = s_uz[lane];
+      (void)tc; (void)pc;
       double ta, tb = 1.0;
       if (soil) {
-        // ref: hland_model.py:1776-1790 Calc_R_SM_V1
-        double r;
-        if (fc > 0.0) {
-          r = in_ * hb_pow(sm * inv_fc, beta, T);
-          const double a = sm + in_ - fc;
-          r = HB_PYMAX(r, a);
-        } else r = in_;
+        double r = c_r;
         sm += in_ - r;
         // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 (uz_prev = UZ at the end of the previous step)
         double cf = 0.0;
@@ -289,77 +382,9 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
       s_a[k * 32 + lane] = ta;
       s_b[k * 32 + lane] = tb;
     }
-    __syncthreads();   // the terms of this step are complete
-    if (elem_role) {
-      double inuz = 0.0, contriarea = 1.0;
-      for (int kk = 0; kk < nz; ++kk) {
-        const int ztk = s_zt[kk * 32 + lane];
-        if (ztk == HB_FIELD || ztk == HB_FOREST) { inuz += s_a[kk * 32 + lane]; contriarea *= s_b[kk * 32 + lane]; }
-        else if (ztk == HB_GLACIER) inuz += s_a[kk * 32 + lane];
-      }
-      if (resp) contriarea = hb_pow(contriarea, beta_last, T);
-      // ref: hland_model.py:2456-2484 Calc_Q0_Perc_UZ_V1
-      double perc_sum = 0.0, q0_sum = 0.0;
-      {
-        const double uz_old = uz;
-        const double dt_inuz = dt * inuz;
-        const double perc_pot = dt_percmax * contriarea;
-        const double inv_ca = 1.0 / contriarea;
-        for (int i = 0; i < recstep; ++i) {
-          const double a = uz + dt_inuz;
-          uz = HB_PYMAX(a, 0.0);
-          const double perc = HB_PYMIN(perc_pot, uz);
-          uz -= perc;
-          perc_sum += perc;
-          if (uz > 0.0) {
-            double q0;
-            if (contriarea > 0.0) {
-              const double x = uz * inv_ca;
-              const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
-              q0 = HB_PYMIN(q, uz);
-            } else q0 = uz;
-            uz -= q0;
-            q0_sum += q0;
-          }
-        }
-        const double error = uz - (uz_old + inuz - perc_sum - q0_sum);
-        if (error > 0.0) {
-          const double factor = 1.0 - error / (perc_sum + q0_sum);
-          perc_sum *= factor;
-          q0_sum *= factor;
-        }
-      }
-      s_uz[lane] = uz;
-      // ref: hland_model.py:3113-3124 Calc_LZ_V1, 3724-3737 Calc_EL_LZ_AETModel_V1
-      if (rellower > 0.0) {
-        lz += up_low * perc_sum;
-        if (einfo & HB_EI_LAKE)
-          for (int kk = 0; kk < nz; ++kk)
-            if (s_zt[kk * 32 + lane] == HB_ILAKE) lz += s_a[kk * 32 + lane];
-      } else lz = 0.0;
-      if (einfo & HB_EI_LAKE)
-        for (int kk = 0; kk < nz; ++kk)
-          if (s_zt[kk * 32 + lane] == HB_ILAKE) lz -= s_b[kk * 32 + lane];
-      // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1
-      double q1 = 0.0;
-      if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
-      lz -= q1;
-      // ref: hland_model.py:3905-3912 Calc_InRC_V1
-      double inrc = relupper * q0_sum + rellower * q1;
-      if (einfo & HB_EI_SEALED)
-        for (int kk = 0; kk < nz; ++kk)
-          if (s_zt[kk * 32 + lane] == HB_SEALED) inrc += s_a[kk * 32 + lane];
-      // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-      double outrc = inrc;
-      if (nu > 0) {
-        outrc = ldg(d.uh + e) * inrc + d.quh[e];
-        for (int j = 1; j < nu; ++j)
-          d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
-      }
-      // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
-      d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
-    }
-    __syncthreads();   // UZ of this step is published, the term buffers are free again
+    HB_BLOCK_BAR();    // the terms of this step are complete
+    if (active && t + 1 < nt) pre(t + 1);
+    HB_BLOCK_BAR();    // UZ of this step is published, the term buffers are free again
   }
 #undef tcorr
 #undef tcalt_dz
@@ -395,7 +420,7 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
 #undef sf
 #undef CS
   if (active) { d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc; }
-  if (elem_role) { d.uz[e] = uz; d.lz[e] = lz; }
+#undef HB_BLOCK_BAR
 }
 
 }  // namespace hb
