@@ -84,7 +84,7 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 // Calc_EL_LZ_V1 / Calc_InRC_V1)
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef HB_ZONE_BLOCKS
-#define HB_ZONE_BLOCKS 4
+#define HB_ZONE_BLOCKS 7
 #endif
 // SOIL = true : the warps whose 32 zones are all FIELD/FOREST with FC > 0 (branch-free step); SOIL = false: all other warps
 // SERIES = true additionally records the requested hland_96 zone sequences (the HBM-bound regime of SURVEY.md §8d-ii)
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
   const bool soil = (zt == HB_FIELD) || (zt == HB_FOREST);
   const bool icept = soil || (zt == HB_SEALED);        // zone types with an interception storage
   const bool resp = (einfo & HB_EI_RESPAREA) != 0;
-  // ---- constants → registers (coalesced: consecutive lanes = consecutive elements) ----
+  // ---- constants (coalesced loads: consecutive lanes = consecutive elements) ----
   const double tcorr = KZ(KZ_TCORR), tcalt_dz = KZ(KZ_TCALT_DZ), tt_hi = KZ(KZ_TT_HI), tt_lo = KZ(KZ_TT_LO),
                inv_ttint = KZ(KZ_INV_TTINT), pcalt_f = KZ(KZ_PCALT_F), pcorr = KZ(KZ_PCORR), inv_rfcf = KZ(KZ_INV_RFCF),
                inv_sfcf = KZ(KZ_INV_SFCF), icmax = KZ(KZ_ICMAX), cfmax = KZ(KZ_CFMAX), cfvar = KZ(KZ_CFVAR),
@@ -123,6 +123,66 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 #undef KZ
   const double sf = d.sfdist[e];
   double ic = d.ic[slot], sm = d.sm[slot], sp = d.sp[slot], wc = d.wc[slot];
+  // The constants move on to shared memory ([constant][thread], conflict-free, 29 KB per block): 72 registers per thread
+  // instead of 128, 7 instead of 4 warps per scheduler, and room for the routing blocks of the previous window beside them.
+  // (ncu: the step is then issue-bound — ≈410 warp instructions per zone-step at ≈80 % issue-slot utilisation.)
+  __shared__ double s_c[28][128];
+  s_c[0][threadIdx.x] = tcorr;
+  s_c[1][threadIdx.x] = tcalt_dz;
+  s_c[2][threadIdx.x] = tt_hi;
+  s_c[3][threadIdx.x] = tt_lo;
+  s_c[4][threadIdx.x] = inv_ttint;
+  s_c[5][threadIdx.x] = pcalt_f;
+  s_c[6][threadIdx.x] = pcorr;
+  s_c[7][threadIdx.x] = inv_rfcf;
+  s_c[8][threadIdx.x] = inv_sfcf;
+  s_c[9][threadIdx.x] = icmax;
+  s_c[10][threadIdx.x] = cfmax;
+  s_c[11][threadIdx.x] = cfvar;
+  s_c[12][threadIdx.x] = ttm;
+  s_c[13][threadIdx.x] = cfr_cfmax;
+  s_c[14][threadIdx.x] = whc;
+  s_c[15][threadIdx.x] = fc;
+  s_c[16][threadIdx.x] = inv_fc;
+  s_c[17][threadIdx.x] = beta;
+  s_c[18][threadIdx.x] = thresh;
+  s_c[19][threadIdx.x] = inv_thresh;
+  s_c[20][threadIdx.x] = excessred;
+  s_c[21][threadIdx.x] = atf;
+  s_c[22][threadIdx.x] = etf;
+  s_c[23][threadIdx.x] = alt_f;
+  s_c[24][threadIdx.x] = neg_pf;
+  s_c[25][threadIdx.x] = w_a;
+  s_c[26][threadIdx.x] = w_b;
+  s_c[27][threadIdx.x] = sf;
+#define tcorr s_c[0][threadIdx.x]
+#define tcalt_dz s_c[1][threadIdx.x]
+#define tt_hi s_c[2][threadIdx.x]
+#define tt_lo s_c[3][threadIdx.x]
+#define inv_ttint s_c[4][threadIdx.x]
+#define pcalt_f s_c[5][threadIdx.x]
+#define pcorr s_c[6][threadIdx.x]
+#define inv_rfcf s_c[7][threadIdx.x]
+#define inv_sfcf s_c[8][threadIdx.x]
+#define icmax s_c[9][threadIdx.x]
+#define cfmax s_c[10][threadIdx.x]
+#define cfvar s_c[11][threadIdx.x]
+#define ttm s_c[12][threadIdx.x]
+#define cfr_cfmax s_c[13][threadIdx.x]
+#define whc s_c[14][threadIdx.x]
+#define fc s_c[15][threadIdx.x]
+#define inv_fc s_c[16][threadIdx.x]
+#define beta s_c[17][threadIdx.x]
+#define thresh s_c[18][threadIdx.x]
+#define inv_thresh s_c[19][threadIdx.x]
+#define excessred s_c[20][threadIdx.x]
+#define atf s_c[21][threadIdx.x]
+#define etf s_c[22][threadIdx.x]
+#define alt_f s_c[23][threadIdx.x]
+#define neg_pf s_c[24][threadIdx.x]
+#define w_a s_c[25][threadIdx.x]
+#define w_b s_c[26][threadIdx.x]
+#define sf s_c[27][threadIdx.x]
 
   const int64_t col = d.fcol[e];
   // all per-step addresses advance by pointer bumps (no 64-bit multiplies in the loop)
@@ -410,6 +470,34 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 #undef HB_ZONE_STEP_END
 #undef SERZ
 #undef SERS
+#undef tcorr
+#undef tcalt_dz
+#undef tt_hi
+#undef tt_lo
+#undef inv_ttint
+#undef pcalt_f
+#undef pcorr
+#undef inv_rfcf
+#undef inv_sfcf
+#undef icmax
+#undef cfmax
+#undef cfvar
+#undef ttm
+#undef cfr_cfmax
+#undef whc
+#undef fc
+#undef inv_fc
+#undef beta
+#undef thresh
+#undef inv_thresh
+#undef excessred
+#undef atf
+#undef etf
+#undef alt_f
+#undef neg_pf
+#undef w_a
+#undef w_b
+#undef sf
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
 }
 
