@@ -84,7 +84,7 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 // Calc_EL_LZ_V1 / Calc_InRC_V1)
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef HB_ZONE_BLOCKS
-#define HB_ZONE_BLOCKS 7
+#define HB_ZONE_BLOCKS 6
 #endif
 // SOIL = true : the warps whose 32 zones are all FIELD/FOREST with FC > 0 (branch-free step); SOIL = false: all other warps
 // SERIES = true additionally records the requested hland_96 zone sequences (the HBM-bound regime of SURVEY.md §8d-ii)
@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       fracrain = (tc <= tt_lo) ? 0.0 : fracrain;
       fracrain = (tc >= tt_hi) ? 1.0 : fracrain;
       const double pc0 = in_p * pcalt_f;
-      double pc = pc0 * (pcorr / (fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf));
+      // pcorr/x as pcorr * rcp(x), rcp correctly rounded (<= 1 ulp from the division, a third of its instructions)
+      double pc = pc0 * (pcorr * __drcp_rn(fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf));
       pc = (pc0 <= 0.0) ? 0.0 : pc;
       // ref: hland_model.py:299-309 Calc_TF_Ic_V1
       const double a = pc - (icmax - ic);
