@@ -427,6 +427,8 @@ def auto_cpu_elements(args: argparse.Namespace) -> int:
 
 
 def main() -> None:
+    # NCCL prints its version banner (and NCCL_DEBUG output) to stdout by default; stdout carries the ONE JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     dist = Dist()
     if args.gpus != dist.world and dist.world > 1:
