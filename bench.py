@@ -427,8 +427,18 @@ def auto_cpu_elements(args: argparse.Namespace) -> int:
 
 
 def main() -> None:
-    # NCCL prints its version banner (and NCCL_DEBUG output) to stdout by default; stdout carries the ONE JSON line only
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the ONE JSON line only: whatever native libraries print (NCCL's version banner, NCCL_DEBUG output)
+    # goes to stderr — file descriptor 1 points to stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     args = parse_args()
     dist = Dist()
     if args.gpus != dist.world and dist.world > 1:
@@ -449,14 +459,14 @@ def main() -> None:
                     "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0,
                 }
-                print(json.dumps(line), flush=True)
+                emit(line)
             return
         result = run_engine(args, dist)
         if dist.rank == 0:
             if dist.world == 1 and not args.no_cpu_baseline:
                 base = cpu_run(args, steps=2, warmup=1, elements=auto_cpu_elements(args))
                 result["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            print(json.dumps(result), flush=True)
+            emit(result)
     finally:
         dist.close()
 
