@@ -99,7 +99,11 @@ struct hb_engine {
   // Three streams form the window pipeline: runoff generation of window w+1 (stream) overlaps routing of window w
   // (s_river) and the device→host copy of its node series (s_copy).  All per-window buffers exist twice; `cur` is the
   // set of the window staged last (it flips in hb_set_forcing / hb_select_window).
-  cudaStream_t stream = nullptr, s_river = nullptr, s_copy = nullptr;
+  cudaStream_t stream = nullptr, s_river = nullptr, s_copy = nullptr, s_comm = nullptr;
+  cudaEvent_t ev_ext_ready[2] = {nullptr, nullptr};   // boundary rows of the window have arrived (NCCL, s_comm)
+  cudaEvent_t ev_send_done[2] = {nullptr, nullptr};   // boundary rows of the window have left (their buffers may be reused)
+  bool ext_async[2] = {false, false};                 // … and the routing of that window has to wait for them
+  bool ext_feeds_reach = true;                        // false: external rows only enter nodes without a downstream reach
   int cur = 0;
   cudaEvent_t ev_land_done[2] = {nullptr, nullptr}, ev_river_done[2] = {nullptr, nullptr},
               ev_copy_done[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
@@ -279,6 +283,11 @@ int hb_create(int device, hb_engine** out) {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStreamCreateWithPriority(&h->s_river, cudaStreamNonBlocking, hi);
     cudaStreamCreateWithPriority(&h->s_copy, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&h->ev_ext_ready[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_ext_ready[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_send_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_send_done[1], cudaEventDisableTiming);
   }
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&h->ev_land_done[i], cudaEventDisableTiming);
@@ -313,6 +322,7 @@ void hb_destroy(hb_engine* h) {
   cudaStreamSynchronize(h->stream);
   if (h->s_river) cudaStreamSynchronize(h->s_river);
   if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+  if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -324,6 +334,9 @@ void hb_destroy(hb_engine* h) {
   if (h->h_wave_err) cudaFreeHost(h->h_wave_err);
   if (h->s_river) cudaStreamDestroy(h->s_river);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_comm) cudaStreamDestroy(h->s_comm);
+  for (cudaEvent_t e : {h->ev_ext_ready[0], h->ev_ext_ready[1], h->ev_send_done[0], h->ev_send_done[1]})
+    if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -754,6 +767,13 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     else node_owner[n] = node_exits[n][0];
   }
   h->n_terminal = (int64_t)terminal.size();
+  h->ext_feeds_reach = false;
+  for (int64_t n = 0; n < nn; ++n) {
+    if (node_exits[n].empty()) continue;
+    if (r->node_mode[n] != HB_NODE_NEWSIM) h->ext_feeds_reach = true;
+    for (int64_t i = r->entry_ptr[n]; i < r->entry_ptr[n + 1]; ++i)
+      if (r->entry_src[i] <= HB_ENTRY_EXT) h->ext_feeds_reach = true;
+  }
   // headwater reaches (level 0, at most HB_BULK_SMAX segments) are handled by two plain launches; the rest forms the
   // wavefront: sorted by level (and by segments within a level), with the list of reaches each one waits for
   std::vector<int32_t> head_all, head_bulk, wave_order, wave_lvl(nlev + 1, 0), dep_reach;
@@ -1119,6 +1139,12 @@ static int run_river(hb_engine* h) {
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
   d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
   int64_t launches = 0;
+  // boundary rows received over NCCL (s_comm): the whole routing waits only if some reach reads external rows;
+  // otherwise just the final sums of the outlet nodes do
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_river, h->ev_send_done[h->cur], 0));   // rows of two windows ago are on their way
+  const bool ext_pending = h->ext_async[h->cur];
+  h->ext_async[h->cur] = false;
+  if (ext_pending && h->ext_feeds_reach) HB_CUDA(h, cudaStreamWaitEvent(h->s_river, h->ev_ext_ready[h->cur], 0));
   if (nt > 0 && h->n_reach > 0 && h->river_sweep == HB_RIVER_LAUNCHES) {
     // one launch per anti-diagonal of the (level, chunk) grid: launch `diag` works on the reaches of level l at chunk diag - l
     for (int diag = 0; diag < nlev + n_chunks - 1; ++diag) {
@@ -1180,6 +1206,7 @@ static int run_river(hb_engine* h) {
     }
   }
   if (nt > 0 && h->n_reach > 0) h->dis_cur = (h->dis_cur + n_chunks) & 1;
+  if (ext_pending && !h->ext_feeds_reach) HB_CUDA(h, cudaStreamWaitEvent(h->s_river, h->ev_ext_ready[h->cur], 0));
   if (nt > 0 && h->n_terminal > 0) {
     const int block = 256, grid = (int)((h->n_terminal * 32 + block - 1) / block);
     node_sum_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_terminal_nodes.p, (int)h->n_terminal);
@@ -1255,6 +1282,7 @@ int hb_wait(hb_engine* h) {
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->s_river));
   HB_CUDA(h, cudaStreamSynchronize(h->s_copy));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_comm));
   int rc;
   if ((rc = resolve_marks(h, h->land_marks, true)) || (rc = resolve_marks(h, h->river_marks, false))) return rc;
   h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
@@ -1319,6 +1347,8 @@ static int join_streams(hb_engine* h) {
   HB_CUDA(h, cudaEventRecord(h->ev_join[1], h->s_copy));
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+  HB_CUDA(h, cudaEventRecord(h->ev_join[0], h->s_comm));   // (the wait above already holds the first recording)
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
   return HB_OK;
 }
 
@@ -1504,11 +1534,15 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
   const double* base = kind == HB_ROW_NODE ? h->d_node_rows[h->cur].p : h->d_reach_out[h->cur].p;
   for (int64_t i = 0; i < n; ++i)
     HB_REQUIRE(h, rows[i] >= 0 && rows[i] < limit, HB_EINVAL, "hb_comm_send_rows: row %d out of range", rows[i]);
+  // all NCCL traffic of this engine runs on ONE stream (s_comm); the send waits for the routing of the window
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
   HB_NCCL(h, h->nccl.GroupStart());
   // the routing kernels wrote the rows in place: they are sent straight from the result buffers over NVLink
   for (int64_t i = 0; i < n; ++i)
-    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->s_river));
+    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
   HB_NCCL(h, h->nccl.GroupEnd());
+  HB_CUDA(h, cudaEventRecord(h->ev_send_done[h->cur], h->s_comm));
+  h->pending = true;
   return HB_OK;
 }
 
@@ -1520,15 +1554,20 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
              "hb_comm_recv_ext: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
   HB_CUDA(h, h->d_ext_rows[h->cur].reserve((size_t)h->n_ext * h->nt));
+  // the routing of two windows ago was the last reader of this buffer set
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
   HB_NCCL(h, h->nccl.GroupStart());
   for (int64_t i = 0; i < n; ++i) {
     HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row out of range");
     // received straight into the external-row buffer the reach kernels read
     HB_NCCL(h, h->nccl.Recv(h->d_ext_rows[h->cur].p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
-                            h->s_river));
+                            h->s_comm));
   }
   HB_NCCL(h, h->nccl.GroupEnd());
+  HB_CUDA(h, cudaEventRecord(h->ev_ext_ready[h->cur], h->s_comm));
+  h->ext_async[h->cur] = true;
   h->have_ext = true;
+  h->pending = true;
   return HB_OK;
 }
 
@@ -1537,9 +1576,9 @@ int hb_comm_barrier(hb_engine* h) {
   HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_barrier: call hb_comm_init first");
   HB_CUDA(h, cudaSetDevice(h->device));
   HB_CUDA(h, h->d_commbuf.reserve(1));
-  HB_CUDA(h, cudaMemsetAsync(h->d_commbuf.p, 0, sizeof(double), h->stream));
-  HB_NCCL(h, h->nccl.AllReduce(h->d_commbuf.p, h->d_commbuf.p, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
-  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->d_commbuf.p, 0, sizeof(double), h->s_comm));
+  HB_NCCL(h, h->nccl.AllReduce(h->d_commbuf.p, h->d_commbuf.p, 1, kNcclFloat64, kNcclSum, h->comm, h->s_comm));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_comm));
   return HB_OK;
 }
 
