@@ -192,8 +192,23 @@ def build_shard(args: argparse.Namespace, rank: int, world: int):
     return land, states, river, discharge
 
 
+def pin_to_gpu_numa_node(device: int) -> None:
+    """Run this rank (and allocate its pinned staging buffers) on the CPU cores next to its GPU: with 8 ranks the
+    device→host copies of the e2e loop otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device))
+    except Exception:   # no NVML, no permission, single-socket box: nothing to gain
+        pass
+
+
 def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     from hydpy_b200 import Engine, synth
+
+    if dist.world > 1:
+        pin_to_gpu_numa_node(dist.local_rank)
 
     K, W, win = args.steps, args.warmup, args.window
     eng = Engine(dist.local_rank)
