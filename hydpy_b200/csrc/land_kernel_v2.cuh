@@ -595,21 +595,39 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       const double dt_inuz = dt * inuz;
       const double perc_pot = dt_percmax * contriarea;
       const double inv_ca = 1.0 / contriarea;
-      for (int i = 0; i < recstep; ++i) {
-        const double a = uz + dt_inuz;
-        uz = HB_PYMAX(a, 0.0);
-        const double perc = HB_PYMIN(perc_pot, uz);
-        uz -= perc;
-        perc_sum += perc;
-        if (uz > 0.0) {
-          double q0;
-          if (contriarea > 0.0) {
-            const double x = uz * inv_ca;
-            const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
-            q0 = HB_PYMIN(q, uz);
-          } else q0 = uz;
-          uz -= q0;
-          q0_sum += q0;
+      // every instruction of this loop sits on one dependent chain (ncu: ≈9.5 cycles per instruction), so the loop is
+      // unswitched on its step-invariant conditions when the whole warp agrees on them — the usual case
+      if (__all_sync(__activemask(), contriarea > 0.0 && !square)) {
+        for (int i = 0; i < recstep; ++i) {
+          const double a = uz + dt_inuz;
+          uz = HB_PYMAX(a, 0.0);
+          const double perc = HB_PYMIN(perc_pot, uz);
+          uz -= perc;
+          perc_sum += perc;
+          if (uz > 0.0) {
+            const double q = dt_k * hb_pow(uz * inv_ca, alpha1, T);
+            const double q0 = HB_PYMIN(q, uz);
+            uz -= q0;
+            q0_sum += q0;
+          }
+        }
+      } else {
+        for (int i = 0; i < recstep; ++i) {
+          const double a = uz + dt_inuz;
+          uz = HB_PYMAX(a, 0.0);
+          const double perc = HB_PYMIN(perc_pot, uz);
+          uz -= perc;
+          perc_sum += perc;
+          if (uz > 0.0) {
+            double q0;
+            if (contriarea > 0.0) {
+              const double x = uz * inv_ca;
+              const double q = dt_k * (square ? x * x : hb_pow(x, alpha1, T));
+              q0 = HB_PYMIN(q, uz);
+            } else q0 = uz;
+            uz -= q0;
+            q0_sum += q0;
+          }
         }
       }
       const double error = uz - (uz_old + inuz - perc_sum - q0_sum);
