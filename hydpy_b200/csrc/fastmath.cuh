@@ -64,7 +64,7 @@ HB_HD double hb_make(int hi, int lo) {
 #define HB_EXP_TABLE_BITS 6
 #define HB_EXP_N (1 << HB_EXP_TABLE_BITS)
 
-struct MathTables {
+struct MathTables {   // (hb_ld_log / hb_ld_exp rely on this layout)
   double log_tab[HB_LOG_N][2];   // {1/c_k rounded to double, -log of that ROUNDED reciprocal}: one 16-byte look-up
   double exp2[HB_EXP_N];         // 2^(j/64)
 };
@@ -77,6 +77,42 @@ inline void make_math_tables(MathTables& t) {
     t.log_tab[k][1] = (k == 0) ? 0.0 : (double)(-logl((long double)t.log_tab[k][0]));
   }
   for (int j = 0; j < HB_EXP_N; ++j) t.exp2[j] = (double)exp2l((long double)j / HB_EXP_N);
+}
+
+// Handle of the tables inside a kernel.  On the device it is the 32-bit shared-memory address of the block's copy: the
+// look-ups become `ld.shared` with a register base — through a generic pointer the compiler re-derives the shared window
+// (S2UR + ULEA) at every look-up, three instructions on the dependent chain of the RecStep loop.
+struct TabRef {
+#ifdef __CUDA_ARCH__
+  uint32_t base;
+#else
+  const MathTables* p;
+#endif
+};
+HB_HD TabRef hb_tabref(const MathTables* T) {
+  TabRef t;
+#ifdef __CUDA_ARCH__
+  t.base = (uint32_t)__cvta_generic_to_shared(T);
+#else
+  t.p = T;
+#endif
+  return t;
+}
+HB_HD void hb_ld_log(TabRef t, int k, double& invc, double& logc) {
+#ifdef __CUDA_ARCH__
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(t.base + (uint32_t)k * 16u));
+#else
+  invc = t.p->log_tab[k][0]; logc = t.p->log_tab[k][1];
+#endif
+}
+HB_HD double hb_ld_exp(TabRef t, int j) {
+#ifdef __CUDA_ARCH__
+  double s;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(t.base + (uint32_t)(HB_LOG_N * 16) + (uint32_t)j * 8u));
+  return s;
+#else
+  return t.p->exp2[j];
+#endif
 }
 
 // literals (see "instruction economy" above)
@@ -99,13 +135,14 @@ static const double hb_math_k_host[HB_K_COUNT] = HB_MATH_LITERALS;
 #define HB_LIT(i) hb_math_k_host[i]
 #endif
 
-HB_HD double hb_log_normal(double x, const MathTables* __restrict__ T) {
+HB_HD double hb_log_normal(double x, TabRef T) {
   // x must be a positive normal number (for anything else the result is garbage, but the evaluation is harmless)
   const int hi = hb_hi(x), lo = hb_lo(x);
   const int e = (hi >> 20) - 1023;
   const int k = ((hi & 0x000fffff) + (1 << (19 - HB_LOG_TABLE_BITS))) >> (20 - HB_LOG_TABLE_BITS);   // nearest centre
   const double m = hb_make((hi & 0x000fffff) | 0x3ff00000, lo);  // [1, 2)
-  const double invc = T->log_tab[k][0], logc = T->log_tab[k][1];
+  double invc, logc;
+  hb_ld_log(T, k, invc, logc);
   const double r = fma(m, invc, -1.0);
   const double r2 = r * r;
   // log1p(r) = r + r^2*(-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7)
@@ -119,7 +156,7 @@ HB_HD double hb_log_normal(double x, const MathTables* __restrict__ T) {
   return fma(de, HB_LIT(HB_K_LN2HI), logc) + fma(de, HB_LIT(HB_K_LN2LO), tail);
 }
 
-HB_HD double hb_exp_bounded(double t, const MathTables* __restrict__ T) {
+HB_HD double hb_exp_bounded(double t, TabRef T) {
   // |t| < 690: the result is a normal number (for anything else the result is garbage, but the evaluation is harmless)
   const double shift = 6755399441055744.0;          // 1.5 * 2^52
   const double kd = fma(t, HB_LIT(HB_K_INV), shift);
@@ -127,7 +164,7 @@ HB_HD double hb_exp_bounded(double t, const MathTables* __restrict__ T) {
   const double n = kd - shift;
   double r = fma(n, -HB_LIT(HB_K_L64HI), t);
   r = fma(n, -HB_LIT(HB_K_L64LO), r);
-  const double s = T->exp2[ki & (HB_EXP_N - 1)];
+  const double s = hb_ld_exp(T, ki & (HB_EXP_N - 1));
   const int q = ki >> HB_EXP_TABLE_BITS;
   const double r2 = r * r;
   double p = fma(r, HB_LIT(HB_K_E5), HB_LIT(HB_K_E4));
@@ -144,7 +181,7 @@ __device__ __noinline__ double hb_pow_slow(double x, double y) { return pow(x, y
 __device__ __noinline__ double hb_exp_slow(double t) { return exp(t); }
 #endif
 
-HB_HD double hb_exp(double t, const MathTables* __restrict__ T) {
+HB_HD double hb_exp(double t, TabRef T) {
   const double r = hb_exp_bounded(t, T);
   if (fabs(t) < 690.0) return r;
 #ifdef __CUDA_ARCH__
@@ -154,7 +191,7 @@ HB_HD double hb_exp(double t, const MathTables* __restrict__ T) {
 #endif
 }
 
-HB_HD double hb_pow(double x, double y, const MathTables* __restrict__ T) {
+HB_HD double hb_pow(double x, double y, TabRef T) {
   // positive normal x: 0x00100000 <= hi < 0x7ff00000
   const bool ok_x = (unsigned)(hb_hi(x) - 0x00100000) < 0x7fe00000u;
   const double t = y * hb_log_normal(x, T);

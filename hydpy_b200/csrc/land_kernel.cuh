@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
     for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const MathTables* T = &s_tables;
+  const TabRef T = hb_tabref(&s_tables);
   const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= d.n_list) return;
   const int64_t e = d.elist ? (int64_t)d.elist[li] : li;

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(MAXT, MINB) coupled_kernel(const LandV2Dev d) 
   __shared__ MathTables s_tables;
   extern __shared__ double c_smem[];   // term_a[zw][32], term_b[zw][32], uz[32], int ztype[zw][32], constants[C_COUNT][zw*32]
   stage_tables(&s_tables, d.tables);
-  const MathTables* T = &s_tables;
+  const TabRef T = hb_tabref(&s_tables);
   const int zw = (int)(blockDim.x >> 5) - 1;            // zone warps
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* s_a = c_smem;

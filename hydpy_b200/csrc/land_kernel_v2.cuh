@@ -92,7 +92,7 @@ template <bool SOIL, bool SERIES>
 __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
-  const MathTables* T = &s_tables;
+  const TabRef T = hb_tabref(&s_tables);
   const int64_t ep = d.e_pad;
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // k*E_pad + e
   const int k = (int)(slot / ep);
@@ -541,7 +541,7 @@ template <bool SERIES>
 __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
-  const MathTables* T = &s_tables;
+  const TabRef T = hb_tabref(&s_tables);
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.n_elem) return;
   const int einfo = d.einfo[e];
