@@ -309,6 +309,19 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     states_after_e2e = eng.get_land_states()
     same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
 
+    # ================= the same kernels timed alone (synchronous windows, nothing overlapping) ===========================
+    iso = {"zone_ms": 0.0, "element_ms": 0.0, "general_ms": 0.0, "river_ms": 0.0}
+    n_iso = 3
+    if dist.world == 1:
+        eng.set_forcing(np.ascontiguousarray(np.concatenate(list(pinned.array[:n_iso]), axis=1)), doys[:n_iso].reshape(-1))
+        eng.timing()
+        for s in range(n_iso):
+            eng.select_window(s * win, win)
+            eng.set_external(no_ext)
+            eng.run(land=True, river=True)
+        t_iso = eng.timing()
+        iso = {k: t_iso[k] / n_iso for k in iso}
+
     # ================= roofline of the dominant kernel ====================================================================
     # Discharge-only mode moves 40 B per element-step, so the bound is the FP64 pipe.
     # Algorithmic work, SURVEY's convention (add/mul/cmp/div/pow/exp = 1 op each): 130 ops per zone-step in the
@@ -327,14 +340,16 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     kernels = {
         "zone_kernel": {"ms": zone_ms_avg, "ops_per_launch": zone_ops, "achieved": tops(zone_ops, zone_ms_avg),
                         "frac": tops(zone_ops, zone_ms_avg) / peak_ops,
+                        "ms_alone": iso["zone_ms"], "frac_alone": tops(zone_ops, iso["zone_ms"]) / peak_ops,
                         "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 40 * land.n_elem * win},
         "element_kernel": {"ms": element_ms_avg, "ops_per_launch": element_ops,
                            "achieved": tops(element_ops, element_ms_avg),
                            "frac": tops(element_ops, element_ms_avg) / peak_ops,
+                           "ms_alone": iso["element_ms"], "frac_alone": tops(element_ops, iso["element_ms"]) / peak_ops,
                            "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win},
         "land_kernel (general)": {"ms": general_ms_avg},
         "routing (reach_head + reach_bulk + reach_wave kernels)": {
-            "ms": float(np.mean(river_ms)),
+            "ms": float(np.mean(river_ms)), "ms_alone": iso["river_ms"],
             "algorithmic_bytes_per_step": 16 * river.n_reach * win + 8 * (river.n_node + land.n_elem) * win},
     }
     dominant = "zone_kernel" if n_fast else "land_kernel (general)"
@@ -372,8 +387,11 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         "roofline": {
             "bound": "fp64", "achieved": achieved_tops, "peak": peak_ops, "unit": "Top/s (FP64 ops, FMA = 1)",
             "frac": achieved_tops / peak_ops, "traffic": traffic,
+            "frac_alone": (kernels["zone_kernel"]["frac_alone"] if n_fast else None),
             "kernel": dominant, "ops_per_launch": dom_ops,
             "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
+            "note": "ms/frac: CUDA events inside the timed, pipelined region (routing of the previous window shares the "
+                    "SMs); ms_alone/frac_alone: the same kernels in synchronous windows right after it",
             "fp64_tflops_measured": fp64_peak,
             "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
