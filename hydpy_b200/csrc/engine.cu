@@ -861,6 +861,7 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     return rc;
   HB_CUDA(h, h->d_progress.reserve((size_t)nr));
   HB_CUDA(h, h->d_wave_ctl.reserve(2));
+  HB_CUDA(h, cudaMemset(h->d_wave_ctl.p, 0, 2 * sizeof(int)));
   if (!h->h_wave_err) HB_CUDA(h, cudaHostAlloc((void**)&h->h_wave_err, sizeof(int), cudaHostAllocDefault));
   *h->h_wave_err = 0;
   HB_CUDA(h, h->d_dis[0].reserve((size_t)r->n_seg));
@@ -1289,6 +1290,7 @@ int hb_wait(hb_engine* h) {
   h->pending = false;
   if (h->h_wave_err && *h->h_wave_err) {
     *h->h_wave_err = 0;
+    cudaMemset(h->d_wave_ctl.p, 0, 2 * sizeof(int));
     return h->fail(HB_ECUDA, "routing wavefront: a task waited beyond the spin limit for its upstream reaches "
                              "(results of this window are invalid; HB_OPT_RIVER_SWEEP = HB_RIVER_LAUNCHES avoids the "
                              "persistent kernel)");

@@ -410,10 +410,10 @@ __global__ void __launch_bounds__(32 * HB_BULK_WARPS) reach_bulk_kernel(const Ri
 }
 
 // ---- persistent wavefront ------------------------------------------------------------------------------------------------
-// queue head and error flag = 0; progress = 0 everywhere, then = n_chunks for the reaches the head kernels complete
+// queue head = 0; progress = 0 everywhere, then = n_chunks for the reaches the head kernels complete
 __global__ void wave_init_kernel(const RiverDev d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { *d.counter = 0; *d.error = 0; }
+  if (i == 0) *d.counter = 0;   // (the error flag is sticky: hb_wait reports and clears it)
   if (i < d.n_reach) d.progress[i] = 0;
 }
 __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restrict__ head, int n_head) {
