@@ -6,6 +6,8 @@ Public API:
     Engine                  1:1 Python face of the C-ABI (`include/hydpy_b200.h`)
     extract / Problem       HydPy objects → SoA bundles
     synth                   synthetic basins of BASELINE.json's configs (bulk SoA API)
+    shard                   element sharding over several GPUs + the NCCL exchange plan
+    calib                   nse/kge/rmse of calibration ensembles from device-reduced statistics
 """
 from .abi import LandBundle, LandStates, RiverBundle
 from .engine import Engine, EngineError, EngineUnavailable, device_count

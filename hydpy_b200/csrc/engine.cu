@@ -179,6 +179,8 @@ struct hb_engine {
   DBuf<int64_t> d_dep_ptr;
   DBuf<ReachMeta> d_reach_meta;
   DBuf<int32_t> d_wave_rec;
+  DBuf<double> d_obs, d_stats;
+  DBuf<int32_t> d_stat_nodes, d_stat_rows;
   DBuf<int> d_progress, d_wave_ctl;     // d_wave_ctl = {queue head, error flag}
   std::vector<int32_t> wave_lvl_ptr;    // [n_levels+1]
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
@@ -1458,6 +1460,32 @@ int hb_get_node_series(hb_engine* h, int64_t n_sel, const int32_t* nodes, double
 int hb_get_node_series_async(hb_engine* h, int64_t n_sel, const int32_t* nodes, double* rows) {
   if (!h) return HB_EINVAL;
   return node_series(h, n_sel, nodes, rows, true);
+}
+
+int hb_node_statistics(hb_engine* h, int64_t n_pair, const int32_t* nodes, const int32_t* obs_row, int64_t n_obs,
+                       const double* obs, int skip_nan, double* out) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_node_statistics: no routing results (call hb_run)");
+  HB_REQUIRE(h, n_pair >= 0 && n_obs >= 0 && (n_pair == 0 || (nodes && obs_row && obs && out)), HB_EINVAL,
+             "hb_node_statistics: invalid argument");
+  for (int64_t i = 0; i < n_pair; ++i)
+    HB_REQUIRE(h, nodes[i] >= 0 && nodes[i] < h->n_node && obs_row[i] >= 0 && obs_row[i] < n_obs, HB_EINVAL,
+               "hb_node_statistics: pair %lld refers to node %d / observation row %d", (long long)i, nodes[i], obs_row[i]);
+  if (n_pair == 0) return HB_OK;
+  HB_CUDA(h, cudaSetDevice(h->device));
+  int rc = hb_wait(h);
+  if (rc) return rc;
+  if ((rc = upload(h, h->d_stat_nodes, nodes, (size_t)n_pair)) || (rc = upload(h, h->d_stat_rows, obs_row, (size_t)n_pair)) ||
+      (rc = upload(h, h->d_obs, obs, (size_t)n_obs * h->nt)))
+    return rc;
+  HB_CUDA(h, h->d_stats.reserve((size_t)n_pair * HB_ST_COUNT));
+  node_statistics_kernel<<<(unsigned)n_pair, 256, 0, h->stream>>>(h->d_node_rows[h->cur].p, h->d_obs.p, h->d_stat_nodes.p,
+                                                                  h->d_stat_rows.p, h->nt, skip_nan, h->d_stats.p);
+  HB_CUDA(h, cudaGetLastError());
+  HB_CUDA(h, cudaMemcpyAsync(out, h->d_stats.p, (size_t)n_pair * HB_ST_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
+                             h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HB_OK;
 }
 
 int hb_get_reach_outflow(hb_engine* h, double* rows) {

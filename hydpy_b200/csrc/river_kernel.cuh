@@ -512,4 +512,57 @@ __global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n
   }
 }
 
+// ---- goodness-of-fit statistics of node series against observations --------------------------------------------------------
+// The sufficient statistics of hydpy/auxs/statstools.py (nse :574-616, kge :944-987, rmse :529-553, corr, bias, std
+// ratio) for many (node, observation row) pairs at once — the objective reduction of a calibration ensemble, so that only
+// HB_ST_COUNT doubles per pair travel to the host instead of the series.  One block per pair, two passes (means first,
+// then centred sums: no cancellation), fixed reduction tree ⇒ deterministic.  skip_nan drops the steps where either value
+// is NaN (`prepare_arrays(skip_nan=True)`, statstools.py:480-483); otherwise NaNs propagate like in NumPy.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(full, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  __syncthreads();
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(256) node_statistics_kernel(const double* __restrict__ node_rows, const double* __restrict__ obs,
+                                                              const int32_t* __restrict__ nodes, const int32_t* __restrict__ obs_row,
+                                                              int64_t nt, int skip_nan, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int pair = blockIdx.x;
+  const double* s = node_rows + (int64_t)nodes[pair] * nt;
+  const double* o = obs + (int64_t)obs_row[pair] * nt;
+  double n = 0.0, ss = 0.0, so = 0.0;
+  for (int64_t t = threadIdx.x; t < nt; t += blockDim.x) {
+    const double a = s[t], b = o[t];
+    if (skip_nan && (isnan(a) || isnan(b))) continue;
+    n += 1.0; ss += a; so += b;
+  }
+  n = block_sum(n, red); ss = block_sum(ss, red); so = block_sum(so, red);
+  const double ms = ss / n, mo = so / n;
+  double e2 = 0.0, vs = 0.0, vo = 0.0, sp = 0.0;
+  for (int64_t t = threadIdx.x; t < nt; t += blockDim.x) {
+    const double a = s[t], b = o[t];
+    if (skip_nan && (isnan(a) || isnan(b))) continue;
+    const double da = a - ms, db = b - mo, d = a - b;
+    e2 += d * d; vs += da * da; vo += db * db; sp += da * db;
+  }
+  e2 = block_sum(e2, red); vs = block_sum(vs, red); vo = block_sum(vo, red); sp = block_sum(sp, red);
+  if (threadIdx.x == 0) {
+    double* r = out + (int64_t)pair * HB_ST_COUNT;
+    r[HB_ST_N] = n; r[HB_ST_MEAN_SIM] = ms; r[HB_ST_MEAN_OBS] = mo; r[HB_ST_SS_ERR] = e2; r[HB_ST_SS_SIM] = vs;
+    r[HB_ST_SS_OBS] = vo; r[HB_ST_SP] = sp;
+  }
+}
+
 }  // namespace hb

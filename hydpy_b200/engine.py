@@ -23,7 +23,7 @@ EXPORTS = (
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
     "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run",
     "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
-    "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
+    "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
     "hb_device_info",
@@ -80,6 +80,7 @@ def load_library() -> C.CDLL:
         "hb_get_node_series": (C.c_int, [H, C.c_int64, i32p, f64p]),
         "hb_get_reach_outflow": (C.c_int, [H, f64p]),
         "hb_get_reach_inflow": (C.c_int, [H, f64p]),
+        "hb_node_statistics": (C.c_int, [H, C.c_int64, i32p, i32p, C.c_int64, f64p, C.c_int, f64p]),
         "hb_get_reach_state_series": (C.c_int, [H, f64p]),
         "hb_get_series": (C.c_int, [H, C.c_int, f64p]),
         "hb_comm_unique_id": (C.c_int, [H, C.c_void_p]),
@@ -321,6 +322,21 @@ class Engine:
         if len(sel):
             self._check(self._lib.hb_get_node_series(self._h, len(sel), ptr(sel, C.c_int32), ptr(out, C.c_double)),
                         "hb_get_node_series")
+        return out
+
+    def node_statistics(self, nodes: Sequence[int], obs: np.ndarray, obs_row: Sequence[int] | None = None,
+                        skip_nan: bool = False) -> np.ndarray:
+        """Sufficient statistics (columns = `layout.STATS`) of the simulated series of `nodes` (last window) against the
+        rows of `obs` — pair i compares `nodes[i]` with `obs[obs_row[i]]` (default: row i).  See `hydpy_b200.calib`."""
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, self.nt)
+        rows = np.arange(len(nodes), dtype=np.int32) if obs_row is None else np.ascontiguousarray(obs_row, dtype=np.int32)
+        if len(rows) != len(nodes):
+            raise ValueError("`obs_row` must have one entry per node")
+        out = np.zeros((len(nodes), len(layout.STATS)))
+        self._check(self._lib.hb_node_statistics(self._h, len(nodes), ptr(nodes, C.c_int32), ptr(rows, C.c_int32),
+                                                 obs.shape[0], ptr(obs, C.c_double), int(bool(skip_nan)),
+                                                 ptr(out, C.c_double)), "hb_node_statistics")
         return out
 
     def get_reach_outflow(self) -> np.ndarray:

@@ -61,3 +61,6 @@ ROW_NODE, ROW_REACH = 0, 1
 ENTRY_EXT = -(1 << 30)
 
 NCCL_ID_BYTES = 128
+
+#: rows of `hb_node_statistics` (enum hb_stat)
+STATS = ("n", "mean_sim", "mean_obs", "ss_err", "ss_sim", "ss_obs", "sp")

@@ -267,6 +267,24 @@ int hb_get_reach_inflow(hb_engine* h, double* rows);
 /* One selected land series (see enum hb_series for the layout). */
 int hb_get_series(hb_engine* h, int series, double* out);
 
+/* ---- objective reduction for calibration ensembles -------------------------------------------------- *
+ * Sufficient statistics of simulated node series of the last window against observation rows, reduced on the device:
+ * from them follow `nse`, `kge`, `rmse`, `corr`, `bias_abs/rel`, `std_ratio` of `hydpy/auxs/statstools.py` (:529-987)
+ * without moving the series to the host.  Pair i compares node `nodes[i]` with row `obs_row[i]` of `obs[n_obs][nt]`;
+ * `out` is [n_pair][HB_ST_COUNT].  skip_nan ≠ 0 drops steps where either value is NaN (`prepare_arrays(skip_nan=True)`). */
+enum hb_stat {
+  HB_ST_N = 0,      /* number of steps used                              */
+  HB_ST_MEAN_SIM,   /* mean(sim)                                          */
+  HB_ST_MEAN_OBS,   /* mean(obs)                                          */
+  HB_ST_SS_ERR,     /* sum((sim - obs)^2)                                 */
+  HB_ST_SS_SIM,     /* sum((sim - mean(sim))^2)                           */
+  HB_ST_SS_OBS,     /* sum((obs - mean(obs))^2)                           */
+  HB_ST_SP,         /* sum((sim - mean(sim)) * (obs - mean(obs)))         */
+  HB_ST_COUNT
+};
+int hb_node_statistics(hb_engine* h, int64_t n_pair, const int32_t* nodes, const int32_t* obs_row, int64_t n_obs,
+                       const double* obs, int skip_nan, double* out);
+
 /* ---- multi-GPU boundary hand-over (NCCL over NVLink) ---------------------------------------------- */
 #define HB_NCCL_ID_BYTES 128
 /* Fill `id` (HB_NCCL_ID_BYTES) on rank 0; broadcast it out of band; then every rank calls hb_comm_init. */

@@ -239,3 +239,33 @@ def test_pipelined_windows_equal_synchronous_windows(engine):
         assert tm["n_runs"] == nw and tm["land_ms"] > 0 and tm["river_ms"] > 0
         for b in bufs:
             b.free()
+
+
+def test_objective_statistics_of_an_ensemble_on_the_device(engine):
+    """hb_node_statistics: nse/kge of every member against the same gauge observations, reduced on the GPU, equal the
+    NumPy formulas of hydpy/auxs/statstools.py evaluated on the downloaded series."""
+    from hydpy_b200 import calib
+
+    ne, nt, m = 48, 240, 6
+    land, states = synth.make_land(ne, "1h", bank=ne)
+    forcing, doy = synth.make_forcing(nt, "1h", bank=ne)
+    river, discharge = synth.make_tree_river(ne, "1h", levels=6)
+    eland, estates = synth.replicate_members(land, states, m, n_node=river.n_node)
+    eriver, edis = synth.replicate_river(river, discharge, m, ne)
+    res = run_problem(Problem(land=eland, states=estates, river=eriver, discharge=edis, forcing=forcing, doy=doy,
+                              ext=np.zeros((0, nt))), engine)
+    gauges = np.array([0, 3, 7])                              # nodes of the base network that carry observations
+    rng = np.random.default_rng(3)
+    obs = res["node_rows"][gauges] * rng.uniform(0.8, 1.2, size=(len(gauges), nt))   # "observed" = perturbed member 0
+    obs[1, 50:60] = np.nan
+    nodes = np.concatenate([gauges + i * river.n_node for i in range(m)])
+    rows = np.tile(np.arange(len(gauges)), m)
+    st = engine.node_statistics(nodes, obs, obs_row=rows, skip_nan=True)
+    ref = calib.statistics_host(res["node_rows"][nodes], obs[rows], skip_nan=True)
+    np.testing.assert_allclose(st, ref, rtol=1e-12, atol=1e-300)
+    for fn in (calib.nse, calib.kge, calib.rmse):
+        np.testing.assert_allclose(fn(st), fn(ref), rtol=1e-10)
+    assert calib.nse(st).reshape(m, -1)[0].min() > 0.5        # member 0 generated the observations
+    # without skip_nan the NaN gap propagates like in NumPy
+    st2 = engine.node_statistics(nodes[:3], obs, obs_row=rows[:3], skip_nan=False)
+    assert np.isnan(calib.nse(st2)[1]) and np.isfinite(calib.nse(st2)[[0, 2]]).all()
