@@ -269,3 +269,34 @@ def test_objective_statistics_of_an_ensemble_on_the_device(engine):
     # without skip_nan the NaN gap propagates like in NumPy
     st2 = engine.node_statistics(nodes[:3], obs, obs_row=rows[:3], skip_nan=False)
     assert np.isnan(calib.nse(st2)[1]) and np.isfinite(calib.nse(st2)[[0, 2]]).all()
+
+
+def test_full_size_routing_sweeps_agree_bit_for_bit():
+    """BASELINE size (10^5 reaches, ≈220 levels): the persistent wavefront (ordered queue, progress flags, ld.cg reads)
+    must reproduce the one-launch-per-diagonal sweep exactly — at the size where races would show — and twice in a row
+    (pipelined windows).  The land paths must agree within the parity bar on the same basin."""
+    ne, win, nw = 100_000, 96, 2
+    land, states = synth.make_land(ne, "1h")
+    river, discharge = synth.make_tree_river(ne, "1h", levels=200)
+    forcing, doy = synth.make_forcing(win * nw, "1h")
+    no_ext = np.zeros((0, win))
+    results = {}
+    with Engine(0) as eng:
+        for sweep, path in (("launches", "auto"), ("persistent", "auto"), ("persistent", "general")):
+            eng.set_land_path(path)
+            eng.set_river_sweep(sweep)
+            eng.set_land(land); eng.set_land_states(states); eng.set_river(river); eng.set_river_states(discharge)
+            bufs = [eng.pinned((river.n_node, win)) for _ in range(nw)]
+            for w in range(nw):
+                eng.set_forcing(forcing[:, w * win:(w + 1) * win], doy[w * win:(w + 1) * win])
+                eng.set_external(no_ext)
+                eng.run_async()
+                eng.get_node_series_async(bufs[w].array)
+            eng.wait()
+            results[(sweep, path)] = (np.concatenate([b.array for b in bufs], axis=1), eng.get_river_states())
+            for b in bufs:
+                b.free()
+    a, b, c = results[("launches", "auto")], results[("persistent", "auto")], results[("persistent", "general")]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.isfinite(a[0]).all() and a[0][0].max() > 0.0
+    assert_close(b[0], c[0], "full size: fast vs general land path, node series")
