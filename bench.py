@@ -290,14 +290,14 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     d2h = river.n_node * win * 8
     dist.barrier()
     for s in range(W):
-        eng.set_forcing(pinned.array[s], doys[s])                 # host → device copy of this window's forcing
+        eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)   # host → device copy of this window's forcing
         step_exchange_and_route()
         eng.get_node_series_async(outs[s & 1].array)              # device → host copy of every node's series
     eng.wait()
     dist.barrier()
     t0 = time.perf_counter()
     for s in range(W, W + K):
-        eng.set_forcing(pinned.array[s], doys[s])
+        eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
         step_exchange_and_route()
         eng.get_node_series_async(outs[s & 1].array)
     eng.wait()                                                    # all K windows' results are in host memory

@@ -99,7 +99,13 @@ struct hb_engine {
   // Three streams form the window pipeline: runoff generation of window w+1 (stream) overlaps routing of window w
   // (s_river) and the device→host copy of its node series (s_copy).  All per-window buffers exist twice; `cur` is the
   // set of the window staged last (it flips in hb_set_forcing / hb_select_window).
-  cudaStream_t stream = nullptr, s_river = nullptr, s_copy = nullptr, s_comm = nullptr;
+  cudaStream_t stream = nullptr, s_river = nullptr, s_copy = nullptr, s_comm = nullptr, s_h2d = nullptr;
+  // forcing is double-buffered as well: the block of the next window is copied (s_h2d) while this window's land part runs
+  int fcur = 0;
+  cudaEvent_t ev_forcing_ready[2] = {nullptr, nullptr};   // H2D copy into forcing buffer f is complete
+  cudaEvent_t ev_forcing_read[2] = {nullptr, nullptr};    // the last land run that reads forcing buffer f is complete
+  double* h_sin[2] = {nullptr, nullptr};                  // pinned staging of the seasonal factor
+  size_t h_sin_cap[2] = {0, 0};
   cudaEvent_t ev_ext_ready[2] = {nullptr, nullptr};   // boundary rows of the window have arrived (NCCL, s_comm)
   cudaEvent_t ev_send_done[2] = {nullptr, nullptr};   // boundary rows of the window have left (their buffers may be reused)
   bool ext_async[2] = {false, false};                 // … and the routing of that window has to wait for them
@@ -163,7 +169,7 @@ struct hb_engine {
   // ---- window ----
   int64_t nt = 0, n_col = 0, nt_total = 0, t0 = 0;
   bool have_forcing = false, have_results = false, have_routed = false;
-  DBuf<double> d_forcing, d_sinfactor, d_qt, d_land_rows[2];
+  DBuf<double> d_forcing[2], d_sinfactor[2], d_qt, d_land_rows[2];
   DBuf<MathTables> d_tables;
 
   // ---- river ----
@@ -286,6 +292,11 @@ int hb_create(int device, hb_engine** out) {
     cudaStreamCreateWithPriority(&h->s_river, cudaStreamNonBlocking, hi);
     cudaStreamCreateWithPriority(&h->s_copy, cudaStreamNonBlocking, hi);
     cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, hi);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&h->ev_forcing_ready[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_forcing_read[i], cudaEventDisableTiming);
+    }
     cudaEventCreateWithFlags(&h->ev_ext_ready[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_ext_ready[1], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_send_done[0], cudaEventDisableTiming);
@@ -325,6 +336,7 @@ void hb_destroy(hb_engine* h) {
   if (h->s_river) cudaStreamSynchronize(h->s_river);
   if (h->s_copy) cudaStreamSynchronize(h->s_copy);
   if (h->s_comm) cudaStreamSynchronize(h->s_comm);
+  if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -337,6 +349,12 @@ void hb_destroy(hb_engine* h) {
   if (h->s_river) cudaStreamDestroy(h->s_river);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_comm) cudaStreamDestroy(h->s_comm);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_forcing_ready[i]) cudaEventDestroy(h->ev_forcing_ready[i]);
+    if (h->ev_forcing_read[i]) cudaEventDestroy(h->ev_forcing_read[i]);
+    if (h->h_sin[i]) cudaFreeHost(h->h_sin[i]);
+  }
   for (cudaEvent_t e : {h->ev_ext_ready[0], h->ev_ext_ready[1], h->ev_send_done[0], h->ev_send_done[1]})
     if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -908,23 +926,36 @@ int hb_get_river_states(hb_engine* h, double* discharge) {
 // ---------------------------------------------------------------------------------------------------------------------
 // window
 // ---------------------------------------------------------------------------------------------------------------------
-int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
-  if (!h) return HB_EINVAL;
+static int stage_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_forcing: call hb_set_land first");
   HB_REQUIRE(h, nt >= 0 && n_col >= (h->n_elem ? 1 : 0) && (nt == 0 || doy) && (nt * n_col == 0 || forcing), HB_EINVAL,
              "hb_set_forcing: invalid argument (nt=%lld, n_col=%lld)", (long long)nt, (long long)n_col);
   HB_CUDA(h, cudaSetDevice(h->device));
-  HB_CUDA(h, cudaStreamSynchronize(h->stream));  // runoff generation of the previous window still reads the old block
+  const int f = h->fcur ^ 1;                      // the buffer the land run before the last one has read
   const size_t n = (size_t)HB_FORCING_COUNT * nt * n_col;
-  HB_CUDA(h, h->d_forcing.reserve(n));
-  if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing.p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // the copy runs on its own stream, behind the last land run that read this buffer, while the current one is busy
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_forcing_read[f], 0));
+  if (n > h->d_forcing[f].cap || (size_t)nt > h->d_sinfactor[f].cap) HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  HB_CUDA(h, h->d_forcing[f].reserve(n));
+  HB_CUDA(h, h->d_sinfactor[f].reserve((size_t)nt));
+  if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing[f].p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
   // 0.5*sin(2*pi*(doy+1)/366-1.39) with the HOST libm, evaluated exactly like the generated C of the reference
   // (ref: hydpy/models/hland/hland_model.py:1056-1058) — the seasonal factor is therefore bit-identical to the CPU path
-  std::vector<double> sf((size_t)nt);
+  if ((size_t)nt > h->h_sin_cap[f]) {
+    if (h->h_sin[f]) { HB_CUDA(h, cudaEventSynchronize(h->ev_forcing_ready[f])); HB_CUDA(h, cudaFreeHost(h->h_sin[f])); }
+    h->h_sin[f] = nullptr;
+    HB_CUDA(h, cudaHostAlloc((void**)&h->h_sin[f], (size_t)nt * sizeof(double), cudaHostAllocDefault));
+    h->h_sin_cap[f] = (size_t)nt;
+  } else if (h->h_sin[f]) {
+    HB_CUDA(h, cudaEventSynchronize(h->ev_forcing_ready[f]));   // the previous copy out of this staging slot is through
+  }
   const double pi = 3.141592653589793;
-  for (int64_t t = 0; t < nt; ++t) sf[t] = 0.5 * sin((((2.0 * pi) * (double)(doy[t] + 1)) / 366.0) - 1.39);
-  int rc = upload(h, h->d_sinfactor, sf);
-  if (rc) return rc;
+  for (int64_t t = 0; t < nt; ++t) h->h_sin[f][t] = 0.5 * sin((((2.0 * pi) * (double)(doy[t] + 1)) / 366.0) - 1.39);
+  if (nt) HB_CUDA(h, cudaMemcpyAsync(h->d_sinfactor[f].p, h->h_sin[f], (size_t)nt * sizeof(double), cudaMemcpyHostToDevice,
+                                     h->s_h2d));
+  HB_CUDA(h, cudaEventRecord(h->ev_forcing_ready[f], h->s_h2d));
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_forcing_ready[f], 0));   // land kernels of the new window wait for it
+  h->fcur = f;
   h->nt = nt;
   h->nt_total = nt;
   h->t0 = 0;
@@ -934,6 +965,22 @@ int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcin
   h->have_results = false;
   h->have_routed = false;
   h->have_ext = false;
+  return HB_OK;
+}
+
+int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
+  if (!h) return HB_EINVAL;
+  int rc = stage_forcing(h, nt, n_col, forcing, doy);
+  if (rc) return rc;
+  HB_CUDA(h, cudaStreamSynchronize(h->s_h2d));   // the caller's buffer is free again
+  return HB_OK;
+}
+
+int hb_set_forcing_async(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy) {
+  if (!h) return HB_EINVAL;
+  int rc = stage_forcing(h, nt, n_col, forcing, doy);
+  if (rc) return rc;
+  h->pending = true;
   return HB_OK;
 }
 
@@ -1008,8 +1055,8 @@ static int run_land(hb_engine* h) {
     v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
     v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
-    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing.p;
-    v.sinfactor = h->d_sinfactor.p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
+    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow;
     int n_staged = 0;
     for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
@@ -1070,8 +1117,8 @@ static int run_land(hb_engine* h) {
     v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
     v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
-    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing.p;
-    v.sinfactor = h->d_sinfactor.p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
+    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
     v.nt = nt; v.t_first = h->t0; v.t_out = 0;
     v.clist = h->d_coupled_list.p; v.n_clist = (int64_t)h->coupled_list.size();
     const int zw = h->zmax;
@@ -1099,8 +1146,8 @@ static int run_land(hb_engine* h) {
     d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
     d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
     d.tables = h->d_tables.p;
-    d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing.p;
-    d.sinfactor = h->d_sinfactor.p; d.qt = h->d_qt.p;
+    d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing[h->fcur].p;
+    d.sinfactor = h->d_sinfactor[h->fcur].p; d.qt = h->d_qt.p;
     for (int s = 0; s < HB_S_COUNT; ++s) d.series[s] = h->series_on[s] ? h->d_series[s].p : nullptr;
     const int block = 128;
     const int grid = (int)((n_general + block - 1) / block);
@@ -1243,6 +1290,7 @@ static int enqueue_run(hb_engine* h, int flags) {
     if ((rc = run_land(h))) return rc;
     h->land_marks.add(HB_K_END, h->stream);
     HB_CUDA(h, cudaEventRecord(h->ev_land_done[c], h->stream));
+    HB_CUDA(h, cudaEventRecord(h->ev_forcing_read[h->fcur], h->stream));
     h->have_results = true;
   }
   if (flags & HB_RUN_RIVER) {
@@ -1286,6 +1334,7 @@ int hb_wait(hb_engine* h) {
   HB_CUDA(h, cudaStreamSynchronize(h->s_river));
   HB_CUDA(h, cudaStreamSynchronize(h->s_copy));
   HB_CUDA(h, cudaStreamSynchronize(h->s_comm));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_h2d));
   int rc;
   if ((rc = resolve_marks(h, h->land_marks, true)) || (rc = resolve_marks(h, h->river_marks, false))) return rc;
   h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;

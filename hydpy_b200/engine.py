@@ -21,7 +21,7 @@ LIBPATH = os.environ.get("HYDPY_B200_LIB") or os.path.join(HERE, "libhydpy_b200.
 EXPORTS = (
     "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
-    "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_select_window", "hb_set_external", "hb_run",
+    "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_set_forcing_async", "hb_select_window", "hb_set_external", "hb_run",
     "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
     "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
         "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
         "hb_set_option": (C.c_int, [H, C.c_int, C.c_int64]),
         "hb_set_forcing": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
+        "hb_set_forcing_async": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
         "hb_select_window": (C.c_int, [H, C.c_int64, C.c_int64]),
         "hb_set_external": (C.c_int, [H, C.c_int64, f64p]),
         "hb_run": (C.c_int, [H, C.c_int]),
@@ -253,7 +254,12 @@ class Engine:
         self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_SWEEP, value), "hb_set_option")
 
     # -- window -----------------------------------------------------------------------------------------------------
-    def set_forcing(self, forcing: np.ndarray, doy: np.ndarray) -> None:
+    def set_forcing(self, forcing: np.ndarray, doy: np.ndarray, asynchronous: bool = False) -> None:
+        """Stage the forcing block [4, nt, n_col] of the next window.  `asynchronous=True` only enqueues the copy
+        (`hb_set_forcing_async`): `forcing` must then be a C-contiguous float64 view of PINNED memory (`Engine.pinned`)
+        that stays untouched until `wait()`."""
+        if asynchronous and not (forcing.dtype == np.float64 and forcing.flags.c_contiguous):
+            raise ValueError("asynchronous staging needs a C-contiguous float64 array in pinned memory")
         forcing = np.ascontiguousarray(forcing, dtype=np.float64)
         if forcing.ndim != 3 or forcing.shape[0] != len(layout.FORCING):
             raise ValueError(f"forcing must have shape (4, nt, n_col), not {forcing.shape}")
@@ -264,8 +270,8 @@ class Engine:
         land = self._need_land()
         if land.n_elem and int(land.forcing_col.max()) >= ncol:
             raise ValueError("forcing has fewer columns than `forcing_col` refers to")
-        self._check(self._lib.hb_set_forcing(self._h, nt, ncol, ptr(forcing, C.c_double), ptr(doy, C.c_int64)),
-                    "hb_set_forcing")
+        fn = self._lib.hb_set_forcing_async if asynchronous else self._lib.hb_set_forcing
+        self._check(fn(self._h, nt, ncol, ptr(forcing, C.c_double), ptr(doy, C.c_int64)), "hb_set_forcing")
         self.nt = nt
 
     def select_window(self, t0: int, nt: int) -> None:

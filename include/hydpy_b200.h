@@ -228,6 +228,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value);
  * hland_derived.DOY at the window's steps (`hland_model.py:1056`; 0-based day of a leap year).  Replaces
  * `load_data` (`modelutils.py:1080-1125`) reading `inputs.<name>._<name>_array[idx]`. */
 int hb_set_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy);
+/* Same for window pipelines: the copy is only enqueued (own stream, behind the land run that last read the target
+ * buffer) and overlaps the land part of the current window.  `forcing` must be page-locked (hb_host_alloc) and stay
+ * untouched until hb_wait; `doy` is consumed before the call returns. */
+int hb_set_forcing_async(hb_engine* h, int64_t nt, int64_t n_col, const double* forcing, const int64_t* doy);
 /* Select the sub-window [t0, t0+nt) of the staged forcing for the next hb_run (default after hb_set_forcing: the whole
  * block).  Lets a caller stage a long forcing block once and advance in chunks — `pub.timegrids.sim` windows inside
  * one `init` period, ref: hydpy/core/hydpytools.py:2804-2825. */

@@ -214,15 +214,20 @@ def test_pipelined_windows_equal_synchronous_windows(engine):
         sync_rows.append(engine.get_node_series())
     sync_states, sync_dis = engine.get_land_states(), engine.get_river_states()
 
-    for resident in (False, True):
+    staged = engine.pinned((nw, 4, win, forcing.shape[2]))          # asynchronous staging reads pinned memory
+    for w in range(nw):
+        staged.array[w] = forcing[:, w * win:(w + 1) * win]
+    for resident in (False, True, "async"):
         setup()
         bufs = [engine.pinned((river.n_node, win)) for _ in range(nw)]
-        if resident:
+        if resident is True:
             engine.set_forcing(forcing, doy)
         engine.timing()                      # reset the sums
         for w in range(nw):
-            if resident:
+            if resident is True:
                 engine.select_window(w * win, win)
+            elif resident == "async":
+                engine.set_forcing(staged.array[w], doy[w * win:(w + 1) * win], asynchronous=True)
             else:
                 engine.set_forcing(forcing[:, w * win:(w + 1) * win], doy[w * win:(w + 1) * win])
             engine.set_external(no_ext)
@@ -239,6 +244,7 @@ def test_pipelined_windows_equal_synchronous_windows(engine):
         assert tm["n_runs"] == nw and tm["land_ms"] > 0 and tm["river_ms"] > 0
         for b in bufs:
             b.free()
+    staged.free()
 
 
 def test_objective_statistics_of_an_ensemble_on_the_device(engine):
