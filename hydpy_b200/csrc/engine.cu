@@ -1062,8 +1062,19 @@ static int run_land(hb_engine* h) {
     for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
     // time chunks bound the two term buffers (3 GB each at most)
     const int64_t per_step = (int64_t)h->zmax * ep;
-    // scratch per simulated step: two term buffers + one staging buffer per recorded zone/snow series; 6 GB in total
-    int64_t chunk_max = (int64_t)(6.0e9 / 8.0) / (per_step * (2 + n_staged));
+    // scratch per simulated step: two term buffers + one staging buffer per recorded zone/snow series.  Budget: 6 GB, or
+    // up to a quarter of the free device memory (at most 32 GB) for large ensembles, whose chunks would otherwise shrink
+    // to a handful of steps per launch
+    double budget = 6.0e9;
+    {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const double held = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);   // already ours, counts as available
+        const double quarter = 0.25 * ((double)free_b + held);
+        if (quarter > budget) budget = quarter < 32.0e9 ? quarter : 32.0e9;
+      }
+    }
+    int64_t chunk_max = (int64_t)(budget / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
     const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
