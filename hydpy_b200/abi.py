@@ -29,11 +29,12 @@ class hb_land_desc(C.Structure):
         ("zonetype", c_i32p), ("zflags", c_i32p), ("zorder", c_i32p),
         ("zpar", c_f64p), ("sfdist", c_f64p), ("uh", c_f64p),
         ("sred_from", c_i32p), ("sred_to", c_i32p), ("sred_adjust", c_f64p),
+        ("model", c_i32p), ("rconc", c_i32p), ("nash_steps", c_i32p),
     ]
 
 
 class hb_land_states(C.Structure):
-    _fields_ = [(n, c_f64p) for n in ("ic", "sm", "sp", "wc", "uz", "lz", "quh")]
+    _fields_ = [(n, c_f64p) for n in ("ic", "sm", "sp", "wc", "uz", "lz", "quh", "suz", "sg1", "bw1", "bw2", "sg2", "sg3")]
 
 
 class hb_river_desc(C.Structure):
@@ -71,7 +72,9 @@ def ptr(a: np.ndarray, ctype: Any) -> Any:
 
 @dataclasses.dataclass
 class LandStates:
-    """hland_96 states + rconc_uh log (`Sequences.conditions`, ref: core/sequencetools.py:807-828)."""
+    """hland_96 states + rconc_uh log (`Sequences.conditions`, ref: core/sequencetools.py:807-828); `quh` also holds
+    `states.sc` of rconc_nash elements.  The states of the sibling models (hland_96p: suz, sg1 per zone, sg2, sg3 per
+    element; hland_96c: bw1, bw2 per zone) default to zeros of the matching size."""
 
     ic: np.ndarray
     sm: np.ndarray
@@ -80,13 +83,29 @@ class LandStates:
     uz: np.ndarray
     lz: np.ndarray
     quh: np.ndarray
+    suz: np.ndarray | None = None
+    sg1: np.ndarray | None = None
+    bw1: np.ndarray | None = None
+    bw2: np.ndarray | None = None
+    sg2: np.ndarray | None = None
+    sg3: np.ndarray | None = None
 
-    NAMES = ("ic", "sm", "sp", "wc", "uz", "lz", "quh")
+    NAMES_V1 = ("ic", "sm", "sp", "wc", "uz", "lz", "quh")
+    NAMES_ZONE2 = ("suz", "sg1", "bw1", "bw2")
+    NAMES_ELEM2 = ("sg2", "sg3")
+    NAMES = NAMES_V1 + NAMES_ZONE2 + NAMES_ELEM2
 
     def copy(self) -> "LandStates":
+        self.normalise()
         return LandStates(**{n: getattr(self, n).copy() for n in self.NAMES})
 
     def normalise(self) -> None:
+        for n in self.NAMES_ZONE2:
+            if getattr(self, n) is None:
+                setattr(self, n, np.zeros(len(self.ic)))
+        for n in self.NAMES_ELEM2:
+            if getattr(self, n) is None:
+                setattr(self, n, np.zeros(len(self.uz)))
         for n in self.NAMES:
             setattr(self, n, _arr(getattr(self, n), np.float64))
 
@@ -122,9 +141,13 @@ class LandBundle:
     sred_from: np.ndarray
     sred_to: np.ndarray
     sred_adjust: np.ndarray
+    model: np.ndarray | None = None        # [n_elem] layout.MODEL_* (None: all hland_96)
+    rconc: np.ndarray | None = None        # [n_elem] layout.RCONC_* (None: all rconc_uh / no submodel)
+    nash_steps: np.ndarray | None = None   # [n_elem] rconc_nash NmbSteps
 
     I64 = ("zone_ptr", "snow_ptr", "sfdist_ptr", "uh_ptr", "sred_ptr")
-    I32 = ("recstep", "eflags", "forcing_col", "outlet_node", "zonetype", "zflags", "zorder", "sred_from", "sred_to")
+    I32 = ("recstep", "eflags", "forcing_col", "outlet_node", "zonetype", "zflags", "zorder", "sred_from", "sred_to",
+           "model", "rconc", "nash_steps")
     F64 = ("epar", "zpar", "sfdist", "uh", "sred_adjust")
 
     @property
@@ -144,6 +167,9 @@ class LandBundle:
         return int(self.uh_ptr[-1])
 
     def normalise(self) -> None:
+        for n in ("model", "rconc", "nash_steps"):
+            if getattr(self, n) is None:
+                setattr(self, n, np.zeros(self.n_elem, np.int32))
         for n in self.I64:
             setattr(self, n, _arr(getattr(self, n), np.int64))
         for n in self.I32:
@@ -151,6 +177,11 @@ class LandBundle:
         for n in self.F64:
             setattr(self, n, _arr(getattr(self, n), np.float64))
         ne, nz = self.n_elem, self.n_zone
+        # bundles of ABI 1 (committed fixtures, hland_96 only): the rows of the sibling models are zero
+        if self.zpar.shape == (layout.N_ZPAR_V1, nz):
+            self.zpar = np.concatenate([self.zpar, np.zeros((len(layout.ZPAR) - layout.N_ZPAR_V1, nz))])
+        if self.epar.shape == (layout.N_EPAR_V1, ne):
+            self.epar = np.concatenate([self.epar, np.zeros((len(layout.EPAR) - layout.N_EPAR_V1, ne))])
         if self.epar.shape != (len(layout.EPAR), ne):
             raise ValueError(f"epar must have shape {(len(layout.EPAR), ne)}, not {self.epar.shape}")
         if self.zpar.shape != (len(layout.ZPAR), nz):
@@ -158,7 +189,7 @@ class LandBundle:
         for n in ("snow_ptr", "sfdist_ptr", "uh_ptr", "sred_ptr"):
             if len(getattr(self, n)) != ne + 1:
                 raise ValueError(f"{n} must have n_elem+1 entries")
-        for n in ("recstep", "eflags", "forcing_col", "outlet_node"):
+        for n in ("recstep", "eflags", "forcing_col", "outlet_node", "model", "rconc", "nash_steps"):
             if len(getattr(self, n)) != ne:
                 raise ValueError(f"{n} must have n_elem entries")
         for n in ("zonetype", "zflags", "zorder"):
@@ -193,11 +224,12 @@ class LandBundle:
         return self.epar[layout.EP[name]]
 
     def to_dict(self, prefix: str = "land_") -> dict[str, np.ndarray]:
+        self.normalise()
         return {prefix + f.name: np.asarray(getattr(self, f.name)) for f in dataclasses.fields(self)}
 
     @classmethod
     def from_dict(cls, d: Any, prefix: str = "land_") -> "LandBundle":
-        return cls(**{f.name: np.asarray(d[prefix + f.name]) for f in dataclasses.fields(cls)})
+        return cls(**{f.name: np.asarray(d[prefix + f.name]) for f in dataclasses.fields(cls) if prefix + f.name in d})
 
 
 @dataclasses.dataclass
@@ -280,8 +312,9 @@ class RiverBundle:
 
 
 def states_to_dict(st: LandStates, prefix: str = "state_") -> dict[str, np.ndarray]:
+    st.normalise()
     return {prefix + n: np.asarray(getattr(st, n)) for n in LandStates.NAMES}
 
 
 def states_from_dict(d: Any, prefix: str = "state_") -> LandStates:
-    return LandStates(**{n: np.array(d[prefix + n], dtype=np.float64) for n in LandStates.NAMES})
+    return LandStates(**{n: np.array(d[prefix + n], dtype=np.float64) for n in LandStates.NAMES if prefix + n in d})

@@ -146,6 +146,12 @@ struct hb_engine {
   int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
   std::vector<int32_t> coupled_list;  // elements of the fused kernel (HB_EI_COUPLED)
   std::vector<int32_t> general_list;  // elements of the general kernel in the current combination of paths
+  // sibling models: hland_96p / hland_96c elements always run through the general kernel, instantiated
+  // for their model
+  std::vector<int32_t> h_model, sibling_list[2];
+  DBuf<int32_t> d_sibling_list[2], d_nash_steps;
+  DBuf<double> d_zx1, d_zx2, d_ex1, d_ex2;   // hland_96p suz, sg1, sg2, sg3 | hland_96c bw1, bw2
+  bool any_sibling = false;
   std::vector<int32_t> h_einfo;
   int general_key = -1;
   DBuf<int32_t> d_coupled_list, d_general_list;
@@ -420,7 +426,24 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   h->outlet_node.assign(ne, -1);
   if (d->outlet_node) h->outlet_node.assign(d->outlet_node, d->outlet_node + ne);
 
-  std::vector<int32_t> nz(ep, 0), nc(ep, 1), nu(ep, 0), recstep(ep, 0), einfo(ep, 0), fcol(ep, 0);
+  std::vector<int32_t> nz(ep, 0), nc(ep, 1), nu(ep, 0), recstep(ep, 0), einfo(ep, 0), fcol(ep, 0), nash(ep, 0);
+  std::vector<int32_t> model(ne, HB_MODEL_HLAND_96), siblings[2];
+  for (int64_t e = 0; e < ne; ++e) {
+    if (d->model) model[e] = d->model[e];
+    HB_REQUIRE(h, model[e] >= HB_MODEL_HLAND_96 && model[e] <= HB_MODEL_HLAND_96C, HB_EINVAL,
+               "hb_set_land: element %lld has unknown model %d", (long long)e, model[e]);
+    if (model[e] != HB_MODEL_HLAND_96) siblings[model[e] - 1].push_back((int32_t)e);
+    const int kind = d->rconc ? d->rconc[e] : HB_RCONC_UH;
+    HB_REQUIRE(h, kind == HB_RCONC_UH || kind == HB_RCONC_NASH, HB_EINVAL, "hb_set_land: unknown rconc kind %d", kind);
+    if (kind == HB_RCONC_NASH) {
+      HB_REQUIRE(h, d->nash_steps && d->nash_steps[e] >= 0, HB_EINVAL, "hb_set_land: rconc_nash needs nash_steps >= 0");
+      const double ksc = d->epar[(int64_t)HB_EP_NASH_KSC * ne + e];
+      // ref: rconc_model.py:183-184 — no storages or an infinite coefficient pass the inflow on
+      nash[e] = (d->uh_ptr[e + 1] == d->uh_ptr[e] || std::isinf(ksc)) ? -1 : d->nash_steps[e];
+      // (NmbSteps == 0 would yield outflow 0; the kernel's 0 means rconc_uh, so that case is refused)
+      HB_REQUIRE(h, nash[e] != 0, HB_EINVAL, "hb_set_land: rconc_nash with NmbSteps == 0");
+    }
+  }
   std::vector<int32_t> zinfo((size_t)zmax * ep, 0), zorder((size_t)zmax * ep, 0);
   std::vector<int64_t> zone0(ep, 0), snow0(ep, 0), sred_ptr(ep + 1, 0);
   std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
@@ -499,10 +522,30 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       o[(size_t)KZ_INV_SFCF * ep] = 1.0 / ZP(SFCF, zz);
       o[(size_t)KZ_INV_FC * ep] = 1.0 / ZP(FC, zz);
       o[(size_t)KZ_INV_THRESH * ep] = 1.0 / (ZP(SOILMOISTURELIMIT, zz) * ZP(MAXSOILWATER, zz));
+      if (model[e] == HB_MODEL_HLAND_96P) {
+        // folded like the reference evaluates them: (suz-sgr)*(1-w0), suz*(1-w1), w2*sg1 + ((1-w2)*k2)*gr1
+        o[(size_t)KZ_X0 * ep] = ZP(SGR, zz);
+        o[(size_t)KZ_X1 * ep] = 1.0 - ZP(W0, zz);
+        o[(size_t)KZ_X2 * ep] = 1.0 - ZP(W1, zz);
+        o[(size_t)KZ_X3 * ep] = ZP(K2, zz);
+        o[(size_t)KZ_X4 * ep] = ZP(W2, zz);
+        o[(size_t)KZ_X5 * ep] = (1.0 - ZP(W2, zz)) * ZP(K2, zz);
+        o[(size_t)KZ_X6 * ep] = ZP(SG1MAX, zz);
+      } else if (model[e] == HB_MODEL_HLAND_96C) {
+        o[(size_t)KZ_X0 * ep] = ZP(H1, zz);
+        o[(size_t)KZ_X1 * ep] = ZP(TAB1, zz);
+        o[(size_t)KZ_X2 * ep] = ZP(TVS1, zz);
+        o[(size_t)KZ_X3 * ep] = ZP(H2, zz);
+        o[(size_t)KZ_X4 * ep] = ZP(TAB2, zz);
+        o[(size_t)KZ_X5 * ep] = ZP(TVS2, zz);
+        o[(size_t)KZ_W_LAND * ep] = ZP(RELZONEAREA, zz) / EPAR(RELLANDAREA, e);
+      }
       if (zt != HB_FIELD && zt != HB_FOREST) soilonly = false;
       if ((zt == HB_FIELD || zt == HB_FOREST) && !(ZP(CFLUX, zz) == 0.0)) coupled = true;
     }
-    if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
+    if (model[e] != HB_MODEL_HLAND_96) { info &= ~HB_EI_RESPAREA; }   // general kernel, instantiated for the model
+    else if (nash[e] != 0) { }                                        // rconc_nash: general kernel (the fast paths convolve a unit hydrograph)
+    else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
     else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX) { info |= HB_EI_COUPLED; coupled_list.push_back((int32_t)e); }
     if (soilonly) info |= HB_EI_SOILONLY;
     if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
@@ -520,6 +563,13 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
     ke[(size_t)KE_RELSOILAREA * ep + e] = relsoil;
     ke[(size_t)KE_RELLANDAREA * ep + e] = EPAR(RELLANDAREA, e);
     ke[(size_t)KE_BETA_LAST * ep + e] = ZP(BETA, z0 + n - 1);
+    ke[(size_t)KE_K3 * ep + e] = EPAR(K3, e);
+    ke[(size_t)KE_W3 * ep + e] = EPAR(W3, e);
+    ke[(size_t)KE_W4 * ep + e] = EPAR(W4, e);
+    ke[(size_t)KE_FSG * ep + e] = EPAR(FSG, e);
+    ke[(size_t)KE_OMFSG * ep + e] = 1.0 - EPAR(FSG, e);
+    ke[(size_t)KE_NASH_DT * ep + e] = EPAR(NASH_DT, e);
+    ke[(size_t)KE_NASH_DTKSC * ep + e] = EPAR(NASH_DT, e) * EPAR(NASH_KSC, e);
     for (int c = 0; c < nc[e]; ++c) sfdist[(size_t)c * ep + e] = d->sfdist[d->sfdist_ptr[e] + c];
     for (int j = 0; j < nu[e]; ++j) uh[(size_t)j * ep + e] = d->uh[d->uh_ptr[e] + j];
   }
@@ -538,6 +588,15 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   }
   h->n_fast = n_fast;
   h->coupled_list = coupled_list;
+  if (h->h_model != model) h->have_states = false;
+  h->h_model = model;
+  h->any_sibling = !siblings[0].empty() || !siblings[1].empty();
+  for (int m = 0; m < 2; ++m) {
+    h->sibling_list[m] = siblings[m];
+    int rc_ = upload(h, h->d_sibling_list[m], siblings[m]);
+    if (rc_) return rc_;
+  }
+  { int rc_ = upload(h, h->d_nash_steps, nash); if (rc_) return rc_; }
   h->h_einfo.assign(einfo.begin(), einfo.begin() + ne);
   h->general_key = -1;
   {
@@ -577,6 +636,10 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   HB_CUDA(h, h->d_sp.reserve(zs * cmax)); HB_CUDA(h, h->d_wc.reserve(zs * cmax));
   HB_CUDA(h, h->d_uz.reserve(ep)); HB_CUDA(h, h->d_lz.reserve(ep)); HB_CUDA(h, h->d_quh.reserve((size_t)umax * ep));
   HB_CUDA(h, h->d_scr_a.reserve(zs)); HB_CUDA(h, h->d_scr_b.reserve(zs));
+  if (h->any_sibling) {
+    HB_CUDA(h, h->d_zx1.reserve(zs)); HB_CUDA(h, h->d_zx2.reserve(zs));
+    HB_CUDA(h, h->d_ex1.reserve(ep)); HB_CUDA(h, h->d_ex2.reserve(ep));
+  }
   HB_CUDA(h, cudaMemsetAsync(h->d_scr_a.p, 0, zs * sizeof(double), h->stream));
   HB_CUDA(h, cudaMemsetAsync(h->d_scr_b.p, 0, zs * sizeof(double), h->stream));
   if (any_snowlimit) {
@@ -621,6 +684,27 @@ int hb_set_land_states(hb_engine* h, const hb_land_states* st) {
       (rc = upload(h, h->d_wc, wc)) || (rc = upload(h, h->d_uz, uz)) || (rc = upload(h, h->d_lz, lz)) ||
       (rc = upload(h, h->d_quh, quh)))
     return rc;
+  if (h->any_sibling) {
+    // states of the sibling models: hland_96p suz, sg1 (zone), sg2, sg3 (element); hland_96c bw1, bw2 (zone)
+    std::vector<double> zx1(zs, 0.0), zx2(zs, 0.0), ex1(ep, 0.0), ex2(ep, 0.0);
+    for (int64_t e = 0; e < ne; ++e) {
+      const int m = h->h_model[e];
+      if (m == HB_MODEL_HLAND_96) continue;
+      const int64_t z0 = h->zone_ptr[e];
+      const double* a = m == HB_MODEL_HLAND_96P ? st->suz : st->bw1;
+      const double* b = m == HB_MODEL_HLAND_96P ? st->sg1 : st->bw2;
+      HB_REQUIRE(h, a && b && (m != HB_MODEL_HLAND_96P || (st->sg2 && st->sg3)), HB_EINVAL,
+                 "hb_set_land_states: NULL state array of a sibling model (element %lld)", (long long)e);
+      for (int k = 0; k < h->h_nz[e]; ++k) {
+        zx1[(size_t)k * ep + e] = a[z0 + k];
+        zx2[(size_t)k * ep + e] = b[z0 + k];
+      }
+      if (m == HB_MODEL_HLAND_96P) { ex1[e] = st->sg2[e]; ex2[e] = st->sg3[e]; }
+    }
+    if ((rc = upload(h, h->d_zx1, zx1)) || (rc = upload(h, h->d_zx2, zx2)) || (rc = upload(h, h->d_ex1, ex1)) ||
+        (rc = upload(h, h->d_ex2, ex2)))
+      return rc;
+  }
   h->have_states = true;
   return HB_OK;
 }
@@ -654,6 +738,31 @@ int hb_get_land_states(hb_engine* h, hb_land_states* st) {
     if (st->lz) st->lz[e] = lz[e];
     if (st->quh)
       for (int j = 0; j < nu; ++j) st->quh[u0 + j] = quh[(size_t)j * ep + e];
+  }
+  // states of the sibling models (cells of elements of another model read 0)
+  {
+    std::vector<double> zx1, zx2, ex1, ex2;
+    if (h->any_sibling) {
+      zx1.resize(zs); zx2.resize(zs); ex1.resize(ep); ex2.resize(ep);
+      HB_CUDA(h, cudaMemcpy(zx1.data(), h->d_zx1.p, zs * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(zx2.data(), h->d_zx2.p, zs * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(ex1.data(), h->d_ex1.p, ep * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(ex2.data(), h->d_ex2.p, ep * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    for (int64_t e = 0; e < ne; ++e) {
+      const int m = h->h_model[e];
+      const int64_t z0 = h->zone_ptr[e];
+      for (int k = 0; k < h->h_nz[e]; ++k) {
+        const double a = m == HB_MODEL_HLAND_96 ? 0.0 : zx1[(size_t)k * ep + e];
+        const double b = m == HB_MODEL_HLAND_96 ? 0.0 : zx2[(size_t)k * ep + e];
+        if (st->suz) st->suz[z0 + k] = m == HB_MODEL_HLAND_96P ? a : 0.0;
+        if (st->sg1) st->sg1[z0 + k] = m == HB_MODEL_HLAND_96P ? b : 0.0;
+        if (st->bw1) st->bw1[z0 + k] = m == HB_MODEL_HLAND_96C ? a : 0.0;
+        if (st->bw2) st->bw2[z0 + k] = m == HB_MODEL_HLAND_96C ? b : 0.0;
+      }
+      if (st->sg2) st->sg2[e] = m == HB_MODEL_HLAND_96P ? ex1[e] : 0.0;
+      if (st->sg3) st->sg3[e] = m == HB_MODEL_HLAND_96P ? ex2[e] : 0.0;
+    }
   }
   return HB_OK;
 }
@@ -1034,6 +1143,7 @@ static int run_land(hb_engine* h) {
     for (int64_t e = 0; e < h->n_elem; ++e) {
       const int info = h->h_einfo[e];
       if ((use_fast && (info & HB_EI_FAST)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
+      if (h->h_model[e] != HB_MODEL_HLAND_96) continue;   // sibling models: own launches below
       h->general_list.push_back((int32_t)e);
     }
     int rc = upload(h, h->d_general_list, h->general_list);
@@ -1045,8 +1155,14 @@ static int run_land(hb_engine* h) {
   if (h->n_elem == 0 || nt == 0) return HB_OK;
   for (int s = 0; s < HB_S_COUNT; ++s) {
     if (!h->series_on[s]) continue;
-    const int64_t width = s < HB_S_FIRST_SNOW ? h->n_zone : s < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+    const int level = HB_S_LEVEL(s);
+    const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : h->n_elem;
     HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
+    // sequences a model does not own read NaN in the cells of its elements
+    const bool partial = s >= HB_S_FIRST_ZONE2 ||
+                         (h->any_sibling && (s == HB_S_CONTRIAREA || s == HB_S_INUZ || s == HB_S_PERC || s == HB_S_Q0 ||
+                                             s == HB_S_Q1 || s == HB_S_UZ || s == HB_S_LZ));
+    if (partial) HB_CUDA(h, cudaMemsetAsync(h->d_series[s].p, 0xFF, (size_t)nt * width * sizeof(double), h->stream));
   }
 
   if (use_fast) {
@@ -1144,7 +1260,8 @@ static int run_land(hb_engine* h) {
     HB_CUDA(h, cudaGetLastError());
     h->timing.land_launches += 1;
   }
-  if (n_general > 0) {
+  const int64_t n_sib[2] = {(int64_t)h->sibling_list[0].size(), (int64_t)h->sibling_list[1].size()};
+  if (n_general > 0 || n_sib[0] > 0 || n_sib[1] > 0) {
     LandDev d{};
     d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
     d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
@@ -1156,18 +1273,35 @@ static int run_land(hb_engine* h) {
     d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
     d.ic = h->d_ic.p; d.sm = h->d_sm.p; d.sp = h->d_sp.p; d.wc = h->d_wc.p; d.uz = h->d_uz.p; d.lz = h->d_lz.p;
     d.quh = h->d_quh.p; d.scr_a = h->d_scr_a.p; d.scr_b = h->d_scr_b.p; d.scr_sred = h->d_scr_sred.p;
+    d.nash_steps = h->d_nash_steps.p; d.zx1 = h->d_zx1.p; d.zx2 = h->d_zx2.p; d.ex1 = h->d_ex1.p; d.ex2 = h->d_ex2.p;
     d.tables = h->d_tables.p;
     d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing[h->fcur].p;
     d.sinfactor = h->d_sinfactor[h->fcur].p; d.qt = h->d_qt.p;
     for (int s = 0; s < HB_S_COUNT; ++s) d.series[s] = h->series_on[s] ? h->d_series[s].p : nullptr;
     const int block = 128;
-    const int grid = (int)((n_general + block - 1) / block);
     h->mark(HB_K_OTHER);
-    if (any_series) land_kernel<true><<<grid, block, 0, h->stream>>>(d);
-    else land_kernel<false><<<grid, block, 0, h->stream>>>(d);
+    if (n_general > 0) {
+      const int grid = (int)((n_general + block - 1) / block);
+      if (any_series) land_kernel<true, HB_MODEL_HLAND_96><<<grid, block, 0, h->stream>>>(d);
+      else land_kernel<false, HB_MODEL_HLAND_96><<<grid, block, 0, h->stream>>>(d);
+      h->timing.land_launches += 1;
+    }
+    // sibling models: the same kernel instantiated for hland_96p / hland_96c on their element lists
+    for (int m = 0; m < 2; ++m) {
+      if (n_sib[m] == 0) continue;
+      d.n_list = n_sib[m]; d.elist = h->d_sibling_list[m].p;
+      const int grid = (int)((n_sib[m] + block - 1) / block);
+      if (m == 0) {
+        if (any_series) land_kernel<true, HB_MODEL_HLAND_96P><<<grid, block, 0, h->stream>>>(d);
+        else land_kernel<false, HB_MODEL_HLAND_96P><<<grid, block, 0, h->stream>>>(d);
+      } else {
+        if (any_series) land_kernel<true, HB_MODEL_HLAND_96C><<<grid, block, 0, h->stream>>>(d);
+        else land_kernel<false, HB_MODEL_HLAND_96C><<<grid, block, 0, h->stream>>>(d);
+      }
+      h->timing.land_launches += 1;
+    }
     h->mark(HB_K_GENERAL);
     HB_CUDA(h, cudaGetLastError());
-    h->timing.land_launches += 1;
   }
   dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
   transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, h->n_elem, ep);
@@ -1576,7 +1710,8 @@ int hb_get_series(hb_engine* h, int series, double* out) {
   HB_REQUIRE(h, h->have_results && h->series_on[series] && h->d_series[series].p, HB_ESTATE,
              "hb_get_series: series %d was not selected before hb_run", series);
   HB_CUDA(h, cudaSetDevice(h->device));
-  const int64_t width = series < HB_S_FIRST_SNOW ? h->n_zone : series < HB_S_FIRST_ELEM ? h->n_snow : h->n_elem;
+  const int level = HB_S_LEVEL(series);
+  const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : h->n_elem;
   return download(h, out, h->d_series[series].p, (size_t)h->nt * width);
 }
 

@@ -55,8 +55,13 @@ enum kz {
   KZ_RELZONEAREA, KZ_TTI,
   // reciprocals used by the fast path only (land_kernel_v2.cuh)
   KZ_INV_TTINT, KZ_INV_RFCF, KZ_INV_SFCF, KZ_INV_FC, KZ_INV_THRESH,
+  // sibling models (a zone belongs to one model, so the rows are shared):
+  //   hland_96p: sgr, 1-w0, 1-w1, k2, w2, (1-w2)*k2, sg1max        hland_96c: h1, tab1, tvs1, h2, tab2, tvs2
+  KZ_X0, KZ_X1, KZ_X2, KZ_X3, KZ_X4, KZ_X5, KZ_X6,
   KZ_COUNT
 };
+// hland_96c weighs its zone outflows with relzonearea/rellandarea (Calc_InRC_V3); the row of the (unused) upper-zone weight holds it
+#define KZ_W_LAND KZ_W_UZ
 
 // per-element constants; rows of ke[KE_COUNT][E_pad]
 enum ke {
@@ -69,6 +74,12 @@ enum ke {
   KE_UP_LOW,          // relupperzonearea/rellowerzonearea
   KE_QFACTOR, KE_RELSOILAREA, KE_RELLANDAREA,
   KE_BETA_LAST,       // beta of the last zone (Calc_ContriArea_V1 quirk, ref: hland_model.py:2236)
+  // hland_96p (KE_DT_PERCMAX = percmax because dt = 1 there, KE_K4 = derived k4)
+  KE_K3, KE_W3, KE_W4, KE_FSG,
+  KE_OMFSG,           // 1 - fsg
+  // rconc_nash
+  KE_NASH_DT,
+  KE_NASH_DTKSC,      // dt*ksc
   KE_COUNT
 };
 
@@ -118,7 +129,13 @@ struct LandDev {
   double* wc;              // [cmax][zmax][E_pad]
   double* uz;              // [E_pad]
   double* lz;              // [E_pad]
-  double* quh;             // [umax][E_pad]
+  double* quh;             // [umax][E_pad]  rconc_uh: logs.quh; rconc_nash: states.sc
+  const int32_t* nash_steps;  // [E_pad] 0: rconc_uh or none; > 0: rconc_nash NmbSteps; -1: rconc_nash passing its inflow on
+  // states of the sibling models: hland_96p suz, sg1 | hland_96c bw1, bw2 per zone; hland_96p sg2, sg3 per element
+  double* zx1;             // [zmax][E_pad]
+  double* zx2;             // [zmax][E_pad]
+  double* ex1;             // [E_pad]
+  double* ex2;             // [E_pad]
   // scratch
   double* scr_a;           // [zmax][E_pad]  r of SEALED zones / pc of ILAKE zones
   double* scr_b;           // [zmax][E_pad]  el of ILAKE zones
@@ -152,8 +169,104 @@ __device__ __forceinline__ void zone_front(const double* __restrict__ kzk, int64
   }
 }
 
-template <bool SERIES>
-__global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
+// ref: hland_model.py:2550-2619 Calc_QAb_QVs_BW_V1 (hland_96c): the reference's tail recursion (t0 := t1) as a loop.
+// `log` is libdevice's (the routine runs in the general kernel only); the iteration cap turns a non-advancing t1 — on
+// which the reference would exhaust its stack — into a NaN result instead of a hang.
+__device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, double& s0, double qz_, double& qa1,
+                                        double& qa2, TabRef T) {
+  double t0 = 0.0;
+  for (int it = 0; it < 4096; ++it) {
+    double s0_ = s0, t1, dt_;
+    if ((k1_ == 0.0) && (s0_ > h_)) {
+      qa1 += s0_ - h_;
+      s0 = s0_ = h_;
+    }
+    if ((k1_ == 0.0) && (s0_ == h_) && (qz_ > h_ / k2_)) {
+      const double qa2_ = h_ / k2_;
+      dt_ = 1.0 - t0;
+      qa2 += dt_ * qa2_;
+      qa1 += dt_ * (qz_ - qa2_);
+      return;
+    } else if (k2_ == 0.0) {
+      qa2 += s0_ + qz_;
+      s0 = 0.0;
+      return;
+    } else if ((s0_ < h_) || (s0_ == h_ && qz_ <= h_ / k2_)) {
+      if ((s0_ == h_) || (qz_ <= h_ / k2_)) t1 = 1.0;
+      else if (isinf(k2_)) t1 = (h_ - s0_) / qz_;
+      else t1 = t0 + k2_ * log((qz_ - s0_ / k2_) / (qz_ - h_ / k2_));
+      if (0.0 < t1 && t1 < 1.0) {
+        qa2 += (t1 - t0) * qz_ - (h_ - s0_);
+        s0 = h_;
+        t0 = t1;
+        continue;
+      } else if (isinf(k2_)) {
+        s0 += (1.0 - t0) * qz_;
+      } else {
+        dt_ = 1.0 - t0;
+        const double k2qz = k2_ * qz_;
+        s0 = k2qz - (k2qz - s0_) * hb_exp(-dt_ / k2_, T);
+        qa2 += s0_ - s0 + dt_ * qz_;
+      }
+      return;
+    } else {
+      const double v1 = 1.0 / k1_ + 1.0 / k2_;
+      const double v2 = qz_ + h_ / k1_;
+      const double nom = v2 - h_ * v1;
+      const double denom = v2 - s0_ * v1;
+      bool one = (s0_ == h_) || (denom == 0.0);
+      if (!one) { const double q = nom / denom; one = !(0.0 < q && q <= 1.0); }
+      if (one) t1 = 1.0;
+      else {
+        t1 = t0 - 1.0 / v1 * log(nom / denom);
+        t1 = HB_PYMIN(t1, 1.0);
+      }
+      dt_ = t1 - t0;
+      const double v3 = (v2 * dt_) / v1;
+      const double v4 = denom / (v1 * v1) * (1.0 - hb_exp(-dt_ * v1, T));
+      const double qa1_ = (v3 - v4 - h_ * dt_) / k1_;
+      const double qa2_ = (v3 - v4) / k2_;
+      qa1 += qa1_;
+      qa2 += qa2_;
+      if (t1 == 1.0) s0 += dt_ * qz_ - qa1_ - qa2_;
+      else s0 = h_;
+      if (t1 < 1.0) { t0 = t1; continue; }
+      return;
+    }
+  }
+  s0 = qa1 = qa2 = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1 (rconc_uh), :179-197
+// Determine_Outflow_V2 (rconc_nash: explicit Euler over NmbSteps sub-steps through the storage cascade)
+__device__ __forceinline__ double rconc_outflow(const double* __restrict__ uh, double* __restrict__ quh,
+                                                const double* __restrict__ ke, int64_t ep, int64_t e, int nu,
+                                                int nash_steps, double inrc) {
+  if (nu <= 0 || nash_steps < 0) return inrc;
+  if (nash_steps > 0) {
+    const double dt = ke[KE_NASH_DT * ep + e], dtksc = ke[KE_NASH_DTKSC * ep + e];
+    double outflow = 0.0;
+    for (int i = 0; i < nash_steps; ++i) {
+      double carry = dt * inrc;                       // what enters storage j in this sub-step
+      for (int j = 0; j < nu; ++j) {
+        double sc = quh[(int64_t)j * ep + e] + carry;
+        const double a = dtksc * sc;
+        const double q = HB_PYMIN(a, sc);
+        sc -= q;
+        quh[(int64_t)j * ep + e] = sc;
+        carry = q;
+      }
+      outflow += carry;
+    }
+    return outflow;
+  }
+  const double outrc = ldg(uh + e) * inrc + quh[e];
+  for (int j = 1; j < nu; ++j) quh[(int64_t)(j - 1) * ep + e] = ldg(uh + (int64_t)j * ep + e) * inrc + quh[(int64_t)j * ep + e];
+  return outrc;
+}
+
+template <bool SERIES, int MODEL>
+__global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
   __shared__ MathTables s_tables;
   {
     const double* src = reinterpret_cast<const double*>(d.tables);
@@ -177,6 +290,10 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
   const bool snowlimit = (einfo & HB_EI_SNOWLIMIT) != 0;
   const int64_t zone0 = SERIES ? d.zone0[e] : 0, snow0 = SERIES ? d.snow0[e] : 0;
   double uz = d.uz[e], lz = d.lz[e];
+  const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
+  // hland_96p: slow-response groundwater storages of the element
+  double sg2 = 0.0, sg3 = 0.0;
+  if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
   const int64_t zstride = (int64_t)d.zmax * ep;  // class stride of sp/wc
   const double* fP = d.forcing + (0 * d.nt_total + d.t0) * d.n_col + col;
   const double* fT = d.forcing + (1 * d.nt_total + d.t0) * d.n_col + col;
@@ -337,6 +454,8 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
 
     // ---- zone loop (all remaining zone-level methods) ----------------------------------------------------------
     double inuz = 0.0, contriarea = 1.0;
+    double gr2 = 0.0, gr3 = 0.0;      // hland_96p: Calc_GR2_GR3_V1 sums
+    double inrc_c = 0.0;              // hland_96c: Calc_InRC_V3 sum
     for (int k = 0; k < nz; ++k) {
       const int64_t ik = (int64_t)k * ep + e;
       const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
@@ -457,8 +576,8 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
           r = HB_PYMAX(r, a);
         } else r = in_;
         sm += in_ - r;
-        // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 (uz = value at the end of the previous step)
-        if (fc > 0.0) {
+        // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 (uz = value at the end of the previous step); hland_96 only
+        if (MODEL == HB_MODEL_HLAND_96 && fc > 0.0) {
           cf = ldg(kzk + KZ_CFLUX * ep) * (1.0 - sm / fc);
           const double a = uz + r;
           cf = HB_PYMIN(cf, a);
@@ -492,14 +611,16 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         sm -= ea;
         if (sm > fc) { r += sm - fc; sm = fc; }
         d.sm[ik] = sm;
-        // ref: hland_model.py:2092-2101 Calc_InUZ_V1
-        inuz += ldg(kzk + KZ_W_UZ * ep) * (r - cf);
-        // ref: hland_model.py:2224-2236 Calc_ContriArea_V1
-        if ((einfo & HB_EI_RESPAREA) && fc > 0.0) contriarea *= hb_pow(sm / fc, ldg(kzk + KZ_W_CONTRI * ep), T);
+        if (MODEL == HB_MODEL_HLAND_96) {
+          // ref: hland_model.py:2092-2101 Calc_InUZ_V1
+          inuz += ldg(kzk + KZ_W_UZ * ep) * (r - cf);
+          // ref: hland_model.py:2224-2236 Calc_ContriArea_V1
+          if ((einfo & HB_EI_RESPAREA) && fc > 0.0) contriarea *= hb_pow(sm / fc, ldg(kzk + KZ_W_CONTRI * ep), T);
+        }
       } else {
         r = in_;
         d.sm[ik] = 0.0;
-        if (zt == HB_GLACIER) inuz += ldg(kzk + KZ_W_UZ * ep) * (r - cf);
+        if (zt == HB_GLACIER) { if (MODEL == HB_MODEL_HLAND_96) inuz += ldg(kzk + KZ_W_UZ * ep) * (r - cf); }
         else if (zt == HB_SEALED) d.scr_a[ik] = r;
         else {  // ILAKE
           d.scr_a[ik] = pc;
@@ -510,6 +631,150 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
       }
       SERZ(HB_S_R, k, r); SERZ(HB_S_CF, k, cf); SERZ(HB_S_EA, k, ea); SERZ(HB_S_SM, k, sm);
       SERZ(HB_S_EL, k, (zt == HB_ILAKE) ? d.scr_b[ik] : 0.0);
+      if (MODEL == HB_MODEL_HLAND_96P) {
+        // ---- hland_96p: upper zone layer and first-order groundwater storage of the zone (models/hland_96p.py) ----
+        double suz = 0.0, sg1 = 0.0, dp = 0.0, rs = 0.0, ri = 0.0, gr1 = 0.0, rg1 = 0.0;
+        if (zt == HB_FIELD || zt == HB_FOREST || zt == HB_GLACIER) {
+          // ref: hland_model.py:2132-2140 Calc_SUZ_V1, 2525-2535 Calc_DP_SUZ_V1
+          suz = d.zx1[ik] + r;
+          dp = HB_PYMIN(suz, dt_percmax);          // dt = 1 for hland_96p elements: dt_percmax = PercMax
+          suz -= dp;
+          // ref: hland_model.py:3012-3033 Calc_RS_RI_SUZ_V1
+          const double sgr = ldg(kzk + KZ_X0 * ep);
+          if (suz > sgr) rs = (suz - sgr) * ldg(kzk + KZ_X1 * ep);
+          ri = suz * ldg(kzk + KZ_X2 * ep);
+          suz -= rs + ri;
+          if (suz < 0.0) {
+            const double f = 1.0 - suz / (rs + ri);
+            rs *= f;
+            ri *= f;
+            suz = 0.0;
+          }
+          // ref: hland_model.py:3233-3243 Calc_GR1_V1
+          const double sg1_old = d.zx2[ik], sg1max = ldg(kzk + KZ_X6 * ep);
+          const double b = (sg1max - sg1_old) / ldg(kzk + KZ_X3 * ep);
+          gr1 = HB_PYMIN(dp, b);
+          const double a = sg1_old + gr1 - sg1max;
+          gr1 -= HB_PYMAX(a, 0.0);
+          // ref: hland_model.py:3290-3304 Calc_RG1_SG1_V1
+          sg1 = ldg(kzk + KZ_X4 * ep) * sg1_old + ldg(kzk + KZ_X5 * ep) * gr1;
+          rg1 = sg1_old + gr1 - sg1;
+          // ref: hland_model.py:3975-3984 Calc_InRC_V2 (term; weighted and summed after the zone loop)
+          d.scr_a[ik] = rs + ri + rg1;
+        }
+        d.zx1[ik] = suz;
+        d.zx2[ik] = sg1;
+        // ref: hland_model.py:3356-3372 Calc_GR2_GR3_V1
+        if (zt != HB_SEALED) {
+          const double weight = ldg(kzk + KZ_W_LZ * ep);
+          const double total = (zt == HB_ILAKE) ? weight * pc : weight * (dp - gr1);
+          gr2 += d.ke[KE_FSG * ep + e] * total;
+          gr3 += d.ke[KE_OMFSG * ep + e] * total;
+        }
+        SERZ(HB_S_DP, k, dp); SERZ(HB_S_RS, k, rs); SERZ(HB_S_RI, k, ri); SERZ(HB_S_GR1, k, gr1); SERZ(HB_S_RG1, k, rg1);
+        SERZ(HB_S_SUZ, k, suz); SERZ(HB_S_SG1, k, sg1);
+      }
+      if (MODEL == HB_MODEL_HLAND_96C) {
+        // ---- hland_96c: surface-flow and interflow storages of the zone (models/hland_96c.py) ----------------------
+        double bw1 = 0.0, bw2 = 0.0, qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
+        if (zt == HB_FIELD || zt == HB_FOREST || zt == HB_GLACIER) {
+          // ref: hland_model.py:2833-2853 Calc_QAb1_QVs1_BW1_V1, 2927-2947 Calc_QAb2_QVs2_BW2_V1
+          bw1 = d.zx1[ik];
+          qab_qvs_bw(ldg(kzk + KZ_X0 * ep), ldg(kzk + KZ_X1 * ep), ldg(kzk + KZ_X2 * ep), bw1, r, qab1, qvs1, T);
+          bw2 = d.zx2[ik];
+          qab_qvs_bw(ldg(kzk + KZ_X3 * ep), ldg(kzk + KZ_X4 * ep), ldg(kzk + KZ_X5 * ep), bw2, qvs1, qab2, qvs2, T);
+          d.scr_a[ik] = qvs2;                       // Calc_LZ_V2 term
+        }
+        d.zx1[ik] = bw1;
+        d.zx2[ik] = bw2;
+        // ref: hland_model.py:4039-4051 Calc_InRC_V3
+        if (zt != HB_ILAKE) {
+          const double weight = ldg(kzk + KZ_W_LAND * ep);
+          if (zt == HB_SEALED) inrc_c += weight * r;
+          else inrc_c += weight * (qab1 + qab2);
+        }
+        SERZ(HB_S_QAB1, k, qab1); SERZ(HB_S_QVS1, k, qvs1); SERZ(HB_S_QAB2, k, qab2); SERZ(HB_S_QVS2, k, qvs2);
+        SERZ(HB_S_BW1, k, bw1); SERZ(HB_S_BW2, k, bw2);
+      }
+    }
+    if (MODEL == HB_MODEL_HLAND_96P) {
+      // ref: hland_model.py:3556-3576 Calc_RG2_SG2_V1, 3646-3665 Calc_RG3_SG3_V1
+      double rg2, rg3;
+      {
+        double s_ = sg2, g_ = gr2, k3 = d.ke[KE_K3 * ep + e], w3 = d.ke[KE_W3 * ep + e];
+        if ((s_ < 0.0) && (0.0 < g_)) {
+          const double a = -sg2;
+          const double add = HB_PYMIN(a, g_);
+          k3 *= g_ / add;
+          w3 = hb_exp(-1.0 / k3, T);
+          s_ += add;
+          g_ -= add;
+        }
+        if (s_ >= 0.0) { sg2 = w3 * s_ + (1.0 - w3) * k3 * g_; rg2 = s_ + g_ - sg2; }
+        else { sg2 = s_; rg2 = 0.0; }
+      }
+      {
+        double s_ = sg3, g_ = gr3, k4_ = k4, w4 = d.ke[KE_W4 * ep + e];
+        if ((s_ < 0.0) && (0.0 < g_)) {
+          const double a = -sg3;
+          const double add = HB_PYMIN(a, g_);
+          k4_ *= g_ / add;
+          w4 = hb_exp(-1.0 / k4_, T);
+          s_ += add;
+          g_ -= add;
+        }
+        if (s_ >= 0.0) { sg3 = w4 * s_ + (1.0 - w4) * k4_ * g_; rg3 = s_ + g_ - sg3; }
+        else { sg3 = s_; rg3 = 0.0; }
+      }
+      // ref: hland_model.py:3444-3460 Calc_EL_SG2_SG3_AETModel_V1
+      if (einfo & HB_EI_LAKE)
+        for (int k = 0; k < nz; ++k) {
+          const int64_t ik = (int64_t)k * ep + e;
+          if (HB_ZI_TYPE(d.zinfo[ik]) == HB_ILAKE) {
+            const double weight = d.kz[((int64_t)k * KZ_COUNT + KZ_W_LZ) * ep + e], el = d.scr_b[ik];
+            sg2 -= d.ke[KE_FSG * ep + e] * weight * el;
+            sg3 -= d.ke[KE_OMFSG * ep + e] * weight * el;
+          }
+        }
+      // ref: hland_model.py:3975-3984 Calc_InRC_V2
+      double inrc = rellower * (rg2 + rg3);
+      for (int k = 0; k < nz; ++k) {
+        const int64_t ik = (int64_t)k * ep + e;
+        if (HB_ZI_TYPE(d.zinfo[ik]) != HB_ILAKE) inrc += d.kz[((int64_t)k * KZ_COUNT + KZ_RELZONEAREA) * ep + e] * d.scr_a[ik];
+      }
+      // ref: hland_model.py:4109-4116 Calc_OutRC_V1, 4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
+      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      const double qt = qfactor * outrc;
+      d.qt[t * ep + e] = qt;
+      SERE(HB_S_GR2, gr2); SERE(HB_S_GR3, gr3); SERE(HB_S_RG2, rg2); SERE(HB_S_RG3, rg3); SERE(HB_S_SG2, sg2);
+      SERE(HB_S_SG3, sg3); SERE(HB_S_INRC, inrc); SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, outrc); SERE(HB_S_QT, qt);
+      continue;
+    }
+    if (MODEL == HB_MODEL_HLAND_96C) {
+      // ref: hland_model.py:4109-4116 Calc_OutRC_V1
+      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc_c);
+      // ref: hland_model.py:3172-3181 Calc_LZ_V2 (scr_a: pc of ILAKE zones, qvs2 of FIELD/FOREST/GLACIER zones)
+      for (int k = 0; k < nz; ++k) {
+        const int64_t ik = (int64_t)k * ep + e;
+        if (HB_ZI_TYPE(d.zinfo[ik]) != HB_SEALED) lz += d.kz[((int64_t)k * KZ_COUNT + KZ_W_LZ) * ep + e] * d.scr_a[ik];
+      }
+      // ref: hland_model.py:3724-3737 Calc_EL_LZ_AETModel_V1
+      if (einfo & HB_EI_LAKE)
+        for (int k = 0; k < nz; ++k) {
+          const int64_t ik = (int64_t)k * ep + e;
+          if (HB_ZI_TYPE(d.zinfo[ik]) == HB_ILAKE) lz -= d.kz[((int64_t)k * KZ_COUNT + KZ_W_LZ) * ep + e] * d.scr_b[ik];
+        }
+      // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1
+      double q1 = 0.0;
+      if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
+      lz -= q1;
+      // ref: hland_model.py:4168-4171 Calc_RT_V2, 4197-4200 Calc_QT_V1
+      const double rt = d.ke[KE_RELLANDAREA * ep + e] * outrc + rellower * q1;
+      const double qt = qfactor * rt;
+      d.qt[t * ep + e] = qt;
+      SERE(HB_S_Q1, q1); SERE(HB_S_INRC, inrc_c); SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, rt); SERE(HB_S_QT, qt);
+      SERE(HB_S_LZ, lz);
+      continue;
     }
     if (einfo & HB_EI_RESPAREA) contriarea = hb_pow(contriarea, beta_last, T);
     SERE(HB_S_INUZ, inuz); SERE(HB_S_CONTRIAREA, contriarea);
@@ -576,11 +841,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
         if (HB_ZI_TYPE(d.zinfo[ik]) == HB_SEALED) inrc += d.kz[((int64_t)k * KZ_COUNT + KZ_RELZONEAREA) * ep + e] * d.scr_a[ik];
       }
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-    double outrc = inrc;
-    if (nu > 0) {
-      outrc = ldg(d.uh + e) * inrc + d.quh[e];
-      for (int j = 1; j < nu; ++j) d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
-    }
+    const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
     d.qt[t * ep + e] = qt;
@@ -589,6 +850,7 @@ __global__ void __launch_bounds__(128) land_kernel(const LandDev d) {
   }
   d.uz[e] = uz;
   d.lz[e] = lz;
+  if (MODEL == HB_MODEL_HLAND_96P) { d.ex1[e] = sg2; d.ex2[e] = sg3; }
 #undef SERZ
 #undef SERS
 #undef SERE

@@ -22,13 +22,19 @@ import numpy as np
 from . import layout
 from .abi import LandBundle, LandStates, RiverBundle
 
-LAND_MODELS = ("hland_96",)
+LAND_MODELS = ("hland_96", "hland_96p", "hland_96c")
 RIVER_MODELS = ("musk_classic",)
 
 _ZONE_CONTROL = (
     "zonez", "pcorr", "pcalt", "rfcf", "sfcf", "tcorr", "tcalt", "icmax", "smax", "tt", "ttint", "cfmax", "cfvar",
-    "gmelt", "gvar", "cfr", "whc", "fc", "beta", "cflux",
+    "gmelt", "gvar", "cfr", "whc", "fc", "beta",
 )
+# model-specific zone parameters: (control names, derived names)
+_ZONE_EXTRA = {
+    "hland_96": (("cflux",), ()),
+    "hland_96p": (("sgr", "k2", "sg1max"), ("w0", "w1", "w2")),
+    "hland_96c": (("h1", "tab1", "tvs1", "h2", "tab2", "tvs2"), ()),
+}
 _AET_CONTROL = ("temperaturethresholdice", "maxsoilwater", "soilmoisturelimit", "excessreduction")
 _PET_CONTROL = (
     "hrualtitude", "evapotranspirationfactor", "altitudefactor", "precipitationfactor", "airtemperaturefactor",
@@ -103,7 +109,7 @@ def _check_land_model(element: Any) -> None:
     aet = getattr(model, "aetmodel", None)
     if aet is None or _modelname(aet) != "evap_aet_hbv96":
         raise UnsupportedModelError(
-            f"element `{element.name}`: hland_96 needs an `evap_aet_hbv96` AET submodel, found "
+            f"element `{element.name}`: {_modelname(model)} needs an `evap_aet_hbv96` AET submodel, found "
             f"`{None if aet is None else _modelname(aet)}`"
         )
     pet = getattr(aet, "petmodel", None)
@@ -115,10 +121,10 @@ def _check_land_model(element: Any) -> None:
     if getattr(aet, "snowycanopymodel", None) is not None:
         raise UnsupportedModelError(f"element `{element.name}`: snowy-canopy submodels are not supported")
     rconc = getattr(model, "rconcmodel", None)
-    if rconc is not None and _modelname(rconc) != "rconc_uh":
+    if rconc is not None and _modelname(rconc) not in ("rconc_uh", "rconc_nash"):
         raise UnsupportedModelError(
-            f"element `{element.name}`: only `rconc_uh` (or no) runoff concentration submodel is supported, found "
-            f"`{_modelname(rconc)}`"
+            f"element `{element.name}`: only `rconc_uh`, `rconc_nash` (or no) runoff concentration submodel is supported, "
+            f"found `{_modelname(rconc)}`"
         )
     for seq in (model.sequences.inputs.p, model.sequences.inputs.t, pet.sequences.inputs.normalairtemperature,
                 pet.sequences.inputs.normalevapotranspiration):
@@ -152,8 +158,14 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
     epar = np.zeros((len(layout.EPAR), ne))
     zt_l, zf_l, zo_l, zp_l, sf_l, uh_l, sr_f, sr_t, sr_a = [], [], [], [], [], [], [], [], []
     ic_l, sm_l, sp_l, wc_l, quh_l = [], [], [], [], []
+    suz_l, sg1_l, bw1_l, bw2_l = [], [], [], []
     uz = np.zeros(ne)
     lz = np.zeros(ne)
+    sg2 = np.zeros(ne)
+    sg3 = np.zeros(ne)
+    model_id = np.zeros(ne, np.int32)
+    rconc_kind = np.zeros(ne, np.int32)
+    nash_steps = np.zeros(ne, np.int32)
     nt = i1 - i0
     forcing = np.zeros((4, nt, ne))
     doy = None
@@ -168,25 +180,46 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         zone_ptr[e + 1] = zone_ptr[e] + nz
         snow_ptr[e + 1] = snow_ptr[e] + nz * nc
         sfdist_ptr[e + 1] = sfdist_ptr[e] + nc
-        recstep[e] = int(con.recstep.value)
-        eflags[e] = layout.EF_RESPAREA if bool(con.resparea.value) else 0
+        mname = _modelname(model)
+        model_id[e] = layout.MODELS[mname]
         ep = layout.EP
         epar[ep["z"], e] = der.z.value
-        epar[ep["relsoilarea"], e] = der.relsoilarea.value
         epar[ep["rellandarea"], e] = der.rellandarea.value
-        epar[ep["relupperzonearea"], e] = der.relupperzonearea.value
         epar[ep["rellowerzonearea"], e] = der.rellowerzonearea.value
-        epar[ep["percmax"], e] = con.percmax.value
-        epar[ep["dt"], e] = der.dt.value
-        epar[ep["alpha"], e] = con.alpha.value
-        epar[ep["k"], e] = con.k.value
-        epar[ep["k4"], e] = con.k4.value
-        epar[ep["gamma"], e] = con.gamma.value
         epar[ep["qfactor"], e] = der.qfactor.value
+        epar[ep["dt"], e] = 1.0
+        if mname == "hland_96":
+            # ref: hydpy/models/hland_96.py (control RecStep, RespArea, PercMax, Alpha, K, K4, Gamma)
+            recstep[e] = int(con.recstep.value)
+            eflags[e] = layout.EF_RESPAREA if bool(con.resparea.value) else 0
+            epar[ep["relsoilarea"], e] = der.relsoilarea.value
+            epar[ep["relupperzonearea"], e] = der.relupperzonearea.value
+            epar[ep["percmax"], e] = con.percmax.value
+            epar[ep["dt"], e] = der.dt.value
+            epar[ep["alpha"], e] = con.alpha.value
+            epar[ep["k"], e] = con.k.value
+            epar[ep["k4"], e] = con.k4.value
+            epar[ep["gamma"], e] = con.gamma.value
+        elif mname == "hland_96p":
+            # ref: hydpy/models/hland_96p.py (control PercMax, K3; derived W3, K4, W4; fixed FSG)
+            epar[ep["percmax"], e] = con.percmax.value
+            epar[ep["k3"], e] = con.k3.value
+            epar[ep["w3"], e] = der.w3.value
+            epar[ep["k4"], e] = der.k4.value
+            epar[ep["w4"], e] = der.w4.value
+            epar[ep["fsg"], e] = model.parameters.fixed.fsg.value
+        else:
+            # ref: hydpy/models/hland_96c.py (control K4, Gamma)
+            epar[ep["k4"], e] = con.k4.value
+            epar[ep["gamma"], e] = con.gamma.value
         epar[ep["petaltitude"], e] = pet.parameters.derived.altitude.value
         zp = np.zeros((len(layout.ZPAR), nz))
         for name in _ZONE_CONTROL:
             zp[layout.ZP[name]] = _f(getattr(con, name), nz)
+        for name in _ZONE_EXTRA[mname][0]:
+            zp[layout.ZP[name]] = _f(getattr(con, name), nz)
+        for name in _ZONE_EXTRA[mname][1]:
+            zp[layout.ZP[name]] = _f(getattr(der, name), nz)
         zp[layout.ZP["ttm"]] = _f(der.ttm, nz)
         zp[layout.ZP["relzonearea"]] = _f(der.relzoneareas, nz)
         for name in _AET_CONTROL:
@@ -217,7 +250,21 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
             sr_t.append(order[:, 1].astype(np.int32))
             sr_a.append(ratios[order[:, 0], order[:, 1]] * sred[order[:, 0], order[:, 1]])
         rconc = getattr(model, "rconcmodel", None)
-        if rconc is not None:
+        if rconc is not None and _modelname(rconc) == "rconc_nash":
+            # ref: hydpy/models/rconc_nash.py — the uh range holds the NmbStorages cells of states.sc
+            rconc_kind[e] = layout.RCONC_NASH
+            rcon, rder = rconc.parameters.control, rconc.parameters.derived
+            nst = int(rcon.nmbstorages.value)
+            nash_steps[e] = int(rcon.nmbsteps.value)
+            epar[ep["nash_ksc"], e] = rder.ksc.value
+            epar[ep["nash_dt"], e] = rder.dt.value
+            sc = np.array(rconc.sequences.states.sc.value, dtype=np.float64).reshape(-1)
+            if len(sc) != nst:
+                raise ValueError(f"element `{element.name}`: `sc` must have nmbstorages entries")
+            uh_l.append(np.zeros(nst))
+            quh_l.append(sc)
+            uh_ptr[e + 1] = uh_ptr[e] + nst
+        elif rconc is not None:
             uh = np.array(rconc.parameters.control.uh.value, dtype=np.float64).reshape(-1)
             quh = np.array(rconc.sequences.logs.quh.value, dtype=np.float64).reshape(-1)
             if quh.shape != uh.shape:
@@ -232,8 +279,19 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         sm_l.append(_f(sta.sm, nz))
         sp_l.append(np.array(sta.sp.value, dtype=np.float64).reshape(nc * nz))
         wc_l.append(np.array(sta.wc.value, dtype=np.float64).reshape(nc * nz))
-        uz[e] = sta.uz.value
-        lz[e] = sta.lz.value
+        zeros = np.zeros(nz)
+        if mname == "hland_96":
+            uz[e] = sta.uz.value
+            lz[e] = sta.lz.value
+        elif mname == "hland_96p":
+            sg2[e] = sta.sg2.value
+            sg3[e] = sta.sg3.value
+        else:
+            lz[e] = sta.lz.value
+        suz_l.append(_f(sta.suz, nz) if mname == "hland_96p" else zeros)
+        sg1_l.append(_f(sta.sg1, nz) if mname == "hland_96p" else zeros)
+        bw1_l.append(_f(sta.bw1, nz) if mname == "hland_96c" else zeros)
+        bw2_l.append(_f(sta.bw2, nz) if mname == "hland_96c" else zeros)
         inp = model.sequences.inputs
         pinp = pet.sequences.inputs
         forcing[0, :, e] = inp.p.series[i0:i1]
@@ -259,11 +317,13 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         zpar=np.concatenate(zp_l, axis=1) if zp_l else np.zeros((len(layout.ZPAR), 0)),
         sfdist=cat(sf_l, np.float64), uh=cat(uh_l, np.float64), sred_from=cat(sr_f, np.int32),
         sred_to=cat(sr_t, np.int32), sred_adjust=cat(sr_a, np.float64),
+        model=model_id, rconc=rconc_kind, nash_steps=nash_steps,
     )
     land.normalise()
     states = LandStates(
         ic=cat(ic_l, np.float64), sm=cat(sm_l, np.float64), sp=cat(sp_l, np.float64), wc=cat(wc_l, np.float64),
-        uz=uz, lz=lz, quh=cat(quh_l, np.float64),
+        uz=uz, lz=lz, quh=cat(quh_l, np.float64), suz=cat(suz_l, np.float64), sg1=cat(sg1_l, np.float64),
+        bw1=cat(bw1_l, np.float64), bw2=cat(bw2_l, np.float64), sg2=sg2, sg3=sg3,
     )
     if doy is None:
         doy = np.zeros(nt, np.int64)
@@ -401,8 +461,8 @@ def requested_series(problem: Problem) -> list[str]:
     for name in layout.SERIES:
         group = layout.SERIES_GROUP[name]
         for element in problem.land_elements:
-            seq = getattr(getattr(element.model.sequences, group), name)
-            if seq.ramflag:
+            seq = getattr(getattr(element.model.sequences, group), name, None)   # sibling models own different sequences
+            if seq is not None and seq.ramflag:
                 wanted.append(name)
                 break
     return wanted
@@ -435,11 +495,25 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
         _set_state(sta.sm, states.sm[z0:z1])
         _set_state(sta.sp, states.sp[s0:s1].reshape(nc, nz))
         _set_state(sta.wc, states.wc[s0:s1].reshape(nc, nz))
-        _set_state(sta.uz, float(states.uz[e]))
-        _set_state(sta.lz, float(states.lz[e]))
+        mid = int(land.model[e])
+        if mid == layout.MODEL_HLAND_96:
+            _set_state(sta.uz, float(states.uz[e]))
+            _set_state(sta.lz, float(states.lz[e]))
+        elif mid == layout.MODEL_HLAND_96P:
+            _set_state(sta.suz, states.suz[z0:z1])
+            _set_state(sta.sg1, states.sg1[z0:z1])
+            _set_state(sta.sg2, float(states.sg2[e]))
+            _set_state(sta.sg3, float(states.sg3[e]))
+        else:
+            _set_state(sta.bw1, states.bw1[z0:z1])
+            _set_state(sta.bw2, states.bw2[z0:z1])
+            _set_state(sta.lz, float(states.lz[e]))
         u0, u1 = int(land.uh_ptr[e]), int(land.uh_ptr[e + 1])
         if u1 > u0:
-            model.rconcmodel.sequences.logs.quh.value = states.quh[u0:u1]
+            if int(land.rconc[e]) == layout.RCONC_NASH:
+                _set_state(model.rconcmodel.sequences.states.sc, states.quh[u0:u1])
+            else:
+                model.rconcmodel.sequences.logs.quh.value = states.quh[u0:u1]
         out = model.sequences.outlets.q
         if getattr(out, "ramflag", False):
             out.series[i0:i1] = land_rows[e]
@@ -447,8 +521,8 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
             out.value = float(land_rows[e, last])
         for name, data in series.items():
             group = layout.SERIES_GROUP[name]
-            seq = getattr(getattr(model.sequences, group), name)
-            if not seq.ramflag:
+            seq = getattr(getattr(model.sequences, group), name, None)
+            if seq is None or not seq.ramflag:
                 continue
             if name in layout.SERIES_ZONE:
                 seq.series[i0:i1] = data[:, z0:z1]

@@ -6,7 +6,7 @@ truth.  Names follow the reference's parameter/sequence names (`hydpy/models/hla
 """
 from __future__ import annotations
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # zone types, `hydpy/models/hland/hland_constants.py`
 FIELD, FOREST, GLACIER, ILAKE, SEALED = 1, 2, 3, 4, 5
@@ -21,30 +21,57 @@ ZPAR = (
     "cfvar", "gmelt", "gvar", "cfr", "whc", "fc", "beta", "cflux", "relzonearea", "temperaturethresholdice",
     "maxsoilwater", "soilmoisturelimit", "excessreduction", "hrualtitude", "evapotranspirationfactor",
     "altitudefactor", "precipitationfactor", "airtemperaturefactor", "hruareafraction",
+    # hland_96p
+    "sgr", "w0", "w1", "k2", "w2", "sg1max",
+    # hland_96c
+    "h1", "tab1", "tvs1", "h2", "tab2", "tvs2",
 )
+N_ZPAR_V1 = 32
 ZP = {name: i for i, name in enumerate(ZPAR)}
 
 EPAR = (
     "z", "relsoilarea", "rellandarea", "relupperzonearea", "rellowerzonearea", "percmax", "dt", "alpha", "k", "k4",
     "gamma", "qfactor", "petaltitude",
+    # hland_96p
+    "k3", "w3", "w4", "fsg",
+    # rconc_nash
+    "nash_ksc", "nash_dt",
 )
+N_EPAR_V1 = 13
+
+# application model of a land element / its runoff concentration submodel
+MODEL_HLAND_96, MODEL_HLAND_96P, MODEL_HLAND_96C = 0, 1, 2
+MODELS = {"hland_96": MODEL_HLAND_96, "hland_96p": MODEL_HLAND_96P, "hland_96c": MODEL_HLAND_96C}
+RCONC_UH, RCONC_NASH = 0, 1
 EP = {name: i for i, name in enumerate(EPAR)}
 
 FORCING = ("p", "t", "normalairtemperature", "normalevapotranspiration")
 
-SERIES_ZONE = (
+SERIES_ZONE1 = (
     "tc", "fracrain", "cfact", "gact", "pc", "ei", "tf", "spl", "wcl", "spg", "wcg", "glmelt", "in_", "r", "sr",
     "ea", "cf", "el", "ic", "sm",
 )
 SERIES_SNOW = ("swe", "melt", "refr", "sp", "wc")
-SERIES_ELEM = ("contriarea", "inuz", "perc", "q0", "q1", "inrc", "outrc", "rt", "qt", "uz", "lz")
-SERIES = SERIES_ZONE + SERIES_SNOW + SERIES_ELEM
+SERIES_ELEM1 = ("contriarea", "inuz", "perc", "q0", "q1", "inrc", "outrc", "rt", "qt", "uz", "lz")
+#: the sequences of hland_96 (the first block of enum hb_series)
+SERIES_96 = SERIES_ZONE1 + SERIES_SNOW + SERIES_ELEM1
+# sibling models (second block): hland_96p zone/element sequences, hland_96c zone sequences
+SERIES_ZONE2 = ("dp", "rs", "ri", "gr1", "rg1", "suz", "sg1", "qab1", "qvs1", "qab2", "qvs2", "bw1", "bw2")
+SERIES_ELEM2 = ("gr2", "gr3", "rg2", "rg3", "sg2", "sg3")
+SERIES = SERIES_96 + SERIES_ZONE2 + SERIES_ELEM2
+SERIES_ZONE = SERIES_ZONE1 + SERIES_ZONE2
+SERIES_ELEM = SERIES_ELEM1 + SERIES_ELEM2
 S = {name: i for i, name in enumerate(SERIES)}
+#: which application models own a sequence (cells of other elements stay NaN)
+SERIES_96P_ONLY = ("dp", "rs", "ri", "gr1", "rg1", "suz", "sg1", "gr2", "gr3", "rg2", "rg3", "sg2", "sg3")
+SERIES_96C_ONLY = ("qab1", "qvs1", "qab2", "qvs2", "bw1", "bw2")
+SERIES_NOT_96P = ("cf", "contriarea", "inuz", "perc", "q0", "q1", "uz", "lz")
+SERIES_NOT_96C = ("cf", "contriarea", "inuz", "perc", "q0", "uz")
 
 #: sequence subgroup of every land series in the reference model (`model.sequences.<group>.<name>`)
 SERIES_GROUP = {
     **{n: "factors" for n in ("tc", "fracrain", "cfact", "gact", "swe", "contriarea")},
-    **{n: "states" for n in ("ic", "sm", "sp", "wc", "uz", "lz")},
+    **{n: "states" for n in ("ic", "sm", "sp", "wc", "uz", "lz", "suz", "sg1", "sg2", "sg3", "bw1", "bw2")},
 }
 for _n in SERIES:
     SERIES_GROUP.setdefault(_n, "fluxes")

@@ -56,6 +56,8 @@ def subset_land(land: LandBundle, states: LandStates, elements: np.ndarray, outl
         idx = np.concatenate([np.arange(ptr_[e], ptr_[e + 1]) for e in elements] + [np.zeros(0, np.int64)]).astype(np.int64)
         return new_ptr, idx
 
+    land.normalise()
+    states.normalise()
     zp, zi = csr(land.zone_ptr)
     sp, si = csr(land.snow_ptr)
     fp, fi = csr(land.sfdist_ptr)
@@ -66,17 +68,22 @@ def subset_land(land: LandBundle, states: LandStates, elements: np.ndarray, outl
         eflags=land.eflags[elements], forcing_col=land.forcing_col[elements], outlet_node=outlet_node,
         epar=land.epar[:, elements], zonetype=land.zonetype[zi], zflags=land.zflags[zi], zorder=land.zorder[zi],
         zpar=land.zpar[:, zi], sfdist=land.sfdist[fi], uh=land.uh[ui], sred_from=land.sred_from[ri],
-        sred_to=land.sred_to[ri], sred_adjust=land.sred_adjust[ri])
+        sred_to=land.sred_to[ri], sred_adjust=land.sred_adjust[ri], model=land.model[elements],
+        rconc=land.rconc[elements], nash_steps=land.nash_steps[elements])
     sub.normalise()
     st = LandStates(ic=states.ic[zi], sm=states.sm[zi], sp=states.sp[si], wc=states.wc[si], uz=states.uz[elements],
-                    lz=states.lz[elements], quh=states.quh[ui])
+                    lz=states.lz[elements], quh=states.quh[ui], suz=states.suz[zi], sg1=states.sg1[zi],
+                    bw1=states.bw1[zi], bw2=states.bw2[zi], sg2=states.sg2[elements], sg3=states.sg3[elements])
     return sub, st
 
 
 def scatter_states(shard: Shard, local: LandStates, land: LandBundle, out: LandStates) -> None:
     """Write a shard's final states back into the global state arrays."""
+    local.normalise()
+    out.normalise()
     for which, ptr_ in (("ic", land.zone_ptr), ("sm", land.zone_ptr), ("sp", land.snow_ptr), ("wc", land.snow_ptr),
-                        ("quh", land.uh_ptr)):
+                        ("quh", land.uh_ptr), ("suz", land.zone_ptr), ("sg1", land.zone_ptr), ("bw1", land.zone_ptr),
+                        ("bw2", land.zone_ptr)):
         src = getattr(local, which)
         dst = getattr(out, which)
         pos = 0
@@ -86,6 +93,8 @@ def scatter_states(shard: Shard, local: LandStates, land: LandBundle, out: LandS
             pos += n
     out.uz[shard.elements] = local.uz
     out.lz[shard.elements] = local.lz
+    out.sg2[shard.elements] = local.sg2
+    out.sg3[shard.elements] = local.sg3
 
 
 def assign_nodes(land: LandBundle, river: RiverBundle, world: int) -> np.ndarray:

@@ -101,7 +101,7 @@ def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, 
         eflags=np.full(ne, int(tpl["eflags"][0]), np.int32), forcing_col=(np.arange(ne) % bank).astype(np.int32),
         outlet_node=(np.arange(ne) if own_nodes else np.full(ne, -1)).astype(np.int32), epar=epar,
         zonetype=zonetype.reshape(-1), zflags=zflags.reshape(-1), zorder=zorder.reshape(-1),
-        zpar=zpar.reshape(len(layout.ZPAR), ne * nz), sfdist=np.ones(ne), uh=np.tile(tpl["uh"], ne),
+        zpar=zpar.reshape(zpar.shape[0], ne * nz), sfdist=np.ones(ne), uh=np.tile(tpl["uh"], ne),
         sred_from=np.zeros(0, np.int32), sred_to=np.zeros(0, np.int32), sred_adjust=np.zeros(0),
     )
     land.normalise()
@@ -190,6 +190,7 @@ def replicate_members(land: LandBundle, states: LandStates, members: int, *, see
     set (member 0 = the given values), sharing structure and forcing columns.  Members become additional elements."""
     m = int(members)
     rng = np.random.default_rng(seed)
+    land.normalise()
     ne, nz = land.n_elem, land.n_zone
     node_stride = int(n_node) if n_node is not None else (int(land.outlet_node.max()) + 1 if ne else 0)
 
@@ -223,9 +224,11 @@ def replicate_members(land: LandBundle, states: LandStates, members: int, *, see
         epar=epar.reshape(len(layout.EPAR), m * ne), zonetype=np.tile(land.zonetype, m), zflags=np.tile(land.zflags, m),
         zorder=np.tile(land.zorder, m), zpar=zpar.reshape(len(layout.ZPAR), m * nz), sfdist=np.tile(land.sfdist, m),
         uh=np.tile(land.uh, m), sred_from=np.tile(land.sred_from, m), sred_to=np.tile(land.sred_to, m),
-        sred_adjust=np.tile(land.sred_adjust, m),
+        sred_adjust=np.tile(land.sred_adjust, m), model=np.tile(land.model, m), rconc=np.tile(land.rconc, m),
+        nash_steps=np.tile(land.nash_steps, m),
     )
     out.normalise()
+    states.normalise()
     st = LandStates(**{n: np.tile(getattr(states, n), m) for n in LandStates.NAMES})
     return out, st
 

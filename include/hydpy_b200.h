@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------------------------------------------ */
 #define HB_OK 0
@@ -52,6 +52,16 @@ extern "C" {
 /* ---- per-element flags, bit set of `eflags[]` --------------------------------------------------------------- */
 #define HB_EF_RESPAREA 1      /* hland_control.RespArea                                                        */
 
+/* ---- application model of a land element (sibling models on the hland_96 skeleton) ------------ *
+ * `hydpy/models/hland_96.py`, `hland_96p.py` (PREVAH response: SUZ/SG1 per zone, SG2/SG3 per element),
+ * `hland_96c.py` (COSERO response: BW1/BW2 per zone, LZ per element).                                            */
+#define HB_MODEL_HLAND_96 0
+#define HB_MODEL_HLAND_96P 1
+#define HB_MODEL_HLAND_96C 2
+/* ---- runoff concentration submodel of a land element (`hydpy/models/rconc_uh.py`, `rconc_nash.py`) ------------- */
+#define HB_RCONC_UH 0     /* rconc_uh, or no submodel when the element's uh range is empty                       */
+#define HB_RCONC_NASH 1   /* rconc_nash: the uh range holds NmbStorages cells of `states.sc` (uh[] unused)        */
+
 /* ---- per-zone double parameters: rows of `zpar[HB_ZP_COUNT][n_zone]` ---------------------------------------- *
  * hland_96 control (`hydpy/models/hland/hland_control.py`), derived (`hland_derived.py`), evap_aet_hbv96 and
  * evap_pet_hbv96 control/derived (`hydpy/models/evap/evap_control.py`, `evap_derived.py`).                      */
@@ -65,6 +75,10 @@ enum hb_zpar {
   HB_ZP_HRUALTITUDE,                     /* pet control                                                        */
   HB_ZP_EVAPOTRANSPIRATIONFACTOR, HB_ZP_ALTITUDEFACTOR, HB_ZP_PRECIPITATIONFACTOR, HB_ZP_AIRTEMPERATUREFACTOR,
   HB_ZP_HRUAREAFRACTION,                 /* pet derived                                                        */
+  /* hland_96p only: control SGR, K2, SG1Max; derived W0, W1, W2 (`hland_derived.py`)                          */
+  HB_ZP_SGR, HB_ZP_W0, HB_ZP_W1, HB_ZP_K2, HB_ZP_W2, HB_ZP_SG1MAX,
+  /* hland_96c only: control H1, TAb1, TVs1, H2, TAb2, TVs2                                                     */
+  HB_ZP_H1, HB_ZP_TAB1, HB_ZP_TVS1, HB_ZP_H2, HB_ZP_TAB2, HB_ZP_TVS2,
   HB_ZP_COUNT
 };
 
@@ -72,7 +86,12 @@ enum hb_zpar {
 enum hb_epar {
   HB_EP_Z = 0 /* hland_derived.Z */, HB_EP_RELSOILAREA, HB_EP_RELLANDAREA, HB_EP_RELUPPERZONEAREA,
   HB_EP_RELLOWERZONEAREA, HB_EP_PERCMAX, HB_EP_DT /* hland_derived.DT = 1/recstep */, HB_EP_ALPHA, HB_EP_K,
-  HB_EP_K4, HB_EP_GAMMA, HB_EP_QFACTOR /* hland_derived.QFactor */, HB_EP_PETALTITUDE /* evap_derived.Altitude */,
+  HB_EP_K4 /* hland_96, hland_96c: control K4; hland_96p: derived K4 */, HB_EP_GAMMA,
+  HB_EP_QFACTOR /* hland_derived.QFactor */, HB_EP_PETALTITUDE /* evap_derived.Altitude */,
+  /* hland_96p only: control K3, derived W3, W4, fixed FSG (`hland_fixed.py`)                                    */
+  HB_EP_K3, HB_EP_W3, HB_EP_W4, HB_EP_FSG,
+  /* rconc_nash only: derived KSC, DT (`hydpy/models/rconc/rconc_derived.py`)                                    */
+  HB_EP_NASH_KSC, HB_EP_NASH_DT,
   HB_EP_COUNT
 };
 
@@ -93,12 +112,23 @@ enum hb_series {
   /* element level */
   HB_S_CONTRIAREA, HB_S_INUZ, HB_S_PERC, HB_S_Q0, HB_S_Q1, HB_S_INRC, HB_S_OUTRC, HB_S_RT, HB_S_QT, HB_S_UZ,
   HB_S_LZ,
+  /* sibling models, zone level: hland_96p fluxes DP, RS, RI, GR1, RG1 and states SUZ, SG1; hland_96c fluxes QAb1, QVs1,
+   * QAb2, QVs2 and states BW1, BW2 (cells of elements of another model keep NaN) */
+  HB_S_DP, HB_S_RS, HB_S_RI, HB_S_GR1, HB_S_RG1, HB_S_SUZ, HB_S_SG1,
+  HB_S_QAB1, HB_S_QVS1, HB_S_QAB2, HB_S_QVS2, HB_S_BW1, HB_S_BW2,
+  /* sibling models, element level: hland_96p fluxes GR2, GR3, RG2, RG3 and states SG2, SG3 */
+  HB_S_GR2, HB_S_GR3, HB_S_RG2, HB_S_RG3, HB_S_SG2, HB_S_SG3,
   HB_S_COUNT
 };
 #define HB_S_FIRST_SNOW HB_S_SWE
 #define HB_S_FIRST_ELEM HB_S_CONTRIAREA
+#define HB_S_FIRST_ZONE2 HB_S_DP    /* second block of zone-level series */
+#define HB_S_FIRST_ELEM2 HB_S_GR2   /* second block of element-level series */
+/* level of a series: 0 zone [nt][n_zone], 1 snow [nt][n_snow], 2 element [nt][n_elem] */
+#define HB_S_LEVEL(s) ((s) < HB_S_FIRST_SNOW ? 0 : (s) < HB_S_FIRST_ELEM ? 1 : (s) < HB_S_FIRST_ZONE2 ? 2 : (s) < HB_S_FIRST_ELEM2 ? 0 : 2)
 
-/* ---- land description: all hland_96 elements (+ evap_aet_hbv96/evap_pet_hbv96, optional rconc_uh) ----------- *
+/* ---- land description: all hland_96 / hland_96p / hland_96c elements (+ evap_aet_hbv96/evap_pet_hbv96, optional
+ * rconc_uh / rconc_nash) --------------------------------------------------------------------------------------- *
  * Replaces the per-element `Parameters`/`ControlParameters`/`DerivedParameters` extension types of
  * `c_hland_96.pyx`, `c_evap_aet_hbv96.pyx`, `c_evap_pet_hbv96.pyx`, `c_rconc_uh.pyx`
  * (generator: `hydpy/cythons/modelutils.py:1000-1050`).  Ragged dimensions are CSR-encoded.                      */
@@ -128,6 +158,10 @@ typedef struct hb_land_desc {
   const int32_t* sred_from;   /* [n_sred]  hland_derived.SRedOrder[:,0] (local zone index)                      */
   const int32_t* sred_to;     /* [n_sred]  hland_derived.SRedOrder[:,1]                                         */
   const double* sred_adjust;  /* [n_sred]  ZoneAreaRatios[f,t]*SRed[f,t]  (`hland_model.py:897`)                 */
+  /* ABI 2: sibling models; each pointer may be NULL (all elements hland_96 / rconc_uh)                           */
+  const int32_t* model;       /* [n_elem]  HB_MODEL_*                                                           */
+  const int32_t* rconc;       /* [n_elem]  HB_RCONC_*                                                           */
+  const int32_t* nash_steps;  /* [n_elem]  rconc_control.NmbSteps (already scaled to the simulation step)       */
 } hb_land_desc;
 
 /* ---- land conditions: hland_96 states + rconc_uh log (`Sequences.conditions`, `sequencetools.py:807-828`) ---- */
@@ -138,7 +172,14 @@ typedef struct hb_land_states {
   double* wc;   /* [n_snow] */
   double* uz;   /* [n_elem] */
   double* lz;   /* [n_elem] */
-  double* quh;  /* [n_uh]   */
+  double* quh;  /* [n_uh]   rconc_uh logs.quh; rconc_nash states.sc                                             */
+  /* ABI 2: states of the sibling models; a pointer may be NULL when no element of that model exists             */
+  double* suz;  /* [n_zone] hland_96p */
+  double* sg1;  /* [n_zone] hland_96p */
+  double* bw1;  /* [n_zone] hland_96c */
+  double* bw2;  /* [n_zone] hland_96c */
+  double* sg2;  /* [n_elem] hland_96p */
+  double* sg3;  /* [n_elem] hland_96p */
 } hb_land_states;
 
 /* ---- river description: all musk_classic elements and the node graph --------------------------------------- *

@@ -35,6 +35,8 @@ DEFAULT_SCRATCH = os.environ.get("HYDPY_B200_REFBUILD", "/tmp/hydpy_b200_refbuil
 MODELS = (
     "hland", "hland_96", "evap", "evap_aet_hbv96", "evap_pet_hbv96",
     "rconc", "rconc_uh", "musk", "musk_classic",
+    # sibling models on the same skeleton
+    "hland_96p", "hland_96c", "rconc_nash",
 )
 
 STUBS = {
@@ -155,7 +157,18 @@ def build(reference: str = "/root/reference", scratch: str = DEFAULT_SCRATCH, fo
         for stage in (["base"], ["interface"], ["models", *MODELS]):
             _run([sys.executable, "_b200_build.py", *stage], cwd=src, env=env)
         with open(marker, "w") as f:
-            f.write("ok\n")
+            f.write("\n".join(MODELS) + "\n")
+    else:
+        # a scratch build of an earlier model list: generate and compile only what is missing
+        built = os.listdir(os.path.join(src, "hydpy", "cythons", "autogen"))
+        missing = [m for m in MODELS if not any(n.startswith(f"c_{m}.") and n.endswith(".so") for n in built)]
+        if missing:
+            env = dict(os.environ)
+            env["PYTHONPATH"] = os.pathsep.join([stubs, src, env.get("PYTHONPATH", "")])
+            env.setdefault("CC", "gcc")
+            _run([sys.executable, "_b200_build.py", "models", *missing], cwd=src, env=env)
+            with open(marker, "w") as f:
+                f.write("\n".join(MODELS) + "\n")
     # copy the binaries (and nothing else) into oracle/_ref
     os.makedirs(OUT, exist_ok=True)
     autogen = os.path.join(src, "hydpy", "cythons", "autogen")

@@ -55,24 +55,105 @@ def snapshot(hp):
                     out[f"{element.name}:states.{seq.name}:new"] = np.array(seq.new)
                     out[f"{element.name}:states.{seq.name}:old"] = np.array(seq.old)
         rc = getattr(element.model, "rconcmodel", None)
-        if rc is not None:
+        if rc is not None and rc.name == "rconc_uh":
             out[f"{element.name}:quh"] = np.array(rc.sequences.logs.quh.value)
+        elif rc is not None:
+            out[f"{element.name}:sc:new"] = np.array(rc.sequences.states.sc.new)
+            out[f"{element.name}:sc:old"] = np.array(rc.sequences.states.sc.old)
     return out
+
+
+def sibling_project():
+    """A small basin of the sibling models built through the reference's own API: one hland_96p and one
+    hland_96c element (four zones each, every zone type but ILAKE/…, rconc_nash) draining through a musk_classic reach."""
+    from hydpy import Element, Elements, HydPy, Node, Nodes
+
+    pub.timegrids = "2000-01-01", "2000-01-09", "1h"
+    n_up, n_out = Node("sib_up"), Node("sib_out")
+    e_p = Element("sib_land_p", outlets=n_up)
+    e_c = Element("sib_land_c", outlets=n_up)
+    e_r = Element("sib_reach", inlets=n_up, outlets=n_out)
+    rng = np.random.default_rng(11)
+    common = """
+parameterstep("1h")
+area(12.0)
+nmbzones(5)
+sclass(2)
+zonetype(FIELD, FOREST, GLACIER, ILAKE, SEALED)
+zonearea(3.0, 3.0, 2.0, 2.0, 2.0)
+psi(1.0)
+zonez(2.0, 3.0, 9.0, 1.0, 2.0)
+pcorr(1.1); pcalt(0.1); rfcf(1.1); sfcf(1.3); tcorr(0.6); tcalt(0.6); icmax(2.0); sfdist(0.8, 1.2); smax(inf)
+sred(0.0); tt(0.0); ttint(2.0); dttm(1.0); cfmax(0.5); cfvar(0.1); gmelt(1.0); gvar(0.2); cfr(0.1); whc(0.4)
+fc(200.0); beta(2.0)
+{special}
+with model.add_aetmodel_v1("evap_aet_hbv96"):
+    temperaturethresholdice(0.0)
+    soilmoisturelimit(0.8)
+    excessreduction(0.5)
+    with model.add_petmodel_v1("evap_pet_hbv96"):
+        evapotranspirationfactor(0.7)
+        airtemperaturefactor(0.1)
+        altitudefactor(-0.1)
+        precipitationfactor(0.1)
+with model.add_rconcmodel_v1("rconc_nash"):
+    retentiontime(3.0)
+    nmbstorages(4)
+    nmbsteps(20)
+"""
+    special = {
+        "hland_96p": "percmax(2.0); sgr(20.0); sg1max(50.0); k0(2.0); k1(10.0); k2(20.0); k3(100.0)",
+        "hland_96c": "h1(10.0); tab1(2.0); tvs1(2.0); h2(10.0); tab2(10.0); tvs2(10.0); k4(0.005); gamma(0.0)",
+    }
+    for element, name in ((e_p, "hland_96p"), (e_c, "hland_96c")):
+        ns: dict = {}
+        exec(f"from hydpy.models.{name} import *\n" + common.format(special=special[name]), ns)   # like a control file
+        element.model = ns["model"]
+    ns = {}
+    exec('from hydpy.models.musk_classic import *\nparameterstep("1h")\nnmbsegments(3)\ncoefficients(damp=0.2)\n', ns)
+    reach = ns["model"]
+    e_r.model = reach
+    hp = HydPy("sibling_project")
+    hp.update_devices(nodes=Nodes(n_up, n_out), elements=Elements(e_p, e_c, e_r))
+    hp.update_parameters()
+    hp.prepare_allseries()
+    nt = len(pub.timegrids.init)
+    for element in (e_p, e_c):
+        model = element.model
+        t = 2.0 + 8.0 * np.sin(np.arange(nt) / 24.0) + rng.normal(0.0, 2.0, nt)
+        model.sequences.inputs.p.series = rng.gamma(0.4, 2.0, nt) * (rng.uniform(size=nt) < 0.5)
+        model.sequences.inputs.t.series = t
+        pet = model.aetmodel.petmodel.sequences.inputs
+        pet.normalairtemperature.series = t - 1.0
+        pet.normalevapotranspiration.series = rng.uniform(0.0, 0.4, nt)
+        sta = model.sequences.states
+        sta.ic(0.5); sta.sp(1.0); sta.wc(0.1); sta.sm(100.0)
+        if model.name == "hland_96p":
+            sta.suz(1.0); sta.sg1(10.0); sta.sg2(10.0); sta.sg3(10.0)
+        else:
+            sta.bw1(2.0); sta.bw2(3.0); sta.lz(10.0)
+        model.rconcmodel.sequences.states.sc(0.05)
+    reach.sequences.states.discharge(0.0)
+    return hp, (("2000-01-01", "2000-01-04"), ("2000-01-04", "2000-01-09"))
 
 
 def main() -> None:
     del pub.projectname
     del pub.timegrids
     pub.options.prepare_testing(usecython=True, threads=0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        hp, _, _ = testtools.prepare_full_example_2(lastdate="1996-03-01")
-    for element in hp.elements:
-        seqs = element.model.sequences
-        for group in ("factors", "fluxes", "states"):
-            for seq in getattr(seqs, group):
-                seq.prepare_series(allocate_ram=True)
-    # two consecutive simulation windows inside the initialisation period, as in hydpy/core/hydpytools.py:2804-2825
-    windows = (("1996-01-01", "1996-02-01"), ("1996-02-01", "1996-03-01"))
+    if "--siblings" in sys.argv:
+        with contextlib.redirect_stdout(io.StringIO()):
+            hp, windows = sibling_project()
+    else:
+        with contextlib.redirect_stdout(io.StringIO()):
+            hp, _, _ = testtools.prepare_full_example_2(lastdate="1996-03-01")
+        for element in hp.elements:
+            seqs = element.model.sequences
+            for group in ("factors", "fluxes", "states"):
+                for seq in getattr(seqs, group):
+                    seq.prepare_series(allocate_ram=True)
+        # two consecutive simulation windows inside the initialisation period, as in hydpy/core/hydpytools.py:2804-2825
+        windows = (("1996-01-01", "1996-02-01"), ("1996-02-01", "1996-03-01"))
 
     import copy
 

@@ -9,6 +9,7 @@ What is produced (all under tests/golden/):
   factor/flux/state series, the outlet node series and the final conditions as raw float64.  While harvesting, the
   docstring is executed by ``doctest``, so the reference build is at the same time checked against its own printed
   6-digit tables.
+* ``hland_96p_integration.npz``, ``hland_96c_integration.npz`` — the same for the sibling models (``--siblings``).
 * ``musk_classic_integration.npz`` — the 3 integration tests of ``hydpy/models/musk_classic.py``.
 * ``lahn_daily.npz`` — the HydPy-H-Lahn example project, 1996-01-01…1998-01-01 daily (config 1 of BASELINE.json):
   problem + all four gauge series + land outflows + final conditions + a few state series.
@@ -57,8 +58,8 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
         arr = np.full((nt, width), np.nan)
         have = False
         for e, element in enumerate(problem.land_elements):
-            seq = getattr(getattr(element.model.sequences, group), name)
-            if not seq.ramflag:
+            seq = getattr(getattr(element.model.sequences, group), name, None)
+            if seq is None or not seq.ramflag:
                 continue
             have = True
             data = np.asarray(seq.series[i0:i1], dtype=np.float64)
@@ -295,6 +296,12 @@ def write_template(daily: dict[str, np.ndarray], hourly: dict[str, np.ndarray]) 
 
 
 def main() -> None:
+    if "--siblings" in sys.argv:
+        # the integration tests of the sibling models' own docstrings (hland_96p: 4, hland_96c: 6 distinct
+        # scenarios, all with rconc_nash)
+        for name in ("hland_96p", "hland_96c"):
+            save_scenarios(os.path.join(HERE, f"{name}_integration.npz"), harvest_module(f"hydpy.models.{name}"))
+        return
     save_scenarios(os.path.join(HERE, "hland_96_integration.npz"), harvest_module("hydpy.models.hland_96"))
     save_scenarios(os.path.join(HERE, "musk_classic_integration.npz"), harvest_module("hydpy.models.musk_classic"))
     daily = lahn_daily()

@@ -125,6 +125,75 @@ def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recst
     return land, states
 
 
+def add_siblings(land: LandBundle, states: LandStates, seed: int = 0, fraction: float = 0.6, nash_fraction: float = 0.6
+                 ) -> None:
+    """Turn `fraction` of the elements into hland_96p / hland_96c elements and give `nash_fraction` of
+    ALL elements a rconc_nash submodel (their uh range becomes the storage cascade) — in place, with its own random
+    stream, so the hland_96 part of the bundle stays what `random_land` drew."""
+    rng = np.random.default_rng(seed + 99)
+    land.normalise()
+    states.normalise()
+    ne, NZ = land.n_elem, land.n_zone
+    ZP, EP = layout.ZP, layout.EP
+    pick = rng.uniform(size=ne)
+    land.model[:] = np.where(pick < fraction / 2, layout.MODEL_HLAND_96P,
+                             np.where(pick < fraction, layout.MODEL_HLAND_96C, layout.MODEL_HLAND_96))
+    zmodel = np.repeat(land.model, np.diff(land.zone_ptr))
+    U = lambda lo, hi, n=NZ: rng.uniform(lo, hi, size=n)  # noqa: E731
+    upper = np.isin(land.zonetype, (1, 2, 3))
+    # hland_96p: control SGR, K2, SG1Max; derived W0 = exp(-1/K0), W1 = exp(-1/K1), W2 = exp(-1/K2), …
+    p = zmodel == layout.MODEL_HLAND_96P
+    k2 = U(10, 200)
+    for name, val in (("sgr", U(2, 30)), ("w0", np.exp(-1.0 / U(2, 20))), ("w1", np.exp(-1.0 / U(10, 100))),
+                      ("k2", k2), ("w2", np.exp(-1.0 / k2)), ("sg1max", U(5, 60))):
+        land.zpar[ZP[name]] = np.where(p, val, 0.0)
+    ep_ = land.model == layout.MODEL_HLAND_96P
+    k3, k4 = rng.uniform(50, 800, ne), rng.uniform(500, 5000, ne)
+    land.epar[EP["k3"]] = np.where(ep_, k3, 0.0)
+    land.epar[EP["w3"]] = np.where(ep_, np.exp(-1.0 / k3), 0.0)
+    land.epar[EP["w4"]] = np.where(ep_, np.exp(-1.0 / k4), 0.0)
+    land.epar[EP["fsg"]] = np.where(ep_, 8.0 / 9.0, 0.0)
+    land.epar[EP["k4"]] = np.where(ep_, k4, land.epar[EP["k4"]])
+    land.epar[EP["percmax"]] = np.where(ep_, rng.uniform(0.05, 1.5, ne), land.epar[EP["percmax"]])
+    # hland_96c: control H1, TAb1, TVs1, H2, TAb2, TVs2 (zero and infinite time constants hit the special branches)
+    c = zmodel == layout.MODEL_HLAND_96C
+
+    def tconst(lo, hi):
+        v = U(lo, hi)
+        r = rng.uniform(size=NZ)
+        return np.where(r < 0.08, 0.0, np.where(r < 0.16, np.inf, v))
+
+    for name, val in (("h1", U(0, 15)), ("tab1", tconst(1, 40)), ("tvs1", tconst(1, 80)), ("h2", U(0, 30)),
+                      ("tab2", tconst(5, 100)), ("tvs2", tconst(5, 200))):
+        land.zpar[ZP[name]] = np.where(c, val, 0.0)
+    # (two degenerate time constants at once divide 0/0 or inf/inf in the reference as well: keep one regular)
+    for a, b in (("tab1", "tvs1"), ("tab2", "tvs2")):
+        both = (~np.isfinite(land.zpar[ZP[a]]) | (land.zpar[ZP[a]] == 0.0)) & \
+               (~np.isfinite(land.zpar[ZP[b]]) | (land.zpar[ZP[b]] == 0.0)) & c
+        land.zpar[ZP[b]] = np.where(both, 7.0, land.zpar[ZP[b]])
+    sib = land.model != layout.MODEL_HLAND_96
+    land.epar[EP["dt"]] = np.where(sib, 1.0, land.epar[EP["dt"]])
+    land.recstep[:] = np.where(sib, 0, land.recstep)
+    land.eflags[:] = np.where(sib, 0, land.eflags)
+    states.suz[:] = np.where(p & upper, U(0, 10), 0.0)
+    states.sg1[:] = np.where(p & upper, U(0, 20), 0.0)
+    states.bw1[:] = np.where(c & upper, U(0, 20), 0.0)
+    states.bw2[:] = np.where(c & upper, U(0, 40), 0.0)
+    states.sg2[:] = np.where(ep_, rng.uniform(-2, 30, ne), 0.0)
+    states.sg3[:] = np.where(ep_, rng.uniform(-2, 60, ne), 0.0)
+    states.uz[:] = np.where(sib, 0.0, states.uz)
+    states.lz[:] = np.where(ep_, 0.0, states.lz)
+    # rconc_nash
+    nash = rng.uniform(size=ne) < nash_fraction
+    land.rconc[:] = np.where(nash, layout.RCONC_NASH, layout.RCONC_UH)
+    steps = rng.integers(1, 9, size=ne)
+    land.nash_steps[:] = np.where(nash, steps, 0)
+    ksc = np.where(rng.uniform(size=ne) < 0.1, np.inf, rng.uniform(0.05, 2.5, ne))
+    land.epar[EP["nash_ksc"]] = np.where(nash, ksc, 0.0)
+    land.epar[EP["nash_dt"]] = np.where(nash, 1.0 / steps, 0.0)
+    land.normalise()
+
+
 def random_forcing(nt: int, ncol: int, seed: int = 0) -> tuple[np.ndarray, np.ndarray]:
     rng = np.random.default_rng(seed + 1000)
     p = rng.gamma(0.4, 2.0, size=(nt, ncol)) * (rng.uniform(size=(nt, ncol)) < 0.5)

@@ -19,3 +19,12 @@ def test_simulate_leaves_hydpy_objects_like_the_reference_does():
                           text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "DROPIN_OK" in proc.stdout
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+def test_simulate_sibling_models_like_the_reference_does():
+    """hland_96p + hland_96c + rconc_nash elements built through the reference API."""
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_worker.py"), "--siblings"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "DROPIN_OK" in proc.stdout

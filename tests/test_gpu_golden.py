@@ -13,6 +13,8 @@ from tests.util import assert_close, load_scenarios
 pytestmark = pytest.mark.gpu
 
 HLAND = load_scenarios("hland_96_integration.npz")
+HLAND_P = load_scenarios("hland_96p_integration.npz")
+HLAND_C = load_scenarios("hland_96c_integration.npz")
 MUSK = load_scenarios("musk_classic_integration.npz")
 LAHN = load_scenarios("lahn_daily.npz")
 LAHN_H = load_scenarios("lahn_hourly_members.npz")
@@ -42,7 +44,8 @@ def run_and_check(engine, sc, window=None):
     wb = p.node_writeback
     assert_close(res["node_rows"][wb], sc.expected("node_rows")[wb], f"{sc.name}:node series")
     for n in res["states"].NAMES:
-        assert_close(getattr(res["states"], n), sc.expected("state_" + n), f"{sc.name}:final state {n}")
+        if sc.expected("state_" + n) is not None:   # fixtures of ABI 1 do not hold the sibling models' states
+            assert_close(getattr(res["states"], n), sc.expected("state_" + n), f"{sc.name}:final state {n}")
     assert_close(res["discharge"], sc.expected("discharge"), f"{sc.name}:final discharge")
     if sc.expected("reach_out") is not None:
         assert_close(res["reach_out"], sc.expected("reach_out"), f"{sc.name}:reach outflow")
@@ -56,7 +59,8 @@ def run_and_check(engine, sc, window=None):
     res0 = run_problem(p, engine, window=window)
     assert_close(res0["node_rows"][wb], sc.expected("node_rows")[wb], f"{sc.name}:node series (discharge-only run)")
     for n in res0["states"].NAMES:
-        assert_close(getattr(res0["states"], n), sc.expected("state_" + n), f"{sc.name}:final state {n} (discharge-only)")
+        if sc.expected("state_" + n) is not None:
+            assert_close(getattr(res0["states"], n), sc.expected("state_" + n), f"{sc.name}:final state {n} (discharge-only)")
     assert_close(res0["discharge"], sc.expected("discharge"), f"{sc.name}:final discharge (discharge-only run)")
     return res, worst
 
@@ -64,6 +68,18 @@ def run_and_check(engine, sc, window=None):
 @pytest.mark.parametrize("name", sorted(HLAND))
 def test_hland_96_integration(engine, name):
     run_and_check(engine, HLAND[name])
+
+
+@pytest.mark.parametrize("name", sorted(HLAND_P))
+def test_hland_96p_integration(engine, name):
+    """hland_96p + rconc_nash, all 41 sequences of the reference's six integration tests."""
+    run_and_check(engine, HLAND_P[name])
+
+
+@pytest.mark.parametrize("name", sorted(HLAND_C))
+def test_hland_96c_integration(engine, name):
+    """hland_96c + rconc_nash, all 36 sequences of the reference's six integration tests."""
+    run_and_check(engine, HLAND_C[name])
 
 
 @pytest.mark.parametrize("name", sorted(MUSK))

@@ -5,7 +5,7 @@ import pytest
 
 from hydpy_b200 import Engine, Problem, layout, run_problem, synth
 from oracle import oracle
-from tests.randland import random_forcing, random_land, random_river
+from tests.randland import add_siblings, random_forcing, random_land, random_river
 from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -63,6 +63,31 @@ def test_random_ragged_problem_all_series(engine, seed):
     res2 = run_problem(problem, engine, window=17)
     for key in ("land_rows", "node_rows", "reach_out", "discharge"):
         assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_ragged_problem_with_sibling_models(engine, seed):
+    """hland_96, hland_96p and hland_96c elements with rconc_uh / rconc_nash / no submodel side by side in one basin
+    (SURVEY.md §8f-3): every sequence against the oracle; cells of sequences a model does not own are NaN on both sides."""
+    ne, nt = 160, 72
+    land, states = random_land(ne, seed=seed + 20)
+    add_siblings(land, states, seed=seed + 20)
+    assert len(set(land.model.tolist())) == 3 and len(set(land.rconc.tolist())) == 2
+    forcing, doy = random_forcing(nt, ne, seed=seed + 20)
+    river, discharge, _ = random_river(ne, 50, seed=seed + 20, n_ext=0)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    ref = oracle_run(problem, series=layout.SERIES)
+    res = run_problem(problem, engine, series=layout.SERIES)
+    compare(res, ref, f"siblings seed {seed}", series=layout.SERIES)
+    assert np.isnan(res["series"]["dp"][:, np.repeat(land.model, np.diff(land.zone_ptr)) != layout.MODEL_HLAND_96P]).all()
+    res1 = run_problem(problem, engine)
+    compare(res1, ref, f"siblings seed {seed} (no series)")
+    res2 = run_problem(problem, engine, window=13)
+    for key in ("land_rows", "node_rows", "reach_out", "discharge"):
+        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+    for n in res1["states"].NAMES:
+        assert np.array_equal(getattr(res1["states"], n), getattr(res2["states"], n), equal_nan=True), n
 
 
 def test_long_reaches_more_than_32_segments(engine):

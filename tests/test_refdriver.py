@@ -23,7 +23,7 @@ def test_lahn_daily_through_reference_binaries():
     node_rows, rout, rin = refdriver.run_river(p.river, dis, qt, p.ext)
     assert np.array_equal(node_rows, sc.expected("node_rows"))
     assert np.array_equal(rout, sc.expected("reach_out"))
-    for n in st.NAMES:
+    for n in st.NAMES_V1:
         assert np.array_equal(getattr(st, n), sc.expected("state_" + n)), n
     assert np.array_equal(dis, sc.expected("discharge"))
     sm = np.concatenate([el.series["sm"] for el in els], axis=1)
