@@ -148,10 +148,12 @@ struct hb_engine {
   std::vector<int32_t> general_list;  // elements of the general kernel in the current combination of paths
   // sibling models: hland_96p / hland_96c elements always run through the general kernel, instantiated
   // for their model
-  std::vector<int32_t> h_model, sibling_list[2];
+  std::vector<int32_t> h_model, all_siblings[2], sibling_list[2];   // all / those the general kernel takes in this run
   DBuf<int32_t> d_sibling_list[2], d_nash_steps;
   DBuf<double> d_zx1, d_zx2, d_ex1, d_ex2;   // hland_96p suz, sg1, sg2, sg3 | hland_96c bw1, bw2
   bool any_sibling = false;
+  int64_t n_fast_sib[2] = {0, 0};            // their elements eligible for the two-kernel fast path
+  bool any_nonsoil_sib[2] = {false, false};
   std::vector<int32_t> h_einfo;
   int general_key = -1;
   DBuf<int32_t> d_coupled_list, d_general_list;
@@ -449,7 +451,7 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
-  int64_t n_fast = 0;
+  int64_t n_fast = 0, n_fast_sib[2] = {0, 0};
   std::vector<int32_t> coupled_list;
 #define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
 #define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
@@ -543,10 +545,17 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       if (zt != HB_FIELD && zt != HB_FOREST) soilonly = false;
       if ((zt == HB_FIELD || zt == HB_FOREST) && !(ZP(CFLUX, zz) == 0.0)) coupled = true;
     }
-    if (model[e] != HB_MODEL_HLAND_96) { info &= ~HB_EI_RESPAREA; }   // general kernel, instantiated for the model
-    else if (nash[e] != 0) { }                                        // rconc_nash: general kernel (the fast paths convolve a unit hydrograph)
+    if (model[e] != HB_MODEL_HLAND_96) {
+      // sibling models have neither a contributing area nor a capillary flux: the time-split fast path always applies
+      info &= ~HB_EI_RESPAREA;
+      if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1) { info |= HB_EI_FAST; ++n_fast_sib[model[e] - 1]; }
+    }
     else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
-    else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX) { info |= HB_EI_COUPLED; coupled_list.push_back((int32_t)e); }
+    else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX && nash[e] == 0) {
+      info |= HB_EI_COUPLED;          // (the fused kernel convolves a unit hydrograph: rconc_nash elements stay general)
+      coupled_list.push_back((int32_t)e);
+    }
+    info |= model[e] << HB_EI_MODEL_SHIFT;
     if (soilonly) info |= HB_EI_SOILONLY;
     if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
     einfo[e] = info;
@@ -578,24 +587,24 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = ne ? d->sred_ptr[ne] : 0;
   h->any_snowlimit = any_snowlimit;
   h->any_nonsoil_warp = false;
-  for (int64_t e = 0; e < ne && !h->any_nonsoil_warp; ++e) {
+  h->any_nonsoil_sib[0] = h->any_nonsoil_sib[1] = false;
+  for (int64_t e = 0; e < ne; ++e) {
     if (!(einfo[e] & HB_EI_FAST)) continue;
+    bool& flag = model[e] == HB_MODEL_HLAND_96 ? h->any_nonsoil_warp : h->any_nonsoil_sib[model[e] - 1];
+    if (flag) continue;
     for (int k = 0; k < nz[e]; ++k) {
       const int zt = zinfo[(size_t)k * ep + e] & 7;
       const double fc = kz[((size_t)k * KZ_COUNT + KZ_FC) * ep + e];
-      if (!((zt == HB_FIELD || zt == HB_FOREST) && fc > 0.0)) { h->any_nonsoil_warp = true; break; }
+      if (!((zt == HB_FIELD || zt == HB_FOREST) && fc > 0.0)) { flag = true; break; }
     }
   }
   h->n_fast = n_fast;
+  h->n_fast_sib[0] = n_fast_sib[0]; h->n_fast_sib[1] = n_fast_sib[1];
   h->coupled_list = coupled_list;
   if (h->h_model != model) h->have_states = false;
   h->h_model = model;
   h->any_sibling = !siblings[0].empty() || !siblings[1].empty();
-  for (int m = 0; m < 2; ++m) {
-    h->sibling_list[m] = siblings[m];
-    int rc_ = upload(h, h->d_sibling_list[m], siblings[m]);
-    if (rc_) return rc_;
-  }
+  for (int m = 0; m < 2; ++m) h->all_siblings[m] = siblings[m];
   { int rc_ = upload(h, h->d_nash_steps, nash); if (rc_) return rc_; }
   h->h_einfo.assign(einfo.begin(), einfo.begin() + ne);
   h->general_key = -1;
@@ -1136,22 +1145,31 @@ static int run_land(hb_engine* h) {
   const bool use_fast = h->n_fast > 0 && h->land_path == HB_LAND_AUTO && !(any_series && h->zmax > 128);
   // elements with capillary flux: fused kernel (no series recording there)
   const bool use_coupled = !h->coupled_list.empty() && h->land_path == HB_LAND_AUTO && !any_series;
+  // sibling models on the fast path: only without series (their zone sequences have no staging buffers)
+  const bool use_fast_sib = (h->n_fast_sib[0] + h->n_fast_sib[1]) > 0 && h->land_path == HB_LAND_AUTO && !any_series;
   // the general kernel takes every element the two special paths do not take in this run
-  const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0);
+  const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0) | (use_fast_sib ? 4 : 0);
   if (general_key != h->general_key) {
     h->general_list.clear();
+    h->sibling_list[0].clear(); h->sibling_list[1].clear();
     for (int64_t e = 0; e < h->n_elem; ++e) {
       const int info = h->h_einfo[e];
+      const int m = h->h_model[e];
+      if (m != HB_MODEL_HLAND_96) {   // sibling models: own instances of the general kernel
+        if (!(use_fast_sib && (info & HB_EI_FAST))) h->sibling_list[m - 1].push_back((int32_t)e);
+        continue;
+      }
       if ((use_fast && (info & HB_EI_FAST)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
-      if (h->h_model[e] != HB_MODEL_HLAND_96) continue;   // sibling models: own launches below
       h->general_list.push_back((int32_t)e);
     }
     int rc = upload(h, h->d_general_list, h->general_list);
     if (rc) return rc;
+    for (int m = 0; m < 2; ++m)
+      if ((rc = upload(h, h->d_sibling_list[m], h->sibling_list[m]))) return rc;
     h->general_key = general_key;
   }
   const int64_t n_general = (int64_t)h->general_list.size();
-  h->timing.n_fast = use_fast ? h->n_fast : 0;
+  h->timing.n_fast = (use_fast ? h->n_fast : 0) + (use_fast_sib ? h->n_fast_sib[0] + h->n_fast_sib[1] : 0);
   if (h->n_elem == 0 || nt == 0) return HB_OK;
   for (int s = 0; s < HB_S_COUNT; ++s) {
     if (!h->series_on[s]) continue;
@@ -1165,7 +1183,7 @@ static int run_land(hb_engine* h) {
     if (partial) HB_CUDA(h, cudaMemsetAsync(h->d_series[s].p, 0xFF, (size_t)nt * width * sizeof(double), h->stream));
   }
 
-  if (use_fast) {
+  if (use_fast || use_fast_sib) {
     LandV2Dev v{};
     v.n_elem = h->n_elem; v.e_pad = ep; v.zmax = h->zmax;
     v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
@@ -1174,6 +1192,7 @@ static int run_land(hb_engine* h) {
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
     v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow;
+    v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
     int n_staged = 0;
     for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
     // time chunks bound the two term buffers (3 GB each at most)
@@ -1211,12 +1230,26 @@ static int run_land(hb_engine* h) {
       v.t_out = c0;
       h->mark(HB_K_OTHER);
       const unsigned zgrid = (unsigned)(per_step / 128), egrid = (unsigned)((h->n_elem + 63) / 64);
-      if (any_series) zone_kernel<true, true><<<zgrid, 128, 0, h->stream>>>(v);
-      else zone_kernel<true, false><<<zgrid, 128, 0, h->stream>>>(v);
-      if (h->any_nonsoil_warp) {
-        if (any_series) zone_kernel<false, true><<<zgrid, 128, 0, h->stream>>>(v);
-        else zone_kernel<false, false><<<zgrid, 128, 0, h->stream>>>(v);
+      if (use_fast) {
+        if (any_series) zone_kernel<true, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
+        else zone_kernel<true, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
+        if (h->any_nonsoil_warp) {
+          if (any_series) zone_kernel<false, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
+          else zone_kernel<false, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
+          h->timing.land_launches += 1;
+        }
         h->timing.land_launches += 1;
+      }
+      // sibling models: the same grid, instantiated for their model (threads of other models retire at once)
+      if (use_fast_sib && h->n_fast_sib[0] > 0) {
+        zone_kernel<true, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, h->stream>>>(v);
+        if (h->any_nonsoil_sib[0]) zone_kernel<false, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, h->stream>>>(v);
+        h->timing.land_launches += 1 + (h->any_nonsoil_sib[0] ? 1 : 0);
+      }
+      if (use_fast_sib && h->n_fast_sib[1] > 0) {
+        zone_kernel<true, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, h->stream>>>(v);
+        if (h->any_nonsoil_sib[1]) zone_kernel<false, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, h->stream>>>(v);
+        h->timing.land_launches += 1 + (h->any_nonsoil_sib[1] ? 1 : 0);
       }
       if (n_staged) {
         dim3 sg((unsigned)((h->n_elem + 31) / 32), (unsigned)(v.nt < 64 ? v.nt : 64));
@@ -1231,10 +1264,20 @@ static int run_land(hb_engine* h) {
         }
       }
       h->mark(HB_K_ZONE);
-      if (any_series) element_kernel<true><<<egrid, 64, 0, h->stream>>>(v);
-      else element_kernel<false><<<egrid, 64, 0, h->stream>>>(v);
+      if (use_fast) {
+        if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, 0, h->stream>>>(v);
+        else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, 0, h->stream>>>(v);
+        h->timing.land_launches += 1;
+      }
+      if (use_fast_sib && h->n_fast_sib[0] > 0) {
+        element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, 0, h->stream>>>(v);
+        h->timing.land_launches += 1;
+      }
+      if (use_fast_sib && h->n_fast_sib[1] > 0) {
+        element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, 0, h->stream>>>(v);
+        h->timing.land_launches += 1;
+      }
       h->mark(HB_K_ELEMENT);
-      h->timing.land_launches += 2;
     }
     HB_CUDA(h, cudaGetLastError());
   }

@@ -91,6 +91,8 @@ enum ke {
 #define HB_EI_FAST 16      // eligible for the two-kernel fast path: one snow class, no snow limit, every CFlux == 0
 #define HB_EI_SOILONLY 32  // all zones are FIELD or FOREST
 #define HB_EI_COUPLED 64   // like HB_EI_FAST but with CFlux > 0 somewhere: fused kernel (land_kernel_coupled.cuh)
+#define HB_EI_MODEL_SHIFT 8   // bits 8..9: HB_MODEL_* of the element
+#define HB_EI_MODEL(i) (((i) >> HB_EI_MODEL_SHIFT) & 3)
 
 // zone info: bits 0..2 zone type, bits 8.. zflags (HB_ZF_*)
 #define HB_ZI_TYPE(i) ((i) & 7)

@@ -69,6 +69,12 @@ struct LandV2Dev {
   // fused kernel for elements with capillary flux (land_kernel_coupled.cuh)
   const int32_t* clist;    // their indices
   int64_t n_clist;
+  // sibling models (hland_96p / hland_96c) and rconc_nash
+  const int32_t* nash_steps;  // [E_pad] see LandDev
+  double* zx1;             // [zmax][E_pad] hland_96p suz | hland_96c bw1
+  double* zx2;             // [zmax][E_pad] hland_96p sg1 | hland_96c bw2
+  double* ex1;             // [E_pad] hland_96p sg2
+  double* ex2;             // [E_pad] hland_96p sg3
 };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
@@ -76,6 +82,33 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
   double* dst = reinterpret_cast<double*>(s);
   for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
   __syncthreads();
+}
+
+// hland_96p, one FIELD/FOREST/GLACIER zone: Calc_SUZ_V1, Calc_DP_SUZ_V1, Calc_RS_RI_SUZ_V1, Calc_GR1_V1, Calc_RG1_SG1_V1
+// (ref: hland_model.py:2132-2140, 2525-2535, 3012-3033, 3233-3243, 3290-3304).  fast = rs + ri + rg1 (Calc_InRC_V2 term),
+// deep = dp - gr1 (Calc_GR2_GR3_V1 term).
+__device__ __forceinline__ void response_96p(double r, double percmax, double sgr, double omw0, double omw1, double k2,
+                                             double w2, double omw2k2, double sg1max, double& suz, double& sg1,
+                                             double& dp, double& rs, double& ri, double& gr1, double& rg1) {
+  suz += r;
+  dp = HB_PYMIN(suz, percmax);
+  suz -= dp;
+  rs = (suz > sgr) ? (suz - sgr) * omw0 : 0.0;
+  ri = suz * omw1;
+  suz -= rs + ri;
+  if (suz < 0.0) {
+    const double f = 1.0 - suz / (rs + ri);
+    rs *= f;
+    ri *= f;
+    suz = 0.0;
+  }
+  const double sg1_old = sg1;
+  const double b = (sg1max - sg1_old) / k2;
+  gr1 = HB_PYMIN(dp, b);
+  const double a = sg1_old + gr1 - sg1max;
+  gr1 -= HB_PYMAX(a, 0.0);
+  sg1 = w2 * sg1_old + omw2k2 * gr1;
+  rg1 = sg1_old + gr1 - sg1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -88,8 +121,11 @@ __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g)
 #endif
 // SOIL = true : the warps whose 32 zones are all FIELD/FOREST with FC > 0 (branch-free step); SOIL = false: all other warps
 // SERIES = true additionally records the requested hland_96 zone sequences (the HBM-bound regime of SURVEY.md §8d-ii)
-template <bool SOIL, bool SERIES>
-__global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2Dev d) {
+// MODEL = HB_MODEL_HLAND_96 / _96P / _96C: every instance works on the fast-path elements of its model only (einfo carries
+// the model).  The sibling models share everything up to the soil routine; their zone response (hland_96p: SUZ, SG1;
+// hland_96c: BW1, BW2) replaces the contributing-area factor, needs no pow() and seven more constants (5 blocks per SM).
+template <bool SOIL, bool SERIES, int MODEL>
+__global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOCKS : 5) zone_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
@@ -99,7 +135,7 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
   const int64_t e = slot - (int64_t)k * ep;
   if (e >= d.n_elem) return;
   const int einfo = d.einfo[e];
-  if (!(einfo & HB_EI_FAST) || k >= d.nz[e]) return;
+  if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL || k >= d.nz[e]) return;
 
   const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
 #define KZ(name) kzk[(int64_t)(name) * ep]
@@ -116,17 +152,42 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
                beta = KZ(KZ_BETA), thresh = KZ(KZ_THRESH), inv_thresh = KZ(KZ_INV_THRESH), excessred = KZ(KZ_EXCESSRED),
                atf = KZ(KZ_ATF), etf = KZ(KZ_ETF), alt_f = KZ(KZ_ALT_F), neg_pf = KZ(KZ_NEG_PF);
   // type-dependent constants share registers
-  const double w_a = soil || zt == HB_GLACIER ? KZ(KZ_W_UZ) : zt == HB_ILAKE ? KZ(KZ_W_LZ) : KZ(KZ_RELZONEAREA);
-  const double w_b = soil ? KZ(KZ_W_CONTRI) : KZ(KZ_W_LZ);
+  // hland_96:  term_a = w_a * (r - cf) | pc | r,  term_b = contributing-area factor | w_b * el
+  // hland_96p: term_a = relzonearea * (rs + ri + rg1) | relzonearea * r (SEALED) | el (ILAKE),  term_b = w_b * (dp - gr1) | w_b * pc
+  // hland_96c: term_a = w_land * (qab1 + qab2) | w_land * r (SEALED) | el (ILAKE),              term_b = w_b * qvs2 | w_b * pc
+  const double w_a = MODEL == HB_MODEL_HLAND_96P   ? KZ(KZ_RELZONEAREA)
+                     : MODEL == HB_MODEL_HLAND_96C ? KZ(KZ_W_LAND)
+                     : soil || zt == HB_GLACIER    ? KZ(KZ_W_UZ)
+                     : zt == HB_ILAKE              ? KZ(KZ_W_LZ)
+                                                   : KZ(KZ_RELZONEAREA);
+  const double w_b = (MODEL == HB_MODEL_HLAND_96 && soil) ? KZ(KZ_W_CONTRI) : KZ(KZ_W_LZ);
+  const bool upper = soil || zt == HB_GLACIER;
   const double g_melt = zt == HB_GLACIER ? KZ(KZ_GMELT) : 0.0, g_var = zt == HB_GLACIER ? KZ(KZ_GVAR) : 0.0;
   const double tti = zt == HB_ILAKE ? KZ(KZ_TTI) : 0.0;
 #undef KZ
+#define KZX(name) kzk[(int64_t)(name) * ep]
   const double sf = d.sfdist[e];
   double ic = d.ic[slot], sm = d.sm[slot], sp = d.sp[slot], wc = d.wc[slot];
+  double zx1 = 0.0, zx2 = 0.0;
+  if (MODEL != HB_MODEL_HLAND_96) { zx1 = d.zx1[slot]; zx2 = d.zx2[slot]; }
   // The constants move on to shared memory ([constant][thread], conflict-free, 29 KB per block): 72 registers per thread
   // instead of 128, 7 instead of 4 warps per scheduler, and room for the routing blocks of the previous window beside them.
   // (ncu: the step is then issue-bound — ≈410 warp instructions per zone-step at ≈80 % issue-slot utilisation.)
-  __shared__ double s_c[28][128];
+  __shared__ double s_c[MODEL == HB_MODEL_HLAND_96 ? 28 : 36][128];
+  if (MODEL != HB_MODEL_HLAND_96) {
+    s_c[28][threadIdx.x] = KZX(KZ_X0); s_c[29][threadIdx.x] = KZX(KZ_X1); s_c[30][threadIdx.x] = KZX(KZ_X2);
+    s_c[31][threadIdx.x] = KZX(KZ_X3); s_c[32][threadIdx.x] = KZX(KZ_X4); s_c[33][threadIdx.x] = KZX(KZ_X5);
+    s_c[34][threadIdx.x] = KZX(KZ_X6);
+    s_c[35][threadIdx.x] = d.ke[KE_DT_PERCMAX * ep + e];   // hland_96p: PercMax (dt = 1)
+  }
+#define kx0 s_c[28][threadIdx.x]
+#define kx1 s_c[29][threadIdx.x]
+#define kx2 s_c[30][threadIdx.x]
+#define kx3 s_c[31][threadIdx.x]
+#define kx4 s_c[32][threadIdx.x]
+#define kx5 s_c[33][threadIdx.x]
+#define kx6 s_c[34][threadIdx.x]
+#define kpercmax s_c[35][threadIdx.x]
   s_c[0][threadIdx.x] = tcorr;
   s_c[1][threadIdx.x] = tcalt_dz;
   s_c[2][threadIdx.x] = tt_hi;
@@ -289,13 +350,14 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         r = HB_PYMAX(r, a2);
       }
       sm += in_ - r;
-      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0
-      double cf = 0.0 * (1.0 - sm * inv_fc);
-      {
+      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0 (hland_96 only)
+      double cf = 0.0;
+      if (MODEL == HB_MODEL_HLAND_96) {
+        cf = 0.0 * (1.0 - sm * inv_fc);
         const double b = fc - sm;
         cf = HB_PYMIN(cf, b);
+        sm += cf;
       }
-      sm += cf;
       // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1 (6657-6672, 7001-7018, 7060-7069)
       double set = pet;
       {
@@ -321,11 +383,24 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         sm = over ? fc : sm;
       }
       SERZ(HB_S_R, r); SERZ(HB_S_CF, cf); SERZ(HB_S_EA, ea); SERZ(HB_S_SM, sm);
-      // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
-      const double contri = hb_pow(sm * inv_fc, w_b, T);
-      HB_ZONE_STEP_END(w_a * (r - cf), resp ? contri : 1.0)
+      if (MODEL == HB_MODEL_HLAND_96) {
+        // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
+        const double contri = hb_pow(sm * inv_fc, w_b, T);
+        HB_ZONE_STEP_END(w_a * (r - cf), resp ? contri : 1.0)
+      } else if (MODEL == HB_MODEL_HLAND_96P) {
+        double dp, rs, ri, gr1, rg1;
+        response_96p(r, kpercmax, kx0, kx1, kx2, kx3, kx4, kx5, kx6, zx1, zx2, dp, rs, ri, gr1, rg1);
+        HB_ZONE_STEP_END(w_a * (rs + ri + rg1), w_b * (dp - gr1))
+      } else {
+        // ref: hland_model.py:2833-2853 Calc_QAb1_QVs1_BW1_V1, 2927-2947 Calc_QAb2_QVs2_BW2_V1
+        double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
+        qab_qvs_bw(kx0, kx1, kx2, zx1, r, qab1, qvs1, T);
+        qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
+        HB_ZONE_STEP_END(w_a * (qab1 + qab2), w_b * qvs2)
+      }
     }
     d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
+    if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
     return;
   }
 
@@ -413,7 +488,8 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
     if (icept) { s_ei = HB_PYMIN(aet_ie, ic); ic -= s_ei; }
     else ic = 0.0;
     SERZ(HB_S_EI, s_ei); SERZ(HB_S_IC, ic);
-    double ta, tb = 1.0;
+    double ta = 0.0, tb = 1.0;
+    double r_z = in_;                 // r of the zone (non-soil zones: r = in_)
     if (soil) {
       // ref: hland_model.py:1776-1790 Calc_R_SM_V1
       double r;
@@ -423,9 +499,9 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
         r = HB_PYMAX(r, a);
       } else r = in_;
       sm += in_ - r;
-      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0: cf = min(0*(1 - sm/fc), fc - sm)
+      // ref: hland_model.py:1904-1919 Calc_CF_SM_V1 with CFlux == 0: cf = min(0*(1 - sm/fc), fc - sm); hland_96 only
       double cf = 0.0;
-      if (fc > 0.0) {
+      if (MODEL == HB_MODEL_HLAND_96 && fc > 0.0) {
         cf = 0.0 * (1.0 - sm * inv_fc);
         const double b = fc - sm;
         cf = HB_PYMIN(cf, b);
@@ -450,8 +526,11 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       sm -= ea;
       if (sm > fc) { r += sm - fc; sm = fc; }
       // ref: hland_model.py:2092-2101 Calc_InUZ_V1 (term), 2224-2236 Calc_ContriArea_V1 (factor)
-      ta = w_a * (r - cf);
-      if (resp && fc > 0.0) tb = hb_pow(sm * inv_fc, w_b, T);
+      r_z = r;
+      if (MODEL == HB_MODEL_HLAND_96) {
+        ta = w_a * (r - cf);
+        if (resp && fc > 0.0) tb = hb_pow(sm * inv_fc, w_b, T);
+      }
       SERZ(HB_S_R, r); SERZ(HB_S_CF, cf); SERZ(HB_S_EA, ea); SERZ(HB_S_SM, sm); SERZ(HB_S_EL, 0.0);
     } else {
       sm = 0.0;
@@ -459,11 +538,27 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
       if (zt == HB_ILAKE) {
         // ref: hland_model.py:3113-3124 Calc_LZ_V1 (term), 3724-3737 Calc_EL_LZ_AETModel_V1 (term);
         // evap_model.py:5673-5681 Calc_WaterEvaporation_V1
-        ta = w_a * pc;
         el = ((zf & HB_ZF_WATER) && tc > tti) ? pet : 0.0;
-        tb = w_b * el;
+        if (MODEL == HB_MODEL_HLAND_96) { ta = w_a * pc; tb = w_b * el; }
+        else { ta = el; tb = w_b * pc; }   // hland_96p: Calc_EL_SG2_SG3 / Calc_GR2_GR3 terms; hland_96c: Calc_EL_LZ / Calc_LZ_V2
       } else ta = w_a * (in_ - 0.0);  // GLACIER: InUZ term; SEALED: InRC term (r = in_, ref: hland_model.py:1528-1535)
       SERZ(HB_S_R, in_); SERZ(HB_S_CF, 0.0); SERZ(HB_S_EA, 0.0); SERZ(HB_S_SM, 0.0); SERZ(HB_S_EL, el);
+    }
+    if (MODEL != HB_MODEL_HLAND_96) {
+      if (upper) {
+        if (MODEL == HB_MODEL_HLAND_96P) {
+          double dp, rs, ri, gr1, rg1;
+          response_96p(r_z, kpercmax, kx0, kx1, kx2, kx3, kx4, kx5, kx6, zx1, zx2, dp, rs, ri, gr1, rg1);
+          ta = w_a * (rs + ri + rg1);
+          tb = w_b * (dp - gr1);
+        } else {
+          double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
+          qab_qvs_bw(kx0, kx1, kx2, zx1, r_z, qab1, qvs1, T);
+          qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
+          ta = w_a * (qab1 + qab2);
+          tb = w_b * qvs2;
+        }
+      } else { zx1 = 0.0; zx2 = 0.0; }   // ILAKE (terms set above), SEALED (ta = w_a * r)
     }
     HB_ZONE_STEP_END(ta, tb)
   }
@@ -499,7 +594,17 @@ __global__ void __launch_bounds__(128, HB_ZONE_BLOCKS) zone_kernel(const LandV2D
 #undef w_a
 #undef w_b
 #undef sf
+#undef kx0
+#undef kx1
+#undef kx2
+#undef kx3
+#undef kx4
+#undef kx5
+#undef kx6
+#undef kpercmax
+#undef KZX
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
+  if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
 }
 
 // staging layout [nt][zmax][E_pad]  →  ABI layout [nt_window][width] for the zones (or snow cells) of the fast-path
@@ -537,7 +642,7 @@ __global__ void __launch_bounds__(256) series_scatter_kernel(const double* __res
 #ifndef HB_ELEM_BLOCKS
 #define HB_ELEM_BLOCKS 12
 #endif
-template <bool SERIES>
+template <bool SERIES, int MODEL>
 __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
@@ -545,9 +650,10 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.n_elem) return;
   const int einfo = d.einfo[e];
-  if (!(einfo & HB_EI_FAST)) return;
+  if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
+  const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
   const double dt = d.ke[KE_DT * ep + e], dt_percmax = d.ke[KE_DT_PERCMAX * ep + e], dt_k = d.ke[KE_DT_K * ep + e],
                alpha1 = d.ke[KE_ALPHA1 * ep + e], k4 = d.ke[KE_K4 * ep + e], gamma1 = d.ke[KE_GAMMA1 * ep + e],
                relupper = d.ke[KE_RELUPPER * ep + e], rellower = d.ke[KE_RELLOWER * ep + e],
@@ -556,6 +662,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const bool resp = (einfo & HB_EI_RESPAREA) != 0, soilonly = (einfo & HB_EI_SOILONLY) != 0;
   const bool square = (alpha1 == 2.0);
   double uz = d.uz[e], lz = d.lz[e];
+  double sg2 = 0.0, sg3 = 0.0;
+  if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
   const int64_t tstride = (int64_t)d.zmax * ep;
   for (int64_t t = 0; t < d.nt; ++t) {
     const double* ta = d.term_a + t * tstride + e;
@@ -574,6 +682,88 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
 #endif
       }
 #endif
+    if (MODEL == HB_MODEL_HLAND_96P) {
+      // ref: hland_model.py:3356-3372 Calc_GR2_GR3_V1 (tb = weight * (dp - gr1) | weight * pc, in zone order)
+      const double fsg = d.ke[KE_FSG * ep + e], omfsg = d.ke[KE_OMFSG * ep + e];
+      double gr2 = 0.0, gr3 = 0.0;
+      for (int k = 0; k < nz; ++k) {
+        if (!soilonly && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) continue;
+        const double total = tb[(int64_t)k * ep];
+        gr2 += fsg * total;
+        gr3 += omfsg * total;
+      }
+      // ref: hland_model.py:3556-3576 Calc_RG2_SG2_V1, 3646-3665 Calc_RG3_SG3_V1
+      double rg2, rg3;
+      {
+        double s_ = sg2, g_ = gr2, k3 = d.ke[KE_K3 * ep + e], w3 = d.ke[KE_W3 * ep + e];
+        if ((s_ < 0.0) && (0.0 < g_)) {
+          const double a = -sg2;
+          const double add = HB_PYMIN(a, g_);
+          k3 *= g_ / add;
+          w3 = hb_exp(-1.0 / k3, T);
+          s_ += add;
+          g_ -= add;
+        }
+        if (s_ >= 0.0) { sg2 = w3 * s_ + (1.0 - w3) * k3 * g_; rg2 = s_ + g_ - sg2; }
+        else { sg2 = s_; rg2 = 0.0; }
+      }
+      {
+        double s_ = sg3, g_ = gr3, k4_ = k4, w4 = d.ke[KE_W4 * ep + e];
+        if ((s_ < 0.0) && (0.0 < g_)) {
+          const double a = -sg3;
+          const double add = HB_PYMIN(a, g_);
+          k4_ *= g_ / add;
+          w4 = hb_exp(-1.0 / k4_, T);
+          s_ += add;
+          g_ -= add;
+        }
+        if (s_ >= 0.0) { sg3 = w4 * s_ + (1.0 - w4) * k4_ * g_; rg3 = s_ + g_ - sg3; }
+        else { sg3 = s_; rg3 = 0.0; }
+      }
+      // ref: hland_model.py:3444-3460 Calc_EL_SG2_SG3_AETModel_V1 (ta of an ILAKE zone = el)
+      if (einfo & HB_EI_LAKE)
+        for (int k = 0; k < nz; ++k)
+          if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) {
+            const double weight = d.kz[((int64_t)k * KZ_COUNT + KZ_W_LZ) * ep + e], el = ta[(int64_t)k * ep];
+            sg2 -= fsg * weight * el;
+            sg3 -= omfsg * weight * el;
+          }
+      // ref: hland_model.py:3975-3984 Calc_InRC_V2 (ta = relzonearea * (rs + ri + rg1) | relzonearea * r)
+      double inrc = rellower * (rg2 + rg3);
+      for (int k = 0; k < nz; ++k) {
+        if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
+        inrc += ta[(int64_t)k * ep];
+      }
+      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
+      continue;
+    }
+    if (MODEL == HB_MODEL_HLAND_96C) {
+      // ref: hland_model.py:4039-4051 Calc_InRC_V3 (ta = weight * (qab1 + qab2) | weight * r, in zone order)
+      double inrc = 0.0;
+      for (int k = 0; k < nz; ++k) {
+        if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
+        inrc += ta[(int64_t)k * ep];
+      }
+      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      // ref: hland_model.py:3172-3181 Calc_LZ_V2 (tb = weight * pc | weight * qvs2)
+      for (int k = 0; k < nz; ++k) {
+        if (!soilonly && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) continue;
+        lz += tb[(int64_t)k * ep];
+      }
+      // ref: hland_model.py:3724-3737 Calc_EL_LZ_AETModel_V1 (ta of an ILAKE zone = el)
+      if (einfo & HB_EI_LAKE)
+        for (int k = 0; k < nz; ++k)
+          if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE)
+            lz -= d.kz[((int64_t)k * KZ_COUNT + KZ_W_LZ) * ep + e] * ta[(int64_t)k * ep];
+      // ref: hland_model.py:3832-3840 Calc_Q1_LZ_V1, 4168-4171 Calc_RT_V2, 4197-4200 Calc_QT_V1
+      double q1 = 0.0;
+      if (lz > 0.0) q1 = k4 * hb_pow(lz, gamma1, T);
+      lz -= q1;
+      const double rt = d.ke[KE_RELLANDAREA * ep + e] * outrc + rellower * q1;
+      d.qt[(d.t_out + t) * ep + e] = qfactor * rt;
+      continue;
+    }
     double inuz = 0.0, contriarea = 1.0;
     if (soilonly) {
       for (int k = 0; k < nz; ++k) {
@@ -657,12 +847,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       for (int k = 0; k < nz; ++k)
         if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-    double outrc = inrc;
-    if (nu > 0) {
-      outrc = ldg(d.uh + e) * inrc + d.quh[e];
-      for (int j = 1; j < nu; ++j)
-        d.quh[(int64_t)(j - 1) * ep + e] = ldg(d.uh + (int64_t)j * ep + e) * inrc + d.quh[(int64_t)j * ep + e];
-    }
+    const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
     d.qt[(d.t_out + t) * ep + e] = qt;
@@ -676,6 +861,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   }
   d.uz[e] = uz;
   d.lz[e] = lz;
+  if (MODEL == HB_MODEL_HLAND_96P) { d.ex1[e] = sg2; d.ex2[e] = sg3; }
 }
 
 }  // namespace hb

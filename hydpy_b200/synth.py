@@ -40,7 +40,7 @@ def load_template(step: str) -> dict[str, np.ndarray]:
 
 def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, bank: int = 1024,
               variants: bool = False, jitter: float = 0.1, area: float = 100.0,
-              own_nodes: bool = True, cflux: float = 0.0) -> tuple[LandBundle, LandStates]:
+              own_nodes: bool = True, cflux: float = 0.0, model: str = "hland_96") -> tuple[LandBundle, LandStates]:
     """`n_elem` synthetic hland_96 elements (configs 3-5).  `cflux` > 0 (mm per simulation step, jittered like the other
     parameters) switches the capillary flux on, i.e. couples the zones to the element's upper zone storage."""
     tpl = load_template(step)
@@ -112,7 +112,71 @@ def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, 
         sp=np.where(lakeless, 5.0, 0.0) * np.ones(ne * nz), wc=np.where(lakeless, 0.2, 0.0) * np.ones(ne * nz),
         uz=np.full(ne, 5.0), lz=np.full(ne, 8.0), quh=np.zeros(ne * nu),
     )
+    if model != "hland_96":
+        to_sibling(land, states, model, step, jitter=jitter, seed=seed)
     return land, states
+
+
+def to_sibling(land: LandBundle, states: LandStates, model: str, step: str = "1h", *, jitter: float = 0.1,
+               seed: int = 1, nash: bool = True) -> None:
+    """Turn a synthetic hland_96 bundle into `hland_96p` / `hland_96c` elements, in place: the snow
+    and soil parameters stay, the runoff response gets the values of the reference's integration tests
+    (ref: hydpy/models/hland_96p.py:83-95, hland_96c.py:83-96, internal = simulation-step related values), jittered per
+    element; `nash` swaps the unit hydrograph for a `rconc_nash` cascade of as many storages."""
+    land.normalise()
+    states.normalise()
+    rng = np.random.default_rng(seed + 77)
+    ne, nzt = land.n_elem, land.n_zone
+    per_day = 24.0 if step == "1h" else 1.0
+    ZP, EP = layout.ZP, layout.EP
+    zone_elem = np.repeat(np.arange(ne), np.diff(land.zone_ptr))
+    jit = lambda: (1.0 + jitter * rng.uniform(-1.0, 1.0, size=ne))  # noqa: E731
+    upper = np.isin(land.zonetype, (layout.FIELD, layout.FOREST, layout.GLACIER))
+    land.model[:] = layout.MODELS[model]
+    land.eflags[:] = 0
+    land.recstep[:] = 0
+    land.epar[EP["dt"]] = 1.0
+    land.zpar[ZP["cflux"]] = 0.0
+    if model == "hland_96p":
+        k0, k1, k2 = 2.0 * per_day * jit(), 10.0 * per_day * jit(), 20.0 * per_day * jit()
+        k3, k4 = 100.0 * per_day * jit(), 300.0 * per_day * jit()
+        land.zpar[ZP["sgr"]] = (20.0 * jit())[zone_elem]
+        land.zpar[ZP["sg1max"]] = (50.0 * jit())[zone_elem]
+        land.zpar[ZP["w0"]] = np.exp(-1.0 / k0)[zone_elem]
+        land.zpar[ZP["w1"]] = np.exp(-1.0 / k1)[zone_elem]
+        land.zpar[ZP["k2"]] = k2[zone_elem]
+        land.zpar[ZP["w2"]] = np.exp(-1.0 / k2)[zone_elem]
+        land.epar[EP["percmax"]] = 2.0 / per_day * jit()
+        land.epar[EP["k3"]], land.epar[EP["w3"]] = k3, np.exp(-1.0 / k3)
+        land.epar[EP["k4"]], land.epar[EP["w4"]] = k4, np.exp(-1.0 / k4)
+        land.epar[EP["fsg"]] = 8.0 / 9.0
+        states.suz[:] = np.where(upper, 1.0, 0.0)
+        states.sg1[:] = np.where(upper, 10.0, 0.0)
+        states.sg2[:] = 10.0
+        states.sg3[:] = 10.0
+        states.uz[:] = 0.0
+        states.lz[:] = 0.0
+    elif model == "hland_96c":
+        for name, days in (("tab1", 2.0), ("tvs1", 2.0), ("tab2", 10.0), ("tvs2", 10.0)):
+            land.zpar[ZP[name]] = (days * per_day * jit())[zone_elem]
+        land.zpar[ZP["h1"]] = (10.0 * jit())[zone_elem]
+        land.zpar[ZP["h2"]] = (10.0 * jit())[zone_elem]
+        states.bw1[:] = np.where(upper, 2.0, 0.0)
+        states.bw2[:] = np.where(upper, 3.0, 0.0)
+        states.uz[:] = 0.0
+    else:
+        raise ValueError(f"unknown sibling model {model!r}")
+    if nash:
+        nst = np.diff(land.uh_ptr)
+        land.rconc[:] = np.where(nst > 0, layout.RCONC_NASH, layout.RCONC_UH)
+        steps = 10
+        land.nash_steps[:] = np.where(nst > 0, steps, 0)
+        # retention time 3 h spread over the storages (ref: rconc_derived.KSC: ksc = nmbstorages / retentiontime)
+        land.epar[EP["nash_ksc"]] = np.where(nst > 0, nst / (3.0 * jit()), 0.0)
+        land.epar[EP["nash_dt"]] = np.where(nst > 0, 1.0 / steps, 0.0)
+        land.uh[:] = 0.0
+        states.quh[:] = 0.05
+    land.normalise()
 
 
 def make_forcing(nt: int, step: str = "1h", *, bank: int = 1024, seed: int = 0, t0: int = 0

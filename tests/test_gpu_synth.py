@@ -122,6 +122,24 @@ def test_synthetic_config4_slice_vs_oracle(engine):
     compare(res, ref, "config-4 slice")
 
 
+@pytest.mark.parametrize("model", ["hland_96p", "hland_96c"])
+def test_synthetic_sibling_basin_vs_oracle(engine, model):
+    """A 2048-element slice of the config-4 basin with hland_96p / hland_96c + rconc_nash elements: on
+    the 'auto' path they run through the sibling instances of the two-kernel fast path."""
+    ne, nt = 2048, 72
+    land, states = synth.make_land(ne, "1h", variants=True, model=model)
+    forcing, doy = synth.make_forcing(nt, "1h")
+    river, discharge = synth.make_tree_river(ne, "1h", levels=40)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)))
+    ref = oracle_run(problem)
+    res = run_problem(problem, engine)
+    compare(res, ref, f"{model} slice")
+    assert np.ptp(ref["land_rows"]) > 0.1 and np.isfinite(ref["land_rows"]).all()
+    res2 = run_problem(problem, engine, window=25)
+    assert np.array_equal(res["node_rows"], res2["node_rows"])
+
+
 def test_synthetic_capillary_flux_vs_oracle(engine):
     """CFlux > 0 couples the zones to the element's UZ of the previous step: fused kernel on the 'auto' path."""
     ne, nt = 1500, 96

@@ -20,10 +20,11 @@ ap.add_argument("--levels", type=int, default=200)
 ap.add_argument("--series", default="", help="comma-separated land series to record ('all' = every hland_96 sequence)")
 ap.add_argument("--path", default="auto")
 ap.add_argument("--cflux", type=float, default=0.0)
+ap.add_argument("--model", default="hland_96", choices=("hland_96", "hland_96p", "hland_96c"))
 args = ap.parse_args()
 
 t = time.time()
-land, states = synth.make_land(args.elements, args.step, cflux=args.cflux)
+land, states = synth.make_land(args.elements, args.step, cflux=args.cflux, model=args.model)
 river, dis = synth.make_tree_river(args.elements, args.step, levels=args.levels)
 print(f"generated in {time.time()-t:.1f}s: zones={land.n_zone} reaches={river.n_reach} segs={river.n_seg}")
 eng = Engine(0)
@@ -31,7 +32,7 @@ print(eng.device_info())
 t = time.time()
 eng.set_land(land); eng.set_land_states(states); eng.set_river(river); eng.set_river_states(dis)
 from hydpy_b200 import layout
-series = list(layout.SERIES) if args.series == "all" else [x for x in args.series.split(",") if x]
+series = list(layout.SERIES_96) if args.series == "all" else [x for x in args.series.split(",") if x]
 eng.select_series(series)
 eng.set_land_path(args.path)
 nbytes = 8 * args.nt * sum(land.n_zone if x in layout.SERIES_ZONE else land.n_snow if x in layout.SERIES_SNOW else land.n_elem for x in series)
