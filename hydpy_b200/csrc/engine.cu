@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -151,7 +152,7 @@ struct hb_engine {
   std::vector<int32_t> h_model, all_siblings[2], sibling_list[2];   // all / those the general kernel takes in this run
   DBuf<int32_t> d_sibling_list[2], d_nash_steps;
   DBuf<double> d_zx1, d_zx2, d_ex1, d_ex2;   // hland_96p suz, sg1, sg2, sg3 | hland_96c bw1, bw2
-  bool any_sibling = false;
+  bool any_sibling = false, any_nash = false;
   int64_t n_fast_sib[2] = {0, 0};            // their elements eligible for the two-kernel fast path
   bool any_nonsoil_sib[2] = {false, false};
   std::vector<int32_t> h_einfo;
@@ -605,6 +606,8 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   h->h_model = model;
   h->any_sibling = !siblings[0].empty() || !siblings[1].empty();
   for (int m = 0; m < 2; ++m) h->all_siblings[m] = siblings[m];
+  h->any_nash = false;
+  for (int64_t e = 0; e < ne; ++e) h->any_nash = h->any_nash || nash[e] > 0;
   { int rc_ = upload(h, h->d_nash_steps, nash); if (rc_) return rc_; }
   h->h_einfo.assign(einfo.begin(), einfo.begin() + ne);
   h->general_key = -1;
@@ -1192,6 +1195,8 @@ static int run_land(hb_engine* h) {
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
     v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow;
+    v.nash_stage = h->any_nash ? 1 : 0;
+    const size_t esmem = h->any_nash ? (size_t)HB_NASH_STAGE * 64 * sizeof(double) : 0;
     v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
     int n_staged = 0;
     for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
@@ -1265,16 +1270,16 @@ static int run_land(hb_engine* h) {
       }
       h->mark(HB_K_ZONE);
       if (use_fast) {
-        if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, 0, h->stream>>>(v);
-        else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, 0, h->stream>>>(v);
+        if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, esmem, h->stream>>>(v);
+        else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, esmem, h->stream>>>(v);
         h->timing.land_launches += 1;
       }
       if (use_fast_sib && h->n_fast_sib[0] > 0) {
-        element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, 0, h->stream>>>(v);
+        element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, h->stream>>>(v);
         h->timing.land_launches += 1;
       }
       if (use_fast_sib && h->n_fast_sib[1] > 0) {
-        element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, 0, h->stream>>>(v);
+        element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, h->stream>>>(v);
         h->timing.land_launches += 1;
       }
       h->mark(HB_K_ELEMENT);
@@ -1497,8 +1502,13 @@ static int enqueue_run(hb_engine* h, int flags) {
 static int resolve_marks(hb_engine* h, hb_engine::Marks& m, bool land) {
   float ms = 0.f;
   size_t begin = 0;
+  static const bool debug = getenv("HB_DEBUG_MARKS") != nullptr;   // development aid: every interval between two marks
   for (size_t i = 0; i < m.n; ++i) {
     const int tag = m.tag[i];
+    if (debug && i > 0 && tag != HB_K_BEGIN) {
+      cudaEventElapsedTime(&ms, m.ev[i - 1], m.ev[i]);
+      fprintf(stderr, "[hb marks] %s interval ending at tag %d: %.3f ms\n", land ? "land" : "river", tag, ms);
+    }
     if (tag == HB_K_BEGIN) { begin = i; continue; }
     if (tag == HB_K_END) {
       HB_CUDA(h, cudaEventElapsedTime(&ms, m.ev[begin], m.ev[i]));

@@ -241,13 +241,38 @@ __device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, doubl
 
 // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1 (rconc_uh), :179-197
 // Determine_Outflow_V2 (rconc_nash: explicit Euler over NmbSteps sub-steps through the storage cascade)
+// STAGED: keep up to HB_NASH_STAGE storages of the cascade in the block's shared memory ([storage][thread], conflict-free)
+// for the NmbSteps sub-steps of a step.  The thread-per-element kernel of the fast path is bound by the latency of this
+// chain; through global memory every one of the NmbSteps x NmbStorages updates is a dependent load-modify-store (and
+// registers for the cascade would cost the occupancy that hides the chain: measured 3.8 -> 5.1 ms).
+#define HB_NASH_STAGE 12
+template <bool STAGED = false>
 __device__ __forceinline__ double rconc_outflow(const double* __restrict__ uh, double* __restrict__ quh,
                                                 const double* __restrict__ ke, int64_t ep, int64_t e, int nu,
-                                                int nash_steps, double inrc) {
+                                                int nash_steps, double inrc, double* s_sc = nullptr, int s_stride = 0) {
   if (nu <= 0 || nash_steps < 0) return inrc;
   if (nash_steps > 0) {
     const double dt = ke[KE_NASH_DT * ep + e], dtksc = ke[KE_NASH_DTKSC * ep + e];
     double outflow = 0.0;
+    if (STAGED && s_sc != nullptr && nu <= HB_NASH_STAGE) {
+      for (int j = 0; j < nu; ++j) s_sc[j * s_stride] = quh[(int64_t)j * ep + e];
+      const double add = dt * inrc;
+      for (int i = 0; i < nash_steps; ++i) {
+        double carry = add;
+#pragma unroll
+        for (int j = 0; j < HB_NASH_STAGE; ++j)
+          if (j < nu) {
+            const double v = s_sc[j * s_stride] + carry;
+            const double a = dtksc * v;
+            const double q = HB_PYMIN(a, v);
+            s_sc[j * s_stride] = v - q;
+            carry = q;
+          }
+        outflow += carry;
+      }
+      for (int j = 0; j < nu; ++j) quh[(int64_t)j * ep + e] = s_sc[j * s_stride];
+      return outflow;
+    }
     for (int i = 0; i < nash_steps; ++i) {
       double carry = dt * inrc;                       // what enters storage j in this sub-step
       for (int j = 0; j < nu; ++j) {

@@ -71,6 +71,7 @@ struct LandV2Dev {
   int64_t n_clist;
   // sibling models (hland_96p / hland_96c) and rconc_nash
   const int32_t* nash_steps;  // [E_pad] see LandDev
+  int32_t nash_stage;      // element kernel: dynamic shared memory for the cascades is present
   double* zx1;             // [zmax][E_pad] hland_96p suz | hland_96c bw1
   double* zx2;             // [zmax][E_pad] hland_96p sg1 | hland_96c bw2
   double* ex1;             // [E_pad] hland_96p sg2
@@ -645,6 +646,8 @@ __global__ void __launch_bounds__(256) series_scatter_kernel(const double* __res
 template <bool SERIES, int MODEL>
 __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
   __shared__ MathTables s_tables;
+  extern __shared__ double s_sc_dyn[];   // rconc_nash cascade of the block's elements, [storage][thread]; only allocated
+  double* const s_sc = d.nash_stage ? s_sc_dyn : nullptr;   // (launch parameter) when some element has a cascade
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
       continue;
     }
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       // ref: hland_model.py:3172-3181 Calc_LZ_V2 (tb = weight * pc | weight * qvs2)
       for (int k = 0; k < nz; ++k) {
         if (!soilonly && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) continue;
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       for (int k = 0; k < nz; ++k)
         if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-    const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+    const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
     d.qt[(d.t_out + t) * ep + e] = qt;
