@@ -48,6 +48,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--levels", type=int, default=200)
     ap.add_argument("--cpu-elements", type=int, default=0, help="element sample of the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wave-blocks", type=int, default=0, help="persistent routing blocks per SM (0 = engine default)")
     return ap.parse_args()
 
 
@@ -218,6 +219,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     eng.set_land_states(states)
     eng.set_river(river)
     eng.set_river_states(discharge)
+    if args.wave_blocks:
+        eng.set_wave_blocks(args.wave_blocks)
     if dist.world > 1:
         uid = dist.bcast_bytes(eng.comm_unique_id() if dist.rank == 0 else None, 128)
         eng.comm_init(dist.rank, dist.world, uid)

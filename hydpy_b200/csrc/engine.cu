@@ -165,6 +165,7 @@ struct hb_engine {
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
   int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
   bool river_state_series = false;        // record musk_classic states.discharge per step
+  int wave_blocks = HB_WAVE_BLOCKS_PER_SM;  // persistent wavefront blocks per SM
   DBuf<double> d_dis_series[2];
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
@@ -785,6 +786,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
     case HB_OPT_LAND_PATH:
       HB_REQUIRE(h, value == HB_LAND_AUTO || value == HB_LAND_GENERAL, HB_EINVAL, "hb_set_option: invalid land path");
       h->land_path = (int)value;
+      return HB_OK;
+    case HB_OPT_RIVER_WAVE_BLOCKS:
+      HB_REQUIRE(h, value >= 1 && value <= 8, HB_EINVAL, "hb_set_option: wavefront blocks per SM must be 1..8");
+      h->wave_blocks = (int)value;
       return HB_OK;
     case HB_OPT_RIVER_STATE_SERIES:
       h->river_state_series = value != 0;
@@ -1439,7 +1444,7 @@ static int run_river(hb_engine* h) {
       const int64_t n_tasks = h->n_wave * n_chunks;
       HB_REQUIRE(h, n_tasks < (int64_t)1 << 31, HB_EINVAL, "hb_run: too many routing tasks for one window; use shorter windows");
       int64_t blocks = (n_tasks + 3) / 4;
-      const int64_t cap = (int64_t)h->prop.multiProcessorCount * HB_WAVE_BLOCKS_PER_SM;
+      const int64_t cap = (int64_t)h->prop.multiProcessorCount * h->wave_blocks;
       if (blocks > cap) blocks = cap;
       const size_t tab = (size_t)(d.n_diag + 1 + nlev + 1) * sizeof(int32_t);
       const int use_smem = tab <= 40 * 1024 ? 1 : 0;

@@ -253,6 +253,11 @@ class Engine:
         value = {"persistent": layout.RIVER_PERSISTENT, "launches": layout.RIVER_LAUNCHES}[mode]
         self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_SWEEP, value), "hb_set_option")
 
+    def set_wave_blocks(self, blocks_per_sm: int) -> None:
+        """Persistent routing wavefront blocks per SM (1..8): how much of every SM the routing of window w takes from the
+        runoff generation of window w+1."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_WAVE_BLOCKS, int(blocks_per_sm)), "hb_set_option")
+
     # -- window -----------------------------------------------------------------------------------------------------
     def set_forcing(self, forcing: np.ndarray, doy: np.ndarray, asynchronous: bool = False) -> None:
         """Stage the forcing block [4, nt, n_col] of the next window.  `asynchronous=True` only enqueues the copy

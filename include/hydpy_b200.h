@@ -262,6 +262,9 @@ int hb_select_series(hb_engine* h, int series, int on);
 /* HB_OPT_RIVER_STATE_SERIES (0/1): record musk_classic `states.discharge` of every step for hb_get_reach_state_series
  * (the `ramflag` of that sequence, `hydpy/models/musk/musk_states.py`). */
 #define HB_OPT_RIVER_STATE_SERIES 2
+/* HB_OPT_RIVER_WAVE_BLOCKS (1..8, default 4): persistent wavefront blocks per SM.  The routing of window w shares the GPU
+ * with the runoff generation of window w+1 (hb_run_async); fewer blocks leave it more of every SM. */
+#define HB_OPT_RIVER_WAVE_BLOCKS 3
 int hb_set_option(hb_engine* h, int option, int64_t value);
 
 /* ---- one simulation window ------------------------------------------------------------------------------------ */
