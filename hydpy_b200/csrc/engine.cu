@@ -1211,7 +1211,9 @@ static int run_land(hb_engine* h) {
     // up to a quarter of the free device memory (at most 32 GB) for large ensembles, whose chunks would otherwise shrink
     // to a handful of steps per launch
     double budget = 6.0e9;
-    {
+    // (cudaMemGetInfo costs up to milliseconds of host time — exposed in synchronous runs — so it is only asked when the
+    // window does not fit the buffers held already)
+    if ((size_t)nt * per_step > h->d_term_a.cap || (size_t)nt * per_step > h->d_term_b.cap || n_staged > 0) {
       size_t free_b = 0, total_b = 0;
       if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         const double held = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);   // already ours, counts as available
@@ -1219,6 +1221,7 @@ static int run_land(hb_engine* h) {
         if (quarter > budget) budget = quarter < 32.0e9 ? quarter : 32.0e9;
       }
     }
+    else budget = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);
     int64_t chunk_max = (int64_t)(budget / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
