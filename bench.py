@@ -368,8 +368,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of one zone_kernel launch (240-step chunk, 10^5 x 12 zones) from the
-    # committed `ncu --set full` capture profiles/r01_final_summary.txt; only valid for the default workload
-    traffic = 5.09e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
+    # committed `ncu --set full` capture profiles/r01_s3_summary.txt (0.40 GB read + 4.59 GB written); only valid for the
+    # default workload
+    traffic = 4.99e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

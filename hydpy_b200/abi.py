@@ -44,7 +44,13 @@ class hb_river_desc(C.Structure):
         ("entry_ptr", c_i64p), ("entry_src", c_i32p), ("node_mode", c_i32p), ("node_ext", c_i32p),
         ("inlet_ptr", c_i64p), ("inlet_node", c_i32p), ("reach_outlet", c_i32p), ("seg_ptr", c_i64p),
         ("coef", c_f64p),
+        ("reach_model", c_i32p), ("nmbruns", c_i32p), ("rpar", c_f64p), ("n_trap", C.c_int64), ("trap_ptr", c_i64p),
+        ("tpar", c_f64p),
     ]
+
+
+class hb_river_states(C.Structure):
+    _fields_ = [(n, c_f64p) for n in ("discharge", "courantnumber", "reynoldsnumber", "referencewaterdepth")]
 
 
 class hb_timing(C.Structure):
@@ -246,9 +252,15 @@ class RiverBundle:
     seg_ptr: np.ndarray
     coef: np.ndarray          # [3, n_reach]
     n_ext: int = 0
+    # musk_mct reaches (None: all musk_classic)
+    reach_model: np.ndarray | None = None   # [n_reach] layout.REACH_*
+    nmbruns: np.ndarray | None = None       # [n_reach]
+    rpar: np.ndarray | None = None          # [len(layout.RPAR), n_reach]
+    trap_ptr: np.ndarray | None = None      # [n_reach+1]
+    tpar: np.ndarray | None = None          # [len(layout.TPAR), n_trap]
 
-    I64 = ("entry_ptr", "inlet_ptr", "seg_ptr")
-    I32 = ("entry_src", "node_mode", "node_ext", "inlet_node", "reach_outlet")
+    I64 = ("entry_ptr", "inlet_ptr", "seg_ptr", "trap_ptr")
+    I32 = ("entry_src", "node_mode", "node_ext", "inlet_node", "reach_outlet", "reach_model", "nmbruns")
 
     @property
     def n_node(self) -> int:
@@ -262,12 +274,33 @@ class RiverBundle:
     def n_seg(self) -> int:
         return int(self.seg_ptr[-1])
 
+    @property
+    def any_mct(self) -> bool:
+        return self.reach_model is not None and bool(np.any(np.asarray(self.reach_model) == layout.REACH_MCT))
+
     def normalise(self) -> None:
+        nr = self.n_reach
+        if self.reach_model is None:
+            self.reach_model = np.zeros(nr, np.int32)
+        if self.nmbruns is None:
+            self.nmbruns = np.ones(nr, np.int32)
+        if self.rpar is None:
+            self.rpar = np.zeros((len(layout.RPAR), nr))
+        if self.trap_ptr is None:
+            self.trap_ptr = np.zeros(nr + 1, np.int64)
+        if self.tpar is None:
+            self.tpar = np.zeros((len(layout.TPAR), 0))
         for n in self.I64:
             setattr(self, n, _arr(getattr(self, n), np.int64))
         for n in self.I32:
             setattr(self, n, _arr(getattr(self, n), np.int32))
         self.coef = _arr(self.coef, np.float64)
+        self.rpar = _arr(self.rpar, np.float64)
+        self.tpar = _arr(self.tpar, np.float64)
+        if self.rpar.shape != (len(layout.RPAR), nr) or len(self.reach_model) != nr or len(self.nmbruns) != nr:
+            raise ValueError("reach_model/nmbruns/rpar do not match n_reach")
+        if len(self.trap_ptr) != nr + 1 or self.tpar.shape != (len(layout.TPAR), int(self.trap_ptr[-1])):
+            raise ValueError("trap_ptr/tpar do not match")
         if self.coef.shape != (3, self.n_reach):
             raise ValueError(f"coef must have shape (3, {self.n_reach}), not {self.coef.shape}")
         if len(self.node_mode) != self.n_node or len(self.node_ext) != self.n_node:
@@ -288,15 +321,19 @@ class RiverBundle:
         for n in self.I32:
             setattr(d, n, ptr(getattr(self, n), C.c_int32))
         d.coef = ptr(self.coef, C.c_double)
+        d.rpar = ptr(self.rpar, C.c_double)
+        d.tpar = ptr(self.tpar, C.c_double)
+        d.n_trap = int(self.trap_ptr[-1])
         d._keep = self  # type: ignore[attr-defined]
         return d
 
     def to_dict(self, prefix: str = "river_") -> dict[str, np.ndarray]:
+        self.normalise()
         return {prefix + f.name: np.asarray(getattr(self, f.name)) for f in dataclasses.fields(self)}
 
     @classmethod
     def from_dict(cls, d: Any, prefix: str = "river_") -> "RiverBundle":
-        kw = {f.name: np.asarray(d[prefix + f.name]) for f in dataclasses.fields(cls)}
+        kw = {f.name: np.asarray(d[prefix + f.name]) for f in dataclasses.fields(cls) if prefix + f.name in d}
         kw["n_ext"] = int(kw["n_ext"])
         return cls(**kw)
 

@@ -78,6 +78,17 @@ for _n in SERIES:
 
 NODE_NEWSIM, NODE_EXT, NODE_OBSNEWSIM = 0, 1, 2
 
+# routing model of a reach; parameters of musk_mct reaches (enum hb_rpar) and of their trapezes (enum hb_tpar)
+REACH_CLASSIC, REACH_MCT = 0, 1
+RPAR = ("tolerancewaterdepth", "tolerancedischarge", "tolerancenegativeinflow", "bottomslope", "seconds",
+        "segmentlength", "wq_bottomslope")
+RP = {name: i for i, name in enumerate(RPAR)}
+TPAR = ("bottomwidth", "sideslope", "stricklercoefficient", "calibrationfactor", "bottomdepth", "trapezeheight",
+        "slopewidth", "perimeterderivative")
+TP = {name: i for i, name in enumerate(TPAR)}
+#: musk_mct conditions beside the discharge state, rows of the `mct_states` array [3, n_seg]
+MCT_STATES = ("courantnumber", "reynoldsnumber", "referencewaterdepth")
+
 RUN_LAND, RUN_RIVER = 1, 2
 OPT_LAND_PATH = 0
 OPT_RIVER_SWEEP = 1

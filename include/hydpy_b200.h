@@ -204,7 +204,41 @@ typedef struct hb_river_desc {
   const int32_t* reach_outlet;/* [n_reach] node receiving the reach outflow (−1: none)                          */
   const int64_t* seg_ptr;     /* [n_reach+1] → discharge[]; NmbSegments = seg_ptr[r+1]-seg_ptr[r]-1             */
   const double* coef;         /* [3][n_reach] musk_control.Coefficients c0,c1,c2 (`musk_control.py:128-315`)    */
+  /* ABI 2: musk_mct reaches (`hydpy/models/musk_mct.py`) with their `wq_trapeze_strickler` cross
+   * sections (`hydpy/models/wq_trapeze_strickler.py`).  reach_model may be NULL (all musk_classic); the other arrays are
+   * only read for HB_REACH_MCT reaches.                                                                           */
+  const int32_t* reach_model; /* [n_reach] HB_REACH_*                                                           */
+  const int32_t* nmbruns;     /* [n_reach] musk_solver.NmbRuns                                                  */
+  const double* rpar;         /* [HB_RP_COUNT][n_reach]                                                         */
+  int64_t n_trap;             /* total number of trapezes                                                       */
+  const int64_t* trap_ptr;    /* [n_reach+1] → tpar columns; wq_control.NmbTrapezes = trap_ptr[r+1]-trap_ptr[r]  */
+  const double* tpar;         /* [HB_TP_COUNT][n_trap]                                                          */
 } hb_river_desc;
+
+#define HB_REACH_CLASSIC 0
+#define HB_REACH_MCT 1
+/* per-reach double parameters of musk_mct: solver tolerances (`musk_solver.py`), control BottomSlope, derived Seconds and
+ * SegmentLength [km] (`musk_derived.py`), and the BottomSlope of the wq submodel (`wq_control.py`) */
+enum hb_rpar {
+  HB_RP_TOLERANCEWATERDEPTH = 0, HB_RP_TOLERANCEDISCHARGE, HB_RP_TOLERANCENEGATIVEINFLOW, HB_RP_BOTTOMSLOPE,
+  HB_RP_SECONDS, HB_RP_SEGMENTLENGTH, HB_RP_WQ_BOTTOMSLOPE, HB_RP_COUNT
+};
+/* per-trapeze double parameters of wq_trapeze_strickler: control BottomWidths, SideSlopes, StricklerCoefficients,
+ * CalibrationFactors; derived BottomDepths, TrapezeHeights, SlopeWidths, PerimeterDerivatives (`wq_derived.py`) */
+enum hb_tpar {
+  HB_TP_BOTTOMWIDTH = 0, HB_TP_SIDESLOPE, HB_TP_STRICKLERCOEFFICIENT, HB_TP_CALIBRATIONFACTOR, HB_TP_BOTTOMDEPTH,
+  HB_TP_TRAPEZEHEIGHT, HB_TP_SLOPEWIDTH, HB_TP_PERIMETERDERIVATIVE, HB_TP_COUNT
+};
+/* musk_mct conditions beside `states.discharge`: states CourantNumber, ReynoldsNumber and the factor
+ * ReferenceWaterDepth (the start value of the next step's root search, `musk_model.py:380-399`), each stored like the
+ * discharge state, i.e. [n_seg] with the last cell of every reach unused.  NULL pointers are allowed when no reach is
+ * a musk_mct reach. */
+typedef struct hb_river_states {
+  double* discharge;           /* [n_seg] */
+  double* courantnumber;       /* [n_seg] */
+  double* reynoldsnumber;      /* [n_seg] */
+  double* referencewaterdepth; /* [n_seg] */
+} hb_river_states;
 
 #define HB_ENTRY_EXT (-1073741824) /* -(1<<30) */
 
@@ -243,6 +277,9 @@ int hb_set_river(hb_engine* h, const hb_river_desc* desc);
 /* musk_classic `states.discharge` (old == new between steps), concatenated, length n_seg. */
 int hb_set_river_states(hb_engine* h, const double* discharge);
 int hb_get_river_states(hb_engine* h, double* discharge);
+/* The same including the musk_mct conditions (ABI 2). */
+int hb_set_river_states2(hb_engine* h, const hb_river_states* st);
+int hb_get_river_states2(hb_engine* h, hb_river_states* st);
 /* Select which optional land series `hb_run` records (on ≠ 0).  Replaces the `ramflag` switches of
  * `IOSequence.prepare_series` (`hydpy/core/sequencetools.py:1912`, save_data `modelutils.py:1127-1167`). */
 int hb_select_series(hb_engine* h, int series, int on);

@@ -36,7 +36,7 @@ MODELS = (
     "hland", "hland_96", "evap", "evap_aet_hbv96", "evap_pet_hbv96",
     "rconc", "rconc_uh", "musk", "musk_classic",
     # sibling models on the same skeleton
-    "hland_96p", "hland_96c", "rconc_nash",
+    "hland_96p", "hland_96c", "rconc_nash", "musk_mct", "wq", "wq_trapeze_strickler",
 )
 
 STUBS = {
