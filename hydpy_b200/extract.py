@@ -23,7 +23,7 @@ from . import layout
 from .abi import LandBundle, LandStates, RiverBundle
 
 LAND_MODELS = ("hland_96", "hland_96p", "hland_96c")
-RIVER_MODELS = ("musk_classic",)
+RIVER_MODELS = ("musk_classic", "musk_mct")
 
 _ZONE_CONTROL = (
     "zonez", "pcorr", "pcalt", "rfcf", "sfcf", "tcorr", "tcalt", "icmax", "smax", "tt", "ttint", "cfmax", "cfvar",
@@ -65,7 +65,7 @@ class Problem:
     land: LandBundle
     states: LandStates
     river: RiverBundle
-    discharge: np.ndarray                 # musk_classic states, concatenated
+    discharge: np.ndarray                 # musk_classic / musk_mct states.discharge, concatenated
     forcing: np.ndarray                   # [4, T, n_col]  (T = i1-i0)
     doy: np.ndarray                       # [T] int64
     ext: np.ndarray                       # [n_ext, T]
@@ -75,6 +75,7 @@ class Problem:
     node_writeback: np.ndarray | None = None  # bool[n_node]: does the run overwrite sim.series of the node?
     i0: int = 0
     i1: int = 0
+    mct_states: np.ndarray | None = None  # [3, n_seg] musk_mct courantnumber, reynoldsnumber, referencewaterdepth
 
     @property
     def nt(self) -> int:
@@ -90,6 +91,8 @@ class Problem:
         d["ext"] = self.ext
         if self.node_writeback is not None:
             d["node_writeback"] = self.node_writeback
+        if self.mct_states is not None:
+            d["mct_states"] = self.mct_states
         return d
 
     @classmethod
@@ -101,6 +104,7 @@ class Problem:
             discharge=np.array(d["discharge"], dtype=np.float64), forcing=np.array(d["forcing"], dtype=np.float64),
             doy=np.array(d["doy"], dtype=np.int64), ext=np.array(d["ext"], dtype=np.float64),
             node_writeback=np.array(d["node_writeback"], dtype=bool) if "node_writeback" in d else None,
+            mct_states=np.array(d["mct_states"], dtype=np.float64) if "mct_states" in d else None,
         )
 
 
@@ -332,8 +336,9 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
 
 def extract_river(elements: Iterable[Any], nodes: list[Any], node_index: dict[Any, int],
                   land_index: dict[Any, int], i0: int, i1: int
-                  ) -> tuple[RiverBundle, np.ndarray, np.ndarray, np.ndarray]:
-    """Gather musk_classic elements + the node graph.  Returns (bundle, discharge, ext rows, node_writeback)."""
+                  ) -> tuple[RiverBundle, np.ndarray, np.ndarray, np.ndarray, np.ndarray | None]:
+    """Gather musk_classic / musk_mct elements + the node graph.  Returns (bundle, discharge, ext rows, node_writeback,
+    musk_mct conditions [3, n_seg] or None)."""
     elements = list(elements)
     reach_index = {el: i for i, el in enumerate(elements)}
     nr, nn, nt = len(elements), len(nodes), i1 - i0
@@ -343,14 +348,57 @@ def extract_river(elements: Iterable[Any], nodes: list[Any], node_index: dict[An
     coef = np.zeros((3, nr))
     inlet_node: list[int] = []
     dis: list[np.ndarray] = []
+    reach_model = np.zeros(nr, np.int32)
+    nmbruns_a = np.ones(nr, np.int32)
+    rpar = np.zeros((len(layout.RPAR), nr))
+    trap_ptr = np.zeros(nr + 1, np.int64)
+    tp_l: list[np.ndarray] = []
+    mct_l: list[np.ndarray] = []
     for r, element in enumerate(elements):
         model = element.model
         con = model.parameters.control
         ns = int(con.nmbsegments.value)
         nmbruns = int(model.parameters.solver.nmbruns.value) if hasattr(model.parameters, "solver") else 1
-        if nmbruns != 1:
-            raise UnsupportedModelError(f"element `{element.name}`: musk_classic with nmbruns != 1 is not supported")
-        coef[:, r] = np.array(con.coefficients.value, dtype=np.float64).reshape(3)
+        trap_ptr[r + 1] = trap_ptr[r]
+        mct = np.zeros((3, ns + 1))
+        if _modelname(model) == "musk_mct":
+            # ref: hydpy/models/musk_mct.py; cross section: hydpy/models/wq_trapeze_strickler.py
+            wq = getattr(model, "wqmodel", None)
+            if wq is None or _modelname(wq) != "wq_trapeze_strickler":
+                raise UnsupportedModelError(
+                    f"element `{element.name}`: musk_mct needs a `wq_trapeze_strickler` cross-section submodel, found "
+                    f"`{None if wq is None else _modelname(wq)}`")
+            reach_model[r] = layout.REACH_MCT
+            nmbruns_a[r] = nmbruns
+            sol, der = model.parameters.solver, model.parameters.derived
+            rp = layout.RP
+            rpar[rp["tolerancewaterdepth"], r] = sol.tolerancewaterdepth.value
+            rpar[rp["tolerancedischarge"], r] = sol.tolerancedischarge.value
+            rpar[rp["tolerancenegativeinflow"], r] = sol.tolerancenegativeinflow.value
+            rpar[rp["bottomslope"], r] = con.bottomslope.value
+            rpar[rp["seconds"], r] = der.seconds.value
+            rpar[rp["segmentlength"], r] = der.segmentlength.value
+            wcon, wder = wq.parameters.control, wq.parameters.derived
+            rpar[rp["wq_bottomslope"], r] = wcon.bottomslope.value
+            ntr = int(wcon.nmbtrapezes.value)
+            tp = np.zeros((len(layout.TPAR), ntr))
+            for name, par in (("bottomwidth", wcon.bottomwidths), ("sideslope", wcon.sideslopes),
+                              ("stricklercoefficient", wcon.stricklercoefficients),
+                              ("calibrationfactor", wcon.calibrationfactors), ("bottomdepth", wder.bottomdepths),
+                              ("trapezeheight", wder.trapezeheights), ("slopewidth", wder.slopewidths),
+                              ("perimeterderivative", wder.perimeterderivatives)):
+                tp[layout.TP[name]] = _f(par, ntr)
+            tp_l.append(tp)
+            trap_ptr[r + 1] = trap_ptr[r] + ntr
+            sta = model.sequences.states
+            mct[0, :ns] = _f(sta.courantnumber, ns) if ns else 0.0
+            mct[1, :ns] = _f(sta.reynoldsnumber, ns) if ns else 0.0
+            mct[2, :ns] = _f(model.sequences.factors.referencewaterdepth, ns) if ns else 0.0
+        else:
+            if nmbruns != 1:
+                raise UnsupportedModelError(f"element `{element.name}`: musk_classic with nmbruns != 1 is not supported")
+            coef[:, r] = np.array(con.coefficients.value, dtype=np.float64).reshape(3)
+        mct_l.append(mct)
         d = np.array(model.sequences.states.discharge.value, dtype=np.float64).reshape(-1)
         if len(d) != ns + 1:
             raise ValueError(f"element `{element.name}`: `discharge` must have nmbsegments+1 entries")
@@ -408,12 +456,14 @@ def extract_river(elements: Iterable[Any], nodes: list[Any], node_index: dict[An
     river = RiverBundle(
         entry_ptr=entry_ptr, entry_src=np.array(entry_src, np.int32), node_mode=node_mode, node_ext=node_ext,
         inlet_ptr=inlet_ptr, inlet_node=np.array(inlet_node, np.int32), reach_outlet=reach_outlet, seg_ptr=seg_ptr,
-        coef=coef, n_ext=len(ext_rows),
+        coef=coef, n_ext=len(ext_rows), reach_model=reach_model, nmbruns=nmbruns_a, rpar=rpar, trap_ptr=trap_ptr,
+        tpar=np.concatenate(tp_l, axis=1) if tp_l else np.zeros((len(layout.TPAR), 0)),
     )
     river.normalise()
     discharge = np.concatenate(dis) if dis else np.zeros(0)
     ext = np.stack(ext_rows) if ext_rows else np.zeros((0, nt))
-    return river, discharge, ext, writeback
+    mct_states = np.concatenate(mct_l, axis=1) if (mct_l and river.any_mct) else None
+    return river, discharge, ext, writeback, mct_states
 
 
 def extract(hp: Any, i0: int, i1: int) -> Problem:
@@ -442,11 +492,11 @@ def extract(hp: Any, i0: int, i1: int) -> Problem:
             raise UnsupportedModelError(f"element `{element.name}`: receiver/sender/observer nodes are not supported")
     land, states, forcing, doy = extract_land(land_elements, node_index, i0, i1)
     land_index = {el: i for i, el in enumerate(land_elements)}
-    river, discharge, ext, writeback = extract_river(river_elements, nodes, node_index, land_index, i0, i1)
+    river, discharge, ext, writeback, mct_states = extract_river(river_elements, nodes, node_index, land_index, i0, i1)
     return Problem(
         land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext,
         land_elements=land_elements, river_elements=river_elements, nodes=nodes, node_writeback=writeback,
-        i0=i0, i1=i1,
+        i0=i0, i1=i1, mct_states=mct_states,
     )
 
 
@@ -480,7 +530,8 @@ def _set_state(seq: Any, value: Any) -> None:
 
 def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, node_rows: np.ndarray,
                land_rows: np.ndarray, reach_out: np.ndarray | None, reach_in: np.ndarray | None,
-               series: dict[str, np.ndarray], reach_state_series: np.ndarray | None = None) -> None:
+               series: dict[str, np.ndarray], reach_state_series: np.ndarray | None = None,
+               mct_states: np.ndarray | None = None) -> None:
     """Store the results of one run in the HydPy objects exactly where the reference leaves them."""
     land, i0, i1 = problem.land, problem.i0, problem.i1
     last = i1 - i0 - 1
@@ -541,6 +592,10 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
         model = element.model
         g0, g1 = int(river.seg_ptr[r]), int(river.seg_ptr[r + 1])
         _set_state(model.sequences.states.discharge, discharge[g0:g1])
+        if mct_states is not None and int(river.reach_model[r]) == layout.REACH_MCT:
+            _set_state(model.sequences.states.courantnumber, mct_states[0, g0:g1 - 1])
+            _set_state(model.sequences.states.reynoldsnumber, mct_states[1, g0:g1 - 1])
+            model.sequences.factors.referencewaterdepth.value = mct_states[2, g0:g1 - 1]
         if reach_state_series is not None and getattr(model.sequences.states.discharge, "ramflag", False):
             model.sequences.states.discharge.series[i0:i1] = reach_state_series[:, g0:g1]
         flu = model.sequences.fluxes

@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 from hydpy_b200 import layout
-from hydpy_b200.abi import LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc, ptr
+from hydpy_b200.abi import (LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc,
+                            hb_river_states, ptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(HERE, "liboracle.so")
@@ -47,6 +48,9 @@ def lib() -> C.CDLL:
         _lib.oracle_river_run.argtypes = [C.POINTER(hb_river_desc), f64p, C.c_int64, f64p, f64p, f64p, f64p, f64p]
         _lib.oracle_river_run2.restype = C.c_int
         _lib.oracle_river_run2.argtypes = [C.POINTER(hb_river_desc), f64p, C.c_int64, f64p, f64p, f64p, f64p, f64p, f64p]
+        _lib.oracle_river_run3.restype = C.c_int
+        _lib.oracle_river_run3.argtypes = [C.POINTER(hb_river_desc), C.POINTER(hb_river_states), C.c_int64, f64p, f64p,
+                                           f64p, f64p, f64p, f64p]
         _lib.oracle_sinfactor.restype = C.c_double
         _lib.oracle_sinfactor.argtypes = [C.c_int64]
     return _lib
@@ -107,9 +111,11 @@ def land_run(land: LandBundle, states: LandStates, forcing: np.ndarray, doy: np.
 
 
 def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, ext: np.ndarray | None = None,
-              dis_series: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Route the window; `discharge` is updated in place.  Returns (node rows, reach outflow, reach inflow).
-    `dis_series` (optional, [nt, n_seg]) receives musk_classic `states.discharge` after every step."""
+              dis_series: np.ndarray | None = None, mct_states: np.ndarray | None = None
+              ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Route the window; `discharge` (and `mct_states` [3, n_seg], the musk_mct conditions) are updated in place.
+    Returns (node rows, reach outflow, reach inflow).  `dis_series` (optional, [nt, n_seg]) receives
+    `states.discharge` after every step."""
     L = lib()
     land_rows = np.ascontiguousarray(land_rows, dtype=np.float64)
     nt = land_rows.shape[1] if land_rows.ndim == 2 and land_rows.shape[0] else (ext.shape[1] if ext is not None else 0)
@@ -123,7 +129,16 @@ def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, 
     assert discharge.dtype == np.float64 and discharge.flags.c_contiguous
     if dis_series is not None:
         assert dis_series.shape == (nt, river.n_seg) and dis_series.dtype == np.float64 and dis_series.flags.c_contiguous
-    rc = L.oracle_river_run2(C.byref(d), ptr(discharge, C.c_double), nt, ptr(land_rows, C.c_double),
+    st = hb_river_states()
+    st.discharge = ptr(discharge, C.c_double)
+    if river.any_mct:
+        if mct_states is None:
+            raise ValueError("the river bundle holds musk_mct reaches: pass their conditions (mct_states [3, n_seg])")
+        assert mct_states.shape == (3, river.n_seg) and mct_states.dtype == np.float64 and mct_states.flags.c_contiguous
+        st.courantnumber = ptr(mct_states[0], C.c_double)
+        st.reynoldsnumber = ptr(mct_states[1], C.c_double)
+        st.referencewaterdepth = ptr(mct_states[2], C.c_double)
+    rc = L.oracle_river_run3(C.byref(d), C.byref(st), nt, ptr(land_rows, C.c_double),
                              ptr(ext, C.c_double), ptr(node_rows, C.c_double), ptr(rout, C.c_double),
                              ptr(rin, C.c_double), ptr(dis_series, C.c_double) if dis_series is not None else None)
     if rc != 0:

@@ -10,6 +10,7 @@ What is produced (all under tests/golden/):
   docstring is executed by ``doctest``, so the reference build is at the same time checked against its own printed
   6-digit tables.
 * ``hland_96p_integration.npz``, ``hland_96c_integration.npz`` — the same for the sibling models (``--siblings``).
+* ``musk_mct_integration.npz`` — the 5 integration tests of ``hydpy/models/musk_mct.py`` (``--musk_mct``).
 * ``musk_classic_integration.npz`` — the 3 integration tests of ``hydpy/models/musk_classic.py``.
 * ``lahn_daily.npz`` — the HydPy-H-Lahn example project, 1996-01-01…1998-01-01 daily (config 1 of BASELINE.json):
   problem + all four gauge series + land outflows + final conditions + a few state series.
@@ -78,6 +79,24 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
     for n in after.states.NAMES:
         out["exp_state_" + n] = getattr(after.states, n)
     out["exp_discharge"] = after.discharge
+    if after.mct_states is not None:
+        out["exp_mct_states"] = after.mct_states
+    # states.discharge of every step (and, for musk_mct, the other per-segment sequences), stored like the state: [nt, n_seg]
+    per_seg = {"dis_series": ("states", "discharge"), "cn_series": ("states", "courantnumber"),
+               "rn_series": ("states", "reynoldsnumber"), "rwd_series": ("factors", "referencewaterdepth")}
+    for key, (group, name) in per_seg.items():
+        arr = np.full((nt, problem.river.n_seg), np.nan)
+        have = False
+        for r, element in enumerate(problem.river_elements):
+            seq = getattr(getattr(element.model.sequences, group, None), name, None)
+            if seq is None or not seq.ramflag:
+                continue
+            data = np.asarray(seq.series[i0:i1], dtype=np.float64).reshape(nt, -1)
+            g0 = int(problem.river.seg_ptr[r])
+            arr[:, g0:g0 + data.shape[1]] = data
+            have = True
+        if have:
+            out["exp_" + key] = arr
     rin, rout = [], []
     for element in problem.river_elements:
         flu = element.model.sequences.fluxes
@@ -90,8 +109,9 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
     return out
 
 
-def harvest_module(modulename: str) -> dict[str, dict[str, np.ndarray]]:
-    """Execute the module docstring with doctest and snapshot every `test("name")` call."""
+def harvest_module(modulename: str, capture_all: bool = False) -> dict[str, dict[str, np.ndarray]]:
+    """Execute the module docstring with doctest and snapshot every `test("name")` call (`capture_all`: also the calls
+    that ask for the conditions of a later date, which the musk_mct tests all do)."""
     captured: dict[str, dict[str, np.ndarray]] = {}
     orig_call = testtools.IntegrationTest.__call__
 
@@ -100,7 +120,7 @@ def harvest_module(modulename: str) -> dict[str, dict[str, np.ndarray]]:
         # same steps as the reference's IntegrationTest.__call__ (hydpy/core/testtools.py:626-645) minus plotting
         self.prepare_model(update_parameters=update_parameters, use_conditions=use_conditions)
         problem = None
-        if get_conditions is None and filename:
+        if (get_conditions is None or capture_all) and filename:
             i0, i1 = pub.timegrids.simindices
             problem = extract(self.hydpy, i0, i1)
         seq2value = self._perform_simulation(get_conditions)
@@ -296,6 +316,10 @@ def write_template(daily: dict[str, np.ndarray], hourly: dict[str, np.ndarray]) 
 
 
 def main() -> None:
+    if "--musk_mct" in sys.argv:
+        save_scenarios(os.path.join(HERE, "musk_mct_integration.npz"),
+                       harvest_module("hydpy.models.musk_mct", capture_all=True))
+        return
     if "--siblings" in sys.argv:
         # the integration tests of the sibling models' own docstrings (hland_96p: 4, hland_96c: 6 distinct
         # scenarios, all with rconc_nash)

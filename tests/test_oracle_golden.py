@@ -18,6 +18,7 @@ HLAND = load_scenarios("hland_96_integration.npz")
 HLAND_P = load_scenarios("hland_96p_integration.npz")
 HLAND_C = load_scenarios("hland_96c_integration.npz")
 MUSK = load_scenarios("musk_classic_integration.npz")
+MUSK_MCT = load_scenarios("musk_mct_integration.npz")
 LAHN = load_scenarios("lahn_daily.npz")
 LAHN_H = load_scenarios("lahn_hourly_members.npz")
 
@@ -27,8 +28,11 @@ def run_oracle(sc, threads=1):
     states = p.states.copy()
     qt, series = oracle.land_run(p.land, states, p.forcing, p.doy, series=sc.expected_series, threads=threads)
     discharge = p.discharge.copy()
-    node_rows, rout, rin = oracle.river_run(p.river, discharge, qt, p.ext)
-    return dict(states=states, qt=qt, series=series, discharge=discharge, node_rows=node_rows, rout=rout, rin=rin)
+    mct = None if p.mct_states is None else p.mct_states.copy()
+    dser = np.full((p.nt, p.river.n_seg), np.nan)
+    node_rows, rout, rin = oracle.river_run(p.river, discharge, qt, p.ext, dis_series=dser, mct_states=mct)
+    return dict(states=states, qt=qt, series=series, discharge=discharge, node_rows=node_rows, rout=rout, rin=rin,
+                mct_states=mct, dis_series=dser)
 
 
 def check(sc, res, exact=True):
@@ -79,6 +83,18 @@ def test_hland_96c_integration(name):
 def test_musk_classic_integration(name):
     sc = MUSK[name]
     check(sc, run_oracle(sc))
+
+
+@pytest.mark.parametrize("name", sorted(MUSK_MCT))
+def test_musk_mct_integration(name):
+    """musk_mct + wq_trapeze_strickler (ref: hydpy/models/musk_mct.py integration tests): outflow,
+    states.discharge of every step and the final conditions (Courant/Reynolds numbers, reference water depths)."""
+    sc = MUSK_MCT[name]
+    res = run_oracle(sc)
+    check(sc, res)
+    exp = sc.expected("dis_series")
+    assert np.array_equal(res["dis_series"][~np.isnan(exp)], exp[~np.isnan(exp)]), "states.discharge series not exact"
+    assert np.array_equal(res["mct_states"], sc.expected("mct_states"), equal_nan=True)
 
 
 def test_lahn_daily():
