@@ -202,6 +202,12 @@ struct hb_engine {
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
   int diag_chunks = -1;                 // n_chunks the uploaded diag_start belongs to
   int* h_wave_err = nullptr;            // pinned copy of the wavefront's error flag
+  // musk_mct reaches
+  bool any_mct = false;
+  DBuf<int32_t> d_nmbruns;
+  DBuf<int64_t> d_trap_ptr;
+  DBuf<double> d_rpar, d_tpar, d_mct_cn, d_mct_rn, d_mct_rwd;
+  int64_t n_trap = 0;
   DBuf<double> d_coef, d_dis[2], d_ext_rows[2], d_node_rows[2], d_reach_in[2], d_reach_out[2], d_gather[2];
   int dis_cur = 0;
   bool have_ext = false;
@@ -926,7 +932,8 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
   std::vector<int64_t> dep_ptr(nr + 1, 0);
   for (int32_t q : reach_order) {
     const int64_t nseg = r->seg_ptr[q + 1] - r->seg_ptr[q] - 1;
-    if (reach_level[q] == 0 && nseg <= HB_BULK_SMAX) {
+    const bool is_mct = r->reach_model && r->reach_model[q] == HB_REACH_MCT;   // musk_mct: always the systolic wavefront
+    if (reach_level[q] == 0 && nseg <= HB_BULK_SMAX && !is_mct) {
       head_all.push_back(q);
       if (nseg >= 1) head_bulk.push_back(q);
     } else {
@@ -957,7 +964,8 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     m.level = reach_level[q];
     m.dep0 = (int32_t)dep_ptr[q];
     m.n_dep = (int32_t)(dep_ptr[q + 1] - dep_ptr[q]);
-    m.simple_node = -1; m.entry0 = 0; m.n_entry = 0; m.owns_node = 0; m.pad = 0;
+    m.simple_node = -1; m.entry0 = 0; m.n_entry = 0; m.owns_node = 0;
+    m.pad = (r->reach_model && r->reach_model[q] == HB_REACH_MCT) ? 1 : 0;
     if (r->inlet_ptr[q + 1] - r->inlet_ptr[q] == 1) {
       const int32_t n = r->inlet_node[r->inlet_ptr[q]];
       const int64_t ne_ = r->entry_ptr[n + 1] - r->entry_ptr[n];
@@ -978,12 +986,36 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     memcpy(w + HB_WR_C0, &m.c0, 8); memcpy(w + HB_WR_C1, &m.c1, 8); memcpy(w + HB_WR_C2, &m.c2, 8);
     w[HB_WR_REACH] = q; w[HB_WR_G0] = m.g0; w[HB_WR_NSEG] = m.nseg; w[HB_WR_LEVEL] = m.level;
     w[HB_WR_NDEP] = m.n_dep; w[HB_WR_NENTRY] = m.n_entry; w[HB_WR_NODE] = m.simple_node; w[HB_WR_OWNS] = m.owns_node;
-    const bool inl = m.simple_node >= 0 && m.n_entry <= HB_WR_MAXLIST && m.n_dep <= HB_WR_MAXLIST;
+    const bool inl = m.simple_node >= 0 && m.n_entry <= HB_WR_MAXLIST && m.n_dep <= HB_WR_MAXLIST && m.pad == 0;
     w[HB_WR_INLINE] = inl ? 1 : 0;
     if (inl) {
       for (int i = 0; i < m.n_entry; ++i) w[HB_WR_ENTRY + i] = r->entry_src[m.entry0 + i];
       for (int i = 0; i < m.n_dep; ++i) w[HB_WR_DEP + i] = dep_reach[m.dep0 + i];
     }
+  }
+  // musk_mct parameters and conditions (Courant/Reynolds numbers start at 0, the reference water depth at NaN = "no
+  // start value yet", like freshly prepared reference objects; hb_set_river_states2 sets them)
+  h->any_mct = false;
+  for (int64_t q = 0; q < nr; ++q) {
+    if (!(r->reach_model && r->reach_model[q] != HB_REACH_CLASSIC)) continue;
+    HB_REQUIRE(h, r->reach_model[q] == HB_REACH_MCT, HB_EINVAL, "hb_set_river: reach %lld has unknown model %d",
+               (long long)q, r->reach_model[q]);
+    HB_REQUIRE(h, r->nmbruns && r->rpar && r->trap_ptr && (r->n_trap == 0 || r->tpar), HB_EINVAL,
+               "hb_set_river: musk_mct reach %lld without parameters", (long long)q);
+    HB_REQUIRE(h, r->nmbruns[q] >= 0 && r->trap_ptr[q + 1] >= r->trap_ptr[q] && r->trap_ptr[q + 1] <= r->n_trap, HB_EINVAL,
+               "hb_set_river: invalid musk_mct description of reach %lld", (long long)q);
+    h->any_mct = true;
+  }
+  h->n_trap = h->any_mct ? r->n_trap : 0;
+  if (h->any_mct) {
+    int rc_;
+    if ((rc_ = upload(h, h->d_nmbruns, r->nmbruns, (size_t)nr)) || (rc_ = upload(h, h->d_rpar, r->rpar, (size_t)HB_RP_COUNT * nr)) ||
+        (rc_ = upload(h, h->d_trap_ptr, r->trap_ptr, (size_t)nr + 1)) ||
+        (rc_ = upload(h, h->d_tpar, r->tpar, (size_t)HB_TP_COUNT * r->n_trap)))
+      return rc_;
+    std::vector<double> zero((size_t)r->n_seg, 0.0), nan_((size_t)r->n_seg, std::nan(""));
+    if ((rc_ = upload(h, h->d_mct_cn, zero)) || (rc_ = upload(h, h->d_mct_rn, zero)) || (rc_ = upload(h, h->d_mct_rwd, nan_)))
+      return rc_;
   }
   h->n_head_all = (int64_t)head_all.size(); h->n_head_bulk = (int64_t)head_bulk.size(); h->n_wave = (int64_t)wave_order.size();
   h->wave_lvl_ptr = wave_lvl;
@@ -1031,6 +1063,39 @@ int hb_set_river_states(hb_engine* h, const double* discharge) {
     HB_CUDA(h, cudaMemcpyAsync(h->d_dis[h->dis_cur].p, discharge, (size_t)h->n_seg * sizeof(double),
                                cudaMemcpyHostToDevice, h->stream));
     HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+int hb_set_river_states2(hb_engine* h, const hb_river_states* st) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, st, HB_EINVAL, "hb_set_river_states2: NULL argument");
+  int rc = hb_set_river_states(h, st->discharge);
+  if (rc) return rc;
+  if (h->any_mct) {
+    HB_REQUIRE(h, st->courantnumber && st->reynoldsnumber && st->referencewaterdepth, HB_EINVAL,
+               "hb_set_river_states2: the network holds musk_mct reaches, their conditions are required");
+    const size_t n = (size_t)h->n_seg;
+    if ((rc = upload(h, h->d_mct_cn, st->courantnumber, n)) || (rc = upload(h, h->d_mct_rn, st->reynoldsnumber, n)) ||
+        (rc = upload(h, h->d_mct_rwd, st->referencewaterdepth, n)))
+      return rc;
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+int hb_get_river_states2(hb_engine* h, hb_river_states* st) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, st, HB_EINVAL, "hb_get_river_states2: NULL argument");
+  int rc = hb_get_river_states(h, st->discharge);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->n_seg * sizeof(double);
+  double* dst[3] = {st->courantnumber, st->reynoldsnumber, st->referencewaterdepth};
+  double* src[3] = {h->d_mct_cn.p, h->d_mct_rn.p, h->d_mct_rwd.p};
+  for (int i = 0; i < 3; ++i) {
+    if (!dst[i] || !bytes) continue;
+    if (h->any_mct) HB_CUDA(h, cudaMemcpy(dst[i], src[i], bytes, cudaMemcpyDeviceToHost));
+    else memset(dst[i], 0, bytes);
   }
   return HB_OK;
 }
@@ -1389,6 +1454,8 @@ static int run_river(hb_engine* h) {
   d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
   d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
+  d.nmbruns = h->d_nmbruns.p; d.rpar = h->d_rpar.p; d.trap_ptr = h->d_trap_ptr.p; d.tpar = h->d_tpar.p; d.n_trap = h->n_trap;
+  d.mct_cn = h->d_mct_cn.p; d.mct_rn = h->d_mct_rn.p; d.mct_rwd = h->d_mct_rwd.p;
   int64_t launches = 0;
   // boundary rows received over NCCL (s_comm): the whole routing waits only if some reach reads external rows;
   // otherwise just the final sums of the outlet nodes do
@@ -1405,7 +1472,8 @@ static int run_river(hb_engine* h) {
       const int n = h->level_reach_ptr[l_hi + 1] - first;
       if (n <= 0) continue;
       const int block = 128, grid = (int)(((int64_t)n * 32 + block - 1) / block);
-      reach_diag_kernel<<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag);
+      if (h->any_mct) reach_diag_kernel<true><<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag);
+      else reach_diag_kernel<false><<<grid, block, 0, h->s_river>>>(d, h->d_reach_order.p + first, n, diag);
       ++launches;
     }
   } else if (nt > 0 && h->n_reach > 0) {
@@ -1451,7 +1519,8 @@ static int run_river(hb_engine* h) {
       if (blocks > cap) blocks = cap;
       const size_t tab = (size_t)(d.n_diag + 1 + nlev + 1) * sizeof(int32_t);
       const int use_smem = tab <= 40 * 1024 ? 1 : 0;
-      reach_wave_kernel<<<(unsigned)blocks, 128, use_smem ? tab : 0, h->s_river>>>(d, (int)n_tasks, use_smem);
+      if (h->any_mct) reach_wave_kernel<true><<<(unsigned)blocks, 128, use_smem ? tab : 0, h->s_river>>>(d, (int)n_tasks, use_smem);
+      else reach_wave_kernel<false><<<(unsigned)blocks, 128, use_smem ? tab : 0, h->s_river>>>(d, (int)n_tasks, use_smem);
       HB_CUDA(h, cudaMemcpyAsync(h->h_wave_err, d.error, sizeof(int), cudaMemcpyDeviceToHost, h->s_river));
       ++launches;
     }

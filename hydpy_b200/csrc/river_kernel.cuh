@@ -48,7 +48,7 @@ struct ReachMeta {
   int32_t simple_node;   // >= 0: the reach has ONE inlet node, in deploy mode newsim, with <= 32 entries (fast inflow)
   int32_t entry0, n_entry;
   int32_t owns_node;     // 1: this reach stores the row of simple_node
-  int32_t pad;
+  int32_t pad;           // 1: musk_mct reach (parameters in RiverDev::rpar/tpar, conditions in mct_cn/mct_rn/mct_rwd)
 };
 static_assert(sizeof(ReachMeta) == 64, "ReachMeta must stay one 64-byte record");
 
@@ -86,6 +86,15 @@ struct RiverDev {
   int* counter;                // task queue head
   int* progress;               // [n_reach] chunks completed in this run
   int* error;                  // set when a wait ran into the spin limit
+  // musk_mct reaches
+  const int32_t* nmbruns;      // [n_reach]
+  const double* rpar;          // [HB_RP_COUNT][n_reach]
+  const int64_t* trap_ptr;     // [n_reach+1]
+  const double* tpar;          // [HB_TP_COUNT][n_trap]
+  int64_t n_trap;
+  double* mct_cn;              // [n_seg] states.courantnumber (updated in place: one task per reach at a time)
+  double* mct_rn;              // [n_seg] states.reynoldsnumber
+  double* mct_rwd;             // [n_seg] factors.referencewaterdepth
 };
 
 #define HB_RIVER_CHUNK 32
@@ -148,6 +157,157 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- musk_mct (ref: hydpy/models/musk_mct.py RUN_METHODS; cross section hydpy/models/wq_trapeze_strickler.py) ----------
+// The Muskingum-Cunge-Todini segment update has the data flow of the classic one (new[i], old[i], old[i+1]), so it runs
+// in the same systolic pipeline: lane i = segment i keeps its Courant/Reynolds numbers and the reference water depth in
+// registers; the coefficients follow from a Pegasus root search for the reference water depth per segment and step.
+#define HB_PYMAX_R(a, b) (((b) > (a)) ? (b) : (a))
+#define HB_PYMIN_R(a, b) (((b) < (a)) ? (b) : (a))
+struct WqDev {
+  int n;
+  const double *wb, *ss, *ks, *cf, *bd, *ht, *ws, *pd;
+  double bottomslope;
+};
+struct WqRes { double wettedarea, surfacewidth, discharge, celerity; };
+
+// ref: wq_model.py Use_WaterDepth_V1 :2176-2252 = Calc_WettedAreas_V1 :580-597, Calc_WettedPerimeters_V1 :936-954,
+// Calc_WettedPerimeterDerivatives_V1 :1178-1189, Calc_SurfaceWidths_V1 :1371-1383, Calc_Discharges_V1 :1632-1649,
+// Calc_DischargeDerivatives_V1 :1860-1882, Calc_Celerity_V1 :2069-2075 and the sums over the trapezes
+__device__ __noinline__ void wq_use_waterdepth(const WqDev& q, double waterdepth, WqRes& o) {
+  double wettedarea = 0.0, surfacewidth = 0.0, discharge = 0.0, dischargederivative = 0.0;
+  const double sqrt_bs = pow(q.bottomslope, 0.5);
+  for (int i = 0; i < q.n; ++i) {
+    const double wb = __ldg(q.wb + i), ss = __ldg(q.ss + i), ht = __ldg(q.ht + i), ws = __ldg(q.ws + i), bd = __ldg(q.bd + i);
+    const double d = waterdepth - bd;
+    double a, p, dp, w;
+    if (d < 0.0) { a = 0.0; p = 0.0; dp = 0.0; w = 0.0; }
+    else if (d < ht) {
+      a = (wb + ss * d) * d;
+      p = wb + 2.0 * d * pow(ss * ss + 1.0, 0.5);   // (reference: pow(pow(ss, 2.0) + 1.0, 0.5); the square is exact either way)
+      dp = __ldg(q.pd + i);
+      w = wb + 2.0 * ss * d;
+    } else {
+      a = (wb + ws / 2.0) * ht + (wb + ws) * (d - ht);
+      p = wb + 2.0 * ht * pow(ss * ss + 1.0, 0.5) + 2.0 * (d - ht);
+      dp = 2.0;
+      w = wb + ws;
+    }
+    wettedarea += a;
+    surfacewidth += w;
+    if (waterdepth > bd) {
+      const double k = __ldg(q.cf + i) * __ldg(q.ks + i) * sqrt_bs;
+      discharge += k * pow(a, 5.0 / 3.0) / pow(p, 2.0 / 3.0);
+      dischargederivative += k * pow(a / p, 2.0 / 3.0) * (5.0 * p * w - 2.0 * a * dp) / (3.0 * p);
+    } else { discharge += 0.0; dischargederivative += 0.0; }
+  }
+  o.wettedarea = wettedarea;
+  o.surfacewidth = surfacewidth;
+  o.discharge = discharge;
+  o.celerity = (surfacewidth > 0.0) ? dischargederivative / surfacewidth : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ref: cythons/rootutils.pyx:25-83 PegasusBase.find_x on Return_ReferenceDischargeError_V1 (musk_model.py:306-314)
+__device__ __noinline__ double mct_find_waterdepth(const WqDev& q, double refq, double x0, double x1, double xmin,
+                                                   double xmax, double xtol, double ytol, int itermax) {
+  WqRes tmp;
+  double x = __longlong_as_double(0x7ff8000000000000LL), y, y0, y1, dx, y0_abs, y1_abs;
+  if (x0 > x1) { const double t = x0; x0 = x1; x1 = t; }
+  if (xmin > xmax) { const double t = xmin; xmin = xmax; xmax = t; }
+  x0 = HB_PYMAX_R(x0, xmin);
+  x1 = HB_PYMIN_R(x1, xmax);
+  for (int guard = 0; guard < 4096; ++guard) {
+    wq_use_waterdepth(q, x0, tmp); y0 = tmp.discharge - refq;
+    y0_abs = fabs(y0);
+    if (y0_abs <= ytol) return x0;
+    wq_use_waterdepth(q, x1, tmp); y1 = tmp.discharge - refq;
+    y1_abs = fabs(y1);
+    if (y1_abs <= ytol) return x1;
+    dx = x1 - x0;
+    if ((y0 < 0 && y1 < 0) || (y0 > 0 && y1 > 0)) {
+      if ((x0 == xmin) && (x1 == xmax)) return (y0_abs <= y1_abs) ? x0 : x1;
+      { const double a = x0 - dx; x0 = HB_PYMAX_R(a, xmin); }
+      { const double a = x1 + dx; x1 = HB_PYMIN_R(a, xmax); }
+    } else {
+      guard = -1;
+      break;
+    }
+  }
+  // (NaN discharges never bracket a root: the reference would loop forever on them, here the search gives up with NaN)
+  if (!(y0 == y0) || !(y1 == y1)) return x;
+  if (fabs(dx) < xtol) return (x0 + x1) / 2;
+  for (int iter = 0; iter < itermax; ++iter) {
+    x = x0 - y0 * dx / (y1 - y0);
+    if (x < xmin) return xmin;
+    else if (x > xmax) return xmax;
+    wq_use_waterdepth(q, x, tmp); y = tmp.discharge - refq;
+    if (fabs(y) < ytol) return x;
+    if (((y1 < 0) && (y < 0)) || ((y1 > 0) && (y > 0))) y0 *= y1 / (y1 + y);
+    else { x0 = x1; y0 = y1; }
+    x1 = x;
+    y1 = y;
+    dx = x1 - x0;
+    if (fabs(dx) < xtol) break;
+  }
+  return x;
+}
+
+// One segment, one step (all NmbRuns repetitions): returns new.discharge[i+1]; cn/rn/rwd: old values in, new values out.
+// ref: musk_model.py:245-254 Calc_ReferenceDischarge_V1, 383-399 Calc_ReferenceWaterDepth_V1, 415-424, 506-512
+// Calc_CorrectingFactor_V1, 548-560 Calc_CourantNumber_V1, 600-616 Calc_ReynoldsNumber_V1, 695-705
+// Calc_Coefficient1_Coefficient2_Coefficient3_V1, 792-806 Calc_Discharge_V2
+__device__ __noinline__ double mct_segment(const RiverDev& d, int64_t r, double in, double prev_in, double prev_out,
+                                           double* st /* cn, rn, rwd */) {
+  const int64_t nr = d.n_reach, t0 = d.trap_ptr[r];
+  WqDev q;
+  q.n = (int)(d.trap_ptr[r + 1] - t0);
+  q.wb = d.tpar + (int64_t)HB_TP_BOTTOMWIDTH * d.n_trap + t0;
+  q.ss = d.tpar + (int64_t)HB_TP_SIDESLOPE * d.n_trap + t0;
+  q.ks = d.tpar + (int64_t)HB_TP_STRICKLERCOEFFICIENT * d.n_trap + t0;
+  q.cf = d.tpar + (int64_t)HB_TP_CALIBRATIONFACTOR * d.n_trap + t0;
+  q.bd = d.tpar + (int64_t)HB_TP_BOTTOMDEPTH * d.n_trap + t0;
+  q.ht = d.tpar + (int64_t)HB_TP_TRAPEZEHEIGHT * d.n_trap + t0;
+  q.ws = d.tpar + (int64_t)HB_TP_SLOPEWIDTH * d.n_trap + t0;
+  q.pd = d.tpar + (int64_t)HB_TP_PERIMETERDERIVATIVE * d.n_trap + t0;
+  q.bottomslope = d.rpar[(int64_t)HB_RP_WQ_BOTTOMSLOPE * nr + r];
+  const double tolwd = d.rpar[(int64_t)HB_RP_TOLERANCEWATERDEPTH * nr + r], tolq = d.rpar[(int64_t)HB_RP_TOLERANCEDISCHARGE * nr + r],
+               bottomslope = d.rpar[(int64_t)HB_RP_BOTTOMSLOPE * nr + r], seconds = d.rpar[(int64_t)HB_RP_SECONDS * nr + r],
+               segmentlength = d.rpar[(int64_t)HB_RP_SEGMENTLENGTH * nr + r];
+  const int nruns = d.nmbruns[r];
+  const double cn_old = st[0], rn_old = st[1];
+  double cn = cn_old, rn = rn_old, rwd = st[2], nv = prev_out;
+  for (int run = 0; run < nruns; ++run) {
+    const double est = (run == 0) ? prev_out + in - prev_in : nv;
+    const double a = (in + est) / 2.0;
+    const double refq = HB_PYMAX_R(a, 0.0);
+    double mn, mx;
+    if (isnan(rwd) || isinf(rwd)) { mn = 0.0; mx = 2.0; }
+    else if (rwd <= 0.001) { mn = 0.0; mx = 0.01; }
+    else { mn = 0.9 * rwd; mx = 1.1 * rwd; }
+    const double b = refq / 10.0;
+    const double tol_q = HB_PYMIN_R(tolq, b);
+    rwd = mct_find_waterdepth(q, refq, mn, mx, 0.0, 1000.0, tolwd, tol_q, 100);
+    WqRes w;
+    wq_use_waterdepth(q, rwd, w);
+    double corr;
+    if (refq == 0.0) { corr = 1.0; cn = 0.0; rn = 0.0; }
+    else {
+      corr = w.celerity * w.wettedarea / refq;
+      cn = (w.celerity / corr) * (seconds / (1000.0 * segmentlength));
+      rn = refq / (corr * w.surfacewidth * bottomslope * w.celerity * (1000.0 * segmentlength));
+    }
+    double f = 1.0 / (1.0 + cn + rn);
+    const double c1 = (cn + rn - 1.0) * f;
+    if (cn_old != 0.0) f *= cn / cn_old;
+    const double c2 = (1 + cn_old - rn_old) * f;
+    const double c3 = (1 - cn_old + rn_old) * f;
+    if (in == prev_in && prev_in == prev_out) nv = in;
+    else nv = c1 * in + c2 * prev_in + c3 * prev_out;
+    nv = HB_PYMAX_R(nv, 0.0);
+  }
+  st[0] = cn; st[1] = rn; st[2] = rwd;
+  return nv;
+}
+
 // One task by one warp.  bulk: reaches with 1..HB_BULK_SMAX segments stop after the inflow (reach_bulk_kernel continues);
 // concurrent: several chunks of this reach run at the same time (head kernel) — only the last one stores the state of
 // a segment-free reach, straight into the final buffer.  WAVE: wait for the tasks this one depends on (persistent
@@ -178,7 +338,10 @@ __device__ __forceinline__ TaskPrep prep_from_meta(const RiverDev& d, int64_t r,
   return p;
 }
 
-template <bool WAVE>
+// MCT: the instance also handles musk_mct reaches (only launched when the network holds some: the calls into the root
+// search cost the lean classic instance its register budget — 56 registers, which is what lets the persistent
+// wavefront share the SMs with the runoff generation of the next window)
+template <bool WAVE, bool MCT>
 __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& tp, int c, int lane, bool bulk,
                                             bool concurrent) {
   const unsigned full = 0xffffffffu;
@@ -274,6 +437,18 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     if (d.dis_series) d.dis_series[t * d.n_seg + g0] = inflow;
     x_own = inflow;
   }
+  const bool mct = MCT && m.pad != 0;
+  if (mct && lane < len) {
+    // ref: musk_model.py:67-74 Adjust_Inflow_V1 (fluxes.inflow holds the adjusted value)
+    if (x_own < 0.0) {
+      const double tolneg = d.rpar[(int64_t)HB_RP_TOLERANCENEGATIVEINFLOW * d.n_reach + r];
+      x_own = (x_own < tolneg) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+      const int64_t t = ta + lane;
+      rin[t] = x_own;
+      if (S == 0) rout[t] = x_own;
+      if (d.dis_series) d.dis_series[t * d.n_seg + g0] = x_own;
+    }
+  }
   if (bulk && S >= 1 && S <= HB_BULK_SMAX) return true;
   const double x_last = __shfl_sync(full, x_own, len - 1);
   if (lane == 0) {
@@ -293,6 +468,12 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
         prev_out = __ldcg(dis_old + g0 + cbase + lane + 1);
       }
     }
+    double mst[3] = {0.0, 0.0, 0.0};                 // musk_mct: Courant number, Reynolds number, reference water depth
+    if (mct && lane < nseg) {
+      mst[0] = __ldcg(d.mct_cn + g0 + cbase + lane);
+      mst[1] = __ldcg(d.mct_rn + g0 + cbase + lane);
+      mst[2] = __ldcg(d.mct_rwd + g0 + cbase + lane);
+    }
     double xb = x_own;                               // input of this segment group at time ta+lane
     double yb = 0.0;                                 // its output at time ta+lane (collected below)
     const int nticks = len + nseg - 1;
@@ -303,7 +484,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       const int tloc = tau - lane;
       if (lane < nseg && tloc >= 0 && tloc < len) {
         // ref: musk_model.py:178-187 Calc_Discharge_V1 — (c0*new[i] + c1*old[i]) + c2*old[i+1]
-        const double nv = c0 * in + c1 * prev_in + c2 * prev_out;
+        const double nv = mct ? mct_segment(d, r, in, prev_in, prev_out, mst) : c0 * in + c1 * prev_in + c2 * prev_out;
         prev_in = in;
         prev_out = nv;
         out = nv;
@@ -314,6 +495,11 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       if (p == lane) yb = y;
     }
     if (lane < nseg) dis_new[g0 + cbase + lane + 1] = prev_out;
+    if (mct && lane < nseg) {
+      d.mct_cn[g0 + cbase + lane] = mst[0];
+      d.mct_rn[g0 + cbase + lane] = mst[1];
+      d.mct_rwd[g0 + cbase + lane] = mst[2];
+    }
     x_own = yb;                                      // the next segment group continues on this output
     if (cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
   }
@@ -321,6 +507,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
 }
 
 // ---- one launch per anti-diagonal ----------------------------------------------------------------------------------------
+template <bool MCT>
 __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const int32_t* __restrict__ reaches, int n,
                                                          int diag) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -328,7 +515,7 @@ __global__ void __launch_bounds__(128) reach_diag_kernel(const RiverDev d, const
   const int64_t r = reaches[warp];
   const int c = diag - d.reach_level[r];
   if (c < 0 || c >= d.n_chunks) return;
-  reach_chunk<false>(d, prep_from_meta(d, r, lane), c, lane, false, false);
+  reach_chunk<false, MCT>(d, prep_from_meta(d, r, lane), c, lane, false, false);
 }
 
 // ---- headwater reaches: every (reach, chunk) at once ------------------------------------------------------------------------
@@ -337,7 +524,7 @@ __global__ void __launch_bounds__(128) reach_head_kernel(const RiverDev d, const
   const int lane = threadIdx.x & 31;
   if (task >= (int64_t)n * d.n_chunks) return;
   const int c = (int)(task / n);
-  reach_chunk<false>(d, prep_from_meta(d, reaches[task - (int64_t)c * n], lane), c, lane, true, true);
+  reach_chunk<false, false>(d, prep_from_meta(d, reaches[task - (int64_t)c * n], lane), c, lane, true, true);
 }
 
 // lane = reach; `reaches` = the head reaches with 1..HB_BULK_SMAX segments (their inflow rows are complete)
@@ -427,6 +614,7 @@ __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restric
 // for task i+1 are in flight while task i runs.  A warp therefore owns up to three tasks, always processed in
 // increasing order, which keeps the no-deadlock argument intact (the smallest unfinished task is always some warp's
 // current task or becomes it as soon as that warp's smaller tasks — already finished — are retired).
+template <bool MCT>
 __global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
   extern __shared__ int32_t wave_tab[];
   const unsigned full = 0xffffffffu;
@@ -496,7 +684,7 @@ __global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n
     }
 #undef HB_W
     const int c = dg_cur - tp.m.level;
-    if (!reach_chunk<true>(d, tp, c, lane, false, false)) {
+    if (!reach_chunk<true, MCT>(d, tp, c, lane, false, false)) {
       if (lane == 0) atomicExch(d.error, 1);
       return;
     }

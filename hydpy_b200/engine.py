@@ -13,7 +13,8 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import layout
-from .abi import (LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc, hb_timing, ptr)
+from .abi import (LandBundle, LandStates, RiverBundle, hb_land_desc, hb_land_states, hb_river_desc, hb_river_states,
+                  hb_timing, ptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get("HYDPY_B200_LIB") or os.path.join(HERE, "libhydpy_b200.so")
@@ -21,6 +22,7 @@ LIBPATH = os.environ.get("HYDPY_B200_LIB") or os.path.join(HERE, "libhydpy_b200.
 EXPORTS = (
     "hb_abi_version", "hb_create", "hb_destroy", "hb_last_error", "hb_host_alloc", "hb_host_free", "hb_set_land",
     "hb_set_land_states", "hb_get_land_states", "hb_set_river", "hb_set_river_states", "hb_get_river_states",
+    "hb_set_river_states2", "hb_get_river_states2",
     "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_set_forcing_async", "hb_select_window", "hb_set_external", "hb_run",
     "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
     "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
@@ -65,6 +67,8 @@ def load_library() -> C.CDLL:
         "hb_set_land_states": (C.c_int, [H, C.POINTER(hb_land_states)]),
         "hb_get_land_states": (C.c_int, [H, C.POINTER(hb_land_states)]),
         "hb_set_river": (C.c_int, [H, C.POINTER(hb_river_desc)]),
+        "hb_set_river_states2": (C.c_int, [H, C.POINTER(hb_river_states)]),
+        "hb_get_river_states2": (C.c_int, [H, C.POINTER(hb_river_states)]),
         "hb_set_river_states": (C.c_int, [H, f64p]),
         "hb_get_river_states": (C.c_int, [H, f64p]),
         "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
@@ -222,12 +226,40 @@ class Engine:
         self._check(self._lib.hb_set_river(self._h, C.byref(d)), "hb_set_river")
         self.river = river
 
-    def set_river_states(self, discharge: np.ndarray) -> None:
+    def set_river_states(self, discharge: np.ndarray, mct_states: np.ndarray | None = None) -> None:
+        """`states.discharge` of all reaches, concatenated; `mct_states` [3, n_seg] = Courant numbers, Reynolds numbers and
+        reference water depths of the musk_mct reaches (required when the network holds such reaches)."""
         river = self._need_river()
         discharge = np.ascontiguousarray(discharge, dtype=np.float64)
         if discharge.shape != (river.n_seg,):
             raise ValueError(f"discharge must have shape ({river.n_seg},), not {discharge.shape}")
-        self._check(self._lib.hb_set_river_states(self._h, ptr(discharge, C.c_double)), "hb_set_river_states")
+        if mct_states is None and not river.any_mct:
+            self._check(self._lib.hb_set_river_states(self._h, ptr(discharge, C.c_double)), "hb_set_river_states")
+            return
+        if mct_states is None:
+            raise ValueError("the network holds musk_mct reaches: their conditions (mct_states [3, n_seg]) are required")
+        mct_states = np.ascontiguousarray(mct_states, dtype=np.float64)
+        if mct_states.shape != (3, river.n_seg):
+            raise ValueError(f"mct_states must have shape (3, {river.n_seg}), not {mct_states.shape}")
+        st = hb_river_states()
+        st.discharge = ptr(discharge, C.c_double)
+        st.courantnumber = ptr(mct_states[0], C.c_double)
+        st.reynoldsnumber = ptr(mct_states[1], C.c_double)
+        st.referencewaterdepth = ptr(mct_states[2], C.c_double)
+        self._check(self._lib.hb_set_river_states2(self._h, C.byref(st)), "hb_set_river_states2")
+
+    def get_river_mct_states(self) -> np.ndarray:
+        """[3, n_seg]: Courant numbers, Reynolds numbers, reference water depths (zeros for musk_classic reaches)."""
+        river = self._need_river()
+        out = np.zeros((3, river.n_seg))
+        dis = np.zeros(river.n_seg)
+        st = hb_river_states()
+        st.discharge = ptr(dis, C.c_double)
+        st.courantnumber = ptr(out[0], C.c_double)
+        st.reynoldsnumber = ptr(out[1], C.c_double)
+        st.referencewaterdepth = ptr(out[2], C.c_double)
+        self._check(self._lib.hb_get_river_states2(self._h, C.byref(st)), "hb_get_river_states2")
+        return out
 
     def get_river_states(self) -> np.ndarray:
         river = self._need_river()

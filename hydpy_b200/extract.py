@@ -518,6 +518,22 @@ def requested_series(problem: Problem) -> list[str]:
     return wanted
 
 
+def check_reach_series(problem: Problem) -> None:
+    """musk_mct: only inflow, outflow and states.discharge are recorded per step; the other sequences (hydraulic factors,
+    Courant/Reynolds numbers) end with their final values but keep no series — asking for them is an error, not a
+    silent gap."""
+    for element in problem.river_elements:
+        model = element.model
+        if _modelname(model) != "musk_mct":
+            continue
+        for group, keep in (("factors", ()), ("fluxes", ("inflow", "outflow")), ("states", ("discharge",))):
+            for seq in getattr(model.sequences, group, ()):
+                if getattr(seq, "ramflag", False) and seq.name not in keep:
+                    raise UnsupportedModelError(
+                        f"element `{element.name}`: the B200 engine does not record the time series of musk_mct "
+                        f"sequence `{seq.name}` (only inflow, outflow and discharge)")
+
+
 def requested_reach_states(problem: Problem) -> bool:
     """True when at least one musk_classic element keeps `states.discharge` in RAM."""
     return any(getattr(el.model.sequences.states.discharge, "ramflag", False) for el in problem.river_elements)

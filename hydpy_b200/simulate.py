@@ -19,7 +19,7 @@ import numpy as np
 
 from .abi import LandStates
 from .engine import Engine
-from .extract import Problem, extract, requested_reach_states, requested_series, write_back
+from .extract import Problem, check_reach_series, extract, requested_reach_states, requested_series, write_back
 
 _engines: dict[int, Engine] = {}
 
@@ -44,7 +44,7 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
     eng.set_land(problem.land)
     eng.set_land_states(problem.states)
     eng.set_river(problem.river)
-    eng.set_river_states(problem.discharge)
+    eng.set_river_states(problem.discharge, problem.mct_states)
     eng.select_series(series)
     eng.record_reach_states(reach_states)
     state_parts: list[np.ndarray] = []
@@ -81,6 +81,8 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
     if reach_states:
         result["reach_state_series"] = (np.concatenate(state_parts, axis=0) if state_parts
                                         else np.zeros((0, problem.river.n_seg)))
+    if problem.river.any_mct:
+        result["mct_states"] = eng.get_river_mct_states()
     return result
 
 
@@ -90,6 +92,7 @@ def simulate(hp: Any, *, device: int = 0, window: int | None = None, engine: Eng
 
     i0, i1 = hydpy.pub.timegrids.simindices
     problem = extract(hp, i0, i1)
+    check_reach_series(problem)
     result = run_problem(problem, engine, series=requested_series(problem), window=window, device=device,
                          reach_states=requested_reach_states(problem))
     write_back(problem, **result)

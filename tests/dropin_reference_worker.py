@@ -33,10 +33,13 @@ def oracle_run_problem(problem, engine=None, *, series=(), window=None, device=0
     st, dis = problem.states.copy(), problem.discharge.copy()
     qt, ser = oracle.land_run(problem.land, st, problem.forcing, problem.doy, series=list(series), threads=2)
     dser = np.zeros((problem.nt, problem.river.n_seg)) if reach_states else None
-    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser)
+    mct = None if problem.mct_states is None else problem.mct_states.copy()
+    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct)
     out = dict(states=st, discharge=dis, node_rows=node_rows, land_rows=qt, reach_out=rout, reach_in=rin, series=ser)
     if reach_states:
         out["reach_state_series"] = dser
+    if mct is not None:
+        out["mct_states"] = mct
     return out
 
 
@@ -54,6 +57,9 @@ def snapshot(hp):
                 if group == "states":
                     out[f"{element.name}:states.{seq.name}:new"] = np.array(seq.new)
                     out[f"{element.name}:states.{seq.name}:old"] = np.array(seq.old)
+        rwd = getattr(getattr(seqs, "factors", None), "referencewaterdepth", None)
+        if rwd is not None:
+            out[f"{element.name}:referencewaterdepth"] = np.array(rwd.value)
         rc = getattr(element.model, "rconcmodel", None)
         if rc is not None and rc.name == "rconc_uh":
             out[f"{element.name}:quh"] = np.array(rc.sequences.logs.quh.value)
@@ -69,10 +75,11 @@ def sibling_project():
     from hydpy import Element, Elements, HydPy, Node, Nodes
 
     pub.timegrids = "2000-01-01", "2000-01-09", "1h"
-    n_up, n_out = Node("sib_up"), Node("sib_out")
+    n_up, n_out, n_end = Node("sib_up"), Node("sib_out"), Node("sib_end")
     e_p = Element("sib_land_p", outlets=n_up)
     e_c = Element("sib_land_c", outlets=n_up)
     e_r = Element("sib_reach", inlets=n_up, outlets=n_out)
+    e_m = Element("sib_reach_mct", inlets=n_out, outlets=n_end)
     rng = np.random.default_rng(11)
     common = """
 parameterstep("1h")
@@ -113,10 +120,31 @@ with model.add_rconcmodel_v1("rconc_nash"):
     exec('from hydpy.models.musk_classic import *\nparameterstep("1h")\nnmbsegments(3)\ncoefficients(damp=0.2)\n', ns)
     reach = ns["model"]
     e_r.model = reach
+    # a musk_mct reach with a two-trapeze cross section downstream (ref: hydpy/models/musk_mct.py:40-72)
+    ns = {}
+    exec("""from hydpy.models.musk_mct import *
+parameterstep("1h")
+nmbsegments(4)
+catchmentarea(2500.0)
+length(20.0)
+bottomslope(0.0005)
+with model.add_wqmodel_v1("wq_trapeze_strickler"):
+    nmbtrapezes(2)
+    bottomlevels(0.0, 1.5)
+    bottomwidths(4.0, 10.0)
+    sideslopes(2.0, 4.0)
+    stricklercoefficients(30.0, 25.0)
+    calibrationfactors(1.0, 1.0)
+""", ns)
+    e_m.model = ns["model"]
     hp = HydPy("sibling_project")
-    hp.update_devices(nodes=Nodes(n_up, n_out), elements=Elements(e_p, e_c, e_r))
+    hp.update_devices(nodes=Nodes(n_up, n_out, n_end), elements=Elements(e_p, e_c, e_r, e_m))
     hp.update_parameters()
     hp.prepare_allseries()
+    for group, keep in (("factors", ()), ("fluxes", ("inflow", "outflow")), ("states", ("discharge",))):
+        for seq in getattr(e_m.model.sequences, group):       # musk_mct: the engine records these three series only
+            if seq.name not in keep:
+                seq.prepare_series(allocate_ram=False)
     nt = len(pub.timegrids.init)
     for element in (e_p, e_c):
         model = element.model
@@ -134,6 +162,9 @@ with model.add_rconcmodel_v1("rconc_nash"):
             sta.bw1(2.0); sta.bw2(3.0); sta.lz(10.0)
         model.rconcmodel.sequences.states.sc(0.05)
     reach.sequences.states.discharge(0.0)
+    e_m.model.sequences.states.discharge(0.5)
+    e_m.model.sequences.states.courantnumber(0.5)
+    e_m.model.sequences.states.reynoldsnumber(1.0)
     return hp, (("2000-01-01", "2000-01-04"), ("2000-01-04", "2000-01-09"))
 
 
@@ -159,8 +190,14 @@ def main() -> None:
 
     initial = copy.deepcopy(hp.conditions)
 
+    # (factors.referencewaterdepth of musk_mct — the start value of its root search — is no condition: reset it by hand)
+    initial_rwd = {el: np.array(el.model.sequences.factors.referencewaterdepth.value) for el in hp.elements
+                   if el.model.name == "musk_mct"}
+
     def run(simulate):
         hp.conditions = copy.deepcopy(initial)
+        for el, value in initial_rwd.items():
+            el.model.sequences.factors.referencewaterdepth.value = value
         for node in hp.nodes:
             node.sequences.sim.series[:] = np.nan
         for element in hp.elements:

@@ -194,6 +194,64 @@ def add_siblings(land: LandBundle, states: LandStates, seed: int = 0, fraction: 
     land.normalise()
 
 
+def add_mct(river: RiverBundle, seed: int = 0, fraction: float = 0.5) -> np.ndarray:
+    """Turn `fraction` of the reaches into musk_mct reaches with 1-3 trapeze cross sections (SURVEY.md §8f-3), in place;
+    returns their conditions [3, n_seg] (Courant numbers, Reynolds numbers, reference water depths — NaN = no start
+    value yet, like a freshly prepared reference model)."""
+    rng = np.random.default_rng(seed + 555)
+    river.normalise()
+    nr = river.n_reach
+    is_mct = rng.uniform(size=nr) < fraction
+    river.reach_model = np.where(is_mct, layout.REACH_MCT, layout.REACH_CLASSIC).astype(np.int32)
+    river.nmbruns = np.where(is_mct, rng.integers(1, 3, size=nr), 1).astype(np.int32)
+    RP, TP = layout.RP, layout.TP
+    rpar = np.zeros((len(layout.RPAR), nr))
+    rpar[RP["tolerancewaterdepth"]] = np.where(rng.uniform(size=nr) < 0.5, 0.0, 1e-4)
+    rpar[RP["tolerancedischarge"]] = rng.uniform(1e-4, 2e-2, nr)
+    rpar[RP["tolerancenegativeinflow"]] = np.where(rng.uniform(size=nr) < 0.5, -np.inf, -0.5)
+    slope = rng.uniform(2e-4, 3e-3, nr)
+    rpar[RP["bottomslope"]] = slope
+    rpar[RP["wq_bottomslope"]] = slope
+    rpar[RP["seconds"]] = 3600.0
+    rpar[RP["segmentlength"]] = rng.uniform(1.0, 8.0, nr)
+    river.rpar = rpar
+    ntr = np.where(is_mct, rng.integers(1, 4, size=nr), 0)
+    river.trap_ptr = np.concatenate([[0], np.cumsum(ntr)]).astype(np.int64)
+    tp = np.zeros((len(layout.TPAR), int(river.trap_ptr[-1])))
+    for q in range(nr):
+        n = int(ntr[q])
+        if not n:
+            continue
+        t0 = int(river.trap_ptr[q])
+        heights = rng.uniform(0.5, 2.5, n)
+        levels = np.concatenate([[0.0], np.cumsum(heights[:-1])])
+        ss = rng.uniform(0.0, 6.0, n)
+        th = np.full(n, np.inf)
+        th[:-1] = np.diff(levels)
+        ws = np.full(n, np.inf)
+        ws[:-1] = 2.0 * ss[:-1] * th[:-1]
+        tp[TP["bottomwidth"], t0:t0 + n] = np.concatenate([[rng.uniform(3.0, 20.0)], rng.uniform(0.0, 30.0, n - 1)])
+        tp[TP["sideslope"], t0:t0 + n] = ss
+        tp[TP["stricklercoefficient"], t0:t0 + n] = rng.uniform(15.0, 40.0, n)
+        tp[TP["calibrationfactor"], t0:t0 + n] = rng.uniform(0.8, 1.2, n)
+        tp[TP["bottomdepth"], t0:t0 + n] = levels - levels[0]
+        tp[TP["trapezeheight"], t0:t0 + n] = th
+        tp[TP["slopewidth"], t0:t0 + n] = ws
+        tp[TP["perimeterderivative"], t0:t0 + n] = 2.0 * (1.0 + ss**2.0) ** 0.5
+    river.tpar = tp
+    river.normalise()
+    mct = np.zeros((3, river.n_seg))
+    for q in range(nr):
+        if not is_mct[q]:
+            continue
+        g0, g1 = int(river.seg_ptr[q]), int(river.seg_ptr[q + 1]) - 1
+        fresh = rng.uniform() < 0.4
+        mct[0, g0:g1] = 0.0 if fresh else rng.uniform(0.2, 1.2, g1 - g0)
+        mct[1, g0:g1] = 0.0 if fresh else rng.uniform(0.3, 3.0, g1 - g0)
+        mct[2, g0:g1] = np.nan if fresh else rng.uniform(0.3, 2.0, g1 - g0)
+    return mct
+
+
 def random_forcing(nt: int, ncol: int, seed: int = 0) -> tuple[np.ndarray, np.ndarray]:
     rng = np.random.default_rng(seed + 1000)
     p = rng.gamma(0.4, 2.0, size=(nt, ncol)) * (rng.uniform(size=(nt, ncol)) < 0.5)

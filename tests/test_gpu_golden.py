@@ -16,6 +16,7 @@ HLAND = load_scenarios("hland_96_integration.npz")
 HLAND_P = load_scenarios("hland_96p_integration.npz")
 HLAND_C = load_scenarios("hland_96c_integration.npz")
 MUSK = load_scenarios("musk_classic_integration.npz")
+MUSK_MCT = load_scenarios("musk_mct_integration.npz")
 LAHN = load_scenarios("lahn_daily.npz")
 LAHN_H = load_scenarios("lahn_hourly_members.npz")
 
@@ -89,6 +90,23 @@ def test_musk_classic_integration(engine, name):
     # routing has no libm call at all: bit-identical
     assert np.array_equal(res["reach_out"], sc.expected("reach_out"))
     assert np.array_equal(res["discharge"], sc.expected("discharge"))
+
+
+@pytest.mark.parametrize("name", sorted(MUSK_MCT))
+def test_musk_mct_integration(engine, name):
+    """musk_mct + wq_trapeze_strickler — outflow, states.discharge of every step, final Courant/Reynolds
+    numbers and reference water depths of the reference's five integration tests (root search included)."""
+    sc = MUSK_MCT[name]
+    p = sc.problem
+    for window in (None, 37):
+        res = run_problem(p, engine, reach_states=True, window=window)
+        assert_close(res["reach_out"], sc.expected("reach_out"), f"{sc.name}: outflow (window {window})")
+        assert_close(res["reach_in"], sc.expected("reach_in"), f"{sc.name}: inflow")
+        assert_close(res["node_rows"][p.node_writeback], sc.expected("node_rows")[p.node_writeback], f"{sc.name}: nodes")
+        assert_close(res["discharge"], sc.expected("discharge"), f"{sc.name}: final discharge")
+        exp = sc.expected("dis_series")
+        assert_close(np.where(np.isnan(exp), np.nan, res["reach_state_series"]), exp, f"{sc.name}: states.discharge series")
+        assert_close(res["mct_states"], sc.expected("mct_states"), f"{sc.name}: final Courant/Reynolds numbers, water depths")
 
 
 def test_lahn_daily(engine):

@@ -5,7 +5,7 @@ import pytest
 
 from hydpy_b200 import Engine, Problem, layout, run_problem, synth
 from oracle import oracle
-from tests.randland import add_siblings, random_forcing, random_land, random_river
+from tests.randland import add_mct, add_siblings, random_forcing, random_land, random_river
 from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -26,9 +26,10 @@ def oracle_run(problem, series=()):
     qt, ser = oracle.land_run(problem.land, st, problem.forcing, problem.doy, series=series, threads=4)
     dis = problem.discharge.copy()
     dser = np.zeros((problem.nt, problem.river.n_seg))
-    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser)
+    mct = None if problem.mct_states is None else problem.mct_states.copy()
+    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct)
     return dict(states=st, land_rows=qt, series=ser, discharge=dis, node_rows=node_rows, reach_out=rout, reach_in=rin,
-                reach_state_series=dser)
+                reach_state_series=dser, mct_states=mct)
 
 
 def compare(res, ref, what, series=()):
@@ -88,6 +89,31 @@ def test_random_ragged_problem_with_sibling_models(engine, seed):
         assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
     for n in res1["states"].NAMES:
         assert np.array_equal(getattr(res1["states"], n), getattr(res2["states"], n), equal_nan=True), n
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_network_with_musk_mct_reaches(engine, seed):
+    """musk_classic and musk_mct reaches (1-3 trapezes, 0..40 segments, one or two runs per segment, fresh and warm start
+    values of the root search) side by side in a random DAG with deploy modes."""
+    ne, nt = 40, 80
+    land, states = random_land(ne, seed=seed + 40)
+    forcing, doy = random_forcing(nt, ne, seed=seed + 40)
+    river, discharge, _ = random_river(ne, 30, seed=seed + 40)
+    mct = add_mct(river, seed=seed + 40)
+    assert river.any_mct and (river.reach_model == layout.REACH_CLASSIC).any()
+    rng = np.random.default_rng(seed)
+    ext = rng.uniform(0, 3, size=(river.n_ext, nt))
+    ext[1::2][rng.uniform(size=ext[1::2].shape) < 0.3] = np.nan
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext,
+                      mct_states=mct)
+    ref = oracle_run(problem)
+    res = run_problem(problem, engine, reach_states=True)
+    compare(res, ref, f"musk_mct seed {seed}")
+    assert_close(res["reach_state_series"], ref["reach_state_series"], "musk_mct: states.discharge of every step")
+    assert_close(res["mct_states"], ref["mct_states"], "musk_mct: final Courant/Reynolds numbers and water depths")
+    res2 = run_problem(problem, engine, window=23)
+    for key in ("node_rows", "reach_out", "discharge", "mct_states"):
+        assert np.array_equal(res[key], res2[key], equal_nan=True), f"window splitting changes {key}"
 
 
 def test_long_reaches_more_than_32_segments(engine):
