@@ -1,4 +1,4 @@
-// river_kernel.cuh — musk_classic routing over the node/reach DAG.
+// river_kernel.cuh — musk_classic (and musk_mct, see "musk_mct" below) routing over the node/reach DAG.
 //
 // Replaces `c_musk_classic.pyx` (`Pick_Inflow_V1`, `Update_Discharge_V1`, `Calc_Discharge_V1`, `Calc_Outflow_V1`,
 // `Pass_Outflow_V1`; ref: hydpy/models/musk/musk_model.py:19-187, 809-848; SegmentModel.run

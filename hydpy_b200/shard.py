@@ -36,6 +36,7 @@ class Shard:
     recv: list[tuple[int, list[int]]]   # … followed by boundary rows: (peer rank, local external rows), peer-sorted
     send: list[tuple[int, list[int]]]   # (peer rank, local reach indices), peer-sorted; order = peer's recv order
     recv_global: dict[int, list[int]] = dataclasses.field(default_factory=dict)  # peer -> global reaches, row order
+    mct_states: np.ndarray | None = None   # [3, n_seg] conditions of the shard's musk_mct reaches
 
     def local_ext(self, ext: np.ndarray, nt: int) -> np.ndarray:
         """The rows of the global external block this shard reads, padded with zero rows for the boundary series."""
@@ -169,7 +170,7 @@ def assign_nodes(land: LandBundle, river: RiverBundle, world: int) -> np.ndarray
 
 
 def partition(land: LandBundle, states: LandStates, river: RiverBundle, discharge: np.ndarray, world: int,
-              node_rank: np.ndarray | None = None) -> list[Shard]:
+              node_rank: np.ndarray | None = None, mct_states: np.ndarray | None = None) -> list[Shard]:
     """Cut the basin into `world` shards (see module docstring).  `node_rank` overrides the built-in assignment."""
     land.normalise()
     river.normalise()
@@ -241,11 +242,18 @@ def partition(land: LandBundle, states: LandStates, river: RiverBundle, discharg
         inlet_node: list[int] = []
         seg_ptr = [0]
         dis_parts = []
+        mct_parts: list[np.ndarray] = []
+        trap_ptr = [0]
+        trap_idx: list[int] = []
         for q in reaches:
             inlet_node.extend(node_l[int(n)] for n in river.inlet_node[river.inlet_ptr[q]:river.inlet_ptr[q + 1]])
             inlet_ptr.append(len(inlet_node))
             seg_ptr.append(seg_ptr[-1] + int(river.seg_ptr[q + 1] - river.seg_ptr[q]))
             dis_parts.append(discharge[river.seg_ptr[q]:river.seg_ptr[q + 1]])
+            if mct_states is not None:
+                mct_parts.append(mct_states[:, river.seg_ptr[q]:river.seg_ptr[q + 1]])
+            trap_ptr.append(trap_ptr[-1] + int(river.trap_ptr[q + 1] - river.trap_ptr[q]))
+            trap_idx.extend(range(int(river.trap_ptr[q]), int(river.trap_ptr[q + 1])))
         outlet = np.array([node_l.get(int(river.reach_outlet[q]), -1) if reach_rank[q] == r and
                            river.reach_outlet[q] >= 0 and node_rank[river.reach_outlet[q]] == r else -1
                            for q in reaches], np.int32)
@@ -254,7 +262,9 @@ def partition(land: LandBundle, states: LandStates, river: RiverBundle, discharg
             node_mode=river.node_mode[nodes], node_ext=np.array(
                 [ext_l[int(x)] if x >= 0 else -1 for x in river.node_ext[nodes]], np.int32),
             inlet_ptr=np.array(inlet_ptr, np.int64), inlet_node=np.array(inlet_node, np.int32), reach_outlet=outlet,
-            seg_ptr=np.array(seg_ptr, np.int64), coef=river.coef[:, reaches], n_ext=k)
+            seg_ptr=np.array(seg_ptr, np.int64), coef=river.coef[:, reaches], n_ext=k,
+            reach_model=river.reach_model[reaches], nmbruns=river.nmbruns[reaches], rpar=river.rpar[:, reaches],
+            trap_ptr=np.array(trap_ptr, np.int64), tpar=river.tpar[:, np.array(trap_idx, np.int64)])
         sub_river.normalise()
         sub_land, sub_states = subset_land(
             land, states, elements,
@@ -262,7 +272,8 @@ def partition(land: LandBundle, states: LandStates, river: RiverBundle, discharg
         shards.append(Shard(
             rank=r, stage=0, elements=elements, nodes=nodes, reaches=reaches, land=sub_land, states=sub_states,
             river=sub_river, discharge=np.concatenate(dis_parts + [np.zeros(0)]),
-            ext_global=np.array(ext_global, np.int64), recv=recv, send=[], recv_global=boundary))
+            ext_global=np.array(ext_global, np.int64), recv=recv, send=[], recv_global=boundary,
+            mct_states=(np.concatenate(mct_parts + [np.zeros((3, 0))], axis=1) if mct_states is not None else None)))
     # sends mirror the receives; stages follow the shard DAG
     for s in shards:
         for peer, _rows in s.recv:

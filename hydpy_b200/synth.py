@@ -301,6 +301,7 @@ def replicate_river(river: RiverBundle, discharge: np.ndarray, members: int, n_l
                     ) -> tuple[RiverBundle, np.ndarray]:
     """Copy the river network once per ensemble member (each member routes its own discharges)."""
     m = int(members)
+    river.normalise()
     nn, nr = river.n_node, river.n_reach
 
     def tile_ptr(p: np.ndarray) -> np.ndarray:
@@ -317,6 +318,8 @@ def replicate_river(river: RiverBundle, discharge: np.ndarray, members: int, n_l
         reach_outlet=np.concatenate([np.where(river.reach_outlet >= 0, river.reach_outlet + i * nn, -1)
                                      for i in range(m)]).astype(np.int32),
         seg_ptr=tile_ptr(river.seg_ptr), coef=np.tile(river.coef, (1, m)), n_ext=river.n_ext,
+        reach_model=np.tile(river.reach_model, m), nmbruns=np.tile(river.nmbruns, m), rpar=np.tile(river.rpar, (1, m)),
+        trap_ptr=tile_ptr(river.trap_ptr), tpar=np.tile(river.tpar, (1, m)),
     )
     out.normalise()
     return out, np.tile(discharge, m)

@@ -9,7 +9,7 @@ import pytest
 
 from hydpy_b200 import layout, shard, synth
 from oracle import oracle
-from tests.randland import random_forcing, random_land, random_river
+from tests.randland import add_mct, random_forcing, random_land, random_river
 
 
 def make_problem(ne=240, nt=40, levels=14, seed=3):
@@ -158,3 +158,41 @@ def test_world_size_2_over_gloo_matches_unsharded(tmp_path):
     land, states, river, discharge, forcing, doy = make_problem(ne=160, nt=24, levels=10)
     ref_nodes, _, _, _ = run_unsharded(land, states, river, discharge, forcing, doy)
     assert np.array_equal(np.load(path), ref_nodes)
+
+
+def test_partition_with_musk_mct_reaches():
+    """A cut through a network of musk_classic and musk_mct reaches: parameters, trapezes and conditions
+    of the musk_mct reaches travel with their shard; executed in stage order the result is the unsharded one bit for bit."""
+    ne, nt = 40, 30
+    land, states = random_land(ne, seed=13)
+    forcing, doy = random_forcing(nt, ne, seed=13)
+    river, discharge, _ = random_river(ne, 30, seed=13, smax=12, n_ext=0)
+    first = river.inlet_ptr[:-1]
+    river.inlet_node = river.inlet_node[first]
+    river.inlet_ptr = np.arange(river.n_reach + 1, dtype=np.int64)
+    river.normalise()
+    mct = add_mct(river, seed=13)
+    st, dis, m = states.copy(), discharge.copy(), mct.copy()
+    qt, _ = oracle.land_run(land, st, forcing, doy)
+    ref_nodes, ref_rout, _ = oracle.river_run(river, dis, qt, None, mct_states=m)
+    node_rank = (np.arange(river.n_node) >= ne + 8).astype(int)
+    s0, s1 = shard.partition(land, states, river, discharge, 2, node_rank=node_rank, mct_states=mct)
+    assert s0.river.any_mct and s1.river.any_mct and s1.recv
+    outs = {}
+    got_mct = np.full_like(mct, np.nan)
+    for s in (s0, s1):
+        ext = s.local_ext(np.zeros((0, nt)), nt)
+        for (peer, rows), (_, sent) in zip(s.recv, s0.send):
+            for row, q_local in zip(rows, sent):
+                ext[row] = outs[peer][1][q_local]
+        st_s, dis_s, m_s = s.states.copy(), s.discharge.copy(), s.mct_states.copy()
+        qt_s, _ = oracle.land_run(s.land, st_s, forcing, doy)
+        outs[s.rank] = oracle.river_run(s.river, dis_s, qt_s, ext, mct_states=m_s)[:2]
+        for i, q in enumerate(s.reaches):
+            got_mct[:, river.seg_ptr[q]:river.seg_ptr[q + 1]] = m_s[:, s.river.seg_ptr[i]:s.river.seg_ptr[i + 1]]
+    nodes = np.zeros_like(ref_nodes)
+    nodes[s0.nodes], nodes[s1.nodes] = outs[0][0], outs[1][0]
+    rout = np.zeros_like(ref_rout)
+    rout[s0.reaches], rout[s1.reaches] = outs[0][1], outs[1][1]
+    assert np.array_equal(nodes, ref_nodes, equal_nan=True) and np.array_equal(rout, ref_rout, equal_nan=True)
+    assert np.array_equal(got_mct, m, equal_nan=True)
