@@ -49,6 +49,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--cpu-elements", type=int, default=0, help="element sample of the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-blocks", type=int, default=0, help="persistent routing blocks per SM (0 = engine default)")
+    ap.add_argument("--river-sweep", default="", help="routing sweep: persistent | grouped | launches (default: engine's)")
     return ap.parse_args()
 
 
@@ -219,6 +220,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     eng.set_land_states(states)
     eng.set_river(river)
     eng.set_river_states(discharge)
+    if args.river_sweep:
+        eng.set_river_sweep(args.river_sweep)
     if args.wave_blocks:
         eng.set_wave_blocks(args.wave_blocks)
     if dist.world > 1:

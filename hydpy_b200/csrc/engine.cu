@@ -166,6 +166,7 @@ struct hb_engine {
   int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
   bool river_state_series = false;        // record musk_classic states.discharge per step
   int wave_blocks = HB_WAVE_BLOCKS_PER_SM;  // persistent wavefront blocks per SM
+  bool wave_blocks_set = false;             // (the grouped wavefront defaults to 2 blocks of 64 threads)
   DBuf<double> d_dis_series[2];
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
@@ -200,6 +201,12 @@ struct hb_engine {
   DBuf<int> d_progress, d_wave_ctl;     // d_wave_ctl = {queue head, error flag}
   std::vector<int32_t> wave_lvl_ptr;    // [n_levels+1]
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
+  // grouped wavefront (HB_RIVER_GROUPED)
+  DBuf<int32_t> d_unit_start, d_unit_reach, d_unit_info, d_unit_lvl_ptr, d_diag_start_g;
+  DBuf<double> d_zero_row;
+  std::vector<int32_t> unit_lvl_ptr;
+  int64_t n_units = 0;
+  int diag_chunks_g = -1;
   int diag_chunks = -1;                 // n_chunks the uploaded diag_start belongs to
   int* h_wave_err = nullptr;            // pinned copy of the wavefront's error flag
   // musk_mct reaches
@@ -796,13 +803,14 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
     case HB_OPT_RIVER_WAVE_BLOCKS:
       HB_REQUIRE(h, value >= 1 && value <= 8, HB_EINVAL, "hb_set_option: wavefront blocks per SM must be 1..8");
       h->wave_blocks = (int)value;
+      h->wave_blocks_set = true;
       return HB_OK;
     case HB_OPT_RIVER_STATE_SERIES:
       h->river_state_series = value != 0;
       if (!value) { h->d_dis_series[0].release(); h->d_dis_series[1].release(); }
       return HB_OK;
     case HB_OPT_RIVER_SWEEP:
-      HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES, HB_EINVAL,
+      HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES || value == HB_RIVER_GROUPED, HB_EINVAL,
                  "hb_set_option: invalid routing sweep");
       h->river_sweep = (int)value;
       return HB_OK;
@@ -1015,6 +1023,40 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
       return rc_;
     std::vector<double> zero((size_t)r->n_seg, 0.0), nan_((size_t)r->n_seg, std::nan(""));
     if ((rc_ = upload(h, h->d_mct_cn, zero)) || (rc_ = upload(h, h->d_mct_rn, zero)) || (rc_ = upload(h, h->d_mct_rwd, nan_)))
+      return rc_;
+  }
+  // units of the grouped wavefront: per level the simple reaches (one inlet node in newsim mode, at most HB_GRP_SMAX
+  // segments, musk_classic) in groups of 32, every other reach on its own
+  {
+    std::vector<int32_t> unit_start{0}, unit_reach, unit_info, unit_lvl(nlev + 1, 0);
+    for (int l = 0; l < nlev; ++l) {
+      std::vector<int32_t> simple, other;
+      for (int i = wave_lvl[l]; i < wave_lvl[l + 1]; ++i) {
+        const int32_t q = wave_order[i];
+        const ReachMeta& m = meta[q];
+        (m.simple_node >= 0 && m.nseg <= HB_GRP_SMAX && m.n_entry <= HB_GRP_EMAX && m.n_dep <= HB_GRP_EMAX && m.pad == 0
+             ? simple : other).push_back(q);
+      }
+      for (size_t i = 0; i < simple.size(); i += 32) {
+        const size_t n = std::min<size_t>(32, simple.size() - i);
+        unit_reach.insert(unit_reach.end(), simple.begin() + i, simple.begin() + i + n);
+        unit_start.push_back((int32_t)unit_reach.size());
+        unit_info.push_back(l | (1 << 30));
+      }
+      for (int32_t q : other) {
+        unit_reach.push_back(q);
+        unit_start.push_back((int32_t)unit_reach.size());
+        unit_info.push_back(l);
+      }
+      unit_lvl[l + 1] = (int32_t)unit_info.size();
+    }
+    { std::vector<double> z(32, 0.0); int rcz = upload(h, h->d_zero_row, z); if (rcz) return rcz; }
+    h->n_units = (int64_t)unit_info.size();
+    h->unit_lvl_ptr = unit_lvl;
+    h->diag_chunks_g = -1;
+    int rc_;
+    if ((rc_ = upload(h, h->d_unit_start, unit_start)) || (rc_ = upload(h, h->d_unit_reach, unit_reach)) ||
+        (rc_ = upload(h, h->d_unit_info, unit_info)) || (rc_ = upload(h, h->d_unit_lvl_ptr, unit_lvl)))
       return rc_;
   }
   h->n_head_all = (int64_t)head_all.size(); h->n_head_bulk = (int64_t)head_bulk.size(); h->n_wave = (int64_t)wave_order.size();
@@ -1454,6 +1496,8 @@ static int run_river(hb_engine* h) {
   d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
   d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
+  d.unit_start = h->d_unit_start.p; d.unit_reach = h->d_unit_reach.p; d.unit_info = h->d_unit_info.p;
+  d.unit_lvl_ptr = h->d_unit_lvl_ptr.p; d.zero_row = h->d_zero_row.p;
   d.nmbruns = h->d_nmbruns.p; d.rpar = h->d_rpar.p; d.trap_ptr = h->d_trap_ptr.p; d.tpar = h->d_tpar.p; d.n_trap = h->n_trap;
   d.mct_cn = h->d_mct_cn.p; d.mct_rn = h->d_mct_rn.p; d.mct_rwd = h->d_mct_rwd.p;
   int64_t launches = 0;
@@ -1492,6 +1536,21 @@ static int run_river(hb_engine* h) {
         h->diag_chunks = n_chunks;
       }
       d.diag_start = h->d_diag_start.p;
+      if (h->river_sweep == HB_RIVER_GROUPED) {
+        if (h->diag_chunks_g != n_chunks) {
+          std::vector<int32_t> ds(d.n_diag + 1, 0);
+          for (int dg = 0; dg < d.n_diag; ++dg) {
+            const int l_lo = dg - n_chunks + 1 > 0 ? dg - n_chunks + 1 : 0;
+            const int l_hi = dg < nlev - 1 ? dg : nlev - 1;
+            ds[dg + 1] = ds[dg] + (h->unit_lvl_ptr[l_hi + 1] - h->unit_lvl_ptr[l_lo]);
+          }
+          HB_CUDA(h, cudaStreamSynchronize(h->s_river));
+          HB_CUDA(h, h->d_diag_start_g.reserve(ds.size()));
+          HB_CUDA(h, cudaMemcpy(h->d_diag_start_g.p, ds.data(), ds.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+          h->diag_chunks_g = n_chunks;
+        }
+        d.diag_start = h->d_diag_start_g.p;
+      }
       wave_init_kernel<<<(unsigned)((h->n_reach + 255) / 256), 256, 0, h->s_river>>>(d);
       ++launches;
     }
@@ -1511,7 +1570,29 @@ static int run_river(hb_engine* h) {
         ++launches;
       }
     }
-    if (h->n_wave > 0) {
+    if (h->n_wave > 0 && h->river_sweep == HB_RIVER_GROUPED) {
+      const int64_t n_tasks = h->n_units * n_chunks;
+      HB_REQUIRE(h, n_tasks < (int64_t)1 << 31, HB_EINVAL, "hb_run: too many routing tasks for one window; use shorter windows");
+      int64_t blocks = (n_tasks + HB_GRP_WARPS - 1) / HB_GRP_WARPS;
+      const int64_t cap = (int64_t)h->prop.multiProcessorCount * (h->wave_blocks_set ? h->wave_blocks : 2);
+      if (blocks > cap) blocks = cap;
+      if (h->any_mct) reach_wave2_kernel<true><<<(unsigned)blocks, 32 * HB_GRP_WARPS, HB_GRP_SMEM, h->s_river>>>(d, (int)n_tasks);
+      else reach_wave2_kernel<false><<<(unsigned)blocks, 32 * HB_GRP_WARPS, HB_GRP_SMEM, h->s_river>>>(d, (int)n_tasks);
+      HB_CUDA(h, cudaMemcpyAsync(h->h_wave_err, d.error, sizeof(int), cudaMemcpyDeviceToHost, h->s_river));
+#ifdef HB_GRP_DEBUG
+      {
+        cudaStreamSynchronize(h->s_river);
+        unsigned long long c_[8];
+        cudaMemcpyFromSymbol(c_, hb_grp_dbg, sizeof c_);
+        fprintf(stderr, "[grp] tasks %llu; cycles per task: meta %.0f wait %.0f state+entries %.0f inflow %.0f recurrence %.0f rows+state %.0f release %.0f\n",
+                c_[7], (double)c_[0] / c_[7], (double)c_[1] / c_[7], (double)c_[2] / c_[7], (double)c_[3] / c_[7],
+                (double)c_[4] / c_[7], (double)c_[5] / c_[7], (double)c_[6] / c_[7]);
+        unsigned long long z_[8] = {0};
+        cudaMemcpyToSymbol(hb_grp_dbg, z_, sizeof z_);
+      }
+#endif
+      ++launches;
+    } else if (h->n_wave > 0) {
       const int64_t n_tasks = h->n_wave * n_chunks;
       HB_REQUIRE(h, n_tasks < (int64_t)1 << 31, HB_EINVAL, "hb_run: too many routing tasks for one window; use shorter windows");
       int64_t blocks = (n_tasks + 3) / 4;

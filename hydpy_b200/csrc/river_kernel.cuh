@@ -86,6 +86,12 @@ struct RiverDev {
   int* counter;                // task queue head
   int* progress;               // [n_reach] chunks completed in this run
   int* error;                  // set when a wait ran into the spin limit
+  // grouped wavefront (reach_wave2_kernel): units = groups of up to 32 simple reaches of one level, or single reaches
+  const int32_t* unit_start;   // [n_units+1] into unit_reach
+  const int32_t* unit_reach;   // member reaches, unit after unit
+  const int32_t* unit_info;    // [n_units] level | (group ? 1 << 30 : 0)
+  const int32_t* unit_lvl_ptr; // [n_levels+1] into the units (sorted by level)
+  const double* zero_row;      // 32 zeros
   // musk_mct reaches
   const int32_t* nmbruns;      // [n_reach]
   const double* rpar;          // [HB_RP_COUNT][n_reach]
@@ -151,6 +157,11 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const RiverDev d, const i
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -373,6 +384,8 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
   if (WAVE) {
     bool ok = true;
     int spins = 0;
+    // (measured: relaxed polls + one acquire fence instead of ld.acquire polls do not help here — 4.07 -> 4.46 ms — because
+    // only a few lanes per warp poll; the grouped wavefront below, where every lane has flags of its own, needs them)
     if (lane == 0)
       while (ld_acquire(d.progress + r) < c) {
         if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
@@ -697,6 +710,216 @@ __global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n
     const int w_nn = load_record(t_nn, dg_nn);
     t_cur = t_nxt; w_cur = w_nxt; dg_cur = dg_nxt;
     t_nxt = t_nn; w_nxt = w_nn; dg_nxt = dg_nn;
+  }
+}
+
+// ---- grouped wavefront ---------------------------------------------------------------------------------------------------
+// The warp-per-task wavefront above spends ≈2000 warp instructions on one (reach, chunk) — 32 + S systolic ticks for S
+// segments — and needs 4 blocks of 128 threads per SM to keep enough tasks in flight; those blocks take registers and
+// issue slots from the runoff generation of the next window, which shares the GPU with the routing (ncu/bench: the
+// zone kernel runs 4.0 ms alone, 5.7 ms beside the wavefront).  Here a task is (GROUP OF 32 REACHES of one level, chunk):
+// lanes over time build the 32 inflow rows into a shared-memory tile (coalesced row reads, like reach_chunk), then
+// lane = reach runs the Muskingum recurrences of its reach with the segment states in registers (like
+// reach_bulk_kernel), ≈140 warp instructions per (reach, chunk).  One small block per SM is enough.  Reaches the group
+// form does not cover (several inlet nodes, deploy modes, more than HB_GRP_SMAX segments, musk_mct) stay single-reach
+// units handled by reach_chunk.  Dependencies, ordering and therefore deadlock freedom are those of reach_wave_kernel:
+// tasks are drawn in anti-diagonal order and only wait for tasks drawn earlier.
+#define HB_GRP_SMAX 24
+#define HB_GRP_EMAX 4       // entries of the inlet node of a group reach (land element + upstream reaches)
+#define HB_GRP_WARPS 2
+#define HB_GRP_SMEM (HB_GRP_WARPS * 32 * 33 * 8)
+
+#ifdef HB_GRP_DEBUG
+__device__ unsigned long long hb_grp_dbg[8];
+#define HB_DBG_T(k) do { if (lane == 0) { const long long now_ = clock64(); atomicAdd(&hb_grp_dbg[k], (unsigned long long)(now_ - t_dbg)); t_dbg = now_; } } while (0)
+#else
+#define HB_DBG_T(k) do { } while (0)
+#endif
+__device__ __forceinline__ bool reach_group_chunk(const RiverDev& d, int64_t r, int c, int lane, double* __restrict__ X) {
+  const unsigned full = 0xffffffffu;
+  const int64_t nt = d.nt;
+  const int64_t ta = (int64_t)c * HB_RIVER_CHUNK;
+  const int len = (int)((ta + HB_RIVER_CHUNK < nt ? ta + HB_RIVER_CHUNK : nt) - ta);
+  const double* dis_old = d.dis[(d.par0 + c) & 1];
+  double* dis_new = d.dis[(d.par0 + c + 1) & 1];
+  ReachMeta m;
+  m.c0 = m.c1 = m.c2 = 0.0; m.g0 = 0; m.nseg = 0; m.level = 0; m.dep0 = 0; m.n_dep = 0; m.simple_node = -1; m.entry0 = 0;
+  m.n_entry = 0; m.owns_node = 0; m.pad = 0;
+#ifdef HB_GRP_DEBUG
+  long long t_dbg = clock64();
+#endif
+  if (r >= 0) m = d.meta[r];
+  const int S = m.nseg;
+  const int64_t g0 = m.g0;
+  HB_DBG_T(0);
+  // The previous chunk of the own reach and the same chunk of every feeding reach.  The warp polls CONVERGED: one
+  // warp-wide relaxed load per flag slot and round, one acquire fence at the end.  (Lane-private ld.acquire loops — 32
+  // divergent spin loops per warp, each with its L1 invalidation — flooded the load/store path of the SM: the loads and
+  // stores of the working warps took 20x longer.)
+  const int* dep_flag[HB_GRP_EMAX];
+#pragma unroll
+  for (int p = 0; p < HB_GRP_EMAX; ++p)
+    dep_flag[p] = (r >= 0 && p < m.n_dep) ? d.progress + __ldg(d.dep_reach + m.dep0 + p) : nullptr;
+  {
+    int spins = 0;
+    for (;;) {
+      bool ready = true;
+      if (r >= 0) ready = ld_relaxed(d.progress + r) >= c;
+#pragma unroll
+      for (int p = 0; p < HB_GRP_EMAX; ++p)
+        if (dep_flag[p] != nullptr) ready = ready && (ld_relaxed(dep_flag[p]) >= c + 1);
+      if (__all_sync(full, ready)) break;
+      if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+      if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_relaxed(d.error) != 0)) return false;   // warp-uniform
+    }
+    __threadfence();   // acquire side of the flags' release stores
+  }
+  HB_DBG_T(1);
+  double q[HB_GRP_SMAX + 1];                          // discharge at the segment points (static indexing only)
+#pragma unroll
+  for (int i = 0; i <= HB_GRP_SMAX; ++i) q[i] = (r >= 0 && i <= S) ? __ldcg(dis_old + g0 + i) : 0.0;
+  int smax = S;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(full, smax, o); smax = v > smax ? v : smax; }
+  // ---- inflow tile: row j = reach of lane j, lanes over time (ref: threadingtools.py:396-415, musk_model.py:26-31) ----
+  // Every lane first resolves the (at most HB_GRP_EMAX) entry rows of ITS reach — one round trip for the whole group —
+  // then the rows are read in batches of 8 reaches x HB_GRP_EMAX entries with all loads in flight at once: the phase costs
+  // a handful of L2 round trips instead of one per (reach, entry).
+  // (slots beyond the entry list point to a row of zeros, so that every load below is unconditional)
+  const double* erow[HB_GRP_EMAX];
+  const int lane_c = lane < len ? lane : len - 1;
+#pragma unroll
+  for (int e = 0; e < HB_GRP_EMAX; ++e) {
+    erow[e] = d.zero_row;
+    if (r >= 0 && e < m.n_entry) {
+      const int32_t s = __ldg(d.entry_src + m.entry0 + e);
+      erow[e] = (s >= 0 ? d.land_rows + (int64_t)s * nt
+                        : s > HB_ENTRY_EXT ? d.reach_out + (int64_t)(-1 - s) * nt : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * nt) + ta;
+    }
+  }
+  HB_DBG_T(2);
+  for (int jb = 0; jb < 32; jb += 8) {
+    double v[8][HB_GRP_EMAX];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int e = 0; e < HB_GRP_EMAX; ++e) {
+        const double* row = (const double*)__shfl_sync(full, (unsigned long long)erow[e], jb + jj);
+        v[jj][e] = __ldcg(row + lane_c);                 // through L2: rows of other SMs' reaches
+      }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = jb + jj;
+      const int64_t rj = __shfl_sync(full, r, j);
+      const int nodej = __shfl_sync(full, m.simple_node, j), ownsj = __shfl_sync(full, m.owns_node, j);
+      const int Sj = __shfl_sync(full, S, j);
+      const int64_t g0j = __shfl_sync(full, g0, j);
+      // 0.0 + entries in the listed order; slots beyond the entry list hold +0.0, and x + 0.0 == x for every x this sum
+      // can take (it starts at +0.0, so it never is -0.0) — unconditional adds keep the loads above in one batch (a
+      // guarded add lets the compiler sink each load to its use, one L2 round trip after the other: 139k cycles per task)
+      double sim = 0.0;
+#pragma unroll
+      for (int e = 0; e < HB_GRP_EMAX; ++e) sim += v[jj][e];
+      if (rj >= 0 && lane < len) {
+        const int64_t t = ta + lane;
+        if (ownsj) d.node_rows[(int64_t)nodej * nt + t] = sim;
+        const double inflow = 0.0 + (0.0 + sim);
+        d.reach_in[rj * nt + t] = inflow;
+        if (Sj == 0) d.reach_out[rj * nt + t] = inflow;
+        if (d.dis_series) d.dis_series[t * d.n_seg + g0j] = inflow;
+        X[j * 33 + lane] = inflow;
+      }
+    }
+  }
+  __syncwarp();
+  HB_DBG_T(3);
+  // ---- lane = reach: the recurrences of the chunk (ref: musk_model.py:178-187 Calc_Discharge_V1) ----------------------
+  if (r >= 0) {
+    const double c0 = m.c0, c1 = m.c1, c2 = m.c2;
+    for (int tt = 0; tt < len; ++tt) {
+      double in = X[lane * 33 + tt];
+      double q_old = q[0];
+      q[0] = in;
+#pragma unroll
+      for (int i = 0; i < HB_GRP_SMAX; ++i) {
+        if (i >= smax) break;                         // warp-uniform
+        if (i < S) {
+          const double q_next = q[i + 1];
+          const double nv = c0 * in + c1 * q_old + c2 * q_next;   // (c0*new[i] + c1*old[i]) + c2*old[i+1]
+          q[i + 1] = nv;
+          q_old = q_next;
+          in = nv;
+          if (d.dis_series) d.dis_series[(ta + tt) * d.n_seg + g0 + i + 1] = nv;
+        }
+      }
+      X[lane * 33 + tt] = in;
+    }
+  }
+  __syncwarp();
+  HB_DBG_T(4);
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+    const int64_t rj = __shfl_sync(full, r, j);
+    const int Sj = __shfl_sync(full, S, j);
+    if (rj >= 0 && Sj > 0 && lane < len) d.reach_out[rj * nt + ta + lane] = X[j * 33 + lane];
+  }
+#pragma unroll
+  for (int i = 0; i <= HB_GRP_SMAX; ++i)
+    if (r >= 0 && i <= S) dis_new[g0 + i] = q[i];
+  // bar.warp.sync orders every lane's stores (rows are written lanes-over-time) before the releases below
+  __syncwarp();
+  HB_DBG_T(5);
+  if (r >= 0) st_release(d.progress + r, c + 1);
+  HB_DBG_T(6);
+#ifdef HB_GRP_DEBUG
+  if (lane == 0) atomicAdd(&hb_grp_dbg[7], 1ull);
+#endif
+  return true;
+}
+
+template <bool MCT>
+__global__ void __launch_bounds__(32 * HB_GRP_WARPS) reach_wave2_kernel(const RiverDev d, int n_tasks) {
+  extern __shared__ double grp_smem[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* X = grp_smem + (size_t)wib * (32 * 33);
+  const int32_t* diag_start = d.diag_start;
+  const int32_t* lvl_ptr = d.unit_lvl_ptr;
+  auto draw = [&]() -> int {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(d.counter, 1);
+    return __shfl_sync(full, t, 0);
+  };
+  int t_cur = draw();
+  while (t_cur < n_tasks) {
+    const int t_nxt = draw();                           // in flight while the current task runs
+    // task index → (anti-diagonal, unit)
+    int lo = 0, hi = d.n_diag;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(diag_start + mid) <= t_cur) lo = mid; else hi = mid;
+    }
+    const int dg = lo;
+    const int l_lo = dg - d.n_chunks + 1 > 0 ? dg - d.n_chunks + 1 : 0;
+    const int unit = __ldg(lvl_ptr + l_lo) + (t_cur - __ldg(diag_start + dg));
+    const int info = __ldg(d.unit_info + unit);
+    const int us = __ldg(d.unit_start + unit), cnt = __ldg(d.unit_start + unit + 1) - us;
+    const int c = dg - (info & 0x3fffffff);
+    bool ok;
+    if (info >> 30) {
+      const int64_t r = lane < cnt ? (int64_t)__ldg(d.unit_reach + us + lane) : -1;
+      ok = reach_group_chunk(d, r, c, lane, X);
+    } else {
+      const int64_t r = __ldg(d.unit_reach + us);
+      ok = reach_chunk<true, MCT>(d, prep_from_meta(d, r, lane), c, lane, false, false);
+      __syncwarp();
+      if (ok && lane == 0) st_release(d.progress + r, c + 1);
+    }
+    if (!ok) {
+      if (lane == 0) atomicExch(d.error, 1);
+      return;
+    }
+    t_cur = t_nxt;
   }
 }
 

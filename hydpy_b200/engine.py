@@ -281,8 +281,10 @@ class Engine:
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_PATH, value), "hb_set_option")
 
     def set_river_sweep(self, mode: str = "persistent") -> None:
-        """'persistent': one persistent wavefront launch (default); 'launches': one launch per anti-diagonal."""
-        value = {"persistent": layout.RIVER_PERSISTENT, "launches": layout.RIVER_LAUNCHES}[mode]
+        """'persistent': one persistent wavefront launch, a warp per (reach, chunk); 'grouped': persistent wavefront with
+        (32 reaches, chunk) tasks, lane = reach; 'launches': one launch per anti-diagonal."""
+        value = {"persistent": layout.RIVER_PERSISTENT, "launches": layout.RIVER_LAUNCHES,
+                 "grouped": layout.RIVER_GROUPED}[mode]
         self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_SWEEP, value), "hb_set_option")
 
     def set_wave_blocks(self, blocks_per_sm: int) -> None:

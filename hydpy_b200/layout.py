@@ -94,7 +94,7 @@ OPT_LAND_PATH = 0
 OPT_RIVER_SWEEP = 1
 OPT_RIVER_STATE_SERIES = 2
 OPT_RIVER_WAVE_BLOCKS = 3
-RIVER_PERSISTENT, RIVER_LAUNCHES = 0, 1
+RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2
 LAND_AUTO, LAND_GENERAL = 0, 1
 ROW_NODE, ROW_REACH = 0, 1
 ENTRY_EXT = -(1 << 30)

@@ -296,6 +296,10 @@ int hb_select_series(hb_engine* h, int series, int on);
 #define HB_OPT_RIVER_SWEEP 1
 #define HB_RIVER_PERSISTENT 0
 #define HB_RIVER_LAUNCHES 1
+/* HB_RIVER_GROUPED: persistent wavefront whose tasks are (group of 32 reaches of one level, chunk): lanes over time build
+ * the inflow rows, then lane = reach runs the recurrences — a tenth of the instructions of the warp-per-reach wavefront
+ * and one small block per SM, so that the routing of window w takes little from the runoff generation of window w+1. */
+#define HB_RIVER_GROUPED 2
 /* HB_OPT_RIVER_STATE_SERIES (0/1): record musk_classic `states.discharge` of every step for hb_get_reach_state_series
  * (the `ramflag` of that sequence, `hydpy/models/musk/musk_states.py`). */
 #define HB_OPT_RIVER_STATE_SERIES 2

@@ -58,7 +58,7 @@ def test_enums_match_layout():
                          ("HB_ROW_NODE", layout.ROW_NODE), ("HB_ROW_REACH", layout.ROW_REACH),
                          ("HB_OPT_LAND_PATH", layout.OPT_LAND_PATH), ("HB_OPT_RIVER_SWEEP", layout.OPT_RIVER_SWEEP), ("HB_OPT_RIVER_STATE_SERIES", layout.OPT_RIVER_STATE_SERIES),
                          ("HB_OPT_RIVER_WAVE_BLOCKS", layout.OPT_RIVER_WAVE_BLOCKS),
-                         ("HB_RIVER_PERSISTENT", layout.RIVER_PERSISTENT), ("HB_RIVER_LAUNCHES", layout.RIVER_LAUNCHES), ("HB_LAND_AUTO", layout.LAND_AUTO),
+                         ("HB_RIVER_PERSISTENT", layout.RIVER_PERSISTENT), ("HB_RIVER_LAUNCHES", layout.RIVER_LAUNCHES), ("HB_RIVER_GROUPED", layout.RIVER_GROUPED), ("HB_LAND_AUTO", layout.LAND_AUTO),
                          ("HB_LAND_GENERAL", layout.LAND_GENERAL), ("HB_NCCL_ID_BYTES", layout.NCCL_ID_BYTES),
                          ("HB_ENTRY_EXT", layout.ENTRY_EXT)):
         assert define(cname) == value, cname

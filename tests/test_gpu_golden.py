@@ -25,13 +25,13 @@ LAHN_H = load_scenarios("lahn_hourly_members.npz")
 EXACT_SERIES = ("tc", "fracrain", "cfact", "gact", "pc")
 
 
-@pytest.fixture(scope="module", params=["auto", "general"])
+@pytest.fixture(scope="module", params=["auto", "general", "grouped"])
 def engine(request):
     """Both land paths ('auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only) and
     both routing sweeps ('auto': headwater kernels + persistent wavefront, 'general': one launch per anti-diagonal)."""
     with Engine(0) as eng:
-        eng.set_land_path(request.param)
-        eng.set_river_sweep("launches" if request.param == "general" else "persistent")
+        eng.set_land_path("auto" if request.param == "grouped" else request.param)
+        eng.set_river_sweep({"auto": "persistent", "general": "launches", "grouped": "grouped"}[request.param])
         eng.path = request.param
         yield eng
 

@@ -11,13 +11,14 @@ from tests.util import assert_close
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["auto", "general"])
+@pytest.fixture(scope="module", params=["auto", "general", "grouped"])
 def engine(request):
-    """Both land paths ('auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only) and
-    both routing sweeps ('auto': headwater kernels + persistent wavefront, 'general': one launch per anti-diagonal)."""
+    """Both land paths ('auto' = two-kernel fast path for the eligible elements, 'general' = general kernel only) and the
+    three routing sweeps ('auto': headwater kernels + persistent warp-per-reach wavefront, 'general': one launch per
+    anti-diagonal, 'grouped': fast land path + persistent wavefront with (32 reaches, chunk) tasks)."""
     with Engine(0) as eng:
-        eng.set_land_path(request.param)
-        eng.set_river_sweep("launches" if request.param == "general" else "persistent")
+        eng.set_land_path("auto" if request.param == "grouped" else request.param)
+        eng.set_river_sweep({"auto": "persistent", "general": "launches", "grouped": "grouped"}[request.param])
         yield eng
 
 
@@ -357,7 +358,7 @@ def test_full_size_routing_sweeps_agree_bit_for_bit():
     no_ext = np.zeros((0, win))
     results = {}
     with Engine(0) as eng:
-        for sweep, path in (("launches", "auto"), ("persistent", "auto"), ("persistent", "general")):
+        for sweep, path in (("launches", "auto"), ("persistent", "auto"), ("persistent", "general"), ("grouped", "auto")):
             eng.set_land_path(path)
             eng.set_river_sweep(sweep)
             eng.set_land(land); eng.set_land_states(states); eng.set_river(river); eng.set_river_states(discharge)
@@ -372,6 +373,8 @@ def test_full_size_routing_sweeps_agree_bit_for_bit():
             for b in bufs:
                 b.free()
     a, b, c = results[("launches", "auto")], results[("persistent", "auto")], results[("persistent", "general")]
+    g = results[("grouped", "auto")]
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1]), "grouped wavefront differs from the diagonal sweep"
     assert np.isfinite(a[0]).all() and a[0][0].max() > 0.0
     assert_close(b[0], c[0], "full size: fast vs general land path, node series")

@@ -20,6 +20,7 @@ ap.add_argument("--levels", type=int, default=200)
 ap.add_argument("--series", default="", help="comma-separated land series to record ('all' = every hland_96 sequence)")
 ap.add_argument("--path", default="auto")
 ap.add_argument("--cflux", type=float, default=0.0)
+ap.add_argument("--sweep", default="", help="routing sweep: persistent | grouped | launches")
 ap.add_argument("--model", default="hland_96", choices=("hland_96", "hland_96p", "hland_96c"))
 args = ap.parse_args()
 
@@ -35,6 +36,8 @@ from hydpy_b200 import layout
 series = list(layout.SERIES_96) if args.series == "all" else [x for x in args.series.split(",") if x]
 eng.select_series(series)
 eng.set_land_path(args.path)
+if args.sweep:
+    eng.set_river_sweep(args.sweep)
 nbytes = 8 * args.nt * sum(land.n_zone if x in layout.SERIES_ZONE else land.n_snow if x in layout.SERIES_SNOW else land.n_elem for x in series)
 print(f"uploaded in {time.time()-t:.2f}s")
 for rep in range(args.reps):
