@@ -190,6 +190,8 @@ def build_shard(args: argparse.Namespace, rank: int, world: int):
             river.seg_ptr = np.append(river.seg_ptr, river.seg_ptr[-1] + nseg + 1)
             river.coef = np.concatenate([river.coef, np.array([[c0], [1 - 2 * c0], [c0]])], axis=1)
             discharge = np.concatenate([discharge, np.zeros(nseg + 1)])
+        # (the per-reach arrays of the musk_mct extension are regenerated for the changed reach count: all musk_classic)
+        river.reach_model = river.nmbruns = river.rpar = river.trap_ptr = river.tpar = None
         river.normalise()
     return land, states, river, discharge
 

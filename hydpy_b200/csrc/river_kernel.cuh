@@ -627,8 +627,11 @@ __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restric
 // for task i+1 are in flight while task i runs.  A warp therefore owns up to three tasks, always processed in
 // increasing order, which keeps the no-deadlock argument intact (the smallest unfinished task is always some warp's
 // current task or becomes it as soon as that warp's smaller tasks — already finished — are retired).
+#ifndef HB_WAVE_MIN_BLOCKS
+#define HB_WAVE_MIN_BLOCKS 1
+#endif
 template <bool MCT>
-__global__ void __launch_bounds__(128) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
+__global__ void __launch_bounds__(128, HB_WAVE_MIN_BLOCKS) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
   extern __shared__ int32_t wave_tab[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;

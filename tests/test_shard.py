@@ -196,3 +196,24 @@ def test_partition_with_musk_mct_reaches():
     rout[s0.reaches], rout[s1.reaches] = outs[0][1], outs[1][1]
     assert np.array_equal(nodes, ref_nodes, equal_nan=True) and np.array_equal(rout, ref_rout, equal_nan=True)
     assert np.array_equal(got_mct, m, equal_nan=True)
+
+
+@pytest.mark.parametrize("rank", [0, 1, 3])
+def test_bench_shards_are_consistent_bundles(rank):
+    """bench.py's per-rank sub-basins (N > 1: an extra boundary reach or extra external entries) must stay valid bundles —
+    the C structs are built from them on every rank."""
+    import argparse
+
+    import bench
+
+    args = argparse.Namespace(elements=300, levels=12)
+    land, states, river, discharge = bench.build_shard(args, rank, 4)
+    land.as_struct()
+    states.as_struct()
+    d = river.as_struct()
+    assert d.n_reach == river.n_reach and len(discharge) == river.n_seg
+    assert len(river.reach_model) == river.n_reach and river.rpar.shape[1] == river.n_reach
+    if rank == 0:
+        assert river.n_ext == 3
+    else:
+        assert river.n_reach == 300 and river.reach_outlet[-1] == -1
