@@ -1496,6 +1496,7 @@ static int run_river(hb_engine* h) {
   d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
   d.progress = h->d_progress.p; d.counter = h->d_wave_ctl.p; d.error = h->d_wave_ctl.p + 1;
+  d.pscale = h->river_sweep == HB_RIVER_GROUPED ? HB_GRP_NSUB : 1;
   d.unit_start = h->d_unit_start.p; d.unit_reach = h->d_unit_reach.p; d.unit_info = h->d_unit_info.p;
   d.unit_lvl_ptr = h->d_unit_lvl_ptr.p; d.zero_row = h->d_zero_row.p;
   d.nmbruns = h->d_nmbruns.p; d.rpar = h->d_rpar.p; d.trap_ptr = h->d_trap_ptr.p; d.tpar = h->d_tpar.p; d.n_trap = h->n_trap;
@@ -1538,18 +1539,22 @@ static int run_river(hb_engine* h) {
       d.diag_start = h->d_diag_start.p;
       if (h->river_sweep == HB_RIVER_GROUPED) {
         if (h->diag_chunks_g != n_chunks) {
-          std::vector<int32_t> ds(d.n_diag + 1, 0);
-          for (int dg = 0; dg < d.n_diag; ++dg) {
-            const int l_lo = dg - n_chunks + 1 > 0 ? dg - n_chunks + 1 : 0;
-            const int l_hi = dg < nlev - 1 ? dg : nlev - 1;
-            ds[dg + 1] = ds[dg] + (h->unit_lvl_ptr[l_hi + 1] - h->unit_lvl_ptr[l_lo]);
-          }
+          // task list of the grouped wavefront, ordered by level + HB_GRP_NSUB * chunk (see reach_wave2_kernel)
+          HB_REQUIRE(h, h->n_units < (1 << 24) && n_chunks < 128, HB_EINVAL,
+                     "hb_run: the grouped routing sweep packs (unit, chunk) into 32 bits; use shorter windows");
+          std::vector<std::vector<int32_t>> by_key((size_t)nlev + (size_t)HB_GRP_NSUB * n_chunks);
+          for (int l = 0; l < nlev; ++l)
+            for (int32_t u = h->unit_lvl_ptr[l]; u < h->unit_lvl_ptr[l + 1]; ++u)
+              for (int c = 0; c < n_chunks; ++c) by_key[(size_t)l + (size_t)HB_GRP_NSUB * c].push_back(u | (c << 24));
+          std::vector<int32_t> tasks;
+          tasks.reserve((size_t)h->n_units * n_chunks);
+          for (const auto& v : by_key) tasks.insert(tasks.end(), v.begin(), v.end());
           HB_CUDA(h, cudaStreamSynchronize(h->s_river));
-          HB_CUDA(h, h->d_diag_start_g.reserve(ds.size()));
-          HB_CUDA(h, cudaMemcpy(h->d_diag_start_g.p, ds.data(), ds.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+          HB_CUDA(h, h->d_diag_start_g.reserve(tasks.size()));
+          HB_CUDA(h, cudaMemcpy(h->d_diag_start_g.p, tasks.data(), tasks.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
           h->diag_chunks_g = n_chunks;
         }
-        d.diag_start = h->d_diag_start_g.p;
+        d.task_list = h->d_diag_start_g.p;
       }
       wave_init_kernel<<<(unsigned)((h->n_reach + 255) / 256), 256, 0, h->s_river>>>(d);
       ++launches;

@@ -84,13 +84,15 @@ struct RiverDev {
   const int32_t* dep_reach;
   int n_levels, n_diag;
   int* counter;                // task queue head
-  int* progress;               // [n_reach] chunks completed in this run
+  int* progress;               // [n_reach] chunks completed in this run, times pscale
+  int pscale;                  // 1; grouped wavefront: HB_GRP_NSUB (its groups publish every sub-chunk of HB_GRP_SUB steps)
   int* error;                  // set when a wait ran into the spin limit
   // grouped wavefront (reach_wave2_kernel): units = groups of up to 32 simple reaches of one level, or single reaches
   const int32_t* unit_start;   // [n_units+1] into unit_reach
   const int32_t* unit_reach;   // member reaches, unit after unit
   const int32_t* unit_info;    // [n_units] level | (group ? 1 << 30 : 0)
   const int32_t* unit_lvl_ptr; // [n_levels+1] into the units (sorted by level)
+  const int32_t* task_list;    // [n_units * n_chunks] unit | chunk << 24, in wavefront order
   const double* zero_row;      // 32 zeros
   // musk_mct reaches
   const int32_t* nmbruns;      // [n_reach]
@@ -387,7 +389,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     // (measured: relaxed polls + one acquire fence instead of ld.acquire polls do not help here — 4.07 -> 4.46 ms — because
     // only a few lanes per warp poll; the grouped wavefront below, where every lane has flags of its own, needs them)
     if (lane == 0)
-      while (ld_acquire(d.progress + r) < c) {
+      while (ld_acquire(d.progress + r) < c * d.pscale) {
         if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
         if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
       }
@@ -400,7 +402,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     for (int p = lane; p < m.n_dep; p += 32) {
       const int* flag = d.progress + (tp.inline_deps ? tp.dep : d.dep_reach[m.dep0 + p]);
       spins = 0;
-      while (ld_acquire(flag) < c + 1) {
+      while (ld_acquire(flag) < (c + 1) * d.pscale) {
         if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
         if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
       }
@@ -618,7 +620,7 @@ __global__ void wave_init_kernel(const RiverDev d) {
 }
 __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restrict__ head, int n_head) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_head) d.progress[head[i]] = d.n_chunks;
+  if (i < n_head) d.progress[head[i]] = d.n_chunks * d.pscale;
 }
 
 // dynamic shared memory: copies of diag_start [n_diag+1] and wave_lvl_ptr [n_levels+1] when they fit (use_smem).
@@ -729,8 +731,13 @@ __global__ void __launch_bounds__(128, HB_WAVE_MIN_BLOCKS) reach_wave_kernel(con
 // tasks are drawn in anti-diagonal order and only wait for tasks drawn earlier.
 #define HB_GRP_SMAX 24
 #define HB_GRP_EMAX 4       // entries of the inlet node of a group reach (land element + upstream reaches)
+#define HB_GRP_SUB 8        // steps of a sub-chunk
+#define HB_GRP_NSUB (HB_RIVER_CHUNK / HB_GRP_SUB)
 #define HB_GRP_WARPS 2
-#define HB_GRP_SMEM (HB_GRP_WARPS * 32 * 33 * 8)
+#ifndef HB_GRP_MIN_BLOCKS
+#define HB_GRP_MIN_BLOCKS 6   // caps the kernel at 168 registers
+#endif
+#define HB_GRP_SMEM (HB_GRP_WARPS * 32 * (HB_GRP_SUB + 1) * 8)
 
 #ifdef HB_GRP_DEBUG
 __device__ unsigned long long hb_grp_dbg[8];
@@ -738,6 +745,27 @@ __device__ unsigned long long hb_grp_dbg[8];
 #else
 #define HB_DBG_T(k) do { } while (0)
 #endif
+__device__ __forceinline__ bool poll_flags(const RiverDev& d, const int* const* flag, int n_slots, int need, bool active) {
+  // converged polling: one warp-wide relaxed load per flag slot and round, ONE acquire fence at the end
+  const unsigned full = 0xffffffffu;
+  int spins = 0;
+  for (;;) {
+    bool ready = true;
+    if (active)
+#pragma unroll
+      for (int p = 0; p < HB_GRP_EMAX; ++p)
+        if (p < n_slots && flag[p] != nullptr) ready = ready && (ld_relaxed(flag[p]) >= need);
+    if (__all_sync(full, ready)) break;
+    if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+    if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_relaxed(d.error) != 0)) return false;   // warp-uniform
+  }
+  __threadfence();   // acquire side of the flags' release stores
+  return true;
+}
+
+// One (group, 32-step chunk) task.  The chunk runs as HB_GRP_NSUB sub-chunks of HB_GRP_SUB steps, each of which waits only
+// for the same sub-chunk of the feeding reaches and publishes itself: consecutive levels of the network overlap inside a
+// chunk, so the latency per level is that of a sub-chunk.  progress[r] counts sub-chunks (d.pscale = HB_GRP_NSUB).
 __device__ __forceinline__ bool reach_group_chunk(const RiverDev& d, int64_t r, int c, int lane, double* __restrict__ X) {
   const unsigned full = 0xffffffffu;
   const int64_t nt = d.nt;
@@ -755,28 +783,22 @@ __device__ __forceinline__ bool reach_group_chunk(const RiverDev& d, int64_t r, 
   const int S = m.nseg;
   const int64_t g0 = m.g0;
   HB_DBG_T(0);
-  // The previous chunk of the own reach and the same chunk of every feeding reach.  The warp polls CONVERGED: one
-  // warp-wide relaxed load per flag slot and round, one acquire fence at the end.  (Lane-private ld.acquire loops — 32
-  // divergent spin loops per warp, each with its L1 invalidation — flooded the load/store path of the SM: the loads and
-  // stores of the working warps took 20x longer.)
+  // flags: the own reach (previous chunk) and the feeding reaches; entry rows (slots beyond the entry list point to a
+  // row of zeros, so that every load below is unconditional)
+  const int* own_flag[HB_GRP_EMAX] = {r >= 0 ? d.progress + r : nullptr, nullptr, nullptr, nullptr};
   const int* dep_flag[HB_GRP_EMAX];
+  const double* erow[HB_GRP_EMAX];
 #pragma unroll
-  for (int p = 0; p < HB_GRP_EMAX; ++p)
+  for (int p = 0; p < HB_GRP_EMAX; ++p) {
     dep_flag[p] = (r >= 0 && p < m.n_dep) ? d.progress + __ldg(d.dep_reach + m.dep0 + p) : nullptr;
-  {
-    int spins = 0;
-    for (;;) {
-      bool ready = true;
-      if (r >= 0) ready = ld_relaxed(d.progress + r) >= c;
-#pragma unroll
-      for (int p = 0; p < HB_GRP_EMAX; ++p)
-        if (dep_flag[p] != nullptr) ready = ready && (ld_relaxed(dep_flag[p]) >= c + 1);
-      if (__all_sync(full, ready)) break;
-      if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
-      if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_relaxed(d.error) != 0)) return false;   // warp-uniform
+    erow[p] = d.zero_row;
+    if (r >= 0 && p < m.n_entry) {
+      const int32_t s = __ldg(d.entry_src + m.entry0 + p);
+      erow[p] = (s >= 0 ? d.land_rows + (int64_t)s * nt
+                        : s > HB_ENTRY_EXT ? d.reach_out + (int64_t)(-1 - s) * nt : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * nt) + ta;
     }
-    __threadfence();   // acquire side of the flags' release stores
   }
+  if (!poll_flags(d, own_flag, 1, c * HB_GRP_NSUB, r >= 0)) return false;
   HB_DBG_T(1);
   double q[HB_GRP_SMAX + 1];                          // discharge at the segment points (static indexing only)
 #pragma unroll
@@ -784,96 +806,91 @@ __device__ __forceinline__ bool reach_group_chunk(const RiverDev& d, int64_t r, 
   int smax = S;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(full, smax, o); smax = v > smax ? v : smax; }
-  // ---- inflow tile: row j = reach of lane j, lanes over time (ref: threadingtools.py:396-415, musk_model.py:26-31) ----
-  // Every lane first resolves the (at most HB_GRP_EMAX) entry rows of ITS reach — one round trip for the whole group —
-  // then the rows are read in batches of 8 reaches x HB_GRP_EMAX entries with all loads in flight at once: the phase costs
-  // a handful of L2 round trips instead of one per (reach, entry).
-  // (slots beyond the entry list point to a row of zeros, so that every load below is unconditional)
-  const double* erow[HB_GRP_EMAX];
-  const int lane_c = lane < len ? lane : len - 1;
-#pragma unroll
-  for (int e = 0; e < HB_GRP_EMAX; ++e) {
-    erow[e] = d.zero_row;
-    if (r >= 0 && e < m.n_entry) {
-      const int32_t s = __ldg(d.entry_src + m.entry0 + e);
-      erow[e] = (s >= 0 ? d.land_rows + (int64_t)s * nt
-                        : s > HB_ENTRY_EXT ? d.reach_out + (int64_t)(-1 - s) * nt : d.ext_rows + (int64_t)(HB_ENTRY_EXT - s) * nt) + ta;
-    }
-  }
+  const double c0 = m.c0, c1 = m.c1, c2 = m.c2;
+  const int jr = lane >> 3, ts = lane & (HB_GRP_SUB - 1);   // inflow/row phases: lane = (reach within a batch of 4, step)
   HB_DBG_T(2);
-  for (int jb = 0; jb < 32; jb += 8) {
+  for (int sub = 0; sub < HB_GRP_NSUB; ++sub) {
+    const int slen = len - sub * HB_GRP_SUB < HB_GRP_SUB ? len - sub * HB_GRP_SUB : HB_GRP_SUB;
+    if (slen <= 0) break;                               // warp-uniform
+    const int64_t t0 = ta + sub * HB_GRP_SUB;
+    const bool last = (sub + 1) * HB_GRP_SUB >= len;
+    if (!poll_flags(d, dep_flag, HB_GRP_EMAX, c * HB_GRP_NSUB + sub + 1, r >= 0)) return false;
+    HB_DBG_T(1);
+    // ---- inflow tile: 8 batches of 4 reaches x 8 steps, all 32 row loads in flight ------------------------------------
+    // (ref: threadingtools.py:396-415 node series = 0.0 + entries in order; musk_model.py:26-31 Pick_Inflow_V1)
+    const int ts_c = ts < slen ? ts : slen - 1;
     double v[8][HB_GRP_EMAX];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
+    for (int jb = 0; jb < 8; ++jb)
 #pragma unroll
       for (int e = 0; e < HB_GRP_EMAX; ++e) {
-        const double* row = (const double*)__shfl_sync(full, (unsigned long long)erow[e], jb + jj);
-        v[jj][e] = __ldcg(row + lane_c);                 // through L2: rows of other SMs' reaches
+        const double* row = (const double*)__shfl_sync(full, (unsigned long long)erow[e], jb * 4 + jr);
+        v[jb][e] = __ldcg(row + sub * HB_GRP_SUB + ts_c);   // through L2: rows of other SMs' reaches
       }
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = jb + jj;
+    for (int jb = 0; jb < 8; ++jb) {
+      const int j = jb * 4 + jr;
       const int64_t rj = __shfl_sync(full, r, j);
       const int nodej = __shfl_sync(full, m.simple_node, j), ownsj = __shfl_sync(full, m.owns_node, j);
       const int Sj = __shfl_sync(full, S, j);
       const int64_t g0j = __shfl_sync(full, g0, j);
-      // 0.0 + entries in the listed order; slots beyond the entry list hold +0.0, and x + 0.0 == x for every x this sum
-      // can take (it starts at +0.0, so it never is -0.0) — unconditional adds keep the loads above in one batch (a
-      // guarded add lets the compiler sink each load to its use, one L2 round trip after the other: 139k cycles per task)
+      // slots beyond the entry list hold +0.0, and x + 0.0 == x for every x this sum can take (it starts at +0.0)
       double sim = 0.0;
 #pragma unroll
-      for (int e = 0; e < HB_GRP_EMAX; ++e) sim += v[jj][e];
-      if (rj >= 0 && lane < len) {
-        const int64_t t = ta + lane;
+      for (int e = 0; e < HB_GRP_EMAX; ++e) sim += v[jb][e];
+      if (rj >= 0 && ts < slen) {
+        const int64_t t = t0 + ts;
         if (ownsj) d.node_rows[(int64_t)nodej * nt + t] = sim;
         const double inflow = 0.0 + (0.0 + sim);
         d.reach_in[rj * nt + t] = inflow;
         if (Sj == 0) d.reach_out[rj * nt + t] = inflow;
         if (d.dis_series) d.dis_series[t * d.n_seg + g0j] = inflow;
-        X[j * 33 + lane] = inflow;
+        X[j * (HB_GRP_SUB + 1) + ts] = inflow;
       }
     }
-  }
-  __syncwarp();
-  HB_DBG_T(3);
-  // ---- lane = reach: the recurrences of the chunk (ref: musk_model.py:178-187 Calc_Discharge_V1) ----------------------
-  if (r >= 0) {
-    const double c0 = m.c0, c1 = m.c1, c2 = m.c2;
-    for (int tt = 0; tt < len; ++tt) {
-      double in = X[lane * 33 + tt];
-      double q_old = q[0];
-      q[0] = in;
+    __syncwarp();
+    HB_DBG_T(3);
+    // ---- lane = reach: the recurrences of the sub-chunk (ref: musk_model.py:178-187 Calc_Discharge_V1) -----------------
+    if (r >= 0) {
+      for (int tt = 0; tt < slen; ++tt) {
+        double in = X[lane * (HB_GRP_SUB + 1) + tt];
+        double q_old = q[0];
+        q[0] = in;
 #pragma unroll
-      for (int i = 0; i < HB_GRP_SMAX; ++i) {
-        if (i >= smax) break;                         // warp-uniform
-        if (i < S) {
-          const double q_next = q[i + 1];
-          const double nv = c0 * in + c1 * q_old + c2 * q_next;   // (c0*new[i] + c1*old[i]) + c2*old[i+1]
-          q[i + 1] = nv;
-          q_old = q_next;
-          in = nv;
-          if (d.dis_series) d.dis_series[(ta + tt) * d.n_seg + g0 + i + 1] = nv;
+        for (int i = 0; i < HB_GRP_SMAX; ++i) {
+          if (i >= smax) break;                         // warp-uniform
+          if (i < S) {
+            const double q_next = q[i + 1];
+            const double nv = c0 * in + c1 * q_old + c2 * q_next;   // (c0*new[i] + c1*old[i]) + c2*old[i+1]
+            q[i + 1] = nv;
+            q_old = q_next;
+            in = nv;
+            if (d.dis_series) d.dis_series[(t0 + tt) * d.n_seg + g0 + i + 1] = nv;
+          }
         }
+        X[lane * (HB_GRP_SUB + 1) + tt] = in;
       }
-      X[lane * 33 + tt] = in;
     }
-  }
-  __syncwarp();
-  HB_DBG_T(4);
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int64_t rj = __shfl_sync(full, r, j);
-    const int Sj = __shfl_sync(full, S, j);
-    if (rj >= 0 && Sj > 0 && lane < len) d.reach_out[rj * nt + ta + lane] = X[j * 33 + lane];
-  }
+    __syncwarp();
+    HB_DBG_T(4);
 #pragma unroll
-  for (int i = 0; i <= HB_GRP_SMAX; ++i)
-    if (r >= 0 && i <= S) dis_new[g0 + i] = q[i];
-  // bar.warp.sync orders every lane's stores (rows are written lanes-over-time) before the releases below
-  __syncwarp();
-  HB_DBG_T(5);
-  if (r >= 0) st_release(d.progress + r, c + 1);
-  HB_DBG_T(6);
+    for (int jb = 0; jb < 8; ++jb) {
+      const int j = jb * 4 + jr;
+      const int64_t rj = __shfl_sync(full, r, j);
+      const int Sj = __shfl_sync(full, S, j);
+      if (rj >= 0 && Sj > 0 && ts < slen) d.reach_out[rj * nt + t0 + ts] = X[j * (HB_GRP_SUB + 1) + ts];
+    }
+    if (last) {
+#pragma unroll
+      for (int i = 0; i <= HB_GRP_SMAX; ++i)
+        if (r >= 0 && i <= S) dis_new[g0 + i] = q[i];
+    }
+    // bar.warp.sync orders every lane's stores (rows are written lanes-over-time) before the releases below
+    __syncwarp();
+    HB_DBG_T(5);
+    if (r >= 0) st_release(d.progress + r, last ? (c + 1) * HB_GRP_NSUB : c * HB_GRP_NSUB + sub + 1);
+    HB_DBG_T(6);
+  }
 #ifdef HB_GRP_DEBUG
   if (lane == 0) atomicAdd(&hb_grp_dbg[7], 1ull);
 #endif
@@ -881,13 +898,11 @@ __device__ __forceinline__ bool reach_group_chunk(const RiverDev& d, int64_t r, 
 }
 
 template <bool MCT>
-__global__ void __launch_bounds__(32 * HB_GRP_WARPS) reach_wave2_kernel(const RiverDev d, int n_tasks) {
+__global__ void __launch_bounds__(32 * HB_GRP_WARPS, HB_GRP_MIN_BLOCKS) reach_wave2_kernel(const RiverDev d, int n_tasks) {
   extern __shared__ double grp_smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* X = grp_smem + (size_t)wib * (32 * 33);
-  const int32_t* diag_start = d.diag_start;
-  const int32_t* lvl_ptr = d.unit_lvl_ptr;
+  double* X = grp_smem + (size_t)wib * (32 * (HB_GRP_SUB + 1));
   auto draw = [&]() -> int {
     int t = 0;
     if (lane == 0) t = atomicAdd(d.counter, 1);
@@ -896,18 +911,13 @@ __global__ void __launch_bounds__(32 * HB_GRP_WARPS) reach_wave2_kernel(const Ri
   int t_cur = draw();
   while (t_cur < n_tasks) {
     const int t_nxt = draw();                           // in flight while the current task runs
-    // task index → (anti-diagonal, unit)
-    int lo = 0, hi = d.n_diag;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(diag_start + mid) <= t_cur) lo = mid; else hi = mid;
-    }
-    const int dg = lo;
-    const int l_lo = dg - d.n_chunks + 1 > 0 ? dg - d.n_chunks + 1 : 0;
-    const int unit = __ldg(lvl_ptr + l_lo) + (t_cur - __ldg(diag_start + dg));
+    // task → (unit, chunk): the host lists the tasks in the order of the sub-chunk wavefront, level + HB_GRP_NSUB * chunk
+    // (a task waits for level - 1 of the same chunk and for the previous chunk of its own level: both earlier in this
+    // order), so that the tasks the warps hold are the ones that can run
+    const int packed = __ldg(d.task_list + t_cur);
+    const int unit = packed & 0xffffff, c = packed >> 24;
     const int info = __ldg(d.unit_info + unit);
     const int us = __ldg(d.unit_start + unit), cnt = __ldg(d.unit_start + unit + 1) - us;
-    const int c = dg - (info & 0x3fffffff);
     bool ok;
     if (info >> 30) {
       const int64_t r = lane < cnt ? (int64_t)__ldg(d.unit_reach + us + lane) : -1;
@@ -916,7 +926,7 @@ __global__ void __launch_bounds__(32 * HB_GRP_WARPS) reach_wave2_kernel(const Ri
       const int64_t r = __ldg(d.unit_reach + us);
       ok = reach_chunk<true, MCT>(d, prep_from_meta(d, r, lane), c, lane, false, false);
       __syncwarp();
-      if (ok && lane == 0) st_release(d.progress + r, c + 1);
+      if (ok && lane == 0) st_release(d.progress + r, (c + 1) * d.pscale);
     }
     if (!ok) {
       if (lane == 0) atomicExch(d.error, 1);
