@@ -629,11 +629,14 @@ __global__ void wave_head_done_kernel(const RiverDev d, const int32_t* __restric
 // for task i+1 are in flight while task i runs.  A warp therefore owns up to three tasks, always processed in
 // increasing order, which keeps the no-deadlock argument intact (the smallest unfinished task is always some warp's
 // current task or becomes it as soon as that warp's smaller tasks — already finished — are retired).
+// 9 blocks of 128 threads per SM cap the kernel at 56 registers (what it needs without spills): every register the
+// wavefront holds is taken from the runoff generation of the next window (at 76 registers the pipelined step lost 0.3 ms;
+// 48/40/32 registers make the routing itself slower than that gains)
 #ifndef HB_WAVE_MIN_BLOCKS
-#define HB_WAVE_MIN_BLOCKS 1
+#define HB_WAVE_MIN_BLOCKS 9
 #endif
 template <bool MCT>
-__global__ void __launch_bounds__(128, HB_WAVE_MIN_BLOCKS) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
+__global__ void __launch_bounds__(128, MCT ? 1 : HB_WAVE_MIN_BLOCKS) reach_wave_kernel(const RiverDev d, int n_tasks, int use_smem) {
   extern __shared__ int32_t wave_tab[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
