@@ -191,6 +191,22 @@ HB_HD double hb_exp(double t, TabRef T) {
 #endif
 }
 
+#ifdef __CUDACC__
+__device__ __noinline__ double hb_log_slow(double x) { return log(x); }
+#endif
+
+// log(x): table path for positive normal x, libm/libdevice for zero, subnormal, negative, inf and nan
+HB_HD double hb_log(double x, TabRef T) {
+  const bool ok_x = (unsigned)(hb_hi(x) - 0x00100000) < 0x7fe00000u;
+  const double r = hb_log_normal(x, T);
+  if (ok_x) return r;
+#ifdef __CUDA_ARCH__
+  return hb_log_slow(x);
+#else
+  return log(x);
+#endif
+}
+
 HB_HD double hb_pow(double x, double y, TabRef T) {
   // positive normal x: 0x00100000 <= hi < 0x7ff00000
   const bool ok_x = (unsigned)(hb_hi(x) - 0x00100000) < 0x7fe00000u;
