@@ -174,77 +174,78 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
   // The constants move on to shared memory ([constant][thread], conflict-free, 29 KB per block): 72 registers per thread
   // instead of 128, 7 instead of 4 warps per scheduler, and room for the routing blocks of the previous window beside them.
   // (ncu: the step is then issue-bound — ≈410 warp instructions per zone-step at ≈80 % issue-slot utilisation.)
-  __shared__ double s_c[MODEL == HB_MODEL_HLAND_96 ? 28 : 36][128];
+  // (constants that are used together share a 16-byte slot: one LDS.128 fetches both)
+  __shared__ double2 s_c[(MODEL == HB_MODEL_HLAND_96 ? 28 : 36) / 2][128];
   if (MODEL != HB_MODEL_HLAND_96) {
-    s_c[28][threadIdx.x] = KZX(KZ_X0); s_c[29][threadIdx.x] = KZX(KZ_X1); s_c[30][threadIdx.x] = KZX(KZ_X2);
-    s_c[31][threadIdx.x] = KZX(KZ_X3); s_c[32][threadIdx.x] = KZX(KZ_X4); s_c[33][threadIdx.x] = KZX(KZ_X5);
-    s_c[34][threadIdx.x] = KZX(KZ_X6);
-    s_c[35][threadIdx.x] = d.ke[KE_DT_PERCMAX * ep + e];   // hland_96p: PercMax (dt = 1)
+    s_c[14][threadIdx.x].x = KZX(KZ_X0); s_c[14][threadIdx.x].y = KZX(KZ_X1); s_c[15][threadIdx.x].x = KZX(KZ_X2);
+    s_c[15][threadIdx.x].y = KZX(KZ_X3); s_c[16][threadIdx.x].x = KZX(KZ_X4); s_c[16][threadIdx.x].y = KZX(KZ_X5);
+    s_c[17][threadIdx.x].x = KZX(KZ_X6);
+    s_c[17][threadIdx.x].y = d.ke[KE_DT_PERCMAX * ep + e];   // hland_96p: PercMax (dt = 1)
   }
-#define kx0 s_c[28][threadIdx.x]
-#define kx1 s_c[29][threadIdx.x]
-#define kx2 s_c[30][threadIdx.x]
-#define kx3 s_c[31][threadIdx.x]
-#define kx4 s_c[32][threadIdx.x]
-#define kx5 s_c[33][threadIdx.x]
-#define kx6 s_c[34][threadIdx.x]
-#define kpercmax s_c[35][threadIdx.x]
-  s_c[0][threadIdx.x] = tcorr;
-  s_c[1][threadIdx.x] = tcalt_dz;
-  s_c[2][threadIdx.x] = tt_hi;
-  s_c[3][threadIdx.x] = tt_lo;
-  s_c[4][threadIdx.x] = inv_ttint;
-  s_c[5][threadIdx.x] = pcalt_f;
-  s_c[6][threadIdx.x] = pcorr;
-  s_c[7][threadIdx.x] = inv_rfcf;
-  s_c[8][threadIdx.x] = inv_sfcf;
-  s_c[9][threadIdx.x] = icmax;
-  s_c[10][threadIdx.x] = cfmax;
-  s_c[11][threadIdx.x] = cfvar;
-  s_c[12][threadIdx.x] = ttm;
-  s_c[13][threadIdx.x] = cfr_cfmax;
-  s_c[14][threadIdx.x] = whc;
-  s_c[15][threadIdx.x] = fc;
-  s_c[16][threadIdx.x] = inv_fc;
-  s_c[17][threadIdx.x] = beta;
-  s_c[18][threadIdx.x] = thresh;
-  s_c[19][threadIdx.x] = inv_thresh;
-  s_c[20][threadIdx.x] = excessred;
-  s_c[21][threadIdx.x] = atf;
-  s_c[22][threadIdx.x] = etf;
-  s_c[23][threadIdx.x] = alt_f;
-  s_c[24][threadIdx.x] = neg_pf;
-  s_c[25][threadIdx.x] = w_a;
-  s_c[26][threadIdx.x] = w_b;
-  s_c[27][threadIdx.x] = sf;
-#define tcorr s_c[0][threadIdx.x]
-#define tcalt_dz s_c[1][threadIdx.x]
-#define tt_hi s_c[2][threadIdx.x]
-#define tt_lo s_c[3][threadIdx.x]
-#define inv_ttint s_c[4][threadIdx.x]
-#define pcalt_f s_c[5][threadIdx.x]
-#define pcorr s_c[6][threadIdx.x]
-#define inv_rfcf s_c[7][threadIdx.x]
-#define inv_sfcf s_c[8][threadIdx.x]
-#define icmax s_c[9][threadIdx.x]
-#define cfmax s_c[10][threadIdx.x]
-#define cfvar s_c[11][threadIdx.x]
-#define ttm s_c[12][threadIdx.x]
-#define cfr_cfmax s_c[13][threadIdx.x]
-#define whc s_c[14][threadIdx.x]
-#define fc s_c[15][threadIdx.x]
-#define inv_fc s_c[16][threadIdx.x]
-#define beta s_c[17][threadIdx.x]
-#define thresh s_c[18][threadIdx.x]
-#define inv_thresh s_c[19][threadIdx.x]
-#define excessred s_c[20][threadIdx.x]
-#define atf s_c[21][threadIdx.x]
-#define etf s_c[22][threadIdx.x]
-#define alt_f s_c[23][threadIdx.x]
-#define neg_pf s_c[24][threadIdx.x]
-#define w_a s_c[25][threadIdx.x]
-#define w_b s_c[26][threadIdx.x]
-#define sf s_c[27][threadIdx.x]
+#define kx0 s_c[14][threadIdx.x].x
+#define kx1 s_c[14][threadIdx.x].y
+#define kx2 s_c[15][threadIdx.x].x
+#define kx3 s_c[15][threadIdx.x].y
+#define kx4 s_c[16][threadIdx.x].x
+#define kx5 s_c[16][threadIdx.x].y
+#define kx6 s_c[17][threadIdx.x].x
+#define kpercmax s_c[17][threadIdx.x].y
+  s_c[0][threadIdx.x].x = tcorr;
+  s_c[0][threadIdx.x].y = tcalt_dz;
+  s_c[1][threadIdx.x].x = tt_hi;
+  s_c[1][threadIdx.x].y = tt_lo;
+  s_c[2][threadIdx.x].x = inv_ttint;
+  s_c[2][threadIdx.x].y = pcalt_f;
+  s_c[3][threadIdx.x].x = pcorr;
+  s_c[3][threadIdx.x].y = inv_rfcf;
+  s_c[4][threadIdx.x].x = inv_sfcf;
+  s_c[4][threadIdx.x].y = icmax;
+  s_c[5][threadIdx.x].x = cfmax;
+  s_c[5][threadIdx.x].y = cfvar;
+  s_c[6][threadIdx.x].x = ttm;
+  s_c[6][threadIdx.x].y = cfr_cfmax;
+  s_c[7][threadIdx.x].x = whc;
+  s_c[7][threadIdx.x].y = fc;
+  s_c[8][threadIdx.x].x = inv_fc;
+  s_c[8][threadIdx.x].y = beta;
+  s_c[9][threadIdx.x].x = thresh;
+  s_c[9][threadIdx.x].y = inv_thresh;
+  s_c[10][threadIdx.x].x = excessred;
+  s_c[10][threadIdx.x].y = atf;
+  s_c[11][threadIdx.x].x = etf;
+  s_c[11][threadIdx.x].y = alt_f;
+  s_c[12][threadIdx.x].x = neg_pf;
+  s_c[12][threadIdx.x].y = w_a;
+  s_c[13][threadIdx.x].x = w_b;
+  s_c[13][threadIdx.x].y = sf;
+#define tcorr s_c[0][threadIdx.x].x
+#define tcalt_dz s_c[0][threadIdx.x].y
+#define tt_hi s_c[1][threadIdx.x].x
+#define tt_lo s_c[1][threadIdx.x].y
+#define inv_ttint s_c[2][threadIdx.x].x
+#define pcalt_f s_c[2][threadIdx.x].y
+#define pcorr s_c[3][threadIdx.x].x
+#define inv_rfcf s_c[3][threadIdx.x].y
+#define inv_sfcf s_c[4][threadIdx.x].x
+#define icmax s_c[4][threadIdx.x].y
+#define cfmax s_c[5][threadIdx.x].x
+#define cfvar s_c[5][threadIdx.x].y
+#define ttm s_c[6][threadIdx.x].x
+#define cfr_cfmax s_c[6][threadIdx.x].y
+#define whc s_c[7][threadIdx.x].x
+#define fc s_c[7][threadIdx.x].y
+#define inv_fc s_c[8][threadIdx.x].x
+#define beta s_c[8][threadIdx.x].y
+#define thresh s_c[9][threadIdx.x].x
+#define inv_thresh s_c[9][threadIdx.x].y
+#define excessred s_c[10][threadIdx.x].x
+#define atf s_c[10][threadIdx.x].y
+#define etf s_c[11][threadIdx.x].x
+#define alt_f s_c[11][threadIdx.x].y
+#define neg_pf s_c[12][threadIdx.x].x
+#define w_a s_c[12][threadIdx.x].y
+#define w_b s_c[13][threadIdx.x].x
+#define sf s_c[13][threadIdx.x].y
 
   const int64_t col = d.fcol[e];
   // all per-step addresses advance by pointer bumps (no 64-bit multiplies in the loop)
