@@ -405,9 +405,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             # what the hardware counters say about the same kernel (one `ncu --set full` capture of a steady-state window,
             # committed under profiles/): a pow/exp is ONE op in SURVEY's convention but ≈24/≈14 FP64 instructions, so the
             # pipe utilisation is the tighter statement about how close the kernel is to the FP64 roof
-            "ncu": {"sm__inst_executed_pipe_fp64_pct_of_peak": 64.4, "smsp__issue_active_pct": 73.6,
-                    "fp64_warp_instructions_per_zone_step": 162, "warp_instructions_per_zone_step": 386,
-                    "source": "profiles/r01_s3_summary.txt (zone_kernel<1,0,0>, 3.97 ms alone)"} if traffic else None,
+            "ncu": {"sm__inst_executed_pipe_fp64_pct_of_peak": 63.8, "smsp__issue_active_pct": 72.0,
+                    "fp64_warp_instructions_per_zone_step": 151, "warp_instructions_per_zone_step": 340,
+                    "source": "profiles/r01_s3_summary.txt (zone_kernel<1,0,0>, 3.74 ms under ncu)"} if traffic else None,
             "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
