@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Secondary measurements beside bench.py (which holds the contract workload, BASELINE.json configs[3]): the other
+"""(Lives under tests/ because it uses the CPU oracle as its checker.)  Secondary measurements beside bench.py (which holds the contract workload, BASELINE.json configs[3]): the other
 configurations of BASELINE.json that fit one GPU, and the sibling models.  One JSON line per case on stdout.
 
   config2   HydPy-H-Lahn hourly x 4096 parameter-ensemble members (real Lahn structure and parameters from the committed
