@@ -207,6 +207,7 @@ struct hb_engine {
   std::vector<int32_t> unit_lvl_ptr;
   int64_t n_units = 0;
   int diag_chunks_g = -1;
+  int group_min_width = 256;            // levels with fewer wavefront reaches run as single-reach (systolic) units
   int diag_chunks = -1;                 // n_chunks the uploaded diag_start belongs to
   int* h_wave_err = nullptr;            // pinned copy of the wavefront's error flag
   // musk_mct reaches
@@ -1025,16 +1026,20 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
     if ((rc_ = upload(h, h->d_mct_cn, zero)) || (rc_ = upload(h, h->d_mct_rn, zero)) || (rc_ = upload(h, h->d_mct_rwd, nan_)))
       return rc_;
   }
+  if (const char* gw = getenv("HB_GROUP_MIN_WIDTH")) h->group_min_width = atoi(gw);   // development aid
   // units of the grouped wavefront: per level the simple reaches (one inlet node in newsim mode, at most HB_GRP_SMAX
   // segments, musk_classic) in groups of 32, every other reach on its own
   {
     std::vector<int32_t> unit_start{0}, unit_reach, unit_info, unit_lvl(nlev + 1, 0);
     for (int l = 0; l < nlev; ++l) {
       std::vector<int32_t> simple, other;
+      // groups pay off where a level is wide (throughput); the narrow tail of a river tree is a chain of dependent
+      // levels, where the systolic single-reach form has the shorter latency per level
+      const bool wide = wave_lvl[l + 1] - wave_lvl[l] >= h->group_min_width;
       for (int i = wave_lvl[l]; i < wave_lvl[l + 1]; ++i) {
         const int32_t q = wave_order[i];
         const ReachMeta& m = meta[q];
-        (m.simple_node >= 0 && m.nseg <= HB_GRP_SMAX && m.n_entry <= HB_GRP_EMAX && m.n_dep <= HB_GRP_EMAX && m.pad == 0
+        (wide && m.simple_node >= 0 && m.nseg <= HB_GRP_SMAX && m.n_entry <= HB_GRP_EMAX && m.n_dep <= HB_GRP_EMAX && m.pad == 0
              ? simple : other).push_back(q);
       }
       for (size_t i = 0; i < simple.size(); i += 32) {
