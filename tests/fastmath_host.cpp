@@ -10,6 +10,7 @@ extern "C" {
 void fm_pow(const double* x, const double* y, double* out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = hb::hb_pow(x[i], y[i], hb::hb_tabref(&g_tables)); }
 void fm_exp(const double* x, double* out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = hb::hb_exp(x[i], hb::hb_tabref(&g_tables)); }
 void fm_log(const double* x, double* out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = hb::hb_log_normal(x[i], hb::hb_tabref(&g_tables)); }
+void fm_logfull(const double* x, double* out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = hb::hb_log(x[i], hb::hb_tabref(&g_tables)); }
 // errors against x87 extended precision libm
 void fm_pow_relerr(const double* x, const double* y, const double* got, double* rel, long n) {
   for (long i = 0; i < n; ++i) { long double r = powl((long double)x[i], (long double)y[i]); rel[i] = (double)fabsl(((long double)got[i] - r) / r); }

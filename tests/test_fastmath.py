@@ -84,3 +84,28 @@ def test_log_absolute_error(fm):
     o = np.zeros(1)
     fm.fm_log(p(one), p(o), 1)
     assert o[0] == 0.0
+
+
+def test_log_special_cases_and_contributing_area_identity(fm):
+    """`hb_log` (used for Calc_ContriArea_V1 in the fast path: (prod (sm/fc)^w)^beta = exp(beta * sum(w * log(sm/fc)))):
+    libm semantics for zero, subnormal, negative, inf, nan; and the identity holds to 1e-14 for the model's ranges."""
+    x = np.array([0.0, 1.0, 1e-310, -1.0, np.inf, np.nan, 0.5])
+    out = np.zeros(len(x))
+    fm.fm_logfull(p(x), p(out), len(x))
+    with np.errstate(all="ignore"):
+        ref = np.log(x)
+    assert out[0] == -np.inf and out[1] == 0.0 and np.isnan(out[3]) and out[4] == np.inf and np.isnan(out[5])
+    np.testing.assert_allclose(out, ref, rtol=1e-15, equal_nan=True)
+    rng = np.random.default_rng(3)
+    nz, ne = 12, 20_000
+    ratio = rng.uniform(1e-4, 1.0, (ne, nz))                  # sm/fc of the soil zones of an element
+    w = rng.uniform(0.2, 1.0, (ne, nz)); w /= w.sum(axis=1, keepdims=True)
+    beta = rng.uniform(1.0, 4.0, ne)
+    lg = np.zeros(ne * nz)
+    fm.fm_logfull(p(np.ascontiguousarray(ratio.reshape(-1))), p(lg), ne * nz)
+    t = beta * np.sum(w * lg.reshape(ne, nz), axis=1)
+    got = np.zeros(ne)
+    fm.fm_exp(p(np.ascontiguousarray(t)), p(got), ne)
+    ref = np.prod(np.power(ratio.astype(np.longdouble), w.astype(np.longdouble)), axis=1) ** beta.astype(np.longdouble)
+    rel = np.abs((got - ref) / ref).astype(np.float64)
+    assert rel.max() < 1e-14, rel.max()
