@@ -245,9 +245,10 @@ __device__ __noinline__ double mct_find_waterdepth(const WqDev& q, double refq, 
       break;
     }
   }
-  // (NaN discharges never bracket a root: the reference would loop forever on them, here the search gives up with NaN)
-  if (!(y0 == y0) || !(y1 == y1)) return x;
   if (fabs(dx) < xtol) return (x0 + x1) / 2;
+  // a NaN reference discharge leaves the bracket loop at once (no comparison holds) and turns every iterate below into
+  // NaN: same result as the reference's itermax rounds (ref: rootutils.pyx:57-78), without evaluating them
+  if (!(y0 == y0) || !(y1 == y1)) return x;
   for (int iter = 0; iter < itermax; ++iter) {
     x = x0 - y0 * dx / (y1 - y0);
     if (x < xmin) return xmin;

@@ -117,6 +117,39 @@ def test_random_network_with_musk_mct_reaches(engine, seed):
         assert np.array_equal(res[key], res2[key], equal_nan=True), f"window splitting changes {key}"
 
 
+def test_nan_forcing_in_a_mixed_basin(engine):
+    """NaN inputs are legal (ref: hydpy/core/hydpytools.py:2889-2906) and spread as Cython's min/max lowering dictates
+     — through hland_96p / hland_96c, the storage cascade of rconc_nash and the root search of musk_mct
+    (ref: rootutils.pyx:35-78: a NaN reference discharge ends the search with NaN).  Engine and oracle must agree on the
+    NaN pattern of every array and on every finite value."""
+    ne, nt = 120, 48
+    land, states = random_land(ne, seed=77)
+    add_siblings(land, states, seed=77)
+    forcing, doy = random_forcing(nt, ne, seed=77)
+    forcing = forcing.copy()
+    rng = np.random.default_rng(77)
+    for col in rng.choice(ne, size=12, replace=False):
+        forcing[int(rng.integers(0, 4)), int(rng.integers(5, nt - 5)), col] = np.nan
+    river, discharge, _ = random_river(ne, 40, seed=77, n_ext=0)
+    mct = add_mct(river, seed=77)
+    problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy,
+                      ext=np.zeros((0, nt)), mct_states=mct)
+    ref = oracle_run(problem, series=layout.SERIES)
+    assert np.isnan(ref["land_rows"]).any() and np.isfinite(ref["land_rows"]).any()
+    mct_reach = np.flatnonzero(river.reach_model == layout.REACH_MCT)
+    assert np.isnan(ref["reach_out"][mct_reach]).any(), "the test must push a NaN through a musk_mct reach"
+    res = run_problem(problem, engine, series=layout.SERIES, reach_states=True)
+    compare(res, ref, "NaN forcing", series=layout.SERIES)
+    assert_close(res["reach_state_series"], ref["reach_state_series"], "NaN forcing: states.discharge of every step")
+    assert_close(res["mct_states"], ref["mct_states"], "NaN forcing: final Courant/Reynolds numbers and water depths")
+    res1 = run_problem(problem, engine)
+    compare(res1, ref, "NaN forcing (no series)")
+    assert_close(res1["mct_states"], ref["mct_states"], "NaN forcing (no series): musk_mct factors")
+    res2 = run_problem(problem, engine, window=11)
+    for key in ("land_rows", "node_rows", "reach_out", "discharge", "mct_states"):
+        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+
+
 def test_long_reaches_more_than_32_segments(engine):
     ne, nt = 8, 150
     land, states = random_land(ne, seed=5, snowlimit_fraction=0.0)
