@@ -168,6 +168,9 @@ struct hb_engine {
   int wave_blocks = HB_WAVE_BLOCKS_PER_SM;  // persistent wavefront blocks per SM
   bool wave_blocks_set = false;             // (the grouped wavefront defaults to 2 blocks of 64 threads)
   DBuf<double> d_dis_series[2];
+  unsigned mct_series_mask = 0;           // musk_mct sequences to record per step (bits of enum hb_mct_series)
+  unsigned mct_series_run[2] = {0, 0};    // mask the window in buffer set 0/1 was routed with
+  DBuf<double> d_mct_series[2];           // [popc(mask)][nt][n_seg]
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
@@ -809,6 +812,11 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
     case HB_OPT_RIVER_STATE_SERIES:
       h->river_state_series = value != 0;
       if (!value) { h->d_dis_series[0].release(); h->d_dis_series[1].release(); }
+      return HB_OK;
+    case HB_OPT_RIVER_MCT_SERIES:
+      HB_REQUIRE(h, value >= 0 && value < (1 << HB_MS_COUNT), HB_EINVAL, "hb_set_option: invalid musk_mct series mask");
+      h->mct_series_mask = (unsigned)value;
+      if (!value) { h->d_mct_series[0].release(); h->d_mct_series[1].release(); }
       return HB_OK;
     case HB_OPT_RIVER_SWEEP:
       HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES || value == HB_RIVER_GROUPED, HB_EINVAL,
@@ -1497,6 +1505,16 @@ static int run_river(hb_engine* h) {
     HB_CUDA(h, h->d_dis_series[h->cur].reserve((size_t)nt * h->n_seg));
     d.dis_series = h->d_dis_series[h->cur].p;
   }
+  d.mct_series = nullptr; d.mct_series_mask = 0;
+  h->mct_series_run[h->cur] = 0;
+  if (h->mct_series_mask && h->any_mct && nt > 0) {
+    // cells of musk_classic reaches and the last point of every reach stay NaN (all-ones bytes are a NaN)
+    const size_t n = (size_t)__builtin_popcount(h->mct_series_mask) * nt * h->n_seg;
+    HB_CUDA(h, h->d_mct_series[h->cur].reserve(n));
+    HB_CUDA(h, cudaMemsetAsync(h->d_mct_series[h->cur].p, 0xFF, n * sizeof(double), h->s_river));
+    d.mct_series = h->d_mct_series[h->cur].p; d.mct_series_mask = h->mct_series_mask;
+    h->mct_series_run[h->cur] = h->mct_series_mask;
+  }
   d.reach_level = h->d_reach_level.p; d.node_owner = h->d_node_owner.p; d.meta = h->d_reach_meta.p;
   d.wave_rec = h->d_wave_rec.p; d.wave_order = h->d_wave_order.p; d.wave_lvl_ptr = h->d_wave_lvl_ptr.p; d.dep_ptr = h->d_dep_ptr.p;
   d.dep_reach = h->d_dep_reach.p; d.n_levels = nlev; d.n_diag = nlev + n_chunks - 1;
@@ -1916,6 +1934,19 @@ int hb_get_reach_state_series(hb_engine* h, double* out) {
              "hb_get_reach_state_series: not recorded (set HB_OPT_RIVER_STATE_SERIES before hb_run)");
   HB_CUDA(h, cudaSetDevice(h->device));
   return download(h, out, h->d_dis_series[h->cur].p, (size_t)h->nt * h->n_seg);
+}
+
+int hb_get_mct_series(hb_engine* h, int which, double* out) {
+  if (!h) return HB_EINVAL;
+  HB_REQUIRE(h, which >= 0 && which < HB_MS_COUNT, HB_EINVAL, "hb_get_mct_series: unknown sequence %d", which);
+  HB_REQUIRE(h, h->have_river && h->have_routed, HB_ESTATE, "hb_get_mct_series: no routing results");
+  const unsigned mask = h->mct_series_run[h->cur];
+  HB_REQUIRE(h, (mask >> which & 1u) && h->d_mct_series[h->cur].p, HB_ESTATE,
+             "hb_get_mct_series: sequence %d was not recorded (set its bit in HB_OPT_RIVER_MCT_SERIES before hb_run; "
+             "the river needs musk_mct reaches)", which);
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const size_t slot = (size_t)__builtin_popcount(mask & ((1u << which) - 1u)), n = (size_t)h->nt * h->n_seg;
+  return download(h, out, h->d_mct_series[h->cur].p + slot * n, n);
 }
 
 int hb_get_reach_inflow(hb_engine* h, double* rows) {

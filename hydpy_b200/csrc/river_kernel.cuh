@@ -94,6 +94,8 @@ struct RiverDev {
   const int32_t* unit_lvl_ptr; // [n_levels+1] into the units (sorted by level)
   const int32_t* task_list;    // [n_units * n_chunks] unit | chunk << 24, in wavefront order
   const double* zero_row;      // 32 zeros
+  double* mct_series;          // optional [popc(mct_series_mask)][nt][n_seg]: 1-D musk_mct sequences at every step
+  unsigned mct_series_mask;    // bits of enum hb_mct_series; slot of a sequence = number of lower bits set
   // musk_mct reaches
   const int32_t* nmbruns;      // [n_reach]
   const double* rpar;          // [HB_RP_COUNT][n_reach]
@@ -269,8 +271,9 @@ __device__ __noinline__ double mct_find_waterdepth(const WqDev& q, double refq, 
 // ref: musk_model.py:245-254 Calc_ReferenceDischarge_V1, 383-399 Calc_ReferenceWaterDepth_V1, 415-424, 506-512
 // Calc_CorrectingFactor_V1, 548-560 Calc_CourantNumber_V1, 600-616 Calc_ReynoldsNumber_V1, 695-705
 // Calc_Coefficient1_Coefficient2_Coefficient3_V1, 792-806 Calc_Discharge_V2
+// rec: cell [t][segment] of the first recorded series (NULL: no series requested)
 __device__ __noinline__ double mct_segment(const RiverDev& d, int64_t r, double in, double prev_in, double prev_out,
-                                           double* st /* cn, rn, rwd */) {
+                                           double* st /* cn, rn, rwd */, double* rec) {
   const int64_t nr = d.n_reach, t0 = d.trap_ptr[r];
   WqDev q;
   q.n = (int)(d.trap_ptr[r + 1] - t0);
@@ -317,6 +320,15 @@ __device__ __noinline__ double mct_segment(const RiverDev& d, int64_t r, double 
     if (in == prev_in && prev_in == prev_out) nv = in;
     else nv = c1 * in + c2 * prev_in + c3 * prev_out;
     nv = HB_PYMAX_R(nv, 0.0);
+    if (rec && run == nruns - 1) {
+      // what save_data finds after the last repetition (ref: modelutils.py:1127-1167)
+      const double vals[HB_MS_COUNT] = {refq, rwd, w.wettedarea, w.surfacewidth, w.celerity, corr, c1, c2, c3, cn, rn};
+      const int64_t stride = d.nt * d.n_seg;
+      int slot = 0;
+#pragma unroll
+      for (int k = 0; k < HB_MS_COUNT; ++k)
+        if (d.mct_series_mask >> k & 1u) rec[(slot++) * stride] = vals[k];
+    }
   }
   st[0] = cn; st[1] = rn; st[2] = rwd;
   return nv;
@@ -500,7 +512,9 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       const int tloc = tau - lane;
       if (lane < nseg && tloc >= 0 && tloc < len) {
         // ref: musk_model.py:178-187 Calc_Discharge_V1 — (c0*new[i] + c1*old[i]) + c2*old[i+1]
-        const double nv = mct ? mct_segment(d, r, in, prev_in, prev_out, mst) : c0 * in + c1 * prev_in + c2 * prev_out;
+        const double nv = mct ? mct_segment(d, r, in, prev_in, prev_out, mst,
+                                            d.mct_series ? d.mct_series + (ta + tloc) * d.n_seg + g0 + cbase + lane : nullptr)
+                              : c0 * in + c1 * prev_in + c2 * prev_out;
         prev_in = in;
         prev_out = nv;
         out = nv;

@@ -25,7 +25,7 @@ EXPORTS = (
     "hb_set_river_states2", "hb_get_river_states2",
     "hb_select_series", "hb_set_option", "hb_set_forcing", "hb_set_forcing_async", "hb_select_window", "hb_set_external", "hb_run",
     "hb_run_async", "hb_wait", "hb_get_land_outflow", "hb_get_node_series", "hb_get_node_series_async",
-    "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
+    "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_mct_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
     "hb_device_info",
@@ -87,6 +87,7 @@ def load_library() -> C.CDLL:
         "hb_get_reach_inflow": (C.c_int, [H, f64p]),
         "hb_node_statistics": (C.c_int, [H, C.c_int64, i32p, i32p, C.c_int64, f64p, C.c_int, f64p]),
         "hb_get_reach_state_series": (C.c_int, [H, f64p]),
+        "hb_get_mct_series": (C.c_int, [H, C.c_int, f64p]),
         "hb_get_series": (C.c_int, [H, C.c_int, f64p]),
         "hb_comm_unique_id": (C.c_int, [H, C.c_void_p]),
         "hb_comm_init": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
@@ -398,6 +399,22 @@ class Engine:
         river = self._need_river()
         out = np.zeros((self.nt, river.n_seg))
         self._check(self._lib.hb_get_reach_state_series(self._h, ptr(out, C.c_double)), "hb_get_reach_state_series")
+        return out
+
+    def record_mct_series(self, names: Iterable[str] = ()) -> None:
+        """musk_mct sequences (names of `layout.MCT_SERIES`) to record at every step (read with `get_mct_series`)."""
+        mask = 0
+        for name in names:
+            if name not in layout.MS:
+                raise ValueError(f"unknown musk_mct sequence `{name}` (known: {', '.join(layout.MCT_SERIES)})")
+            mask |= 1 << layout.MS[name]
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_MCT_SERIES, mask), "hb_set_option")
+
+    def get_mct_series(self, name: str) -> np.ndarray:
+        """[nt, n_seg]: segment i of reach r at seg_ptr[r] + i, NaN elsewhere."""
+        river = self._need_river()
+        out = np.zeros((self.nt, river.n_seg))
+        self._check(self._lib.hb_get_mct_series(self._h, layout.MS[name], ptr(out, C.c_double)), "hb_get_mct_series")
         return out
 
     def get_reach_inflow(self) -> np.ndarray:

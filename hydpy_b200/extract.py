@@ -519,19 +519,35 @@ def requested_series(problem: Problem) -> list[str]:
 
 
 def check_reach_series(problem: Problem) -> None:
-    """musk_mct: only inflow, outflow and states.discharge are recorded per step; the other sequences (hydraulic factors,
-    Courant/Reynolds numbers) end with their final values but keep no series — asking for them is an error, not a
-    silent gap."""
+    """musk_mct: inflow, outflow, states.discharge and the 1-D sequences of `layout.MCT_SERIES` are recorded per step —
+    that is every sequence the model owns; a sequence this engine does not know (a future reference version) is an
+    error, not a silent gap."""
     for element in problem.river_elements:
         model = element.model
         if _modelname(model) != "musk_mct":
             continue
-        for group, keep in (("factors", ()), ("fluxes", ("inflow", "outflow")), ("states", ("discharge",))):
+        for group in ("factors", "fluxes", "states"):
             for seq in getattr(model.sequences, group, ()):
-                if getattr(seq, "ramflag", False) and seq.name not in keep:
+                if getattr(seq, "ramflag", False) and seq.name not in ("inflow", "outflow", "discharge") and (
+                        layout.MCT_SERIES_GROUP.get(seq.name, "factors") != group or seq.name not in layout.MS):
                     raise UnsupportedModelError(
                         f"element `{element.name}`: the B200 engine does not record the time series of musk_mct "
-                        f"sequence `{seq.name}` (only inflow, outflow and discharge)")
+                        f"sequence `{seq.name}`")
+
+
+def requested_mct_series(problem: Problem) -> list[str]:
+    """The 1-D musk_mct sequences at least one element keeps in RAM (`seq.ramflag`), in `layout.MCT_SERIES` order."""
+    wanted = []
+    for name in layout.MCT_SERIES:
+        group = layout.MCT_SERIES_GROUP.get(name, "factors")
+        for element in problem.river_elements:
+            if _modelname(element.model) != "musk_mct":
+                continue
+            seq = getattr(getattr(element.model.sequences, group), name, None)
+            if seq is not None and getattr(seq, "ramflag", False):
+                wanted.append(name)
+                break
+    return wanted
 
 
 def requested_reach_states(problem: Problem) -> bool:
@@ -547,7 +563,7 @@ def _set_state(seq: Any, value: Any) -> None:
 def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, node_rows: np.ndarray,
                land_rows: np.ndarray, reach_out: np.ndarray | None, reach_in: np.ndarray | None,
                series: dict[str, np.ndarray], reach_state_series: np.ndarray | None = None,
-               mct_states: np.ndarray | None = None) -> None:
+               mct_states: np.ndarray | None = None, mct_series: dict[str, np.ndarray] | None = None) -> None:
     """Store the results of one run in the HydPy objects exactly where the reference leaves them."""
     land, i0, i1 = problem.land, problem.i0, problem.i1
     last = i1 - i0 - 1
@@ -612,6 +628,13 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
             _set_state(model.sequences.states.courantnumber, mct_states[0, g0:g1 - 1])
             _set_state(model.sequences.states.reynoldsnumber, mct_states[1, g0:g1 - 1])
             model.sequences.factors.referencewaterdepth.value = mct_states[2, g0:g1 - 1]
+        if mct_series and int(river.reach_model[r]) == layout.REACH_MCT:
+            for name, data in mct_series.items():
+                seq = getattr(getattr(model.sequences, layout.MCT_SERIES_GROUP.get(name, "factors")), name)
+                if getattr(seq, "ramflag", False):
+                    seq.series[i0:i1] = data[:, g0:g1 - 1]
+                if last >= 0 and name not in ("courantnumber", "reynoldsnumber", "referencewaterdepth"):
+                    seq.value = data[last, g0:g1 - 1]
         if reach_state_series is not None and getattr(model.sequences.states.discharge, "ramflag", False):
             model.sequences.states.discharge.series[i0:i1] = reach_state_series[:, g0:g1]
         flu = model.sequences.fluxes

@@ -88,12 +88,19 @@ TPAR = ("bottomwidth", "sideslope", "stricklercoefficient", "calibrationfactor",
 TP = {name: i for i, name in enumerate(TPAR)}
 #: musk_mct conditions beside the discharge state, rows of the `mct_states` array [3, n_seg]
 MCT_STATES = ("courantnumber", "reynoldsnumber", "referencewaterdepth")
+#: 1-D musk_mct sequences recorded per step on request (enum hb_mct_series; factors, fluxes.referencedischarge, states)
+MCT_SERIES = ("referencedischarge", "referencewaterdepth", "wettedarea", "surfacewidth", "celerity", "correctingfactor",
+              "coefficient1", "coefficient2", "coefficient3", "courantnumber", "reynoldsnumber")
+MS = {name: i for i, name in enumerate(MCT_SERIES)}
+#: sequence group of each of them in the reference (`hydpy/models/musk/musk_factors.py`, `musk_fluxes.py`, `musk_states.py`)
+MCT_SERIES_GROUP = {"referencedischarge": "fluxes", "courantnumber": "states", "reynoldsnumber": "states"}
 
 RUN_LAND, RUN_RIVER = 1, 2
 OPT_LAND_PATH = 0
 OPT_RIVER_SWEEP = 1
 OPT_RIVER_STATE_SERIES = 2
 OPT_RIVER_WAVE_BLOCKS = 3
+OPT_RIVER_MCT_SERIES = 4
 RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2
 LAND_AUTO, LAND_GENERAL = 0, 1
 ROW_NODE, ROW_REACH = 0, 1

@@ -19,7 +19,8 @@ import numpy as np
 
 from .abi import LandStates
 from .engine import Engine
-from .extract import Problem, check_reach_series, extract, requested_reach_states, requested_series, write_back
+from .extract import (Problem, check_reach_series, extract, requested_mct_series, requested_reach_states, requested_series,
+                      write_back)
 
 _engines: dict[int, Engine] = {}
 
@@ -32,11 +33,13 @@ def get_engine(device: int = 0) -> Engine:
 
 
 def run_problem(problem: Problem, engine: Engine | None = None, *, series: Iterable[str] = (),
-                window: int | None = None, device: int = 0, reach_states: bool = False) -> dict[str, Any]:
+                window: int | None = None, device: int = 0, reach_states: bool = False,
+                mct_series: Iterable[str] = ()) -> dict[str, Any]:
     """Run an extracted problem on the engine, optionally in time windows of `window` steps.
 
     Returns the keyword arguments of `extract.write_back` (states, discharge, node_rows, land_rows, reach_out,
-    reach_in, series and — with `reach_states` — reach_state_series = musk_classic `states.discharge` per step).
+    reach_in, series and — with `reach_states` — reach_state_series = musk_classic `states.discharge` per step; with
+    `mct_series` (names of `layout.MCT_SERIES`) — mct_series = {name: [nt, n_seg]}, the 1-D musk_mct sequences per step).
     """
     eng = engine if engine is not None else get_engine(device)
     series = list(series)
@@ -47,6 +50,9 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
     eng.set_river_states(problem.discharge, problem.mct_states)
     eng.select_series(series)
     eng.record_reach_states(reach_states)
+    mct_series = list(mct_series) if problem.river.any_mct else []
+    eng.record_mct_series(mct_series)
+    mct_parts: dict[str, list[np.ndarray]] = {name: [] for name in mct_series}
     state_parts: list[np.ndarray] = []
     window = nt if not window or window <= 0 else min(int(window), nt)
     node_rows = np.zeros((problem.river.n_node, nt))
@@ -69,6 +75,8 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
                 out_series[name].append(eng.get_series(name))
             if reach_states:
                 state_parts.append(eng.get_reach_state_series())
+            for name in mct_series:
+                mct_parts[name].append(eng.get_mct_series(name))
         t0 = t1
         if nt == 0:
             break
@@ -83,6 +91,9 @@ def run_problem(problem: Problem, engine: Engine | None = None, *, series: Itera
                                         else np.zeros((0, problem.river.n_seg)))
     if problem.river.any_mct:
         result["mct_states"] = eng.get_river_mct_states()
+    if mct_series:
+        result["mct_series"] = {n: (np.concatenate(v, axis=0) if v else np.zeros((0, problem.river.n_seg)))
+                                for n, v in mct_parts.items()}
     return result
 
 
@@ -94,7 +105,7 @@ def simulate(hp: Any, *, device: int = 0, window: int | None = None, engine: Eng
     problem = extract(hp, i0, i1)
     check_reach_series(problem)
     result = run_problem(problem, engine, series=requested_series(problem), window=window, device=device,
-                         reach_states=requested_reach_states(problem))
+                         reach_states=requested_reach_states(problem), mct_series=requested_mct_series(problem))
     write_back(problem, **result)
 
 

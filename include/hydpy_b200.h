@@ -306,6 +306,16 @@ int hb_select_series(hb_engine* h, int series, int on);
 /* HB_OPT_RIVER_WAVE_BLOCKS (1..8, default 4): persistent wavefront blocks per SM.  The routing of window w shares the GPU
  * with the runoff generation of window w+1 (hb_run_async); fewer blocks leave it more of every SM. */
 #define HB_OPT_RIVER_WAVE_BLOCKS 3
+/* HB_OPT_RIVER_MCT_SERIES (bit mask over enum hb_mct_series, default 0): musk_mct sequences to record at every step for
+ * hb_get_mct_series — the `ramflag` of the 1-D factor, flux and state sequences of `hydpy/models/musk/musk_factors.py`,
+ * `musk_fluxes.py:14` and `musk_states.py:10-17` (values of the last of the NmbRuns repetitions, as `save_data` sees
+ * them, ref: hydpy/cythons/modelutils.py:1127-1167). */
+#define HB_OPT_RIVER_MCT_SERIES 4
+enum hb_mct_series {
+  HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
+  HB_MS_CORRECTINGFACTOR, HB_MS_COEFFICIENT1, HB_MS_COEFFICIENT2, HB_MS_COEFFICIENT3, HB_MS_COURANTNUMBER,
+  HB_MS_REYNOLDSNUMBER, HB_MS_COUNT
+};
 int hb_set_option(hb_engine* h, int option, int64_t value);
 
 /* ---- one simulation window ------------------------------------------------------------------------------------ */
@@ -351,6 +361,9 @@ int hb_get_reach_outflow(hb_engine* h, double* rows);
 /* musk_classic states.discharge per step: host [nt][n_seg] (points of all reaches concatenated like the state itself);
  * needs HB_OPT_RIVER_STATE_SERIES. */
 int hb_get_reach_state_series(hb_engine* h, double* out);
+/* One recorded musk_mct sequence per step: host [nt][n_seg]; segment i of reach r sits at seg_ptr[r] + i (like the
+ * musk_mct conditions of hb_river_states), all other cells are NaN.  Needs the bit in HB_OPT_RIVER_MCT_SERIES. */
+int hb_get_mct_series(hb_engine* h, int which, double* out);
 /* musk_classic fluxes.inflow of every reach: host [n_reach][nt]. */
 int hb_get_reach_inflow(hb_engine* h, double* rows);
 /* One selected land series (see enum hb_series for the layout). */

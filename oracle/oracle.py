@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         _lib.oracle_river_run3.restype = C.c_int
         _lib.oracle_river_run3.argtypes = [C.POINTER(hb_river_desc), C.POINTER(hb_river_states), C.c_int64, f64p, f64p,
                                            f64p, f64p, f64p, f64p]
+        _lib.oracle_river_run4.restype = C.c_int
+        _lib.oracle_river_run4.argtypes = _lib.oracle_river_run3.argtypes + [f64p]
         _lib.oracle_sinfactor.restype = C.c_double
         _lib.oracle_sinfactor.argtypes = [C.c_int64]
     return _lib
@@ -111,11 +113,12 @@ def land_run(land: LandBundle, states: LandStates, forcing: np.ndarray, doy: np.
 
 
 def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, ext: np.ndarray | None = None,
-              dis_series: np.ndarray | None = None, mct_states: np.ndarray | None = None
-              ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+              dis_series: np.ndarray | None = None, mct_states: np.ndarray | None = None,
+              mct_series: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Route the window; `discharge` (and `mct_states` [3, n_seg], the musk_mct conditions) are updated in place.
     Returns (node rows, reach outflow, reach inflow).  `dis_series` (optional, [nt, n_seg]) receives
-    `states.discharge` after every step."""
+    `states.discharge` after every step, `mct_series` (optional, [len(layout.MCT_SERIES), nt, n_seg], NaN-filled by the
+    caller) the 1-D musk_mct sequences after every step."""
     L = lib()
     land_rows = np.ascontiguousarray(land_rows, dtype=np.float64)
     nt = land_rows.shape[1] if land_rows.ndim == 2 and land_rows.shape[0] else (ext.shape[1] if ext is not None else 0)
@@ -138,9 +141,13 @@ def river_run(river: RiverBundle, discharge: np.ndarray, land_rows: np.ndarray, 
         st.courantnumber = ptr(mct_states[0], C.c_double)
         st.reynoldsnumber = ptr(mct_states[1], C.c_double)
         st.referencewaterdepth = ptr(mct_states[2], C.c_double)
-    rc = L.oracle_river_run3(C.byref(d), C.byref(st), nt, ptr(land_rows, C.c_double),
+    if mct_series is not None:
+        assert mct_series.shape == (len(layout.MCT_SERIES), nt, river.n_seg) and mct_series.dtype == np.float64
+        assert mct_series.flags.c_contiguous
+    rc = L.oracle_river_run4(C.byref(d), C.byref(st), nt, ptr(land_rows, C.c_double),
                              ptr(ext, C.c_double), ptr(node_rows, C.c_double), ptr(rout, C.c_double),
-                             ptr(rin, C.c_double), ptr(dis_series, C.c_double) if dis_series is not None else None)
+                             ptr(rin, C.c_double), ptr(dis_series, C.c_double) if dis_series is not None else None,
+                             ptr(mct_series, C.c_double) if mct_series is not None else None)
     if rc != 0:
         raise RuntimeError(f"oracle_river_run failed with code {rc}")
     return node_rows, rout, rin

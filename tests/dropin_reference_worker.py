@@ -28,18 +28,23 @@ import hydpy_b200  # noqa: E402
 simulate_module = sys.modules["hydpy_b200.simulate"]   # (the package exports the function under the same name)
 
 
-def oracle_run_problem(problem, engine=None, *, series=(), window=None, device=0, reach_states=False):
+def oracle_run_problem(problem, engine=None, *, series=(), window=None, device=0, reach_states=False, mct_series=()):
     """Same contract as hydpy_b200.run_problem, executed by the CPU oracle."""
     st, dis = problem.states.copy(), problem.discharge.copy()
     qt, ser = oracle.land_run(problem.land, st, problem.forcing, problem.doy, series=list(series), threads=2)
     dser = np.zeros((problem.nt, problem.river.n_seg)) if reach_states else None
     mct = None if problem.mct_states is None else problem.mct_states.copy()
-    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct)
+    mct_series = list(mct_series) if problem.river.any_mct else []
+    mser = np.full((len(hydpy_b200.layout.MCT_SERIES), problem.nt, problem.river.n_seg), np.nan) if mct_series else None
+    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct,
+                                            mct_series=mser)
     out = dict(states=st, discharge=dis, node_rows=node_rows, land_rows=qt, reach_out=rout, reach_in=rin, series=ser)
     if reach_states:
         out["reach_state_series"] = dser
     if mct is not None:
         out["mct_states"] = mct
+    if mct_series:
+        out["mct_series"] = {name: mser[hydpy_b200.layout.MS[name]] for name in mct_series}
     return out
 
 
@@ -140,11 +145,7 @@ with model.add_wqmodel_v1("wq_trapeze_strickler"):
     hp = HydPy("sibling_project")
     hp.update_devices(nodes=Nodes(n_up, n_out, n_end), elements=Elements(e_p, e_c, e_r, e_m))
     hp.update_parameters()
-    hp.prepare_allseries()
-    for group, keep in (("factors", ()), ("fluxes", ("inflow", "outflow")), ("states", ("discharge",))):
-        for seq in getattr(e_m.model.sequences, group):       # musk_mct: the engine records these three series only
-            if seq.name not in keep:
-                seq.prepare_series(allocate_ram=False)
+    hp.prepare_allseries()                                    # musk_mct included: every factor, flux and state series
     nt = len(pub.timegrids.init)
     for element in (e_p, e_c):
         model = element.model

@@ -84,6 +84,8 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
     # states.discharge of every step (and, for musk_mct, the other per-segment sequences), stored like the state: [nt, n_seg]
     per_seg = {"dis_series": ("states", "discharge"), "cn_series": ("states", "courantnumber"),
                "rn_series": ("states", "reynoldsnumber"), "rwd_series": ("factors", "referencewaterdepth")}
+    for name in layout.MCT_SERIES:   # every 1-D musk_mct sequence: exp_mct_<name>
+        per_seg["mct_" + name] = (layout.MCT_SERIES_GROUP.get(name, "factors"), name)
     for key, (group, name) in per_seg.items():
         arr = np.full((nt, problem.river.n_seg), np.nan)
         have = False

@@ -7,7 +7,7 @@ operations in the same order (-fmad=false) and the seasonal sine is taken from t
 import numpy as np
 import pytest
 
-from hydpy_b200 import Engine, run_problem
+from hydpy_b200 import Engine, layout, run_problem
 from tests.util import assert_close, load_scenarios
 
 pytestmark = pytest.mark.gpu
@@ -99,7 +99,9 @@ def test_musk_mct_integration(engine, name):
     sc = MUSK_MCT[name]
     p = sc.problem
     for window in (None, 37):
-        res = run_problem(p, engine, reach_states=True, window=window)
+        res = run_problem(p, engine, reach_states=True, window=window, mct_series=layout.MCT_SERIES)
+        for seq in layout.MCT_SERIES:   # hydraulic factors, reference discharge, Courant/Reynolds numbers of every step
+            assert_close(res["mct_series"][seq], sc.expected("mct_" + seq), f"{sc.name}: series of {seq} (window {window})")
         assert_close(res["reach_out"], sc.expected("reach_out"), f"{sc.name}: outflow (window {window})")
         assert_close(res["reach_in"], sc.expected("reach_in"), f"{sc.name}: inflow")
         assert_close(res["node_rows"][p.node_writeback], sc.expected("node_rows")[p.node_writeback], f"{sc.name}: nodes")

@@ -28,9 +28,12 @@ def oracle_run(problem, series=()):
     dis = problem.discharge.copy()
     dser = np.zeros((problem.nt, problem.river.n_seg))
     mct = None if problem.mct_states is None else problem.mct_states.copy()
-    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct)
+    mser = None if mct is None else np.full((len(layout.MCT_SERIES), problem.nt, problem.river.n_seg), np.nan)
+    node_rows, rout, rin = oracle.river_run(problem.river, dis, qt, problem.ext, dis_series=dser, mct_states=mct,
+                                            mct_series=mser)
     return dict(states=st, land_rows=qt, series=ser, discharge=dis, node_rows=node_rows, reach_out=rout, reach_in=rin,
-                reach_state_series=dser, mct_states=mct)
+                reach_state_series=dser, mct_states=mct,
+                mct_series=None if mser is None else dict(zip(layout.MCT_SERIES, mser)))
 
 
 def compare(res, ref, what, series=()):
@@ -108,13 +111,22 @@ def test_random_network_with_musk_mct_reaches(engine, seed):
     problem = Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext,
                       mct_states=mct)
     ref = oracle_run(problem)
-    res = run_problem(problem, engine, reach_states=True)
+    res = run_problem(problem, engine, reach_states=True, mct_series=layout.MCT_SERIES)
     compare(res, ref, f"musk_mct seed {seed}")
     assert_close(res["reach_state_series"], ref["reach_state_series"], "musk_mct: states.discharge of every step")
     assert_close(res["mct_states"], ref["mct_states"], "musk_mct: final Courant/Reynolds numbers and water depths")
-    res2 = run_problem(problem, engine, window=23)
+    for seq in layout.MCT_SERIES:   # NaN in the cells of musk_classic reaches and at the last point of every reach
+        assert_close(res["mct_series"][seq], ref["mct_series"][seq], f"musk_mct: series of {seq}")
+    some = ("celerity", "coefficient2", "reynoldsnumber")
+    res2 = run_problem(problem, engine, window=23, mct_series=some)
+    assert sorted(res2["mct_series"]) == sorted(some)
     for key in ("node_rows", "reach_out", "discharge", "mct_states"):
         assert np.array_equal(res[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+    for seq in some:
+        assert np.array_equal(res["mct_series"][seq], res2["mct_series"][seq], equal_nan=True), f"window splitting changes {seq}"
+    with pytest.raises(Exception, match="was not recorded"):
+        engine.get_mct_series("wettedarea")
+    engine.record_mct_series(())
 
 
 def test_nan_forcing_in_a_mixed_basin(engine):
@@ -138,8 +150,10 @@ def test_nan_forcing_in_a_mixed_basin(engine):
     assert np.isnan(ref["land_rows"]).any() and np.isfinite(ref["land_rows"]).any()
     mct_reach = np.flatnonzero(river.reach_model == layout.REACH_MCT)
     assert np.isnan(ref["reach_out"][mct_reach]).any(), "the test must push a NaN through a musk_mct reach"
-    res = run_problem(problem, engine, series=layout.SERIES, reach_states=True)
+    res = run_problem(problem, engine, series=layout.SERIES, reach_states=True, mct_series=layout.MCT_SERIES)
     compare(res, ref, "NaN forcing", series=layout.SERIES)
+    for seq in layout.MCT_SERIES:
+        assert_close(res["mct_series"][seq], ref["mct_series"][seq], f"NaN forcing: series of {seq}")
     assert_close(res["reach_state_series"], ref["reach_state_series"], "NaN forcing: states.discharge of every step")
     assert_close(res["mct_states"], ref["mct_states"], "NaN forcing: final Courant/Reynolds numbers and water depths")
     res1 = run_problem(problem, engine)

@@ -11,6 +11,7 @@ bar is nevertheless the north_star tolerance (1e-9) plus an explicit report of e
 import numpy as np
 import pytest
 
+from hydpy_b200 import layout
 from oracle import oracle
 from tests.util import assert_close, load_scenarios
 
@@ -30,9 +31,11 @@ def run_oracle(sc, threads=1):
     discharge = p.discharge.copy()
     mct = None if p.mct_states is None else p.mct_states.copy()
     dser = np.full((p.nt, p.river.n_seg), np.nan)
-    node_rows, rout, rin = oracle.river_run(p.river, discharge, qt, p.ext, dis_series=dser, mct_states=mct)
+    mser = np.full((len(layout.MCT_SERIES), p.nt, p.river.n_seg), np.nan) if p.river.any_mct else None
+    node_rows, rout, rin = oracle.river_run(p.river, discharge, qt, p.ext, dis_series=dser, mct_states=mct,
+                                            mct_series=mser)
     return dict(states=states, qt=qt, series=series, discharge=discharge, node_rows=node_rows, rout=rout, rin=rin,
-                mct_states=mct, dis_series=dser)
+                mct_states=mct, dis_series=dser, mct_series=mser)
 
 
 def check(sc, res, exact=True):
@@ -95,6 +98,9 @@ def test_musk_mct_integration(name):
     exp = sc.expected("dis_series")
     assert np.array_equal(res["dis_series"][~np.isnan(exp)], exp[~np.isnan(exp)]), "states.discharge series not exact"
     assert np.array_equal(res["mct_states"], sc.expected("mct_states"), equal_nan=True)
+    # every 1-D sequence of every step (hydraulic factors, reference discharge, Courant and Reynolds numbers): bit for bit
+    for k, seq in enumerate(layout.MCT_SERIES):
+        assert np.array_equal(res["mct_series"][k], sc.expected("mct_" + seq), equal_nan=True), f"series of {seq}"
 
 
 def test_lahn_daily():

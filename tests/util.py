@@ -47,7 +47,9 @@ def assert_close(actual: np.ndarray, desired: np.ndarray, what: str, rtol: float
     nan_a, nan_d = np.isnan(actual), np.isnan(desired)
     assert np.array_equal(nan_a, nan_d), f"{what}: NaN pattern differs"
     a, d = actual[~nan_a], desired[~nan_d]
-    err = np.abs(a - d)
+    same = a == d                                    # equal infinities included (inf - inf would be NaN)
+    err = np.zeros(a.shape)
+    err[~same] = np.abs(a[~same] - d[~same])
     tol = atol + rtol * np.abs(d)
     if np.any(err > tol):
         i = int(np.argmax(err - tol))
