@@ -48,6 +48,7 @@ def test_enums_match_layout():
     assert [m[len("HB_F_"):].lower() for m in enum_members("hb_forcing")[:-1]] == list(layout.FORCING)
     series = [m[len("HB_S_"):].lower() for m in enum_members("hb_series")[:-1]]
     assert series == [s.rstrip("_") for s in layout.SERIES]
+    assert [m[len("HB_MS_"):].lower() for m in enum_members("hb_mct_series")[:-1]] == list(layout.MCT_SERIES)
     for cname, value in (("HB_FIELD", layout.FIELD), ("HB_FOREST", layout.FOREST), ("HB_GLACIER", layout.GLACIER),
                          ("HB_ILAKE", layout.ILAKE), ("HB_SEALED", layout.SEALED), ("HB_ZF_WATER", layout.ZF_WATER),
                          ("HB_ZF_INTERCEPTION", layout.ZF_INTERCEPTION), ("HB_ZF_SOIL", layout.ZF_SOIL),
@@ -58,6 +59,7 @@ def test_enums_match_layout():
                          ("HB_ROW_NODE", layout.ROW_NODE), ("HB_ROW_REACH", layout.ROW_REACH),
                          ("HB_OPT_LAND_PATH", layout.OPT_LAND_PATH), ("HB_OPT_RIVER_SWEEP", layout.OPT_RIVER_SWEEP), ("HB_OPT_RIVER_STATE_SERIES", layout.OPT_RIVER_STATE_SERIES),
                          ("HB_OPT_RIVER_WAVE_BLOCKS", layout.OPT_RIVER_WAVE_BLOCKS),
+                         ("HB_OPT_RIVER_MCT_SERIES", layout.OPT_RIVER_MCT_SERIES),
                          ("HB_RIVER_PERSISTENT", layout.RIVER_PERSISTENT), ("HB_RIVER_LAUNCHES", layout.RIVER_LAUNCHES), ("HB_RIVER_GROUPED", layout.RIVER_GROUPED), ("HB_LAND_AUTO", layout.LAND_AUTO),
                          ("HB_LAND_GENERAL", layout.LAND_GENERAL), ("HB_NCCL_ID_BYTES", layout.NCCL_ID_BYTES),
                          ("HB_ENTRY_EXT", layout.ENTRY_EXT)):

@@ -110,3 +110,23 @@ def test_nan_forcing_is_handled_like_in_the_reference(engine):
         assert np.isnan(got.uz[affected]).all() and np.isfinite(got.uz[np.setdiff1d(np.arange(land.n_elem), affected)]).all()
         ok = ~np.isnan(qt)
         np.testing.assert_allclose(rows[ok], qt[ok], rtol=1e-9, atol=1e-12)
+
+
+def test_mct_series_need_a_request_and_musk_mct_reaches(engine):
+    """hb_get_mct_series: recorded only for the bits of HB_OPT_RIVER_MCT_SERIES and only when the river holds musk_mct
+    reaches — everything else is an error, never a buffer of zeros."""
+    land, states, river, discharge, forcing, doy = small()
+    engine.set_land(land); engine.set_land_states(states); engine.set_river(river); engine.set_river_states(discharge)
+    engine.set_forcing(forcing, doy)
+    engine.record_mct_series(("celerity",))
+    engine.run()
+    with pytest.raises(EngineError, match="was not recorded"):
+        engine.get_mct_series("celerity")              # musk_classic reaches only
+    with pytest.raises(EngineError, match="unknown sequence"):
+        engine._check(engine._lib.hb_get_mct_series(engine._h, 99, None), "hb_get_mct_series")
+    with pytest.raises(EngineError, match="invalid musk_mct series mask"):
+        engine._check(engine._lib.hb_set_option(engine._h, layout.OPT_RIVER_MCT_SERIES, 1 << len(layout.MCT_SERIES)),
+                      "hb_set_option")
+    with pytest.raises(ValueError, match="unknown musk_mct sequence"):
+        engine.record_mct_series(("discharge",))
+    engine.record_mct_series(())
