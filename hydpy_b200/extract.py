@@ -133,17 +133,55 @@ def _check_land_model(element: Any) -> None:
     for seq in (model.sequences.inputs.p, model.sequences.inputs.t, pet.sequences.inputs.normalairtemperature,
                 pet.sequences.inputs.normalevapotranspiration):
         if getattr(seq, "node2idx", None):
-            raise UnsupportedModelError(
-                f"element `{element.name}`: input sequence `{seq.name}` is fed by an input node, which the engine "
-                f"does not support yet"
-            )
+            continue                                  # fed by an input node: see `_input_series`
         if not seq.ramflag:
             raise RuntimeError(
                 f"element `{element.name}`: the time series of input sequence `{seq.name}` is not available in "
                 f"RAM (just-in-time NetCDF reading is not possible with the B200 engine)"
             )
-    if len(tuple(getattr(element, "outputs", ()))) or len(tuple(getattr(element, "inputs", ()))):
-        raise UnsupportedModelError(f"element `{element.name}`: input/output nodes are not supported")
+    if len(tuple(getattr(element, "outputs", ()))):
+        raise UnsupportedModelError(f"element `{element.name}`: output nodes are not supported")
+
+
+def _input_series(element: Any, seq: Any, i0: int, i1: int) -> np.ndarray:
+    """The values `load_data` hands to one input sequence during [i0, i1): its own series or, when an input node feeds it
+    (`inputflag`, ref: hydpy/cythons/modelutils.py:1080-1125 + hydpy/core/devicetools.py `Node.get_double("inputs")`),
+    what that node holds at each step.  Per deploy mode (ref: hydpy/core/hydpytools.py:2704-2722, 2726-2733):
+    `oldsim` → sim.series; `obs` → obs.series; `obs_oldsim` → obs.series where available, else sim.series; `newsim` /
+    `obs_newsim` → the node is reset to zero at every step (nothing inside the run feeds it), observations on top."""
+    nodes = list(getattr(seq, "node2idx", None) or ())
+    if not nodes:
+        return np.array(seq.series[i0:i1], dtype=np.float64)
+    if len(nodes) > 1:
+        raise UnsupportedModelError(
+            f"element `{element.name}`: input sequence `{seq.name}` is connected to {len(nodes)} nodes")
+    node = nodes[0]
+    if len(tuple(getattr(node, "entries", ()))):
+        raise UnsupportedModelError(
+            f"element `{element.name}`: input node `{node.name}` is fed by other elements within the run, which the "
+            f"B200 engine does not support")
+    mode = str(node.deploymode)
+    nt = i1 - i0
+
+    def series(name: str) -> np.ndarray:
+        sub = getattr(node.sequences, name)
+        if not sub.ramflag:
+            raise RuntimeError(f"input node `{node.name}`: the time series of `{name}` is not available in RAM")
+        return np.array(sub.series[i0:i1], dtype=np.float64)
+
+    if mode in ("oldsim", "oldsim_bi"):
+        return series("sim")
+    if mode in ("obs", "obs_bi"):
+        return series("obs")
+    if mode == "obs_oldsim":
+        obs = series("obs")
+        return np.where(np.isnan(obs), series("sim"), obs)
+    if mode == "newsim":
+        return np.zeros(nt)
+    if mode == "obs_newsim":
+        obs = series("obs")
+        return np.where(np.isnan(obs), 0.0, obs)
+    raise UnsupportedModelError(f"input node `{node.name}`: deploy mode `{mode}` is not supported")
 
 
 def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i1: int
@@ -298,10 +336,10 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         bw2_l.append(_f(sta.bw2, nz) if mname == "hland_96c" else zeros)
         inp = model.sequences.inputs
         pinp = pet.sequences.inputs
-        forcing[0, :, e] = inp.p.series[i0:i1]
-        forcing[1, :, e] = inp.t.series[i0:i1]
-        forcing[2, :, e] = pinp.normalairtemperature.series[i0:i1]
-        forcing[3, :, e] = pinp.normalevapotranspiration.series[i0:i1]
+        forcing[0, :, e] = _input_series(element, inp.p, i0, i1)
+        forcing[1, :, e] = _input_series(element, inp.t, i0, i1)
+        forcing[2, :, e] = _input_series(element, pinp.normalairtemperature, i0, i1)
+        forcing[3, :, e] = _input_series(element, pinp.normalevapotranspiration, i0, i1)
         this_doy = np.array(der.doy.value, dtype=np.int64)[i0:i1]
         if doy is None:
             doy = this_doy
@@ -591,6 +629,13 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
             _set_state(sta.bw1, states.bw1[z0:z1])
             _set_state(sta.bw2, states.bw2[z0:z1])
             _set_state(sta.lz, float(states.lz[e]))
+        # input sequences fed by nodes keep what they received (save_data, ref: modelutils.py:1127-1167)
+        pinp = model.aetmodel.petmodel.sequences.inputs
+        col = int(land.forcing_col[e])
+        for k, seq in enumerate((model.sequences.inputs.p, model.sequences.inputs.t, pinp.normalairtemperature,
+                                 pinp.normalevapotranspiration)):
+            if getattr(seq, "node2idx", None) and seq.ramflag:
+                seq.series[i0:i1] = problem.forcing[k, :, col]
         u0, u1 = int(land.uh_ptr[e]), int(land.uh_ptr[e + 1])
         if u1 > u0:
             if int(land.rconc[e]) == layout.RCONC_NASH:

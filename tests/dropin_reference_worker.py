@@ -55,7 +55,7 @@ def snapshot(hp):
         out[f"nodevalue:{node.name}"] = np.array(node.sequences.sim.value)
     for element in hp.elements:
         seqs = element.model.sequences
-        for group in ("factors", "fluxes", "states", "outlets"):
+        for group in ("inputs", "factors", "fluxes", "states", "outlets"):
             for seq in getattr(seqs, group, ()):
                 if getattr(seq, "ramflag", False):
                     out[f"{element.name}:{group}.{seq.name}:series"] = np.array(seq.series)
@@ -65,6 +65,11 @@ def snapshot(hp):
         rwd = getattr(getattr(seqs, "factors", None), "referencewaterdepth", None)
         if rwd is not None:
             out[f"{element.name}:referencewaterdepth"] = np.array(rwd.value)
+        pet = getattr(getattr(element.model, "aetmodel", None), "petmodel", None)
+        if pet is not None:
+            for seq in pet.sequences.inputs:
+                if getattr(seq, "ramflag", False):
+                    out[f"{element.name}:pet.inputs.{seq.name}:series"] = np.array(seq.series)
         rc = getattr(element.model, "rconcmodel", None)
         if rc is not None and rc.name == "rconc_uh":
             out[f"{element.name}:quh"] = np.array(rc.sequences.logs.quh.value)
@@ -169,6 +174,46 @@ with model.add_wqmodel_v1("wq_trapeze_strickler"):
     return hp, (("2000-01-01", "2000-01-04"), ("2000-01-04", "2000-01-09"))
 
 
+def add_input_nodes(hp):
+    """Feed three of the four meteorological inputs of two Lahn sub-basins through input nodes in different deploy
+    modes (ref: hydpy/core/devicetools.py `Element.inputs`, hydpy/core/modeltools.py:1533 `_connect_inputs`)."""
+    from hydpy import Element, Node, Nodes
+    from hydpy.models.evap.evap_inputs import NormalAirTemperature, NormalEvapotranspiration
+    from hydpy.models.hland.hland_inputs import P, T
+
+    nt = len(pub.timegrids.init)
+    rng = np.random.default_rng(11)
+    t_node, p_node = Node("t_dill", variable=T), Node("p_dill", variable=P)
+    nat_node, net_node = Node("nat_marb", variable=NormalAirTemperature), Node("net_marb", variable=NormalEvapotranspiration)
+    p2_node = Node("p_marb", variable=P)
+    Element("land_dill_assl", inputs=(t_node, p_node))
+    Element("land_lahn_marb", inputs=(nat_node, net_node, p2_node))
+    new = Nodes(t_node, p_node, nat_node, net_node, p2_node)
+    hp.update_devices(nodes=hp.nodes + new, elements=hp.elements)
+    for name in ("land_dill_assl", "land_lahn_marb"):
+        hp.elements[name].model.connect()
+    for node in new:
+        node.prepare_allseries()
+    with pub.options.checkseries(False):
+        t_node.deploymode = "oldsim"
+        t_node.sequences.sim.series = 4.0 * np.sin(np.arange(nt) / 9.0) + rng.normal(0.0, 1.0, nt)
+        p_node.deploymode = "obs"
+        p_node.sequences.obs.series = rng.gamma(0.5, 3.0, nt)
+        nat_node.deploymode = "obs_oldsim"
+        nat_node.sequences.sim.series = 1.0
+        gaps = rng.uniform(0.0, 6.0, nt)
+        gaps[rng.uniform(size=nt) < 0.4] = np.nan
+        nat_node.sequences.obs.series = gaps
+        net_node.deploymode = "obs_newsim"        # gaps fall back to the reset value 0.0
+        gaps = rng.uniform(0.0, 3.0, nt)
+        gaps[rng.uniform(size=nt) < 0.3] = np.nan
+        net_node.sequences.obs.series = gaps
+        p2_node.deploymode = "newsim"             # nothing feeds it: 0.0 at every step
+    # the elements' own series must be ignored from now on
+    hp.elements.land_dill_assl.model.sequences.inputs.t.series = 1e6
+    hp.elements.land_dill_assl.model.sequences.inputs.p.series = 1e6
+
+
 def main() -> None:
     del pub.projectname
     del pub.timegrids
@@ -184,6 +229,8 @@ def main() -> None:
             for group in ("factors", "fluxes", "states"):
                 for seq in getattr(seqs, group):
                     seq.prepare_series(allocate_ram=True)
+        if "--inputnodes" in sys.argv:
+            add_input_nodes(hp)
         # two consecutive simulation windows inside the initialisation period, as in hydpy/core/hydpytools.py:2804-2825
         windows = (("1996-01-01", "1996-02-01"), ("1996-02-01", "1996-03-01"))
 
@@ -206,6 +253,10 @@ def main() -> None:
                 for seq in getattr(element.model.sequences, group, ()):
                     if getattr(seq, "ramflag", False):
                         seq.series[:] = np.nan
+            pet = getattr(getattr(element.model, "aetmodel", None), "petmodel", None)
+            for seq in list(getattr(element.model.sequences, "inputs", ())) + list(pet.sequences.inputs if pet else ()):
+                if getattr(seq, "node2idx", None) and seq.ramflag:
+                    seq.series[:] = 1e6               # node-fed inputs: overwritten by what the node delivers
         snaps = []
         for first, last in windows:
             pub.timegrids.sim.firstdate = first

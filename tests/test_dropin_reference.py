@@ -28,3 +28,14 @@ def test_simulate_sibling_models_like_the_reference_does():
                           capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "DROPIN_OK" in proc.stdout
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+def test_simulate_with_input_nodes_like_the_reference_does():
+    """Meteorological inputs fed through input nodes (`Element.inputs`) in the deploy modes oldsim, obs, obs_oldsim,
+    obs_newsim and newsim: the same values reach the model, the input sequences keep them, the nodes end as in the
+    reference (ref: hydpy/core/hydpytools.py:2704-2733, hydpy/cythons/modelutils.py:1080-1167)."""
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_worker.py"), "--inputnodes"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "DROPIN_OK" in proc.stdout
