@@ -220,4 +220,28 @@ HB_HD double hb_pow(double x, double y, TabRef T) {
 #endif
 }
 
+// hb_pow(x, y) for a caller that already holds lgn = hb_log_normal(x): the same bits as hb_pow, without the second log
+HB_HD double hb_pow_from_log(double x, double lgn, double y, TabRef T) {
+  const bool ok_x = (unsigned)(hb_hi(x) - 0x00100000) < 0x7fe00000u;
+  const double t = y * lgn;
+  const double r = hb_exp_bounded(t, T);
+  if (ok_x && fabs(t) < 690.0) return r;
+#ifdef __CUDA_ARCH__
+  return hb_pow_slow(x, y);
+#else
+  return pow(x, y);
+#endif
+}
+
+// hb_log(x) from lgn = hb_log_normal(x)
+HB_HD double hb_log_from_normal(double x, double lgn) {
+  const bool ok_x = (unsigned)(hb_hi(x) - 0x00100000) < 0x7fe00000u;
+  if (ok_x) return lgn;
+#ifdef __CUDA_ARCH__
+  return hb_log_slow(x);
+#else
+  return log(x);
+#endif
+}
+
 }  // namespace hb

@@ -282,6 +282,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
   if (__all_sync(amask, soil && fc > 0.0) != SOIL) return;
   if (SOIL) {
     const bool f_icept = (zf & HB_ZF_INTERCEPTION) != 0, f_soil = (zf & HB_ZF_SOIL) != 0;
+    // hland_96: log(sm/fc) of the soil moisture at the end of a step serves the contributing area of that step AND the
+    // power function of Calc_R_SM_V1 of the next one (same argument, same bits as two evaluations)
+    double lgn = (MODEL == HB_MODEL_HLAND_96) ? hb_log_normal(sm * inv_fc, T) : 0.0;
     for (int t = 0; t < nt; ++t) {
       HB_ZONE_STEP_BEGIN
       // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
@@ -346,7 +349,8 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         SERZ(HB_S_EI, ei); SERZ(HB_S_IC, ic);
       }
       // ref: hland_model.py:1776-1790 Calc_R_SM_V1
-      double r = in_ * hb_pow(sm * inv_fc, beta, T);
+      double r = in_ * ((MODEL == HB_MODEL_HLAND_96) ? hb_pow_from_log(sm * inv_fc, lgn, beta, T)
+                                                     : hb_pow(sm * inv_fc, beta, T));
       {
         const double a2 = sm + in_ - fc;
         r = HB_PYMAX(r, a2);
@@ -390,7 +394,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         // (sm/fc)^weight, raised to beta, is evaluated as exp(beta * sum(weight * log(sm/fc))) — one log per zone-step here,
         // one exp per element-step in the element kernel instead of a pow (log + exp) per zone-step (-26 of 386 warp
         // instructions per zone-step); relative deviation from the product form <= 1e-14
-        const double contri = w_b * hb_log(sm * inv_fc, T);
+        const double x_end = sm * inv_fc;
+        lgn = hb_log_normal(x_end, T);
+        const double contri = w_b * hb_log_from_normal(x_end, lgn);
         HB_ZONE_STEP_END(w_a * (r - cf), resp ? contri : 0.0)
       } else if (MODEL == HB_MODEL_HLAND_96P) {
         double dp, rs, ri, gr1, rg1;
