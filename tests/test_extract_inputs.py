@@ -1,0 +1,82 @@
+"""Host logic of `hydpy_b200.extract` that needs no reference objects: what an input sequence receives from an input node
+in each deploy mode (ref: hydpy/core/hydpytools.py:2704-2733; the same cases run against real reference objects in
+tests/test_dropin_reference.py where the reference build exists) and which musk_mct series a project asks for."""
+import types
+
+import numpy as np
+import pytest
+
+from hydpy_b200 import layout
+from hydpy_b200.extract import UnsupportedModelError, _input_series, check_reach_series, requested_mct_series
+
+
+def seq(series=None, ramflag=True, nodes=(), name="t"):
+    return types.SimpleNamespace(series=None if series is None else np.asarray(series, dtype=float), ramflag=ramflag,
+                                 node2idx={n: None for n in nodes}, name=name)
+
+
+class Node:
+    def __init__(self, mode, sim=None, obs=None, entries=()):
+        self.name, self.deploymode, self.entries = "n", mode, entries
+        self.sequences = types.SimpleNamespace(sim=seq(sim, sim is not None), obs=seq(obs, obs is not None))
+
+
+ELEMENT = types.SimpleNamespace(name="land")
+SIM = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+OBS = np.array([10.0, np.nan, 30.0, np.nan, 50.0])
+
+
+def test_own_series_without_a_node():
+    assert np.array_equal(_input_series(ELEMENT, seq(SIM), 1, 4), SIM[1:4])
+
+
+@pytest.mark.parametrize("mode, expected", [
+    ("oldsim", SIM), ("oldsim_bi", SIM), ("obs", OBS), ("obs_bi", OBS),
+    ("obs_oldsim", np.array([10.0, 2.0, 30.0, 4.0, 50.0])),     # observations where available, else the old simulation
+    ("newsim", np.zeros(5)),                                     # reset at every step, nothing feeds the node
+    ("obs_newsim", np.array([10.0, 0.0, 30.0, 0.0, 50.0])),
+])
+def test_node_fed_input_per_deploy_mode(mode, expected):
+    node = Node(mode, sim=SIM, obs=OBS)
+    got = _input_series(ELEMENT, seq(np.full(5, 1e6), nodes=(node,)), 0, 5)     # the own series is ignored
+    assert np.array_equal(got, expected, equal_nan=True)
+    assert np.array_equal(_input_series(ELEMENT, seq(None, False, nodes=(node,)), 2, 4), expected[2:4], equal_nan=True)
+
+
+def test_node_fed_input_errors():
+    with pytest.raises(UnsupportedModelError, match="fed by other elements"):
+        _input_series(ELEMENT, seq(SIM, nodes=(Node("newsim", entries=("upstream",)),)), 0, 5)
+    with pytest.raises(UnsupportedModelError, match="connected to 2 nodes"):
+        _input_series(ELEMENT, seq(SIM, nodes=(Node("oldsim", sim=SIM), Node("obs", obs=OBS))), 0, 5)
+    with pytest.raises(UnsupportedModelError, match="deploy mode"):
+        _input_series(ELEMENT, seq(SIM, nodes=(Node("newsim_update", sim=SIM),)), 0, 5)
+    with pytest.raises(RuntimeError, match="not available in RAM"):
+        _input_series(ELEMENT, seq(SIM, nodes=(Node("oldsim"),)), 0, 5)
+
+
+class Group(types.SimpleNamespace):
+    """Sequence sub-group look-alike: attribute access by name, iteration over the sequences."""
+
+    def __iter__(self):
+        return iter(vars(self).values())
+
+
+def mct_element(ram):
+    groups = {"factors": Group(), "fluxes": Group(), "states": Group()}
+    for name in layout.MCT_SERIES + ("inflow", "outflow", "discharge"):
+        group = layout.MCT_SERIES_GROUP.get(name, "states" if name == "discharge" else
+                                            "fluxes" if name in ("inflow", "outflow") else "factors")
+        setattr(groups[group], name, types.SimpleNamespace(name=name, ramflag=name in ram))
+    return types.SimpleNamespace(name="reach", model=types.SimpleNamespace(name="musk_mct",
+                                                                           sequences=types.SimpleNamespace(**groups)))
+
+
+def test_requested_mct_series_follow_the_ramflags():
+    problem = types.SimpleNamespace(river_elements=[mct_element({"celerity", "courantnumber", "outflow"}),
+                                                    mct_element({"referencedischarge"})])
+    assert requested_mct_series(problem) == ["referencedischarge", "celerity", "courantnumber"]
+    check_reach_series(problem)                                  # every owned sequence is recordable
+    odd = mct_element({"celerity"})
+    odd.model.sequences.factors.froudenumber = types.SimpleNamespace(name="froudenumber", ramflag=True)
+    with pytest.raises(UnsupportedModelError, match="froudenumber"):
+        check_reach_series(types.SimpleNamespace(river_elements=[odd]))
