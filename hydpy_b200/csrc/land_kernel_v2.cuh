@@ -794,7 +794,9 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
     if (resp) contriarea = hb_exp(beta_last * logsum, T);
     // ref: hland_model.py:2456-2484 Calc_Q0_Perc_UZ_V1
     double perc_sum = 0.0, q0_sum = 0.0;
-    {
+    // an empty upper zone without recharge stays empty through all RecStep sub-steps (uz = max(0 + 0, 0), perc = q0 = 0,
+    // no error correction): dry spells skip the chain — the same bits, nothing to wait for
+    if (!(uz == 0.0 && inuz == 0.0)) {
       const double uz_old = uz;
       const double dt_inuz = dt * inuz;
       const double perc_pot = dt_percmax * contriarea;
@@ -840,7 +842,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         perc_sum *= factor;
         q0_sum *= factor;
       }
-    }
+    } else uz = 0.0;   // (-0.0 + 0.0 = +0.0 in the loop)
     // ref: hland_model.py:3113-3124 Calc_LZ_V1, 3724-3737 Calc_EL_LZ_AETModel_V1
     if (rellower > 0.0) {
       lz += up_low * perc_sum;
