@@ -349,8 +349,14 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         SERZ(HB_S_EI, ei); SERZ(HB_S_IC, ic);
       }
       // ref: hland_model.py:1776-1790 Calc_R_SM_V1
-      double r = in_ * ((MODEL == HB_MODEL_HLAND_96) ? hb_pow_from_log(sm * inv_fc, lgn, beta, T)
-                                                     : hb_pow(sm * inv_fc, beta, T));
+      double r;
+      if (MODEL == HB_MODEL_HLAND_96) {
+        // nothing reaches the soil of any zone of this warp (dry hour, or the canopy holds the rain back): in_ * pow(...)
+        // is in_ itself — 0.0 times a finite power (0 < sm/fc <= 1) — and the exp half of the power function can stay out
+        const double x = sm * inv_fc;
+        if (__all_sync(amask, in_ == 0.0 && x > 0.0 && x <= 1.0)) r = in_;
+        else r = in_ * hb_pow_from_log(x, lgn, beta, T);
+      } else r = in_ * hb_pow(sm * inv_fc, beta, T);
       {
         const double a2 = sm + in_ - fc;
         r = HB_PYMAX(r, a2);
