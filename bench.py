@@ -373,9 +373,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of one zone_kernel launch (240-step chunk, 10^5 x 12 zones) from the
-    # committed `ncu --set full` capture profiles/r01_s3b_summary.txt (0.41 GB read + 4.59 GB written); only valid for the
+    # committed `ncu --set full` capture profiles/r01_s3c_summary.txt (0.38 GB read + 4.59 GB written); only valid for the
     # default workload
-    traffic = 5.00e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
+    traffic = 4.97e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -405,9 +405,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             # what the hardware counters say about the same kernel (one `ncu --set full` capture of a steady-state window,
             # committed under profiles/): a pow/exp is ONE op in SURVEY's convention but ≈24/≈14 FP64 instructions, so the
             # pipe utilisation is the tighter statement about how close the kernel is to the FP64 roof
-            "ncu": {"sm__inst_executed_pipe_fp64_pct_of_peak": 64.0, "smsp__issue_active_pct": 73.3,
-                    "fp64_warp_instructions_per_zone_step": 140, "warp_instructions_per_zone_step": 321,
-                    "source": "profiles/r01_s3b_summary.txt (zone_kernel<1,0,0>, 3.47 ms under ncu)"} if traffic else None,
+            "ncu": {"sm__inst_executed_pipe_fp64_pct_of_peak": 62.9, "smsp__issue_active_pct": 72.5,
+                    "fp64_warp_instructions_per_zone_step": 133, "warp_instructions_per_zone_step": 300,
+                    "source": "profiles/r01_s3c_summary.txt (zone_kernel<1,0,0>, 3.28 ms under ncu)"} if traffic else None,
             "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
