@@ -386,6 +386,10 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             "river_levels": n_levels, "window_steps": win, "recstep_per_step": R, "uh_ordinates": U,
             "forcing_bank": 1024, "parallelism": f"element-sharded x{dist.world}" if dist.world > 1 else "single GPU",
             "l2": "per step 4.6 GB of zone terms + 0.4 GB of rows stream through HBM (> 126 MB L2); no flush needed",
+            "forcing": "synth.make_forcing (SURVEY config 3): gamma(0.3, 3)/24 mm of rain in every hour and column, "
+                       "fresh per window; the canopy holds most of it back, so about nine of ten warp-steps see no "
+                       "water at the soil and take the engine's exact shortcuts (no exp of Calc_R_SM's power, no "
+                       "RecStep chain for an empty upper zone: results unchanged bit for bit, see DESIGN.md section 4)",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
