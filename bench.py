@@ -44,7 +44,11 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("engine", "reference"), default="engine")
     ap.add_argument("--elements", type=int, default=100_000, help="hland_96 elements per GPU")
-    ap.add_argument("--window", type=int, default=240, help="simulation steps (hours) per bench step")
+    ap.add_argument("--window", type=int, default=438,
+                    help="simulation steps (hours) per bench step; 20 timed steps of 438 h span one year")
+    ap.add_argument("--forcing", choices=("storms", "dry"), default="storms",
+                    help="synthetic forcing (hydpy_b200.synth.make_forcing): 'storms' = event-based, humid water balance "
+                         "(default); 'dry' = round 1's hourly drizzle that never reaches the soil")
     ap.add_argument("--levels", type=int, default=200)
     ap.add_argument("--cpu-elements", type=int, default=0, help="element sample of the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,7 +257,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     pinned = eng.pinned((n_steps, 4, win, 1024))
     doys = np.zeros((n_steps, win), np.int64)
     for s in range(n_steps):
-        f, doys[s] = synth.make_forcing(win, "1h", seed=dist.rank, t0=s * win)
+        f, doys[s] = synth.make_forcing(win, "1h", seed=dist.rank, t0=s * win, kind=args.forcing)
         pinned.array[s] = f
     zone_steps_per_step = land.n_zone * win
     launches = 0
@@ -332,39 +336,78 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
 
     # ================= roofline of the dominant kernel ====================================================================
     # Discharge-only mode moves 40 B per element-step, so the bound is the FP64 pipe.
-    # Algorithmic work, SURVEY's convention (add/mul/cmp/div/pow/exp = 1 op each): 130 ops per zone-step in the
-    # thread-per-zone kernel, 14 R + 2 U + 32 ops per element-step in the thread-per-element kernel.
+    # Work in SURVEY's convention (add/mul/cmp/div/pow/exp = 1 op each): 130 ops per zone-step in the thread-per-zone
+    # kernel, 14 R + 2 U + 32 ops per element-step in the thread-per-element kernel — counted as EXECUTED: the device
+    # counters of the timed region (hb_get_timing) say how many element-steps ran the RecStep chain (6 ops per sub-step)
+    # and how many sub-steps had water in the upper zone (8 more ops, one of them the pow); skipped work does not count.
     fp64_peak = eng.measure_fp64_peak()
     peak_ops = fp64_peak / 2.0                                             # T FP64 instructions/s (an FMA = 1 op)
     R, U, Z = int(land.recstep[0]), int(land.uh_ptr[1] - land.uh_ptr[0]), land.n_zone / land.n_elem
-    zone_ops = 130.0 * land.n_zone * win
-    element_ops = (14.0 * R + 2.0 * U + 32.0) * land.n_elem * win
+    cnt = {k: float(tm[k]) / K for k in ("zone_warpsteps", "zone_warpsteps_dry", "zone_steps", "zone_steps_wet",
+                                        "elem_steps", "elem_steps_run", "substeps_pow")}
+    executed = {
+        "recstep_executed_frac": cnt["elem_steps_run"] / cnt["elem_steps"] if cnt["elem_steps"] else None,
+        "recstep_substeps_with_pow_frac": (cnt["substeps_pow"] / (R * cnt["elem_steps"])) if cnt["elem_steps"] and R else None,
+        "soil_input_frac": cnt["zone_steps_wet"] / cnt["zone_steps"] if cnt["zone_steps"] else None,
+        "dry_shortcut_warpstep_frac": cnt["zone_warpsteps_dry"] / cnt["zone_warpsteps"] if cnt["zone_warpsteps"] else None,
+    }
+    zone_ops_alg = 130.0 * land.n_zone * win
+    element_ops_alg = (14.0 * R + 2.0 * U + 32.0) * land.n_elem * win
+    # executed: a zone-step of a dry warp-step leaves out the exp half of its pow (still one op: not subtracted);
+    # the element kernel executes 6 ops per sub-step of a running chain and 8 more where uz > 0
+    zone_ops = zone_ops_alg
+    element_ops = (2.0 * U + 32.0) * land.n_elem * win + 6.0 * R * cnt["elem_steps_run"] + 8.0 * cnt["substeps_pow"]
     land_ms_avg, zone_ms_avg, element_ms_avg = float(np.mean(land_ms)), float(np.mean(zone_ms)), float(np.mean(element_ms))
     general_ms_avg = float(np.mean(general_ms))
 
     def tops(ops: float, ms: float) -> float:
         return ops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
 
+    # hardware counters of the same kernels (ncu --set full of one steady-state window of THIS workload), written by
+    # tools/ncu_summary.py json into profiles/; absent or for another workload: null
+    ncu = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_kernels.json")) as f:
+            rec = json.load(f)
+        if rec.get("workload") == {"elements": land.n_elem, "zones": land.n_zone, "window": win, "forcing": args.forcing}:
+            ncu = rec
+    except (OSError, ValueError):
+        pass
+
+    def ncu_of(kernel: str, key: str):
+        return ncu["kernels"].get(kernel, {}).get(key) if ncu else None
+
     kernels = {
         "zone_kernel": {"ms": zone_ms_avg, "ops_per_launch": zone_ops, "achieved": tops(zone_ops, zone_ms_avg),
                         "frac": tops(zone_ops, zone_ms_avg) / peak_ops,
                         "ms_alone": iso["zone_ms"], "frac_alone": tops(zone_ops, iso["zone_ms"]) / peak_ops,
-                        "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 40 * land.n_elem * win},
+                        "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 40 * land.n_elem * win,
+                        "ncu_fp64_pipe_pct": ncu_of("zone_kernel", "fp64_pipe_pct"),
+                        "ncu_dram_bytes": ncu_of("zone_kernel", "dram_bytes")},
         "element_kernel": {"ms": element_ms_avg, "ops_per_launch": element_ops,
+                           "ops_per_launch_algorithmic": element_ops_alg,
                            "achieved": tops(element_ops, element_ms_avg),
                            "frac": tops(element_ops, element_ms_avg) / peak_ops,
                            "ms_alone": iso["element_ms"], "frac_alone": tops(element_ops, iso["element_ms"]) / peak_ops,
-                           "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win},
+                           "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win,
+                           "ncu_fp64_pipe_pct": ncu_of("element_kernel", "fp64_pipe_pct"),
+                           "ncu_dram_bytes": ncu_of("element_kernel", "dram_bytes")},
         "land_kernel (general)": {"ms": general_ms_avg},
         "routing (reach_head + reach_bulk + reach_wave kernels)": {
             "ms": float(np.mean(river_ms)), "ms_alone": iso["river_ms"],
             "algorithmic_bytes_per_step": 16 * river.n_reach * win + 8 * (river.n_node + land.n_elem) * win},
     }
-    dominant = "zone_kernel" if n_fast else "land_kernel (general)"
-    dom_ms = zone_ms_avg if n_fast else general_ms_avg
-    dom_ops = zone_ops if n_fast else zone_ops + element_ops
+    # dominant kernel = the one with the larger share of the step
+    if not n_fast:
+        dominant, dom_ms, dom_ops = "land_kernel (general)", general_ms_avg, zone_ops + element_ops
+        dom_bytes = 40 * land.n_elem * win
+    elif element_ms_avg > zone_ms_avg:
+        dominant, dom_ms, dom_ops = "element_kernel", element_ms_avg, element_ops
+        dom_bytes = kernels["element_kernel"]["algorithmic_bytes_per_launch"]
+    else:
+        dominant, dom_ms, dom_ops = "zone_kernel", zone_ms_avg, zone_ops
+        dom_bytes = kernels["zone_kernel"]["algorithmic_bytes_per_launch"]
     achieved_tops = tops(dom_ops, dom_ms)
-    dom_bytes = kernels["zone_kernel"]["algorithmic_bytes_per_launch"] if n_fast else 40 * land.n_elem * win
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -372,10 +415,13 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dram__bytes_read.sum + dram__bytes_write.sum of one zone_kernel launch (240-step chunk, 10^5 x 12 zones) from the
-    # committed `ncu --set full` capture profiles/r01_s3c_summary.txt (0.38 GB read + 4.59 GB written); only valid for the
-    # default workload
-    traffic = 4.97e9 if (n_fast == 100_000 and win == 240 and land.n_zone == 1_200_000) else None
+    forcing_note = {
+        "storms": "synth.make_forcing(kind='storms'): per day and bank column a Gamma(0.3, 8) mm depth in an event of 1-6 "
+                  "wet hours, seasonal temperature and evapotranspiration (P 880 mm/a against 580 mm/a potential "
+                  "evapotranspiration: the humid balance of the Lahn basin); the timed steps cover one year",
+        "dry": "synth.make_forcing(kind='dry'), round 1's forcing: gamma(0.3, 3)/24 mm of rain in every hour, all of it "
+               "evaporated from the canopy - the upper zone stays empty and the kernels take their exact dry shortcuts",
+    }[args.forcing]
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -383,13 +429,12 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         "config": {
             "workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, hourly, discharge-only",
             "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
-            "river_levels": n_levels, "window_steps": win, "recstep_per_step": R, "uh_ordinates": U,
+            "river_levels": n_levels, "window_steps": win, "simulated_days_timed": K * win / 24.0,
+            "recstep_per_step": R, "uh_ordinates": U,
             "forcing_bank": 1024, "parallelism": f"element-sharded x{dist.world}" if dist.world > 1 else "single GPU",
-            "l2": "per step 4.6 GB of zone terms + 0.4 GB of rows stream through HBM (> 126 MB L2); no flush needed",
-            "forcing": "synth.make_forcing (SURVEY config 3): gamma(0.3, 3)/24 mm of rain in every hour and column, "
-                       "fresh per window; the canopy holds most of it back, so about nine of ten warp-steps see no "
-                       "water at the soil and take the engine's exact shortcuts (no exp of Calc_R_SM's power, no "
-                       "RecStep chain for an empty upper zone: results unchanged bit for bit, see DESIGN.md section 4)",
+            "l2": "per step the zone terms (16 B per zone-step) and the node/reach rows stream through HBM "
+                  "(> 126 MB L2); no flush needed",
+            "forcing": forcing_note, **executed,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
@@ -399,19 +444,18 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
                                "note": "the two run on different streams and overlap across windows (hb_run_async)"},
         "roofline": {
             "bound": "fp64", "achieved": achieved_tops, "peak": peak_ops, "unit": "Top/s (FP64 ops, FMA = 1)",
-            "frac": achieved_tops / peak_ops, "traffic": traffic,
-            "frac_alone": (kernels["zone_kernel"]["frac_alone"] if n_fast else None),
+            "frac": achieved_tops / peak_ops,
+            "traffic": kernels[dominant].get("ncu_dram_bytes") if dominant in kernels else None,
+            "frac_alone": (kernels[dominant]["frac_alone"] if n_fast else None),
             "kernel": dominant, "ops_per_launch": dom_ops,
+            "ops": "EXECUTED operations in SURVEY.md section 8d's convention, from the device counters of the timed "
+                   "region (config.recstep_executed_frac …); a pow counts as one op but costs about 35 FP64 "
+                   "instructions, so ncu's FP64-pipe utilisation (kernels.*.ncu_fp64_pipe_pct) is the tighter figure",
             "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
             "note": "ms/frac: CUDA events inside the timed, pipelined region (routing of the previous window shares the "
                     "SMs); ms_alone/frac_alone: the same kernels in synchronous windows right after it",
             "fp64_tflops_measured": fp64_peak,
-            # what the hardware counters say about the same kernel (one `ncu --set full` capture of a steady-state window,
-            # committed under profiles/): a pow/exp is ONE op in SURVEY's convention but ≈24/≈14 FP64 instructions, so the
-            # pipe utilisation is the tighter statement about how close the kernel is to the FP64 roof
-            "ncu": {"sm__inst_executed_pipe_fp64_pct_of_peak": 62.9, "smsp__issue_active_pct": 72.5,
-                    "fp64_warp_instructions_per_zone_step": 133, "warp_instructions_per_zone_step": 300,
-                    "source": "profiles/r01_s3c_summary.txt (zone_kernel<1,0,0>, 3.28 ms under ncu)"} if traffic else None,
+            "ncu_source": ncu.get("source") if ncu else None,
             "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
@@ -443,7 +487,7 @@ def cpu_run(args: argparse.Namespace, steps: int, warmup: int, elements: int) ->
     zone_steps = land.n_zone * win
     times = []
     for s in range(warmup + steps):
-        forcing, doy = synth.make_forcing(win, "1h", seed=0, t0=s * win)
+        forcing, doy = synth.make_forcing(win, "1h", seed=0, t0=s * win, kind=args.forcing)
         if kind == "reference":
             if s == 0:
                 els = refdriver.prepare_land(land, states, forcing, doy)   # object set-up (once) is not timed

@@ -59,6 +59,9 @@ class hb_timing(C.Structure):
         ("land_launches", C.c_int64), ("river_launches", C.c_int64), ("n_levels", C.c_int64),
         ("zone_ms", C.c_double), ("element_ms", C.c_double), ("general_ms", C.c_double), ("n_fast", C.c_int64),
         ("n_runs", C.c_int64),
+        ("zone_warpsteps", C.c_int64), ("zone_warpsteps_dry", C.c_int64), ("zone_steps", C.c_int64),
+        ("zone_steps_wet", C.c_int64), ("elem_steps", C.c_int64), ("elem_steps_run", C.c_int64),
+        ("substeps_pow", C.c_int64),
     ]
 
 

@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhydpy_b200.so")
 SOURCES = ("engine.cu",)
-DEPENDS = ("engine.cu", "land_kernel.cuh", "river_kernel.cuh", os.path.join("..", "..", "include", "hydpy_b200.h"))
+DEPENDS = ("engine.cu", "land_kernel.cuh", "land_kernel_v2.cuh", "land_kernel_coupled.cuh", "fastmath.cuh",
+           "river_kernel.cuh", os.path.join("..", "..", "include", "hydpy_b200.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -159,6 +159,7 @@ struct hb_engine {
   int general_key = -1;
   DBuf<int32_t> d_coupled_list, d_general_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
+  DBuf<unsigned long long> d_counters;   // HB_CNT_*: what the fast-path kernels executed since the last hb_get_timing
   DBuf<double> d_series_stage[HB_S_FIRST_ELEM];   // chunk-local staging of the zone/snow series (fast path)
   DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
   DBuf<int64_t> d_zone_cell0, d_snow_cell0;       // [E_pad+1] first ABI cell of every element
@@ -351,6 +352,12 @@ int hb_create(int device, hb_engine** out) {
       return HB_ECUDA;
     }
   }
+  if (h->d_counters.reserve(HB_CNT_COUNT) != cudaSuccess ||
+      cudaMemset(h->d_counters.p, 0, HB_CNT_COUNT * sizeof(unsigned long long)) != cudaSuccess) {
+    g_create_error = "hb_create: cannot allocate the work counters";
+    hb_destroy(h);
+    return HB_ECUDA;
+  }
   *out = h;
   return HB_OK;
 }
@@ -421,8 +428,12 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   HB_REQUIRE(h, ne == 0 || (d->zone_ptr && d->snow_ptr && d->sfdist_ptr && d->uh_ptr && d->sred_ptr && d->recstep &&
                             d->eflags && d->forcing_col && d->epar && d->zpar && d->zonetype && d->zflags && d->zorder),
              HB_EINVAL, "hb_set_land: NULL array in description");
+  // device states survive a new parameter set only if every element keeps its slots: same zones, snow cells and
+  // unit-hydrograph ordinates per element (the layout is [zmax|cmax|umax][E_pad])
   const bool same_structure = h->have_land && h->n_elem == ne && h->n_zone == d->n_zone && h->n_snow == d->n_snow &&
-                              h->n_uh == d->n_uh;
+                              h->n_uh == d->n_uh && std::equal(h->zone_ptr.begin(), h->zone_ptr.end(), d->zone_ptr) &&
+                              std::equal(h->snow_ptr.begin(), h->snow_ptr.end(), d->snow_ptr) &&
+                              std::equal(h->uh_ptr.begin(), h->uh_ptr.end(), d->uh_ptr);
   int zmax = 1, cmax = 1, umax = 1;
   for (int64_t e = 0; e < ne; ++e) {
     const int64_t nz = d->zone_ptr[e + 1] - d->zone_ptr[e], nc = d->sfdist_ptr[e + 1] - d->sfdist_ptr[e],
@@ -774,10 +785,11 @@ int hb_get_land_states(hb_engine* h, hb_land_states* st) {
     std::vector<double> zx1, zx2, ex1, ex2;
     if (h->any_sibling) {
       zx1.resize(zs); zx2.resize(zs); ex1.resize(ep); ex2.resize(ep);
-      HB_CUDA(h, cudaMemcpy(zx1.data(), h->d_zx1.p, zs * sizeof(double), cudaMemcpyDeviceToHost));
-      HB_CUDA(h, cudaMemcpy(zx2.data(), h->d_zx2.p, zs * sizeof(double), cudaMemcpyDeviceToHost));
-      HB_CUDA(h, cudaMemcpy(ex1.data(), h->d_ex1.p, ep * sizeof(double), cudaMemcpyDeviceToHost));
-      HB_CUDA(h, cudaMemcpy(ex2.data(), h->d_ex2.p, ep * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpyAsync(zx1.data(), h->d_zx1.p, zs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(zx2.data(), h->d_zx2.p, zs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(ex1.data(), h->d_ex1.p, ep * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(ex2.data(), h->d_ex2.p, ep * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      HB_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     for (int64_t e = 0; e < ne; ++e) {
       const int m = h->h_model[e];
@@ -1320,6 +1332,7 @@ static int run_land(hb_engine* h) {
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
     v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow;
+    v.counters = h->d_counters.p;
     v.nash_stage = h->any_nash ? 1 : 0;
     const size_t esmem = h->any_nash ? (size_t)HB_NASH_STAGE * 64 * sizeof(double) : 0;
     v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
@@ -1815,6 +1828,20 @@ int hb_timer_stop(hb_engine* h, double* ms) {
 int hb_get_timing(hb_engine* h, hb_timing* out) {
   if (!h || !out) return HB_EINVAL;
   if (h->pending) { int rc = hb_wait(h); if (rc) return rc; }
+  {
+    unsigned long long c[HB_CNT_COUNT];
+    HB_CUDA(h, cudaSetDevice(h->device));
+    HB_CUDA(h, cudaMemcpyAsync(c, h->d_counters.p, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof c, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->timing.zone_warpsteps = (int64_t)c[HB_CNT_ZONE_WARPSTEPS];
+    h->timing.zone_warpsteps_dry = (int64_t)c[HB_CNT_ZONE_WARPSTEPS_DRY];
+    h->timing.zone_steps = (int64_t)c[HB_CNT_ZONE_STEPS];
+    h->timing.zone_steps_wet = (int64_t)c[HB_CNT_ZONE_STEPS_WET];
+    h->timing.elem_steps = (int64_t)c[HB_CNT_ELEM_STEPS];
+    h->timing.elem_steps_run = (int64_t)c[HB_CNT_ELEM_STEPS_RUN];
+    h->timing.substeps_pow = (int64_t)c[HB_CNT_SUBSTEPS_POW];
+  }
   *out = h->timing;
   // sums restart with the next run
   const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast;
@@ -2030,12 +2057,13 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
   HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || ext_rows), HB_EINVAL,
              "hb_comm_recv_ext: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
+  for (int64_t i = 0; i < n; ++i)   // (before the group opens: no error path may leave it open)
+    HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row %d out of range", ext_rows[i]);
   HB_CUDA(h, h->d_ext_rows[h->cur].reserve((size_t)h->n_ext * h->nt));
   // the routing of two windows ago was the last reader of this buffer set
   HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
   HB_NCCL(h, h->nccl.GroupStart());
   for (int64_t i = 0; i < n; ++i) {
-    HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row out of range");
     // received straight into the external-row buffer the reach kernels read
     HB_NCCL(h, h->nccl.Recv(h->d_ext_rows[h->cur].p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
                             h->s_comm));

@@ -76,7 +76,19 @@ struct LandV2Dev {
   double* zx2;             // [zmax][E_pad] hland_96p sg1 | hland_96c bw2
   double* ex1;             // [E_pad] hland_96p sg2
   double* ex2;             // [E_pad] hland_96p sg3
+  // what the kernels actually executed (hb_get_timing): see enum below; one atomicAdd per warp and counter at kernel end
+  unsigned long long* counters;
 };
+
+// slots of LandV2Dev::counters
+enum { HB_CNT_ZONE_WARPSTEPS = 0,   // warp-steps of the branch-free (FIELD/FOREST) zone step
+       HB_CNT_ZONE_WARPSTEPS_DRY,   // … that took the dry shortcut (no water at the soil of any of the 32 zones)
+       HB_CNT_ZONE_STEPS,           // zone-steps of those warps (active lanes)
+       HB_CNT_ZONE_STEPS_WET,       // … with in_ > 0 (water reaches the soil: Calc_R_SM_V1 pays for its power function)
+       HB_CNT_ELEM_STEPS,           // element-steps of the element kernel (hland_96)
+       HB_CNT_ELEM_STEPS_RUN,       // … that ran the RecStep chain of Calc_Q0_Perc_UZ_V1
+       HB_CNT_SUBSTEPS_POW,         // RecStep sub-steps with uz > 0 (a pow each), per element
+       HB_CNT_COUNT };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
   const double* src = reinterpret_cast<const double*>(g);
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
     // hland_96: log(sm/fc) of the soil moisture at the end of a step serves the contributing area of that step AND the
     // power function of Calc_R_SM_V1 of the next one (same argument, same bits as two evaluations)
     double lgn = (MODEL == HB_MODEL_HLAND_96) ? hb_log_normal(sm * inv_fc, T) : 0.0;
+    unsigned n_dry = 0, n_wet = 0;   // warp-uniform: dry warp-steps, lanes with in_ > 0 (summed over the steps)
     for (int t = 0; t < nt; ++t) {
       HB_ZONE_STEP_BEGIN
       // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
@@ -354,7 +367,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         // nothing reaches the soil of any zone of this warp (dry hour, or the canopy holds the rain back): in_ * pow(...)
         // is in_ itself — 0.0 times a finite power (0 < sm/fc <= 1) — and the exp half of the power function can stay out
         const double x = sm * inv_fc;
-        if (__all_sync(amask, in_ == 0.0 && x > 0.0 && x <= 1.0)) r = in_;
+        const unsigned none = __ballot_sync(amask, in_ == 0.0);   // (in_ >= 0 or NaN: every other lane counts as wet)
+        n_wet += __popc(amask ^ none);
+        if (none == amask && __all_sync(amask, x > 0.0 && x <= 1.0)) { r = in_; ++n_dry; }
         else r = in_ * hb_pow_from_log(x, lgn, beta, T);
       } else r = in_ * hb_pow(sm * inv_fc, beta, T);
       {
@@ -418,6 +433,12 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
     }
     d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
     if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
+    if (MODEL == HB_MODEL_HLAND_96 && d.counters && (threadIdx.x & 31) == __ffs(amask) - 1) {
+      atomicAdd(d.counters + HB_CNT_ZONE_WARPSTEPS, (unsigned long long)nt);
+      atomicAdd(d.counters + HB_CNT_ZONE_WARPSTEPS_DRY, (unsigned long long)n_dry);
+      atomicAdd(d.counters + HB_CNT_ZONE_STEPS, (unsigned long long)nt * __popc(amask));
+      atomicAdd(d.counters + HB_CNT_ZONE_STEPS_WET, (unsigned long long)n_wet);
+    }
     return;
   }
 
@@ -684,6 +705,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   double sg2 = 0.0, sg3 = 0.0;
   if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
   const int64_t tstride = (int64_t)d.zmax * ep;
+  unsigned n_run = 0, n_pow = 0;   // element-steps that ran the RecStep chain, sub-steps with uz > 0
   for (int64_t t = 0; t < d.nt; ++t) {
     const double* ta = d.term_a + t * tstride + e;
     const double* tb = d.term_b + t * tstride + e;
@@ -803,6 +825,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
     // an empty upper zone without recharge stays empty through all RecStep sub-steps (uz = max(0 + 0, 0), perc = q0 = 0,
     // no error correction): dry spells skip the chain — the same bits, nothing to wait for
     if (!(uz == 0.0 && inuz == 0.0)) {
+      ++n_run;
       const double uz_old = uz;
       const double dt_inuz = dt * inuz;
       const double perc_pot = dt_percmax * contriarea;
@@ -821,6 +844,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
             const double q0 = HB_PYMIN(q, uz);
             uz -= q0;
             q0_sum += q0;
+            ++n_pow;
           }
         }
       } else {
@@ -839,6 +863,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
             } else q0 = uz;
             uz -= q0;
             q0_sum += q0;
+            ++n_pow;
           }
         }
       }
@@ -884,6 +909,15 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   d.uz[e] = uz;
   d.lz[e] = lz;
   if (MODEL == HB_MODEL_HLAND_96P) { d.ex1[e] = sg2; d.ex2[e] = sg3; }
+  if (MODEL == HB_MODEL_HLAND_96 && d.counters) {
+    const unsigned m = __activemask();
+    const unsigned run = __reduce_add_sync(m, n_run), pw = __reduce_add_sync(m, n_pow);
+    if ((threadIdx.x & 31) == __ffs(m) - 1) {
+      atomicAdd(d.counters + HB_CNT_ELEM_STEPS, (unsigned long long)d.nt * __popc(m));
+      atomicAdd(d.counters + HB_CNT_ELEM_STEPS_RUN, (unsigned long long)run);
+      atomicAdd(d.counters + HB_CNT_SUBSTEPS_POW, (unsigned long long)pw);
+    }
+  }
 }
 
 }  // namespace hb

@@ -407,6 +407,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
         if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
       }
     if (!__all_sync(full, ok)) return false;
+    __syncwarp();     // acquire side: the polling lane's ld.acquire is ordered before every lane's loads below
     if (lane < S) {   // through L2: the previous chunk may have been written by another SM
       st_in = __ldcg(dis_old + g0 + lane);
       st_out = __ldcg(dis_old + g0 + lane + 1);
@@ -421,6 +422,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       }
     }
     if (!__all_sync(full, ok)) return false;
+    __syncwarp();
   } else if (lane < S) {
     st_in = dis_old[g0 + lane];
     st_out = dis_old[g0 + lane + 1];

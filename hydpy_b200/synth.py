@@ -179,21 +179,60 @@ def to_sibling(land: LandBundle, states: LandStates, model: str, step: str = "1h
     land.normalise()
 
 
-def make_forcing(nt: int, step: str = "1h", *, bank: int = 1024, seed: int = 0, t0: int = 0
+#: mean daily precipitation depth of the "storms" forcing = 0.3 * STORM_SCALE mm (Gamma(shape 0.3) keeps the survey's
+#: wet-day statistics; the scale puts the annual sum at ≈ 880 mm against ≈ 600 mm of potential evapotranspiration, the
+#: humid balance of the Lahn basin the parameters come from)
+STORM_SCALE = 8.0
+
+
+def make_forcing(nt: int, step: str = "1h", *, bank: int = 1024, seed: int = 0, t0: int = 0, kind: str = "storms"
                  ) -> tuple[np.ndarray, np.ndarray]:
     """Forcing bank [4, nt, bank] + doy[nt] for steps t0 … t0+nt-1.
 
-    Each window is seeded with (seed, window start), so consecutive windows are reproducible independently.
+    kind = "storms" (default): every DAY draws, per bank column, a precipitation depth ~ Gamma(0.3, STORM_SCALE) mm, an
+    event of 1-6 consecutive wet hours inside the day that carries it (hourly step), a temperature anomaly ~ N(0, 3) K on
+    top of the seasonal normal 8 + 10 sin(2 pi doy / 365) °C (plus a diurnal cycle of ±3 K in hourly runs), and a seasonal
+    normal evapotranspiration of 1.6 + 1.3 sin(2 pi doy / 365) mm/d.  Days are seeded with (seed, day), so any window of
+    any length reproduces the same series.
+    kind = "dry": the first round's forcing — an independent Gamma(0.3, 3)/24 drizzle in every hour, which the canopy
+    evaporates completely (0.9 mm/d against 2 mm/d of potential evapotranspiration: a basin in terminal drought).
     """
     per_day = 24 if step == "1h" else 1
-    rng = np.random.default_rng([seed, t0])
     steps = np.arange(t0, t0 + nt)
     day = steps // per_day
     doy = (day % 365).astype(np.int64)
-    p = rng.gamma(0.3, 3.0, size=(nt, bank)) / per_day
-    t = 8.0 + 10.0 * np.sin(2.0 * np.pi * doy / 365.0)[:, None] + rng.normal(0.0, 3.0, size=(nt, bank))
-    nat = np.full((nt, bank), 8.0)
-    net = np.full((nt, bank), 2.0 / per_day)
+    if kind == "dry":
+        rng = np.random.default_rng([seed, t0])
+        p = rng.gamma(0.3, 3.0, size=(nt, bank)) / per_day
+        t = 8.0 + 10.0 * np.sin(2.0 * np.pi * doy / 365.0)[:, None] + rng.normal(0.0, 3.0, size=(nt, bank))
+        nat = np.full((nt, bank), 8.0)
+        net = np.full((nt, bank), 2.0 / per_day)
+        return np.stack([p, t, nat, net]), doy
+    if kind != "storms":
+        raise ValueError(f"unknown forcing kind {kind!r}")
+    season = np.sin(2.0 * np.pi * doy / 365.0)
+    p = np.zeros((nt, bank))
+    t = np.zeros((nt, bank))
+    hour = steps % per_day
+    for d in range(int(day[0]) if nt else 0, int(day[-1]) + 1 if nt else 0):
+        rng = np.random.default_rng([seed, 7919, d])
+        depth = rng.gamma(0.3, STORM_SCALE, size=bank)
+        dur = rng.integers(1, 7, size=bank)
+        start = (rng.uniform(size=bank) * (per_day - dur + 1)).astype(np.int64)
+        anomaly = rng.normal(0.0, 3.0, size=bank)
+        rows = np.nonzero(day == d)[0]
+        if per_day == 1:
+            p[rows] = depth
+        else:
+            h = hour[rows][:, None]
+            wet = (h >= start[None, :]) & (h < (start + dur)[None, :])
+            p[rows] = np.where(wet, (depth / dur)[None, :], 0.0)
+        t[rows] = anomaly[None, :]
+    diurnal = 3.0 * np.sin(2.0 * np.pi * (hour - 9.0) / 24.0) if per_day > 1 else np.zeros(nt)
+    normal_t = 8.0 + 10.0 * season
+    t += (normal_t + diurnal)[:, None]
+    nat = np.repeat(normal_t[:, None], bank, axis=1)
+    net = np.repeat(((1.6 + 1.3 * season) / per_day)[:, None], bank, axis=1)
     return np.stack([p, t, nat, net]), doy
 
 

@@ -414,6 +414,14 @@ typedef struct hb_timing {
   double general_ms;       /* runoff generation, general kernel (elements the fast path does not cover, or series)  */
   int64_t n_fast;          /* land elements on the fast path in the last hb_run                                     */
   int64_t n_runs;          /* hb_run / hb_run_async calls the sums above cover                                      */
+  /* what the fast-path kernels of hland_96 EXECUTED (device counters; the kernels take exact shortcuts in dry spells):  */
+  int64_t zone_warpsteps;      /* warp-steps (32 zones x 1 step) of the branch-free FIELD/FOREST zone step               */
+  int64_t zone_warpsteps_dry;  /* ... in which no zone receives water at the soil (no exp of Calc_R_SM_V1's power)       */
+  int64_t zone_steps;          /* zone-steps of those warps                                                             */
+  int64_t zone_steps_wet;      /* ... with in_ > 0                                                                      */
+  int64_t elem_steps;          /* element-steps of the element kernel                                                   */
+  int64_t elem_steps_run;      /* ... that ran the RecStep chain of Calc_Q0_Perc_UZ_V1 (not: uz == 0 and inuz == 0)     */
+  int64_t substeps_pow;        /* RecStep sub-steps with uz > 0, i.e. with a pow (of recstep * elem_steps_run)          */
 } hb_timing;
 /* Times and launch counts are SUMS over all runs since the previous hb_get_timing call (which resets them); after a
  * single hb_run they are that run's figures.  Waits for pending asynchronous work. */

@@ -11,8 +11,11 @@ The reference is Python + generated Cython.  This recip
    ``masterinterface``, and ``Cythonizer.pyxwriter.write()`` for the nine hot-path model modules) and
    compiles the generated sources with the reference's own flags (``-O2``; ``cdivision``/``cpow`` etc.
    come from the directives the generator writes into each ``.pyx``),
-4. copies ONLY the resulting shared objects into ``oracle/_ref/hydpy/cythons/autogen/`` (git-ignored,
-   not gpurun-ignored → they travel to the GPU box).  No reference source file enters the repo.
+4. copies the resulting shared objects into ``oracle/_ref/hydpy/cythons/autogen/`` and — like ``pip install --target``
+   would — the reference's Python package beside them (``oracle/_ref/hydpy``, plus the stubs in ``oracle/_ref/_stubs``),
+   so that ``oracle/_ref`` is an importable installation of the unmodified reference.  The directory is git-ignored,
+   not gpurun-ignored: it travels to the GPU box, where the ``-m gpu`` drop-in tests run ``HydPy.simulate`` of real
+   reference objects against the engine.  No reference file enters the repository's history.
 
 The scratch copy (default ``/tmp/hydpy_b200_refbuild/src``) stays importable in THIS container and is what
 ``tests/golden/make_golden.py`` uses to generate the committed fixtures.
@@ -132,6 +135,48 @@ def scratch_paths(scratch: str = DEFAULT_SCRATCH) -> tuple[str, str]:
     return os.path.join(scratch, "src"), os.path.join(scratch, "stubs")
 
 
+INSTALL = os.path.join(HERE, "_ref")
+INSTALL_STUBS = os.path.join(INSTALL, "_stubs")
+
+
+def installed() -> bool:
+    """True when oracle/_ref holds the importable installation (Python package + binaries), here or on the GPU box."""
+    return os.path.exists(os.path.join(INSTALL, "hydpy", "__init__.py")) and os.path.isdir(INSTALL_STUBS) and any(
+        n.startswith("c_hland_96.") and n.endswith(".so") for n in os.listdir(OUT))
+
+
+def import_paths() -> tuple[str, str] | None:
+    """(package root, stubs) to put in front of sys.path for `import hydpy`: the installation in oracle/_ref when it is
+    complete, else the scratch build of this container, else None."""
+    if installed():
+        return INSTALL, INSTALL_STUBS
+    src, stubs = scratch_paths()
+    if os.path.exists(os.path.join(os.path.dirname(src), ".built")):
+        return src, stubs
+    return None
+
+
+def install_package(src: str, stubs: str) -> None:
+    """Copy the reference's Python package (no generated C, no build leftovers) and the stubs next to the binaries."""
+    skip = shutil.ignore_patterns("*.c", "*.cpp", "*.pyx", "*.html", "*.so", "*.o", "__pycache__", "build", "build_tmp",
+                                  "_build", "html_")
+    pkg = os.path.join(INSTALL, "hydpy")
+    binaries = {n: os.path.join(OUT, n) for n in os.listdir(OUT) if n.endswith(".so")} if os.path.isdir(OUT) else {}
+    tmp = os.path.join(INSTALL, "_hydpy_new")
+    if os.path.isdir(tmp):
+        shutil.rmtree(tmp)
+    shutil.copytree(os.path.join(src, "hydpy"), tmp, ignore=skip, symlinks=False)
+    os.makedirs(os.path.join(tmp, "cythons", "autogen"), exist_ok=True)
+    for name, path in binaries.items():
+        shutil.copy2(path, os.path.join(tmp, "cythons", "autogen", name))
+    if os.path.isdir(pkg):
+        shutil.rmtree(pkg)
+    os.rename(tmp, pkg)
+    if os.path.isdir(INSTALL_STUBS):
+        shutil.rmtree(INSTALL_STUBS)
+    shutil.copytree(stubs, INSTALL_STUBS, ignore=shutil.ignore_patterns("__pycache__"))
+
+
 def build(reference: str = "/root/reference", scratch: str = DEFAULT_SCRATCH, force: bool = False) -> str:
     src, stubs = scratch_paths(scratch)
     marker = os.path.join(scratch, ".built")
@@ -178,6 +223,8 @@ def build(reference: str = "/root/reference", scratch: str = DEFAULT_SCRATCH, fo
             shutil.copy2(os.path.join(autogen, name), os.path.join(OUT, name))
             copied.append(name)
     print(f"oracle/_ref: {len(copied)} shared objects -> {OUT}")
+    install_package(src, stubs)
+    print(f"oracle/_ref: Python package of the reference + stubs installed beside them ({INSTALL})")
     return src
 
 

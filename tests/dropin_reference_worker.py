@@ -2,8 +2,10 @@
 
 The drop-in `hydpy_b200.simulate(hp)` on REAL objects of the unmodified reference (built by oracle/build_ref.py in
 this container): extract → run → write_back must leave `hp` exactly as the reference's own `hp.simulate()` leaves it.
-There is no GPU here, so the engine call in the middle is replaced by the CPU oracle (bit-exact with the reference),
-which makes the comparison a bit-for-bit check of the host-side layers."""
+Without `--engine` (no GPU: the build container) the engine call in the middle is replaced by the CPU oracle (bit-exact
+with the reference), which makes the comparison a bit-for-bit check of the host-side layers.  With `--engine` (GPU box,
+tests/test_gpu_dropin.py) nothing is replaced: extract → CUDA engine → write_back runs as one piece and every array must
+agree with the reference's own `hp.simulate()` within the parity bar of tests/util.py (rtol 1e-9, atol 1e-12)."""
 import contextlib
 import io
 import os
@@ -16,8 +18,12 @@ sys.path.insert(0, ROOT)
 
 from oracle import build_ref, oracle  # noqa: E402
 
-SRC, STUBS = build_ref.scratch_paths()
+_paths = build_ref.import_paths()
+if _paths is None:
+    raise SystemExit("no importable reference: run oracle/build_ref.py where /root/reference exists")
+SRC, STUBS = _paths
 sys.path[:0] = [STUBS, SRC]
+ENGINE = "--engine" in sys.argv
 
 import hydpy  # noqa: E402
 from hydpy import pub  # noqa: E402
@@ -266,9 +272,18 @@ def main() -> None:
             snaps.append(snapshot(hp))
         return snaps
 
+    import time
+
+    t0 = time.perf_counter()
     ref = run(hp.simulate)
-    simulate_module.run_problem = oracle_run_problem            # the engine call, replaced by the oracle
+    t_ref = time.perf_counter() - t0
+    if not ENGINE:
+        simulate_module.run_problem = oracle_run_problem        # the engine call, replaced by the oracle
+    else:
+        hydpy_b200.simulate(hp)                                 # first call: CUDA context, library load (not timed)
+    t0 = time.perf_counter()
     got = run(lambda: hydpy_b200.simulate(hp))
+    t_got = time.perf_counter() - t0
     hydpy_b200.install()
     got_installed = run(hp.simulate)                            # the monkey-patched HydPy.simulate
     hydpy_b200.uninstall()
@@ -280,16 +295,30 @@ def main() -> None:
                 bad = np.argwhere(x != y)
                 print("DIFF", key, x.shape, "first", bad[0], x[tuple(bad[0])], y[tuple(bad[0])])
     n = 0
+    worst = 0.0
     for which, snaps in (("simulate", got), ("install", got_installed)):
         for w, (a, b) in enumerate(zip(ref, snaps)):
             assert a.keys() == b.keys()
             for key in a:
-                if not np.array_equal(a[key], b[key], equal_nan=True):
+                if ENGINE:
+                    x, y = np.asarray(a[key], float), np.asarray(b[key], float)
+                    assert x.shape == y.shape, key
+                    if not np.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True):
+                        idx = np.flatnonzero(~np.isclose(np.ravel(x), np.ravel(y), rtol=1e-9, atol=1e-12, equal_nan=True))
+                        raise AssertionError(f"{which}, window {w}: {key} differs beyond 1e-9 at {idx[:8]} of {x.size}: "
+                                             f"{np.ravel(x)[idx[:4]]} vs {np.ravel(y)[idx[:4]]}")
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        dev = np.abs(x - y) / np.maximum(np.abs(x), 1e-3)
+                    worst = max(worst, float(np.nanmax(dev)) if dev.size and np.isfinite(dev).any() else 0.0)
+                elif not np.array_equal(a[key], b[key], equal_nan=True):
                     idx = np.flatnonzero(~np.isclose(np.ravel(a[key]), np.ravel(b[key]), rtol=0, atol=0, equal_nan=True))
                     raise AssertionError(f"{which}, window {w}: {key} differs at {idx[:8]} of {np.size(a[key])}: "
                                          f"{np.ravel(a[key])[idx[:4]]} vs {np.ravel(b[key])[idx[:4]]}")
                 n += 1
-    print(f"DROPIN_OK compared {n} arrays over {len(windows)} windows, {len(hp.elements)} elements, {len(hp.nodes)} nodes")
+    print(f"DROPIN_OK compared {n} arrays over {len(windows)} windows, {len(hp.elements)} elements, {len(hp.nodes)} nodes"
+          + (f"; CUDA engine in the middle, worst deviation {worst:.2e} (bar 1e-9); wall: reference hp.simulate() "
+             f"{t_ref:.3f} s, hydpy_b200.simulate(hp) {t_got:.3f} s for both windows" if ENGINE else
+             "; oracle in the middle, bit for bit"))
 
 
 if __name__ == "__main__":

@@ -9,8 +9,7 @@ import pytest
 from oracle import build_ref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC, _ = build_ref.scratch_paths()
-BUILT = os.path.exists(os.path.join(os.path.dirname(SRC), ".built"))
+BUILT = build_ref.import_paths() is not None
 
 
 @pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")

@@ -58,8 +58,46 @@ def full(paths: list[str]) -> None:
                     print(f"  {m} [{units[i]}] = {r[i]}")
 
 
+def to_json(source: str, elements: int, zones: int, window: int, forcing: str, paths: list[str]) -> None:
+    """profiles/ncu_kernels.json for bench.py: FP64-pipe utilisation and DRAM bytes per launch of the land kernels."""
+    import json
+
+    kernels: dict[str, dict] = {}
+    for path in paths:
+        rows = list(csv.reader(open(path, errors="replace")))
+        hdr = next(r for r in rows if "Kernel Name" in r)
+        units = rows[rows.index(hdr) + 1]
+
+        def val(r: list[str], name: str) -> float:
+            i = hdr.index(name)
+            v = float(r[i].replace(",", ""))
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6}
+            return v * scale.get(units[i], 1.0)
+
+        for r in rows[rows.index(hdr) + 2:]:
+            if len(r) != len(hdr):
+                continue
+            name = r[hdr.index("Kernel Name")]
+            key = "zone_kernel" if "zone_kernel" in name else "element_kernel" if "element_kernel" in name else \
+                "reach_wave_kernel" if "reach_wave_kernel" in name else None
+            if key is None or key in kernels:
+                continue
+            kernels[key] = {
+                "name": name, "ms": val(r, "gpu__time_duration.sum"),
+                "fp64_pipe_pct": val(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "dram_bytes": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
+                "inst_executed": val(r, "inst_executed"),
+                "registers": val(r, "launch__registers_per_thread"),
+            }
+    print(json.dumps({"source": source, "workload": {"elements": elements, "zones": zones, "window": window,
+                                                     "forcing": forcing}, "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "json":   # json <source note> <elements> <zones> <window> <forcing> <raw.csv> [...]
+        to_json(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6], sys.argv[7:])
     else:
         full(sys.argv[2:])

@@ -22,6 +22,9 @@ ap.add_argument("--path", default="auto")
 ap.add_argument("--cflux", type=float, default=0.0)
 ap.add_argument("--sweep", default="", help="routing sweep: persistent | grouped | launches")
 ap.add_argument("--model", default="hland_96", choices=("hland_96", "hland_96p", "hland_96c"))
+ap.add_argument("--kind", default="storms", help="forcing kind of synth.make_forcing: storms | dry")
+ap.add_argument("--spinup", type=int, default=0, help="windows simulated (untimed output) before the first rep")
+ap.add_argument("--wave-blocks", type=int, default=0)
 args = ap.parse_args()
 
 t = time.time()
@@ -40,8 +43,10 @@ if args.sweep:
     eng.set_river_sweep(args.sweep)
 nbytes = 8 * args.nt * sum(land.n_zone if x in layout.SERIES_ZONE else land.n_snow if x in layout.SERIES_SNOW else land.n_elem for x in series)
 print(f"uploaded in {time.time()-t:.2f}s")
-for rep in range(args.reps):
-    forcing, doy = synth.make_forcing(args.nt, args.step, t0=rep * args.nt)
+if args.wave_blocks:
+    eng.set_wave_blocks(args.wave_blocks)
+for rep in range(-args.spinup, args.reps):
+    forcing, doy = synth.make_forcing(args.nt, args.step, t0=(rep + args.spinup) * args.nt, kind=args.kind)
     t = time.time()
     eng.set_forcing(forcing, doy); eng.set_external(np.zeros((0, args.nt)))
     t1 = time.time()
@@ -51,7 +56,11 @@ for rep in range(args.reps):
     zs = land.n_zone * args.nt
     print(f"rep {rep}: h2d {1e3*(t1-t):.1f} ms  run wall {1e3*(t2-t1):.1f} ms  land {tm['land_ms']:.2f} ms (zone {tm['zone_ms']:.2f} element {tm['element_ms']:.2f})  river {tm['river_ms']:.2f} ms "
           f"({tm['river_launches']} launches, {tm['n_levels']} levels)  -> {zs/tm['total_ms']*1e3:.3e} zone-steps/s (device)"
-          + (f"  series {nbytes/1e9:.2f} GB -> {nbytes/1e6/tm['land_ms']:.0f} GB/s of land time" if series else ""))
+          + (f"  series {nbytes/1e9:.2f} GB -> {nbytes/1e6/tm['land_ms']:.0f} GB/s of land time" if series else "")
+          + (f"  | RecStep chain ran in {tm['elem_steps_run']/tm['elem_steps']:.1%} of the element-steps, pow in "
+             f"{tm['substeps_pow']/max(1, tm['elem_steps'])/max(1, int(land.recstep[0])):.1%} of the sub-steps; water at the soil in "
+             f"{tm['zone_steps_wet']/max(1, tm['zone_steps']):.1%} of the zone-steps, dry shortcut in "
+             f"{tm['zone_warpsteps_dry']/max(1, tm['zone_warpsteps']):.1%} of the warp-steps" if tm['elem_steps'] else ""))
 t = time.time()
 rows = eng.get_node_series() if not args.no_river else eng.get_land_outflow()
 print(f"d2h {rows.nbytes/1e6:.0f} MB in {1e3*(time.time()-t):.1f} ms; finite={np.isfinite(rows).all()} mean={rows.mean():.4f}")
