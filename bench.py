@@ -54,6 +54,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-blocks", type=int, default=0, help="persistent routing blocks per SM (0 = engine default)")
     ap.add_argument("--river-sweep", default="", help="routing sweep: persistent | grouped | launches (default: engine's)")
+    ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
+    ap.add_argument("--land-chunk", type=int, default=0, help="time chunk of the fast land path in steps (0 = engine default)")
     return ap.parse_args()
 
 
@@ -230,6 +232,10 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         eng.set_river_sweep(args.river_sweep)
     if args.wave_blocks:
         eng.set_wave_blocks(args.wave_blocks)
+    if args.land_slabs:
+        eng.set_land_slabs(args.land_slabs)
+    if args.land_chunk:
+        eng.set_land_chunk(args.land_chunk)
     if dist.world > 1:
         uid = dist.bcast_bytes(eng.comm_unique_id() if dist.rank == 0 else None, 128)
         eng.comm_init(dist.rank, dist.world, uid)

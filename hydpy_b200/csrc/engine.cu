@@ -29,6 +29,7 @@ using namespace hb;
 #ifndef HB_WAVE_BLOCKS_PER_SM
 #define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
+#define HB_MAX_SLABS 8
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
@@ -164,6 +165,13 @@ struct hb_engine {
   DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
   DBuf<int64_t> d_zone_cell0, d_snow_cell0;       // [E_pad+1] first ABI cell of every element
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
+  // element slabs of the fast path: slab 0 runs on `stream`, slab s on s_slab[s-1]; s_join collects them
+  int land_slabs = 2;
+  int64_t land_chunk = 0;             // steps per time chunk of the fast path (0 = automatic)
+  cudaStream_t s_slab[HB_MAX_SLABS - 1] = {}, s_join = nullptr;
+  cudaEvent_t ev_slab_fork = nullptr, ev_slab_zone[HB_MAX_SLABS] = {}, ev_slab_done[HB_MAX_SLABS] = {};
+  int slabs_used = 1;                 // slabs of the current run_land
+  int64_t slab_elem_lo[HB_MAX_SLABS + 1] = {};
   int river_sweep = HB_RIVER_PERSISTENT;  // HB_RIVER_PERSISTENT / HB_RIVER_LAUNCHES
   bool river_state_series = false;        // record musk_classic states.discharge per step
   int wave_blocks = HB_WAVE_BLOCKS_PER_SM;  // persistent wavefront blocks per SM
@@ -336,7 +344,14 @@ int hb_create(int device, hb_engine** out) {
     cudaEventCreateWithFlags(&h->ev_copy_done[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
   }
-  if (!h->s_river || !h->s_copy || !h->ev_join[1]) {
+  for (auto& st : h->s_slab) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_join, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_slab_fork, cudaEventDisableTiming);
+  for (int i = 0; i < HB_MAX_SLABS; ++i) {
+    cudaEventCreateWithFlags(&h->ev_slab_zone[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_slab_done[i], cudaEventDisableTiming);
+  }
+  if (!h->s_river || !h->s_copy || !h->ev_join[1] || !h->s_join || !h->ev_slab_done[HB_MAX_SLABS - 1]) {
     g_create_error = "hb_create: cannot create the pipeline streams/events";
     hb_destroy(h);
     return HB_ECUDA;
@@ -371,6 +386,14 @@ void hb_destroy(hb_engine* h) {
   if (h->s_copy) cudaStreamSynchronize(h->s_copy);
   if (h->s_comm) cudaStreamSynchronize(h->s_comm);
   if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+  for (auto& st : h->s_slab)
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (h->s_join) { cudaStreamSynchronize(h->s_join); cudaStreamDestroy(h->s_join); }
+  if (h->ev_slab_fork) cudaEventDestroy(h->ev_slab_fork);
+  for (int i = 0; i < HB_MAX_SLABS; ++i) {
+    if (h->ev_slab_zone[i]) cudaEventDestroy(h->ev_slab_zone[i]);
+    if (h->ev_slab_done[i]) cudaEventDestroy(h->ev_slab_done[i]);
+  }
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -830,6 +853,14 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       h->mct_series_mask = (unsigned)value;
       if (!value) { h->d_mct_series[0].release(); h->d_mct_series[1].release(); }
       return HB_OK;
+    case HB_OPT_LAND_SLABS:
+      HB_REQUIRE(h, value >= 1 && value <= HB_MAX_SLABS, HB_EINVAL, "hb_set_option: land slabs must be 1..%d", HB_MAX_SLABS);
+      h->land_slabs = (int)value;
+      return HB_OK;
+    case HB_OPT_LAND_CHUNK:
+      HB_REQUIRE(h, value >= 0, HB_EINVAL, "hb_set_option: negative land chunk");
+      h->land_chunk = value;
+      return HB_OK;
     case HB_OPT_RIVER_SWEEP:
       HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES || value == HB_RIVER_GROUPED, HB_EINVAL,
                  "hb_set_option: invalid routing sweep");
@@ -1193,7 +1224,10 @@ static int stage_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* 
   const size_t n = (size_t)HB_FORCING_COUNT * nt * n_col;
   // the copy runs on its own stream, behind the last land run that read this buffer, while the current one is busy
   HB_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_forcing_read[f], 0));
-  if (n > h->d_forcing[f].cap || (size_t)nt > h->d_sinfactor[f].cap) HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (n > h->d_forcing[f].cap || (size_t)nt > h->d_sinfactor[f].cap) {
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (auto& st : h->s_slab) HB_CUDA(h, cudaStreamSynchronize(st));
+  }
   HB_CUDA(h, h->d_forcing[f].reserve(n));
   HB_CUDA(h, h->d_sinfactor[f].reserve((size_t)nt));
   if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing[f].p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
@@ -1310,7 +1344,12 @@ static int run_land(hb_engine* h) {
   }
   const int64_t n_general = (int64_t)h->general_list.size();
   h->timing.n_fast = (use_fast ? h->n_fast : 0) + (use_fast_sib ? h->n_fast_sib[0] + h->n_fast_sib[1] : 0);
-  if (h->n_elem == 0 || nt == 0) return HB_OK;
+  h->slabs_used = 1;
+  if (h->n_elem == 0 || nt == 0) {
+    HB_CUDA(h, cudaEventRecord(h->ev_slab_done[0], h->stream));
+    HB_CUDA(h, cudaStreamWaitEvent(h->s_join, h->ev_slab_done[0], 0));
+    return HB_OK;
+  }
   for (int s = 0; s < HB_S_COUNT; ++s) {
     if (!h->series_on[s]) continue;
     const int level = HB_S_LEVEL(s);
@@ -1357,6 +1396,7 @@ static int run_land(hb_engine* h) {
     else budget = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);
     int64_t chunk_max = (int64_t)(budget / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
+    if (h->land_chunk > 0 && h->land_chunk < chunk_max) chunk_max = h->land_chunk;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
     const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
     HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
@@ -1370,61 +1410,89 @@ static int run_land(hb_engine* h) {
         v.series[s] = h->d_series_stage[s].p;
       } else v.series[s] = h->d_series[s].p;
     }
+    // ---- element slabs: slab s works on the elements [slab_lo[s], slab_lo[s+1]) * 128 on a stream of its own.  The zone
+    // kernel of slab s starts when the zone kernel of slab s-1 (same chunk) is through, so the slabs run staggered: the
+    // element kernel of one (few warps following their sequential RecStep chains, latency-bound) shares the SMs with the
+    // zone kernel of the next (throughput-bound).  Series recording keeps one slab.
+    const int64_t nblk_total = ep / 128;
+    int n_slabs = (any_series || n_staged) ? 1 : h->land_slabs;
+    if (n_slabs > nblk_total) n_slabs = (int)nblk_total;
+    if (n_slabs < 1) n_slabs = 1;
+    int64_t slab_lo[HB_MAX_SLABS + 1];
+    for (int sl = 0; sl <= n_slabs; ++sl) slab_lo[sl] = nblk_total * sl / n_slabs;
+    cudaStream_t slab_stream[HB_MAX_SLABS];
+    for (int sl = 0; sl < n_slabs; ++sl) slab_stream[sl] = sl == 0 ? h->stream : h->s_slab[sl - 1];
+    if (n_slabs > 1) {
+      HB_CUDA(h, cudaEventRecord(h->ev_slab_fork, h->stream));   // everything the land stream has waited for so far
+      for (int sl = 1; sl < n_slabs; ++sl) HB_CUDA(h, cudaStreamWaitEvent(slab_stream[sl], h->ev_slab_fork, 0));
+    }
+    h->slabs_used = n_slabs;
     for (int64_t c0 = 0; c0 < nt; c0 += chunk) {
       v.nt = (nt - c0 < chunk) ? (nt - c0) : chunk;
       v.t_first = h->t0 + c0;
       v.t_out = c0;
-      h->mark(HB_K_OTHER);
-      const unsigned zgrid = (unsigned)(per_step / 128), egrid = (unsigned)((h->n_elem + 63) / 64);
-      if (use_fast) {
-        if (any_series) zone_kernel<true, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
-        else zone_kernel<true, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
-        if (h->any_nonsoil_warp) {
-          if (any_series) zone_kernel<false, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
-          else zone_kernel<false, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, h->stream>>>(v);
+      for (int sl = 0; sl < n_slabs; ++sl) {
+        cudaStream_t st = slab_stream[sl];
+        v.e_lo = slab_lo[sl] * 128;
+        v.slab_blocks = (int32_t)(slab_lo[sl + 1] - slab_lo[sl]);
+        if (v.slab_blocks == 0) continue;
+        const int64_t e_hi = std::min<int64_t>(h->n_elem, slab_lo[sl + 1] * 128);
+        if (e_hi <= v.e_lo) continue;
+        if (sl == 0) h->mark(HB_K_OTHER);
+        else HB_CUDA(h, cudaStreamWaitEvent(st, h->ev_slab_zone[sl - 1], 0));
+        const unsigned zgrid = (unsigned)((int64_t)h->zmax * v.slab_blocks), egrid = (unsigned)((e_hi - v.e_lo + 63) / 64);
+        if (use_fast) {
+          if (any_series) zone_kernel<true, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
+          else zone_kernel<true, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
+          if (h->any_nonsoil_warp) {
+            if (any_series) zone_kernel<false, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
+            else zone_kernel<false, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
+            h->timing.land_launches += 1;
+          }
           h->timing.land_launches += 1;
         }
-        h->timing.land_launches += 1;
-      }
-      // sibling models: the same grid, instantiated for their model (threads of other models retire at once)
-      if (use_fast_sib && h->n_fast_sib[0] > 0) {
-        zone_kernel<true, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, h->stream>>>(v);
-        if (h->any_nonsoil_sib[0]) zone_kernel<false, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, h->stream>>>(v);
-        h->timing.land_launches += 1 + (h->any_nonsoil_sib[0] ? 1 : 0);
-      }
-      if (use_fast_sib && h->n_fast_sib[1] > 0) {
-        zone_kernel<true, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, h->stream>>>(v);
-        if (h->any_nonsoil_sib[1]) zone_kernel<false, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, h->stream>>>(v);
-        h->timing.land_launches += 1 + (h->any_nonsoil_sib[1] ? 1 : 0);
-      }
-      if (n_staged) {
-        dim3 sg((unsigned)((h->n_elem + 31) / 32), (unsigned)(v.nt < 64 ? v.nt : 64));
-        const size_t sm_bytes = (size_t)h->zmax * 33 * sizeof(double);
-        for (int s = 0; s < HB_S_FIRST_ELEM; ++s) {
-          if (!h->series_on[s]) continue;
-          const bool snow = s >= HB_S_FIRST_SNOW;
-          series_scatter_kernel<<<sg, 256, sm_bytes, h->stream>>>(
-              h->d_series_stage[s].p, h->d_series[s].p, snow ? h->d_snow_cell0.p : h->d_zone_cell0.p,
-              snow ? h->d_snow_slot.p : h->d_zone_slot.p, h->n_elem, ep, h->zmax, snow ? h->n_snow : h->n_zone, (int)v.nt, c0);
+        // sibling models: the same grid, instantiated for their model (threads of other models retire at once)
+        if (use_fast_sib && h->n_fast_sib[0] > 0) {
+          zone_kernel<true, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+          if (h->any_nonsoil_sib[0]) zone_kernel<false, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+          h->timing.land_launches += 1 + (h->any_nonsoil_sib[0] ? 1 : 0);
+        }
+        if (use_fast_sib && h->n_fast_sib[1] > 0) {
+          zone_kernel<true, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+          if (h->any_nonsoil_sib[1]) zone_kernel<false, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+          h->timing.land_launches += 1 + (h->any_nonsoil_sib[1] ? 1 : 0);
+        }
+        if (n_slabs > 1) HB_CUDA(h, cudaEventRecord(h->ev_slab_zone[sl], st));
+        if (n_staged) {   // (one slab)
+          dim3 sg((unsigned)((h->n_elem + 31) / 32), (unsigned)(v.nt < 64 ? v.nt : 64));
+          const size_t sm_bytes = (size_t)h->zmax * 33 * sizeof(double);
+          for (int s = 0; s < HB_S_FIRST_ELEM; ++s) {
+            if (!h->series_on[s]) continue;
+            const bool snow = s >= HB_S_FIRST_SNOW;
+            series_scatter_kernel<<<sg, 256, sm_bytes, st>>>(
+                h->d_series_stage[s].p, h->d_series[s].p, snow ? h->d_snow_cell0.p : h->d_zone_cell0.p,
+                snow ? h->d_snow_slot.p : h->d_zone_slot.p, h->n_elem, ep, h->zmax, snow ? h->n_snow : h->n_zone, (int)v.nt, c0);
+            h->timing.land_launches += 1;
+          }
+        }
+        if (sl == 0) h->mark(HB_K_ZONE);
+        if (use_fast) {
+          if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, esmem, st>>>(v);
+          else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, esmem, st>>>(v);
           h->timing.land_launches += 1;
         }
+        if (use_fast_sib && h->n_fast_sib[0] > 0) {
+          element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, st>>>(v);
+          h->timing.land_launches += 1;
+        }
+        if (use_fast_sib && h->n_fast_sib[1] > 0) {
+          element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, st>>>(v);
+          h->timing.land_launches += 1;
+        }
+        if (sl == 0) h->mark(HB_K_ELEMENT);
       }
-      h->mark(HB_K_ZONE);
-      if (use_fast) {
-        if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, esmem, h->stream>>>(v);
-        else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, esmem, h->stream>>>(v);
-        h->timing.land_launches += 1;
-      }
-      if (use_fast_sib && h->n_fast_sib[0] > 0) {
-        element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, h->stream>>>(v);
-        h->timing.land_launches += 1;
-      }
-      if (use_fast_sib && h->n_fast_sib[1] > 0) {
-        element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, h->stream>>>(v);
-        h->timing.land_launches += 1;
-      }
-      h->mark(HB_K_ELEMENT);
     }
+    for (int sl = 0; sl <= n_slabs; ++sl) h->slab_elem_lo[sl] = std::min<int64_t>(h->n_elem, slab_lo[sl] * 128);
     HB_CUDA(h, cudaGetLastError());
   }
   if (use_coupled) {
@@ -1492,10 +1560,35 @@ static int run_land(hb_engine* h) {
     h->mark(HB_K_GENERAL);
     HB_CUDA(h, cudaGetLastError());
   }
-  dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
-  transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, h->n_elem, ep);
+  // qt [nt][E_pad] -> land rows [n_elem][nt].  A run of fast-path slabs only: every slab transposes its own columns on its
+  // own stream and the land stream goes on to the next window without waiting for the others (s_join collects them for
+  // the consumers of the rows); otherwise all slabs join the land stream first, which transposes everything.
+  const int ns = (use_fast || use_fast_sib) ? h->slabs_used : 1;
+  const bool slabs_only = ns > 1 && !use_coupled && n_general == 0 && n_sib[0] == 0 && n_sib[1] == 0;
+  if (slabs_only) {
+    for (int sl = 0; sl < ns; ++sl) {
+      cudaStream_t st = sl == 0 ? h->stream : h->s_slab[sl - 1];
+      const int64_t e_a = h->slab_elem_lo[sl], e_b = h->slab_elem_lo[sl + 1];
+      if (e_b > e_a) {
+        dim3 tg((unsigned)((e_b - e_a + 31) / 32), (unsigned)((nt + 31) / 32));
+        transpose_qt_kernel<<<tg, 256, 0, st>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, e_b, ep, e_a);
+        h->timing.land_launches += 1;
+      }
+      HB_CUDA(h, cudaEventRecord(h->ev_slab_done[sl], st));
+      HB_CUDA(h, cudaStreamWaitEvent(h->s_join, h->ev_slab_done[sl], 0));
+    }
+  } else {
+    for (int sl = 1; sl < ns; ++sl) {
+      HB_CUDA(h, cudaEventRecord(h->ev_slab_done[sl], h->s_slab[sl - 1]));
+      HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_slab_done[sl], 0));
+    }
+    dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
+    transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, h->n_elem, ep, 0);
+    h->timing.land_launches += 1;
+    HB_CUDA(h, cudaEventRecord(h->ev_slab_done[0], h->stream));
+    HB_CUDA(h, cudaStreamWaitEvent(h->s_join, h->ev_slab_done[0], 0));
+  }
   HB_CUDA(h, cudaGetLastError());
-  h->timing.land_launches += 1;
   return HB_OK;
 }
 
@@ -1681,8 +1774,9 @@ static int enqueue_run(hb_engine* h, int flags) {
     h->land_marks.add(HB_K_BEGIN, h->stream);
     if ((rc = run_land(h))) return rc;
     h->land_marks.add(HB_K_END, h->stream);
-    HB_CUDA(h, cudaEventRecord(h->ev_land_done[c], h->stream));
-    HB_CUDA(h, cudaEventRecord(h->ev_forcing_read[h->fcur], h->stream));
+    // (s_join has been made to wait for every slab stream of this run)
+    HB_CUDA(h, cudaEventRecord(h->ev_land_done[c], h->s_join));
+    HB_CUDA(h, cudaEventRecord(h->ev_forcing_read[h->fcur], h->s_join));
     h->have_results = true;
   }
   if (flags & HB_RUN_RIVER) {
@@ -1728,6 +1822,8 @@ int hb_wait(hb_engine* h) {
   if (!h) return HB_EINVAL;
   HB_CUDA(h, cudaSetDevice(h->device));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (auto& st : h->s_slab) HB_CUDA(h, cudaStreamSynchronize(st));
+  HB_CUDA(h, cudaStreamSynchronize(h->s_join));
   HB_CUDA(h, cudaStreamSynchronize(h->s_river));
   HB_CUDA(h, cudaStreamSynchronize(h->s_copy));
   HB_CUDA(h, cudaStreamSynchronize(h->s_comm));
@@ -1798,6 +1894,12 @@ static int join_streams(hb_engine* h) {
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
   HB_CUDA(h, cudaEventRecord(h->ev_join[0], h->s_comm));   // (the wait above already holds the first recording)
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+  for (auto& st : h->s_slab) {
+    HB_CUDA(h, cudaEventRecord(h->ev_join[0], st));
+    HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+  }
+  HB_CUDA(h, cudaEventRecord(h->ev_join[0], h->s_join));
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
   return HB_OK;
 }

@@ -35,6 +35,11 @@ namespace hb {
 struct LandV2Dev {
   int64_t n_elem, e_pad;
   int32_t zmax;
+  // slab of elements this launch works on (multiples of 128; the whole basin: e_lo = 0, slab_blocks = E_pad / 128).
+  // Slabs run on streams of their own, so that the latency-bound element kernel of one slab shares the SMs with the
+  // throughput-bound zone kernel of another (engine.cu: run_land)
+  int64_t e_lo;
+  int32_t slab_blocks;
   const int32_t* nz;       // [E_pad]
   const int32_t* nu;       // [E_pad]
   const int32_t* recstep;  // [E_pad]
@@ -143,9 +148,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
   const int64_t ep = d.e_pad;
-  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // k*E_pad + e
-  const int k = (int)(slot / ep);
-  const int64_t e = slot - (int64_t)k * ep;
+  const int k = (int)(blockIdx.x / (unsigned)d.slab_blocks);
+  const int64_t e = d.e_lo + (int64_t)(blockIdx.x - (unsigned)k * (unsigned)d.slab_blocks) * 128 + threadIdx.x;
+  const int64_t slot = (int64_t)k * ep + e;   // k*E_pad + e
   if (e >= d.n_elem) return;
   const int einfo = d.einfo[e];
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL || k >= d.nz[e]) return;
@@ -687,8 +692,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   double* const s_sc = d.nash_stage ? s_sc_dyn : nullptr;   // (launch parameter) when some element has a cascade
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.n_elem) return;
+  const int64_t e = d.e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.n_elem || e >= d.e_lo + (int64_t)d.slab_blocks * 128) return;
   const int einfo = d.einfo[e];
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
   const int64_t ep = d.e_pad;

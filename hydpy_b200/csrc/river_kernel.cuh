@@ -120,10 +120,11 @@ struct RiverDev {
 #endif
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
+// (elements e_begin .. n_elem-1 with a grid of ceil((n_elem - e_begin) / 32) x ceil(nt / 32) blocks)
 __global__ void __launch_bounds__(256) transpose_qt_kernel(const double* __restrict__ qt, double* __restrict__ rows,
-                                                           int64_t nt, int64_t n_elem, int64_t e_pad) {
+                                                           int64_t nt, int64_t n_elem, int64_t e_pad, int64_t e_begin) {
   __shared__ double tile[32][33];
-  const int64_t e0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+  const int64_t e0 = e_begin + (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int j = ty; j < 32; j += 8) {
     const int64_t t = t0 + j, e = e0 + tx;

@@ -288,6 +288,14 @@ class Engine:
                  "grouped": layout.RIVER_GROUPED}[mode]
         self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_SWEEP, value), "hb_set_option")
 
+    def set_land_slabs(self, slabs: int) -> None:
+        """Element slabs (streams) of the fast runoff-generation path, 1..8 (performance only; same results)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_SLABS, int(slabs)), "hb_set_option")
+
+    def set_land_chunk(self, steps: int) -> None:
+        """Time chunk of the fast runoff-generation path in steps (0 = automatic)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_CHUNK, int(steps)), "hb_set_option")
+
     def set_wave_blocks(self, blocks_per_sm: int) -> None:
         """Persistent routing wavefront blocks per SM (1..8): how much of every SM the routing of window w takes from the
         runoff generation of window w+1."""

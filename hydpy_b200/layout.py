@@ -101,6 +101,8 @@ OPT_RIVER_SWEEP = 1
 OPT_RIVER_STATE_SERIES = 2
 OPT_RIVER_WAVE_BLOCKS = 3
 OPT_RIVER_MCT_SERIES = 4
+OPT_LAND_SLABS = 5
+OPT_LAND_CHUNK = 6
 RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2
 LAND_AUTO, LAND_GENERAL = 0, 1
 ROW_NODE, ROW_REACH = 0, 1

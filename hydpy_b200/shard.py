@@ -46,24 +46,30 @@ class Shard:
         return out
 
 
+def _gather(ptr_: np.ndarray, items: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """CSR rows `items` of a CSR structure: (new row pointer, flat indices into the old value arrays)."""
+    items = np.asarray(items, np.int64)
+    lens = (ptr_[1:] - ptr_[:-1])[items].astype(np.int64)
+    new_ptr = np.zeros(len(items) + 1, np.int64)
+    np.cumsum(lens, out=new_ptr[1:])
+    total = int(new_ptr[-1])
+    if total == 0:
+        return new_ptr, np.zeros(0, np.int64)
+    idx = np.arange(total, dtype=np.int64) - np.repeat(new_ptr[:-1], lens) + np.repeat(ptr_[:-1][items].astype(np.int64), lens)
+    return new_ptr, idx
+
+
 def subset_land(land: LandBundle, states: LandStates, elements: np.ndarray, outlet_node: np.ndarray
                 ) -> tuple[LandBundle, LandStates]:
     """The elements `elements` (global indices) as a bundle of their own; `outlet_node` = their local outlet nodes."""
     elements = np.asarray(elements, np.int64)
-
-    def csr(ptr_: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
-        lens = (ptr_[1:] - ptr_[:-1])[elements]
-        new_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        idx = np.concatenate([np.arange(ptr_[e], ptr_[e + 1]) for e in elements] + [np.zeros(0, np.int64)]).astype(np.int64)
-        return new_ptr, idx
-
     land.normalise()
     states.normalise()
-    zp, zi = csr(land.zone_ptr)
-    sp, si = csr(land.snow_ptr)
-    fp, fi = csr(land.sfdist_ptr)
-    up, ui = csr(land.uh_ptr)
-    rp, ri = csr(land.sred_ptr)
+    zp, zi = _gather(land.zone_ptr, elements)
+    sp, si = _gather(land.snow_ptr, elements)
+    fp, fi = _gather(land.sfdist_ptr, elements)
+    up, ui = _gather(land.uh_ptr, elements)
+    rp, ri = _gather(land.sred_ptr, elements)
     sub = LandBundle(
         zone_ptr=zp, snow_ptr=sp, sfdist_ptr=fp, uh_ptr=up, sred_ptr=rp, recstep=land.recstep[elements],
         eflags=land.eflags[elements], forcing_col=land.forcing_col[elements], outlet_node=outlet_node,
@@ -85,26 +91,29 @@ def scatter_states(shard: Shard, local: LandStates, land: LandBundle, out: LandS
     for which, ptr_ in (("ic", land.zone_ptr), ("sm", land.zone_ptr), ("sp", land.snow_ptr), ("wc", land.snow_ptr),
                         ("quh", land.uh_ptr), ("suz", land.zone_ptr), ("sg1", land.zone_ptr), ("bw1", land.zone_ptr),
                         ("bw2", land.zone_ptr)):
-        src = getattr(local, which)
-        dst = getattr(out, which)
-        pos = 0
-        for e in shard.elements:
-            n = int(ptr_[e + 1] - ptr_[e])
-            dst[ptr_[e]:ptr_[e] + n] = src[pos:pos + n]
-            pos += n
+        _, idx = _gather(ptr_, shard.elements)
+        getattr(out, which)[idx] = getattr(local, which)
     out.uz[shard.elements] = local.uz
     out.lz[shard.elements] = local.lz
     out.sg2[shard.elements] = local.sg2
     out.sg3[shard.elements] = local.sg3
 
 
-def assign_nodes(land: LandBundle, river: RiverBundle, world: int) -> np.ndarray:
-    """Rank of every node: contiguous upstream sub-networks of roughly equal zone count.
+def assign_nodes(land: LandBundle | None, river: RiverBundle, world: int, *, outlet_node: np.ndarray | None = None,
+                 zones: np.ndarray | None = None) -> np.ndarray:
+    """Rank of every node: `world` ranges of equal weight (zones of the land elements + a share for the reach segments)
+    of an UPSTREAM-FIRST ordering of the network.
 
-    Nodes that feed the same reach are kept together (a reach reads all its inlet nodes locally); a reach lives with
-    its inlet nodes.  Greedy bottom-up accumulation: walking the DAG upstream-first, a sub-network is split off as soon
-    as it has collected total/world zones."""
+    Nodes that feed the same reach are kept together (a reach reads all its inlet nodes locally; a reach lives with its
+    inlet nodes).  The order is the post-order of a depth-first walk from the outlets towards the headwaters, so sub-
+    networks are contiguous in it and every node comes after everything upstream of it: cutting the order into ranges
+    gives balanced shards whose boundary series only travel from lower to higher ranks (an acyclic shard graph)."""
     nn, nr = river.n_node, river.n_reach
+    if outlet_node is None:
+        outlet_node = land.outlet_node if land is not None else np.zeros(0, np.int32)
+    if zones is None:
+        zones = np.diff(land.zone_ptr).astype(float) if land is not None else np.ones(len(outlet_node))
+    # groups of nodes that feed the same reach (union-find over the reaches with several inlet nodes only)
     parent = np.arange(nn)
 
     def find(a: int) -> int:
@@ -113,172 +122,198 @@ def assign_nodes(land: LandBundle, river: RiverBundle, world: int) -> np.ndarray
             a = parent[a]
         return a
 
-    for q in range(nr):
+    n_in = np.diff(river.inlet_ptr)
+    for q in np.flatnonzero(n_in > 1):
         ins = river.inlet_node[river.inlet_ptr[q]:river.inlet_ptr[q + 1]]
         for n in ins[1:]:
             ra, rb = find(int(ins[0])), find(int(n))
             if ra != rb:
                 parent[rb] = ra
-    group = np.array([find(n) for n in range(nn)])
+    if np.any(n_in > 1):
+        group = np.array([find(n) for n in range(nn)])
+    else:
+        group = parent
     weight = np.zeros(nn)
-    zones = np.diff(land.zone_ptr).astype(float)
-    for e, n in enumerate(land.outlet_node):
-        if n >= 0:
-            weight[group[n]] += zones[e]
-    segs = np.diff(river.seg_ptr).astype(float)
-    down = np.full(nn, -1)                       # downstream group of a group (first reach with an outlet elsewhere)
-    children: list[list[int]] = [[] for _ in range(nn)]
-    indeg = np.zeros(nn, int)
-    for q in range(nr):
-        if river.inlet_ptr[q + 1] == river.inlet_ptr[q]:
+    ok = np.asarray(outlet_node) >= 0
+    np.add.at(weight, group[np.asarray(outlet_node)[ok]], np.asarray(zones, float)[ok])
+    has_in = n_in > 0
+    first_in = np.zeros(nr, np.int64)
+    first_in[has_in] = river.inlet_node[river.inlet_ptr[:-1][has_in]]
+    g_of_reach = group[first_in]
+    np.add.at(weight, g_of_reach[has_in], 0.05 * np.diff(river.seg_ptr).astype(float)[has_in])
+    # upstream adjacency of the groups: edge g -> d for every reach of g that ends in a node of another group d
+    out_ok = has_in & (river.reach_outlet >= 0)
+    src_g = g_of_reach[out_ok]
+    dst_g = group[river.reach_outlet[out_ok]]
+    keep = src_g != dst_g
+    src_g, dst_g = src_g[keep], dst_g[keep]
+    order_e = np.argsort(dst_g, kind="stable")
+    up_of = src_g[order_e]                                   # upstream groups, grouped by downstream group
+    up_ptr = np.zeros(nn + 1, np.int64)
+    np.add.at(up_ptr, dst_g + 1, 1)
+    np.cumsum(up_ptr, out=up_ptr)
+    is_group = np.zeros(nn, bool)
+    is_group[group] = True
+    has_down = np.zeros(nn, bool)
+    has_down[src_g] = True
+    roots = np.flatnonzero(is_group & ~has_down)
+    visited = np.zeros(nn, bool)
+    post: list[int] = []
+    up_ptr_l, up_of_l = up_ptr.tolist(), up_of.tolist()
+    for root in roots.tolist():
+        if visited[root]:
             continue
-        g = group[river.inlet_node[river.inlet_ptr[q]]]
-        weight[g] += 0.05 * segs[q]
-        o = river.reach_outlet[q]
-        if o >= 0 and group[o] != g and down[g] < 0:
-            down[g] = group[o]
-            children[group[o]].append(g)
-            indeg[group[o]] += 1
-    roots = [g for g in np.unique(group)]
-    rank = np.full(nn, -1)
-    target = weight[np.unique(group)].sum() / max(world, 1)
-    acc = weight.copy()
-    order = [g for g in roots if indeg[g] == 0]
-    next_rank = 0
-    i = 0
-    while i < len(order):
-        g = order[i]
-        i += 1
-        if next_rank < world - 1 and acc[g] >= target:
-            stack = [g]
-            while stack:                          # the not yet assigned part of the sub-network above g
-                u = stack.pop()
-                if rank[u] >= 0:
-                    continue
-                rank[u] = next_rank
-                stack.extend(c for c in children[u] if rank[c] < 0)
-            next_rank += 1
-            acc[g] = 0.0
-        d = down[g]
-        if d >= 0:
-            acc[d] += acc[g]
-            indeg[d] -= 1
-            if indeg[d] == 0:
-                order.append(d)
-    rank[rank < 0] = next_rank                    # the remainder (holds the outlets)
+        visited[root] = True
+        stack = [(root, up_ptr_l[root])]
+        while stack:
+            u, i = stack[-1]
+            if i < up_ptr_l[u + 1]:
+                stack[-1] = (u, i + 1)
+                c = up_of_l[i]
+                if not visited[c]:
+                    visited[c] = True
+                    stack.append((c, up_ptr_l[c]))
+            else:
+                post.append(u)
+                stack.pop()
+    post_arr = np.array(post, np.int64)
+    if len(post_arr) != int(is_group.sum()):                 # groups on a cycle (refused later by the engine): append them
+        rest = np.flatnonzero(is_group & ~visited)
+        post_arr = np.concatenate([post_arr, rest])
+    w = weight[post_arr]
+    total = float(w.sum())
+    if total <= 0.0:
+        w = np.ones(len(post_arr))
+        total = float(len(post_arr))
+    mid = np.cumsum(w) - 0.5 * w
+    rank_of_group = np.minimum((mid / (total / max(world, 1))).astype(np.int64), world - 1)
+    rank = np.zeros(nn, np.int64)
+    rank[post_arr] = rank_of_group
     return rank[group]
 
 
-def partition(land: LandBundle, states: LandStates, river: RiverBundle, discharge: np.ndarray, world: int,
-              node_rank: np.ndarray | None = None, mct_states: np.ndarray | None = None) -> list[Shard]:
-    """Cut the basin into `world` shards (see module docstring).  `node_rank` overrides the built-in assignment."""
-    land.normalise()
+def partition(land: LandBundle | None, states: LandStates | None, river: RiverBundle, discharge: np.ndarray, world: int,
+              node_rank: np.ndarray | None = None, mct_states: np.ndarray | None = None,
+              ranks: Sequence[int] | None = None, outlet_node: np.ndarray | None = None) -> list[Shard]:
+    """Cut the basin into `world` shards (see module docstring).  `node_rank` overrides the built-in assignment.
+
+    `ranks`: the shards to build completely (default: all); the others only carry what the exchange plan needs
+    (`nodes`, `reaches`, `elements`, `recv`, `send`, `stage`) — on a large basin every rank builds its own bundles only.
+    `land`/`states` may be None when the caller brings the land elements of its shard itself (`outlet_node` then says
+    which node each global element drains to)."""
+    if land is not None:
+        land.normalise()
     river.normalise()
     nn, nr = river.n_node, river.n_reach
-    node_rank = assign_nodes(land, river, world) if node_rank is None else np.asarray(node_rank)
-    reach_rank = np.zeros(nr, int)
-    for q in range(nr):
-        ins = river.inlet_node[river.inlet_ptr[q]:river.inlet_ptr[q + 1]]
-        reach_rank[q] = node_rank[ins[0]] if len(ins) else (node_rank[river.reach_outlet[q]] if river.reach_outlet[q] >= 0 else 0)
-        if len(ins) and np.any(node_rank[ins] != reach_rank[q]):
-            raise ValueError(f"reach {q} reads inlet nodes of different ranks")
-    elem_rank = np.where(land.outlet_node >= 0, node_rank[np.maximum(land.outlet_node, 0)], 0)
+    if outlet_node is None:
+        outlet_node = land.outlet_node if land is not None else np.zeros(0, np.int32)
+    outlet_node = np.asarray(outlet_node, np.int64)
+    node_rank = (assign_nodes(land, river, world, outlet_node=outlet_node) if node_rank is None
+                 else np.asarray(node_rank)).astype(np.int64)
+    n_in = np.diff(river.inlet_ptr)
+    has_in = n_in > 0
+    first_in = np.zeros(nr, np.int64)
+    first_in[has_in] = river.inlet_node[river.inlet_ptr[:-1][has_in]]
+    reach_rank = np.where(has_in, node_rank[first_in],
+                          np.where(river.reach_outlet >= 0, node_rank[np.maximum(river.reach_outlet, 0)], 0)).astype(np.int64)
+    if len(river.inlet_node):
+        inlet_reach = np.repeat(np.arange(nr), n_in)
+        bad = node_rank[river.inlet_node] != reach_rank[inlet_reach]
+        if np.any(bad):
+            raise ValueError(f"reach {int(inlet_reach[np.argmax(bad)])} reads inlet nodes of different ranks")
+    elem_rank = np.where(outlet_node >= 0, node_rank[np.maximum(outlet_node, 0)], 0)
+    build = set(range(world)) if ranks is None else {int(r) for r in ranks}
+    # every boundary edge of the network at once: entries of reaches that live on another rank than the node
+    entry_node = np.repeat(np.arange(nn), np.diff(river.entry_ptr))
+    esrc = river.entry_src.astype(np.int64)
+    is_reach_entry = (esrc < 0) & (esrc > layout.ENTRY_EXT)
+    eq = -1 - esrc[is_reach_entry]
+    consumer = node_rank[entry_node[is_reach_entry]]
+    producer = reach_rank[eq]
+    cross = consumer != producer
+    b_cons, b_prod, b_reach = consumer[cross], producer[cross], eq[cross]
+    order = np.lexsort((b_reach, b_prod, b_cons))
+    b_cons, b_prod, b_reach = b_cons[order], b_prod[order], b_reach[order]
+    if len(b_reach) > 1:   # (a reach enters one node: duplicates would mean a malformed network)
+        dup = (b_cons[1:] == b_cons[:-1]) & (b_reach[1:] == b_reach[:-1])
+        keep = np.concatenate([[True], ~dup])
+        b_cons, b_prod, b_reach = b_cons[keep], b_prod[keep], b_reach[keep]
     shards: list[Shard] = []
-    # boundary edges, in the order the consumer meets them: (consumer, producer) -> [global reach]
     for r in range(world):
         nodes = np.flatnonzero(node_rank == r)
         reaches = np.flatnonzero(reach_rank == r)
         elements = np.flatnonzero(elem_rank == r)
-        node_l = {int(n): i for i, n in enumerate(nodes)}
-        reach_l = {int(q): i for i, q in enumerate(reaches)}
-        elem_l = {int(e): i for i, e in enumerate(elements)}
-        ext_global: list[int] = []
-        ext_l: dict[int, int] = {}
-
-        def ext_row(g: int) -> int:
-            if g not in ext_l:
-                ext_l[g] = len(ext_global)
-                ext_global.append(g)
-            return ext_l[g]
-
-        # first pass: global external rows used here (their local numbers come first)
-        for n in nodes:
-            if river.node_ext[n] >= 0:
-                ext_row(int(river.node_ext[n]))
-            for s in river.entry_src[river.entry_ptr[n]:river.entry_ptr[n + 1]]:
-                if s <= layout.ENTRY_EXT:
-                    ext_row(int(layout.ENTRY_EXT - s))
-        boundary: dict[int, list[int]] = {}       # producer rank -> global reaches, in order of first use
-        brow: dict[int, int] = {}
-        for n in nodes:
-            for s in river.entry_src[river.entry_ptr[n]:river.entry_ptr[n + 1]]:
-                if layout.ENTRY_EXT < s < 0 and reach_rank[-1 - s] != r:
-                    boundary.setdefault(int(reach_rank[-1 - s]), []).append(int(-1 - s))
+        mine = b_cons == r
+        boundary: dict[int, list[int]] = {}
+        for peer in np.unique(b_prod[mine]).tolist():
+            boundary[int(peer)] = b_reach[mine & (b_prod == peer)].tolist()
+        # global external rows used here come first (ascending), then the boundary rows, peer by peer
+        eptr, eidx = _gather(river.entry_ptr, nodes)
+        src = esrc[eidx]
+        used_ext = np.concatenate([river.node_ext[nodes][river.node_ext[nodes] >= 0].astype(np.int64),
+                                   layout.ENTRY_EXT - src[src <= layout.ENTRY_EXT]])
+        ext_global = np.unique(used_ext)
         n_own_ext = len(ext_global)
         recv: list[tuple[int, list[int]]] = []
         k = n_own_ext
+        brow_q: list[int] = []
         for peer in sorted(boundary):
-            rows = []
-            for q in boundary[peer]:
-                brow[q] = k
-                rows.append(k)
-                k += 1
+            rows = list(range(k, k + len(boundary[peer])))
+            brow_q.extend(boundary[peer])
+            k += len(rows)
             recv.append((peer, rows))
-        entry_ptr = [0]
-        entry_src: list[int] = []
-        for n in nodes:
-            for s in river.entry_src[river.entry_ptr[n]:river.entry_ptr[n + 1]]:
-                s = int(s)
-                if s >= 0:
-                    entry_src.append(elem_l[s])
-                elif s <= layout.ENTRY_EXT:
-                    entry_src.append(layout.ENTRY_EXT - ext_l[layout.ENTRY_EXT - s])
-                elif reach_rank[-1 - s] == r:
-                    entry_src.append(-1 - reach_l[-1 - s])
-                else:
-                    entry_src.append(layout.ENTRY_EXT - brow[-1 - s])
-            entry_ptr.append(len(entry_src))
-        inlet_ptr = [0]
-        inlet_node: list[int] = []
-        seg_ptr = [0]
-        dis_parts = []
-        mct_parts: list[np.ndarray] = []
-        trap_ptr = [0]
-        trap_idx: list[int] = []
-        for q in reaches:
-            inlet_node.extend(node_l[int(n)] for n in river.inlet_node[river.inlet_ptr[q]:river.inlet_ptr[q + 1]])
-            inlet_ptr.append(len(inlet_node))
-            seg_ptr.append(seg_ptr[-1] + int(river.seg_ptr[q + 1] - river.seg_ptr[q]))
-            dis_parts.append(discharge[river.seg_ptr[q]:river.seg_ptr[q + 1]])
-            if mct_states is not None:
-                mct_parts.append(mct_states[:, river.seg_ptr[q]:river.seg_ptr[q + 1]])
-            trap_ptr.append(trap_ptr[-1] + int(river.trap_ptr[q + 1] - river.trap_ptr[q]))
-            trap_idx.extend(range(int(river.trap_ptr[q]), int(river.trap_ptr[q + 1])))
-        outlet = np.array([node_l.get(int(river.reach_outlet[q]), -1) if reach_rank[q] == r and
-                           river.reach_outlet[q] >= 0 and node_rank[river.reach_outlet[q]] == r else -1
-                           for q in reaches], np.int32)
+        sh = Shard(rank=r, stage=0, elements=elements, nodes=nodes, reaches=reaches, land=None, states=None, river=None,
+                   discharge=None, ext_global=ext_global, recv=recv, send=[], recv_global=boundary, mct_states=None)
+        shards.append(sh)
+        if r not in build:
+            continue
+        node_l = np.full(nn, -1, np.int64)
+        node_l[nodes] = np.arange(len(nodes))
+        reach_l = np.full(nr, -1, np.int64)
+        reach_l[reaches] = np.arange(len(reaches))
+        elem_l = np.full(len(outlet_node), -1, np.int64)
+        elem_l[elements] = np.arange(len(elements))
+        new_src = np.zeros(len(src), np.int64)
+        m_land = src >= 0
+        new_src[m_land] = elem_l[src[m_land]]
+        m_ext = src <= layout.ENTRY_EXT
+        new_src[m_ext] = layout.ENTRY_EXT - np.searchsorted(ext_global, layout.ENTRY_EXT - src[m_ext])
+        m_reach = ~m_land & ~m_ext
+        q = -1 - src[m_reach]
+        local = reach_rank[q] == r
+        val = np.zeros(len(q), np.int64)
+        val[local] = -1 - reach_l[q[local]]
+        if np.any(~local):
+            brow_arr = np.array(brow_q, np.int64)
+            sorter = np.argsort(brow_arr)
+            pos = sorter[np.searchsorted(brow_arr, q[~local], sorter=sorter)]
+            val[~local] = layout.ENTRY_EXT - (n_own_ext + pos)
+        new_src[m_reach] = val
+        iptr, iidx = _gather(river.inlet_ptr, reaches)
+        sptr, sidx = _gather(river.seg_ptr, reaches)
+        tptr, tidx = _gather(river.trap_ptr, reaches)
+        ro = river.reach_outlet[reaches].astype(np.int64)
+        outlet = np.where((ro >= 0) & (node_rank[np.maximum(ro, 0)] == r), node_l[np.maximum(ro, 0)], -1).astype(np.int32)
+        node_ext_g = river.node_ext[nodes].astype(np.int64)
+        node_ext_l = np.where(node_ext_g >= 0, np.searchsorted(ext_global, np.maximum(node_ext_g, 0)), -1).astype(np.int32)
         sub_river = RiverBundle(
-            entry_ptr=np.array(entry_ptr, np.int64), entry_src=np.array(entry_src, np.int32),
-            node_mode=river.node_mode[nodes], node_ext=np.array(
-                [ext_l[int(x)] if x >= 0 else -1 for x in river.node_ext[nodes]], np.int32),
-            inlet_ptr=np.array(inlet_ptr, np.int64), inlet_node=np.array(inlet_node, np.int32), reach_outlet=outlet,
-            seg_ptr=np.array(seg_ptr, np.int64), coef=river.coef[:, reaches], n_ext=k,
+            entry_ptr=eptr, entry_src=new_src.astype(np.int32), node_mode=river.node_mode[nodes], node_ext=node_ext_l,
+            inlet_ptr=iptr, inlet_node=node_l[river.inlet_node[iidx]].astype(np.int32), reach_outlet=outlet,
+            seg_ptr=sptr, coef=river.coef[:, reaches], n_ext=k,
             reach_model=river.reach_model[reaches], nmbruns=river.nmbruns[reaches], rpar=river.rpar[:, reaches],
-            trap_ptr=np.array(trap_ptr, np.int64), tpar=river.tpar[:, np.array(trap_idx, np.int64)])
+            trap_ptr=tptr, tpar=river.tpar[:, tidx])
         sub_river.normalise()
-        sub_land, sub_states = subset_land(
-            land, states, elements,
-            np.array([node_l.get(int(land.outlet_node[e]), -1) for e in elements], np.int32))
-        shards.append(Shard(
-            rank=r, stage=0, elements=elements, nodes=nodes, reaches=reaches, land=sub_land, states=sub_states,
-            river=sub_river, discharge=np.concatenate(dis_parts + [np.zeros(0)]),
-            ext_global=np.array(ext_global, np.int64), recv=recv, send=[], recv_global=boundary,
-            mct_states=(np.concatenate(mct_parts + [np.zeros((3, 0))], axis=1) if mct_states is not None else None)))
+        sh.river = sub_river
+        sh.discharge = np.ascontiguousarray(discharge[sidx])
+        sh.mct_states = np.ascontiguousarray(mct_states[:, sidx]) if mct_states is not None else None
+        if land is not None:
+            local_outlet = np.where(outlet_node[elements] >= 0, node_l[np.maximum(outlet_node[elements], 0)], -1)
+            sh.land, sh.states = subset_land(land, states, elements, local_outlet.astype(np.int32))
     # sends mirror the receives; stages follow the shard DAG
     for s in shards:
         for peer, _rows in s.recv:
-            reach_l = {int(q): i for i, q in enumerate(shards[peer].reaches)}
-            shards[peer].send.append((s.rank, [reach_l[q] for q in s.recv_global[peer]]))
+            local_q = np.searchsorted(shards[peer].reaches, np.array(s.recv_global[peer], np.int64))
+            shards[peer].send.append((s.rank, local_q.tolist()))
     for s in shards:
         s.send.sort(key=lambda x: x[0])
     changed = True

@@ -311,6 +311,12 @@ int hb_select_series(hb_engine* h, int series, int on);
  * `musk_fluxes.py:14` and `musk_states.py:10-17` (values of the last of the NmbRuns repetitions, as `save_data` sees
  * them, ref: hydpy/cythons/modelutils.py:1127-1167). */
 #define HB_OPT_RIVER_MCT_SERIES 4
+/* HB_OPT_LAND_SLABS (1..8, default 2): the fast path of the runoff generation works on this many slabs of elements, each
+ * on a stream of its own: while the thread-per-element kernel of one slab follows its sequential RecStep chains (few
+ * warps, latency-bound) the thread-per-zone kernel of another slab fills the SMs.  Results do not depend on it. */
+#define HB_OPT_LAND_SLABS 5
+/* HB_OPT_LAND_CHUNK (0 = as long as the scratch memory allows, default; else steps): time chunk of the fast path. */
+#define HB_OPT_LAND_CHUNK 6
 enum hb_mct_series {
   HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
   HB_MS_CORRECTINGFACTOR, HB_MS_COEFFICIENT1, HB_MS_COEFFICIENT2, HB_MS_COEFFICIENT3, HB_MS_COURANTNUMBER,

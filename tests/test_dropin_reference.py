@@ -38,3 +38,14 @@ def test_simulate_with_input_nodes_like_the_reference_does():
                           capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "DROPIN_OK" in proc.stdout
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+@pytest.mark.parametrize("module", ["hland_96", "musk_classic", "hland_96p", "hland_96c", "musk_mct"])
+def test_reference_integration_doctests_with_the_dropin_installed(module):
+    """The reference's own integration-test docstrings (every sequence of every step, six digits) with `HydPy.simulate`
+    replaced by `hydpy_b200.install()`; the oracle stands in for the engine here (tests/test_gpu_dropin.py: the engine)."""
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "doctest_reference_worker.py"), module],
+                          capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-3000:]
+    assert "DOCTEST_OK" in proc.stdout

@@ -425,3 +425,42 @@ def test_full_size_routing_sweeps_agree_bit_for_bit():
     assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1]), "grouped wavefront differs from the diagonal sweep"
     assert np.isfinite(a[0]).all() and a[0][0].max() > 0.0
     assert_close(b[0], c[0], "full size: fast vs general land path, node series")
+
+
+def test_element_slabs_and_time_chunks_do_not_change_a_bit():
+    """HB_OPT_LAND_SLABS / HB_OPT_LAND_CHUNK only decide which stream and launch computes what: every combination must
+    give the bits of the single-slab, single-chunk run — pipelined windows included (slabs of consecutive windows overlap)."""
+    ne, win, nw = 5000, 36, 4
+    land, states = synth.make_land(ne, "1h", variants=True)
+    river, discharge = synth.make_tree_river(ne, "1h", levels=25)
+    forcing, doy = synth.make_forcing(win * nw, "1h")
+    no_ext = np.zeros((0, win))
+    results = []
+    with Engine(0) as eng:
+        for slabs, chunk in ((1, 0), (2, 0), (3, 7), (8, 5), (5, 36)):
+            eng.set_land(land)
+            eng.set_land_states(states)
+            eng.set_river(river)
+            eng.set_river_states(discharge)
+            eng.set_land_slabs(slabs)
+            eng.set_land_chunk(chunk)
+            eng.set_forcing(forcing, doy)
+            bufs = [eng.pinned((river.n_node, win)) for _ in range(nw)]
+            for w in range(nw):
+                eng.select_window(w * win, win)
+                eng.set_external(no_ext)
+                eng.run_async()
+                eng.get_node_series_async(bufs[w].array)
+            eng.wait()
+            st = eng.get_land_states()
+            results.append(([b.array.copy() for b in bufs], st, eng.get_river_states()))
+            for b in bufs:
+                b.free()
+    rows0, st0, dis0 = results[0]
+    assert np.isfinite(rows0[-1]).all() and rows0[-1].max() > 0.0
+    for rows, st, dis in results[1:]:
+        for a, b in zip(rows0, rows):
+            assert np.array_equal(a, b)
+        assert np.array_equal(dis0, dis)
+        for n in st0.NAMES:
+            assert np.array_equal(getattr(st0, n), getattr(st, n)), n
