@@ -2,18 +2,23 @@
 """bench.py — zone-timesteps/s of the hland_96 + musk_classic hot path on N B200s (contract: see the task prompt).
 
 Workload (``config.workload``): BASELINE.json configs[3] — the synthetic 10^5-element hland_96 + 10^5-reach
-musk_classic river tree (≈200 topological levels), HOURLY, discharge-only output — the configuration the
-north_star's ≥100x target is quoted on.  One *step* = one simulation window of ``--window`` hours (default 240 = 10 days)
-for ALL elements followed by routing through the whole network; consecutive steps continue the same simulation
-(states stay on the device), so K steps simulate K*window hours of the 10-year period.
+musk_classic river tree (≈200 topological levels), HOURLY, discharge-only — the configuration the
+north_star's ≥100x target is quoted on.  One *step* = one simulation window of ``--window`` hours (default 438: the 20
+timed steps of the driver cover one year) for ALL elements followed by routing through the whole network; consecutive
+steps continue the same simulation (states stay on the device).
 
 * ``value``  — whole-job zone-timesteps/s with the forcing of all K windows already resident in HBM (device time, CUDA
   events on the engine stream, max over ranks).
 * ``e2e``    — the same loop through the public API with HOST buffers: every step copies that window's forcing from
   pinned host memory to the device and reads every node's discharge series back to pinned host memory.
-* N > 1     — weak scaling, element-sharded: every rank owns one 10^5-element sub-basin; the outlet reach of each
-  upstream shard hands its outflow series to the shard owning the downstream node with NCCL send/recv over NVLink
-  (the one real exchange step of the path).
+* N > 1     — ONE river basin, cut by ``hydpy_b200.shard`` into N sub-networks of equal weight (one process per GPU):
+  every boundary reach hands its outflow series to the rank that owns the downstream node with NCCL send/recv over
+  NVLink, and the receiving rank's routing WAITS for it (the one real exchange step of the path).
+  ``--scaling weak`` (default): the basin grows with N (N x 10^5 elements, the same depth); ``--scaling strong``: the
+  10^5-element basin of N = 1 is cut into N parts.  The last rank re-runs the first window of the WHOLE basin on its own
+  GPU and compares its nodes bit for bit (``multi_gpu_parity``).
+* ``--config 1`` / ``--config 4`` — BASELINE.json configs[1] (HydPy-H-Lahn hourly x 4096 parameter-ensemble members) and
+  configs[4] (10^6 zones x 512 members), member-sharded over the ranks (no exchange: every member is a complete basin).
 * ``--impl reference`` — the reference's own CPU implementation of the same window on a bounded element sample with all
   host threads (oracle/_ref = unmodified reference binaries when present, else the C restatement).
 """
@@ -54,6 +59,11 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-blocks", type=int, default=0, help="persistent routing blocks per SM (0 = engine default)")
     ap.add_argument("--river-sweep", default="", help="routing sweep: persistent | grouped | launches (default: engine's)")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="N > 1: weak = one basin of N x --elements elements, strong = the --elements basin cut into N parts")
+    ap.add_argument("--config", type=int, choices=(1, 3, 4), default=3, help="BASELINE.json configs[i] (default 3)")
+    ap.add_argument("--members", type=int, default=0, help="ensemble members of --config 1 / 4 in total (0 = 4096 / 512)")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the unsharded run")
     ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
     ap.add_argument("--land-chunk", type=int, default=0, help="time chunk of the fast land path in steps (0 = engine default)")
     return ap.parse_args()
@@ -86,6 +96,18 @@ class Dist:
 
         t = torch.tensor([value], dtype=torch.float64)
         self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t[0])
+
+    def min(self, value: float) -> float:
+        return -self.max(-value)
+
+    def bcast_float(self, value: float, src: int) -> float:
+        if self.pg is None:
+            return value
+        import torch
+
+        t = torch.tensor([value], dtype=torch.float64)
+        self.pg.broadcast(t, src=src)
         return float(t[0])
 
     def sum(self, value: float) -> float:
@@ -167,39 +189,58 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------------
-def build_shard(args: argparse.Namespace, rank: int, world: int):
-    """Sub-basin of one rank: land elements, river tree and — for world > 1 — the cut edges."""
-    from hydpy_b200 import layout, synth
+class Workload:
+    """What one rank simulates: its bundles, the exchange plan of a window and how to describe / verify it."""
 
-    land, states = synth.make_land(args.elements, "1h", seed=1 + rank)
-    river, discharge = synth.make_tree_river(args.elements, "1h", seed=2 + rank, levels=args.levels)
-    if world > 1:
-        rng = np.random.default_rng(100 + rank)
-        if rank == 0:
-            # the root node additionally receives the outflow of every upstream shard as external rows
-            ext_entries = [layout.ENTRY_EXT - k for k in range(world - 1)]
-            src = river.entry_src.tolist()
-            end0 = int(river.entry_ptr[1])
-            src[end0:end0] = ext_entries
-            river.entry_src = np.array(src, np.int32)
-            river.entry_ptr = river.entry_ptr.copy()
-            river.entry_ptr[1:] += len(ext_entries)
-            river.n_ext = world - 1
-        else:
-            # one more reach routes this shard's root node towards the downstream shard (owner of the reach = upstream)
-            nseg = int(rng.integers(1, 24))
-            damp = float(rng.uniform(0, 1))
-            c0 = damp / (1.0 + damp)
-            river.inlet_ptr = np.append(river.inlet_ptr, river.inlet_ptr[-1] + 1)
-            river.inlet_node = np.append(river.inlet_node, 0).astype(np.int32)
-            river.reach_outlet = np.append(river.reach_outlet, -1).astype(np.int32)
-            river.seg_ptr = np.append(river.seg_ptr, river.seg_ptr[-1] + nseg + 1)
-            river.coef = np.concatenate([river.coef, np.array([[c0], [1 - 2 * c0], [c0]])], axis=1)
-            discharge = np.concatenate([discharge, np.zeros(nseg + 1)])
-        # (the per-reach arrays of the musk_mct extension are regenerated for the changed reach count: all musk_classic)
-        river.reach_model = river.nmbruns = river.rpar = river.trap_ptr = river.tpar = None
-        river.normalise()
-    return land, states, river, discharge
+    def __init__(self, land, states, river, discharge, recv=(), send=(), *, desc: dict, forcing_seed: int = 0,
+                 forcing_fixed=None, members: int = 1, verify=None):
+        self.land, self.states, self.river, self.discharge = land, states, river, discharge
+        self.recv, self.send = list(recv), list(send)
+        self.desc, self.forcing_seed, self.forcing_fixed = desc, forcing_seed, forcing_fixed
+        self.members = members            # ensemble members on this rank (created on the device: hb_set_members)
+        self.verify = verify
+
+
+def build_shard(args: argparse.Namespace, rank: int, world: int) -> Workload:
+    """configs[3]: this rank's part of ONE river basin.  N = 1: the whole basin.  The basin is generated
+    as a whole where that is cheap (river tree, random draws of the land parameters); the land bundles — the bulk of the
+    memory — only for the rank's own elements."""
+    from hydpy_b200 import shard, synth
+
+    n_total = args.elements * (world if args.scaling == "weak" else 1)
+    river_g, dis_g = synth.make_tree_river(n_total, "1h", seed=2, levels=args.levels)
+    desc = {"workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, hourly, discharge-only",
+            "basin_elements": n_total}
+    if world == 1:
+        land, states = synth.make_land(n_total, "1h", seed=1)
+        return Workload(land, states, river_g, dis_g, desc=desc)
+    outlet = np.arange(n_total)
+    node_rank = shard.assign_nodes(None, river_g, world, outlet_node=outlet, zones=np.full(n_total, 12.0))
+    s = shard.partition(None, None, river_g, dis_g, world, node_rank=node_rank, ranks=[rank], outlet_node=outlet)[rank]
+    land, states = synth.make_land(n_total, "1h", seed=1, select=s.elements)   # element i drains to node i: local = local
+    desc.update({"shard_elements": int(len(s.elements)), "shard_stage": int(s.stage),
+                 "boundary_rows_received": int(sum(len(r) for _, r in s.recv)),
+                 "boundary_rows_sent": int(sum(len(r) for _, r in s.send))})
+
+    def verify(eng, forcing, doy, rows_sharded: np.ndarray) -> bool:
+        """The whole basin on this rank's GPU, first window from the initial states: this rank's nodes, bit for bit."""
+        g_land, g_states = synth.make_land(n_total, "1h", seed=1)
+        eng.set_land(g_land)
+        eng.set_land_states(g_states)
+        eng.set_river(river_g)
+        eng.set_river_states(dis_g)
+        eng.set_forcing(forcing, doy)
+        eng.set_external(np.zeros((0, forcing.shape[1])))
+        eng.run(land=True, river=True)
+        return bool(np.array_equal(eng.get_node_series(nodes=s.nodes), rows_sharded))
+
+    return Workload(land, states, s.river, s.discharge, s.recv, s.send, desc=desc, verify=verify)
+
+
+def build_workload(args: argparse.Namespace, dist: "Dist") -> Workload:
+    if args.config == 3:
+        return build_shard(args, dist.rank, dist.world)
+    return build_members(args, dist.rank, dist.world)
 
 
 def pin_to_gpu_numa_node(device: int) -> None:
@@ -223,7 +264,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     K, W, win = args.steps, args.warmup, args.window
     eng = Engine(dist.local_rank)
     info = eng.device_info()
-    land, states, river, discharge = build_shard(args, dist.rank, dist.world)
+    wl = build_workload(args, dist)
+    land, states, river, discharge = wl.land, wl.states, wl.river, wl.discharge
     eng.set_land(land)
     eng.set_land_states(states)
     eng.set_river(river)
@@ -239,31 +281,29 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     if dist.world > 1:
         uid = dist.bcast_bytes(eng.comm_unique_id() if dist.rank == 0 else None, 128)
         eng.comm_init(dist.rank, dist.world, uid)
-    boundary_reach = river.n_reach - 1
-    no_ext = np.zeros((0, win))
+    own_ext = np.zeros((river.n_ext, win))      # (no rows of the global external block in these workloads: all zero)
 
     def step_exchange_and_route() -> None:
         """land → (NVLink hand-over of the boundary series) → routing, for the currently staged window.  Enqueued on
-        the engine's pipeline (hb_run_async): the next window's runoff generation overlaps this window's routing."""
-        if dist.world == 1:
-            eng.set_external(no_ext)
+        the engine's pipeline (hb_run_async): the next window's runoff generation overlaps this window's routing, and
+        an upstream rank works on window w+1 while the ranks below it still route window w."""
+        if not wl.recv:
+            eng.set_external(own_ext)
             eng.run_async(land=True, river=True)
-        elif dist.rank == 0:
-            eng.run_async(land=True, river=False)
-            for peer in range(1, dist.world):
-                eng.comm_recv_ext(peer, [peer - 1])
-            eng.run_async(land=False, river=True)
         else:
-            eng.set_external(no_ext)
-            eng.run_async(land=True, river=True)
-            eng.comm_send_rows(0, [boundary_reach], kind="reach")
+            eng.run_async(land=True, river=False)
+            for peer, rows in wl.recv:                      # straight into the external rows the reaches read
+                eng.comm_recv_ext(peer, rows)
+            eng.run_async(land=False, river=True)           # (waits on the device for the received rows)
+        for peer, reaches in wl.send:                       # straight from the routing result buffer
+            eng.comm_send_rows(peer, reaches, kind="reach")
 
     n_steps = W + K
     # ---- forcing of all windows: generated up front (synthetic, seeded per window) in pinned host memory ----------------
     pinned = eng.pinned((n_steps, 4, win, 1024))
     doys = np.zeros((n_steps, win), np.int64)
     for s in range(n_steps):
-        f, doys[s] = synth.make_forcing(win, "1h", seed=dist.rank, t0=s * win, kind=args.forcing)
+        f, doys[s] = synth.make_forcing(win, "1h", seed=wl.forcing_seed, t0=s * win, kind=args.forcing)
         pinned.array[s] = f
     zone_steps_per_step = land.n_zone * win
     launches = 0
@@ -326,6 +366,55 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     checksum = float(outs[(W + K - 1) & 1].array[0].sum())
     states_after_e2e = eng.get_land_states()
     same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
+
+    # ---- the same with the gauged nodes only (1 % of the nodes, hb_get_node_series_async with a selection): what a user
+    # who keeps the series of the gauges pays; at 8 ranks the copy of ALL node series is bound by the host's memory
+    gauges = np.sort(np.random.default_rng(5).choice(river.n_node, size=max(1, river.n_node // 100), replace=False))
+    gouts = [eng.pinned((len(gauges), win)), eng.pinned((len(gauges), win))]
+    eng.set_land_states(states)
+    eng.set_river_states(discharge)
+    dist.barrier()
+    for s in range(W):
+        eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
+        step_exchange_and_route()
+        eng.get_node_series_async(gouts[s & 1].array, gauges)
+    eng.wait()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
+        step_exchange_and_route()
+        eng.get_node_series_async(gouts[s & 1].array, gauges)
+    eng.wait()
+    e2e_g_s = time.perf_counter() - t0
+    dist.barrier()
+    e2e_gauged = {"value": total_zone_steps / dist.max(e2e_g_s), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": int(len(gauges)) * win * 8, "ms_per_step": 1e3 * dist.max(e2e_g_s) / K,
+                  "nodes_returned_per_rank": int(len(gauges)),
+                  "same_rows_as_full_copy": bool(np.array_equal(gouts[(W + K - 1) & 1].array,
+                                                                outs[(W + K - 1) & 1].array[gauges]))}
+    for o in gouts:
+        o.free()
+
+    # ================= N > 1: the sharded run against the unsharded one ==================================================
+    parity = None
+    if dist.world > 1 and not args.no_verify and wl.verify is not None:
+        eng.set_land_states(states)
+        eng.set_river_states(discharge)
+        eng.set_forcing(np.ascontiguousarray(pinned.array[0]), doys[0])
+        step_exchange_and_route()
+        eng.wait()
+        rows0 = eng.get_node_series()
+        dist.barrier()
+        ok = 1.0
+        checker = dist.world - 1                             # the last rank holds the outlet (and the highest stage)
+        if dist.rank == checker:
+            ok = 1.0 if wl.verify(eng, np.ascontiguousarray(pinned.array[0]), doys[0], rows0) else 0.0
+            # (the engine now holds the whole basin; nothing below uses the shard again)
+        ok = dist.min(ok)
+        parity = {"bit_identical_to_unsharded_run": bool(ok == 1.0), "checked_on_rank": checker,
+                  "nodes_compared": int(dist.bcast_float(float(river.n_node), checker)), "window": 0}
+        dist.barrier()
 
     # ================= the same kernels timed alone (synchronous windows, nothing overlapping) ===========================
     iso = {"zone_ms": 0.0, "element_ms": 0.0, "general_ms": 0.0, "river_ms": 0.0}
@@ -430,20 +519,26 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     }[args.forcing]
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": K, "warmup": W,
-        "ms_per_step": device_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": device_ms_max / K, "higher_is_better": True,
+        "scaling": args.scaling if args.config == 3 else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, hourly, discharge-only",
+            **wl.desc,
             "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
             "river_levels": n_levels, "window_steps": win, "simulated_days_timed": K * win / 24.0,
             "recstep_per_step": R, "uh_ordinates": U,
-            "forcing_bank": 1024, "parallelism": f"element-sharded x{dist.world}" if dist.world > 1 else "single GPU",
+            "forcing_bank": 1024,
+            "parallelism": (f"one basin, element-sharded x{dist.world} by hydpy_b200.shard.partition, NCCL boundary "
+                            f"series feed the downstream reaches" if dist.world > 1 and args.config == 3 else
+                            f"member-sharded x{dist.world}" if dist.world > 1 else "single GPU"),
+            "nvlink_bytes_per_step_this_rank": 8 * win * (sum(len(r) for _, r in wl.recv) + sum(len(r) for _, r in wl.send)),
             "l2": "per step the zone terms (16 B per zone-step) and the node/reach rows stream through HBM "
                   "(> 126 MB L2); no flush needed",
             "forcing": forcing_note, **executed,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
+        "e2e_gauged_nodes": e2e_gauged, "multi_gpu_parity": parity,
         "gpu_launches": launches,
         "kernel_ms_per_step": {"runoff_generation": land_ms_avg, "routing": float(np.mean(river_ms)),
                                "wall": wall_ms / K,

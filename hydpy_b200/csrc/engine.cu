@@ -237,6 +237,11 @@ struct hb_engine {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DBuf<double> d_commbuf;
+  // boundary rows travel packed: one message per peer and window.  Staging buffers per (window buffer set, call of the
+  // window); `comm_calls` counts the send/receive calls since the window was staged
+  std::vector<DBuf<double>> d_comm_stage[2];
+  std::vector<DBuf<int32_t>> d_comm_rows[2];
+  int comm_calls[2] = {0, 0};
 
   hb_timing timing{};
 
@@ -1253,6 +1258,7 @@ static int stage_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* 
   h->t0 = 0;
   h->n_col = n_col;
   h->cur ^= 1;
+  h->comm_calls[h->cur] = 0;
   h->have_forcing = true;
   h->have_results = false;
   h->have_routed = false;
@@ -1285,6 +1291,7 @@ int hb_select_window(hb_engine* h, int64_t t0, int64_t nt) {
   h->t0 = t0;
   h->nt = nt;
   h->cur ^= 1;
+  h->comm_calls[h->cur] = 0;
   h->have_results = false;
   h->have_routed = false;
   h->have_ext = false;
@@ -2128,6 +2135,26 @@ int hb_comm_init(hb_engine* h, int rank, int world, const void* id) {
   return HB_OK;
 }
 
+__global__ void scatter_rows_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                    const int32_t* __restrict__ sel, int64_t n_sel, int64_t nt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sel * nt) return;
+  const int64_t r = i / nt, t = i - r * nt;
+  dst[(int64_t)sel[r] * nt + t] = src[i];
+}
+
+// staging slot of the next send/receive call of the current window
+static int comm_slot(hb_engine* h, size_t n_rows, size_t n_values, double** stage, int32_t** rows_dev) {
+  const int c = h->cur;
+  const size_t slot = (size_t)h->comm_calls[c]++;
+  if (h->d_comm_stage[c].size() <= slot) { h->d_comm_stage[c].resize(slot + 1); h->d_comm_rows[c].resize(slot + 1); }
+  HB_CUDA(h, h->d_comm_stage[c][slot].reserve(n_values));
+  HB_CUDA(h, h->d_comm_rows[c][slot].reserve(n_rows));
+  *stage = h->d_comm_stage[c][slot].p;
+  *rows_dev = h->d_comm_rows[c][slot].p;
+  return HB_OK;
+}
+
 int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t* rows) {
   if (!h) return HB_EINVAL;
   HB_REQUIRE(h, h->comm, HB_ESTATE, "hb_comm_send_rows: call hb_comm_init first");
@@ -2140,13 +2167,24 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
   const double* base = kind == HB_ROW_NODE ? h->d_node_rows[h->cur].p : h->d_reach_out[h->cur].p;
   for (int64_t i = 0; i < n; ++i)
     HB_REQUIRE(h, rows[i] >= 0 && rows[i] < limit, HB_EINVAL, "hb_comm_send_rows: row %d out of range", rows[i]);
+  if (n == 0 || h->nt == 0) return HB_OK;
   // all NCCL traffic of this engine runs on ONE stream (s_comm); the send waits for the routing of the window
   HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
-  HB_NCCL(h, h->nccl.GroupStart());
-  // the routing kernels wrote the rows in place: they are sent straight from the result buffers over NVLink
-  for (int64_t i = 0; i < n; ++i)
-    HB_NCCL(h, h->nccl.Send(base + (int64_t)rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
-  HB_NCCL(h, h->nccl.GroupEnd());
+  const double* src = base + (int64_t)rows[0] * h->nt;
+  if (n > 1) {
+    // the rows of a peer travel as ONE message: packed by a gather kernel behind the routing (a basin cut into sub-basins
+    // hands over hundreds of short series per window; one NCCL operation per row would cost more than the transfer)
+    double* stage = nullptr;
+    int32_t* rows_dev = nullptr;
+    int rc = comm_slot(h, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
+    if (rc) return rc;
+    HB_CUDA(h, cudaMemcpyAsync(rows_dev, rows, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_comm));
+    const size_t total = (size_t)n * h->nt;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comm>>>(base, stage, rows_dev, n, h->nt);
+    HB_CUDA(h, cudaGetLastError());
+    src = stage;
+  }
+  HB_NCCL(h, h->nccl.Send(src, (size_t)n * h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
   HB_CUDA(h, cudaEventRecord(h->ev_send_done[h->cur], h->s_comm));
   h->pending = true;
   return HB_OK;
@@ -2159,21 +2197,38 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
   HB_REQUIRE(h, peer >= 0 && peer < h->world && peer != h->rank && n >= 0 && (n == 0 || ext_rows), HB_EINVAL,
              "hb_comm_recv_ext: invalid argument");
   HB_CUDA(h, cudaSetDevice(h->device));
-  for (int64_t i = 0; i < n; ++i)   // (before the group opens: no error path may leave it open)
+  bool contiguous = true;
+  for (int64_t i = 0; i < n; ++i) {   // (before any NCCL call: no error path may leave an operation half posted)
     HB_REQUIRE(h, ext_rows[i] >= 0 && ext_rows[i] < h->n_ext, HB_EINVAL, "hb_comm_recv_ext: row %d out of range", ext_rows[i]);
-  HB_CUDA(h, h->d_ext_rows[h->cur].reserve((size_t)h->n_ext * h->nt));
-  // the routing of two windows ago was the last reader of this buffer set
-  HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
-  HB_NCCL(h, h->nccl.GroupStart());
-  for (int64_t i = 0; i < n; ++i) {
-    // received straight into the external-row buffer the reach kernels read
-    HB_NCCL(h, h->nccl.Recv(h->d_ext_rows[h->cur].p + (int64_t)ext_rows[i] * h->nt, (size_t)h->nt, kNcclFloat64, peer, h->comm,
-                            h->s_comm));
+    if (i > 0 && ext_rows[i] != ext_rows[i - 1] + 1) contiguous = false;
   }
-  HB_NCCL(h, h->nccl.GroupEnd());
-  HB_CUDA(h, cudaEventRecord(h->ev_ext_ready[h->cur], h->s_comm));
+  HB_CUDA(h, h->d_ext_rows[h->cur].reserve((size_t)h->n_ext * h->nt));
   h->ext_async[h->cur] = true;
   h->have_ext = true;
+  if (n == 0 || h->nt == 0) {
+    HB_CUDA(h, cudaEventRecord(h->ev_ext_ready[h->cur], h->s_comm));
+    return HB_OK;
+  }
+  // the routing of two windows ago was the last reader of this buffer set
+  HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
+  // ONE message per peer (see hb_comm_send_rows).  Consecutive external rows — what hydpy_b200.shard hands out — are
+  // received straight into the buffer the reach kernels read; any other selection goes through a staging buffer
+  if (contiguous) {
+    HB_NCCL(h, h->nccl.Recv(h->d_ext_rows[h->cur].p + (int64_t)ext_rows[0] * h->nt, (size_t)n * h->nt, kNcclFloat64, peer,
+                            h->comm, h->s_comm));
+  } else {
+    double* stage = nullptr;
+    int32_t* rows_dev = nullptr;
+    int rc = comm_slot(h, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
+    if (rc) return rc;
+    HB_CUDA(h, cudaMemcpyAsync(rows_dev, ext_rows, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_comm));
+    HB_NCCL(h, h->nccl.Recv(stage, (size_t)n * h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
+    const size_t total = (size_t)n * h->nt;
+    scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comm>>>(stage, h->d_ext_rows[h->cur].p, rows_dev, n,
+                                                                               h->nt);
+    HB_CUDA(h, cudaGetLastError());
+  }
+  HB_CUDA(h, cudaEventRecord(h->ev_ext_ready[h->cur], h->s_comm));
   h->pending = true;
   return HB_OK;
 }

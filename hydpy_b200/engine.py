@@ -345,14 +345,20 @@ class Engine:
     def wait(self) -> None:
         self._check(self._lib.hb_wait(self._h), "hb_wait")
 
-    def get_node_series_async(self, out: np.ndarray) -> None:
-        """Copy all node series of the current window into the PINNED array `out` behind its routing; valid after
-        `wait()`."""
+    def get_node_series_async(self, out: np.ndarray, nodes: np.ndarray | None = None) -> None:
+        """Copy the node series of the current window — all nodes, or the rows of `nodes` (e.g. the gauged ones) — into
+        the PINNED array `out` behind its routing; valid after `wait()`."""
         river = self._need_river()
-        if out.shape != (river.n_node, self.nt) or out.dtype != np.float64 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous float64 array of shape (n_node, nt)")
-        self._check(self._lib.hb_get_node_series_async(self._h, 0, None, ptr(out, C.c_double)),
-                    "hb_get_node_series_async")
+        n_rows = river.n_node if nodes is None else len(nodes)
+        if out.shape != (n_rows, self.nt) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (number of rows, nt)")
+        if nodes is None:
+            self._check(self._lib.hb_get_node_series_async(self._h, 0, None, ptr(out, C.c_double)),
+                        "hb_get_node_series_async")
+        elif n_rows:
+            sel = np.ascontiguousarray(nodes, dtype=np.int32)
+            self._check(self._lib.hb_get_node_series_async(self._h, n_rows, ptr(sel, C.c_int32), ptr(out, C.c_double)),
+                        "hb_get_node_series_async")
 
     @property
     def window_steps(self) -> int:

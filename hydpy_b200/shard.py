@@ -100,14 +100,20 @@ def scatter_states(shard: Shard, local: LandStates, land: LandBundle, out: LandS
 
 
 def assign_nodes(land: LandBundle | None, river: RiverBundle, world: int, *, outlet_node: np.ndarray | None = None,
-                 zones: np.ndarray | None = None) -> np.ndarray:
-    """Rank of every node: `world` ranges of equal weight (zones of the land elements + a share for the reach segments)
-    of an UPSTREAM-FIRST ordering of the network.
+                 zones: np.ndarray | None = None, method: str = "subtrees", granularity: int = 8) -> np.ndarray:
+    """Rank of every node: `world` parts of equal weight (zones of the land elements + a share for the reach segments).
 
     Nodes that feed the same reach are kept together (a reach reads all its inlet nodes locally; a reach lives with its
-    inlet nodes).  The order is the post-order of a depth-first walk from the outlets towards the headwaters, so sub-
-    networks are contiguous in it and every node comes after everything upstream of it: cutting the order into ranges
-    gives balanced shards whose boundary series only travel from lower to higher ranks (an acyclic shard graph)."""
+    inlet nodes).  Two methods, both on an UPSTREAM-FIRST ordering of the network (the post-order of a depth-first walk
+    from the outlets towards the headwaters: sub-networks are contiguous in it):
+
+    * "subtrees" (river trees; the default): the largest sub-basins are split at their outlet node until none is heavier
+      than 1/(granularity * world) of the basin; the split nodes form the *trunk*, the remaining complete sub-basins are
+      packed into `world` bins of equal weight (largest first), the trunk joins the last one.  Ranks 0 … world-2 then own
+      complete sub-basins only — they never wait for anybody — and the last rank routes the trunk: the shard graph is
+      one stage deep, so the skew between ranks is ONE routing pass whatever the number of GPUs;
+    * "ranges": the order is cut into `world` ranges of equal weight; boundary series only travel from lower to higher
+      ranks (acyclic for any DAG), but the stages form a chain.  Fallback for networks with bifurcations."""
     nn, nr = river.n_node, river.n_reach
     if outlet_node is None:
         outlet_node = land.outlet_node if land is not None else np.zeros(0, np.int32)
@@ -147,16 +153,18 @@ def assign_nodes(land: LandBundle | None, river: RiverBundle, world: int, *, out
     dst_g = group[river.reach_outlet[out_ok]]
     keep = src_g != dst_g
     src_g, dst_g = src_g[keep], dst_g[keep]
-    order_e = np.argsort(dst_g, kind="stable")
-    up_of = src_g[order_e]                                   # upstream groups, grouped by downstream group
+    if len(src_g):                                           # (parallel reaches between two groups: one edge)
+        pair = np.unique(np.stack([dst_g, src_g], axis=1), axis=0)
+        dst_g, src_g = pair[:, 0], pair[:, 1]
+    up_of = src_g                                            # upstream groups, sorted by downstream group
     up_ptr = np.zeros(nn + 1, np.int64)
     np.add.at(up_ptr, dst_g + 1, 1)
     np.cumsum(up_ptr, out=up_ptr)
     is_group = np.zeros(nn, bool)
     is_group[group] = True
-    has_down = np.zeros(nn, bool)
-    has_down[src_g] = True
-    roots = np.flatnonzero(is_group & ~has_down)
+    n_down = np.zeros(nn, np.int64)
+    np.add.at(n_down, src_g, 1)
+    roots = np.flatnonzero(is_group & (n_down == 0))
     visited = np.zeros(nn, bool)
     post: list[int] = []
     up_ptr_l, up_of_l = up_ptr.tolist(), up_of.tolist()
@@ -185,9 +193,50 @@ def assign_nodes(land: LandBundle | None, river: RiverBundle, world: int, *, out
     if total <= 0.0:
         w = np.ones(len(post_arr))
         total = float(len(post_arr))
+    rank = np.zeros(nn, np.int64)
+    is_tree = bool(np.all(n_down[post_arr] <= 1)) and len(post_arr) == len(post)
+    if method == "subtrees" and is_tree and world > 1:
+        import heapq
+
+        # sub-basin of a group = a contiguous stretch of the post-order that ends at the group
+        pos = np.zeros(nn, np.int64)
+        pos[post_arr] = np.arange(len(post_arr))
+        down = np.full(nn, -1, np.int64)
+        down[src_g] = dst_g
+        acc = np.zeros(nn)
+        acc[post_arr] = w
+        size = np.zeros(nn, np.int64)
+        size[post_arr] = 1
+        acc_l, size_l, down_l = acc.tolist(), size.tolist(), down.tolist()
+        for g in post_arr.tolist():                          # upstream first: every group hands its sum downstream
+            d = down_l[g]
+            if d >= 0:
+                acc_l[d] += acc_l[g]
+                size_l[d] += size_l[g]
+        limit = total / (max(granularity, 1) * world)
+        heap = [(-acc_l[r], r) for r in roots.tolist()]
+        heapq.heapify(heap)
+        trunk: list[int] = []
+        parts: list[tuple[float, int]] = []
+        while heap:
+            neg, g = heapq.heappop(heap)
+            if -neg <= limit or up_ptr_l[g] == up_ptr_l[g + 1]:
+                parts.append((-neg, g))
+                continue
+            trunk.append(g)
+            for i in range(up_ptr_l[g], up_ptr_l[g + 1]):
+                c = up_of_l[i]
+                heapq.heappush(heap, (-acc_l[c], c))
+        bins = [0.0] * world
+        bins[world - 1] = float(sum(weight[g] for g in trunk))
+        rank_of_group = np.full(nn, world - 1, np.int64)     # the trunk stays with the last rank
+        for wt, g in sorted(parts, reverse=True):
+            b = min(range(world), key=lambda i: (bins[i], -i))
+            bins[b] += wt
+            rank_of_group[post_arr[pos[g] - size_l[g] + 1:pos[g] + 1]] = b
+        return rank_of_group[group]
     mid = np.cumsum(w) - 0.5 * w
     rank_of_group = np.minimum((mid / (total / max(world, 1))).astype(np.int64), world - 1)
-    rank = np.zeros(nn, np.int64)
     rank[post_arr] = rank_of_group
     return rank[group]
 

@@ -40,32 +40,43 @@ def load_template(step: str) -> dict[str, np.ndarray]:
 
 def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, bank: int = 1024,
               variants: bool = False, jitter: float = 0.1, area: float = 100.0,
-              own_nodes: bool = True, cflux: float = 0.0, model: str = "hland_96") -> tuple[LandBundle, LandStates]:
+              own_nodes: bool = True, cflux: float = 0.0, model: str = "hland_96",
+              select: np.ndarray | None = None) -> tuple[LandBundle, LandStates]:
     """`n_elem` synthetic hland_96 elements (configs 3-5).  `cflux` > 0 (mm per simulation step, jittered like the other
-    parameters) switches the capillary flux on, i.e. couples the zones to the element's upper zone storage."""
+    parameters) switches the capillary flux on, i.e. couples the zones to the element's upper zone storage.
+
+    `select` (ascending global element indices): build only these elements of the `n_elem`-element basin — the random
+    draws are those of the whole basin, so a shard of a large basin gets exactly the elements the whole would have
+    (forcing columns follow the global index; the outlet nodes are numbered locally, 0 … len(select)-1)."""
     tpl = load_template(step)
     tz = tpl["zpar"].shape[1]
     rng = np.random.default_rng(seed)
-    ne, nz = int(n_elem), int(zones)
+    n_all, nz = int(n_elem), int(zones)
+    sel = np.arange(n_all) if select is None else np.asarray(select, np.int64)
+    ne = len(sel)
+
+    def draw(size) -> np.ndarray:     # one draw per element of the WHOLE basin, then the selection
+        return rng.uniform(-1.0, 1.0, size=size)[sel]
+
     idx = np.arange(nz) % tz                      # template zone used for every slot (FIELD/FOREST alternating)
     zpar = np.repeat(tpl["zpar"][:, idx][:, None, :], ne, axis=1)        # [P, ne, nz]
     zonetype = np.repeat(tpl["zonetype"][idx][None, :], ne, axis=0).astype(np.int32)
     zflags = np.repeat(tpl["zflags"][idx][None, :], ne, axis=0).astype(np.int32)
     ZP = layout.ZP
     for name in JITTER_ZONE:
-        f = 1.0 + jitter * rng.uniform(-1.0, 1.0, size=(ne, 1))
+        f = 1.0 + jitter * draw((n_all, 1))
         zpar[ZP[name]] *= f
-    zpar[ZP["tt"]] += jitter * rng.uniform(-1.0, 1.0, size=(ne, 1))
+    zpar[ZP["tt"]] += jitter * draw((n_all, 1))
     zpar[ZP["ttm"]] = zpar[ZP["tt"]]                                      # dttm = 0 as in the Lahn project
     zpar[ZP["maxsoilwater"]] = zpar[ZP["fc"]]
     zpar[ZP["smax"]] = np.inf
-    zpar[ZP["cflux"]] = 0.0 * zpar[ZP["cflux"]] + cflux * (1.0 + jitter * rng.uniform(-1.0, 1.0, size=(ne, 1)))
+    zpar[ZP["cflux"]] = 0.0 * zpar[ZP["cflux"]] + cflux * (1.0 + jitter * draw((n_all, 1)))
     zonez = np.linspace(2.0, 7.0, nz)
     zpar[ZP["zonez"]] = zonez[None, :]
     zpar[ZP["hrualtitude"]] = 100.0 * zonez[None, :]
     if variants:
         # 5 % of the elements get one GLACIER, one ILAKE and one SEALED zone (last three slots)
-        special = rng.uniform(size=ne) < 0.05
+        special = rng.uniform(size=n_all)[sel] < 0.05
         for slot, ztype, flags in ((nz - 1, layout.GLACIER, 0), (nz - 2, layout.ILAKE, layout.ZF_WATER),
                                    (nz - 3, layout.SEALED, layout.ZF_INTERCEPTION)):
             zonetype[special, slot] = ztype
@@ -83,7 +94,7 @@ def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, 
     epar = np.repeat(tpl["epar"][:, :1], ne, axis=1)
     EP = layout.EP
     for name in JITTER_ELEM:
-        epar[EP[name]] *= 1.0 + jitter * rng.uniform(-1.0, 1.0, size=ne)
+        epar[EP[name]] *= 1.0 + jitter * draw(n_all)
     epar[EP["z"]] = np.sum(rel * zonez[None, :], axis=1)
     epar[EP["relsoilarea"]] = rsum(soil)
     epar[EP["rellandarea"]] = rsum(zonetype != layout.ILAKE)
@@ -98,7 +109,7 @@ def make_land(n_elem: int, step: str = "1h", *, zones: int = 12, seed: int = 1, 
         zone_ptr=np.arange(ne + 1, dtype=np.int64) * nz, snow_ptr=np.arange(ne + 1, dtype=np.int64) * nz,
         sfdist_ptr=np.arange(ne + 1, dtype=np.int64), uh_ptr=np.arange(ne + 1, dtype=np.int64) * nu,
         sred_ptr=np.zeros(ne + 1, np.int64), recstep=np.full(ne, int(tpl["recstep"][0]), np.int32),
-        eflags=np.full(ne, int(tpl["eflags"][0]), np.int32), forcing_col=(np.arange(ne) % bank).astype(np.int32),
+        eflags=np.full(ne, int(tpl["eflags"][0]), np.int32), forcing_col=(sel % bank).astype(np.int32),
         outlet_node=(np.arange(ne) if own_nodes else np.full(ne, -1)).astype(np.int32), epar=epar,
         zonetype=zonetype.reshape(-1), zflags=zflags.reshape(-1), zorder=zorder.reshape(-1),
         zpar=zpar.reshape(zpar.shape[0], ne * nz), sfdist=np.ones(ne), uh=np.tile(tpl["uh"], ne),

@@ -400,7 +400,10 @@ int hb_comm_unique_id(hb_engine* h, void* id);
 int hb_comm_init(hb_engine* h, int rank, int world, const void* id);
 /* Send the window's simulated rows of `n` local nodes (kind HB_ROW_NODE) or the outflow rows of `n` local reaches
  * (kind HB_ROW_REACH) to rank `peer` / receive `n` rows into the external rows `ext_rows[]` from rank `peer`.  Calls
- * between matching ranks must pair up (grouped internally per call). */
+ * between matching ranks must pair up with the same `n`: the rows of a call travel as ONE message (packed by a gather
+ * kernel behind the routing; received straight into the external-row buffer when `ext_rows[]` is consecutive, through a
+ * staging buffer otherwise).  Both calls only enqueue (stream of their own); the routing of the window waits on the device
+ * for rows that feed a reach. */
 #define HB_ROW_NODE 0
 #define HB_ROW_REACH 1
 int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t* rows);

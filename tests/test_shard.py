@@ -198,22 +198,50 @@ def test_partition_with_musk_mct_reaches():
     assert np.array_equal(got_mct, m, equal_nan=True)
 
 
-@pytest.mark.parametrize("rank", [0, 1, 3])
-def test_bench_shards_are_consistent_bundles(rank):
-    """bench.py's per-rank sub-basins (N > 1: an extra boundary reach or extra external entries) must stay valid bundles —
-    the C structs are built from them on every rank."""
+@pytest.mark.parametrize("scaling", ["weak", "strong"])
+def test_bench_workload_of_several_ranks_is_the_unsharded_basin(scaling):
+    """bench.py's per-rank workloads for N > 1 (ONE basin cut by shard.partition, land elements built per rank with
+    `make_land(select=…)`) executed with the oracle in stage order must give the unsharded basin bit for bit — boundary
+    series feed downstream REACHES here, not only outlet nodes."""
     import argparse
 
     import bench
 
-    args = argparse.Namespace(elements=300, levels=12)
-    land, states, river, discharge = bench.build_shard(args, rank, 4)
-    land.as_struct()
-    states.as_struct()
-    d = river.as_struct()
-    assert d.n_reach == river.n_reach and len(discharge) == river.n_seg
-    assert len(river.reach_model) == river.n_reach and river.rpar.shape[1] == river.n_reach
-    if rank == 0:
-        assert river.n_ext == 3
-    else:
-        assert river.n_reach == 300 and river.reach_outlet[-1] == -1
+    world, nt = 4, 30
+    args = argparse.Namespace(elements=90 if scaling == "weak" else 360, levels=12, scaling=scaling, config=3)
+    wls = [bench.build_shard(args, rank, world) for rank in range(world)]
+    n_total = 360
+    assert sum(w.land.n_elem for w in wls) == n_total and all(w.land.n_elem > 40 for w in wls)
+    assert sum(w.river.n_reach for w in wls) == n_total - 1
+    for w in wls:
+        w.land.as_struct(); w.states.as_struct(); w.river.as_struct()
+        assert len(w.discharge) == w.river.n_seg
+    assert any(w.recv for w in wls) and any(w.send for w in wls)
+    forcing, doy = synth.make_forcing(nt, "1h", seed=0)
+    land, states = synth.make_land(n_total, "1h", seed=1)
+    river, discharge = synth.make_tree_river(n_total, "1h", seed=2, levels=12)
+    ref_nodes, _, _, _ = run_unsharded(land, states, river, discharge, forcing, doy)
+    node_rank = shard.assign_nodes(None, river, world, outlet_node=np.arange(n_total), zones=np.full(n_total, 12.0))
+    stages = [w.desc["shard_stage"] for w in wls]
+    out_rows: dict[int, np.ndarray] = {}
+    nodes = np.zeros_like(ref_nodes)
+    fed_reach = False
+    for rank in sorted(range(world), key=lambda r: stages[r]):
+        w = wls[rank]
+        ext = np.zeros((w.river.n_ext, nt))
+        for peer, rows in w.recv:
+            sent = dict(wls[peer].send)[rank]
+            assert stages[peer] < stages[rank] and len(sent) == len(rows)
+            for row, q_local in zip(rows, sent):
+                ext[row] = out_rows[peer][q_local]
+        st, dis = w.states.copy(), w.discharge.copy()
+        qt, _ = oracle.land_run(w.land, st, forcing, doy, threads=1)
+        n_rows, r_rows, _ = oracle.river_run(w.river, dis, qt, ext)
+        out_rows[rank] = r_rows
+        nodes[np.flatnonzero(node_rank == rank)] = n_rows
+        # some received row enters a node that a local reach drains: the exchange is on the routing's critical path
+        ext_nodes = {n for n in range(w.river.n_node)
+                     for s_ in w.river.entry_src[w.river.entry_ptr[n]:w.river.entry_ptr[n + 1]] if s_ <= layout.ENTRY_EXT}
+        fed_reach = fed_reach or bool(ext_nodes & set(w.river.inlet_node.tolist()))
+    assert fed_reach
+    assert np.array_equal(nodes, ref_nodes)
