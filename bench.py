@@ -237,6 +237,36 @@ def build_shard(args: argparse.Namespace, rank: int, world: int) -> Workload:
     return Workload(land, states, s.river, s.discharge, s.recv, s.send, desc=desc, verify=verify)
 
 
+def build_members(args: argparse.Namespace, rank: int, world: int) -> Workload:
+    """configs[1] / configs[4]: a parameter ensemble, member-sharded (every member is a complete basin, so nothing crosses
+    ranks).  The rank describes ONE basin to the engine; its members are created on the device (`hb_set_members`)."""
+    from hydpy_b200 import synth
+
+    total = args.members or (4096 if args.config == 1 else 512)
+    per_rank = max(1, total // world)
+    lo = rank * per_rank
+    mods_all = synth.member_mods(per_rank * world)            # member 0 = the shipped parameter values
+    mods = {k: (m[lo:lo + per_rank], a[lo:lo + per_rank]) for k, (m, a) in mods_all.items()}
+    if args.config == 1:
+        from tests.util import load_scenarios                  # (the committed fixture of the real Lahn basin)
+
+        p = load_scenarios("lahn_hourly_members.npz")["member0"].problem
+        desc = {"workload": f"configs[1]: HydPy-H-Lahn hourly x {per_rank * world} parameter-ensemble members "
+                            f"(4 hland_96 elements, 49 zones, 3 musk_classic reaches per member), members created on the "
+                            f"device (hb_set_members)", "basin_elements": p.land.n_elem}
+        wl = Workload(p.land, p.states, p.river, p.discharge, desc=desc, forcing_fixed=(p.forcing, p.doy), members=per_rank)
+    else:
+        land, states = synth.make_land(83_334, "1h", seed=1)
+        river, discharge = synth.make_tree_river(83_334, "1h", seed=2, levels=args.levels)
+        desc = {"workload": f"configs[4]: 10^6-zone hland_96 + musk_classic basin (83 334 elements) x {per_rank * world} "
+                            f"ensemble members, hourly, members created on the device (hb_set_members)",
+                "basin_elements": land.n_elem}
+        wl = Workload(land, states, river, discharge, desc=desc, members=per_rank)
+    wl.mods = mods
+    wl.desc.update({"members_total": per_rank * world, "members_per_gpu": per_rank})
+    return wl
+
+
 def build_workload(args: argparse.Namespace, dist: "Dist") -> Workload:
     if args.config == 3:
         return build_shard(args, dist.rank, dist.world)
@@ -265,11 +295,26 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     eng = Engine(dist.local_rank)
     info = eng.device_info()
     wl = build_workload(args, dist)
-    land, states, river, discharge = wl.land, wl.states, wl.river, wl.discharge
-    eng.set_land(land)
+    if wl.forcing_fixed is not None:
+        win = wl.forcing_fixed[0].shape[1]
+    elif args.config == 4 and win == 438:
+        win = 120        # 5·10^6 nodes per GPU: the node/reach rows of a 438-h window would not fit beside the constants
+    states, discharge = wl.states, wl.discharge
+    eng.set_land(wl.land)
     eng.set_land_states(states)
-    eng.set_river(river)
+    eng.set_river(wl.river)
     eng.set_river_states(discharge)
+    if wl.members > 1:
+        eng.set_members(wl.members, wl.mods)
+    land, river = eng.land, eng.river       # (sizes of everything on the device: all members)
+    ensemble = wl.members > 1
+
+    def reset_conditions() -> None:
+        """Back to the initial conditions (an ensemble simply goes on: its conditions live on the device only)."""
+        if not ensemble:
+            eng.set_land_states(states)
+            eng.set_river_states(discharge)
+
     if args.river_sweep:
         eng.set_river_sweep(args.river_sweep)
     if args.wave_blocks:
@@ -300,10 +345,14 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
 
     n_steps = W + K
     # ---- forcing of all windows: generated up front (synthetic, seeded per window) in pinned host memory ----------------
-    pinned = eng.pinned((n_steps, 4, win, 1024))
+    bank = wl.forcing_fixed[0].shape[2] if wl.forcing_fixed is not None else 1024
+    pinned = eng.pinned((n_steps, 4, win, bank))
     doys = np.zeros((n_steps, win), np.int64)
     for s in range(n_steps):
-        f, doys[s] = synth.make_forcing(win, "1h", seed=wl.forcing_seed, t0=s * win, kind=args.forcing)
+        if wl.forcing_fixed is not None:
+            f, doys[s] = wl.forcing_fixed
+        else:
+            f, doys[s] = synth.make_forcing(win, "1h", seed=wl.forcing_seed, t0=s * win, kind=args.forcing)
         pinned.array[s] = f
     zone_steps_per_step = land.n_zone * win
     launches = 0
@@ -338,69 +387,80 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     total_zone_steps = dist.sum(float(zone_steps_per_step * K))
     value = total_zone_steps / (device_ms_max * 1e-3)
     n_levels = int(tm["n_levels"])
-    states_after_value = eng.get_land_states()
+    states_after_value = None if ensemble else eng.get_land_states()
 
     # ================= end-to-end run through the public API with host buffers (e2e) =====================================
-    eng.set_land_states(states)
-    eng.set_river_states(discharge)
-    outs = [eng.pinned((river.n_node, win)), eng.pinned((river.n_node, win))]
-    h2d = 4 * win * 1024 * 8 + win * 8
-    d2h = river.n_node * win * 8
+    # every step: forcing of the window host -> device, node series device -> host.  A single basin returns ALL its node
+    # series; an ensemble the series of every member's outlet (what a calibration run reads)
+    reset_conditions()
+    if ensemble:
+        nn_base = wl.river.n_node
+        terminal = int(np.setdiff1d(np.arange(nn_base), wl.river.inlet_node)[0]) if nn_base else 0
+        e2e_nodes = (np.arange(wl.members) * nn_base + terminal).astype(np.int32)
+    else:
+        e2e_nodes = None
+    n_out = river.n_node if e2e_nodes is None else len(e2e_nodes)
+    outs = [eng.pinned((n_out, win)), eng.pinned((n_out, win))]
+    h2d = 4 * win * bank * 8 + win * 8
+    d2h = n_out * win * 8
     dist.barrier()
     for s in range(W):
         eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)   # host → device copy of this window's forcing
         step_exchange_and_route()
-        eng.get_node_series_async(outs[s & 1].array)              # device → host copy of every node's series
+        eng.get_node_series_async(outs[s & 1].array, e2e_nodes)   # device → host copy of the node series
     eng.wait()
     dist.barrier()
     t0 = time.perf_counter()
     for s in range(W, W + K):
         eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
         step_exchange_and_route()
-        eng.get_node_series_async(outs[s & 1].array)
+        eng.get_node_series_async(outs[s & 1].array, e2e_nodes)
     eng.wait()                                                    # all K windows' results are in host memory
     e2e_s = time.perf_counter() - t0
     dist.barrier()
     e2e_s_max = dist.max(e2e_s)
     e2e_value = total_zone_steps / e2e_s_max
     checksum = float(outs[(W + K - 1) & 1].array[0].sum())
-    states_after_e2e = eng.get_land_states()
-    same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
+    if ensemble:
+        same = None
+    else:
+        states_after_e2e = eng.get_land_states()
+        same = all(np.array_equal(getattr(states_after_value, n), getattr(states_after_e2e, n)) for n in states.NAMES)
 
     # ---- the same with the gauged nodes only (1 % of the nodes, hb_get_node_series_async with a selection): what a user
     # who keeps the series of the gauges pays; at 8 ranks the copy of ALL node series is bound by the host's memory
     gauges = np.sort(np.random.default_rng(5).choice(river.n_node, size=max(1, river.n_node // 100), replace=False))
+    if ensemble:
+        gauges = np.asarray(e2e_nodes)
     gouts = [eng.pinned((len(gauges), win)), eng.pinned((len(gauges), win))]
-    eng.set_land_states(states)
-    eng.set_river_states(discharge)
+    reset_conditions()
     dist.barrier()
-    for s in range(W):
+    for s in range(W if not ensemble else 0):
         eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
         step_exchange_and_route()
         eng.get_node_series_async(gouts[s & 1].array, gauges)
     eng.wait()
     dist.barrier()
     t0 = time.perf_counter()
-    for s in range(W, W + K):
+    for s in range(W, W + K) if not ensemble else ():
         eng.set_forcing(pinned.array[s], doys[s], asynchronous=True)
         step_exchange_and_route()
         eng.get_node_series_async(gouts[s & 1].array, gauges)
     eng.wait()
-    e2e_g_s = time.perf_counter() - t0
+    e2e_g_s = time.perf_counter() - t0 if not ensemble else e2e_s
     dist.barrier()
     e2e_gauged = {"value": total_zone_steps / dist.max(e2e_g_s), "unit": UNIT, "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": int(len(gauges)) * win * 8, "ms_per_step": 1e3 * dist.max(e2e_g_s) / K,
                   "nodes_returned_per_rank": int(len(gauges)),
-                  "same_rows_as_full_copy": bool(np.array_equal(gouts[(W + K - 1) & 1].array,
-                                                                outs[(W + K - 1) & 1].array[gauges]))}
+                  "same_rows_as_full_copy": None if ensemble else bool(np.array_equal(
+                      gouts[(W + K - 1) & 1].array, outs[(W + K - 1) & 1].array[gauges]))}
     for o in gouts:
         o.free()
 
     # ================= N > 1: the sharded run against the unsharded one ==================================================
     parity = None
     if dist.world > 1 and not args.no_verify and wl.verify is not None:
-        eng.set_land_states(states)
-        eng.set_river_states(discharge)
+        reset_conditions()
         eng.set_forcing(np.ascontiguousarray(pinned.array[0]), doys[0])
         step_exchange_and_route()
         eng.wait()
@@ -527,7 +587,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
             "river_levels": n_levels, "window_steps": win, "simulated_days_timed": K * win / 24.0,
             "recstep_per_step": R, "uh_ordinates": U,
-            "forcing_bank": 1024,
+            "forcing_bank": bank,
             "parallelism": (f"one basin, element-sharded x{dist.world} by hydpy_b200.shard.partition, NCCL boundary "
                             f"series feed the downstream reaches" if dist.world > 1 and args.config == 3 else
                             f"member-sharded x{dist.world}" if dist.world > 1 else "single GPU"),
@@ -537,7 +597,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             "forcing": forcing_note, **executed,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s_max / K, "same_final_states_as_resident_run": bool(same)},
+                "ms_per_step": 1e3 * e2e_s_max / K,
+                "same_final_states_as_resident_run": None if same is None else bool(same),
+                "node_series_returned": "all nodes" if e2e_nodes is None else "the outlet node of every member"},
         "e2e_gauged_nodes": e2e_gauged, "multi_gpu_parity": parity,
         "gpu_launches": launches,
         "kernel_ms_per_step": {"runoff_generation": land_ms_avg, "routing": float(np.mean(river_ms)),

@@ -96,8 +96,66 @@ const int kNcclFloat64 = 8, kNcclSum = 0;
 
 }  // namespace
 
+
+// deep copies of the last basin descriptions (hb_set_members builds the ensemble from them)
+struct LandBase {
+  bool valid = false;
+  hb_land_desc d{};
+  std::vector<int64_t> zone_ptr, snow_ptr, sfdist_ptr, uh_ptr, sred_ptr;
+  std::vector<int32_t> recstep, eflags, forcing_col, outlet_node, zonetype, zflags, zorder, sred_from, sred_to, model, rconc,
+      nash_steps;
+  std::vector<double> epar, zpar, sfdist, uh, sred_adjust;
+  template <typename T>
+  static const T* cp(std::vector<T>& v, const T* src, size_t n) {
+    if (!src) { v.clear(); return nullptr; }
+    v.assign(src, src + n);
+    if (v.empty()) v.resize(1);
+    return v.data();
+  }
+  void keep(const hb_land_desc* s) {
+    d = *s;
+    const size_t ne = (size_t)s->n_elem;
+    d.zone_ptr = cp(zone_ptr, s->zone_ptr, ne + 1); d.snow_ptr = cp(snow_ptr, s->snow_ptr, ne + 1);
+    d.sfdist_ptr = cp(sfdist_ptr, s->sfdist_ptr, ne + 1); d.uh_ptr = cp(uh_ptr, s->uh_ptr, ne + 1);
+    d.sred_ptr = cp(sred_ptr, s->sred_ptr, ne + 1); d.recstep = cp(recstep, s->recstep, ne);
+    d.eflags = cp(eflags, s->eflags, ne); d.forcing_col = cp(forcing_col, s->forcing_col, ne);
+    d.outlet_node = cp(outlet_node, s->outlet_node, ne); d.epar = cp(epar, s->epar, (size_t)HB_EP_COUNT * ne);
+    d.zonetype = cp(zonetype, s->zonetype, (size_t)s->n_zone); d.zflags = cp(zflags, s->zflags, (size_t)s->n_zone);
+    d.zorder = cp(zorder, s->zorder, (size_t)s->n_zone); d.zpar = cp(zpar, s->zpar, (size_t)HB_ZP_COUNT * s->n_zone);
+    d.sfdist = cp(sfdist, s->sfdist, (size_t)s->n_sfdist); d.uh = cp(uh, s->uh, (size_t)s->n_uh);
+    d.sred_from = cp(sred_from, s->sred_from, (size_t)s->n_sred); d.sred_to = cp(sred_to, s->sred_to, (size_t)s->n_sred);
+    d.sred_adjust = cp(sred_adjust, s->sred_adjust, (size_t)s->n_sred); d.model = cp(model, s->model, ne);
+    d.rconc = cp(rconc, s->rconc, ne); d.nash_steps = cp(nash_steps, s->nash_steps, ne);
+    valid = true;
+  }
+};
+struct RiverBase {
+  bool valid = false;
+  hb_river_desc d{};
+  std::vector<int64_t> entry_ptr, inlet_ptr, seg_ptr, trap_ptr;
+  std::vector<int32_t> entry_src, node_mode, node_ext, inlet_node, reach_outlet, reach_model, nmbruns;
+  std::vector<double> coef, rpar, tpar;
+  void keep(const hb_river_desc* s) {
+    d = *s;
+    const size_t nn = (size_t)s->n_node, nr = (size_t)s->n_reach;
+    d.entry_ptr = LandBase::cp(entry_ptr, s->entry_ptr, nn + 1); d.entry_src = LandBase::cp(entry_src, s->entry_src, (size_t)s->n_entry);
+    d.node_mode = LandBase::cp(node_mode, s->node_mode, nn); d.node_ext = LandBase::cp(node_ext, s->node_ext, nn);
+    d.inlet_ptr = LandBase::cp(inlet_ptr, s->inlet_ptr, nr + 1); d.inlet_node = LandBase::cp(inlet_node, s->inlet_node, (size_t)s->n_inlet);
+    d.reach_outlet = LandBase::cp(reach_outlet, s->reach_outlet, nr); d.seg_ptr = LandBase::cp(seg_ptr, s->seg_ptr, nr + 1);
+    d.coef = LandBase::cp(coef, s->coef, 3 * nr); d.reach_model = LandBase::cp(reach_model, s->reach_model, nr);
+    d.nmbruns = LandBase::cp(nmbruns, s->nmbruns, nr); d.rpar = LandBase::cp(rpar, s->rpar, (size_t)HB_RP_COUNT * nr);
+    d.trap_ptr = LandBase::cp(trap_ptr, s->trap_ptr, s->trap_ptr ? nr + 1 : 0);
+    d.tpar = LandBase::cp(tpar, s->tpar, (size_t)HB_TP_COUNT * (size_t)s->n_trap);
+    valid = true;
+  }
+};
+
 struct hb_engine {
   int device = 0;
+  // ensemble members (hb_set_members): the land and river descriptions on the device are `members` copies of the base
+  int64_t members = 1, river_members = 1, member_node_stride = 0;
+  LandBase base_land;
+  RiverBase base_river;
   // Three streams form the window pipeline: runoff generation of window w+1 (stream) overlaps routing of window w
   // (s_river) and the device→host copy of its node series (s_copy).  All per-window buffers exist twice; `cur` is the
   // set of the window staged last (it flips in hb_set_forcing / hb_select_window).
@@ -266,6 +324,99 @@ struct hb_engine {
 
 #define HB_REQUIRE(h, cond, code, ...) \
   do { if (!(cond)) return (h)->fail(code, __VA_ARGS__); } while (0)
+
+
+// ---- folding of the reference's parameters into the constants the kernels work with ----------------------------------
+// Evaluated exactly as the reference evaluates the sub-expressions (same operands, same order, IEEE binary64; this
+// translation unit is compiled with -fmad=false and host code never contracts).  __host__ __device__: hb_set_land folds
+// on the host, hb_set_members on the device (fold_members_kernel) — one source, the same bits.
+// zv = the zone's row of zpar[HB_ZP_COUNT], ev = the element's row of epar[HB_EP_COUNT]; o[j * stride] = constant j.
+__host__ __device__ inline void fold_zone(const double* zv, const double* ev, int model, double* o, size_t stride) {
+  const double z = ev[HB_EP_Z], relsoil = ev[HB_EP_RELSOILAREA], relupper = ev[HB_EP_RELUPPERZONEAREA],
+               rellower = ev[HB_EP_RELLOWERZONEAREA], petalt = ev[HB_EP_PETALTITUDE];
+  const double dz = zv[HB_ZP_ZONEZ] - z;
+  const double half = zv[HB_ZP_TTINT] / 2.0;
+  o[(size_t)KZ_TCORR * stride] = zv[HB_ZP_TCORR];
+  o[(size_t)KZ_TCALT_DZ * stride] = zv[HB_ZP_TCALT] * dz;
+  o[(size_t)KZ_TT_HI * stride] = zv[HB_ZP_TT] + half;
+  o[(size_t)KZ_TT_LO * stride] = zv[HB_ZP_TT] - half;
+  o[(size_t)KZ_TTINT * stride] = zv[HB_ZP_TTINT];
+  o[(size_t)KZ_PCALT_F * stride] = 1.0 + zv[HB_ZP_PCALT] * dz;
+  o[(size_t)KZ_PCORR * stride] = zv[HB_ZP_PCORR];
+  o[(size_t)KZ_RFCF * stride] = zv[HB_ZP_RFCF];
+  o[(size_t)KZ_SFCF * stride] = zv[HB_ZP_SFCF];
+  o[(size_t)KZ_ICMAX * stride] = zv[HB_ZP_ICMAX];
+  o[(size_t)KZ_CFMAX * stride] = zv[HB_ZP_CFMAX];
+  o[(size_t)KZ_CFVAR * stride] = zv[HB_ZP_CFVAR];
+  o[(size_t)KZ_TTM * stride] = zv[HB_ZP_TTM];
+  o[(size_t)KZ_CFR_CFMAX * stride] = zv[HB_ZP_CFR] * zv[HB_ZP_CFMAX];
+  o[(size_t)KZ_WHC * stride] = zv[HB_ZP_WHC];
+  o[(size_t)KZ_FC * stride] = zv[HB_ZP_FC];
+  o[(size_t)KZ_BETA * stride] = zv[HB_ZP_BETA];
+  o[(size_t)KZ_CFLUX * stride] = zv[HB_ZP_CFLUX];
+  o[(size_t)KZ_W_UZ * stride] = zv[HB_ZP_RELZONEAREA] / relupper;
+  o[(size_t)KZ_W_CONTRI * stride] = zv[HB_ZP_RELZONEAREA] / relsoil;
+  o[(size_t)KZ_THRESH * stride] = zv[HB_ZP_SOILMOISTURELIMIT] * zv[HB_ZP_MAXSOILWATER];
+  o[(size_t)KZ_EXCESSRED * stride] = zv[HB_ZP_EXCESSREDUCTION];
+  o[(size_t)KZ_ATF * stride] = zv[HB_ZP_AIRTEMPERATUREFACTOR];
+  o[(size_t)KZ_ETF * stride] = zv[HB_ZP_EVAPOTRANSPIRATIONFACTOR];
+  o[(size_t)KZ_ALT_F * stride] = 1.0 - zv[HB_ZP_ALTITUDEFACTOR] / 100.0 * (zv[HB_ZP_HRUALTITUDE] - petalt);
+  o[(size_t)KZ_NEG_PF * stride] = -zv[HB_ZP_PRECIPITATIONFACTOR];
+  o[(size_t)KZ_SMAX * stride] = zv[HB_ZP_SMAX];
+  o[(size_t)KZ_GMELT * stride] = zv[HB_ZP_GMELT];
+  o[(size_t)KZ_GVAR * stride] = zv[HB_ZP_GVAR];
+  o[(size_t)KZ_W_LZ * stride] = zv[HB_ZP_RELZONEAREA] / rellower;
+  o[(size_t)KZ_RELZONEAREA * stride] = zv[HB_ZP_RELZONEAREA];
+  o[(size_t)KZ_TTI * stride] = zv[HB_ZP_TEMPERATURETHRESHOLDICE];
+  o[(size_t)KZ_INV_TTINT * stride] = 1.0 / zv[HB_ZP_TTINT];
+  o[(size_t)KZ_INV_RFCF * stride] = 1.0 / zv[HB_ZP_RFCF];
+  o[(size_t)KZ_INV_SFCF * stride] = 1.0 / zv[HB_ZP_SFCF];
+  o[(size_t)KZ_INV_FC * stride] = 1.0 / zv[HB_ZP_FC];
+  o[(size_t)KZ_INV_THRESH * stride] = 1.0 / (zv[HB_ZP_SOILMOISTURELIMIT] * zv[HB_ZP_MAXSOILWATER]);
+  if (model == HB_MODEL_HLAND_96P) {
+    // folded like the reference evaluates them: (suz-sgr)*(1-w0), suz*(1-w1), w2*sg1 + ((1-w2)*k2)*gr1
+    o[(size_t)KZ_X0 * stride] = zv[HB_ZP_SGR];
+    o[(size_t)KZ_X1 * stride] = 1.0 - zv[HB_ZP_W0];
+    o[(size_t)KZ_X2 * stride] = 1.0 - zv[HB_ZP_W1];
+    o[(size_t)KZ_X3 * stride] = zv[HB_ZP_K2];
+    o[(size_t)KZ_X4 * stride] = zv[HB_ZP_W2];
+    o[(size_t)KZ_X5 * stride] = (1.0 - zv[HB_ZP_W2]) * zv[HB_ZP_K2];
+    o[(size_t)KZ_X6 * stride] = zv[HB_ZP_SG1MAX];
+  } else if (model == HB_MODEL_HLAND_96C) {
+    o[(size_t)KZ_X0 * stride] = zv[HB_ZP_H1];
+    o[(size_t)KZ_X1 * stride] = zv[HB_ZP_TAB1];
+    o[(size_t)KZ_X2 * stride] = zv[HB_ZP_TVS1];
+    o[(size_t)KZ_X3 * stride] = zv[HB_ZP_H2];
+    o[(size_t)KZ_X4 * stride] = zv[HB_ZP_TAB2];
+    o[(size_t)KZ_X5 * stride] = zv[HB_ZP_TVS2];
+    o[(size_t)KZ_W_LAND * stride] = zv[HB_ZP_RELZONEAREA] / ev[HB_EP_RELLANDAREA];
+  }
+}
+
+// beta_last = Beta of the element's last zone (ref: hland_model.py:2233-2236 `contriarea **= beta[k]` after the loop)
+__host__ __device__ inline void fold_element(const double* ev, double beta_last, double* o, size_t stride) {
+  const double dt = ev[HB_EP_DT], relupper = ev[HB_EP_RELUPPERZONEAREA], rellower = ev[HB_EP_RELLOWERZONEAREA];
+  o[(size_t)KE_DT * stride] = dt;
+  o[(size_t)KE_DT_PERCMAX * stride] = dt * ev[HB_EP_PERCMAX];
+  o[(size_t)KE_DT_K * stride] = dt * ev[HB_EP_K];
+  o[(size_t)KE_ALPHA1 * stride] = 1.0 + ev[HB_EP_ALPHA];
+  o[(size_t)KE_K4 * stride] = ev[HB_EP_K4];
+  o[(size_t)KE_GAMMA1 * stride] = 1.0 + ev[HB_EP_GAMMA];
+  o[(size_t)KE_RELUPPER * stride] = relupper;
+  o[(size_t)KE_RELLOWER * stride] = rellower;
+  o[(size_t)KE_UP_LOW * stride] = relupper / rellower;
+  o[(size_t)KE_QFACTOR * stride] = ev[HB_EP_QFACTOR];
+  o[(size_t)KE_RELSOILAREA * stride] = ev[HB_EP_RELSOILAREA];
+  o[(size_t)KE_RELLANDAREA * stride] = ev[HB_EP_RELLANDAREA];
+  o[(size_t)KE_BETA_LAST * stride] = beta_last;
+  o[(size_t)KE_K3 * stride] = ev[HB_EP_K3];
+  o[(size_t)KE_W3 * stride] = ev[HB_EP_W3];
+  o[(size_t)KE_W4 * stride] = ev[HB_EP_W4];
+  o[(size_t)KE_FSG * stride] = ev[HB_EP_FSG];
+  o[(size_t)KE_OMFSG * stride] = 1.0 - ev[HB_EP_FSG];
+  o[(size_t)KE_NASH_DT * stride] = ev[HB_EP_NASH_DT];
+  o[(size_t)KE_NASH_DTKSC * stride] = ev[HB_EP_NASH_DT] * ev[HB_EP_NASH_KSC];
+}
 
 template <typename T>
 static int upload(hb_engine* h, DBuf<T>& buf, const T* src, size_t n) {
@@ -447,23 +598,72 @@ int hb_host_free(hb_engine* h, void* p) {
 // ---------------------------------------------------------------------------------------------------------------------
 // land setup
 // ---------------------------------------------------------------------------------------------------------------------
-int hb_set_land(hb_engine* h, const hb_land_desc* d) {
-  if (!h) return HB_EINVAL;
-  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
-  HB_REQUIRE(h, d && d->n_elem >= 0, HB_EINVAL, "hb_set_land: invalid description");
-  HB_CUDA(h, cudaSetDevice(h->device));
-  const int64_t ne = d->n_elem;
-  HB_REQUIRE(h, ne == 0 || (d->zone_ptr && d->snow_ptr && d->sfdist_ptr && d->uh_ptr && d->sred_ptr && d->recstep &&
-                            d->eflags && d->forcing_col && d->epar && d->zpar && d->zonetype && d->zflags && d->zorder),
+// ---- member modifications (hb_set_members): value' = value * mul + add for selected control parameters ---------------
+struct MemberMods {
+  int64_t members = 1, n_mod = 0;
+  const int32_t* par = nullptr;     // [n_mod] HB_ZP_* or HB_MOD_EPAR + HB_EP_*
+  const double* mul = nullptr;      // [members][n_mod]
+  const double* add = nullptr;
+  const uint8_t* mask = nullptr;    // [n_mod][n_elem of the base basin] or NULL: elements a modification applies to
+  int64_t n_elem_base = 0;
+  // modifications act in the listed order on the running value (rules of disjoint selections: one of them per element)
+  double val(int id, double v, int64_t m, int64_t eb) const {
+    for (int64_t j = 0; j < n_mod; ++j)
+      if (par[j] == id && (!mask || mask[j * n_elem_base + eb])) v = v * mul[m * n_mod + j] + add[m * n_mod + j];
+    return v;
+  }
+  double zval(int p, double base, int64_t m, int64_t eb) const { return n_mod ? val(p, base, m, eb) : base; }
+  double eval(int p, double base, int64_t m, int64_t eb) const { return n_mod ? val(HB_MOD_EPAR + p, base, m, eb) : base; }
+};
+
+// Device twin of the host folding (fold_zone / fold_element are __host__ __device__): one thread per (member, zone slot of
+// the base basin).  Raw parameters of the base basin + the member's modifications -> the constants the kernels read.
+__global__ void __launch_bounds__(128) fold_members_kernel(
+    const double* __restrict__ zpar, const double* __restrict__ epar, const int64_t* __restrict__ zone_ptr_b,
+    const int32_t* __restrict__ model_b, int64_t n_elem_b, int64_t n_zone_b, int64_t members, int64_t n_mod,
+    const int32_t* __restrict__ par, const double* __restrict__ mul, const double* __restrict__ add,
+    const uint8_t* __restrict__ mask, int zmax, int64_t ep, double* __restrict__ kz, double* __restrict__ ke) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (member, base element)
+  if (i >= members * n_elem_b) return;
+  const int64_t m = i / n_elem_b, eb = i - m * n_elem_b, e = i;
+  const int64_t z0 = zone_ptr_b[eb];
+  const int n = (int)(zone_ptr_b[eb + 1] - z0);
+  const double* mm = mul + m * n_mod;
+  const double* aa = add + m * n_mod;
+  double ev[HB_EP_COUNT];
+  for (int p = 0; p < HB_EP_COUNT; ++p) ev[p] = epar[(int64_t)p * n_elem_b + eb];
+  for (int64_t j = 0; j < n_mod; ++j)   // in the listed order, on the running value (MemberMods::val)
+    if (par[j] >= HB_MOD_EPAR && (!mask || mask[j * n_elem_b + eb])) {
+      double& v = ev[par[j] - HB_MOD_EPAR];
+      v = v * mm[j] + aa[j];
+    }
+  double beta_last = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double zv[HB_ZP_COUNT];
+    for (int p = 0; p < HB_ZP_COUNT; ++p) zv[p] = zpar[(int64_t)p * n_zone_b + z0 + k];
+    for (int64_t j = 0; j < n_mod; ++j)
+      if (par[j] < HB_MOD_EPAR && (!mask || mask[j * n_elem_b + eb])) {
+        double& v = zv[par[j]];
+        v = v * mm[j] + aa[j];
+      }
+    fold_zone(zv, ev, model_b[eb], kz + ((size_t)k * KZ_COUNT) * ep + e, (size_t)ep);
+    if (k == n - 1) beta_last = zv[HB_ZP_BETA];
+  }
+  fold_element(ev, beta_last, ke + e, (size_t)ep);
+}
+
+// All land setup: `d` describes ONE basin; with mods.members > 1 every member is a copy of it (member-major: element
+// e = m * n_elem + eb, zone cells m * n_zone + …) whose control parameters follow `mods`.
+static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& mods) {
+  const int64_t M = mods.members;
+  const int64_t neb = d->n_elem, ne = M * neb;
+  const int64_t n_zone = M * d->n_zone, n_snow = M * d->n_snow, n_uh = M * d->n_uh;
+  HB_REQUIRE(h, neb == 0 || (d->zone_ptr && d->snow_ptr && d->sfdist_ptr && d->uh_ptr && d->sred_ptr && d->recstep &&
+                             d->eflags && d->forcing_col && d->epar && d->zpar && d->zonetype && d->zflags && d->zorder),
              HB_EINVAL, "hb_set_land: NULL array in description");
-  // device states survive a new parameter set only if every element keeps its slots: same zones, snow cells and
-  // unit-hydrograph ordinates per element (the layout is [zmax|cmax|umax][E_pad])
-  const bool same_structure = h->have_land && h->n_elem == ne && h->n_zone == d->n_zone && h->n_snow == d->n_snow &&
-                              h->n_uh == d->n_uh && std::equal(h->zone_ptr.begin(), h->zone_ptr.end(), d->zone_ptr) &&
-                              std::equal(h->snow_ptr.begin(), h->snow_ptr.end(), d->snow_ptr) &&
-                              std::equal(h->uh_ptr.begin(), h->uh_ptr.end(), d->uh_ptr);
+  HB_REQUIRE(h, M == 1 || d->n_sred == 0, HB_EINVAL, "hb_set_members: basins with snow redistribution are not supported");
   int zmax = 1, cmax = 1, umax = 1;
-  for (int64_t e = 0; e < ne; ++e) {
+  for (int64_t e = 0; e < neb; ++e) {
     const int64_t nz = d->zone_ptr[e + 1] - d->zone_ptr[e], nc = d->sfdist_ptr[e + 1] - d->sfdist_ptr[e],
                   nu = d->uh_ptr[e + 1] - d->uh_ptr[e];
     HB_REQUIRE(h, nz >= 1 && nc >= 1 && nu >= 0, HB_EINVAL, "hb_set_land: element %lld has %lld zones, %lld snow classes",
@@ -475,60 +675,77 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
     if (nc > cmax) cmax = (int)nc;
     if (nu > umax) umax = (int)nu;
   }
-  HB_REQUIRE(h, (ne == 0 ? 0 : d->zone_ptr[ne]) == d->n_zone, HB_EINVAL, "hb_set_land: zone_ptr does not end at n_zone");
+  HB_REQUIRE(h, (neb == 0 ? 0 : d->zone_ptr[neb]) == d->n_zone, HB_EINVAL, "hb_set_land: zone_ptr does not end at n_zone");
   const int64_t ep = ((ne + 127) / 128) * 128 + (ne == 0 ? 128 : 0);
+  // device states survive a new parameter set only if every element keeps its slots: same zones, snow cells and
+  // unit-hydrograph ordinates per element (the layout is [zmax|cmax|umax][E_pad])
+  std::vector<int64_t> zone_ptr(ne + 1), snow_ptr(ne + 1), uh_ptr(ne + 1);
+  for (int64_t m = 0; m < M; ++m)
+    for (int64_t e = 0; e < neb; ++e) {
+      zone_ptr[m * neb + e] = m * d->n_zone + d->zone_ptr[e];
+      snow_ptr[m * neb + e] = m * d->n_snow + d->snow_ptr[e];
+      uh_ptr[m * neb + e] = m * d->n_uh + d->uh_ptr[e];
+    }
+  zone_ptr[ne] = n_zone; snow_ptr[ne] = n_snow; uh_ptr[ne] = n_uh;
+  const bool same_structure = h->have_land && h->n_elem == ne && h->n_zone == n_zone && h->n_snow == n_snow &&
+                              h->n_uh == n_uh && h->zone_ptr == zone_ptr && h->snow_ptr == snow_ptr && h->uh_ptr == uh_ptr;
   if (!same_structure) h->have_states = false;
-  h->n_elem = ne; h->e_pad = ep; h->n_zone = d->n_zone; h->n_snow = d->n_snow; h->n_uh = d->n_uh;
+  h->n_elem = ne; h->e_pad = ep; h->n_zone = n_zone; h->n_snow = n_snow; h->n_uh = n_uh;
   h->zmax = zmax; h->cmax = cmax; h->umax = umax;
-  h->zone_ptr.assign(d->zone_ptr, d->zone_ptr + ne + 1);
-  h->snow_ptr.assign(d->snow_ptr, d->snow_ptr + ne + 1);
-  h->uh_ptr.assign(d->uh_ptr, d->uh_ptr + ne + 1);
+  h->zone_ptr.swap(zone_ptr); h->snow_ptr.swap(snow_ptr); h->uh_ptr.swap(uh_ptr);
   h->outlet_node.assign(ne, -1);
-  if (d->outlet_node) h->outlet_node.assign(d->outlet_node, d->outlet_node + ne);
+  if (d->outlet_node)
+    for (int64_t m = 0; m < M; ++m)
+      for (int64_t e = 0; e < neb; ++e)   // (member m's nodes follow member m-1's: hb_set_members replicates the river)
+        h->outlet_node[m * neb + e] = d->outlet_node[e] < 0 ? -1 : (int32_t)(d->outlet_node[e] + m * h->member_node_stride);
 
   std::vector<int32_t> nz(ep, 0), nc(ep, 1), nu(ep, 0), recstep(ep, 0), einfo(ep, 0), fcol(ep, 0), nash(ep, 0);
   std::vector<int32_t> model(ne, HB_MODEL_HLAND_96), siblings[2];
   for (int64_t e = 0; e < ne; ++e) {
-    if (d->model) model[e] = d->model[e];
+    const int64_t eb = e % (neb ? neb : 1);
+    if (d->model) model[e] = d->model[eb];
     HB_REQUIRE(h, model[e] >= HB_MODEL_HLAND_96 && model[e] <= HB_MODEL_HLAND_96C, HB_EINVAL,
                "hb_set_land: element %lld has unknown model %d", (long long)e, model[e]);
     if (model[e] != HB_MODEL_HLAND_96) siblings[model[e] - 1].push_back((int32_t)e);
-    const int kind = d->rconc ? d->rconc[e] : HB_RCONC_UH;
+    const int kind = d->rconc ? d->rconc[eb] : HB_RCONC_UH;
     HB_REQUIRE(h, kind == HB_RCONC_UH || kind == HB_RCONC_NASH, HB_EINVAL, "hb_set_land: unknown rconc kind %d", kind);
     if (kind == HB_RCONC_NASH) {
-      HB_REQUIRE(h, d->nash_steps && d->nash_steps[e] >= 0, HB_EINVAL, "hb_set_land: rconc_nash needs nash_steps >= 0");
-      const double ksc = d->epar[(int64_t)HB_EP_NASH_KSC * ne + e];
+      HB_REQUIRE(h, d->nash_steps && d->nash_steps[eb] >= 0, HB_EINVAL, "hb_set_land: rconc_nash needs nash_steps >= 0");
+      const double ksc = mods.eval(HB_EP_NASH_KSC, d->epar[(int64_t)HB_EP_NASH_KSC * neb + eb], e / (neb ? neb : 1), eb);
       // ref: rconc_model.py:183-184 — no storages or an infinite coefficient pass the inflow on
-      nash[e] = (d->uh_ptr[e + 1] == d->uh_ptr[e] || std::isinf(ksc)) ? -1 : d->nash_steps[e];
+      nash[e] = (d->uh_ptr[eb + 1] == d->uh_ptr[eb] || std::isinf(ksc)) ? -1 : d->nash_steps[eb];
       // (NmbSteps == 0 would yield outflow 0; the kernel's 0 means rconc_uh, so that case is refused)
       HB_REQUIRE(h, nash[e] != 0, HB_EINVAL, "hb_set_land: rconc_nash with NmbSteps == 0");
     }
   }
+  const bool host_fold = M == 1;     // (members: folded on the device, the big arrays never exist on the host)
   std::vector<int32_t> zinfo((size_t)zmax * ep, 0), zorder((size_t)zmax * ep, 0);
   std::vector<int64_t> zone0(ep, 0), snow0(ep, 0), sred_ptr(ep + 1, 0);
-  std::vector<double> kz((size_t)zmax * KZ_COUNT * ep, 0.0), ke((size_t)KE_COUNT * ep, 0.0),
+  std::vector<double> kz(host_fold ? (size_t)zmax * KZ_COUNT * ep : 0, 0.0), ke(host_fold ? (size_t)KE_COUNT * ep : 0, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
   int64_t n_fast = 0, n_fast_sib[2] = {0, 0};
   std::vector<int32_t> coupled_list;
-#define ZP(name, z) d->zpar[(int64_t)HB_ZP_##name * d->n_zone + (z)]
-#define EPAR(name, e) d->epar[(int64_t)HB_EP_##name * ne + (e)]
+  h->any_nonsoil_warp = false;
+  h->any_nonsoil_sib[0] = h->any_nonsoil_sib[1] = false;
   for (int64_t e = 0; e < ne; ++e) {
-    const int64_t z0 = d->zone_ptr[e];
-    const int n = (int)(d->zone_ptr[e + 1] - z0);
+    const int64_t m = e / neb, eb = e - m * neb;
+    const int64_t z0 = d->zone_ptr[eb];
+    const int n = (int)(d->zone_ptr[eb + 1] - z0);
     nz[e] = n;
-    nc[e] = (int)(d->sfdist_ptr[e + 1] - d->sfdist_ptr[e]);
-    nu[e] = (int)(d->uh_ptr[e + 1] - d->uh_ptr[e]);
-    recstep[e] = d->recstep[e];
-    fcol[e] = d->forcing_col[e];
-    zone0[e] = z0;
-    snow0[e] = d->snow_ptr[e];
-    sred_ptr[e] = d->sred_ptr[e];
-    const double z = EPAR(Z, e), relsoil = EPAR(RELSOILAREA, e), relupper = EPAR(RELUPPERZONEAREA, e),
-                 rellower = EPAR(RELLOWERZONEAREA, e), dt = EPAR(DT, e), petalt = EPAR(PETALTITUDE, e);
+    nc[e] = (int)(d->sfdist_ptr[eb + 1] - d->sfdist_ptr[eb]);
+    nu[e] = (int)(d->uh_ptr[eb + 1] - d->uh_ptr[eb]);
+    recstep[e] = d->recstep[eb];
+    fcol[e] = d->forcing_col[eb];
+    zone0[e] = h->zone_ptr[e];
+    snow0[e] = h->snow_ptr[e];
+    sred_ptr[e] = d->sred_ptr[eb];
+    double ev[HB_EP_COUNT];
+    for (int p = 0; p < HB_EP_COUNT; ++p) ev[p] = mods.eval(p, d->epar[(int64_t)p * neb + eb], m, eb);
     int info = 0;
-    bool soilonly = true, coupled = false;
-    if ((d->eflags[e] & HB_EF_RESPAREA) && relsoil > 0.0) info |= HB_EI_RESPAREA;
+    bool soilonly = true, coupled = false, nonsoil = false;
+    if ((d->eflags[eb] & HB_EF_RESPAREA) && ev[HB_EP_RELSOILAREA] > 0.0) info |= HB_EI_RESPAREA;
+    double beta_last = 0.0;
     for (int k = 0; k < n; ++k) {
       const int64_t zz = z0 + k;
       const int zt = d->zonetype[zz];
@@ -537,71 +754,23 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       HB_REQUIRE(h, d->zorder[zz] >= 0 && d->zorder[zz] < n, HB_EINVAL, "hb_set_land: zorder out of range");
       if (zt == HB_ILAKE) info |= HB_EI_LAKE;
       if (zt == HB_SEALED) info |= HB_EI_SEALED;
-      if (zt != HB_ILAKE && !std::isinf(ZP(SMAX, zz))) info |= HB_EI_SNOWLIMIT;
+      const double smax = mods.zval(HB_ZP_SMAX, d->zpar[(int64_t)HB_ZP_SMAX * d->n_zone + zz], m, eb);
+      const double cflux = mods.zval(HB_ZP_CFLUX, d->zpar[(int64_t)HB_ZP_CFLUX * d->n_zone + zz], m, eb);
+      const double fc = mods.zval(HB_ZP_FC, d->zpar[(int64_t)HB_ZP_FC * d->n_zone + zz], m, eb);
+      if (zt != HB_ILAKE && !std::isinf(smax)) info |= HB_EI_SNOWLIMIT;
       zinfo[(size_t)k * ep + e] = zt | (d->zflags[zz] << 8);
       zorder[(size_t)k * ep + e] = d->zorder[zz];
-      double* o = kz.data() + ((size_t)k * KZ_COUNT) * ep + e;
-      // folded exactly as the reference evaluates the sub-expressions (same operands, same order, IEEE binary64;
-      // this translation unit is compiled with -fmad=false and host code never contracts)
-      const double dz = ZP(ZONEZ, zz) - z;
-      const double half = ZP(TTINT, zz) / 2.0;
-      o[(size_t)KZ_TCORR * ep] = ZP(TCORR, zz);
-      o[(size_t)KZ_TCALT_DZ * ep] = ZP(TCALT, zz) * dz;
-      o[(size_t)KZ_TT_HI * ep] = ZP(TT, zz) + half;
-      o[(size_t)KZ_TT_LO * ep] = ZP(TT, zz) - half;
-      o[(size_t)KZ_TTINT * ep] = ZP(TTINT, zz);
-      o[(size_t)KZ_PCALT_F * ep] = 1.0 + ZP(PCALT, zz) * dz;
-      o[(size_t)KZ_PCORR * ep] = ZP(PCORR, zz);
-      o[(size_t)KZ_RFCF * ep] = ZP(RFCF, zz);
-      o[(size_t)KZ_SFCF * ep] = ZP(SFCF, zz);
-      o[(size_t)KZ_ICMAX * ep] = ZP(ICMAX, zz);
-      o[(size_t)KZ_CFMAX * ep] = ZP(CFMAX, zz);
-      o[(size_t)KZ_CFVAR * ep] = ZP(CFVAR, zz);
-      o[(size_t)KZ_TTM * ep] = ZP(TTM, zz);
-      o[(size_t)KZ_CFR_CFMAX * ep] = ZP(CFR, zz) * ZP(CFMAX, zz);
-      o[(size_t)KZ_WHC * ep] = ZP(WHC, zz);
-      o[(size_t)KZ_FC * ep] = ZP(FC, zz);
-      o[(size_t)KZ_BETA * ep] = ZP(BETA, zz);
-      o[(size_t)KZ_CFLUX * ep] = ZP(CFLUX, zz);
-      o[(size_t)KZ_W_UZ * ep] = ZP(RELZONEAREA, zz) / relupper;
-      o[(size_t)KZ_W_CONTRI * ep] = ZP(RELZONEAREA, zz) / relsoil;
-      o[(size_t)KZ_THRESH * ep] = ZP(SOILMOISTURELIMIT, zz) * ZP(MAXSOILWATER, zz);
-      o[(size_t)KZ_EXCESSRED * ep] = ZP(EXCESSREDUCTION, zz);
-      o[(size_t)KZ_ATF * ep] = ZP(AIRTEMPERATUREFACTOR, zz);
-      o[(size_t)KZ_ETF * ep] = ZP(EVAPOTRANSPIRATIONFACTOR, zz);
-      o[(size_t)KZ_ALT_F * ep] = 1.0 - ZP(ALTITUDEFACTOR, zz) / 100.0 * (ZP(HRUALTITUDE, zz) - petalt);
-      o[(size_t)KZ_NEG_PF * ep] = -ZP(PRECIPITATIONFACTOR, zz);
-      o[(size_t)KZ_SMAX * ep] = ZP(SMAX, zz);
-      o[(size_t)KZ_GMELT * ep] = ZP(GMELT, zz);
-      o[(size_t)KZ_GVAR * ep] = ZP(GVAR, zz);
-      o[(size_t)KZ_W_LZ * ep] = ZP(RELZONEAREA, zz) / rellower;
-      o[(size_t)KZ_RELZONEAREA * ep] = ZP(RELZONEAREA, zz);
-      o[(size_t)KZ_TTI * ep] = ZP(TEMPERATURETHRESHOLDICE, zz);
-      o[(size_t)KZ_INV_TTINT * ep] = 1.0 / ZP(TTINT, zz);
-      o[(size_t)KZ_INV_RFCF * ep] = 1.0 / ZP(RFCF, zz);
-      o[(size_t)KZ_INV_SFCF * ep] = 1.0 / ZP(SFCF, zz);
-      o[(size_t)KZ_INV_FC * ep] = 1.0 / ZP(FC, zz);
-      o[(size_t)KZ_INV_THRESH * ep] = 1.0 / (ZP(SOILMOISTURELIMIT, zz) * ZP(MAXSOILWATER, zz));
-      if (model[e] == HB_MODEL_HLAND_96P) {
-        // folded like the reference evaluates them: (suz-sgr)*(1-w0), suz*(1-w1), w2*sg1 + ((1-w2)*k2)*gr1
-        o[(size_t)KZ_X0 * ep] = ZP(SGR, zz);
-        o[(size_t)KZ_X1 * ep] = 1.0 - ZP(W0, zz);
-        o[(size_t)KZ_X2 * ep] = 1.0 - ZP(W1, zz);
-        o[(size_t)KZ_X3 * ep] = ZP(K2, zz);
-        o[(size_t)KZ_X4 * ep] = ZP(W2, zz);
-        o[(size_t)KZ_X5 * ep] = (1.0 - ZP(W2, zz)) * ZP(K2, zz);
-        o[(size_t)KZ_X6 * ep] = ZP(SG1MAX, zz);
-      } else if (model[e] == HB_MODEL_HLAND_96C) {
-        o[(size_t)KZ_X0 * ep] = ZP(H1, zz);
-        o[(size_t)KZ_X1 * ep] = ZP(TAB1, zz);
-        o[(size_t)KZ_X2 * ep] = ZP(TVS1, zz);
-        o[(size_t)KZ_X3 * ep] = ZP(H2, zz);
-        o[(size_t)KZ_X4 * ep] = ZP(TAB2, zz);
-        o[(size_t)KZ_X5 * ep] = ZP(TVS2, zz);
-        o[(size_t)KZ_W_LAND * ep] = ZP(RELZONEAREA, zz) / EPAR(RELLANDAREA, e);
+      if (host_fold) {
+        // folded exactly as the reference evaluates the sub-expressions (same operands, same order, IEEE binary64;
+        // this translation unit is compiled with -fmad=false and host code never contracts)
+        double zv[HB_ZP_COUNT];
+        for (int p = 0; p < HB_ZP_COUNT; ++p) zv[p] = mods.zval(p, d->zpar[(int64_t)p * d->n_zone + zz], m, eb);
+        fold_zone(zv, ev, model[e], kz.data() + ((size_t)k * KZ_COUNT) * ep + e, (size_t)ep);
       }
+      if (k == n - 1) beta_last = mods.zval(HB_ZP_BETA, d->zpar[(int64_t)HB_ZP_BETA * d->n_zone + zz], m, eb);
       if (zt != HB_FIELD && zt != HB_FOREST) soilonly = false;
-      if ((zt == HB_FIELD || zt == HB_FOREST) && !(ZP(CFLUX, zz) == 0.0)) coupled = true;
+      if ((zt == HB_FIELD || zt == HB_FOREST) && !(cflux == 0.0)) coupled = true;
+      if (!((zt == HB_FIELD || zt == HB_FOREST) && fc > 0.0)) nonsoil = true;
     }
     if (model[e] != HB_MODEL_HLAND_96) {
       // sibling models have neither a contributing area nor a capillary flux: the time-split fast path always applies
@@ -613,49 +782,18 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       info |= HB_EI_COUPLED;          // (the fused kernel convolves a unit hydrograph: rconc_nash elements stay general)
       coupled_list.push_back((int32_t)e);
     }
+    if ((info & HB_EI_FAST) && nonsoil)
+      (model[e] == HB_MODEL_HLAND_96 ? h->any_nonsoil_warp : h->any_nonsoil_sib[model[e] - 1]) = true;
     info |= model[e] << HB_EI_MODEL_SHIFT;
     if (soilonly) info |= HB_EI_SOILONLY;
     if (info & HB_EI_SNOWLIMIT) any_snowlimit = true;
     einfo[e] = info;
-    ke[(size_t)KE_DT * ep + e] = dt;
-    ke[(size_t)KE_DT_PERCMAX * ep + e] = dt * EPAR(PERCMAX, e);
-    ke[(size_t)KE_DT_K * ep + e] = dt * EPAR(K, e);
-    ke[(size_t)KE_ALPHA1 * ep + e] = 1.0 + EPAR(ALPHA, e);
-    ke[(size_t)KE_K4 * ep + e] = EPAR(K4, e);
-    ke[(size_t)KE_GAMMA1 * ep + e] = 1.0 + EPAR(GAMMA, e);
-    ke[(size_t)KE_RELUPPER * ep + e] = relupper;
-    ke[(size_t)KE_RELLOWER * ep + e] = rellower;
-    ke[(size_t)KE_UP_LOW * ep + e] = relupper / rellower;
-    ke[(size_t)KE_QFACTOR * ep + e] = EPAR(QFACTOR, e);
-    ke[(size_t)KE_RELSOILAREA * ep + e] = relsoil;
-    ke[(size_t)KE_RELLANDAREA * ep + e] = EPAR(RELLANDAREA, e);
-    ke[(size_t)KE_BETA_LAST * ep + e] = ZP(BETA, z0 + n - 1);
-    ke[(size_t)KE_K3 * ep + e] = EPAR(K3, e);
-    ke[(size_t)KE_W3 * ep + e] = EPAR(W3, e);
-    ke[(size_t)KE_W4 * ep + e] = EPAR(W4, e);
-    ke[(size_t)KE_FSG * ep + e] = EPAR(FSG, e);
-    ke[(size_t)KE_OMFSG * ep + e] = 1.0 - EPAR(FSG, e);
-    ke[(size_t)KE_NASH_DT * ep + e] = EPAR(NASH_DT, e);
-    ke[(size_t)KE_NASH_DTKSC * ep + e] = EPAR(NASH_DT, e) * EPAR(NASH_KSC, e);
-    for (int c = 0; c < nc[e]; ++c) sfdist[(size_t)c * ep + e] = d->sfdist[d->sfdist_ptr[e] + c];
-    for (int j = 0; j < nu[e]; ++j) uh[(size_t)j * ep + e] = d->uh[d->uh_ptr[e] + j];
+    if (host_fold) fold_element(ev, beta_last, ke.data() + e, (size_t)ep);
+    for (int c = 0; c < nc[e]; ++c) sfdist[(size_t)c * ep + e] = d->sfdist[d->sfdist_ptr[eb] + c];
+    for (int j = 0; j < nu[e]; ++j) uh[(size_t)j * ep + e] = d->uh[d->uh_ptr[eb] + j];
   }
-#undef ZP
-#undef EPAR
-  for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = ne ? d->sred_ptr[ne] : 0;
+  for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = neb ? d->sred_ptr[neb] : 0;
   h->any_snowlimit = any_snowlimit;
-  h->any_nonsoil_warp = false;
-  h->any_nonsoil_sib[0] = h->any_nonsoil_sib[1] = false;
-  for (int64_t e = 0; e < ne; ++e) {
-    if (!(einfo[e] & HB_EI_FAST)) continue;
-    bool& flag = model[e] == HB_MODEL_HLAND_96 ? h->any_nonsoil_warp : h->any_nonsoil_sib[model[e] - 1];
-    if (flag) continue;
-    for (int k = 0; k < nz[e]; ++k) {
-      const int zt = zinfo[(size_t)k * ep + e] & 7;
-      const double fc = kz[((size_t)k * KZ_COUNT + KZ_FC) * ep + e];
-      if (!((zt == HB_FIELD || zt == HB_FOREST) && fc > 0.0)) { flag = true; break; }
-    }
-  }
   h->n_fast = n_fast;
   h->n_fast_sib[0] = n_fast_sib[0]; h->n_fast_sib[1] = n_fast_sib[1];
   h->coupled_list = coupled_list;
@@ -670,15 +808,15 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   h->general_key = -1;
   {
     HB_REQUIRE(h, (int64_t)zmax * ep < ((int64_t)1 << 31), HB_EINVAL, "hb_set_land: too many zone slots for 32-bit indices");
-    std::vector<int32_t> zone_slot((size_t)d->n_zone, -1), snow_slot((size_t)d->n_snow, -1);
-    std::vector<int64_t> zone_cell0(ep + 1, d->n_zone), snow_cell0(ep + 1, d->n_snow);
+    std::vector<int32_t> zone_slot((size_t)n_zone, -1), snow_slot((size_t)n_snow, -1);
+    std::vector<int64_t> zone_cell0(ep + 1, n_zone), snow_cell0(ep + 1, n_snow);
     for (int64_t e = 0; e < ne; ++e) {
-      zone_cell0[e] = d->zone_ptr[e];
-      snow_cell0[e] = d->snow_ptr[e];
+      zone_cell0[e] = h->zone_ptr[e];
+      snow_cell0[e] = h->snow_ptr[e];
       if (!(einfo[e] & HB_EI_FAST)) continue;
       for (int k = 0; k < nz[e]; ++k) {
-        zone_slot[(size_t)d->zone_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);
-        snow_slot[(size_t)d->snow_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);   // fast path: one snow class
+        zone_slot[(size_t)h->zone_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);
+        snow_slot[(size_t)h->snow_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);   // fast path: one snow class
       }
     }
     int rc2;
@@ -692,10 +830,38 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
       (rc = upload(h, h->d_recstep, recstep)) || (rc = upload(h, h->d_einfo, einfo)) ||
       (rc = upload(h, h->d_fcol, fcol)) || (rc = upload(h, h->d_zinfo, zinfo)) || (rc = upload(h, h->d_zorder, zorder)) ||
       (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) ||
-      (rc = upload(h, h->d_sred_ptr, sred_ptr)) || (rc = upload(h, h->d_kz, kz)) || (rc = upload(h, h->d_ke, ke)) ||
+      (rc = upload(h, h->d_sred_ptr, sred_ptr)) ||
       (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)) ||
       (rc = upload(h, h->d_coupled_list, coupled_list)))
     return rc;
+  if (host_fold) {
+    if ((rc = upload(h, h->d_kz, kz)) || (rc = upload(h, h->d_ke, ke))) return rc;
+  } else {
+    // raw parameters of the base basin + the members' modifications -> folded constants, on the device
+    DBuf<double> d_zpar, d_epar, d_mul, d_add;
+    DBuf<int64_t> d_zptr;
+    DBuf<int32_t> d_model, d_par;
+    DBuf<uint8_t> d_mask;
+    if (mods.mask && (rc = upload(h, d_mask, mods.mask, (size_t)(mods.n_mod * neb)))) return rc;
+    std::vector<int32_t> model_b(neb, HB_MODEL_HLAND_96);
+    if (d->model) model_b.assign(d->model, d->model + neb);
+    const size_t nm = (size_t)(M * mods.n_mod);
+    if ((rc = upload(h, d_zpar, d->zpar, (size_t)HB_ZP_COUNT * d->n_zone)) ||
+        (rc = upload(h, d_epar, d->epar, (size_t)HB_EP_COUNT * neb)) || (rc = upload(h, d_zptr, d->zone_ptr, (size_t)neb + 1)) ||
+        (rc = upload(h, d_model, model_b)) || (rc = upload(h, d_par, mods.par, (size_t)mods.n_mod)) ||
+        (rc = upload(h, d_mul, mods.mul, nm)) || (rc = upload(h, d_add, mods.add, nm)))
+      return rc;
+    HB_CUDA(h, h->d_kz.reserve((size_t)zmax * KZ_COUNT * ep));
+    HB_CUDA(h, h->d_ke.reserve((size_t)KE_COUNT * ep));
+    HB_CUDA(h, cudaMemsetAsync(h->d_kz.p, 0, (size_t)zmax * KZ_COUNT * ep * sizeof(double), h->stream));
+    HB_CUDA(h, cudaMemsetAsync(h->d_ke.p, 0, (size_t)KE_COUNT * ep * sizeof(double), h->stream));
+    fold_members_kernel<<<(unsigned)((ne + 127) / 128), 128, 0, h->stream>>>(
+        d_zpar.p, d_epar.p, d_zptr.p, d_model.p, neb, d->n_zone, M, mods.n_mod, d_par.p, d_mul.p, d_add.p,
+        mods.mask ? d_mask.p : nullptr, zmax, ep,
+        h->d_kz.p, h->d_ke.p);
+    HB_CUDA(h, cudaGetLastError());
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));   // (the temporary buffers die here)
+  }
   if ((rc = upload(h, h->d_sred_from, d->sred_from, (size_t)d->n_sred)) ||
       (rc = upload(h, h->d_sred_to, d->sred_to, (size_t)d->n_sred)) ||
       (rc = upload(h, h->d_sred_adjust, d->sred_adjust, (size_t)d->n_sred)))
@@ -718,6 +884,21 @@ int hb_set_land(hb_engine* h, const hb_land_desc* d) {
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_land = true;
   h->have_results = false;
+  return HB_OK;
+}
+
+int hb_set_land(hb_engine* h, const hb_land_desc* d) {
+  if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
+  HB_REQUIRE(h, d && d->n_elem >= 0, HB_EINVAL, "hb_set_land: invalid description");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  MemberMods mods;
+  h->members = 1;
+  h->member_node_stride = 0;
+  if (h->river_members > 1) { h->have_river = false; h->river_members = 1; }   // (the replicated network belongs to the old land)
+  int rc = set_land_core(h, d, mods);
+  if (rc) return rc;
+  h->base_land.keep(d);          // (hb_set_members builds the ensemble from this copy)
   return HB_OK;
 }
 
@@ -887,9 +1068,7 @@ int hb_select_series(hb_engine* h, int series, int on) {
 // ---------------------------------------------------------------------------------------------------------------------
 // river setup
 // ---------------------------------------------------------------------------------------------------------------------
-int hb_set_river(hb_engine* h, const hb_river_desc* r) {
-  if (!h) return HB_EINVAL;
-  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
+static int set_river_core(hb_engine* h, const hb_river_desc* r) {
   HB_REQUIRE(h, h->have_land, HB_ESTATE, "hb_set_river: call hb_set_land first");
   HB_REQUIRE(h, r && r->n_node >= 0 && r->n_reach >= 0, HB_EINVAL, "hb_set_river: invalid description");
   HB_CUDA(h, cudaSetDevice(h->device));
@@ -1153,6 +1332,196 @@ int hb_set_river(hb_engine* h, const hb_river_desc* r) {
   h->dis_cur = 0;
   h->have_river = true;
   h->have_ext = false;
+  return HB_OK;
+}
+
+int hb_set_river(hb_engine* h, const hb_river_desc* r) {
+  if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
+  HB_REQUIRE(h, h->members == 1, HB_ESTATE, "hb_set_river: the land part holds ensemble members; describe the basin "
+                                            "(hb_set_land, hb_set_river) first, then call hb_set_members");
+  int rc = set_river_core(h, r);
+  if (rc) return rc;
+  h->base_river.keep(r);
+  h->river_members = 1;
+  return HB_OK;
+}
+
+// dst[row][m * n + i] = base[row][i] for m = 0 .. members-1 (row pitch `pitch` elements)
+__global__ void tile_rows_kernel(double* __restrict__ dst, const double* __restrict__ base, int64_t rows, int64_t n,
+                                 int64_t members, int64_t pitch) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * members * n) return;
+  const int64_t row = i / (members * n), j = i - row * members * n;
+  dst[row * pitch + j] = base[row * n + j % n];
+}
+
+// the first `n` cells of every row of a device state array ([rows][pitch_old]), i.e. member 0 / the base basin
+static int grab_rows(hb_engine* h, std::vector<double>& out, const double* dev, int64_t rows, int64_t n, int64_t pitch_old) {
+  out.assign((size_t)(rows * n), 0.0);
+  if (rows * n == 0) return HB_OK;
+  HB_CUDA(h, cudaMemcpy2D(out.data(), (size_t)n * sizeof(double), dev, (size_t)pitch_old * sizeof(double),
+                          (size_t)n * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost));
+  return HB_OK;
+}
+static int tile_rows(hb_engine* h, DBuf<double>& dst, const std::vector<double>& base, int64_t rows, int64_t n,
+                     int64_t members, int64_t pitch) {
+  if (rows * n == 0) return HB_OK;
+  DBuf<double> tmp;
+  int rc = upload(h, tmp, base.data(), base.size());
+  if (rc) return rc;
+  HB_CUDA(h, dst.reserve((size_t)(rows * pitch)));
+  HB_CUDA(h, cudaMemsetAsync(dst.p, 0, (size_t)(rows * pitch) * sizeof(double), h->stream));
+  const int64_t total = rows * members * n;
+  tile_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(dst.p, tmp.p, rows, n, members, pitch);
+  HB_CUDA(h, cudaGetLastError());
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HB_OK;
+}
+
+int hb_set_members(hb_engine* h, int64_t members, int64_t n_mod, const int32_t* mod_par, const double* mul,
+                   const double* add, const uint8_t* mod_mask) {
+  if (!h) return HB_EINVAL;
+  if (h->pending) { int rc_ = hb_wait(h); if (rc_) return rc_; }
+  HB_REQUIRE(h, h->have_land && h->base_land.valid, HB_ESTATE, "hb_set_members: call hb_set_land first");
+  HB_REQUIRE(h, members >= 1 && n_mod >= 0 && (n_mod == 0 || (mod_par && mul && add)), HB_EINVAL,
+             "hb_set_members: invalid argument");
+  HB_CUDA(h, cudaSetDevice(h->device));
+  const hb_land_desc* d = &h->base_land.d;
+  MemberMods mods;
+  mods.members = members; mods.n_mod = n_mod; mods.par = mod_par; mods.mul = mul; mods.add = add;
+  mods.mask = n_mod ? mod_mask : nullptr; mods.n_elem_base = d->n_elem;
+  for (int64_t j = 0; j < n_mod; ++j) {
+    const int p = mod_par[j];
+    const bool zone = p >= 0 && p < HB_ZP_COUNT, elem = p >= HB_MOD_EPAR && p < HB_MOD_EPAR + HB_EP_COUNT;
+    HB_REQUIRE(h, zone || elem, HB_EINVAL, "hb_set_members: unknown parameter id %d", p);
+    // structure and derived geometry stay what hb_set_land was given
+    HB_REQUIRE(h, !(zone && (p == HB_ZP_SMAX || p == HB_ZP_RELZONEAREA || p == HB_ZP_HRUAREAFRACTION || p == HB_ZP_ZONEZ ||
+                             p == HB_ZP_HRUALTITUDE)) &&
+                      !(elem && (p - HB_MOD_EPAR == HB_EP_Z || p - HB_MOD_EPAR == HB_EP_RELSOILAREA ||
+                                 p - HB_MOD_EPAR == HB_EP_RELLANDAREA || p - HB_MOD_EPAR == HB_EP_RELUPPERZONEAREA ||
+                                 p - HB_MOD_EPAR == HB_EP_RELLOWERZONEAREA || p - HB_MOD_EPAR == HB_EP_DT ||
+                                 p - HB_MOD_EPAR == HB_EP_QFACTOR || p - HB_MOD_EPAR == HB_EP_PETALTITUDE)),
+               HB_EINVAL, "hb_set_members: parameter id %d is structural / derived from the geometry and cannot vary "
+                          "between members", p);
+  }
+  // ---- the conditions of the base basin (member 0) on the device, before the arrays are rebuilt -----------------------
+  const int64_t neb = d->n_elem, ep_old = h->e_pad;
+  const int zmax_o = h->zmax, cmax_o = h->cmax, umax_o = h->umax;
+  const bool had_states = h->have_states;
+  std::vector<double> b_ic, b_sm, b_sp, b_wc, b_uz, b_lz, b_quh, b_zx1, b_zx2, b_ex1, b_ex2;
+  const bool had_sib = h->any_sibling;
+  if (had_states) {
+    int rc;
+    if ((rc = grab_rows(h, b_ic, h->d_ic.p, zmax_o, neb, ep_old)) || (rc = grab_rows(h, b_sm, h->d_sm.p, zmax_o, neb, ep_old)) ||
+        (rc = grab_rows(h, b_sp, h->d_sp.p, (int64_t)zmax_o * cmax_o, neb, ep_old)) ||
+        (rc = grab_rows(h, b_wc, h->d_wc.p, (int64_t)zmax_o * cmax_o, neb, ep_old)) ||
+        (rc = grab_rows(h, b_uz, h->d_uz.p, 1, neb, ep_old)) || (rc = grab_rows(h, b_lz, h->d_lz.p, 1, neb, ep_old)) ||
+        (rc = grab_rows(h, b_quh, h->d_quh.p, umax_o, neb, ep_old)))
+      return rc;
+    if (had_sib && ((rc = grab_rows(h, b_zx1, h->d_zx1.p, zmax_o, neb, ep_old)) ||
+                    (rc = grab_rows(h, b_zx2, h->d_zx2.p, zmax_o, neb, ep_old)) ||
+                    (rc = grab_rows(h, b_ex1, h->d_ex1.p, 1, neb, ep_old)) || (rc = grab_rows(h, b_ex2, h->d_ex2.p, 1, neb, ep_old))))
+      return rc;
+  }
+  std::vector<double> b_dis, b_cn, b_rn, b_rwd;
+  const bool had_river = h->have_river && h->base_river.valid;
+  const int64_t nsb = had_river ? h->base_river.d.n_seg : 0;
+  const bool had_mct = had_river && h->any_mct;
+  if (had_river && nsb) {
+    b_dis.resize((size_t)nsb);
+    HB_CUDA(h, cudaMemcpy(b_dis.data(), h->d_dis[h->dis_cur].p, (size_t)nsb * sizeof(double), cudaMemcpyDeviceToHost));
+    if (had_mct) {
+      b_cn.resize((size_t)nsb); b_rn.resize((size_t)nsb); b_rwd.resize((size_t)nsb);
+      HB_CUDA(h, cudaMemcpy(b_cn.data(), h->d_mct_cn.p, (size_t)nsb * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(b_rn.data(), h->d_mct_rn.p, (size_t)nsb * sizeof(double), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(b_rwd.data(), h->d_mct_rwd.p, (size_t)nsb * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
+  // ---- land: `members` copies, constants folded on the device --------------------------------------------------------
+  h->members = members;
+  h->member_node_stride = had_river ? h->base_river.d.n_node : 0;
+  if (!had_river && d->outlet_node)
+    for (int64_t e = 0; e < neb; ++e)
+      if (d->outlet_node[e] + 1 > h->member_node_stride) h->member_node_stride = d->outlet_node[e] + 1;
+  int rc = set_land_core(h, d, mods);
+  if (rc) return rc;
+  if (had_states) {
+    const int64_t ep = h->e_pad;
+    if ((rc = tile_rows(h, h->d_ic, b_ic, zmax_o, neb, members, ep)) || (rc = tile_rows(h, h->d_sm, b_sm, zmax_o, neb, members, ep)) ||
+        (rc = tile_rows(h, h->d_sp, b_sp, (int64_t)zmax_o * cmax_o, neb, members, ep)) ||
+        (rc = tile_rows(h, h->d_wc, b_wc, (int64_t)zmax_o * cmax_o, neb, members, ep)) ||
+        (rc = tile_rows(h, h->d_uz, b_uz, 1, neb, members, ep)) || (rc = tile_rows(h, h->d_lz, b_lz, 1, neb, members, ep)) ||
+        (rc = tile_rows(h, h->d_quh, b_quh, umax_o, neb, members, ep)))
+      return rc;
+    if (had_sib && ((rc = tile_rows(h, h->d_zx1, b_zx1, zmax_o, neb, members, ep)) ||
+                    (rc = tile_rows(h, h->d_zx2, b_zx2, zmax_o, neb, members, ep)) ||
+                    (rc = tile_rows(h, h->d_ex1, b_ex1, 1, neb, members, ep)) || (rc = tile_rows(h, h->d_ex2, b_ex2, 1, neb, members, ep))))
+      return rc;
+    h->have_states = true;
+  }
+  // ---- river: `members` copies of the network (member m's nodes, reaches and segments follow member m-1's) ------------
+  if (had_river) {
+    const hb_river_desc* r = &h->base_river.d;
+    const int64_t nn = r->n_node, nr = r->n_reach, M = members;
+    hb_river_desc t = *r;
+    t.n_node = M * nn; t.n_reach = M * nr; t.n_entry = M * r->n_entry; t.n_inlet = M * r->n_inlet; t.n_seg = M * r->n_seg;
+    t.n_trap = M * r->n_trap;
+    std::vector<int64_t> entry_ptr(t.n_node + 1), inlet_ptr(t.n_reach + 1), seg_ptr(t.n_reach + 1), trap_ptr(t.n_reach + 1, 0);
+    std::vector<int32_t> entry_src((size_t)t.n_entry), node_mode((size_t)t.n_node), node_ext((size_t)t.n_node),
+        inlet_node((size_t)t.n_inlet), reach_outlet((size_t)t.n_reach), reach_model, nmbruns;
+    std::vector<double> coef((size_t)3 * t.n_reach), rpar, tpar;
+    HB_REQUIRE(h, t.n_node < ((int64_t)1 << 30) && t.n_reach < ((int64_t)1 << 30) && M * neb < ((int64_t)1 << 30), HB_EINVAL,
+               "hb_set_members: too many members for 32-bit indices");
+    if (r->reach_model) { reach_model.resize((size_t)t.n_reach); nmbruns.resize((size_t)t.n_reach); rpar.resize((size_t)HB_RP_COUNT * t.n_reach); }
+    if (r->n_trap) tpar.resize((size_t)HB_TP_COUNT * t.n_trap);
+    for (int64_t m = 0; m < M; ++m) {
+      for (int64_t n = 0; n < nn; ++n) {
+        entry_ptr[m * nn + n] = m * r->n_entry + r->entry_ptr[n];
+        node_mode[m * nn + n] = r->node_mode[n];
+        node_ext[m * nn + n] = r->node_ext[n];           // observation / boundary rows are shared by the members
+      }
+      for (int64_t i = 0; i < r->n_entry; ++i) {
+        const int32_t v = r->entry_src[i];
+        entry_src[m * r->n_entry + i] = v >= 0 ? (int32_t)(v + m * neb) : v <= HB_ENTRY_EXT ? v : (int32_t)(v - m * nr);
+      }
+      for (int64_t q = 0; q < nr; ++q) {
+        inlet_ptr[m * nr + q] = m * r->n_inlet + r->inlet_ptr[q];
+        seg_ptr[m * nr + q] = m * r->n_seg + r->seg_ptr[q];
+        reach_outlet[m * nr + q] = r->reach_outlet[q] < 0 ? -1 : (int32_t)(r->reach_outlet[q] + m * nn);
+        for (int j = 0; j < 3; ++j) coef[(size_t)j * t.n_reach + m * nr + q] = r->coef[(size_t)j * nr + q];
+        if (r->reach_model) {
+          reach_model[m * nr + q] = r->reach_model[q];
+          nmbruns[m * nr + q] = r->nmbruns ? r->nmbruns[q] : 1;
+          for (int j = 0; j < HB_RP_COUNT; ++j)
+            rpar[(size_t)j * t.n_reach + m * nr + q] = r->rpar ? r->rpar[(size_t)j * nr + q] : 0.0;
+        }
+        if (r->trap_ptr) trap_ptr[m * nr + q] = m * r->n_trap + r->trap_ptr[q];
+      }
+      for (int64_t i = 0; i < r->n_inlet; ++i) inlet_node[m * r->n_inlet + i] = (int32_t)(r->inlet_node[i] + m * nn);
+      for (int64_t i = 0; i < r->n_trap; ++i)
+        for (int j = 0; j < HB_TP_COUNT; ++j) tpar[(size_t)j * t.n_trap + m * r->n_trap + i] = r->tpar[(size_t)j * r->n_trap + i];
+    }
+    entry_ptr[t.n_node] = t.n_entry; inlet_ptr[t.n_reach] = t.n_inlet; seg_ptr[t.n_reach] = t.n_seg; trap_ptr[t.n_reach] = t.n_trap;
+    t.entry_ptr = entry_ptr.data(); t.entry_src = entry_src.data(); t.node_mode = node_mode.data(); t.node_ext = node_ext.data();
+    t.inlet_ptr = inlet_ptr.data(); t.inlet_node = inlet_node.data(); t.reach_outlet = reach_outlet.data();
+    t.seg_ptr = seg_ptr.data(); t.coef = coef.data();
+    t.reach_model = r->reach_model ? reach_model.data() : nullptr; t.nmbruns = r->reach_model ? nmbruns.data() : nullptr;
+    t.rpar = r->reach_model ? rpar.data() : nullptr; t.trap_ptr = r->trap_ptr ? trap_ptr.data() : nullptr;
+    t.tpar = r->n_trap ? tpar.data() : nullptr;
+    if ((rc = set_river_core(h, &t))) return rc;
+    h->river_members = members;
+    if (nsb) {
+      // (discharge and the musk_mct conditions are [n_seg] arrays: the members' copies follow each other)
+      for (DBuf<double>* dst : {&h->d_dis[h->dis_cur]})
+        if ((rc = tile_rows(h, *dst, b_dis, 1, nsb, members, members * nsb))) return rc;
+      if (had_mct && h->any_mct &&
+          ((rc = tile_rows(h, h->d_mct_cn, b_cn, 1, nsb, members, members * nsb)) ||
+           (rc = tile_rows(h, h->d_mct_rn, b_rn, 1, nsb, members, members * nsb)) ||
+           (rc = tile_rows(h, h->d_mct_rwd, b_rwd, 1, nsb, members, members * nsb))))
+        return rc;
+    }
+  }
   return HB_OK;
 }
 

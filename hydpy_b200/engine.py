@@ -28,7 +28,7 @@ EXPORTS = (
     "hb_node_statistics", "hb_get_reach_outflow", "hb_get_reach_inflow", "hb_get_reach_state_series", "hb_get_mct_series", "hb_get_series", "hb_comm_unique_id", "hb_comm_init",
     "hb_comm_send_rows", "hb_comm_recv_ext", "hb_comm_barrier", "hb_get_timing", "hb_timer_start", "hb_timer_stop",
     "hb_measure_fp64_peak",
-    "hb_device_info",
+    "hb_device_info", "hb_set_members",
 )
 
 
@@ -73,6 +73,8 @@ def load_library() -> C.CDLL:
         "hb_get_river_states": (C.c_int, [H, f64p]),
         "hb_select_series": (C.c_int, [H, C.c_int, C.c_int]),
         "hb_set_option": (C.c_int, [H, C.c_int, C.c_int64]),
+        "hb_set_members": (C.c_int, [H, C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_uint8)]),
         "hb_set_forcing": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
         "hb_set_forcing_async": (C.c_int, [H, C.c_int64, C.c_int64, f64p, i64p]),
         "hb_select_window": (C.c_int, [H, C.c_int64, C.c_int64]),
@@ -153,6 +155,18 @@ class PinnedArray:
         self._p = None
 
 
+class _Members:
+    """Sizes of an ensemble on the device: `members` copies of a base bundle (hb_set_members)."""
+
+    def __init__(self, base, members: int, names: tuple[str, ...]):
+        self.base, self.members = base, int(members)
+        for n in names:
+            setattr(self, n, getattr(base, n) * self.members)
+
+    def __getattr__(self, name):          # everything that is not a size (any_mct, n_ext, …) is the base's
+        return getattr(self.base, name)
+
+
 class Engine:
     """One engine = one GPU (`hb_create`).  Methods map 1:1 to the C entry points."""
 
@@ -207,6 +221,47 @@ class Engine:
         d = land.as_struct()
         self._check(self._lib.hb_set_land(self._h, C.byref(d)), "hb_set_land")
         self.land = land
+
+    def set_members(self, members: int, mods=None) -> None:
+        """Turn the basin on the device (land, river and their conditions) into `members` copies of itself — the batched
+        calibration caller (`hb_set_members`).  `mods`: parameter name (a row of `layout.ZPAR` or `layout.EPAR`) →
+        (mul[members], add[members]) — member m computes with `value * mul[m] + add[m]` for every zone / element — or a
+        list of (name, mul, add, mask) with `mask` = None or a bool array over the basin's elements (a rule bound to a
+        selection); list entries act in the given order.  All results then hold `members` times the rows / cells of the
+        basin, member after member."""
+        mods = mods or {}
+        entries = [(n, m_, a_, None) for n, (m_, a_) in mods.items()] if isinstance(mods, dict) else list(mods)
+        base_land = self.land.base if isinstance(self.land, _Members) else self._need_land()
+        base_river = getattr(self, "river", None)
+        base_river = base_river.base if isinstance(base_river, _Members) else base_river
+        ids, mul, add, masks = [], [], [], []
+        for name, m_, a_, mask_ in entries:
+            masks.append(None if mask_ is None else np.asarray(mask_, bool))
+            if name in layout.ZP:
+                ids.append(layout.ZP[name])
+            elif name in layout.EP:
+                ids.append(layout.MOD_EPAR + layout.EP[name])
+            else:
+                raise ValueError(f"unknown parameter {name!r}")
+            mul.append(np.broadcast_to(np.asarray(m_, np.float64), (members,)))
+            add.append(np.broadcast_to(np.asarray(a_, np.float64), (members,)))
+        par = np.ascontiguousarray(ids, dtype=np.int32)
+        mul_a = np.ascontiguousarray(np.stack(mul, axis=1) if mul else np.zeros((members, 0)))
+        add_a = np.ascontiguousarray(np.stack(add, axis=1) if add else np.zeros((members, 0)))
+        mask_a = None
+        if any(k is not None for k in masks):
+            mask_a = np.ascontiguousarray(np.stack([np.ones(base_land.n_elem, bool) if k is None else k for k in masks])
+                                          .astype(np.uint8))
+            if mask_a.shape != (len(ids), base_land.n_elem):
+                raise ValueError("a modification mask must have one entry per element of the basin")
+        self._check(self._lib.hb_set_members(self._h, int(members), len(ids), ptr(par, C.c_int32) if len(ids) else None,
+                                             ptr(mul_a, C.c_double) if len(ids) else None,
+                                             ptr(add_a, C.c_double) if len(ids) else None,
+                                             ptr(mask_a, C.c_uint8) if mask_a is not None else None), "hb_set_members")
+        self.members = int(members)
+        self.land = _Members(base_land, members, ("n_elem", "n_zone", "n_snow", "n_uh")) if members > 1 else base_land
+        if base_river is not None:
+            self.river = (_Members(base_river, members, ("n_node", "n_reach", "n_seg")) if members > 1 else base_river)
 
     def set_land_states(self, states: LandStates) -> None:
         s = states.as_struct()

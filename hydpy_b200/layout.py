@@ -6,7 +6,7 @@ truth.  Names follow the reference's parameter/sequence names (`hydpy/models/hla
 """
 from __future__ import annotations
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # zone types, `hydpy/models/hland/hland_constants.py`
 FIELD, FOREST, GLACIER, ILAKE, SEALED = 1, 2, 3, 4, 5
@@ -101,6 +101,7 @@ OPT_RIVER_SWEEP = 1
 OPT_RIVER_STATE_SERIES = 2
 OPT_RIVER_WAVE_BLOCKS = 3
 OPT_RIVER_MCT_SERIES = 4
+MOD_EPAR = 1000
 OPT_LAND_SLABS = 5
 OPT_LAND_CHUNK = 6
 RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2

@@ -347,6 +347,33 @@ def replicate_members(land: LandBundle, states: LandStates, members: int, *, see
     return out, st
 
 
+def member_mods(members: int, *, seed: int = 20260101, jitter: float = 0.25) -> dict[str, tuple[np.ndarray, np.ndarray]]:
+    """The parameter sets of `replicate_members` as modifications for `Engine.set_members` (`hb_set_members`): parameter
+    name → (mul[members], add[members]), member 0 = the given values.  Same random draws, same arithmetic (one
+    multiplication or one addition per value), so the ensemble built on the device equals the replicated bundle bit for
+    bit."""
+    m = int(members)
+    rng = np.random.default_rng(seed)
+    one, zero = np.ones(m), np.zeros(m)
+    mods: dict[str, tuple[np.ndarray, np.ndarray]] = {}
+
+    def fac() -> np.ndarray:
+        f = 1.0 + jitter * rng.uniform(-1.0, 1.0, size=(m, 1))
+        f[0] = 1.0
+        return f[:, 0]
+
+    for name in ("fc", "beta", "cfmax", "whc"):
+        mods[name] = (fac(), zero)
+    mods["maxsoilwater"] = mods["fc"]
+    shift = jitter * rng.uniform(-1.0, 1.0, size=(m, 1))
+    shift[0] = 0.0
+    mods["tt"] = (one, shift[:, 0])
+    mods["ttm"] = (one, shift[:, 0])
+    for name in ("percmax", "k", "k4", "alpha"):
+        mods[name] = (fac(), zero)
+    return mods
+
+
 def replicate_river(river: RiverBundle, discharge: np.ndarray, members: int, n_land: int
                     ) -> tuple[RiverBundle, np.ndarray]:
     """Copy the river network once per ensemble member (each member routes its own discharges)."""

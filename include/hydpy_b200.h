@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 2
+#define HB_ABI_VERSION 3
 
 /* ---- return codes ------------------------------------------------------------------------------------------ */
 #define HB_OK 0
@@ -392,6 +392,27 @@ enum hb_stat {
 };
 int hb_node_statistics(hb_engine* h, int64_t n_pair, const int32_t* nodes, const int32_t* obs_row, int64_t n_obs,
                        const double* obs, int skip_nan, double* out);
+
+/* ---- ensemble members: the batched calibration caller ------------------------------------------------ *
+ * After ONE basin has been described (hb_set_land, hb_set_river) and its conditions set (hb_set_land_states,
+ * hb_set_river_states), hb_set_members turns it into `members` copies ON THE DEVICE: member m's elements, zones, nodes,
+ * reaches and segments follow member m-1's in every array of the ABI (results are [members * n_node][nt] and so on);
+ * forcing columns and external rows are shared; every member starts from the conditions of the basin.  The members differ
+ * in control parameters: modification j gives parameter `mod_par[j]` (HB_ZP_* for a zone parameter, HB_MOD_EPAR + HB_EP_*
+ * for an element parameter) of every zone / element of member m the value
+ *        value * mul[m * n_mod + j] + add[m * n_mod + j]
+ * (`mod_mask`, NULL or [n_mod][n_elem] bytes: the elements of the basin a modification applies to — a rule bound to a
+ * `Selection`; modifications of the same parameter act in the listed order on the running value)
+ * — the Replace / Add / Multiply rules of `hydpy/auxs/calibtools.py:1181` (`CalibrationInterface.apply_values`
+ * `:2134-2150`) are (0, v), (1, v) and (v, 0).  The constants the kernels work with are folded from the modified values on
+ * the device with the operations hb_set_land uses on the host, so a member equals a basin uploaded with those values bit for
+ * bit, and an ensemble of 10^8 zones never exists on the host.  Structural parameters (SMax, areas, altitudes, derived
+ * geometry) cannot vary; derived values the reference recomputes (TTM = TT + DTTM, MaxSoilWater = FC, W0…W4 of hland_96p)
+ * are the caller's to list.  hb_set_members(h, 1, 0, …) returns to the single basin.  Calling it again replaces the
+ * members (the conditions are then those of member 0). */
+#define HB_MOD_EPAR 1000
+int hb_set_members(hb_engine* h, int64_t members, int64_t n_mod, const int32_t* mod_par, const double* mul,
+                   const double* add, const uint8_t* mod_mask);
 
 /* ---- multi-GPU boundary hand-over (NCCL over NVLink) ---------------------------------------------- */
 #define HB_NCCL_ID_BYTES 128

@@ -60,7 +60,7 @@ def test_enums_match_layout():
                          ("HB_OPT_LAND_PATH", layout.OPT_LAND_PATH), ("HB_OPT_RIVER_SWEEP", layout.OPT_RIVER_SWEEP), ("HB_OPT_RIVER_STATE_SERIES", layout.OPT_RIVER_STATE_SERIES),
                          ("HB_OPT_RIVER_WAVE_BLOCKS", layout.OPT_RIVER_WAVE_BLOCKS),
                          ("HB_OPT_RIVER_MCT_SERIES", layout.OPT_RIVER_MCT_SERIES),
-                         ("HB_OPT_LAND_SLABS", layout.OPT_LAND_SLABS), ("HB_OPT_LAND_CHUNK", layout.OPT_LAND_CHUNK),
+                         ("HB_OPT_LAND_SLABS", layout.OPT_LAND_SLABS), ("HB_MOD_EPAR", layout.MOD_EPAR), ("HB_OPT_LAND_CHUNK", layout.OPT_LAND_CHUNK),
                          ("HB_RIVER_PERSISTENT", layout.RIVER_PERSISTENT), ("HB_RIVER_LAUNCHES", layout.RIVER_LAUNCHES), ("HB_RIVER_GROUPED", layout.RIVER_GROUPED), ("HB_LAND_AUTO", layout.LAND_AUTO),
                          ("HB_LAND_GENERAL", layout.LAND_GENERAL), ("HB_NCCL_ID_BYTES", layout.NCCL_ID_BYTES),
                          ("HB_ENTRY_EXT", layout.ENTRY_EXT)):

@@ -49,3 +49,14 @@ def test_reference_integration_doctests_with_the_dropin_installed(module):
                           capture_output=True, text=True, timeout=900)
     assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-3000:]
     assert "DOCTEST_OK" in proc.stdout
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+def test_calibration_rules_become_the_modifications_the_reference_would_apply():
+    """`CalibrationAdapter.mods` (Replace / Add / Multiply rules with selections and parameter steps → hb_set_members
+    modifications) against `rule.apply_value()` + `update_parameters()` of the reference on real objects
+    (ref: hydpy/auxs/calibtools.py:892-1178, 2134-2150)."""
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "calib_reference_worker.py")], capture_output=True,
+                          text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "CALIB_RULES_OK" in proc.stdout

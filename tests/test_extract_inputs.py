@@ -80,3 +80,28 @@ def test_requested_mct_series_follow_the_ramflags():
     odd.model.sequences.factors.froudenumber = types.SimpleNamespace(name="froudenumber", ramflag=True)
     with pytest.raises(UnsupportedModelError, match="froudenumber"):
         check_reach_series(types.SimpleNamespace(river_elements=[odd]))
+
+
+def test_elements_with_receiver_sender_or_observer_nodes_are_refused():
+    """Elements fed by `newsim`/`obs_newsim` RECEIVER nodes (or sending / observing) exchange values inside a time step
+    (ref: hydpy/core/threadingtools.py:117-131, hydpytools.py:3102-3123); the whole-period engine cannot honour that and
+    must say so instead of simulating something else."""
+    import types
+
+    import pytest
+
+    from hydpy_b200.extract import UnsupportedModelError, extract
+
+    def element(**links):
+        model = types.SimpleNamespace(name="hland_96")
+        return types.SimpleNamespace(name="land_x", model=model, receivers=links.get("receivers", ()),
+                                     senders=links.get("senders", ()), observers=links.get("observers", ()))
+
+    class Node:
+        name = "n"
+
+    node = Node()
+    for kind in ("receivers", "senders", "observers"):
+        hp = types.SimpleNamespace(nodes=[node], elements=[element(**{kind: (node,)})])
+        with pytest.raises(UnsupportedModelError, match="receiver/sender/observer"):
+            extract(hp, 0, 10)

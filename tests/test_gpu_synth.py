@@ -464,3 +464,92 @@ def test_element_slabs_and_time_chunks_do_not_change_a_bit():
         assert np.array_equal(dis0, dis)
         for n in st0.NAMES:
             assert np.array_equal(getattr(st0, n), getattr(st, n)), n
+
+
+@pytest.mark.parametrize("case", ["lahn", "variants"])
+def test_members_built_on_the_device_equal_the_replicated_bundle(case):
+    """hb_set_members (constants folded on the device from the base basin + per-member parameter modifications, river and
+    conditions replicated on the device) must give what the same ensemble gives when every member is uploaded as
+    additional elements through hb_set_land: bit for bit, states included."""
+    from tests.util import load_scenarios
+
+    members = 7
+    if case == "lahn":
+        p = load_scenarios("lahn_hourly_members.npz")["member0"].problem
+        land, states, river, discharge, forcing, doy = p.land, p.states, p.river, p.discharge, p.forcing, p.doy
+    else:
+        land, states = synth.make_land(300, "1h", variants=True, seed=9)
+        river, discharge = synth.make_tree_river(300, "1h", levels=9, seed=10)
+        discharge = np.random.default_rng(3).uniform(0, 2, river.n_seg)
+        forcing, doy = synth.make_forcing(72, "1h")
+    nt = forcing.shape[1]
+    eland, estates = synth.replicate_members(land, states, members, n_node=river.n_node)
+    eriver, edis = synth.replicate_river(river, discharge, members, land.n_elem)
+    with Engine(0) as eng:
+        ref = run_problem(Problem(land=eland, states=estates, river=eriver, discharge=edis, forcing=forcing, doy=doy,
+                                  ext=np.zeros((0, nt))), eng)
+        eng.set_land(land)
+        eng.set_land_states(states)
+        eng.set_river(river)
+        eng.set_river_states(discharge)
+        eng.set_members(members, synth.member_mods(members))
+        eng.set_forcing(forcing, doy)
+        eng.set_external(np.zeros((0, nt)))
+        eng.run()
+        rows = eng.get_node_series()
+        st = eng.get_land_states()
+        dis = eng.get_river_states()
+        assert rows.shape == (members * river.n_node, nt)
+        assert np.array_equal(rows, ref["node_rows"])
+        assert np.array_equal(dis, ref["discharge"])
+        for n in ("ic", "sm", "sp", "wc", "uz", "lz", "quh"):
+            assert np.array_equal(getattr(st, n), getattr(ref["states"], n)), n
+        assert not np.array_equal(rows[:river.n_node], rows[river.n_node:2 * river.n_node])
+        # a second window continues every member from its own conditions; going back to one basin keeps member 0
+        eng.set_forcing(forcing, doy)
+        eng.set_external(np.zeros((0, nt)))
+        eng.run()
+        rows2 = eng.get_node_series()
+        sm2 = eng.get_land_states().sm
+        eng.set_members(1)
+        assert np.array_equal(eng.get_land_states().sm, sm2[:land.n_zone])
+        eng.set_forcing(forcing, doy)
+        eng.set_external(np.zeros((0, nt)))
+        eng.run()
+        assert eng.get_node_series().shape == (river.n_node, nt)
+    ref2_states = ref["states"]
+    with Engine(0) as eng:   # the replicated bundle, second window
+        eng.set_land(eland); eng.set_land_states(ref2_states); eng.set_river(eriver); eng.set_river_states(ref["discharge"])
+        eng.set_forcing(forcing, doy); eng.set_external(np.zeros((0, nt))); eng.run()
+        assert np.array_equal(eng.get_node_series(), rows2)
+
+
+def test_sixty_four_parameter_sets_in_one_run_equal_sequential_oracle_runs():
+    """The batched calibration caller: `calib.evaluate` — M = 64 parameter sets as one ensemble on the
+    device, objective reduction on the device, windows merged — against 64 sequential oracle runs judged with NumPy:
+    NSE and KGE within the parity bar."""
+    from hydpy_b200 import calib
+    from tests.util import load_scenarios
+
+    p = load_scenarios("lahn_hourly_members.npz")["member0"].problem
+    members, nt = 64, p.nt
+    mods = synth.member_mods(members, seed=7, jitter=0.3)
+    mask = np.array([True, False, True, True])                        # one more rule, bound to three of the four elements
+    entries = [(n, m, a, None) for n, (m, a) in mods.items()] + [("icmax", np.linspace(0.5, 1.5, members), np.zeros(members), mask)]
+    nodes = [p.river.n_node - 1, 0]
+    base = oracle_run(p)
+    rng = np.random.default_rng(1)
+    obs = base["node_rows"][nodes] * rng.uniform(0.8, 1.25, size=(len(nodes), nt))
+    with Engine(0) as eng:
+        got_nse = calib.evaluate(p, members, entries, nodes, obs, criterion="nse", engine=eng, window=100)
+        got_kge = calib.evaluate(p, members, entries, nodes, obs, criterion="kge", engine=eng)
+    ref_nse, ref_kge = np.zeros((members, len(nodes))), np.zeros((members, len(nodes)))
+    for m in range(members):
+        land_m = calib.apply_mods(p.land, entries, m)
+        r = oracle_run(Problem(land=land_m, states=p.states, river=p.river, discharge=p.discharge, forcing=p.forcing,
+                               doy=p.doy, ext=p.ext, mct_states=p.mct_states))
+        st = calib.statistics_host(r["node_rows"][nodes], obs)
+        ref_nse[m], ref_kge[m] = calib.nse(st), calib.kge(st)
+    assert_close(got_nse, ref_nse, "NSE of 64 parameter sets")
+    assert_close(got_kge, ref_kge, "KGE of 64 parameter sets")
+    assert np.ptp(ref_nse[:, 0]) > 1e-3            # the sets really differ
