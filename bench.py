@@ -292,6 +292,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         pin_to_gpu_numa_node(dist.local_rank)
 
     K, W, win = args.steps, args.warmup, args.window
+    t_setup = time.perf_counter()
     eng = Engine(dist.local_rank)
     info = eng.device_info()
     wl = build_workload(args, dist)
@@ -308,6 +309,11 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         eng.set_members(wl.members, wl.mods)
     land, river = eng.land, eng.river       # (sizes of everything on the device: all members)
     ensemble = wl.members > 1
+    import resource
+
+    print(f"[bench] rank {dist.rank}: workload on the device after {time.perf_counter() - t_setup:.1f} s "
+          f"({land.n_elem} elements, {river.n_reach} reaches; host peak RSS "
+          f"{resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6:.1f} GB)", file=sys.stderr, flush=True)
 
     def reset_conditions() -> None:
         """Back to the initial conditions (an ensemble simply goes on: its conditions live on the device only)."""
@@ -484,7 +490,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         eng.timing()
         for s in range(n_iso):
             eng.select_window(s * win, win)
-            eng.set_external(no_ext)
+            eng.set_external(own_ext)
             eng.run(land=True, river=True)
         t_iso = eng.timing()
         iso = {k: t_iso[k] / n_iso for k in iso}
