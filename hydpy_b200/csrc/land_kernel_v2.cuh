@@ -458,7 +458,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
     else fracrain = (tc - tt_lo) * inv_ttint;
     double pc = in_p * pcalt_f;
     if (pc <= 0.0) pc = 0.0;
-    else pc *= pcorr / (fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf);
+    // (the very expression of the branch-free step above: which of the two steps a FIELD/FOREST zone runs depends on the
+    // other 31 zones of its warp, i.e. on where its element sits — the results must not)
+    else pc = pc * (pcorr * __drcp_rn(fracrain * inv_rfcf + (1.0 - fracrain) * inv_sfcf));
     // ref: hland_model.py:299-309 Calc_TF_Ic_V1
     double tf;
     if (icept) {

@@ -47,6 +47,18 @@ def main() -> None:
                                       doy=doy, ext=np.zeros((0, win * nw))), eng, window=win)
             same = np.array_equal(full.numpy(), ref["node_rows"])
             sizes = [len(x.elements) for x in shards]
+            if not same:
+                got, want = full.numpy(), ref["node_rows"]
+                bad = np.argwhere(got != want)
+                node_rank = np.zeros(river.n_node, int)
+                for x in shards:
+                    node_rank[x.nodes] = x.rank
+                nodes_bad = np.unique(bad[:, 0])
+                print(f"MULTI_GPU_DIFF {len(bad)} cells, {len(nodes_bad)} nodes on ranks "
+                      f"{np.bincount(node_rank[nodes_bad], minlength=world).tolist()}, first step {bad[:, 1].min()}, "
+                      f"windows {np.unique(bad[:, 1] // win).tolist()}, max abs diff {np.abs(got - want).max():.3e}, "
+                      f"example node {bad[0, 0]} step {bad[0, 1]}: {got[bad[0, 0], bad[0, 1]]!r} vs {want[bad[0, 0], bad[0, 1]]!r}",
+                      flush=True)
             print(f"MULTI_GPU_PARITY world={world} shard_elements={sizes} stages={[x.stage for x in shards]} "
                   f"bit_identical={same}", flush=True)
             if not same:

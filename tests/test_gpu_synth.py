@@ -553,3 +553,31 @@ def test_sixty_four_parameter_sets_in_one_run_equal_sequential_oracle_runs():
     assert_close(got_nse, ref_nse, "NSE of 64 parameter sets")
     assert_close(got_kge, ref_kge, "KGE of 64 parameter sets")
     assert np.ptp(ref_nse[:, 0]) > 1e-3            # the sets really differ
+
+
+def test_results_do_not_depend_on_where_an_element_sits():
+    """The fast path groups 32 consecutive elements into warps and lets warp-wide votes pick between equivalent code paths
+    (branch-free or general zone step, dry shortcuts, unswitched RecStep loop).  Shuffling the elements — what sharding a
+    basin over several GPUs does — must therefore not change a single bit of any element's outflow or state."""
+    from hydpy_b200.abi import RiverBundle
+    from hydpy_b200.shard import subset_land
+
+    ne, nt = 2100, 96
+    land, states = synth.make_land(ne, "1h", variants=True, seed=21)
+    forcing, doy = synth.make_forcing(nt, "1h")
+    perm = np.random.default_rng(4).permutation(ne)
+    pland, pstates = subset_land(land, states, perm, np.full(ne, -1, np.int32))
+    out = []
+    with Engine(0) as eng:
+        for ld, st in ((land, states), (pland, pstates)):
+            eng.set_land(ld)
+            eng.set_land_states(st)
+            eng.set_river(RiverBundle.empty(0))
+            eng.set_forcing(forcing, doy)
+            eng.run(land=True, river=False)
+            out.append((eng.get_land_outflow(), eng.get_land_states()))
+    (q0, s0), (q1, s1) = out
+    assert np.array_equal(q0[perm], q1)
+    assert np.array_equal(s0.uz[perm], s1.uz) and np.array_equal(s0.lz[perm], s1.lz)
+    zone_of = np.concatenate([np.arange(land.zone_ptr[e], land.zone_ptr[e + 1]) for e in perm])
+    assert np.array_equal(s0.sm[zone_of], s1.sm) and np.array_equal(s0.ic[zone_of], s1.ic)
