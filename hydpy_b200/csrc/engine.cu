@@ -30,6 +30,8 @@ using namespace hb;
 #define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
 #define HB_MAX_SLABS 8
+// zone/snow series the fast path of hland_96 stages in its own layout (first block + the evap submodels' block)
+#define HB_S_STAGED(s) ((s) < HB_S_FIRST_ELEM || ((s) >= HB_S_FIRST_ZONE3 && (s) < HB_S_SC))
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
@@ -219,7 +221,7 @@ struct hb_engine {
   DBuf<int32_t> d_coupled_list, d_general_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
   DBuf<unsigned long long> d_counters;   // HB_CNT_*: what the fast-path kernels executed since the last hb_get_timing
-  DBuf<double> d_series_stage[HB_S_FIRST_ELEM];   // chunk-local staging of the zone/snow series (fast path)
+  DBuf<double> d_series_stage[HB_S_COUNT];   // chunk-local staging of the zone/snow series (fast path)
   DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
   DBuf<int64_t> d_zone_cell0, d_snow_cell0;       // [E_pad+1] first ABI cell of every element
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
@@ -241,7 +243,7 @@ struct hb_engine {
   std::vector<int64_t> zone_ptr, snow_ptr, uh_ptr;
   std::vector<int32_t> h_nz, h_nc, h_nu, outlet_node;
   DBuf<int32_t> d_nz, d_nc, d_nu, d_recstep, d_einfo, d_fcol, d_zinfo, d_zorder, d_sred_from, d_sred_to;
-  DBuf<int64_t> d_zone0, d_snow0, d_sred_ptr;
+  DBuf<int64_t> d_zone0, d_snow0, d_uh0, d_sred_ptr;
   DBuf<double> d_kz, d_ke, d_sfdist, d_uh, d_sred_adjust;
   DBuf<double> d_ic, d_sm, d_sp, d_wc, d_uz, d_lz, d_quh, d_scr_a, d_scr_b, d_scr_sred;
   bool series_on[HB_S_COUNT] = {};
@@ -720,7 +722,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   }
   const bool host_fold = M == 1;     // (members: folded on the device, the big arrays never exist on the host)
   std::vector<int32_t> zinfo((size_t)zmax * ep, 0), zorder((size_t)zmax * ep, 0);
-  std::vector<int64_t> zone0(ep, 0), snow0(ep, 0), sred_ptr(ep + 1, 0);
+  std::vector<int64_t> zone0(ep, 0), snow0(ep, 0), uh0(ep, 0), sred_ptr(ep + 1, 0);
   std::vector<double> kz(host_fold ? (size_t)zmax * KZ_COUNT * ep : 0, 0.0), ke(host_fold ? (size_t)KE_COUNT * ep : 0, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
@@ -739,6 +741,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
     fcol[e] = d->forcing_col[eb];
     zone0[e] = h->zone_ptr[e];
     snow0[e] = h->snow_ptr[e];
+    uh0[e] = h->uh_ptr[e];
     sred_ptr[e] = d->sred_ptr[eb];
     double ev[HB_EP_COUNT];
     for (int p = 0; p < HB_EP_COUNT; ++p) ev[p] = mods.eval(p, d->epar[(int64_t)p * neb + eb], m, eb);
@@ -829,7 +832,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   if ((rc = upload(h, h->d_nz, nz)) || (rc = upload(h, h->d_nc, nc)) || (rc = upload(h, h->d_nu, nu)) ||
       (rc = upload(h, h->d_recstep, recstep)) || (rc = upload(h, h->d_einfo, einfo)) ||
       (rc = upload(h, h->d_fcol, fcol)) || (rc = upload(h, h->d_zinfo, zinfo)) || (rc = upload(h, h->d_zorder, zorder)) ||
-      (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) ||
+      (rc = upload(h, h->d_zone0, zone0)) || (rc = upload(h, h->d_snow0, snow0)) || (rc = upload(h, h->d_uh0, uh0)) ||
       (rc = upload(h, h->d_sred_ptr, sred_ptr)) ||
       (rc = upload(h, h->d_sfdist, sfdist)) || (rc = upload(h, h->d_uh, uh)) ||
       (rc = upload(h, h->d_coupled_list, coupled_list)))
@@ -1729,10 +1732,10 @@ static int run_land(hb_engine* h) {
   for (int s = 0; s < HB_S_COUNT; ++s) {
     if (!h->series_on[s]) continue;
     const int level = HB_S_LEVEL(s);
-    const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : h->n_elem;
+    const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : level == 2 ? h->n_elem : h->n_uh;
     HB_CUDA(h, h->d_series[s].reserve((size_t)nt * width));
     // sequences a model does not own read NaN in the cells of its elements
-    const bool partial = s >= HB_S_FIRST_ZONE2 ||
+    const bool partial = (s >= HB_S_FIRST_ZONE2 && s < HB_S_FIRST_ZONE3) || s == HB_S_SC ||
                          (h->any_sibling && (s == HB_S_CONTRIAREA || s == HB_S_INUZ || s == HB_S_PERC || s == HB_S_Q0 ||
                                              s == HB_S_Q1 || s == HB_S_UZ || s == HB_S_LZ));
     if (partial) HB_CUDA(h, cudaMemsetAsync(h->d_series[s].p, 0xFF, (size_t)nt * width * sizeof(double), h->stream));
@@ -1746,13 +1749,13 @@ static int run_land(hb_engine* h) {
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
     v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
-    v.n_zone = h->n_zone; v.n_snow = h->n_snow;
+    v.n_zone = h->n_zone; v.n_snow = h->n_snow; v.n_uh = h->n_uh; v.uh0 = h->d_uh0.p;
     v.counters = h->d_counters.p;
     v.nash_stage = h->any_nash ? 1 : 0;
     const size_t esmem = h->any_nash ? (size_t)HB_NASH_STAGE * 64 * sizeof(double) : 0;
     v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
     int n_staged = 0;
-    for (int s = 0; s < HB_S_FIRST_ELEM; ++s) n_staged += h->series_on[s] ? 1 : 0;
+    for (int s = 0; s < HB_S_COUNT; ++s) n_staged += (HB_S_STAGED(s) && h->series_on[s]) ? 1 : 0;
     // time chunks bound the two term buffers (3 GB each at most)
     const int64_t per_step = (int64_t)h->zmax * ep;
     // scratch per simulated step: two term buffers + one staging buffer per recorded zone/snow series.  Budget: 6 GB, or
@@ -1781,7 +1784,7 @@ static int run_land(hb_engine* h) {
     for (int s = 0; s < HB_S_COUNT; ++s) {
       v.series[s] = nullptr;
       if (!h->series_on[s]) continue;
-      if (s < HB_S_FIRST_ELEM) {
+      if (HB_S_STAGED(s)) {
         HB_CUDA(h, h->d_series_stage[s].reserve((size_t)chunk * per_step));
         v.series[s] = h->d_series_stage[s].p;
       } else v.series[s] = h->d_series[s].p;
@@ -1842,9 +1845,9 @@ static int run_land(hb_engine* h) {
         if (n_staged) {   // (one slab)
           dim3 sg((unsigned)((h->n_elem + 31) / 32), (unsigned)(v.nt < 64 ? v.nt : 64));
           const size_t sm_bytes = (size_t)h->zmax * 33 * sizeof(double);
-          for (int s = 0; s < HB_S_FIRST_ELEM; ++s) {
-            if (!h->series_on[s]) continue;
-            const bool snow = s >= HB_S_FIRST_SNOW;
+          for (int s = 0; s < HB_S_COUNT; ++s) {
+            if (!HB_S_STAGED(s) || !h->series_on[s]) continue;
+            const bool snow = HB_S_LEVEL(s) == 1;
             series_scatter_kernel<<<sg, 256, sm_bytes, st>>>(
                 h->d_series_stage[s].p, h->d_series[s].p, snow ? h->d_snow_cell0.p : h->d_zone_cell0.p,
                 snow ? h->d_snow_slot.p : h->d_zone_slot.p, h->n_elem, ep, h->zmax, snow ? h->n_snow : h->n_zone, (int)v.nt, c0);
@@ -1900,7 +1903,7 @@ static int run_land(hb_engine* h) {
     d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
     d.n_list = n_general; d.elist = n_general == h->n_elem ? nullptr : h->d_general_list.p;
     d.nz = h->d_nz.p; d.nc = h->d_nc.p; d.nu = h->d_nu.p; d.recstep = h->d_recstep.p; d.einfo = h->d_einfo.p;
-    d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p;
+    d.fcol = h->d_fcol.p; d.zinfo = h->d_zinfo.p; d.zone0 = h->d_zone0.p; d.snow0 = h->d_snow0.p; d.uh0 = h->d_uh0.p; d.n_uh = h->n_uh;
     d.kz = h->d_kz.p; d.ke = h->d_ke.p; d.sfdist = h->d_sfdist.p; d.uh = h->d_uh.p;
     d.sred_ptr = h->d_sred_ptr.p; d.sred_from = h->d_sred_from.p; d.sred_to = h->d_sred_to.p;
     d.sred_adjust = h->d_sred_adjust.p; d.zorder = h->d_zorder.p;
@@ -2468,7 +2471,7 @@ int hb_get_series(hb_engine* h, int series, double* out) {
              "hb_get_series: series %d was not selected before hb_run", series);
   HB_CUDA(h, cudaSetDevice(h->device));
   const int level = HB_S_LEVEL(series);
-  const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : h->n_elem;
+  const int64_t width = level == 0 ? h->n_zone : level == 1 ? h->n_snow : level == 2 ? h->n_elem : h->n_uh;
   return download(h, out, h->d_series[series].p, (size_t)h->nt * width);
 }
 

@@ -99,7 +99,8 @@ enum ke {
 #define HB_ZI_FLAGS(i) ((i) >> 8)
 
 struct LandDev {
-  int64_t n_elem, e_pad, n_zone, n_snow;
+  int64_t n_elem, e_pad, n_zone, n_snow, n_uh;
+  const int64_t* uh0;      // [E_pad] first storage / ordinate of the element in ABI order (series HB_S_SC)
   int32_t zmax, cmax, umax;
   int64_t n_list;          // number of elements this launch works on
   const int32_t* elist;    // [n_list] their indices (NULL: elements 0..n_list-1)
@@ -290,6 +291,13 @@ __device__ __forceinline__ double rconc_outflow(const double* __restrict__ uh, d
   const double outrc = ldg(uh + e) * inrc + quh[e];
   for (int j = 1; j < nu; ++j) quh[(int64_t)(j - 1) * ep + e] = ldg(uh + (int64_t)j * ep + e) * inrc + quh[(int64_t)j * ep + e];
   return outrc;
+}
+
+// rconc_nash states.sc after the step (ref: hydpy/models/rconc/rconc_model.py:179-197; save_data keeps the new state)
+__device__ __forceinline__ void record_sc(double* series, int64_t t, int64_t n_uh, int64_t uh0, const double* quh, int64_t ep,
+                                          int64_t e, int nu, int nash_steps) {
+  if (!series || nash_steps == 0) return;
+  for (int j = 0; j < nu; ++j) series[t * n_uh + uh0 + j] = quh[(int64_t)j * ep + e];
 }
 
 template <bool SERIES, int MODEL>
@@ -582,10 +590,17 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
         pet = ret * ldg(kzk + KZ_ALT_F * ep);
         if (pet <= 0.0) pet = 0.0;
         else pet *= hb_exp(ldg(kzk + KZ_NEG_PF * ep) * pc, T);
+        SERZ(HB_S_REFERENCEEVAPOTRANSPIRATION, k, ret); SERZ(HB_S_POTENTIALEVAPOTRANSPIRATION, k, pet);
       }
       // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1 (f = 1: no snow evaporation, hland_model.py:4425-4430)
       double aet_ie = 0.0;
       if (zf & HB_ZF_INTERCEPTION) aet_ie = HB_PYMIN(pet, ic);
+      if (SERIES) {   // sequences of the evap submodels: what their save_data keeps at the end of the step
+        SERZ(HB_S_INTERCEPTEDWATER, k, ic); SERZ(HB_S_INTERCEPTIONEVAPORATION, k, aet_ie);
+        SERZ(HB_S_SNOWCOVER, k, ncover / dnc);
+        SERZ(HB_S_WATEREVAPORATION, k, ((zf & HB_ZF_WATER) && tc > ldg(kzk + KZ_TTI * ep)) ? pet : 0.0);
+      }
+      double aet_set = 0.0, aet_sw = 0.0;
       // ref: hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
       double ei = 0.0;
       if (zt == HB_FIELD || zt == HB_FOREST || zt == HB_SEALED) { ei = HB_PYMIN(aet_ie, ic); ic -= ei; }
@@ -612,6 +627,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
           cf = HB_PYMIN(cf, b);
         }
         sm += cf;
+        aet_sw = sm;
         // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1
         double set = 0.0;
         if (zf & HB_ZF_SOIL) {
@@ -633,6 +649,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
           // ref: evap_model.py:7060-7069 Update_SoilEvapotranspiration_V2
           set *= 1.0 - ncover / dnc;
         }
+        aet_set = set;
         // ref: hland_model.py:2002-2018 Calc_EA_SM_AETModel_V1
         ea = HB_PYMIN(set, sm);
         sm -= ea;
@@ -658,6 +675,21 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
       }
       SERZ(HB_S_R, k, r); SERZ(HB_S_CF, k, cf); SERZ(HB_S_EA, k, ea); SERZ(HB_S_SM, k, sm);
       SERZ(HB_S_EL, k, (zt == HB_ILAKE) ? d.scr_b[ik] : 0.0);
+      if (SERIES) {
+        if (!(zt == HB_FIELD || zt == HB_FOREST) && (zf & HB_ZF_SOIL)) {
+          // (a zone without soil whose Soil flag is set: the submodel sees an empty soil; evap_model.py:6657-6672 …)
+          double set = pet;
+          const double thresh = ldg(kzk + KZ_THRESH * ep);
+          if (set > 0.0 && 0.0 < thresh) set *= 0.0 / thresh;
+          const double rr = ldg(kzk + KZ_EXCESSRED * ep);
+          const double petc = rr * pet + (1.0 - rr) * (pet + pet) / 2.0;
+          const double excess = set + aet_ie - petc;
+          if ((petc >= 0.0) && (excess > 0.0)) set -= rr * excess;
+          else if ((petc < 0.0) && (excess < 0.0)) set -= rr * excess;
+          aet_set = set * (1.0 - ncover / dnc);
+        }
+        SERZ(HB_S_SOILWATER, k, aet_sw); SERZ(HB_S_SOILEVAPOTRANSPIRATION, k, aet_set);
+      }
       if (MODEL == HB_MODEL_HLAND_96P) {
         // ---- hland_96p: upper zone layer and first-order groundwater storage of the zone (models/hland_96p.py) ----
         double suz = 0.0, sg1 = 0.0, dp = 0.0, rs = 0.0, ri = 0.0, gr1 = 0.0, rg1 = 0.0;
@@ -771,6 +803,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
       }
       // ref: hland_model.py:4109-4116 Calc_OutRC_V1, 4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
       const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+      if (SERIES) record_sc(d.series[HB_S_SC], t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
       const double qt = qfactor * outrc;
       d.qt[t * ep + e] = qt;
       SERE(HB_S_GR2, gr2); SERE(HB_S_GR3, gr3); SERE(HB_S_RG2, rg2); SERE(HB_S_RG3, rg3); SERE(HB_S_SG2, sg2);
@@ -780,6 +813,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
     if (MODEL == HB_MODEL_HLAND_96C) {
       // ref: hland_model.py:4109-4116 Calc_OutRC_V1
       const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc_c);
+      if (SERIES) record_sc(d.series[HB_S_SC], t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
       // ref: hland_model.py:3172-3181 Calc_LZ_V2 (scr_a: pc of ILAKE zones, qvs2 of FIELD/FOREST/GLACIER zones)
       for (int k = 0; k < nz; ++k) {
         const int64_t ik = (int64_t)k * ep + e;
@@ -869,6 +903,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
       }
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
     const double outrc = rconc_outflow(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc);
+    if (SERIES) record_sc(d.series[HB_S_SC], t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
     d.qt[t * ep + e] = qt;

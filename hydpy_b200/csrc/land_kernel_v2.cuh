@@ -69,7 +69,8 @@ struct LandV2Dev {
   // optional series (SERIES kernels).  Element level: ABI layout [nt_window][n_elem], written in place.  Zone and
   // snow level: the zone kernel writes a chunk-local staging buffer in ITS layout [nt][zmax][E_pad] (coalesced);
   // series_scatter_kernel then moves the chunk into the ABI layout [nt_window][n_zone] with coalesced stores.
-  int64_t n_zone, n_snow;
+  int64_t n_zone, n_snow, n_uh;
+  const int64_t* uh0;      // [E_pad] first storage of the element in ABI order (series HB_S_SC)
   double* series[HB_S_COUNT];
   // fused kernel for elements with capillary flux (land_kernel_coupled.cuh)
   const int32_t* clist;    // their indices
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
       const double a = pc - (icmax - ic);
       const double tf = HB_PYMAX(a, 0.0);
       ic += pc - tf;
+      SERZ(HB_S_INTERCEPTEDWATER, ic);   // evap_aet_hbv96 factors.InterceptedWater: what the submodel is shown
       // ref: hland_model.py:484-499 Calc_SP_WC_V1, 1050-1062 Calc_CFAct_V1
       wc += sf * (tf * fracrain);
       sp += sf * (tf * (1.0 - fracrain));
@@ -357,10 +359,16 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         pet = ret * alt_f;
         const double damp = hb_exp(neg_pf * pc, T);
         pet = (pet <= 0.0) ? 0.0 : pet * damp;
+        SERZ(HB_S_REFERENCEEVAPOTRANSPIRATION, ret); SERZ(HB_S_POTENTIALEVAPOTRANSPIRATION, pet);
       }
       // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1; hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
       double aet_ie = HB_PYMIN(pet, ic);
       aet_ie = f_icept ? aet_ie : 0.0;
+      if (SERIES) {
+        SERZ(HB_S_INTERCEPTIONEVAPORATION, aet_ie); SERZ(HB_S_SNOWCOVER, ncover);
+        // ref: evap_model.py:5673-5681 Calc_WaterEvaporation_V1 (all zones, whatever their type)
+        SERZ(HB_S_WATEREVAPORATION, ((zf & HB_ZF_WATER) && tc > KZX(KZ_TTI)) ? pet : 0.0);
+      }
       {
         const double ei = HB_PYMIN(aet_ie, ic);
         ic -= ei;
@@ -390,6 +398,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         cf = HB_PYMIN(cf, b);
         sm += cf;
       }
+      SERZ(HB_S_SOILWATER, sm);          // evap_aet_hbv96 factors.SoilWater
       // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1 (6657-6672, 7001-7018, 7060-7069)
       double set = pet;
       {
@@ -405,6 +414,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         set *= 1.0 - ncover;
         set = f_soil ? set : 0.0;
       }
+      SERZ(HB_S_SOILEVAPOTRANSPIRATION, set);
       // ref: hland_model.py:2002-2018 Calc_EA_SM_AETModel_V1
       const double ea = HB_PYMIN(set, sm);
       sm -= ea;
@@ -468,6 +478,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
       tf = HB_PYMAX(a, 0.0);
       ic += pc - tf;
     } else { tf = pc; ic = 0.0; }
+    SERZ(HB_S_INTERCEPTEDWATER, ic);
     double in_ = tf, ncover = 0.0;
     bool bare = true;
     double s_cfact = 0.0, s_gact = 0.0, s_melt = 0.0, s_refr = 0.0, s_glmelt = 0.0;   // recorded only
@@ -525,10 +536,15 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
       pet = ret * alt_f;
       if (pet <= 0.0) pet = 0.0;
       else pet *= hb_exp(neg_pf * pc, T);
+      SERZ(HB_S_REFERENCEEVAPOTRANSPIRATION, ret); SERZ(HB_S_POTENTIALEVAPOTRANSPIRATION, pet);
     }
     // ref: evap_model.py:6068-6086 Calc_InterceptionEvaporation_V1; hland_model.py:383-396 Calc_EI_Ic_AETModel_V1
     double aet_ie = 0.0;
     if (zf & HB_ZF_INTERCEPTION) aet_ie = HB_PYMIN(pet, ic);
+    if (SERIES) {
+      SERZ(HB_S_INTERCEPTIONEVAPORATION, aet_ie); SERZ(HB_S_SNOWCOVER, ncover);
+      SERZ(HB_S_WATEREVAPORATION, ((zf & HB_ZF_WATER) && tc > KZX(KZ_TTI)) ? pet : 0.0);
+    }
     double s_ei = 0.0;
     if (icept) { s_ei = HB_PYMIN(aet_ie, ic); ic -= s_ei; }
     else ic = 0.0;
@@ -552,6 +568,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         cf = HB_PYMIN(cf, b);
       }
       sm += cf;
+      SERZ(HB_S_SOILWATER, sm);
       // ref: evap_model.py:7630-7658 Determine_SoilEvapotranspiration_V1 (6657-6672, 7001-7018, 7060-7069)
       double set = 0.0;
       if (zf & HB_ZF_SOIL) {
@@ -566,6 +583,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         else if ((petc < 0.0) && (excess < 0.0)) set -= excessred * excess;
         set *= 1.0 - ncover;
       }
+      SERZ(HB_S_SOILEVAPOTRANSPIRATION, set);
       // ref: hland_model.py:2002-2018 Calc_EA_SM_AETModel_V1
       const double ea = HB_PYMIN(set, sm);
       sm -= ea;
@@ -588,6 +606,21 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         else { ta = el; tb = w_b * pc; }   // hland_96p: Calc_EL_SG2_SG3 / Calc_GR2_GR3 terms; hland_96c: Calc_EL_LZ / Calc_LZ_V2
       } else ta = w_a * (in_ - 0.0);  // GLACIER: InUZ term; SEALED: InRC term (r = in_, ref: hland_model.py:1528-1535)
       SERZ(HB_S_R, in_); SERZ(HB_S_CF, 0.0); SERZ(HB_S_EA, 0.0); SERZ(HB_S_SM, 0.0); SERZ(HB_S_EL, el);
+      // (a zone without soil: the submodel sees an empty soil; its Soil flag may still be set)
+      if (SERIES) {
+        SERZ(HB_S_SOILWATER, 0.0);
+        double set = 0.0;
+        if (zf & HB_ZF_SOIL) {   // ref: evap_model.py:6657-6672, 7001-7018, 7060-7069 with soilwater = 0
+          set = pet;
+          if (set > 0.0) set = (0.0 < thresh) ? set * (0.0 * inv_thresh) : set;
+          const double petc = excessred * pet + (1.0 - excessred) * (pet + pet) / 2.0;
+          const double excess = set + aet_ie - petc;
+          if ((petc >= 0.0) && (excess > 0.0)) set -= excessred * excess;
+          else if ((petc < 0.0) && (excess < 0.0)) set -= excessred * excess;
+          set *= 1.0 - ncover;
+        }
+        SERZ(HB_S_SOILEVAPOTRANSPIRATION, set);
+      }
     }
     if (MODEL != HB_MODEL_HLAND_96) {
       if (upper) {
@@ -902,6 +935,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
     const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
+    if (SERIES) record_sc(d.series[HB_S_SC], d.t_out + t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
     d.qt[(d.t_out + t) * ep + e] = qt;

@@ -494,7 +494,7 @@ class Engine:
 
     def get_series(self, name: str) -> np.ndarray:
         land = self._need_land()
-        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_elem
+        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_uh if name in layout.SERIES_UH else land.n_elem
         out = np.zeros((self.nt, width))
         self._check(self._lib.hb_get_series(self._h, layout.S[name], ptr(out, C.c_double)), "hb_get_series")
         return out

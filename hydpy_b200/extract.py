@@ -543,9 +543,72 @@ def extract(hp: Any, i0: int, i1: int) -> Problem:
 # ---------------------------------------------------------------------------------------------------------------------
 
 
+def _submodel(model: Any, path: str) -> Any:
+    sub = model
+    for part in path.split("."):
+        sub = getattr(sub, part, None)
+        if sub is None:
+            return None
+    return sub
+
+
+def _io_sequences(model: Any):
+    """(group name, sequence) of every IO sequence of a model (no submodels)."""
+    for group in ("inputs", "factors", "fluxes", "states", "inlets", "outlets", "receivers", "senders", "observers"):
+        for seq in getattr(model.sequences, group, None) or ():
+            yield group, seq
+
+
+#: the models below a land element: path from the main model ("" = the main model itself)
+_LAND_PATHS = ("", "aetmodel", "aetmodel.petmodel", "rconcmodel")
+
+
+def check_deliverable(problem: Problem) -> None:
+    """Everything the reference's `save_data` / `load_data` would serve during the run must be something the engine can
+    serve (ref: hydpy/cythons/modelutils.py:1080-1167): refuse just-in-time NetCDF reading and writing (`diskflag`) and
+    series kept in RAM (`ramflag`, set by `prepare_allseries()` down to every submodel) that the engine does not compute —
+    instead of leaving them stale (no silent fallback)."""
+    known = {(path, group, name) for (path, group, name) in layout.SUBMODEL_SERIES} | set(layout.SUBMODEL_DERIVED)
+    for element in problem.land_elements:
+        for path in _LAND_PATHS:
+            sub = _submodel(element.model, path) if path else element.model
+            if sub is None:
+                continue
+            for group, seq in _io_sequences(sub):
+                if getattr(seq, "diskflag_reading", False) or getattr(seq, "diskflag_writing", False):
+                    raise UnsupportedModelError(
+                        f"element `{element.name}`: sequence `{seq.name}` of `{_modelname(sub)}` reads or writes its "
+                        f"time series just in time (NetCDF); the B200 engine only serves series kept in RAM")
+                if not getattr(seq, "ramflag", False) or group in ("inputs", "outlets", "inlets"):
+                    continue
+                if path == "":
+                    if seq.name in layout.SERIES:
+                        continue
+                elif (path, group, seq.name) in known:
+                    continue
+                raise UnsupportedModelError(
+                    f"element `{element.name}`: the series of `{group}.{seq.name}` of `{_modelname(sub)}` is requested "
+                    f"(ramflag), but the B200 engine does not deliver it")
+    for element in problem.river_elements:
+        for group, seq in _io_sequences(element.model):
+            if getattr(seq, "diskflag_reading", False) or getattr(seq, "diskflag_writing", False):
+                raise UnsupportedModelError(
+                    f"element `{element.name}`: sequence `{seq.name}` reads or writes its time series just in time "
+                    f"(NetCDF); the B200 engine only serves series kept in RAM")
+    for node in problem.nodes:
+        for name in ("sim", "obs"):
+            seq = getattr(node.sequences, name, None)
+            if seq is not None and (getattr(seq, "diskflag_reading", False) or getattr(seq, "diskflag_writing", False)):
+                raise UnsupportedModelError(
+                    f"node `{node.name}`: sequence `{name}` reads or writes its time series just in time (NetCDF); the "
+                    f"B200 engine only serves series kept in RAM")
+
+
 def requested_series(problem: Problem) -> list[str]:
-    """Names of the land series at least one element keeps in RAM (`ramflag`)."""
-    wanted = []
+    """Names of the land series at least one element keeps in RAM (`ramflag`) — its own sequences and those of its
+    evap / rconc submodels (`layout.SUBMODEL_SERIES`: each is a copy of an engine series)."""
+    check_deliverable(problem)
+    wanted: list[str] = []
     for name in layout.SERIES:
         group = layout.SERIES_GROUP[name]
         for element in problem.land_elements:
@@ -553,7 +616,18 @@ def requested_series(problem: Problem) -> list[str]:
             if seq is not None and seq.ramflag:
                 wanted.append(name)
                 break
-    return wanted
+    extra = dict(layout.SUBMODEL_SERIES)
+    extra[("aetmodel.petmodel", "fluxes", "meanpotentialevapotranspiration")] = "potentialevapotranspiration"
+    for (path, group, seqname), name in extra.items():
+        if name in wanted:
+            continue
+        for element in problem.land_elements:
+            sub = _submodel(element.model, path)
+            seq = getattr(getattr(sub.sequences, group, None), seqname, None) if sub is not None else None
+            if seq is not None and getattr(seq, "ramflag", False):
+                wanted.append(name)
+                break
+    return [n for n in layout.SERIES if n in wanted]
 
 
 def check_reach_series(problem: Problem) -> None:
@@ -664,6 +738,43 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
                 seq.series[i0:i1] = data[:, e]
                 if last >= 0 and group != "states":
                     seq.value = float(data[last, e])
+        # sequences of the submodels: copies of engine series (`layout.SUBMODEL_SERIES`) and three derived ones
+        for (path, group, seqname), name in layout.SUBMODEL_SERIES.items():
+            sub = _submodel(model, path)
+            seq = getattr(getattr(sub.sequences, group, None), seqname, None) if sub is not None else None
+            if seq is None or name not in series:
+                continue
+            data = series[name]
+            if name in layout.SERIES_UH:       # rconc_nash states.sc: the state itself is set from `states.quh` above
+                if getattr(seq, "ramflag", False) and int(land.rconc[e]) == layout.RCONC_NASH:
+                    seq.series[i0:i1] = data[:, u0:u1]
+            elif name in layout.SERIES_ZONE:
+                if getattr(seq, "ramflag", False):
+                    seq.series[i0:i1] = data[:, z0:z1]
+                if last >= 0:
+                    seq.value = data[last, z0:z1]
+            else:
+                if getattr(seq, "ramflag", False):
+                    seq.series[i0:i1] = data[:, e]
+                if last >= 0:
+                    seq.value = float(data[last, e])
+        for (path, group, seqname), kind in layout.SUBMODEL_DERIVED.items():
+            sub = _submodel(model, path)
+            seq = getattr(getattr(sub.sequences, group, None), seqname, None) if sub is not None else None
+            if seq is None or not getattr(seq, "ramflag", False):
+                continue
+            if kind == "zero":
+                seq.series[i0:i1] = 0.0
+            elif kind == "input_t":
+                seq.series[i0:i1] = problem.forcing[1, :, col]
+            elif kind == "meanpet" and "potentialevapotranspiration" in series:
+                # ref: evap_model.py:5489-5498 — Σ hruareafraction[k] * potentialevapotranspiration[k], k = 0 … Z-1
+                frac = land.zp("hruareafraction")[z0:z1]
+                pet = series["potentialevapotranspiration"][:, z0:z1]
+                acc = np.zeros(pet.shape[0])
+                for k in range(nz):
+                    acc = acc + frac[k] * pet[:, k]
+                seq.series[i0:i1] = acc
     river = problem.river
     for r, element in enumerate(problem.river_elements):
         model = element.model

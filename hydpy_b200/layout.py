@@ -58,8 +58,13 @@ SERIES_96 = SERIES_ZONE1 + SERIES_SNOW + SERIES_ELEM1
 # sibling models (second block): hland_96p zone/element sequences, hland_96c zone sequences
 SERIES_ZONE2 = ("dp", "rs", "ri", "gr1", "rg1", "suz", "sg1", "qab1", "qvs1", "qab2", "qvs2", "bw1", "bw2")
 SERIES_ELEM2 = ("gr2", "gr3", "rg2", "rg3", "sg2", "sg3")
-SERIES = SERIES_96 + SERIES_ZONE2 + SERIES_ELEM2
-SERIES_ZONE = SERIES_ZONE1 + SERIES_ZONE2
+# evap submodels (third block), zone level
+SERIES_ZONE3 = ("referenceevapotranspiration", "potentialevapotranspiration", "interceptionevaporation",
+                "soilevapotranspiration", "waterevaporation", "interceptedwater", "soilwater", "snowcover")
+#: storage level [nt, n_uh]: rconc_nash states.sc
+SERIES_UH = ("sc",)
+SERIES = SERIES_96 + SERIES_ZONE2 + SERIES_ELEM2 + SERIES_ZONE3 + SERIES_UH
+SERIES_ZONE = SERIES_ZONE1 + SERIES_ZONE2 + SERIES_ZONE3
 SERIES_ELEM = SERIES_ELEM1 + SERIES_ELEM2
 S = {name: i for i, name in enumerate(SERIES)}
 #: which application models own a sequence (cells of other elements stay NaN)
@@ -73,8 +78,39 @@ SERIES_GROUP = {
     **{n: "factors" for n in ("tc", "fracrain", "cfact", "gact", "swe", "contriarea")},
     **{n: "states" for n in ("ic", "sm", "sp", "wc", "uz", "lz", "suz", "sg1", "sg2", "sg3", "bw1", "bw2")},
 }
+SERIES_GROUP["sc"] = "states"          # (of the rconc_nash submodel)
 for _n in SERIES:
     SERIES_GROUP.setdefault(_n, "fluxes")
+
+#: sequences of the submodels of a land element → the engine series that holds their values
+#: (`Element.prepare_allseries()` keeps them in RAM too; ref: hydpy/cythons/modelutils.py:1127-1167 `save_data` of every
+#: submodel).  Key: (path from the main model, sequence group, sequence name).
+SUBMODEL_SERIES = {
+    ("aetmodel.petmodel", "fluxes", "referenceevapotranspiration"): "referenceevapotranspiration",
+    ("aetmodel.petmodel", "fluxes", "potentialevapotranspiration"): "potentialevapotranspiration",
+    ("aetmodel.petmodel", "fluxes", "precipitation"): "pc",
+    ("aetmodel", "fluxes", "potentialinterceptionevaporation"): "potentialevapotranspiration",
+    ("aetmodel", "fluxes", "potentialsoilevapotranspiration"): "potentialevapotranspiration",
+    ("aetmodel", "fluxes", "potentialwaterevaporation"): "potentialevapotranspiration",
+    ("aetmodel", "fluxes", "interceptionevaporation"): "interceptionevaporation",
+    ("aetmodel", "fluxes", "soilevapotranspiration"): "soilevapotranspiration",
+    ("aetmodel", "fluxes", "waterevaporation"): "waterevaporation",
+    ("aetmodel", "factors", "airtemperature"): "tc",
+    ("aetmodel", "factors", "interceptedwater"): "interceptedwater",
+    ("aetmodel", "factors", "soilwater"): "soilwater",
+    ("aetmodel", "factors", "snowcover"): "snowcover",
+    ("rconcmodel", "fluxes", "inflow"): "inrc",
+    ("rconcmodel", "fluxes", "outflow"): "outrc",
+    ("rconcmodel", "states", "sc"): "sc",
+}
+#: … and the ones the host layer derives: snowycanopy = 0 (no snowy-canopy submodel, ref: evap_model.py:4259-4261),
+#: meanairtemperature = the input T (ref: hland_model.py:4267-4270), meanpotentialevapotranspiration = Σ hruareafraction ·
+#: potentialevapotranspiration in zone order (ref: evap_model.py:5489-5498)
+SUBMODEL_DERIVED = {
+    ("aetmodel", "factors", "snowycanopy"): "zero",
+    ("aetmodel.petmodel", "factors", "meanairtemperature"): "input_t",
+    ("aetmodel.petmodel", "fluxes", "meanpotentialevapotranspiration"): "meanpet",
+}
 
 NODE_NEWSIM, NODE_EXT, NODE_OBSNEWSIM = 0, 1, 2
 

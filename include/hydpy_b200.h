@@ -118,14 +118,25 @@ enum hb_series {
   HB_S_QAB1, HB_S_QVS1, HB_S_QAB2, HB_S_QVS2, HB_S_BW1, HB_S_BW2,
   /* sibling models, element level: hland_96p fluxes GR2, GR3, RG2, RG3 and states SG2, SG3 */
   HB_S_GR2, HB_S_GR3, HB_S_RG2, HB_S_RG3, HB_S_SG2, HB_S_SG3,
+  /* sequences of the evap submodels (every land model has them), zone level: evap_pet_hbv96 fluxes
+   * ReferenceEvapotranspiration, PotentialEvapotranspiration; evap_aet_hbv96 fluxes InterceptionEvaporation,
+   * SoilEvapotranspiration, WaterEvaporation and factors InterceptedWater, SoilWater, SnowCover
+   * (`hydpy/models/evap/evap_fluxes.py`, `evap_factors.py`).  The other submodel sequences are copies the host layer
+   * makes: AirTemperature = TC, Precipitation = PC, the three potential fluxes of evap_aet_hbv96 = PotentialEvapotranspiration,
+   * rconc Inflow/Outflow = InRC/OutRC. */
+  HB_S_REFERENCEEVAPOTRANSPIRATION, HB_S_POTENTIALEVAPOTRANSPIRATION, HB_S_INTERCEPTIONEVAPORATION,
+  HB_S_SOILEVAPOTRANSPIRATION, HB_S_WATEREVAPORATION, HB_S_INTERCEPTEDWATER, HB_S_SOILWATER, HB_S_SNOWCOVER,
+  /* storage level [nt][n_uh]: rconc_nash states.sc of every step (cells of rconc_uh elements keep NaN) */
+  HB_S_SC,
   HB_S_COUNT
 };
 #define HB_S_FIRST_SNOW HB_S_SWE
 #define HB_S_FIRST_ELEM HB_S_CONTRIAREA
 #define HB_S_FIRST_ZONE2 HB_S_DP    /* second block of zone-level series */
 #define HB_S_FIRST_ELEM2 HB_S_GR2   /* second block of element-level series */
-/* level of a series: 0 zone [nt][n_zone], 1 snow [nt][n_snow], 2 element [nt][n_elem] */
-#define HB_S_LEVEL(s) ((s) < HB_S_FIRST_SNOW ? 0 : (s) < HB_S_FIRST_ELEM ? 1 : (s) < HB_S_FIRST_ZONE2 ? 2 : (s) < HB_S_FIRST_ELEM2 ? 0 : 2)
+#define HB_S_FIRST_ZONE3 HB_S_REFERENCEEVAPOTRANSPIRATION   /* third block: zone-level series of the evap submodels */
+/* level of a series: 0 zone [nt][n_zone], 1 snow [nt][n_snow], 2 element [nt][n_elem], 3 storage [nt][n_uh] */
+#define HB_S_LEVEL(s) ((s) < HB_S_FIRST_SNOW ? 0 : (s) < HB_S_FIRST_ELEM ? 1 : (s) < HB_S_FIRST_ZONE2 ? 2 : (s) < HB_S_FIRST_ELEM2 ? 0 : (s) < HB_S_FIRST_ZONE3 ? 2 : (s) < HB_S_SC ? 0 : 3)
 
 /* ---- land description: all hland_96 / hland_96p / hland_96c elements (+ evap_aet_hbv96/evap_pet_hbv96, optional
  * rconc_uh / rconc_nash) --------------------------------------------------------------------------------------- *

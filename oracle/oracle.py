@@ -77,7 +77,7 @@ def land_run(land: LandBundle, states: LandStates, forcing: np.ndarray, doy: np.
     out: dict[str, np.ndarray] = {}
     arr = (C.POINTER(C.c_double) * len(layout.SERIES))()
     for name in series:
-        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_elem
+        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_uh if name in layout.SERIES_UH else land.n_elem
         out[name] = np.full((nt, width), np.nan)
         arr[layout.S[name]] = ptr(out[name], C.c_double)
     sp = arr if series else None

@@ -68,6 +68,17 @@ def snapshot(hp):
                 if group == "states":
                     out[f"{element.name}:states.{seq.name}:new"] = np.array(seq.new)
                     out[f"{element.name}:states.{seq.name}:old"] = np.array(seq.old)
+        # sequences of the submodels (`prepare_allseries()` keeps them in RAM as well; ref: modelutils.py:1127-1167)
+        for path in ("aetmodel", "aetmodel.petmodel", "rconcmodel"):
+            sub = element.model
+            for part in path.split("."):
+                sub = getattr(sub, part, None)
+            if sub is None:
+                continue
+            for group in ("factors", "fluxes", "states"):
+                for seq in getattr(sub.sequences, group, ()) or ():
+                    if getattr(seq, "ramflag", False):
+                        out[f"{element.name}:{path}.{group}.{seq.name}:series"] = np.array(seq.series)
         rwd = getattr(getattr(seqs, "factors", None), "referencewaterdepth", None)
         if rwd is not None:
             out[f"{element.name}:referencewaterdepth"] = np.array(rwd.value)
@@ -235,6 +246,10 @@ def main() -> None:
             for group in ("factors", "fluxes", "states"):
                 for seq in getattr(seqs, group):
                     seq.prepare_series(allocate_ram=True)
+            for sub in element.model.find_submodels(include_mainmodel=False).values():   # evap_aet/pet, rconc
+                for group in ("factors", "fluxes", "states"):
+                    for seq in getattr(sub.sequences, group, ()) or ():
+                        seq.prepare_series(allocate_ram=True)
         if "--inputnodes" in sys.argv:
             add_input_nodes(hp)
         # two consecutive simulation windows inside the initialisation period, as in hydpy/core/hydpytools.py:2804-2825
@@ -259,6 +274,11 @@ def main() -> None:
                 for seq in getattr(element.model.sequences, group, ()):
                     if getattr(seq, "ramflag", False):
                         seq.series[:] = np.nan
+            for sub in element.model.find_submodels(include_mainmodel=False).values():
+                for group in ("factors", "fluxes", "states"):
+                    for seq in getattr(sub.sequences, group, ()) or ():
+                        if getattr(seq, "ramflag", False):
+                            seq.series[:] = np.nan
             pet = getattr(getattr(element.model, "aetmodel", None), "petmodel", None)
             for seq in list(getattr(element.model.sequences, "inputs", ())) + list(pet.sequences.inputs if pet else ()):
                 if getattr(seq, "node2idx", None) and seq.ramflag:

@@ -55,7 +55,7 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
     out: dict[str, np.ndarray] = {}
     for name in layout.SERIES:
         group = layout.SERIES_GROUP[name]
-        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_elem
+        width = land.n_zone if name in layout.SERIES_ZONE else land.n_snow if name in layout.SERIES_SNOW else land.n_uh if name in layout.SERIES_UH else land.n_elem
         arr = np.full((nt, width), np.nan)
         have = False
         for e, element in enumerate(problem.land_elements):
@@ -72,6 +72,33 @@ def gather_expected(problem, hp) -> dict[str, np.ndarray]:
                 arr[:, e] = data
         if have:
             out["exp_" + name] = arr
+    # sequences of the evap submodels (third block of layout.SERIES): read from the submodel that owns them
+    for (path, group, seqname), name in layout.SUBMODEL_SERIES.items():
+        if name not in layout.SERIES_ZONE3 or seqname != name:
+            continue
+        arr = np.full((nt, land.n_zone), np.nan)
+        have = False
+        for e, element in enumerate(problem.land_elements):
+            sub = element.model
+            for part in path.split("."):
+                sub = getattr(sub, part, None)
+            seq = getattr(getattr(sub.sequences, group), seqname, None) if sub is not None else None
+            if seq is None or not seq.ramflag:
+                continue
+            have = True
+            arr[:, land.zone_ptr[e]:land.zone_ptr[e + 1]] = np.asarray(seq.series[i0:i1], dtype=np.float64)
+        if have:
+            out["exp_" + name] = arr
+    arr = np.full((nt, land.n_uh), np.nan)
+    have = False
+    for e, element in enumerate(problem.land_elements):
+        rc = getattr(element.model, "rconcmodel", None)
+        seq = getattr(getattr(rc.sequences, "states", None), "sc", None) if rc is not None else None
+        if seq is not None and seq.ramflag:
+            have = True
+            arr[:, land.uh_ptr[e]:land.uh_ptr[e + 1]] = np.asarray(seq.series[i0:i1], dtype=np.float64)
+    if have:
+        out["exp_sc"] = arr
     out["exp_node_rows"] = np.stack(
         [np.asarray(n.sequences.sim.series[i0:i1], dtype=np.float64) for n in problem.nodes]
     ) if problem.nodes else np.zeros((0, nt))

@@ -105,3 +105,47 @@ def test_elements_with_receiver_sender_or_observer_nodes_are_refused():
         hp = types.SimpleNamespace(nodes=[node], elements=[element(**{kind: (node,)})])
         with pytest.raises(UnsupportedModelError, match="receiver/sender/observer"):
             extract(hp, 0, 10)
+
+
+def test_just_in_time_netcdf_and_undeliverable_series_are_refused():
+    """`diskflag_reading` / `diskflag_writing` (just-in-time NetCDF, ref: hydpy/core/sequencetools.py:1876-1992) and series
+    in RAM the engine does not compute must raise instead of staying stale (no silent fallback)."""
+    import types
+
+    import pytest
+
+    from hydpy_b200.extract import Problem, UnsupportedModelError, check_deliverable
+
+    def seq(name, **flags):
+        return types.SimpleNamespace(name=name, ramflag=flags.get("ram", False),
+                                     diskflag_reading=flags.get("reading", False),
+                                     diskflag_writing=flags.get("writing", False))
+
+    def model(name, **groups):
+        return types.SimpleNamespace(name=name, sequences=types.SimpleNamespace(**groups))
+
+    def problem(land_model=None, river_model=None, node=None):
+        p = Problem.__new__(Problem)
+        p.land_elements = [types.SimpleNamespace(name="land_x", model=land_model)] if land_model else []
+        p.river_elements = [types.SimpleNamespace(name="stream_x", model=river_model)] if river_model else []
+        p.nodes = [node] if node else []
+        return p
+
+    ok = model("hland_96", fluxes=[seq("pc", ram=True)], states=[seq("sm", ram=True)])
+    ok.aetmodel = model("evap_aet_hbv96", fluxes=[seq("soilevapotranspiration", ram=True)], factors=[seq("snowycanopy", ram=True)])
+    ok.aetmodel.petmodel = model("evap_pet_hbv96", fluxes=[seq("meanpotentialevapotranspiration", ram=True)])
+    ok.rconcmodel = model("rconc_nash", states=[seq("sc", ram=True)], fluxes=[seq("inflow", ram=True)])
+    check_deliverable(problem(land_model=ok))
+
+    bad = model("hland_96", fluxes=[seq("pc", writing=True)])
+    with pytest.raises(UnsupportedModelError, match="just in time"):
+        check_deliverable(problem(land_model=bad))
+    bad = model("hland_96", fluxes=[])
+    bad.aetmodel = model("evap_aet_hbv96", fluxes=[seq("somethingnew", ram=True)])
+    with pytest.raises(UnsupportedModelError, match="does not deliver"):
+        check_deliverable(problem(land_model=bad))
+    with pytest.raises(UnsupportedModelError, match="just in time"):
+        check_deliverable(problem(river_model=model("musk_classic", fluxes=[seq("outflow", reading=True)])))
+    node = types.SimpleNamespace(name="n", sequences=types.SimpleNamespace(sim=seq("sim", writing=True), obs=seq("obs")))
+    with pytest.raises(UnsupportedModelError, match="node `n`"):
+        check_deliverable(problem(node=node))
