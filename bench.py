@@ -110,6 +110,17 @@ class Dist:
         self.pg.broadcast(t, src=src)
         return float(t[0])
 
+    def all_gather(self, values: list[float]) -> list[list[float]]:
+        """One row of `values` per rank."""
+        if self.pg is None:
+            return [list(values)]
+        import torch
+
+        mine = torch.tensor(values, dtype=torch.float64)
+        out = [torch.zeros_like(mine) for _ in range(self.world)]
+        self.pg.all_gather(out, mine)
+        return [[float(x) for x in t] for t in out]
+
     def sum(self, value: float) -> float:
         if self.pg is None:
             return value
@@ -217,7 +228,18 @@ def build_shard(args: argparse.Namespace, rank: int, world: int) -> Workload:
     outlet = np.arange(n_total)
     node_rank = shard.assign_nodes(None, river_g, world, outlet_node=outlet, zones=np.full(n_total, 12.0))
     s = shard.partition(None, None, river_g, dis_g, world, node_rank=node_rank, ranks=[rank], outlet_node=outlet)[rank]
-    land, states = synth.make_land(n_total, "1h", seed=1, select=s.elements)   # element i drains to node i: local = local
+    # the shard's elements in the order of their forcing columns (a shard is a scattered subset of the basin's elements:
+    # in index order the 32 elements of a warp would read 32 distant columns of the forcing bank, in this order they read
+    # the same or neighbouring ones, like the consecutive elements of the whole basin do).  Element g drains to node g.
+    order = np.argsort(s.elements % 1024, kind="stable")
+    land, states = synth.make_land(n_total, "1h", seed=1, select=s.elements[order])
+    land.outlet_node = order.astype(np.int32)              # local node of local element j = the old local position
+    inv = np.empty(len(order), np.int64)
+    inv[order] = np.arange(len(order))
+    src = s.river.entry_src.astype(np.int64)
+    s.river.entry_src = np.where(src >= 0, inv[np.maximum(src, 0)], src).astype(np.int32)
+    land.normalise()
+    s.river.normalise()
     desc.update({"shard_elements": int(len(s.elements)), "shard_stage": int(s.stage),
                  "boundary_rows_received": int(sum(len(r) for _, r in s.recv)),
                  "boundary_rows_sent": int(sum(len(r) for _, r in s.send))})
@@ -389,6 +411,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     launches = int(tm["land_launches"] + tm["river_launches"])
     n_fast = int(tm["n_fast"])
     dist.barrier()
+    per_rank = dist.all_gather([device_ms / K, tm["land_ms"] / K, tm["river_ms"] / K, wall_ms / K])
     device_ms_max = dist.max(device_ms)
     total_zone_steps = dist.sum(float(zone_steps_per_step * K))
     value = total_zone_steps / (device_ms_max * 1e-3)
@@ -607,6 +630,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
                 "same_final_states_as_resident_run": None if same is None else bool(same),
                 "node_series_returned": "all nodes" if e2e_nodes is None else "the outlet node of every member"},
         "e2e_gauged_nodes": e2e_gauged, "multi_gpu_parity": parity,
+        "per_rank_ms_per_step": {"columns": ["device (timed region / K)", "runoff generation", "routing", "host wall"],
+                                 "rows": [[round(x, 3) for x in row] for row in per_rank]},
         "gpu_launches": launches,
         "kernel_ms_per_step": {"runoff_generation": land_ms_avg, "routing": float(np.mean(river_ms)),
                                "wall": wall_ms / K,

@@ -37,10 +37,13 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPENDS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple[str, ...] = ()) -> str:
+    """`variant` / `defines`: a development build `libhydpy_b200_<variant>.so` with extra -D flags beside the product
+    library (select it with HYDPY_B200_LIB=… for A/B measurements on the GPU box)."""
+    out = LIB if not variant else os.path.join(HERE, f"libhydpy_b200_{variant}.so")
+    if not variant and not force and not is_stale():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    cmd = [nvcc(), *NVCC_FLAGS, *defines, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd))
@@ -50,8 +53,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         print(proc.stdout + proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, variant=name,
+          defines=tuple(a for a in sys.argv[1:] if a.startswith("-D")))

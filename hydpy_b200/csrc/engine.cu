@@ -301,6 +301,7 @@ struct hb_engine {
   // window); `comm_calls` counts the send/receive calls since the window was staged
   std::vector<DBuf<double>> d_comm_stage[2];
   std::vector<DBuf<int32_t>> d_comm_rows[2];
+  std::vector<std::vector<int32_t>> comm_rows_host[2];   // what d_comm_rows holds (the same lists come back every window)
   int comm_calls[2] = {0, 0};
 
   hb_timing timing{};
@@ -2515,13 +2516,23 @@ __global__ void scatter_rows_kernel(const double* __restrict__ src, double* __re
   dst[(int64_t)sel[r] * nt + t] = src[i];
 }
 
-// staging slot of the next send/receive call of the current window
-static int comm_slot(hb_engine* h, size_t n_rows, size_t n_values, double** stage, int32_t** rows_dev) {
+// staging slot of the next send/receive call of the current window; the row list is uploaded only when it differs from what
+// the slot holds (a sharded run repeats the same lists every window: no per-window host-to-device copy on the comm stream)
+static int comm_slot(hb_engine* h, const int32_t* rows, size_t n_rows, size_t n_values, double** stage, int32_t** rows_dev) {
   const int c = h->cur;
   const size_t slot = (size_t)h->comm_calls[c]++;
-  if (h->d_comm_stage[c].size() <= slot) { h->d_comm_stage[c].resize(slot + 1); h->d_comm_rows[c].resize(slot + 1); }
+  if (h->d_comm_stage[c].size() <= slot) {
+    h->d_comm_stage[c].resize(slot + 1); h->d_comm_rows[c].resize(slot + 1); h->comm_rows_host[c].resize(slot + 1);
+  }
   HB_CUDA(h, h->d_comm_stage[c][slot].reserve(n_values));
   HB_CUDA(h, h->d_comm_rows[c][slot].reserve(n_rows));
+  std::vector<int32_t>& held = h->comm_rows_host[c][slot];
+  if (held.size() != n_rows || !std::equal(held.begin(), held.end(), rows)) {
+    held.assign(rows, rows + n_rows);
+    // (the previous message of this slot — two windows ago — must be through before its row list changes)
+    HB_CUDA(h, cudaStreamSynchronize(h->s_comm));
+    HB_CUDA(h, cudaMemcpy(h->d_comm_rows[c][slot].p, held.data(), n_rows * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   *stage = h->d_comm_stage[c][slot].p;
   *rows_dev = h->d_comm_rows[c][slot].p;
   return HB_OK;
@@ -2548,9 +2559,8 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
     // hands over hundreds of short series per window; one NCCL operation per row would cost more than the transfer)
     double* stage = nullptr;
     int32_t* rows_dev = nullptr;
-    int rc = comm_slot(h, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
+    int rc = comm_slot(h, rows, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
     if (rc) return rc;
-    HB_CUDA(h, cudaMemcpyAsync(rows_dev, rows, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_comm));
     const size_t total = (size_t)n * h->nt;
     gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comm>>>(base, stage, rows_dev, n, h->nt);
     HB_CUDA(h, cudaGetLastError());
@@ -2583,6 +2593,9 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
   }
   // the routing of two windows ago was the last reader of this buffer set
   HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
+  // an NCCL receive occupies SMs from its launch until the peer's data is in: it is posted behind the runoff generation of
+  // the window (when there is one in flight), i.e. about when the upstream ranks start routing the same window
+  if (h->have_results) HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_land_done[h->cur], 0));
   // ONE message per peer (see hb_comm_send_rows).  Consecutive external rows — what hydpy_b200.shard hands out — are
   // received straight into the buffer the reach kernels read; any other selection goes through a staging buffer
   if (contiguous) {
@@ -2591,9 +2604,8 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
   } else {
     double* stage = nullptr;
     int32_t* rows_dev = nullptr;
-    int rc = comm_slot(h, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
+    int rc = comm_slot(h, ext_rows, (size_t)n, (size_t)n * h->nt, &stage, &rows_dev);
     if (rc) return rc;
-    HB_CUDA(h, cudaMemcpyAsync(rows_dev, ext_rows, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_comm));
     HB_NCCL(h, h->nccl.Recv(stage, (size_t)n * h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
     const size_t total = (size_t)n * h->nt;
     scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comm>>>(stage, h->d_ext_rows[h->cur].p, rows_dev, n,

@@ -118,6 +118,25 @@ struct RiverDev {
 #ifndef HB_SPIN_SLEEP
 #define HB_SPIN_SLEEP 256
 #endif
+// Polls of tasks that wait long (the narrow tail of a river tree offers fewer tasks than the kernel has warps; ncu, r02a:
+// 22 % of the wavefront's instructions are polls of tasks waiting for their own previous chunk) could pause longer:
+// HB_SPIN_MAXSHIFT > 0 doubles the pause every HB_SPIN_STEP polls up to HB_SPIN_SLEEP << HB_SPIN_MAXSHIFT ns.  Measured
+// (profiles/r02i_spin_backoff.txt, 438-h windows): the runoff generation beside it gains 0.2-0.6 ms, but the wavefront
+// itself wakes up late on its critical path (6.2 -> 7.2 / 9.8 ms alone for 4 / 16 us) and the pipelined step LOSES
+// (18.7 -> 20.2 / 20.8 ms).  The default stays a constant pause.
+#ifndef HB_SPIN_STEP
+#define HB_SPIN_STEP 4
+#endif
+#ifndef HB_SPIN_MAXSHIFT
+#define HB_SPIN_MAXSHIFT 0
+#endif
+__device__ __forceinline__ void spin_pause(int spins) {
+  if (spins > HB_SPIN_FAST) {
+    int sh = (spins - HB_SPIN_FAST) / HB_SPIN_STEP;
+    sh = sh > HB_SPIN_MAXSHIFT ? HB_SPIN_MAXSHIFT : sh;
+    __nanosleep((unsigned)HB_SPIN_SLEEP << sh);
+  }
+}
 
 // qt [nt][e_pad]  →  land rows [n_elem][nt]   (32x32 shared-memory tile transpose, both sides coalesced)
 // (elements e_begin .. n_elem-1 with a grid of ceil((n_elem - e_begin) / 32) x ceil(nt / 32) blocks)
@@ -404,7 +423,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     // only a few lanes per warp poll; the grouped wavefront below, where every lane has flags of its own, needs them)
     if (lane == 0)
       while (ld_acquire(d.progress + r) < c * d.pscale) {
-        if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+        spin_pause(++spins);
         if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
       }
     if (!__all_sync(full, ok)) return false;
@@ -418,7 +437,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       const int* flag = d.progress + (tp.inline_deps ? tp.dep : d.dep_reach[m.dep0 + p]);
       spins = 0;
       while (ld_acquire(flag) < (c + 1) * d.pscale) {
-        if (++spins > HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+        spin_pause(++spins);
         if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
       }
     }
