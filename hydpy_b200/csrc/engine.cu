@@ -194,7 +194,7 @@ struct hb_engine {
       tag[n] = t;
       return cudaEventRecord(ev[n++], st) == cudaSuccess ? 0 : -1;
     }
-  } land_marks, river_marks;
+  } land_marks, river_marks, comm_marks;   // (comm_marks: only with HB_DEBUG_TIMELINE)
   int mark(int tag) { return land_marks.add(tag, stream); }
   std::string error;
   cudaDeviceProp prop{};
@@ -227,7 +227,13 @@ struct hb_engine {
   int land_path = 0;                  // HB_LAND_AUTO / HB_LAND_GENERAL
   // element slabs of the fast path: slab 0 runs on `stream`, slab s on s_slab[s-1]; s_join collects them
   int land_slabs = 2;
-  int64_t land_chunk = 0;             // steps per time chunk of the fast path (0 = automatic)
+  // steps per time chunk of the fast path (0 = as long as the scratch memory allows).  Kernels of ≈1-3 ms instead of
+  // ≈5-10 ms: the thread-per-element kernel holds its share of every SM's registers until its LAST block retires, and a
+  // kernel that needs a whole CTA slot (the NCCL send/receive of a boundary hand-over) waits that long — measured on 2 GPUs
+  // (profiles/r02h_timeline.txt): the boundary rows arrived 7.4 ms late, the downstream rank lost 2.2 ms per step
+  // (default -1: 128 steps once the engine takes part in a multi-GPU run, else as long as the memory allows: one GPU
+  // alone measured 18.7-18.9 ms per 438-h step unchunked against 18.9-19.8 ms in chunks of 110)
+  int64_t land_chunk = -1;
   cudaStream_t s_slab[HB_MAX_SLABS - 1] = {}, s_join = nullptr;
   cudaEvent_t ev_slab_fork = nullptr, ev_slab_zone[HB_MAX_SLABS] = {}, ev_slab_done[HB_MAX_SLABS] = {};
   int slabs_used = 1;                 // slabs of the current run_land
@@ -1048,7 +1054,7 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       h->land_slabs = (int)value;
       return HB_OK;
     case HB_OPT_LAND_CHUNK:
-      HB_REQUIRE(h, value >= 0, HB_EINVAL, "hb_set_option: negative land chunk");
+      HB_REQUIRE(h, value >= -1, HB_EINVAL, "hb_set_option: invalid land chunk");
       h->land_chunk = value;
       return HB_OK;
     case HB_OPT_RIVER_SWEEP:
@@ -1776,7 +1782,8 @@ static int run_land(hb_engine* h) {
     else budget = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);
     int64_t chunk_max = (int64_t)(budget / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
-    if (h->land_chunk > 0 && h->land_chunk < chunk_max) chunk_max = h->land_chunk;
+    const int64_t want = h->land_chunk >= 0 ? h->land_chunk : (h->comm ? 128 : 0);
+    if (want > 0 && want < chunk_max) chunk_max = want;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
     const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
     HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
@@ -2182,6 +2189,14 @@ static int resolve_marks(hb_engine* h, hb_engine::Marks& m, bool land) {
       cudaEventElapsedTime(&ms, m.ev[i - 1], m.ev[i]);
       fprintf(stderr, "[hb marks] %s interval ending at tag %d: %.3f ms\n", land ? "land" : "river", tag, ms);
     }
+    static const bool timeline = getenv("HB_DEBUG_TIMELINE") != nullptr;   // development aid: when did each window's part
+    if (timeline && (tag == HB_K_BEGIN || tag == HB_K_END) && h->ev[3]) {  // begin / end, relative to hb_timer_start
+      float at = 0.f;
+      if (cudaEventElapsedTime(&at, h->ev[3], m.ev[i]) == cudaSuccess)
+        fprintf(stderr, "[hb timeline] rank %d %s %s at %.3f ms\n", h->rank, land ? "land" : "river",
+                tag == HB_K_BEGIN ? "begin" : "end", at);
+      else cudaGetLastError();
+    }
     if (tag == HB_K_BEGIN) { begin = i; continue; }
     if (tag == HB_K_END) {
       HB_CUDA(h, cudaEventElapsedTime(&ms, m.ev[begin], m.ev[i]));
@@ -2210,6 +2225,14 @@ int hb_wait(hb_engine* h) {
   HB_CUDA(h, cudaStreamSynchronize(h->s_h2d));
   int rc;
   if ((rc = resolve_marks(h, h->land_marks, true)) || (rc = resolve_marks(h, h->river_marks, false))) return rc;
+  for (size_t i = 0; i < h->comm_marks.n; ++i) {   // (HB_DEBUG_TIMELINE)
+    float at = 0.f;
+    static const char* what[] = {"send: routing done", "send: rows packed", "send: done", "recv: done"};
+    if (h->ev[3] && cudaEventElapsedTime(&at, h->ev[3], h->comm_marks.ev[i]) == cudaSuccess)
+      fprintf(stderr, "[hb timeline] rank %d comm %s at %.3f ms\n", h->rank, what[h->comm_marks.tag[i] - 100], at);
+    else cudaGetLastError();
+  }
+  h->comm_marks.n = 0;
   h->timing.total_ms = h->timing.land_ms + h->timing.river_ms;
   h->pending = false;
   if (h->h_wave_err && *h->h_wave_err) {
@@ -2553,6 +2576,8 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
   if (n == 0 || h->nt == 0) return HB_OK;
   // all NCCL traffic of this engine runs on ONE stream (s_comm); the send waits for the routing of the window
   HB_CUDA(h, cudaStreamWaitEvent(h->s_comm, h->ev_river_done[h->cur], 0));
+  static const bool timeline = getenv("HB_DEBUG_TIMELINE") != nullptr;
+  if (timeline) h->comm_marks.add(100, h->s_comm);     // the routing of the window is through
   const double* src = base + (int64_t)rows[0] * h->nt;
   if (n > 1) {
     // the rows of a peer travel as ONE message: packed by a gather kernel behind the routing (a basin cut into sub-basins
@@ -2566,7 +2591,9 @@ int hb_comm_send_rows(hb_engine* h, int peer, int kind, int64_t n, const int32_t
     HB_CUDA(h, cudaGetLastError());
     src = stage;
   }
+  if (timeline) h->comm_marks.add(101, h->s_comm);     // rows packed
   HB_NCCL(h, h->nccl.Send(src, (size_t)n * h->nt, kNcclFloat64, peer, h->comm, h->s_comm));
+  if (timeline) h->comm_marks.add(102, h->s_comm);     // sent
   HB_CUDA(h, cudaEventRecord(h->ev_send_done[h->cur], h->s_comm));
   h->pending = true;
   return HB_OK;
@@ -2611,6 +2638,10 @@ int hb_comm_recv_ext(hb_engine* h, int peer, int64_t n, const int32_t* ext_rows)
     scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comm>>>(stage, h->d_ext_rows[h->cur].p, rows_dev, n,
                                                                                h->nt);
     HB_CUDA(h, cudaGetLastError());
+  }
+  {
+    static const bool timeline = getenv("HB_DEBUG_TIMELINE") != nullptr;
+    if (timeline) h->comm_marks.add(103, h->s_comm);   // received
   }
   HB_CUDA(h, cudaEventRecord(h->ev_ext_ready[h->cur], h->s_comm));
   h->pending = true;

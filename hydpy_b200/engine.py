@@ -348,7 +348,7 @@ class Engine:
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_SLABS, int(slabs)), "hb_set_option")
 
     def set_land_chunk(self, steps: int) -> None:
-        """Time chunk of the fast runoff-generation path in steps (0 = automatic)."""
+        """Time chunk of the fast runoff-generation path in steps (0 = as long as the scratch memory allows; -1 = the engine's default)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_CHUNK, int(steps)), "hb_set_option")
 
     def set_wave_blocks(self, blocks_per_sm: int) -> None:

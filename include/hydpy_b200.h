@@ -326,7 +326,9 @@ int hb_select_series(hb_engine* h, int series, int on);
  * on a stream of its own: while the thread-per-element kernel of one slab follows its sequential RecStep chains (few
  * warps, latency-bound) the thread-per-zone kernel of another slab fills the SMs.  Results do not depend on it. */
 #define HB_OPT_LAND_SLABS 5
-/* HB_OPT_LAND_CHUNK (0 = as long as the scratch memory allows, default; else steps): time chunk of the fast path. */
+/* HB_OPT_LAND_CHUNK (steps; 0 = as long as the scratch memory allows; default -1 = 128 once hb_comm_init has been called,
+ * else 0): time chunk of the fast path.  Shorter kernels let kernels that need a whole CTA slot (the NCCL hand-over of the
+ * boundary rows) onto the SMs sooner. */
 #define HB_OPT_LAND_CHUNK 6
 enum hb_mct_series {
   HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
