@@ -2346,6 +2346,8 @@ int hb_get_timing(hb_engine* h, hb_timing* out) {
     h->timing.elem_steps = (int64_t)c[HB_CNT_ELEM_STEPS];
     h->timing.elem_steps_run = (int64_t)c[HB_CNT_ELEM_STEPS_RUN];
     h->timing.substeps_pow = (int64_t)c[HB_CNT_SUBSTEPS_POW];
+    h->timing.elem_warpsteps = (int64_t)c[HB_CNT_ELEM_WARPSTEPS];
+    h->timing.elem_warpsteps_run = (int64_t)c[HB_CNT_ELEM_WARPSTEPS_RUN];
   }
   *out = h->timing;
   // sums restart with the next run

@@ -94,6 +94,8 @@ enum { HB_CNT_ZONE_WARPSTEPS = 0,   // warp-steps of the branch-free (FIELD/FORE
        HB_CNT_ELEM_STEPS,           // element-steps of the element kernel (hland_96)
        HB_CNT_ELEM_STEPS_RUN,       // … that ran the RecStep chain of Calc_Q0_Perc_UZ_V1
        HB_CNT_SUBSTEPS_POW,         // RecStep sub-steps with uz > 0 (a pow each), per element
+       HB_CNT_ELEM_WARPSTEPS,       // warp-steps of the element kernel (32 elements x 1 step)
+       HB_CNT_ELEM_WARPSTEPS_RUN,   // … in which at least one lane ran the chain (what the FP64 pipe is busy with)
        HB_CNT_COUNT };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
@@ -746,6 +748,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
   const int64_t tstride = (int64_t)d.zmax * ep;
   unsigned n_run = 0, n_pow = 0;   // element-steps that ran the RecStep chain, sub-steps with uz > 0
+  unsigned n_wrun = 0;             // (warp-uniform) steps in which some lane of the warp ran it
+  const unsigned emask = __activemask();
   for (int64_t t = 0; t < d.nt; ++t) {
     const double* ta = d.term_a + t * tstride + e;
     const double* tb = d.term_b + t * tstride + e;
@@ -864,6 +868,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
     double perc_sum = 0.0, q0_sum = 0.0;
     // an empty upper zone without recharge stays empty through all RecStep sub-steps (uz = max(0 + 0, 0), perc = q0 = 0,
     // no error correction): dry spells skip the chain — the same bits, nothing to wait for
+    if (MODEL == HB_MODEL_HLAND_96) n_wrun += __any_sync(emask, !(uz == 0.0 && inuz == 0.0)) ? 1u : 0u;
     if (!(uz == 0.0 && inuz == 0.0)) {
       ++n_run;
       const double uz_old = uz;
@@ -957,6 +962,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       atomicAdd(d.counters + HB_CNT_ELEM_STEPS, (unsigned long long)d.nt * __popc(m));
       atomicAdd(d.counters + HB_CNT_ELEM_STEPS_RUN, (unsigned long long)run);
       atomicAdd(d.counters + HB_CNT_SUBSTEPS_POW, (unsigned long long)pw);
+      atomicAdd(d.counters + HB_CNT_ELEM_WARPSTEPS, (unsigned long long)d.nt);
+      atomicAdd(d.counters + HB_CNT_ELEM_WARPSTEPS_RUN, (unsigned long long)n_wrun);
     }
   }
 }

@@ -465,6 +465,8 @@ typedef struct hb_timing {
   int64_t elem_steps;          /* element-steps of the element kernel                                                   */
   int64_t elem_steps_run;      /* ... that ran the RecStep chain of Calc_Q0_Perc_UZ_V1 (not: uz == 0 and inuz == 0)     */
   int64_t substeps_pow;        /* RecStep sub-steps with uz > 0, i.e. with a pow (of recstep * elem_steps_run)          */
+  int64_t elem_warpsteps;      /* warp-steps (32 elements x 1 step) of the element kernel                               */
+  int64_t elem_warpsteps_run;  /* ... in which at least one lane ran the chain                                          */
 } hb_timing;
 /* Times and launch counts are SUMS over all runs since the previous hb_get_timing call (which resets them); after a
  * single hb_run they are that run's figures.  Waits for pending asynchronous work. */
