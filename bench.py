@@ -65,6 +65,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--members", type=int, default=0, help="ensemble members of --config 1 / 4 in total (0 = 4096 / 512)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the unsharded run")
     ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
+    ap.add_argument("--no-land-fuse", action="store_true",
+                    help="hand the zone terms over through HBM instead of adding them inside the zone kernel (A/B timing)")
     ap.add_argument("--land-chunk", type=int, default=0, help="time chunk of the fast land path in steps (0 = engine default)")
     return ap.parse_args()
 
@@ -349,6 +351,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         eng.set_wave_blocks(args.wave_blocks)
     if args.land_slabs:
         eng.set_land_slabs(args.land_slabs)
+    if args.no_land_fuse:
+        eng.set_land_fuse(False)
     if args.land_chunk:
         eng.set_land_chunk(args.land_chunk)
     if dist.world > 1:

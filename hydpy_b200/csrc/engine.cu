@@ -30,6 +30,9 @@ using namespace hb;
 #define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
 #define HB_MAX_SLABS 8
+#define HB_FUSE_ZMAX 16      // fused reduction: one warp per zone of a 32-element group, at most 16 warps per block
+// dynamic shared memory of zone_kernel<…, ZW>: constants [14][ZW*32] double2 + term buffers [G][2][ZW][32] doubles
+#define HB_FUSE_SMEM(zw) ((size_t)(zw) * 32 * (14 * 16 + ZoneGeom<zw>::G * 2 * 8))
 // zone/snow series the fast path of hland_96 stages in its own layout (first block + the evap submodels' block)
 #define HB_S_STAGED(s) ((s) < HB_S_FIRST_ELEM || ((s) >= HB_S_FIRST_ZONE3 && (s) < HB_S_SC))
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
@@ -220,6 +223,10 @@ struct hb_engine {
   int general_key = -1;
   DBuf<int32_t> d_coupled_list, d_general_list;
   DBuf<double> d_term_a, d_term_b;    // zone terms of one time chunk, [chunk][zmax][E_pad]
+  DBuf<double> d_red_a, d_red_b;      // fused reduction: two sums per element-step of one time chunk, [chunk][E_pad]
+  DBuf<int32_t> d_gwarps;             // [E_pad/32] zone warps of a fused 32-element group, 0 = group not fused
+  int64_t n_fused = 0;                // elements with HB_EI_FUSED
+  int land_fuse = 1;                  // HB_OPT_LAND_FUSE: add the zone terms inside the zone kernel where a group allows
   DBuf<unsigned long long> d_counters;   // HB_CNT_*: what the fast-path kernels executed since the last hb_get_timing
   DBuf<double> d_series_stage[HB_S_COUNT];   // chunk-local staging of the zone/snow series (fast path)
   DBuf<int32_t> d_zone_slot, d_snow_slot;         // ABI cell → k*E_pad + e (fast-path elements), -1 otherwise
@@ -260,6 +267,7 @@ struct hb_engine {
   bool have_forcing = false, have_results = false, have_routed = false;
   DBuf<double> d_forcing[2], d_sinfactor[2], d_qt, d_land_rows[2];
   DBuf<MathTables> d_tables;
+  DBuf<ChainTables> d_chain_tables;
 
   // ---- river ----
   bool have_river = false;
@@ -478,6 +486,11 @@ int hb_create(int device, hb_engine** out) {
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
   cudaFuncSetAttribute(reach_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_BULK_SMEM);
+#define HB_FUSE_ATTR(zw) cudaFuncSetAttribute(zone_kernel<true, false, HB_MODEL_HLAND_96, zw>, \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB_FUSE_SMEM(zw))
+  HB_FUSE_ATTR(1); HB_FUSE_ATTR(2); HB_FUSE_ATTR(3); HB_FUSE_ATTR(4); HB_FUSE_ATTR(6); HB_FUSE_ATTR(8); HB_FUSE_ATTR(12);
+  HB_FUSE_ATTR(16);
+#undef HB_FUSE_ATTR
   {
     const int cs = (int)HB_COUPLED_SMEM(HB_COUPLED_ZMAX);
     cudaFuncSetAttribute(coupled_kernel<288, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs);
@@ -526,6 +539,15 @@ int hb_create(int device, hb_engine** out) {
     make_math_tables(t);
     if (h->d_tables.reserve(1) != cudaSuccess ||
         cudaMemcpy(h->d_tables.p, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) {
+      g_create_error = "hb_create: cannot upload the math tables";
+      cudaStreamDestroy(h->stream);
+      delete h;
+      return HB_ECUDA;
+    }
+    ChainTables ct;
+    make_chain_tables(ct);
+    if (h->d_chain_tables.reserve(1) != cudaSuccess ||
+        cudaMemcpy(h->d_chain_tables.p, &ct, sizeof ct, cudaMemcpyHostToDevice) != cudaSuccess) {
       g_create_error = "hb_create: cannot upload the math tables";
       cudaStreamDestroy(h->stream);
       delete h;
@@ -735,6 +757,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   bool any_snowlimit = false;
   int64_t n_fast = 0, n_fast_sib[2] = {0, 0};
   std::vector<int32_t> coupled_list;
+  std::vector<char> soilwarp_ok((size_t)ep, 0);   // fast hland_96 element, every zone FIELD/FOREST with FC > 0
   h->any_nonsoil_warp = false;
   h->any_nonsoil_sib[0] = h->any_nonsoil_sib[1] = false;
   for (int64_t e = 0; e < ne; ++e) {
@@ -792,6 +815,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
       info |= HB_EI_COUPLED;          // (the fused kernel convolves a unit hydrograph: rconc_nash elements stay general)
       coupled_list.push_back((int32_t)e);
     }
+    if ((info & HB_EI_FAST) && model[e] == HB_MODEL_HLAND_96 && !nonsoil && n > 0) soilwarp_ok[e] = 1;
     if ((info & HB_EI_FAST) && nonsoil)
       (model[e] == HB_MODEL_HLAND_96 ? h->any_nonsoil_warp : h->any_nonsoil_sib[model[e] - 1]) = true;
     info |= model[e] << HB_EI_MODEL_SHIFT;
@@ -803,6 +827,23 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
     for (int j = 0; j < nu[e]; ++j) uh[(size_t)j * ep + e] = d->uh[d->uh_ptr[eb] + j];
   }
   for (int64_t e = ne; e <= ep; ++e) sred_ptr[e] = neb ? d->sred_ptr[neb] : 0;
+  // fused reduction (land_kernel_v2.cuh, zone_kernel<…, ZW>): groups of 32 consecutive elements whose zones all run the
+  // branch-free step; the group's block has one warp per zone (at most HB_FUSE_ZMAX)
+  std::vector<int32_t> gwarps((size_t)(ep / 32), 0);
+  int64_t n_fused = 0;
+  if (zmax <= HB_FUSE_ZMAX)
+    for (int64_t g = 0; g * 32 < ne; ++g) {
+      const int64_t lo = g * 32, hi = std::min<int64_t>(ne, lo + 32);
+      bool ok = true;
+      int w = 0;
+      for (int64_t e = lo; e < hi; ++e) { ok = ok && soilwarp_ok[e]; w = std::max(w, (int)nz[e]); }
+      if (!ok) continue;
+      gwarps[g] = w;
+      for (int64_t e = lo; e < hi; ++e) einfo[e] |= HB_EI_FUSED;
+      n_fused += hi - lo;
+    }
+  h->n_fused = n_fused;
+  { int rc_ = upload(h, h->d_gwarps, gwarps); if (rc_) return rc_; }
   h->any_snowlimit = any_snowlimit;
   h->n_fast = n_fast;
   h->n_fast_sib[0] = n_fast_sib[0]; h->n_fast_sib[1] = n_fast_sib[1];
@@ -1056,6 +1097,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
     case HB_OPT_LAND_CHUNK:
       HB_REQUIRE(h, value >= -1, HB_EINVAL, "hb_set_option: invalid land chunk");
       h->land_chunk = value;
+      return HB_OK;
+    case HB_OPT_LAND_FUSE:
+      HB_REQUIRE(h, value == 0 || value == 1, HB_EINVAL, "hb_set_option: land fuse must be 0 or 1");
+      h->land_fuse = (int)value;
       return HB_OK;
     case HB_OPT_RIVER_SWEEP:
       HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES || value == HB_RIVER_GROUPED, HB_EINVAL,
@@ -1755,16 +1800,23 @@ static int run_land(hb_engine* h) {
     v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
-    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.chain_tables = h->d_chain_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow; v.n_uh = h->n_uh; v.uh0 = h->d_uh0.p;
     v.counters = h->d_counters.p;
-    v.nash_stage = h->any_nash ? 1 : 0;
-    const size_t esmem = h->any_nash ? (size_t)HB_NASH_STAGE * 64 * sizeof(double) : 0;
+    // [storage | ordinate][thread] staging of the runoff concentration: the rconc_nash cascade of a step, the rconc_uh
+    // memory for the whole launch
+    v.nash_stage = 1;
+    const size_t esmem = (size_t)HB_NASH_STAGE * 64 * sizeof(double);
     v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
     int n_staged = 0;
     for (int s = 0; s < HB_S_COUNT; ++s) n_staged += (HB_S_STAGED(s) && h->series_on[s]) ? 1 : 0;
+    // fused reduction: the groups whose zone terms the zone kernel adds itself (no series recording there)
+    const bool fuse = use_fast && !any_series && h->land_fuse && h->n_fused > 0;
+    const bool all_fused = fuse && h->n_fused == h->n_fast && !use_fast_sib;   // then no term buffers at all
+    v.fused = fuse ? 1 : 0;
+    v.gwarps = h->d_gwarps.p;
     // time chunks bound the two term buffers (3 GB each at most)
-    const int64_t per_step = (int64_t)h->zmax * ep;
+    const int64_t per_step = all_fused ? ep : (int64_t)h->zmax * ep;   // (all fused: [chunk][E_pad] sums instead)
     // scratch per simulated step: two term buffers + one staging buffer per recorded zone/snow series.  Budget: 6 GB, or
     // up to a quarter of the free device memory (at most 32 GB) for large ensembles, whose chunks would otherwise shrink
     // to a handful of steps per launch
@@ -1786,9 +1838,16 @@ static int run_land(hb_engine* h) {
     if (want > 0 && want < chunk_max) chunk_max = want;
     const int64_t n_chunks = (nt + chunk_max - 1) / chunk_max;
     const int64_t chunk = (nt + n_chunks - 1) / n_chunks;
-    HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
-    HB_CUDA(h, h->d_term_b.reserve((size_t)chunk * per_step));
+    if (!all_fused) {
+      HB_CUDA(h, h->d_term_a.reserve((size_t)chunk * per_step));
+      HB_CUDA(h, h->d_term_b.reserve((size_t)chunk * per_step));
+    }
+    if (fuse) {
+      HB_CUDA(h, h->d_red_a.reserve((size_t)chunk * ep));
+      HB_CUDA(h, h->d_red_b.reserve((size_t)chunk * ep));
+    }
     v.term_a = h->d_term_a.p; v.term_b = h->d_term_b.p;
+    v.red_a = h->d_red_a.p; v.red_b = h->d_red_b.p;
     for (int s = 0; s < HB_S_COUNT; ++s) {
       v.series[s] = nullptr;
       if (!h->series_on[s]) continue;
@@ -1828,7 +1887,26 @@ static int run_land(hb_engine* h) {
         if (sl == 0) h->mark(HB_K_OTHER);
         else HB_CUDA(h, cudaStreamWaitEvent(st, h->ev_slab_zone[sl - 1], 0));
         const unsigned zgrid = (unsigned)((int64_t)h->zmax * v.slab_blocks), egrid = (unsigned)((e_hi - v.e_lo + 63) / 64);
-        if (use_fast) {
+        if (fuse) {
+          // one block per 32-element group of the slab, one warp per zone
+          const unsigned fgrid = (unsigned)v.slab_blocks * 4u;
+          const int zw = h->zmax <= 1 ? 1 : h->zmax <= 2 ? 2 : h->zmax <= 3 ? 3 : h->zmax <= 4 ? 4 : h->zmax <= 6 ? 6
+                         : h->zmax <= 8 ? 8 : h->zmax <= 12 ? 12 : 16;
+#define HB_FUSE_LAUNCH(zw_) zone_kernel<true, false, HB_MODEL_HLAND_96, zw_><<<fgrid, zw_ * 32, HB_FUSE_SMEM(zw_), st>>>(v)
+          switch (zw) {
+            case 1: HB_FUSE_LAUNCH(1); break;
+            case 2: HB_FUSE_LAUNCH(2); break;
+            case 3: HB_FUSE_LAUNCH(3); break;
+            case 4: HB_FUSE_LAUNCH(4); break;
+            case 6: HB_FUSE_LAUNCH(6); break;
+            case 8: HB_FUSE_LAUNCH(8); break;
+            case 12: HB_FUSE_LAUNCH(12); break;
+            default: HB_FUSE_LAUNCH(16); break;
+          }
+#undef HB_FUSE_LAUNCH
+          h->timing.land_launches += 1;
+        }
+        if (use_fast && !all_fused) {
           if (any_series) zone_kernel<true, true, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
           else zone_kernel<true, false, HB_MODEL_HLAND_96><<<zgrid, 128, 0, st>>>(v);
           if (h->any_nonsoil_warp) {
@@ -1863,7 +1941,11 @@ static int run_land(hb_engine* h) {
           }
         }
         if (sl == 0) h->mark(HB_K_ZONE);
-        if (use_fast) {
+        if (fuse) {
+          element_kernel<false, HB_MODEL_HLAND_96, true><<<egrid, 64, esmem, st>>>(v);
+          h->timing.land_launches += 1;
+        }
+        if (use_fast && !all_fused) {
           if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, esmem, st>>>(v);
           else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, esmem, st>>>(v);
           h->timing.land_launches += 1;
@@ -1889,7 +1971,7 @@ static int run_land(hb_engine* h) {
     v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;
-    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.qt = h->d_qt.p;
+    v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.chain_tables = h->d_chain_tables.p; v.qt = h->d_qt.p;
     v.nt = nt; v.t_first = h->t0; v.t_out = 0;
     v.clist = h->d_coupled_list.p; v.n_clist = (int64_t)h->coupled_list.size();
     const int zw = h->zmax;

@@ -244,4 +244,134 @@ HB_HD double hb_log_from_normal(double x, double lgn) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// RecStep chain (Calc_Q0_Perc_UZ_V1, hydpy/models/hland/hland_model.py:2456-2484): q = dt*k * (uz/contriarea)^(1+alpha)
+// once per sub-step, every instruction on ONE dependent chain per element (the sub-steps of an element are sequential
+// and all 10^5 chains are resident at once, so the kernel's time is instructions-on-the-chain x their latency).  The
+// routine below is built for the shortest chain, not for generality:
+//
+//   q = 2^(y*log2(d) + c2),   c2 = log2(dt*k) - y*log2(contriarea)  (step-invariant, off the chain)
+//   log2(d) = e + log2(c_k) + log1p(r)/ln2 with 512 interval centres (|r| <= 2^-10: a degree-4 polynomial reaches
+//             2e-16, three dependent FMAs with 1/ln2 folded into the coefficients);
+//   2^t     = 2^q * 2^(j/256) * (1 + p(r)),  n = rint(256 t), r = t - n/256 EXACT (no two-part reduction constant),
+//             degree-4 polynomial in r with the powers of ln2 folded in.
+//
+// 15 dependent fp64 instructions from d to q instead of 26, two shared-memory look-ups (10 KB of tables per block).
+// Accuracy: relative error of q < 2.3e-16 * (4 + 1.5 T), T = the magnitudes of the terms of log2 q (one double), i.e.
+// < 2e-14 on everything the model feeds it — tests/test_fastmath.py checks THIS code on the host against x87 extended
+// precision.  Valid for positive normal d and |t| < 1000; the caller checks t and repeats the step with the general code
+// otherwise.
+#define HB_CHAIN_LOG_BITS 9
+#define HB_CHAIN_LOG_N (1 << HB_CHAIN_LOG_BITS)   // centres 1 + k/512, k = 0..511 (a mantissa that rounds up to 2 is the
+                                                  // centre 1 of the next binade: the rounding carries into the exponent)
+#define HB_CHAIN_EXP_BITS 8
+#define HB_CHAIN_EXP_N (1 << HB_CHAIN_EXP_BITS)
+
+struct ChainTables {
+  double log_tab[HB_CHAIN_LOG_N][2];   // {1/c_k rounded to double, -log2 of that ROUNDED reciprocal}
+  double exp2[HB_CHAIN_EXP_N];         // 2^(j/256)
+};
+
+inline void make_chain_tables(ChainTables& t) {
+  for (int k = 0; k < HB_CHAIN_LOG_N; ++k) {
+    const long double c = 1.0L + (long double)k / HB_CHAIN_LOG_N;
+    t.log_tab[k][0] = (double)(1.0L / c);
+    t.log_tab[k][1] = (k == 0) ? 0.0 : (double)(-log2l((long double)t.log_tab[k][0]));
+  }
+  for (int j = 0; j < HB_CHAIN_EXP_N; ++j) t.exp2[j] = (double)exp2l((long double)j / HB_CHAIN_EXP_N);
+}
+
+// On the device the tables are ONE block-wide shared-memory object at namespace scope (only kernels that use it pay for
+// it): the look-ups are `LDS [index + window + constant]` — through a pointer the table base costs an add on the chain.
+#ifdef __CUDACC__
+__shared__ ChainTables hb_chain_smem;
+__device__ __forceinline__ void hb_chain_stage(const ChainTables* g) {   // all threads of the block, before a barrier
+  const double* src = reinterpret_cast<const double*>(g);
+  double* dst = reinterpret_cast<double*>(&hb_chain_smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(ChainTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+}
+#endif
+struct ChainRef {
+#ifndef __CUDA_ARCH__
+  const ChainTables* p;
+#endif
+};
+HB_HD ChainRef hb_chainref(const ChainTables* T) {
+  ChainRef t;
+#ifndef __CUDA_ARCH__
+  t.p = T;
+#else
+  (void)T;
+#endif
+  return t;
+}
+HB_HD void hb_ld_clog(ChainRef t, int byte_off, double& invc, double& l2c) {   // byte_off = 16 k
+#ifdef __CUDA_ARCH__
+  const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(hb_chain_smem.log_tab) + byte_off);
+  invc = v.x; l2c = v.y;
+#else
+  invc = t.p->log_tab[byte_off >> 4][0]; l2c = t.p->log_tab[byte_off >> 4][1];
+#endif
+}
+HB_HD double hb_ld_cexp(ChainRef t, int byte_off) {                             // byte_off = 8 j
+#ifdef __CUDA_ARCH__
+  return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(hb_chain_smem.exp2) + byte_off);
+#else
+  return t.p->exp2[byte_off >> 3];
+#endif
+}
+
+enum {
+  HB_C_L4 = 0, HB_C_L3, HB_C_L2, HB_C_L1, HB_C_E4, HB_C_E3, HB_C_E2, HB_C_E1, HB_C_COUNT
+};
+#define HB_CHAIN_LITERALS                                                                                             \
+  {-0.36067376022224085 /* -1/(4 ln2) */, 0.48089834696298783 /* 1/(3 ln2) */, -0.72134752044448170 /* -1/(2 ln2) */, \
+   1.4426950408889634 /* 1/ln2 */, 9.6181291076284772e-03 /* ln2^4/24 */, 5.5504108664821580e-02 /* ln2^3/6 */,       \
+   2.4022650695910071e-01 /* ln2^2/2 */, 6.9314718055994531e-01 /* ln2 */}
+#ifdef __CUDACC__
+__constant__ double hb_chain_k_dev[HB_C_COUNT] = HB_CHAIN_LITERALS;
+#endif
+static const double hb_chain_k_host[HB_C_COUNT] = HB_CHAIN_LITERALS;
+#ifdef __CUDA_ARCH__
+#define HB_CLIT(i) hb_chain_k_dev[i]
+#else
+#define HB_CLIT(i) hb_chain_k_host[i]
+#endif
+
+// 2^t with t = y*log2(d) + c2, for positive normal d and |t| < 1000; `t` is returned for the caller's range check.  Anything
+// else (zero, negative, subnormal, inf, nan d; |t| >= 1000) yields garbage without side effects.  With y >= 1,
+// c2 <= 200 y and a subnormal or zero d the garbage announces itself: t < -800.
+HB_HD double hb_chain_pow2(double d, double y, double c2, ChainRef T, double& t) {
+  const int hi = hb_hi(d), lo = hb_lo(d);
+  const int hr = hi + (1 << (19 - HB_CHAIN_LOG_BITS));      // mantissa rounded to the nearest centre (may carry: see above)
+  const int top = hr & (int)0xfff00000;
+  const double m = hb_make(hi - top + 0x3ff00000, lo);      // d / 2^e in [1 - 2^-11, 2 - 2^-10)
+  double invc, l2c;
+  hb_ld_clog(T, (hr >> (16 - HB_CHAIN_LOG_BITS)) & ((HB_CHAIN_LOG_N - 1) << 4), invc, l2c);
+  const double r = fma(m, invc, -1.0);
+  const double r2 = r * r;
+  const double rl = r * HB_CLIT(HB_C_L1);
+  // log1p(r)/ln2 = r/ln2 + r^2*(-1/2 + r/3 - r^2/4)/ln2
+  double q = fma(r, HB_CLIT(HB_C_L4), HB_CLIT(HB_C_L3));
+  q = fma(q, r, HB_CLIT(HB_C_L2));
+  const double tail = fma(r2, q, rl);
+  const double de = (double)((hr >> 20) - 1023);
+  const double base = fma(y, l2c, fma(y, de, c2));          // off the chain: ready before the polynomial
+  t = fma(y, tail, base);
+  // 2^t
+  const double shift = 6755399441055744.0;                  // 1.5 * 2^52
+  const double kd = fma(t, (double)HB_CHAIN_EXP_N, shift);
+  const int ki = hb_lo(kd);
+  const double n = kd - shift;
+  const double s = hb_ld_cexp(T, (ki << 3) & ((HB_CHAIN_EXP_N - 1) << 3));
+  const double f = fma(n, -1.0 / HB_CHAIN_EXP_N, t);        // exact
+  const double f2 = f * f;
+  const double fl = f * HB_CLIT(HB_C_E1);
+  double p = fma(f, HB_CLIT(HB_C_E4), HB_CLIT(HB_C_E3));
+  p = fma(p, f, HB_CLIT(HB_C_E2));
+  p = fma(f2, p, fl);                                       // 2^f - 1
+  const double v = fma(s, p, s);
+  return hb_make(hb_hi(v) + ((ki >> HB_CHAIN_EXP_BITS) << 20), hb_lo(v));
+}
+
 }  // namespace hb

@@ -91,6 +91,8 @@ enum ke {
 #define HB_EI_FAST 16      // eligible for the two-kernel fast path: one snow class, no snow limit, every CFlux == 0
 #define HB_EI_SOILONLY 32  // all zones are FIELD or FOREST
 #define HB_EI_COUPLED 64   // like HB_EI_FAST but with CFlux > 0 somewhere: fused kernel (land_kernel_coupled.cuh)
+#define HB_EI_FUSED 128    // HB_EI_FAST hland_96 element of a 32-element group whose zones are all FIELD/FOREST with FC > 0:
+                           // the zone kernel can add the group's zone terms itself (land_kernel_v2.cuh, zone_kernel<…, ZW>)
 #define HB_EI_MODEL_SHIFT 8   // bits 8..9: HB_MODEL_* of the element
 #define HB_EI_MODEL(i) (((i) >> HB_EI_MODEL_SHIFT) & 3)
 

@@ -62,8 +62,15 @@ struct LandV2Dev {
   const double* forcing;
   const double* sinfactor;  // [nt_total]
   const MathTables* tables;
+  const ChainTables* chain_tables;   // RecStep chain (hb_chain_pow2), staged by the hland_96 element kernel
   double* term_a;          // [nt][zmax][E_pad]
   double* term_b;          // [nt][zmax][E_pad]
+  // fused reduction (zone_kernel<…, ZW>): the zone terms of an element are added IN ZONE ORDER inside the zone kernel and
+  // leave it as two sums per element-step — 16 B instead of 16 B per ZONE-step through HBM
+  double* red_a;           // [nt][E_pad] InUZ (Calc_InUZ_V1)
+  double* red_b;           // [nt][E_pad] sum of weight * log(sm/fc) (Calc_ContriArea_V1)
+  const int32_t* gwarps;   // [E_pad/32] zone warps of the 32-element group (max zone count) if the group is fused, else 0
+  int32_t fused;           // this run reduces the fused groups in the zone kernel (they carry HB_EI_FUSED)
   double* qt;              // [nt_window][E_pad], chunk starts at row t_out
   int64_t t_out;
   // optional series (SERIES kernels).  Element level: ABI layout [nt_window][n_elem], written in place.  Zone and
@@ -145,18 +152,56 @@ __device__ __forceinline__ void response_96p(double r, double percmax, double sg
 // MODEL = HB_MODEL_HLAND_96 / _96P / _96C: every instance works on the fast-path elements of its model only (einfo carries
 // the model).  The sibling models share everything up to the soil routine; their zone response (hland_96p: SUZ, SG1;
 // hland_96c: BW1, BW2) replaces the contributing-area factor, needs no pow() and seven more constants (5 blocks per SM).
-template <bool SOIL, bool SERIES, int MODEL>
-__global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOCKS : 5) zone_kernel(const LandV2Dev d) {
+// ZW > 0 (SOIL, no SERIES, hland_96 only): FUSED REDUCTION.  A block is the ZW zone warps of ONE group of 32 consecutive
+// elements (warp k = zone k, lane = element) instead of one zone of 128 elements.  The warps leave the two terms of G
+// consecutive steps in shared memory; then — between two block barriers — 2 G warps add them per element in ZONE ORDER
+// (the reference's order of additions in Calc_InUZ_V1 / Calc_ContriArea_V1, same bits as the element kernel's loop over
+// the term buffers), one thread per (step, sum, element), and store two sums per element-step.  HBM traffic of the
+// hand-over: 16 B per element-step instead of 2 x 16 B per zone-step.  (Measured: a barrier and a reduction every step
+// — two warps adding while the others run ahead into the next barrier — cost the zone kernel 30 %; every G = 4 steps 2 %.)
+template <int ZW> struct ZoneGeom {
+  static constexpr int threads = ZW > 0 ? ZW * 32 : 128;
+  static constexpr int blocks = ZW > 0 ? (24 / ZW > 0 ? 24 / ZW : 1) : HB_ZONE_BLOCKS;
+  static constexpr int G = ZW == 6 ? 3 : 4;      // steps per reduction (shared memory: ZW*32*(224 + 16 G) bytes per block)
+};
+template <bool SOIL, bool SERIES, int MODEL, int ZW = 0>
+__global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND_96 ? ZoneGeom<ZW>::blocks : 5) zone_kernel(const LandV2Dev d) {
+  static_assert(ZW == 0 || (SOIL && !SERIES && MODEL == HB_MODEL_HLAND_96), "fused reduction: branch-free hland_96 step only");
+  constexpr int NTH = ZoneGeom<ZW>::threads;
   __shared__ MathTables s_tables;
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
   const int64_t ep = d.e_pad;
-  const int k = (int)(blockIdx.x / (unsigned)d.slab_blocks);
-  const int64_t e = d.e_lo + (int64_t)(blockIdx.x - (unsigned)k * (unsigned)d.slab_blocks) * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int k, gw = 0;          // zone index; fused: zone warps of this group
+  int64_t e;
+  if (ZW > 0) {
+    const int64_t g = d.e_lo / 32 + blockIdx.x;
+    gw = d.gwarps[g];
+    k = threadIdx.x >> 5;
+    e = g * 32 + lane;
+    if (k >= gw) return;                  // group not fused (gw = 0), or a warp beyond its zone counts: whole warps leave
+  } else {
+    k = (int)(blockIdx.x / (unsigned)d.slab_blocks);
+    e = d.e_lo + (int64_t)(blockIdx.x - (unsigned)k * (unsigned)d.slab_blocks) * 128 + threadIdx.x;
+  }
+  // fused: the lanes of a live warp stay for the block barriers; `active` lanes own a zone.  A lane without a zone (its
+  // element has fewer zones than the group's largest, or lies beyond the basin) shadows zone 0 of its element (of the
+  // group's first element): the same instructions on valid data, nothing stored — cheaper than a branch around the step,
+  // which costs ~25 register moves per step at its join.  (The warp votes of the step only choose between code paths
+  // with identical results, so shadows cannot change a bit.)
+  const int nz_e = (ZW > 0) ? ((e < d.n_elem) ? d.nz[e] : 0) : 0;
+  const bool active = (ZW > 0) ? (k < nz_e) : true;
+  const int64_t e_own = e;
+  if (ZW > 0 && !active) { if (e >= d.n_elem) e = e - lane; k = 0; }
   const int64_t slot = (int64_t)k * ep + e;   // k*E_pad + e
-  if (e >= d.n_elem) return;
+  if (ZW == 0) {
+    if (e >= d.n_elem) return;
+    const int einfo0 = d.einfo[e];
+    if (!(einfo0 & HB_EI_FAST) || HB_EI_MODEL(einfo0) != MODEL || k >= d.nz[e]) return;
+    if (d.fused && (einfo0 & HB_EI_FUSED)) return;   // reduced by the fused instance of this run
+  }
   const int einfo = d.einfo[e];
-  if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL || k >= d.nz[e]) return;
 
   const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
 #define KZ(name) kzk[(int64_t)(name) * ep]
@@ -195,7 +240,11 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
   // instead of 128, 7 instead of 4 warps per scheduler, and room for the routing blocks of the previous window beside them.
   // (ncu: the step is then issue-bound — ≈410 warp instructions per zone-step at ≈80 % issue-slot utilisation.)
   // (constants that are used together share a 16-byte slot: one LDS.128 fetches both)
-  __shared__ double2 s_c[(MODEL == HB_MODEL_HLAND_96 ? 28 : 36) / 2][128];
+  extern __shared__ double2 s_dyn[];      // fused: constants [14][NTH] + term buffers [2][2][ZW][32] doubles
+  __shared__ double2 s_static[ZW > 0 ? 1 : (MODEL == HB_MODEL_HLAND_96 ? 28 : 36) / 2][ZW > 0 ? 1 : 128];
+  double2 (*const s_c)[NTH] = ZW > 0 ? reinterpret_cast<double2 (*)[NTH]>(s_dyn) : reinterpret_cast<double2 (*)[NTH]>(s_static);
+  double* const s_terms = reinterpret_cast<double*>(s_dyn + 14 * NTH);   // (fused only) [G][2][ZW][32]
+  constexpr int G = ZoneGeom<ZW>::G;
   if (MODEL != HB_MODEL_HLAND_96) {
     s_c[14][threadIdx.x].x = KZX(KZ_X0); s_c[14][threadIdx.x].y = KZX(KZ_X1); s_c[15][threadIdx.x].x = KZX(KZ_X2);
     s_c[15][threadIdx.x].y = KZX(KZ_X3); s_c[16][threadIdx.x].x = KZX(KZ_X4); s_c[16][threadIdx.x].y = KZX(KZ_X5);
@@ -287,8 +336,9 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
     fP += fstride; fT += fstride; fA += fstride; fE += fstride; ++sinp;                                          \
     n_p = ldg(fP); n_t = ldg(fT); n_nat = ldg(fA); n_net = ldg(fE); n_sin = ldg(sinp);                           \
   }
-#define HB_ZONE_STEP_END(va, vb) \
-  *out_a = (va); *out_b = (vb); out_a += tstride; out_b += tstride;
+#define HB_ZONE_STEP_END(va, vb)                                                                   \
+  if (ZW > 0) { s_terms[tb_off + zw_off] = (va); s_terms[tb_off + ZW * 32 + zw_off] = (vb); }       \
+  else { *out_a = (va); *out_b = (vb); out_a += tstride; out_b += tstride; }
   const int nt = (int)d.nt;
 #define SERZ(id, v) do { if (SERIES && d.series[id]) d.series[id][(int64_t)t * tstride + slot] = (v); } while (0)
 #define SERS(id, v) SERZ(id, v)
@@ -298,8 +348,12 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
   // the same bit for bit (x - 0.0 == x, x * 1 == x …); the point is one large basic block in which the scheduler can
   // interleave the independent chains (snow, exp of PET, pow of R, pow of ContriArea) — with 4 warps per scheduler the
   // kernel is latency-bound otherwise (ncu: 62 % issue utilisation, half of the stall cycles are fixed-latency waits).
-  const unsigned amask = __activemask();
-  if (__all_sync(amask, soil && fc > 0.0) != SOIL) return;
+  const unsigned amask = __activemask();                                             // (fused: all 32 lanes)
+  const unsigned omask = ZW > 0 ? __ballot_sync(0xffffffffu, active) : amask;         // lanes that own a zone
+  if (ZW == 0 && __all_sync(amask, soil && fc > 0.0) != SOIL) return;
+  // fused: offsets into the term buffers [G][2][ZW][32]
+  const int zw_off = (int)(threadIdx.x >> 5) * 32 + lane;   // (a shadow lane writes its own, never read, cell)
+  int tb_off = 0, gs = 0;
   if (SOIL) {
     const bool f_icept = (zf & HB_ZF_INTERCEPTION) != 0, f_soil = (zf & HB_ZF_SOIL) != 0;
     // hland_96: log(sm/fc) of the soil moisture at the end of a step serves the contributing area of that step AND the
@@ -383,7 +437,7 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         // is in_ itself — 0.0 times a finite power (0 < sm/fc <= 1) — and the exp half of the power function can stay out
         const double x = sm * inv_fc;
         const unsigned none = __ballot_sync(amask, in_ == 0.0);   // (in_ >= 0 or NaN: every other lane counts as wet)
-        n_wet += __popc(amask ^ none);
+        n_wet += __popc(omask & ~none);
         if (none == amask && __all_sync(amask, x > 0.0 && x <= 1.0)) { r = in_; ++n_dry; }
         else r = in_ * hb_pow_from_log(x, lgn, beta, T);
       } else r = in_ * hb_pow(sm * inv_fc, beta, T);
@@ -447,13 +501,40 @@ __global__ void __launch_bounds__(128, MODEL == HB_MODEL_HLAND_96 ? HB_ZONE_BLOC
         qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
         HB_ZONE_STEP_END(w_a * (qab1 + qab2), w_b * qvs2)
       }
+      if (ZW > 0) {
+        tb_off += 2 * ZW * 32;
+        if (++gs == G || t == nt - 1) {
+          // every lane of every live warp: the terms of the last gs steps are complete
+          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"r"(gw * 32) : "memory");
+          // warp w2 < 2 gs: step w2 / 2 of the batch, sum w2 & 1 (0: Calc_InUZ_V1, ref: hland_model.py:2092-2101; 1: the
+          // weighted logarithms of Calc_ContriArea_V1, :2224-2236), lane = element, zones in their order
+          for (int w2 = (int)(threadIdx.x >> 5); w2 < 2 * gs; w2 += gw) {
+            const double* src = s_terms + (w2 >> 1) * (2 * ZW * 32) + (w2 & 1) * (ZW * 32) + lane;
+            double sum = 0.0;
+            if (__all_sync(0xffffffffu, nz_e == ZW)) {   // the usual case: all look-ups in flight at once
+              double v[ZW > 0 ? ZW : 1];
+#pragma unroll
+              for (int kk = 0; kk < ZW; ++kk) v[kk] = src[kk * 32];
+#pragma unroll
+              for (int kk = 0; kk < ZW; ++kk) sum += v[kk];
+            } else
+              for (int kk = 0; kk < nz_e; ++kk) sum += src[kk * 32];
+            if (e_own < d.n_elem) ((w2 & 1) ? d.red_b : d.red_a)[(int64_t)(t + 1 - gs + (w2 >> 1)) * ep + e_own] = sum;
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(gw * 32) : "memory");   // the buffers are free again
+          gs = 0;
+          tb_off = 0;
+        }
+      }
     }
+    if (ZW > 0 && !active) return;
     d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
     if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
-    if (MODEL == HB_MODEL_HLAND_96 && d.counters && (threadIdx.x & 31) == __ffs(amask) - 1) {
+    if (MODEL == HB_MODEL_HLAND_96 && d.counters && (threadIdx.x & 31) == __ffs(omask) - 1) {
       atomicAdd(d.counters + HB_CNT_ZONE_WARPSTEPS, (unsigned long long)nt);
       atomicAdd(d.counters + HB_CNT_ZONE_WARPSTEPS_DRY, (unsigned long long)n_dry);
-      atomicAdd(d.counters + HB_CNT_ZONE_STEPS, (unsigned long long)nt * __popc(amask));
+      atomicAdd(d.counters + HB_CNT_ZONE_STEPS, (unsigned long long)nt * __popc(omask));
       atomicAdd(d.counters + HB_CNT_ZONE_STEPS_WET, (unsigned long long)n_wet);
     }
     return;
@@ -716,26 +797,45 @@ __global__ void __launch_bounds__(256) series_scatter_kernel(const double* __res
 // ---------------------------------------------------------------------------------------------------------------------
 // element kernel: ordered zone sums + Calc_Q0_Perc_UZ_V1 … Calc_QT_V1
 // ---------------------------------------------------------------------------------------------------------------------
+// rconc_uh (ref: hydpy/models/rconc/rconc_model.py:89-95 Determine_Outflow_V1) with the element's `quh` resident in shared
+// memory ([ordinate][thread], 64 threads per block) for the whole launch: the per-step loads of the global copy wait for
+// the L2 (stores bypass the L1), a quarter of the element kernel's stall cycles once the zone sums arrive ready-made
+__device__ __forceinline__ double uh_outflow_staged(const double* __restrict__ uh, int64_t ep, int64_t e, int nu,
+                                                    double inrc, double* s_q) {
+  const double outrc = ldg(uh + e) * inrc + s_q[0];
+  for (int j = 1; j < nu; ++j) s_q[(j - 1) * 64] = ldg(uh + (int64_t)j * ep + e) * inrc + s_q[j * 64];
+  return outrc;
+}
+
 #ifndef HB_ELEM_PREFETCH
 #define HB_ELEM_PREFETCH 1
 #endif
 #ifndef HB_ELEM_BLOCKS
 #define HB_ELEM_BLOCKS 12
 #endif
-template <bool SERIES, int MODEL>
+// FUSED: the elements whose zone terms were added inside the zone kernel (HB_EI_FUSED in a run with d.fused): two sums per
+// step arrive instead of two terms per zone
+template <bool SERIES, int MODEL, bool FUSED = false>
 __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV2Dev d) {
+  static_assert(!FUSED || (!SERIES && MODEL == HB_MODEL_HLAND_96), "fused reduction: hland_96 without series only");
   __shared__ MathTables s_tables;
   extern __shared__ double s_sc_dyn[];   // rconc_nash cascade of the block's elements, [storage][thread]; only allocated
   double* const s_sc = d.nash_stage ? s_sc_dyn : nullptr;   // (launch parameter) when some element has a cascade
+  if (MODEL == HB_MODEL_HLAND_96) hb_chain_stage(d.chain_tables);   // (before the barrier of stage_tables)
   stage_tables(&s_tables, d.tables);
   const TabRef T = hb_tabref(&s_tables);
+  const ChainRef CT = hb_chainref(nullptr);
   const int64_t e = d.e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.n_elem || e >= d.e_lo + (int64_t)d.slab_blocks * 128) return;
   const int einfo = d.einfo[e];
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
+  if (((einfo & HB_EI_FUSED) != 0 && d.fused != 0) != FUSED) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
+  const bool uh_smem = s_sc != nullptr && nash_steps == 0 && nu > 0 && nu <= HB_NASH_STAGE;
+  if (uh_smem)
+    for (int j = 0; j < nu; ++j) s_sc[threadIdx.x + j * 64] = d.quh[(int64_t)j * ep + e];
   const double dt = d.ke[KE_DT * ep + e], dt_percmax = d.ke[KE_DT_PERCMAX * ep + e], dt_k = d.ke[KE_DT_K * ep + e],
                alpha1 = d.ke[KE_ALPHA1 * ep + e], k4 = d.ke[KE_K4 * ep + e], gamma1 = d.ke[KE_GAMMA1 * ep + e],
                relupper = d.ke[KE_RELUPPER * ep + e], rellower = d.ke[KE_RELLOWER * ep + e],
@@ -743,6 +843,11 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
                beta_last = d.ke[KE_BETA_LAST * ep + e];
   const bool resp = (einfo & HB_EI_RESPAREA) != 0, soilonly = (einfo & HB_EI_SOILONLY) != 0;
   const bool square = (alpha1 == 2.0);
+  // RecStep chain in its short form (recstep_chain below): log2(dt*k) once per thread; the form needs a positive normal
+  // dt*k and a finite exponent, everything else keeps the general loop
+  // (the bounds make an out-of-range argument of the power function visible in its exponent, see hb_chain_pow2)
+  const bool chain_ok = MODEL == HB_MODEL_HLAND_96 && dt_k >= 1e-30 && dt_k <= 1e20 && alpha1 >= 1.0 && alpha1 <= 64.0;
+  const double log2_dtk = chain_ok ? log2(dt_k) : 0.0;
   double uz = d.uz[e], lz = d.lz[e];
   double sg2 = 0.0, sg3 = 0.0;
   if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
@@ -750,13 +855,15 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   unsigned n_run = 0, n_pow = 0;   // element-steps that ran the RecStep chain, sub-steps with uz > 0
   unsigned n_wrun = 0;             // (warp-uniform) steps in which some lane of the warp ran it
   const unsigned emask = __activemask();
+  double nx_a = 0.0, nx_b = 0.0;    // FUSED: the sums of the next step, loaded one step ahead
+  if (FUSED && d.nt > 0) { nx_a = ldg(d.red_a + e); nx_b = ldg(d.red_b + e); }
   for (int64_t t = 0; t < d.nt; ++t) {
-    const double* ta = d.term_a + t * tstride + e;
-    const double* tb = d.term_b + t * tstride + e;
+    const double* ta = FUSED ? nullptr : d.term_a + t * tstride + e;
+    const double* tb = FUSED ? nullptr : d.term_b + t * tstride + e;
 #if HB_ELEM_PREFETCH
     // the terms of the NEXT step are pulled towards the SM while the RecStep loop of this step runs (they were written
     // by the zone kernel gigabytes ago, i.e. they come from HBM); costs no registers
-    if (t + 1 < d.nt)
+    if (!FUSED && t + 1 < d.nt)
       for (int k = 0; k < nz; ++k) {
 #if HB_ELEM_PREFETCH == 1
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ta + tstride + (int64_t)k * ep));
@@ -819,7 +926,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
+      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+                                 : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
       continue;
     }
@@ -830,7 +938,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
+      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+                                 : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       // ref: hland_model.py:3172-3181 Calc_LZ_V2 (tb = weight * pc | weight * qvs2)
       for (int k = 0; k < nz; ++k) {
         if (!soilonly && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) continue;
@@ -850,7 +959,10 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       continue;
     }
     double inuz = 0.0, contriarea = 1.0, logsum = 0.0;   // logsum: sum of weight * log(sm/fc) over the soil zones
-    if (soilonly) {
+    if (FUSED) {
+      inuz = nx_a; logsum = nx_b;
+      if (t + 1 < d.nt) { nx_a = ldg(d.red_a + (t + 1) * ep + e); nx_b = ldg(d.red_b + (t + 1) * ep + e); }
+    } else if (soilonly) {
       for (int k = 0; k < nz; ++k) {
         inuz += ta[(int64_t)k * ep];
         logsum += tb[(int64_t)k * ep];
@@ -874,25 +986,68 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       const double uz_old = uz;
       const double dt_inuz = dt * inuz;
       const double perc_pot = dt_percmax * contriarea;
-      const double inv_ca = 1.0 / contriarea;
-      // every instruction of this loop sits on one dependent chain (ncu: ≈9.5 cycles per instruction), so the loop is
-      // unswitched on its step-invariant conditions when the whole warp agrees on them — the usual case
-      if (__all_sync(__activemask(), contriarea > 0.0 && !square)) {
-        for (int i = 0; i < recstep; ++i) {
-          const double a = uz + dt_inuz;
-          uz = HB_PYMAX(a, 0.0);
-          const double perc = HB_PYMIN(perc_pot, uz);
-          uz -= perc;
-          perc_sum += perc;
-          if (uz > 0.0) {
-            const double q = dt_k * hb_pow(uz * inv_ca, alpha1, T);
-            const double q0 = HB_PYMIN(q, uz);
-            uz -= q0;
-            q0_sum += q0;
-            ++n_pow;
+      // The loop below is the reference's; every instruction of it sits on one dependent chain.  Three exact or
+      // (power function only) 1e-14-equivalent forms take its place where an element's OWN data allow — the choice never
+      // depends on the warp neighbours, so an element's bits do not depend on where it is placed:
+      //  * with uz >= 0 and recharge >= 0, `max(uz + dt*inuz, 0)` is the sum itself, and percolation + outflow become
+      //    d = a - perc_pot; perc = d > 0 ? perc_pot : a;  u = d - q; q0 = u < 0 ? d : q;  uz = u > 0 ? u : 0
+      //    (the same values: x < y <=> x - y < 0 in IEEE arithmetic with gradual underflow);
+      //  * the power function runs on d whether or not d > 0 (no branch on the chain; lanes without outflow drop the
+      //    garbage), as 2^(y*log2(d) + c2) with the step-invariant factors folded into c2 (hb_chain_pow2);
+      //  * a quadratic response (alpha = 1, the Lahn default) needs no power function at all: exact.
+      const bool lane_plain = chain_ok && uz >= 0.0 && uz <= 1e300 && dt_inuz >= 0.0 && dt_inuz <= 1e300 &&
+                              perc_pot >= 0.0 && perc_pot <= 1e300 && contriarea >= 1e-30 && contriarea <= 2.0;
+      bool redo = !lane_plain;
+      if (lane_plain) {
+        // (whole warp) no sub-step leaves water for the outflow: uz + dt*inuz <= perc_pot now, and dt*inuz <= perc_pot
+        // from then on because every sub-step empties the storage — percolation takes everything, 50 additions remain
+        if (__all_sync(__activemask(), uz + dt_inuz <= perc_pot)) {
+          perc_sum = uz + dt_inuz;
+          for (int i = 1; i < recstep; ++i) perc_sum += dt_inuz;
+          uz = 0.0;
+        } else if (square) {
+          const double inv_ca = 1.0 / contriarea;
+          double a = uz + dt_inuz, u = 0.0;
+          bool pos = false;
+          for (int i = 0; i < recstep; ++i) {
+            const double dd = a - perc_pot;
+            const bool p = dd > 0.0;
+            perc_sum += p ? perc_pot : a;
+            const double x = dd * inv_ca;
+            const double q = dt_k * (x * x);
+            u = dd - q;
+            pos = p && (u > 0.0);
+            if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
+            n_pow += p ? 1u : 0u;
+            a = pos ? u + dt_inuz : dt_inuz;
           }
+          uz = pos ? u : 0.0;
+        } else {
+          // c2 = log2(dt*k) - y*log2(contriarea); ln(contriarea) = beta*logsum is what contriarea was made from
+          const double c2 = resp ? fma(-alpha1 * HB_CLIT(HB_C_L1), beta_last * logsum, log2_dtk) : log2_dtk;
+          double a = uz + dt_inuz, u = 0.0;
+          bool pos = false, bad = false;
+          unsigned np_ = 0;
+          for (int i = 0; i < recstep; ++i) {
+            const double dd = a - perc_pot;
+            const bool p = dd > 0.0;
+            perc_sum += p ? perc_pot : a;
+            double tq;
+            const double q = hb_chain_pow2(dd, alpha1, c2, CT, tq);
+            bad |= p && !(fabs(tq) < 800.0);
+            u = dd - q;
+            pos = p && (u > 0.0);
+            if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
+            np_ += p ? 1u : 0u;
+            a = pos ? u + dt_inuz : dt_inuz;
+          }
+          uz = pos ? u : 0.0;
+          if (bad) { redo = true; uz = uz_old; perc_sum = 0.0; q0_sum = 0.0; }   // out-of-range power: general loop
+          else n_pow += np_;
         }
-      } else {
+      }
+      if (redo) {
+        const double inv_ca = 1.0 / contriarea;
         for (int i = 0; i < recstep; ++i) {
           const double a = uz + dt_inuz;
           uz = HB_PYMAX(a, 0.0);
@@ -939,7 +1094,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       for (int k = 0; k < nz; ++k)
         if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-    const double outrc = rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
+    const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+                                 : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
     if (SERIES) record_sc(d.series[HB_S_SC], d.t_out + t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1
     const double qt = qfactor * outrc;
@@ -954,6 +1110,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   }
   d.uz[e] = uz;
   d.lz[e] = lz;
+  if (uh_smem)
+    for (int j = 0; j < nu; ++j) d.quh[(int64_t)j * ep + e] = s_sc[threadIdx.x + j * 64];
   if (MODEL == HB_MODEL_HLAND_96P) { d.ex1[e] = sg2; d.ex2[e] = sg3; }
   if (MODEL == HB_MODEL_HLAND_96 && d.counters) {
     const unsigned m = __activemask();

@@ -347,6 +347,10 @@ class Engine:
         """Element slabs (streams) of the fast runoff-generation path, 1..8 (performance only; same results)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_SLABS, int(slabs)), "hb_set_option")
 
+    def set_land_fuse(self, on: bool) -> None:
+        """Zone terms added inside the thread-per-zone kernel where a 32-element group allows (default on; same results)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_FUSE, 1 if on else 0), "hb_set_option")
+
     def set_land_chunk(self, steps: int) -> None:
         """Time chunk of the fast runoff-generation path in steps (0 = as long as the scratch memory allows; -1 = the engine's default)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_CHUNK, int(steps)), "hb_set_option")

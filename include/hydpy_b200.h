@@ -330,6 +330,11 @@ int hb_select_series(hb_engine* h, int series, int on);
  * else 0): time chunk of the fast path.  Shorter kernels let kernels that need a whole CTA slot (the NCCL hand-over of the
  * boundary rows) onto the SMs sooner. */
 #define HB_OPT_LAND_CHUNK 6
+/* HB_OPT_LAND_FUSE (0 | 1, default 1): where every zone of a group of 32 consecutive elements runs the branch-free
+ * FIELD/FOREST step (and no land series is selected), the thread-per-zone kernel adds the zone terms of Calc_InUZ_V1 /
+ * Calc_ContriArea_V1 itself — in zone order, i.e. the same bits — and hands two sums per element-step to the
+ * thread-per-element kernel instead of two terms per zone-step.  0 keeps the term buffers (development, A/B timing). */
+#define HB_OPT_LAND_FUSE 7
 enum hb_mct_series {
   HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
   HB_MS_CORRECTINGFACTOR, HB_MS_COEFFICIENT1, HB_MS_COEFFICIENT2, HB_MS_COEFFICIENT3, HB_MS_COURANTNUMBER,

@@ -10,14 +10,19 @@ from hydpy_b200.abi import LandBundle, LandStates, RiverBundle
 
 
 def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recstep: int = 20, bank: int | None = None,
-                snowlimit_fraction: float = 0.3, fast_fraction: float = 0.4) -> tuple[LandBundle, LandStates]:
+                snowlimit_fraction: float = 0.3, fast_fraction: float = 0.4, soil_runs: int = 0
+                ) -> tuple[LandBundle, LandStates]:
     """`fast_fraction` of the elements get one snow class, CFlux = 0 and SMax = inf, i.e. they qualify for the engine's
-    two-kernel fast path (all zone types still occur); the others exercise the general kernel."""
+    two-kernel fast path (all zone types still occur); the others exercise the general kernel.  `soil_runs` > 0: every
+    other run of that many consecutive elements is fast with FIELD/FOREST zones and FC > 0 only (ragged zone counts) —
+    the 32-element groups inside such runs qualify for the reduction inside the zone kernel."""
     rng = np.random.default_rng(seed)
     ne = n_elem
     nz = rng.integers(1, zmax + 1, size=ne)
     nc = rng.integers(1, cmax + 1, size=ne)
     fast = np.random.default_rng(seed + 4242).uniform(size=ne) < fast_fraction
+    in_run = ((np.arange(ne) // soil_runs) % 2 == 0) if soil_runs > 0 else np.zeros(ne, bool)
+    fast |= in_run
     nc[fast] = 1
     nu = rng.integers(0, 6, size=ne)
     zone_ptr = np.concatenate([[0], np.cumsum(nz)]).astype(np.int64)
@@ -26,6 +31,8 @@ def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recst
     uh_ptr = np.concatenate([[0], np.cumsum(nu)]).astype(np.int64)
     NZ = int(zone_ptr[-1])
     zonetype = rng.choice([1, 2, 3, 4, 5], size=NZ, p=[0.35, 0.35, 0.1, 0.1, 0.1]).astype(np.int32)
+    run_zone = np.repeat(in_run, nz)
+    zonetype = np.where(run_zone, 1 + (np.arange(NZ) + seed) % 2, zonetype).astype(np.int32)
     ZP, EP = layout.ZP, layout.EP
     zpar = np.zeros((len(layout.ZPAR), NZ))
     U = lambda lo, hi, n=NZ: rng.uniform(lo, hi, size=n)  # noqa: E731
@@ -36,6 +43,7 @@ def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recst
     zpar[ZP["ttm"]] = zpar[ZP["tt"]] + U(-0.5, 0.5); zpar[ZP["cfmax"]] = U(0.05, 0.3); zpar[ZP["cfvar"]] = U(0, 0.05)
     zpar[ZP["gmelt"]] = U(0.05, 0.3); zpar[ZP["gvar"]] = U(0, 0.05); zpar[ZP["cfr"]] = U(0, 0.1)
     zpar[ZP["whc"]] = U(0, 0.3); zpar[ZP["fc"]] = np.where(rng.uniform(size=NZ) < 0.03, 0.0, U(50, 300))
+    zpar[ZP["fc"]] = np.where(run_zone & (zpar[ZP["fc"]] == 0.0), 120.0, zpar[ZP["fc"]])
     zpar[ZP["beta"]] = U(1, 4); zpar[ZP["cflux"]] = np.where(rng.uniform(size=NZ) < 0.5, 0.0, U(0, 0.05))
     zpar[ZP["temperaturethresholdice"]] = np.where(rng.uniform(size=NZ) < 0.3, np.nan, U(-1, 1))
     zpar[ZP["maxsoilwater"]] = np.maximum(zpar[ZP["fc"]], 1.0); zpar[ZP["soilmoisturelimit"]] = U(0.5, 1.0)

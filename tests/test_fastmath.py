@@ -109,3 +109,35 @@ def test_log_special_cases_and_contributing_area_identity(fm):
     ref = np.prod(np.power(ratio.astype(np.longdouble), w.astype(np.longdouble)), axis=1) ** beta.astype(np.longdouble)
     rel = np.abs((got - ref) / ref).astype(np.float64)
     assert rel.max() < 1e-14, rel.max()
+
+
+def test_recstep_chain_pow(fm):
+    """`hb_chain_pow2`, the base-2 power function of the RecStep chain (Calc_Q0_Perc_UZ_V1): dt*k*(uz/contriarea)^(1+alpha)
+    over the model's ranges within 2e-14 of extended precision; out-of-range arguments are flagged, never trusted."""
+    rng = np.random.default_rng(4)
+    n = 400_000
+    d = np.concatenate([np.exp(rng.uniform(-30, 8, n // 2)), rng.uniform(1e-6, 200.0, n // 2)])   # uz [mm]
+    y = rng.uniform(1.0, 4.0, n)                        # 1 + alpha
+    dtk = np.exp(rng.uniform(-14, 0, n))                # k / recstep
+    ca = np.exp(rng.uniform(-12, 0, n))                 # contributing area (0, 1]
+    out, rel = np.zeros(n), np.zeros(n)
+    ok = np.zeros(n, np.int32)
+    fm.fm_chain(p(d), p(y), p(dtk), p(ca), p(out), p(rel), ok.ctypes.data_as(C.POINTER(C.c_int)), n)
+    assert ok.all()
+    # the exponent log2(q) is accumulated in one double (like hb_pow's): c2 and the partial sums round at the magnitude
+    # of their terms, the table/polynomial steps add about 4 ulp
+    t = np.abs(np.log2(dtk)) + y * np.abs(np.log2(ca)) + y * np.abs(np.log2(d))
+    bound = 2.3e-16 * (4.0 + 1.5 * t)
+    assert np.all(rel <= bound), (rel.max(), (rel / bound).max())
+    typical = (d > 1e-3) & (ca > 0.01)                          # what the model produces
+    assert rel[typical].max() < 2e-14, rel[typical].max()
+    print("chain pow: max rel err %.3e, median %.3e" % (rel.max(), np.median(rel)))
+    # flagged: zero, negative, subnormal, inf, nan arguments and exponents beyond +-1000
+    d = np.array([0.0, -1.0, 1e-310, np.inf, np.nan, 1e300, 1e-300, 1.0])
+    y = np.array([2.0, 2.0, 2.0, 2.0, 2.0, 4.0, 4.0, 2.0])
+    dtk = np.full(8, 0.01); ca = np.full(8, 0.5)
+    out, rel = np.zeros(8), np.zeros(8)
+    ok = np.ones(8, np.int32)
+    fm.fm_chain(p(d), p(y), p(dtk), p(ca), p(out), p(rel), ok.ctypes.data_as(C.POINTER(C.c_int)), 8)
+    assert list(ok) == [0, 0, 0, 0, 0, 0, 0, 1]
+    assert out[7] == pytest.approx(0.04, rel=1e-15)

@@ -555,6 +555,86 @@ def test_sixty_four_parameter_sets_in_one_run_equal_sequential_oracle_runs():
     assert np.ptp(ref_nse[:, 0]) > 1e-3            # the sets really differ
 
 
+@pytest.mark.parametrize("case", ["synthetic", "ragged"])
+def test_zone_terms_added_inside_the_zone_kernel_give_the_same_bits(case):
+    """HB_OPT_LAND_FUSE: groups of 32 consecutive elements whose zones all run the branch-free step have their zone terms
+    added inside the thread-per-zone kernel (in zone order) instead of the thread-per-element kernel.  Same bits as the
+    hand-over through the term buffers, for mixed basins (fused and other groups side by side), ragged zone counts,
+    element slabs and time chunks; and the same values as the oracle."""
+    if case == "synthetic":
+        ne, nt = 4200, 60
+        land, states = synth.make_land(ne, "1h", variants=True, seed=5)
+        forcing, doy = synth.make_forcing(nt, "1h", t0=2000)
+    else:
+        ne, nt = 700, 48
+        land, states = random_land(ne, seed=11, zmax=12, bank=64, soil_runs=70)
+        forcing, doy = random_forcing(nt, 64, seed=3)
+    from hydpy_b200.abi import RiverBundle
+
+    out = []
+    with Engine(0) as eng:
+        for fuse, slabs, chunk in ((False, 1, 0), (True, 1, 0), (True, 3, 7)):
+            eng.set_land(land)
+            eng.set_land_states(states)
+            eng.set_river(RiverBundle.empty(0))
+            eng.set_land_fuse(fuse)
+            eng.set_land_slabs(slabs)
+            eng.set_land_chunk(chunk)
+            eng.set_forcing(forcing, doy)
+            eng.run(land=True, river=False)
+            out.append((eng.get_land_outflow(), eng.get_land_states(), eng.timing()))
+    q0, s0, _ = out[0]
+    assert np.isfinite(q0).all() and q0.max() > 0.0
+    for q, s, tm in out[1:]:
+        assert np.array_equal(q0, q)
+        for n in s0.NAMES:
+            assert np.array_equal(getattr(s0, n), getattr(s, n)), n
+    st = states.copy()
+    qt, _ = oracle.land_run(land, st, forcing, doy, threads=4)
+    assert_close(q0, qt, f"{case}: land outflow")
+    for n in st.NAMES:
+        assert_close(getattr(s0, n), getattr(st, n), f"{case}: final {n}")
+
+
+def test_recstep_chain_with_out_of_range_power_arguments():
+    """The short form of the RecStep chain evaluates dt*k*(uz/contriarea)^(1+alpha) as 2^(y*log2(uz) + c2) for exponents
+    below 800 in magnitude; beyond that (here: tiny storages under exponents up to 64, huge ones under large exponents)
+    and for parameters outside its bounds the element repeats the step with the general loop — same values as the oracle."""
+    from hydpy_b200.abi import RiverBundle
+
+    ne, nt = 256, 30
+    land, states = synth.make_land(ne, "1h", seed=9)
+    EP = layout.EP
+    rng = np.random.default_rng(5)
+    # (steep responses only with tiny rate constants: dt*k*(uz/ca)^41 near uz/ca = 1 makes the explicit sub-steps unstable —
+    # the last bits of ANY power function then decide the result, the reference's included)
+    alpha = rng.choice([0.0, 0.5, 1.0, 3.0, 20.0, 40.0, 63.0, 70.0], size=ne)
+    land.epar[EP["alpha"]] = alpha
+    land.epar[EP["k"]] = np.where(alpha > 3.0, rng.choice([1e-40, 1e-12], size=ne), rng.choice([1e-40, 1e-12, 1e-3, 0.05], size=ne))
+    states.uz[:] = rng.choice([0.0, 1e-300, 1e-200, 1e-12, 1e-3, 5.0, 1e4, 1e30], size=ne)
+    forcing, doy = synth.make_forcing(nt, "1h", t0=3000)
+    # ... and no recharge for them: a steep response under strong recharge settles where (1 + alpha) * q0 > 2 * uz per
+    # sub-step, i.e. where the explicit scheme oscillates, whatever the rate constant
+    forcing[0][:, np.unique(land.forcing_col[alpha > 3.0])] = 0.0
+    states.sp[:] = 0.0
+    states.wc[:] = 0.0
+    with Engine(0) as eng:
+        eng.set_land(land)
+        eng.set_land_states(states)
+        eng.set_river(RiverBundle.empty(0))
+        eng.set_forcing(forcing, doy)
+        eng.run(land=True, river=False)
+        q, st_e = eng.get_land_outflow(), eng.get_land_states()
+        tm = eng.timing()
+    assert 0 < tm["elem_steps_run"] < tm["elem_steps"]
+    st = states.copy()
+    qt, _ = oracle.land_run(land, st, forcing, doy, threads=4)
+    assert np.isfinite(qt).all()
+    assert_close(q, qt, "extreme response parameters: land outflow")
+    for n in st.NAMES:
+        assert_close(getattr(st_e, n), getattr(st, n), f"extreme response parameters: final {n}")
+
+
 def test_results_do_not_depend_on_where_an_element_sits():
     """The fast path groups 32 consecutive elements into warps and lets warp-wide votes pick between equivalent code paths
     (branch-free or general zone step, dry shortcuts, unswitched RecStep loop).  Shuffling the elements — what sharding a

@@ -25,6 +25,8 @@ ap.add_argument("--model", default="hland_96", choices=("hland_96", "hland_96p",
 ap.add_argument("--kind", default="storms", help="forcing kind of synth.make_forcing: storms | dry")
 ap.add_argument("--spinup", type=int, default=0, help="windows simulated (untimed output) before the first rep")
 ap.add_argument("--wave-blocks", type=int, default=0)
+ap.add_argument("--land-slabs", type=int, default=0)
+ap.add_argument("--no-fuse", action="store_true")
 args = ap.parse_args()
 
 t = time.time()
@@ -45,6 +47,10 @@ nbytes = 8 * args.nt * sum(land.n_zone if x in layout.SERIES_ZONE else land.n_sn
 print(f"uploaded in {time.time()-t:.2f}s")
 if args.wave_blocks:
     eng.set_wave_blocks(args.wave_blocks)
+if args.land_slabs:
+    eng.set_land_slabs(args.land_slabs)
+if args.no_fuse:
+    eng.set_land_fuse(False)
 for rep in range(-args.spinup, args.reps):
     forcing, doy = synth.make_forcing(args.nt, args.step, t0=(rep + args.spinup) * args.nt, kind=args.kind)
     t = time.time()
