@@ -191,6 +191,35 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Wait until the progress counter *flag has reached `need`.  Most of a task's life in the persistent wavefront is this
+// loop (ncu, r02a: 83 polls per task, half of the kernel's instructions), and its issue slots are taken from the runoff
+// generation of the next window on the same SMs — so the poll is a relaxed load (an `ld.acquire` per poll also invalidates
+// the SM's L1: CCTL.IVALL, 13 % of the kernel's stall samples), the bookkeeping of the bounded spin runs every 1024th
+// poll, and ONE acquire load of the same counter after the loop orders the reads that follow.  False: spin limit / error.
+#ifndef HB_WAVE_POLL
+#define HB_WAVE_POLL 2
+#endif
+__device__ __forceinline__ bool wait_progress(const int* flag, int need, const int* error) {
+#if HB_WAVE_POLL == 2
+  if (ld_relaxed(flag) < need) {
+    int spins = 0;
+    for (;;) {
+      if (spins >= HB_SPIN_FAST) __nanosleep(HB_SPIN_SLEEP);
+      if (ld_relaxed(flag) >= need) break;
+      if ((++spins & 1023) == 0 && (spins > HB_SPIN_LIMIT || ld_relaxed(error) != 0)) return false;
+    }
+  }
+  (void)ld_acquire(flag);
+  return true;
+#else
+  int spins = 0;
+  while (ld_acquire(flag) < need) {
+    spin_pause(++spins);
+    if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(error) != 0)) return false;
+  }
+  return true;
+#endif
+}
 
 // ---- musk_mct (ref: hydpy/models/musk_mct.py RUN_METHODS; cross section hydpy/models/wq_trapeze_strickler.py) ----------
 // The Muskingum-Cunge-Todini segment update has the data flow of the classic one (new[i], old[i], old[i+1]), so it runs
@@ -418,14 +447,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
   double st_in = 0.0, st_out = 0.0;
   if (WAVE) {
     bool ok = true;
-    int spins = 0;
-    // (measured: relaxed polls + one acquire fence instead of ld.acquire polls do not help here — 4.07 -> 4.46 ms — because
-    // only a few lanes per warp poll; the grouped wavefront below, where every lane has flags of its own, needs them)
-    if (lane == 0)
-      while (ld_acquire(d.progress + r) < c * d.pscale) {
-        spin_pause(++spins);
-        if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
-      }
+    if (lane == 0) ok = wait_progress(d.progress + r, c * d.pscale, d.error);
     if (!__all_sync(full, ok)) return false;
     __syncwarp();     // acquire side: the polling lane's ld.acquire is ordered before every lane's loads below
     if (lane < S) {   // through L2: the previous chunk may have been written by another SM
@@ -433,14 +455,8 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       st_out = __ldcg(dis_old + g0 + lane + 1);
     }
     // same chunk of every feeding reach (lanes over dependencies)
-    for (int p = lane; p < m.n_dep; p += 32) {
-      const int* flag = d.progress + (tp.inline_deps ? tp.dep : d.dep_reach[m.dep0 + p]);
-      spins = 0;
-      while (ld_acquire(flag) < (c + 1) * d.pscale) {
-        spin_pause(++spins);
-        if (spins > HB_SPIN_LIMIT || ((spins & 1023) == 0 && ld_acquire(d.error) != 0)) { ok = false; break; }
-      }
-    }
+    for (int p = lane; p < m.n_dep; p += 32)
+      ok = ok && wait_progress(d.progress + (tp.inline_deps ? tp.dep : d.dep_reach[m.dep0 + p]), (c + 1) * d.pscale, d.error);
     if (!__all_sync(full, ok)) return false;
     __syncwarp();
   } else if (lane < S) {
@@ -527,6 +543,13 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     double xb = x_own;                               // input of this segment group at time ta+lane
     double yb = 0.0;                                 // its output at time ta+lane (collected below)
     const int nticks = len + nseg - 1;
+    // (≈40 warp instructions per tick for five flops: everything that does not depend on the tick stays out of the loop)
+    const bool record = d.dis_series != nullptr;
+#ifndef HB_WAVE_TICK
+#define HB_WAVE_TICK 1
+#endif
+    const bool single = HB_WAVE_TICK == 2 && S <= 32;   // one segment group: its last lane stores the outflow row itself
+    const bool tail = lane == nseg - 1;
     for (int tau = 0; tau < nticks; ++tau) {
       const double x0 = __shfl_sync(full, xb, tau & 31);   // only meaningful while tau < len
       const double up = __shfl_up_sync(full, out, 1);
@@ -540,11 +563,14 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
         prev_in = in;
         prev_out = nv;
         out = nv;
-        if (d.dis_series) d.dis_series[(ta + tloc) * d.n_seg + g0 + cbase + lane + 1] = nv;
+        if (record) d.dis_series[(ta + tloc) * d.n_seg + g0 + cbase + lane + 1] = nv;
+        if (single && tail) rout[ta + tloc] = nv;
       }
-      const double y = __shfl_sync(full, out, nseg - 1);
-      const int p = tau - (nseg - 1);
-      if (p == lane) yb = y;
+      if (!single) {
+        const double y = __shfl_sync(full, out, nseg - 1);
+        const int p = tau - (nseg - 1);
+        if (p == lane) yb = y;
+      }
     }
     if (lane < nseg) dis_new[g0 + cbase + lane + 1] = prev_out;
     if (mct && lane < nseg) {
@@ -553,7 +579,7 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
       d.mct_rwd[g0 + cbase + lane] = mst[2];
     }
     x_own = yb;                                      // the next segment group continues on this output
-    if (cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
+    if (!single && cbase + 32 >= S && lane < len) rout[ta + lane] = yb;
   }
   return true;
 }
