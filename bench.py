@@ -514,6 +514,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     n_iso = 3
     if dist.world == 1:
         eng.set_forcing(np.ascontiguousarray(np.concatenate(list(pinned.array[:n_iso]), axis=1)), doys[:n_iso].reshape(-1))
+        eng.set_land_slabs(1)      # whole-basin launches: the per-kernel events then bracket ALL elements
         eng.timing()
         for s in range(n_iso):
             eng.select_window(s * win, win)
@@ -545,6 +546,12 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     # the element kernel executes 6 ops per sub-step of a running chain and 8 more where uz > 0
     zone_ops = zone_ops_alg
     element_ops = (2.0 * U + 32.0) * land.n_elem * win + 6.0 * R * cnt["elem_steps_run"] + 8.0 * cnt["substeps_pow"]
+    # inside the timed region the land kernels run in element slabs on streams of their own and the events bracket the
+    # launches of slab 0: its share of the elements (engine.cu run_land: slabs of 128-element blocks, block s*n/slabs)
+    n_slabs = args.land_slabs or 2
+    nblk = (land.n_elem + 127) // 128
+    slab0_share = min(land.n_elem, (nblk // n_slabs) * 128) / land.n_elem if n_slabs > 1 and nblk >= n_slabs else 1.0
+    fused = int(tm.get("n_fused", 0)) == land.n_elem              # every group's terms are added in the zone kernel
     land_ms_avg, zone_ms_avg, element_ms_avg = float(np.mean(land_ms)), float(np.mean(zone_ms)), float(np.mean(element_ms))
     general_ms_avg = float(np.mean(general_ms))
 
@@ -565,20 +572,29 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     def ncu_of(kernel: str, key: str):
         return ncu["kernels"].get(kernel, {}).get(key) if ncu else None
 
+    # algorithmic HBM bytes per launch: zone kernel = the forcing of its elements (32 B per
+    # element-step, shared by the zones) + the hand-over; element kernel = the hand-over + 8 B of outflow per element-step.
+    # Hand-over: 16 B per element-step when the zone kernel adds the terms itself (HB_OPT_LAND_FUSE), else 16 B per zone-step
+    handover = 16 * (land.n_elem if fused else land.n_zone) * win
     kernels = {
-        "zone_kernel": {"ms": zone_ms_avg, "ops_per_launch": zone_ops, "achieved": tops(zone_ops, zone_ms_avg),
-                        "frac": tops(zone_ops, zone_ms_avg) / peak_ops,
+        "zone_kernel": {"ms_slab0": zone_ms_avg, "slab0_share_of_elements": slab0_share,
+                        "ops_per_launch": zone_ops, "achieved": tops(zone_ops * slab0_share, zone_ms_avg),
+                        "frac": tops(zone_ops * slab0_share, zone_ms_avg) / peak_ops,
                         "ms_alone": iso["zone_ms"], "frac_alone": tops(zone_ops, iso["zone_ms"]) / peak_ops,
-                        "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 40 * land.n_elem * win,
+                        "algorithmic_bytes_per_launch": handover + 32 * land.n_elem * win,
+                        "terms_added_in_zone_kernel": bool(fused),
                         "ncu_fp64_pipe_pct": ncu_of("zone_kernel", "fp64_pipe_pct"),
+                        "ncu_issue_active_pct": ncu_of("zone_kernel", "issue_active_pct"),
                         "ncu_dram_bytes": ncu_of("zone_kernel", "dram_bytes")},
-        "element_kernel": {"ms": element_ms_avg, "ops_per_launch": element_ops,
+        "element_kernel": {"ms_slab0": element_ms_avg, "slab0_share_of_elements": slab0_share,
+                           "ops_per_launch": element_ops,
                            "ops_per_launch_algorithmic": element_ops_alg,
-                           "achieved": tops(element_ops, element_ms_avg),
-                           "frac": tops(element_ops, element_ms_avg) / peak_ops,
+                           "achieved": tops(element_ops * slab0_share, element_ms_avg),
+                           "frac": tops(element_ops * slab0_share, element_ms_avg) / peak_ops,
                            "ms_alone": iso["element_ms"], "frac_alone": tops(element_ops, iso["element_ms"]) / peak_ops,
-                           "algorithmic_bytes_per_launch": 16 * land.n_zone * win + 8 * land.n_elem * win,
+                           "algorithmic_bytes_per_launch": handover + 8 * land.n_elem * win,
                            "ncu_fp64_pipe_pct": ncu_of("element_kernel", "fp64_pipe_pct"),
+                           "ncu_issue_active_pct": ncu_of("element_kernel", "issue_active_pct"),
                            "ncu_dram_bytes": ncu_of("element_kernel", "dram_bytes")},
         "land_kernel (general)": {"ms": general_ms_avg},
         "routing (reach_head + reach_bulk + reach_wave kernels)": {
@@ -590,11 +606,11 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         dominant, dom_ms, dom_ops = "land_kernel (general)", general_ms_avg, zone_ops + element_ops
         dom_bytes = 40 * land.n_elem * win
     elif element_ms_avg > zone_ms_avg:
-        dominant, dom_ms, dom_ops = "element_kernel", element_ms_avg, element_ops
-        dom_bytes = kernels["element_kernel"]["algorithmic_bytes_per_launch"]
+        dominant, dom_ms, dom_ops = "element_kernel", element_ms_avg, element_ops * slab0_share
+        dom_bytes = kernels["element_kernel"]["algorithmic_bytes_per_launch"] * slab0_share
     else:
-        dominant, dom_ms, dom_ops = "zone_kernel", zone_ms_avg, zone_ops
-        dom_bytes = kernels["zone_kernel"]["algorithmic_bytes_per_launch"]
+        dominant, dom_ms, dom_ops = "zone_kernel", zone_ms_avg, zone_ops * slab0_share
+        dom_bytes = kernels["zone_kernel"]["algorithmic_bytes_per_launch"] * slab0_share
     achieved_tops = tops(dom_ops, dom_ms)
     peaks = {}
     try:
@@ -625,8 +641,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
                             f"series feed the downstream reaches" if dist.world > 1 and args.config == 3 else
                             f"member-sharded x{dist.world}" if dist.world > 1 else "single GPU"),
             "nvlink_bytes_per_step_this_rank": 8 * win * (sum(len(r) for _, r in wl.recv) + sum(len(r) for _, r in wl.send)),
-            "l2": "per step the zone terms (16 B per zone-step) and the node/reach rows stream through HBM "
-                  "(> 126 MB L2); no flush needed",
+            "l2": "per step the forcing block, the zone-to-element hand-over (16 B per element-step) and the node/reach rows "
+                  "(16 B per reach-step) stream through HBM: about 2.5 GB per 438-h step, far beyond the 126 MB L2; no flush "
+                  "needed",
             "forcing": forcing_note, **executed,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -647,11 +664,14 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
             "frac_alone": (kernels[dominant]["frac_alone"] if n_fast else None),
             "kernel": dominant, "ops_per_launch": dom_ops,
             "ops": "EXECUTED operations in SURVEY.md section 8d's convention, from the device counters of the timed "
-                   "region (config.recstep_executed_frac …); a pow counts as one op but costs about 35 FP64 "
+                   "region (config.recstep_executed_frac …); a pow counts as one op but costs about 25 FP64 "
                    "instructions, so ncu's FP64-pipe utilisation (kernels.*.ncu_fp64_pipe_pct) is the tighter figure",
             "peak_source": "hb_measure_fp64_peak (DFMA micro-benchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
-            "note": "ms/frac: CUDA events inside the timed, pipelined region (routing of the previous window shares the "
-                    "SMs); ms_alone/frac_alone: the same kernels in synchronous windows right after it",
+            "note": "ms_slab0/frac: CUDA events around the launches of element slab 0 inside the timed, pipelined region "
+                    "(the other slab's kernels and the routing of the previous window share the SMs), ops scaled to the "
+                    "slab; ms_alone/frac_alone: whole-basin launches in synchronous windows right after it.  The RecStep "
+                    "chain is sequential per element: 10^5 elements are 5.3 warps per scheduler, each a dependent chain, "
+                    "which bounds the element kernel near 0.7 instructions per cycle and scheduler (DESIGN.md section 4)",
             "fp64_tflops_measured": fp64_peak,
             "ncu_source": ncu.get("source") if ncu else None,
             "hbm": {"achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",

@@ -1837,6 +1837,7 @@ static int run_land(hb_engine* h) {
     const bool fuse = use_fast && !any_series && h->land_fuse && h->n_fused > 0;
     const bool all_fused = fuse && h->n_fused == h->n_fast && !use_fast_sib;   // then no term buffers at all
     v.fused = fuse ? 1 : 0;
+    h->timing.n_fused = fuse ? h->n_fused : 0;
     v.gwarps = h->d_gwarps.p;
     // time chunks bound the two term buffers (3 GB each at most)
     const int64_t per_step = all_fused ? ep : (int64_t)h->zmax * ep;   // (all fused: [chunk][E_pad] sums instead)
@@ -2462,10 +2463,11 @@ int hb_get_timing(hb_engine* h, hb_timing* out) {
   }
   *out = h->timing;
   // sums restart with the next run
-  const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast;
+  const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast, n_fused = h->timing.n_fused;
   h->timing = hb_timing{};
   h->timing.n_levels = n_levels;
   h->timing.n_fast = n_fast;
+  h->timing.n_fused = n_fused;
   return HB_OK;
 }
 

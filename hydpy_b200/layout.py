@@ -6,7 +6,7 @@ truth.  Names follow the reference's parameter/sequence names (`hydpy/models/hla
 """
 from __future__ import annotations
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # zone types, `hydpy/models/hland/hland_constants.py`
 FIELD, FOREST, GLACIER, ILAKE, SEALED = 1, 2, 3, 4, 5

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 3
+#define HB_ABI_VERSION 4
 
 /* ---- return codes ------------------------------------------------------------------------------------------ */
 #define HB_OK 0
@@ -472,6 +472,7 @@ typedef struct hb_timing {
   int64_t substeps_pow;        /* RecStep sub-steps with uz > 0, i.e. with a pow (of recstep * elem_steps_run)          */
   int64_t elem_warpsteps;      /* warp-steps (32 elements x 1 step) of the element kernel                               */
   int64_t elem_warpsteps_run;  /* ... in which at least one lane ran the chain                                          */
+  int64_t n_fused;             /* elements whose zone terms the zone kernel added itself (HB_OPT_LAND_FUSE), last run    */
 } hb_timing;
 /* Times and launch counts are SUMS over all runs since the previous hb_get_timing call (which resets them); after a
  * single hb_run they are that run's figures.  Waits for pending asynchronous work. */
