@@ -294,6 +294,9 @@ struct hb_engine {
   DBuf<int> d_progress, d_wave_ctl;     // d_wave_ctl = {queue head, error flag}
   std::vector<int32_t> wave_lvl_ptr;    // [n_levels+1]
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
+  std::vector<int32_t> plain_ptr_all, plain_ptr_bulk;   // [n_plain_levels+1] into head_all / head_bulk
+  int n_plain_levels = 0;
+  int64_t river_plain_min = 2048;       // HB_OPT_RIVER_PLAIN_MIN (read by hb_set_river)
   // grouped wavefront (HB_RIVER_GROUPED)
   DBuf<int32_t> d_unit_start, d_unit_reach, d_unit_info, d_unit_lvl_ptr, d_diag_start_g;
   DBuf<double> d_zero_row;
@@ -1121,6 +1124,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
       HB_REQUIRE(h, value >= -1, HB_EINVAL, "hb_set_option: invalid land chunk");
       h->land_chunk = value;
       return HB_OK;
+    case HB_OPT_RIVER_PLAIN_MIN:
+      HB_REQUIRE(h, value >= 0, HB_EINVAL, "hb_set_option: invalid minimum width of a plain routing level");
+      h->river_plain_min = value;
+      return HB_OK;
     case HB_OPT_LAND_FUSE:
       HB_REQUIRE(h, value == 0 || value == 1, HB_EINVAL, "hb_set_option: land fuse must be 0 or 1");
       h->land_fuse = (int)value;
@@ -1248,20 +1255,51 @@ static int set_river_core(hb_engine* h, const hb_river_desc* r) {
     for (int64_t i = r->entry_ptr[n]; i < r->entry_ptr[n + 1]; ++i)
       if (r->entry_src[i] <= HB_ENTRY_EXT) h->ext_feeds_reach = true;
   }
-  // headwater reaches (level 0, at most HB_BULK_SMAX segments) are handled by two plain launches; the rest forms the
-  // wavefront: sorted by level (and by segments within a level), with the list of reaches each one waits for
+  // The wide upstream levels of a river tree are routed by two plain launches per level (reach_head_kernel: inflow of every
+  // (reach, chunk); reach_bulk_kernel: lane = reach, the whole window): ≈0.3 warp instructions per reach-segment-step
+  // against ≈100 per reach-step of the persistent wavefront's systolic tasks.  Level l qualifies while every level below
+  // it does and at least `river_plain_min` of its reaches are simple (at most HB_BULK_SMAX segments, musk_classic, fed
+  // by plain reaches only); level 0 always does.  Everything else forms the wavefront: sorted by level (and by segments
+  // within a level), with the list of reaches each one waits for.
   std::vector<int32_t> head_all, head_bulk, wave_order, wave_lvl(nlev + 1, 0), dep_reach;
+  std::vector<int32_t> plain_ptr_all{0}, plain_ptr_bulk{0};
   std::vector<int64_t> dep_ptr(nr + 1, 0);
-  for (int32_t q : reach_order) {
-    const int64_t nseg = r->seg_ptr[q + 1] - r->seg_ptr[q] - 1;
-    const bool is_mct = r->reach_model && r->reach_model[q] == HB_REACH_MCT;   // musk_mct: always the systolic wavefront
-    if (reach_level[q] == 0 && nseg <= HB_BULK_SMAX && !is_mct) {
-      head_all.push_back(q);
-      if (nseg >= 1) head_bulk.push_back(q);
-    } else {
-      wave_order.push_back(q);
-      wave_lvl[reach_level[q] + 1]++;
+  {
+    std::vector<char> plain((size_t)nr, 0);
+    auto simple = [&](int32_t q) {
+      const int64_t nseg = r->seg_ptr[q + 1] - r->seg_ptr[q] - 1;
+      if (nseg > HB_BULK_SMAX || (r->reach_model && r->reach_model[q] == HB_REACH_MCT)) return false;
+      for (int64_t i = r->inlet_ptr[q]; i < r->inlet_ptr[q + 1]; ++i) {
+        const int32_t n = r->inlet_node[i];
+        for (int64_t k = r->entry_ptr[n]; k < r->entry_ptr[n + 1]; ++k) {
+          const int32_t s_ = r->entry_src[k];
+          if (s_ < 0 && s_ > HB_ENTRY_EXT && !plain[-1 - s_]) return false;
+        }
+      }
+      return true;
+    };
+    int n_plain_levels = 0;
+    for (int l = 0; l < nlev; ++l) {
+      std::vector<int32_t> cand;
+      for (int32_t i = lrp[l]; i < lrp[l + 1]; ++i)
+        if (simple(reach_order[i])) cand.push_back(reach_order[i]);
+      if (l > 0 && (int64_t)cand.size() < h->river_plain_min) break;
+      for (int32_t q : cand) {
+        plain[q] = 1;
+        head_all.push_back(q);
+        if (r->seg_ptr[q + 1] - r->seg_ptr[q] - 1 >= 1) head_bulk.push_back(q);
+      }
+      plain_ptr_all.push_back((int32_t)head_all.size());
+      plain_ptr_bulk.push_back((int32_t)head_bulk.size());
+      n_plain_levels = l + 1;
     }
+    h->plain_ptr_all = plain_ptr_all; h->plain_ptr_bulk = plain_ptr_bulk;
+    h->n_plain_levels = n_plain_levels;
+    for (int32_t q : reach_order)
+      if (!plain[q]) {
+        wave_order.push_back(q);
+        wave_lvl[reach_level[q] + 1]++;
+      }
   }
   for (int l = 0; l < nlev; ++l) wave_lvl[l + 1] += wave_lvl[l];
   for (int64_t q = 0; q < nr; ++q) {
@@ -2188,14 +2226,21 @@ static int run_river(hb_engine* h) {
       ++launches;
     }
     if (h->n_head_all > 0) {
-      const int64_t warps = h->n_head_all * n_chunks;
-      reach_head_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, h->s_river>>>(d, h->d_head_all.p, (int)h->n_head_all);
-      ++launches;
-      if (h->n_head_bulk > 0) {
-        const int per_block = 32 * HB_BULK_WARPS;
-        reach_bulk_kernel<<<(unsigned)((h->n_head_bulk + per_block - 1) / per_block), per_block, HB_BULK_SMEM, h->s_river>>>(
-            d, h->d_head_bulk.p, (int)h->n_head_bulk);
-        ++launches;
+      // level by level: the outflow rows of level l - 1 are complete when the launches of level l start
+      for (int l = 0; l < h->n_plain_levels; ++l) {
+        const int32_t a0 = h->plain_ptr_all[l], na = h->plain_ptr_all[l + 1] - a0;
+        const int32_t b0 = h->plain_ptr_bulk[l], nb = h->plain_ptr_bulk[l + 1] - b0;
+        if (na > 0) {
+          const int64_t warps = (int64_t)na * n_chunks;
+          reach_head_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, h->s_river>>>(d, h->d_head_all.p + a0, na);
+          ++launches;
+        }
+        if (nb > 0) {
+          const int per_block = 32 * HB_BULK_WARPS;
+          reach_bulk_kernel<<<(unsigned)((nb + per_block - 1) / per_block), per_block, HB_BULK_SMEM, h->s_river>>>(
+              d, h->d_head_bulk.p + b0, nb);
+          ++launches;
+        }
       }
       if (h->n_wave > 0) {
         wave_head_done_kernel<<<(unsigned)((h->n_head_all + 255) / 256), 256, 0, h->s_river>>>(d, h->d_head_all.p,

@@ -347,6 +347,11 @@ class Engine:
         """Element slabs (streams) of the fast runoff-generation path, 1..8 (performance only; same results)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_SLABS, int(slabs)), "hb_set_option")
 
+    def set_river_plain_min(self, reaches: int) -> None:
+        """Minimum number of simple reaches for which a level is routed by plain per-level launches (takes effect with the
+        next `set_river`; performance only, same results)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_RIVER_PLAIN_MIN, int(reaches)), "hb_set_option")
+
     def set_land_fuse(self, on: bool) -> None:
         """Zone terms added inside the thread-per-zone kernel where a 32-element group allows (default on; same results)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_FUSE, 1 if on else 0), "hb_set_option")

@@ -141,6 +141,7 @@ MOD_EPAR = 1000
 OPT_LAND_SLABS = 5
 OPT_LAND_CHUNK = 6
 OPT_LAND_FUSE = 7
+OPT_RIVER_PLAIN_MIN = 8
 RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2
 LAND_AUTO, LAND_GENERAL = 0, 1
 ROW_NODE, ROW_REACH = 0, 1

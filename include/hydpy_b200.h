@@ -335,6 +335,11 @@ int hb_select_series(hb_engine* h, int series, int on);
  * Calc_ContriArea_V1 itself — in zone order, i.e. the same bits — and hands two sums per element-step to the
  * thread-per-element kernel instead of two terms per zone-step.  0 keeps the term buffers (development, A/B timing). */
 #define HB_OPT_LAND_FUSE 7
+/* HB_OPT_RIVER_PLAIN_MIN (reaches, default 2048; read by the next hb_set_river): the upstream levels of the network are
+ * routed level by level with one thread per reach over the whole window while a level offers at least this many simple
+ * reaches (musk_classic, at most 32 segments, fed by such reaches only); headwater reaches always are.  The rest of the
+ * network — the narrow, deep part of a river tree — runs in the persistent wavefront.  Same bits either way. */
+#define HB_OPT_RIVER_PLAIN_MIN 8
 enum hb_mct_series {
   HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
   HB_MS_CORRECTINGFACTOR, HB_MS_COEFFICIENT1, HB_MS_COEFFICIENT2, HB_MS_COEFFICIENT3, HB_MS_COURANTNUMBER,

@@ -427,6 +427,44 @@ def test_full_size_routing_sweeps_agree_bit_for_bit():
     assert_close(b[0], c[0], "full size: fast vs general land path, node series")
 
 
+@pytest.mark.parametrize("sweep", ["persistent", "grouped"])
+def test_plain_routing_levels_give_the_same_bits(sweep):
+    """HB_OPT_RIVER_PLAIN_MIN: upstream levels routed by plain per-level launches (one thread per reach) instead of wavefront
+    tasks.  Random networks (deploy modes, external rows, reaches with 0 and with more than 32 segments, musk_mct reaches
+    that break the run of plain levels) and a river tree: every setting gives the bits of the one-launch-per-diagonal sweep,
+    over two windows."""
+    cases = []
+    ne = 300
+    land, states = random_land(ne, seed=7)
+    forcing, doy = random_forcing(64, ne, seed=7)
+    river, discharge, _ = random_river(ne, 260, seed=7)
+    rng = np.random.default_rng(7)
+    ext = rng.uniform(0, 3, size=(river.n_ext, 64))
+    cases.append(Problem(land=land, states=states, river=river, discharge=discharge, forcing=forcing, doy=doy, ext=ext))
+    river2, discharge2, _ = random_river(ne, 260, seed=8)
+    mct2 = add_mct(river2, seed=8, fraction=0.1)
+    cases.append(Problem(land=land, states=states, river=river2, discharge=discharge2, forcing=forcing, doy=doy,
+                         ext=rng.uniform(0, 3, size=(river2.n_ext, 64)), mct_states=mct2))
+    ne3 = 3000
+    land3, states3 = synth.make_land(ne3, "1h")
+    river3, discharge3 = synth.make_tree_river(ne3, "1h", levels=40)
+    forcing3, doy3 = synth.make_forcing(64, "1h")
+    cases.append(Problem(land=land3, states=states3, river=river3, discharge=discharge3, forcing=forcing3, doy=doy3,
+                         ext=np.zeros((0, 64))))
+    with Engine(0) as eng:
+        for i, problem in enumerate(cases):
+            eng.set_river_sweep("launches")
+            ref = run_problem(problem, eng, window=32)
+            eng.set_river_sweep(sweep)
+            for plain_min in (0, 1, 25, 10**9):
+                eng.set_river_plain_min(plain_min)
+                res = run_problem(problem, eng, window=32)
+                for key in ("node_rows", "reach_out", "reach_in", "discharge"):
+                    assert np.array_equal(res[key], ref[key], equal_nan=True), (i, plain_min, key)
+                if problem.mct_states is not None:
+                    assert np.array_equal(res["mct_states"], ref["mct_states"], equal_nan=True), (i, plain_min)
+
+
 def test_element_slabs_and_time_chunks_do_not_change_a_bit():
     """HB_OPT_LAND_SLABS / HB_OPT_LAND_CHUNK only decide which stream and launch computes what: every combination must
     give the bits of the single-slab, single-chunk run — pipelined windows included (slabs of consecutive windows overlap)."""
