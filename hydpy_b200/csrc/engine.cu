@@ -30,7 +30,8 @@ using namespace hb;
 #define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
 #define HB_MAX_SLABS 8
-#define HB_FUSE_ZMAX 16      // fused reduction: one warp per zone of a 32-element group, at most 16 warps per block
+#define HB_FUSE_ZMAX 12      // fused reduction: one warp per zone of a 32-element group; beyond 12 zones only one block
+                             // (16 warps) would fit an SM and the term buffers win (measured on the Lahn ensemble)
 // dynamic shared memory of zone_kernel<…, ZW>: constants [14][ZW*32] double2 + term buffers [G][2][ZW][32] doubles
 #define HB_FUSE_SMEM(zw) ((size_t)(zw) * 32 * (14 * 16 + ZoneGeom<zw>::G * 2 * 8))
 // zone/snow series the fast path of hland_96 stages in its own layout (first block + the evap submodels' block)
@@ -247,8 +248,9 @@ struct hb_engine {
   // the (latency-bound, few-warps) element kernel must reach the SMs first — the zone blocks then fill what is left.  In
   // the other order two zone blocks take an SM's shared memory and the element kernel waits for the whole zone kernel
   // (measured, two slabs, 438 h: 14.8 instead of 11.0 ms, at random from process to process)
-  cudaStream_t s_elem[HB_MAX_SLABS] = {};
-  cudaEvent_t ev_slab_zdone[HB_MAX_SLABS] = {}, ev_slab_edone[HB_MAX_SLABS] = {};
+  cudaStream_t s_elem[HB_MAX_SLABS][4] = {};   // [slab][fused hland_96 | hland_96 | hland_96p | hland_96c]: these kernels follow
+                                               // sequential chains — side by side, never one after the other
+  cudaEvent_t ev_slab_zdone[HB_MAX_SLABS] = {}, ev_slab_edone[HB_MAX_SLABS][4] = {};
   cudaEvent_t ev_slab_fork = nullptr, ev_slab_zone[HB_MAX_SLABS] = {}, ev_slab_done[HB_MAX_SLABS] = {};
   int slabs_used = 1;                 // slabs of the current run_land
   int64_t slab_elem_lo[HB_MAX_SLABS + 1] = {};
@@ -538,10 +540,11 @@ int hb_create(int device, hb_engine** out) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     const int pe = hi + 1 <= lo ? hi + 1 : hi;       // just below the routing
-    for (auto& st : h->s_elem) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pe);
+    for (auto& row : h->s_elem)
+      for (auto& st : row) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pe);
     for (int i = 0; i < HB_MAX_SLABS; ++i) {
       cudaEventCreateWithFlags(&h->ev_slab_zdone[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&h->ev_slab_edone[i], cudaEventDisableTiming);
+      for (auto& e : h->ev_slab_edone[i]) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     }
   }
   cudaEventCreateWithFlags(&h->ev_slab_fork, cudaEventDisableTiming);
@@ -597,11 +600,13 @@ void hb_destroy(hb_engine* h) {
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   if (h->s_join) { cudaStreamSynchronize(h->s_join); cudaStreamDestroy(h->s_join); }
   if (h->ev_slab_fork) cudaEventDestroy(h->ev_slab_fork);
-  for (auto& st : h->s_elem)
-    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto& row : h->s_elem)
+    for (auto& st : row)
+      if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < HB_MAX_SLABS; ++i) {
     if (h->ev_slab_zdone[i]) cudaEventDestroy(h->ev_slab_zdone[i]);
-    if (h->ev_slab_edone[i]) cudaEventDestroy(h->ev_slab_edone[i]);
+    for (auto& e : h->ev_slab_edone[i])
+      if (e) cudaEventDestroy(e);
   }
   for (int i = 0; i < HB_MAX_SLABS; ++i) {
     if (h->ev_slab_zone[i]) cudaEventDestroy(h->ev_slab_zone[i]);
@@ -1867,7 +1872,23 @@ static int run_land(hb_engine* h) {
     // [storage | ordinate][thread] staging of the runoff concentration: the rconc_nash cascade of a step, the rconc_uh
     // memory for the whole launch
     v.nash_stage = 1;
-    const size_t esmem = (size_t)HB_NASH_STAGE * 64 * sizeof(double);
+    // ordinates staged per element: the basin's longest unit hydrograph (at most 32) if the blocks an SM has to hold at
+    // once (every chain of the slab resident: <= 12 blocks of 64 threads) still fit its shared memory, else 12
+    const int slabs_est = any_series ? 1 : (h->land_slabs > 0 ? h->land_slabs : 1);   // (series recording keeps one slab)
+    const int64_t eblocks_total = (ep / 64 + slabs_est - 1) / slabs_est;
+    const int sms = h->prop.multiProcessorCount > 0 ? h->prop.multiProcessorCount : 148;
+    const int eblk_per_sm = (int)std::min<int64_t>(12, (eblocks_total + sms - 1) / sms);
+    int uh_stage = std::max(HB_NASH_STAGE, std::min(h->umax, 32));
+    if ((size_t)eblk_per_sm * (sizeof(MathTables) + sizeof(ChainTables) + (size_t)uh_stage * 64 * 8 + 1024) > 227 * 1024)
+      uh_stage = HB_NASH_STAGE;
+    v.uh_stage = uh_stage;
+    // … and the ordinates' weights behind them when there is room for both (the L1 is what the resident blocks leave of
+    // the SM's 256 KB: with the launch bounds' 12 blocks in mind the driver leaves 28 KB, which the weights of a long unit
+    // hydrograph miss — Lahn ensemble: 4.1 instead of 2.5 ms; an explicit carve-out per kernel is no way out, kernels
+    // with different carve-outs do not share an SM)
+    // (only where the element blocks stay a small tenant of the SM: a zone block of the next slab must still fit beside them)
+    v.uh_weights = (size_t)eblk_per_sm * (sizeof(MathTables) + sizeof(ChainTables) + (size_t)uh_stage * 64 * 16 + 1024) <= 96 * 1024;
+    const size_t esmem = (size_t)uh_stage * 64 * sizeof(double) * (v.uh_weights ? 2 : 1);
     v.nash_steps = h->d_nash_steps.p; v.zx1 = h->d_zx1.p; v.zx2 = h->d_zx2.p; v.ex1 = h->d_ex1.p; v.ex2 = h->d_ex2.p;
     int n_staged = 0;
     for (int s = 0; s < HB_S_COUNT; ++s) n_staged += (HB_S_STAGED(s) && h->series_on[s]) ? 1 : 0;
@@ -2004,28 +2025,38 @@ static int run_land(hb_engine* h) {
         }
         if (sl == 0) h->mark(HB_K_ZONE);
         // element kernels: high-priority stream of the slab (see s_elem); the slab's stream continues behind them
-        cudaStream_t se = h->s_elem[sl];
         HB_CUDA(h, cudaEventRecord(h->ev_slab_zdone[sl], st));
-        HB_CUDA(h, cudaStreamWaitEvent(se, h->ev_slab_zdone[sl], 0));
+        auto elem_stream = [&](int kind) -> cudaStream_t {
+          cudaStream_t se = h->s_elem[sl][kind];
+          cudaStreamWaitEvent(se, h->ev_slab_zdone[sl], 0);
+          return se;
+        };
+        auto elem_done = [&](int kind) {
+          cudaEventRecord(h->ev_slab_edone[sl][kind], h->s_elem[sl][kind]);
+          cudaStreamWaitEvent(st, h->ev_slab_edone[sl][kind], 0);
+        };
         if (fuse) {
-          element_kernel<false, HB_MODEL_HLAND_96, true><<<egrid, 64, esmem, se>>>(v);
+          element_kernel<false, HB_MODEL_HLAND_96, true><<<egrid, 64, esmem, elem_stream(0)>>>(v);
           h->timing.land_launches += 1;
+          elem_done(0);
         }
         if (use_fast && !all_fused) {
+          cudaStream_t se = elem_stream(1);
           if (any_series) element_kernel<true, HB_MODEL_HLAND_96><<<egrid, 64, esmem, se>>>(v);
           else element_kernel<false, HB_MODEL_HLAND_96><<<egrid, 64, esmem, se>>>(v);
           h->timing.land_launches += 1;
+          elem_done(1);
         }
         if (use_fast_sib && h->n_fast_sib[0] > 0) {
-          element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, se>>>(v);
+          element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, elem_stream(2)>>>(v);
           h->timing.land_launches += 1;
+          elem_done(2);
         }
         if (use_fast_sib && h->n_fast_sib[1] > 0) {
-          element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, se>>>(v);
+          element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, elem_stream(3)>>>(v);
           h->timing.land_launches += 1;
+          elem_done(3);
         }
-        HB_CUDA(h, cudaEventRecord(h->ev_slab_edone[sl], se));
-        HB_CUDA(h, cudaStreamWaitEvent(st, h->ev_slab_edone[sl], 0));
         if (sl == 0) h->mark(HB_K_ELEMENT);
       }
     }

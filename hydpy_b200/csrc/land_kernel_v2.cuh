@@ -85,6 +85,8 @@ struct LandV2Dev {
   // sibling models (hland_96p / hland_96c) and rconc_nash
   const int32_t* nash_steps;  // [E_pad] see LandDev
   int32_t nash_stage;      // element kernel: dynamic shared memory for the cascades is present
+  int32_t uh_stage;        // … with room for this many rconc_uh ordinates per element (>= HB_NASH_STAGE)
+  int32_t uh_weights;      // … and for their weights behind them ([uh_stage][64] memory, [uh_stage][64] weights)
   double* zx1;             // [zmax][E_pad] hland_96p suz | hland_96c bw1
   double* zx2;             // [zmax][E_pad] hland_96p sg1 | hland_96c bw2
   double* ex1;             // [E_pad] hland_96p sg2
@@ -801,7 +803,12 @@ __global__ void __launch_bounds__(256) series_scatter_kernel(const double* __res
 // memory ([ordinate][thread], 64 threads per block) for the whole launch: the per-step loads of the global copy wait for
 // the L2 (stores bypass the L1), a quarter of the element kernel's stall cycles once the zone sums arrive ready-made
 __device__ __forceinline__ double uh_outflow_staged(const double* __restrict__ uh, int64_t ep, int64_t e, int nu,
-                                                    double inrc, double* s_q) {
+                                                    double inrc, double* s_q, const double* s_w) {
+  if (s_w != nullptr) {   // weights staged as well
+    const double outrc = s_w[0] * inrc + s_q[0];
+    for (int j = 1; j < nu; ++j) s_q[(j - 1) * 64] = s_w[j * 64] * inrc + s_q[j * 64];
+    return outrc;
+  }
   const double outrc = ldg(uh + e) * inrc + s_q[0];
   for (int j = 1; j < nu; ++j) s_q[(j - 1) * 64] = ldg(uh + (int64_t)j * ep + e) * inrc + s_q[j * 64];
   return outrc;
@@ -833,9 +840,17 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
-  const bool uh_smem = s_sc != nullptr && nash_steps == 0 && nu > 0 && nu <= HB_NASH_STAGE;
+#ifdef HB_ELEM_NO_UHSMEM
+  const bool uh_smem = false;
+#else
+  const bool uh_smem = s_sc != nullptr && nash_steps == 0 && nu > 0 && nu <= d.uh_stage;
+#endif
+  const double* const s_uw = (uh_smem && d.uh_weights) ? s_sc + (size_t)d.uh_stage * 64 + threadIdx.x : nullptr;
   if (uh_smem)
-    for (int j = 0; j < nu; ++j) s_sc[threadIdx.x + j * 64] = d.quh[(int64_t)j * ep + e];
+    for (int j = 0; j < nu; ++j) {
+      s_sc[threadIdx.x + j * 64] = d.quh[(int64_t)j * ep + e];
+      if (d.uh_weights) s_sc[(size_t)d.uh_stage * 64 + threadIdx.x + j * 64] = d.uh[(int64_t)j * ep + e];
+    }
   const double dt = d.ke[KE_DT * ep + e], dt_percmax = d.ke[KE_DT_PERCMAX * ep + e], dt_k = d.ke[KE_DT_K * ep + e],
                alpha1 = d.ke[KE_ALPHA1 * ep + e], k4 = d.ke[KE_K4 * ep + e], gamma1 = d.ke[KE_GAMMA1 * ep + e],
                relupper = d.ke[KE_RELUPPER * ep + e], rellower = d.ke[KE_RELLOWER * ep + e],
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x, s_uw)
                                  : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
       continue;
@@ -938,7 +953,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
         if ((einfo & HB_EI_LAKE) && HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_ILAKE) continue;
         inrc += ta[(int64_t)k * ep];
       }
-      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+      const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x, s_uw)
                                  : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       // ref: hland_model.py:3172-3181 Calc_LZ_V2 (tb = weight * pc | weight * qvs2)
       for (int k = 0; k < nz; ++k) {
@@ -997,8 +1012,13 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       //  * a quadratic response (alpha = 1, the Lahn default) needs no power function at all: exact.
       const bool lane_plain = chain_ok && uz >= 0.0 && uz <= 1e300 && dt_inuz >= 0.0 && dt_inuz <= 1e300 &&
                               perc_pot >= 0.0 && perc_pot <= 1e300 && contriarea >= 1e-30 && contriarea <= 2.0;
+#ifdef HB_ELEM_NO_FAST
+      bool redo = true;
+      if (false) {
+#else
       bool redo = !lane_plain;
       if (lane_plain) {
+#endif
         // (whole warp) no sub-step leaves water for the outflow: uz + dt*inuz <= perc_pot now, and dt*inuz <= perc_pot
         // from then on because every sub-step empties the storage — percolation takes everything, 50 additions remain
         if (__all_sync(__activemask(), uz + dt_inuz <= perc_pot)) {
@@ -1009,17 +1029,30 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
           const double inv_ca = 1.0 / contriarea;
           double a = uz + dt_inuz, u = 0.0;
           bool pos = false;
-          for (int i = 0; i < recstep; ++i) {
-            const double dd = a - perc_pot;
-            const bool p = dd > 0.0;
-            perc_sum += p ? perc_pot : a;
-            const double x = dd * inv_ca;
-            const double q = dt_k * (x * x);
-            u = dd - q;
-            pos = p && (u > 0.0);
-            if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
-            n_pow += p ? 1u : 0u;
-            a = pos ? u + dt_inuz : dt_inuz;
+          const bool refill = dt_inuz > perc_pot;    // recharge alone can lift the storage above the percolation again
+          // sub-steps in runs of 2, 6 and the rest: after the first two runs, if every storage of the warp is empty for good, percolation
+          // takes the recharge of each remaining sub-step — additions only, what the reference's loop does in dry hours
+          // without its branches.  (The test sits between plain counted loops: inside the loop it costs the unrolling.)
+          for (int i = 0, hi = 2; i < recstep; hi = hi == 2 ? 8 : recstep) {
+            const int end = hi < recstep ? hi : recstep;
+            for (; i < end; ++i) {
+              const double dd = a - perc_pot;
+              const bool p = dd > 0.0;
+              perc_sum += p ? perc_pot : a;
+              const double x = dd * inv_ca;
+              const double q = dt_k * (x * x);
+              u = dd - q;
+              pos = p && (u > 0.0);
+              if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
+              n_pow += p ? 1u : 0u;
+              a = pos ? u + dt_inuz : dt_inuz;
+            }
+#ifndef HB_ELEM_NO_EARLYOUT
+            if (i < recstep && __all_sync(__activemask(), !pos && !refill)) {
+              for (; i < recstep; ++i) perc_sum += dt_inuz;
+              break;
+            }
+#endif
           }
           uz = pos ? u : 0.0;
         } else {
@@ -1028,18 +1061,28 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
           double a = uz + dt_inuz, u = 0.0;
           bool pos = false, bad = false;
           unsigned np_ = 0;
-          for (int i = 0; i < recstep; ++i) {
-            const double dd = a - perc_pot;
-            const bool p = dd > 0.0;
-            perc_sum += p ? perc_pot : a;
-            double tq;
-            const double q = hb_chain_pow2(dd, alpha1, c2, CT, tq);
-            bad |= p && !(fabs(tq) < 800.0);
-            u = dd - q;
-            pos = p && (u > 0.0);
-            if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
-            np_ += p ? 1u : 0u;
-            a = pos ? u + dt_inuz : dt_inuz;
+          const bool refill = dt_inuz > perc_pot;
+          for (int i = 0, hi = 2; i < recstep; hi = hi == 2 ? 8 : recstep) {   // (runs of 2, 6 and the rest: see the quadratic loop)
+            const int end = hi < recstep ? hi : recstep;
+            for (; i < end; ++i) {
+              const double dd = a - perc_pot;
+              const bool p = dd > 0.0;
+              perc_sum += p ? perc_pot : a;
+              double tq;
+              const double q = hb_chain_pow2(dd, alpha1, c2, CT, tq);
+              bad |= p && !(fabs(tq) < 800.0);
+              u = dd - q;
+              pos = p && (u > 0.0);
+              if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
+              np_ += p ? 1u : 0u;
+              a = pos ? u + dt_inuz : dt_inuz;
+            }
+#ifndef HB_ELEM_NO_EARLYOUT
+            if (i < recstep && __all_sync(__activemask(), !pos && !refill)) {
+              for (; i < recstep; ++i) perc_sum += dt_inuz;
+              break;
+            }
+#endif
           }
           uz = pos ? u : 0.0;
           if (bad) { redo = true; uz = uz_old; perc_sum = 0.0; q0_sum = 0.0; }   // out-of-range power: general loop
@@ -1094,7 +1137,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       for (int k = 0; k < nz; ++k)
         if (HB_ZI_TYPE(d.zinfo[(int64_t)k * ep + e]) == HB_SEALED) inrc += ta[(int64_t)k * ep];
     // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1
-    const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x)
+    const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x, s_uw)
                                  : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
     if (SERIES) record_sc(d.series[HB_S_SC], d.t_out + t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
     // ref: hland_model.py:4139-4141 Calc_RT_V1, 4197-4200 Calc_QT_V1

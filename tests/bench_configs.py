@@ -99,8 +99,14 @@ def main() -> None:
     ap.add_argument("--members", type=int, default=4096)
     ap.add_argument("--elements", type=int, default=100_000)
     ap.add_argument("--members5", type=int, default=16)
+    ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
+    ap.add_argument("--no-land-fuse", action="store_true", help="zone terms through HBM (A/B timing)")
     args = ap.parse_args()
     eng = Engine(0)
+    if args.land_slabs:
+        eng.set_land_slabs(args.land_slabs)
+    if args.no_land_fuse:
+        eng.set_land_fuse(False)
     info = eng.device_info()
     for case in args.cases.split(","):
         if case == "config2":
