@@ -65,6 +65,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--members", type=int, default=0, help="ensemble members of --config 1 / 4 in total (0 = 4096 / 512)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the unsharded run")
     ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
+    ap.add_argument("--river-plain-min", type=int, default=-1,
+                    help="minimum width of a routing level for plain per-level launches (-1 = engine default)")
     ap.add_argument("--no-land-fuse", action="store_true",
                     help="hand the zone terms over through HBM instead of adding them inside the zone kernel (A/B timing)")
     ap.add_argument("--land-chunk", type=int, default=0, help="time chunk of the fast land path in steps (0 = engine default)")
@@ -325,6 +327,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     elif args.config == 4 and win == 438:
         win = 120        # 5·10^6 nodes per GPU: the node/reach rows of a 438-h window would not fit beside the constants
     states, discharge = wl.states, wl.discharge
+    if args.river_plain_min >= 0:
+        eng.set_river_plain_min(args.river_plain_min)
     eng.set_land(wl.land)
     eng.set_land_states(states)
     eng.set_river(wl.river)
