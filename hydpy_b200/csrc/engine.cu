@@ -27,7 +27,7 @@ using namespace hb;
 #define HB_COUPLED_B448 2   // blocks per SM the fused capillary-flux kernel is compiled for at <= 13 warps per block
 #endif
 #ifndef HB_WAVE_BLOCKS_PER_SM
-#define HB_WAVE_BLOCKS_PER_SM 4   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
+#define HB_WAVE_BLOCKS_PER_SM 3   // persistent wavefront blocks per SM: leaves registers for the land kernels of the next window
 #endif
 #define HB_MAX_SLABS 8
 #define HB_FUSE_ZMAX 12      // fused reduction: one warp per zone of a 32-element group; beyond 12 zones only one block
@@ -298,7 +298,7 @@ struct hb_engine {
   int64_t n_head_all = 0, n_head_bulk = 0, n_wave = 0;
   std::vector<int32_t> plain_ptr_all, plain_ptr_bulk;   // [n_plain_levels+1] into head_all / head_bulk
   int n_plain_levels = 0;
-  int64_t river_plain_min = 2048;       // HB_OPT_RIVER_PLAIN_MIN (read by hb_set_river)
+  int64_t river_plain_min = 4096;       // HB_OPT_RIVER_PLAIN_MIN (read by hb_set_river)
   // grouped wavefront (HB_RIVER_GROUPED)
   DBuf<int32_t> d_unit_start, d_unit_reach, d_unit_info, d_unit_lvl_ptr, d_diag_start_g;
   DBuf<double> d_zero_row;

@@ -314,7 +314,7 @@ int hb_select_series(hb_engine* h, int series, int on);
 /* HB_OPT_RIVER_STATE_SERIES (0/1): record musk_classic `states.discharge` of every step for hb_get_reach_state_series
  * (the `ramflag` of that sequence, `hydpy/models/musk/musk_states.py`). */
 #define HB_OPT_RIVER_STATE_SERIES 2
-/* HB_OPT_RIVER_WAVE_BLOCKS (1..8, default 4): persistent wavefront blocks per SM.  The routing of window w shares the GPU
+/* HB_OPT_RIVER_WAVE_BLOCKS (1..8, default 3): persistent wavefront blocks per SM.  The routing of window w shares the GPU
  * with the runoff generation of window w+1 (hb_run_async); fewer blocks leave it more of every SM. */
 #define HB_OPT_RIVER_WAVE_BLOCKS 3
 /* HB_OPT_RIVER_MCT_SERIES (bit mask over enum hb_mct_series, default 0): musk_mct sequences to record at every step for
@@ -335,7 +335,7 @@ int hb_select_series(hb_engine* h, int series, int on);
  * Calc_ContriArea_V1 itself — in zone order, i.e. the same bits — and hands two sums per element-step to the
  * thread-per-element kernel instead of two terms per zone-step.  0 keeps the term buffers (development, A/B timing). */
 #define HB_OPT_LAND_FUSE 7
-/* HB_OPT_RIVER_PLAIN_MIN (reaches, default 2048; read by the next hb_set_river): the upstream levels of the network are
+/* HB_OPT_RIVER_PLAIN_MIN (reaches, default 4096; read by the next hb_set_river): the upstream levels of the network are
  * routed level by level with one thread per reach over the whole window while a level offers at least this many simple
  * reaches (musk_classic, at most 32 segments, fed by such reaches only); headwater reaches always are.  The rest of the
  * network — the narrow, deep part of a river tree — runs in the persistent wavefront.  Same bits either way. */
