@@ -210,6 +210,7 @@ struct hb_engine {
   bool any_snowlimit = false;
   bool any_nonsoil_warp = false;      // some warp of the zone kernel holds a fast-path zone that is not FIELD/FOREST with FC > 0
   int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
+  int64_t n_fast_classes = 0;         // … of them with several snow classes (fast only while no series is recorded)
   std::vector<int32_t> coupled_list;  // elements of the fused kernel (HB_EI_COUPLED)
   std::vector<int32_t> general_list;  // elements of the general kernel in the current combination of paths
   // sibling models: hland_96p / hland_96c elements always run through the general kernel, instantiated
@@ -786,7 +787,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   std::vector<double> kz(host_fold ? (size_t)zmax * KZ_COUNT * ep : 0, 0.0), ke(host_fold ? (size_t)KE_COUNT * ep : 0, 0.0),
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
-  int64_t n_fast = 0, n_fast_sib[2] = {0, 0};
+  int64_t n_fast = 0, n_fast_sib[2] = {0, 0}, n_fast_classes = 0;
   std::vector<int32_t> coupled_list;
   std::vector<char> soilwarp_ok((size_t)ep, 0);   // fast hland_96 element, every zone FIELD/FOREST with FC > 0
   h->any_nonsoil_warp = false;
@@ -841,7 +842,12 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
       info &= ~HB_EI_RESPAREA;
       if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1) { info |= HB_EI_FAST; ++n_fast_sib[model[e] - 1]; }
     }
-    else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && !coupled) { info |= HB_EI_FAST; ++n_fast; }
+    else if (!(info & HB_EI_SNOWLIMIT) && !coupled) {
+      // (several snow classes: the general zone step of the fast path loops over them; not while series are recorded)
+      info |= HB_EI_FAST;
+      ++n_fast;
+      if (nc[e] > 1) { nonsoil = true; ++n_fast_classes; }
+    }
     else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX && nash[e] == 0) {
       info |= HB_EI_COUPLED;          // (the fused kernel convolves a unit hydrograph: rconc_nash elements stay general)
       coupled_list.push_back((int32_t)e);
@@ -877,6 +883,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   { int rc_ = upload(h, h->d_gwarps, gwarps); if (rc_) return rc_; }
   h->any_snowlimit = any_snowlimit;
   h->n_fast = n_fast;
+  h->n_fast_classes = n_fast_classes;
   h->n_fast_sib[0] = n_fast_sib[0]; h->n_fast_sib[1] = n_fast_sib[1];
   h->coupled_list = coupled_list;
   if (h->h_model != model) h->have_states = false;
@@ -895,7 +902,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
     for (int64_t e = 0; e < ne; ++e) {
       zone_cell0[e] = h->zone_ptr[e];
       snow_cell0[e] = h->snow_ptr[e];
-      if (!(einfo[e] & HB_EI_FAST)) continue;
+      if (!(einfo[e] & HB_EI_FAST) || nc[e] > 1) continue;   // (several snow classes: the general kernel records their series)
       for (int k = 0; k < nz[e]; ++k) {
         zone_slot[(size_t)h->zone_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);
         snow_slot[(size_t)h->snow_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);   // fast path: one snow class
@@ -1819,7 +1826,8 @@ static int run_land(hb_engine* h) {
   // sibling models on the fast path: only without series (their zone sequences have no staging buffers)
   const bool use_fast_sib = (h->n_fast_sib[0] + h->n_fast_sib[1]) > 0 && h->land_path == HB_LAND_AUTO && !any_series;
   // the general kernel takes every element the two special paths do not take in this run
-  const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0) | (use_fast_sib ? 4 : 0);
+  const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0) | (use_fast_sib ? 4 : 0) |
+                          ((any_series && h->n_fast_classes > 0) ? 8 : 0);
   if (general_key != h->general_key) {
     h->general_list.clear();
     h->sibling_list[0].clear(); h->sibling_list[1].clear();
@@ -1830,7 +1838,7 @@ static int run_land(hb_engine* h) {
         if (!(use_fast_sib && (info & HB_EI_FAST))) h->sibling_list[m - 1].push_back((int32_t)e);
         continue;
       }
-      if ((use_fast && (info & HB_EI_FAST)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
+      if ((use_fast && (info & HB_EI_FAST) && !(any_series && h->h_nc[e] > 1)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
       h->general_list.push_back((int32_t)e);
     }
     int rc = upload(h, h->d_general_list, h->general_list);
@@ -1863,6 +1871,7 @@ static int run_land(hb_engine* h) {
     LandV2Dev v{};
     v.n_elem = h->n_elem; v.e_pad = ep; v.zmax = h->zmax;
     v.nz = h->d_nz.p; v.nu = h->d_nu.p; v.recstep = h->d_recstep.p; v.einfo = h->d_einfo.p; v.fcol = h->d_fcol.p;
+    v.nc = h->d_nc.p; v.skip_classes = any_series ? 1 : 0;
     v.zinfo = h->d_zinfo.p; v.kz = h->d_kz.p; v.ke = h->d_ke.p; v.sfdist = h->d_sfdist.p; v.uh = h->d_uh.p;
     v.ic = h->d_ic.p; v.sm = h->d_sm.p; v.sp = h->d_sp.p; v.wc = h->d_wc.p; v.uz = h->d_uz.p; v.lz = h->d_lz.p;
     v.quh = h->d_quh.p; v.n_col = h->n_col; v.nt_total = h->nt_total; v.forcing = h->d_forcing[h->fcur].p;

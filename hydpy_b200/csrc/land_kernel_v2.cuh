@@ -41,6 +41,8 @@ struct LandV2Dev {
   int64_t e_lo;
   int32_t slab_blocks;
   const int32_t* nz;       // [E_pad]
+  const int32_t* nc;       // [E_pad] snow classes (fast path: class 0 in registers, further classes [c][zmax][E_pad] in place)
+  int32_t skip_classes;    // this run records series: elements with several snow classes go to the general kernel
   const int32_t* nu;       // [E_pad]
   const int32_t* recstep;  // [E_pad]
   const int32_t* einfo;    // [E_pad]  HB_EI_* incl. HB_EI_FAST / HB_EI_SOILONLY
@@ -204,6 +206,9 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
     if (d.fused && (einfo0 & HB_EI_FUSED)) return;   // reduced by the fused instance of this run
   }
   const int einfo = d.einfo[e];
+  // several snow classes (hland_96 only, never in a fused group): the general step below loops over them
+  const int ncls = (ZW == 0 && MODEL == HB_MODEL_HLAND_96) ? d.nc[e] : 1;
+  if (ZW == 0 && ncls > 1 && d.skip_classes) return;
 
   const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
 #define KZ(name) kzk[(int64_t)(name) * ep]
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
   // kernel is latency-bound otherwise (ncu: 62 % issue utilisation, half of the stall cycles are fixed-latency waits).
   const unsigned amask = __activemask();                                             // (fused: all 32 lanes)
   const unsigned omask = ZW > 0 ? __ballot_sync(0xffffffffu, active) : amask;         // lanes that own a zone
-  if (ZW == 0 && __all_sync(amask, soil && fc > 0.0) != SOIL) return;
+  if (ZW == 0 && __all_sync(amask, soil && fc > 0.0 && ncls == 1) != SOIL) return;
   // fused: offsets into the term buffers [G][2][ZW][32]
   const int zw_off = (int)(threadIdx.x >> 5) * 32 + lane;   // (a shadow lane writes its own, never read, cell)
   int tb_off = 0, gs = 0;
@@ -593,17 +598,54 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
       in_ = wc_old - wc;
       bare = sp <= 0.0;
       ncover = (sp > 0.0) ? 1.0 : 0.0;
+      int nbare = bare ? 1 : 0;
+      if (ncls > 1) {
+        // further snow classes (ref: the `for c in range(con.sclass)` loops of the same four methods): their states stay
+        // in the state arrays [class][zone][element], read and written in place (coalesced, L1/L2-resident)
+        const double dnc = (double)ncls;
+        in_ = 0.0 + in_ / dnc;
+        const double rain = tf * fracrain, snow = tf * (1.0 - fracrain);
+        for (int c = 1; c < ncls; ++c) {
+          const int64_t ick = (int64_t)c * tstride + slot;
+          const double sfc = d.sfdist[(int64_t)c * ep + e];
+          double sp_c = d.sp[ick] + sfc * snow, wc_c = d.wc[ick] + sfc * rain;
+          if (tc > ttm) {
+            const double potmelt = cfact * (tc - ttm);
+            const double melt = HB_PYMIN(potmelt, sp_c);
+            sp_c -= melt; wc_c += melt;
+          } else if (tc < ttm) {
+            const double potrefr = cfr_cfmax * (ttm - tc);
+            const double refr = HB_PYMIN(potrefr, wc_c);
+            sp_c += refr; wc_c -= refr;
+          }
+          const double wo = wc_c, lm = whc * sp_c;
+          wc_c = HB_PYMIN(wo, lm);
+          in_ += (wo - wc_c) / dnc;
+          d.sp[ick] = sp_c; d.wc[ick] = wc_c;
+          nbare += (sp_c <= 0.0) ? 1 : 0;
+          ncover += (sp_c > 0.0) ? 1.0 : 0.0;
+        }
+        ncover = ncover / dnc;
+      }
       // ref: hland_model.py:1607-1619 Calc_GAct_V1, 1688-1701 Calc_GlMelt_In_V1
       if (zt == HB_GLACIER) {
         const double ga = g_melt + sinf * g_var;
         const double gact = HB_PYMAX(ga, 0.0);
         s_gact = gact;
-        if (tc > ttm && bare) {
+        if (ncls > 1) {
+          if (tc > ttm) {
+            const double glmeltpot = gact / (double)ncls * (tc - ttm);
+            for (int c = 0; c < nbare; ++c) { s_glmelt += glmeltpot; in_ += glmeltpot; }
+          }
+        } else if (tc > ttm && bare) {
           s_glmelt = gact * (tc - ttm);
           in_ += s_glmelt;
         }
       }
-    } else { sp = 0.0; wc = 0.0; }
+    } else {
+      sp = 0.0; wc = 0.0;
+      for (int c = 1; c < ncls; ++c) { d.sp[(int64_t)c * tstride + slot] = 0.0; d.wc[(int64_t)c * tstride + slot] = 0.0; }
+    }
     if (SERIES) {
       SERZ(HB_S_TC, tc); SERZ(HB_S_FRACRAIN, fracrain); SERZ(HB_S_PC, pc); SERZ(HB_S_TF, tf); SERZ(HB_S_CFACT, s_cfact);
       SERZ(HB_S_GACT, s_gact); SERZ(HB_S_SPL, 0.0); SERZ(HB_S_WCL, 0.0); SERZ(HB_S_SPG, 0.0); SERZ(HB_S_WCG, 0.0);
@@ -837,6 +879,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const int einfo = d.einfo[e];
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
   if (((einfo & HB_EI_FUSED) != 0 && d.fused != 0) != FUSED) return;
+  if (MODEL == HB_MODEL_HLAND_96 && d.skip_classes && d.nc[e] > 1) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;

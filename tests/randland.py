@@ -23,7 +23,9 @@ def random_land(n_elem: int, seed: int = 0, zmax: int = 14, cmax: int = 3, recst
     fast = np.random.default_rng(seed + 4242).uniform(size=ne) < fast_fraction
     in_run = ((np.arange(ne) // soil_runs) % 2 == 0) if soil_runs > 0 else np.zeros(ne, bool)
     fast |= in_run
-    nc[fast] = 1
+    # (the fast path takes several snow classes too: half of the fast elements outside the soil runs keep theirs)
+    one_class = fast & (in_run | (np.random.default_rng(seed + 777).uniform(size=ne) < 0.5))
+    nc[one_class] = 1
     nu = rng.integers(0, 6, size=ne)
     zone_ptr = np.concatenate([[0], np.cumsum(nz)]).astype(np.int64)
     snow_ptr = np.concatenate([[0], np.cumsum(nz * nc)]).astype(np.int64)

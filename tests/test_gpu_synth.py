@@ -673,6 +673,59 @@ def test_recstep_chain_with_out_of_range_power_arguments():
         assert_close(getattr(st_e, n), getattr(st, n), f"extreme response parameters: final {n}")
 
 
+def test_snow_classes_run_on_the_fast_path():
+    """SClass > 1 (ref: hland_model.py:484-499, 1166-1187, 1318-1341, 1434-1448: the `for c in range(con.sclass)` loops):
+    the fast path's general zone step loops over the classes, the general kernel is not launched — unless series are
+    recorded, which sends these elements (and only them) back to it.  Same values as the oracle either way."""
+    import copy
+
+    from hydpy_b200.abi import RiverBundle
+
+    ne, nt = 1500, 72
+    land1, states1 = synth.make_land(ne, "1h", variants=True, seed=3)
+    nz = np.diff(land1.zone_ptr)
+    ncls = 1 + (np.arange(ne) % 3)                      # 1, 2, 3 classes side by side
+    land = copy.deepcopy(land1)
+    land.sfdist_ptr = np.concatenate([[0], np.cumsum(ncls)]).astype(np.int64)
+    rng = np.random.default_rng(9)
+    land.sfdist = np.concatenate([(lambda w: w / w.mean())(rng.uniform(0.5, 1.5, size=c)) for c in ncls])
+    land.snow_ptr = np.concatenate([[0], np.cumsum(nz * ncls)]).astype(np.int64)
+    land.normalise()
+    states = states1.copy()
+    ns = int(land.snow_ptr[-1])
+    states.sp = rng.uniform(0, 20, ns) * (rng.uniform(size=ns) < 0.6)
+    states.wc = rng.uniform(0, 1, ns)
+    for e in range(ne):                                 # lake zones carry no snow
+        lk = np.tile(land.zonetype[land.zone_ptr[e]:land.zone_ptr[e + 1]] == layout.ILAKE, int(ncls[e]))
+        states.sp[land.snow_ptr[e]:land.snow_ptr[e + 1]][lk] = 0.0
+        states.wc[land.snow_ptr[e]:land.snow_ptr[e + 1]][lk] = 0.0
+    forcing, doy = synth.make_forcing(nt, "1h", t0=24 * 20)        # snowfall, melt and refreezing side by side:
+    forcing[1] -= 10.0                                  # around the freezing point
+    st = states.copy()
+    qt, ser = oracle.land_run(land, st, forcing, doy, threads=4, series=("sp", "wc", "in_"))
+    with Engine(0) as eng:
+        eng.set_land(land)
+        eng.set_land_states(states)
+        eng.set_river(RiverBundle.empty(0))
+        eng.set_forcing(forcing, doy)
+        eng.run(land=True, river=False)
+        tm = eng.timing()
+        q, st_e = eng.get_land_outflow(), eng.get_land_states()
+        assert tm["n_fast"] == ne and tm["general_ms"] == 0.0
+        assert_close(q, qt, "snow classes: land outflow")
+        for n in st.NAMES:
+            assert_close(getattr(st_e, n), getattr(st, n), f"snow classes: final {n}")
+        eng.set_land_states(states)
+        eng.select_series(["sp", "wc", "in_"])
+        eng.run(land=True, river=False)
+        tm = eng.timing()
+        assert tm["general_ms"] > 0.0                   # the multi-class elements, with their series
+        assert_close(eng.get_land_outflow(), qt, "snow classes with series: land outflow")
+        for name in ("sp", "wc", "in_"):
+            assert_close(eng.get_series(name), ser[name], f"snow classes: series {name}")
+        eng.select_series([])
+
+
 def test_results_do_not_depend_on_where_an_element_sits():
     """The fast path groups 32 consecutive elements into warps and lets warp-wide votes pick between equivalent code paths
     (branch-free or general zone step, dry shortcuts, unswitched RecStep loop).  Shuffling the elements — what sharding a
