@@ -17,6 +17,8 @@ steps continue the same simulation (states stay on the device).
   ``--scaling weak`` (default): the basin grows with N (N x 10^5 elements, the same depth); ``--scaling strong``: the
   10^5-element basin of N = 1 is cut into N parts.  The last rank re-runs the first window of the WHOLE basin on its own
   GPU and compares its nodes bit for bit (``multi_gpu_parity``).
+* ``--config 2`` — BASELINE.json configs[2]: the 10^5-element basin with DAILY steps (1200 RecStep sub-steps per step), runoff
+  generation only; a step is one simulated year.
 * ``--config 1`` / ``--config 4`` — BASELINE.json configs[1] (HydPy-H-Lahn hourly x 4096 parameter-ensemble members) and
   configs[4] (10^6 zones x 512 members), member-sharded over the ranks (no exchange: every member is a complete basin).
 * ``--impl reference`` — the reference's own CPU implementation of the same window on a bounded element sample with all
@@ -61,7 +63,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--river-sweep", default="", help="routing sweep: persistent | grouped | launches (default: engine's)")
     ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
                     help="N > 1: weak = one basin of N x --elements elements, strong = the --elements basin cut into N parts")
-    ap.add_argument("--config", type=int, choices=(1, 3, 4), default=3, help="BASELINE.json configs[i] (default 3)")
+    ap.add_argument("--config", type=int, choices=(1, 2, 3, 4), default=3, help="BASELINE.json configs[i] (default 3)")
     ap.add_argument("--members", type=int, default=0, help="ensemble members of --config 1 / 4 in total (0 = 4096 / 512)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the unsharded run")
     ap.add_argument("--land-slabs", type=int, default=0, help="element slabs of the fast land path (0 = engine default)")
@@ -208,7 +210,8 @@ class Workload:
     """What one rank simulates: its bundles, the exchange plan of a window and how to describe / verify it."""
 
     def __init__(self, land, states, river, discharge, recv=(), send=(), *, desc: dict, forcing_seed: int = 0,
-                 forcing_fixed=None, members: int = 1, verify=None):
+                 forcing_fixed=None, members: int = 1, verify=None, step: str = "1h"):
+        self.step = step                  # simulation step of the synthetic forcing
         self.land, self.states, self.river, self.discharge = land, states, river, discharge
         self.recv, self.send = list(recv), list(send)
         self.desc, self.forcing_seed, self.forcing_fixed = desc, forcing_seed, forcing_fixed
@@ -293,9 +296,30 @@ def build_members(args: argparse.Namespace, rank: int, world: int) -> Workload:
     return wl
 
 
+def build_daily(args: argparse.Namespace, rank: int, world: int) -> Workload:
+    """configs[2]: 10^5 hland_96 elements x 12 zones, DAILY steps (RecStep = 1200 sub-steps per step), runoff generation only:
+    every element drains into a node of its own, no reaches.  N > 1: independent replicas of the basin's elements (the
+    elements do not interact: nothing to exchange)."""
+    from hydpy_b200 import synth
+    from hydpy_b200.abi import RiverBundle
+
+    ne = args.elements
+    land, states = synth.make_land(ne, "1d", seed=1 + rank)
+    river = RiverBundle.empty(ne)
+    river.entry_ptr = np.arange(ne + 1, dtype=np.int64)
+    river.entry_src = np.arange(ne, dtype=np.int32)
+    river.normalise()
+    desc = {"workload": "configs[2]: synthetic 10^5-element hland_96 basin, 12 zones per element, daily steps (1200 RecStep "
+                        "sub-steps per step), runoff generation only (every element drains into its own node, no reaches)",
+            "basin_elements": ne * world}
+    return Workload(land, states, river, np.zeros(river.n_seg), desc=desc, step="1d")
+
+
 def build_workload(args: argparse.Namespace, dist: "Dist") -> Workload:
     if args.config == 3:
         return build_shard(args, dist.rank, dist.world)
+    if args.config == 2:
+        return build_daily(args, dist.rank, dist.world)
     return build_members(args, dist.rank, dist.world)
 
 
@@ -324,6 +348,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     wl = build_workload(args, dist)
     if wl.forcing_fixed is not None:
         win = wl.forcing_fixed[0].shape[1]
+    elif args.config == 2 and win == 438:
+        win = 365        # one simulated year per step
     elif args.config == 4 and win == 438:
         win = 120        # 5·10^6 nodes per GPU: the node/reach rows of a 438-h window would not fit beside the constants
     states, discharge = wl.states, wl.discharge
@@ -388,7 +414,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         if wl.forcing_fixed is not None:
             f, doys[s] = wl.forcing_fixed
         else:
-            f, doys[s] = synth.make_forcing(win, "1h", seed=wl.forcing_seed, t0=s * win, kind=args.forcing)
+            f, doys[s] = synth.make_forcing(win, wl.step, seed=wl.forcing_seed, t0=s * win, kind=args.forcing)
         pinned.array[s] = f
     zone_steps_per_step = land.n_zone * win
     launches = 0
@@ -638,7 +664,8 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
         "config": {
             **wl.desc,
             "elements_per_gpu": land.n_elem, "zones_per_element": Z, "reaches_per_gpu": river.n_reach,
-            "river_levels": n_levels, "window_steps": win, "simulated_days_timed": K * win / 24.0,
+            "river_levels": n_levels, "window_steps": win,
+            "simulated_days_timed": K * win / (24.0 if wl.step == "1h" else 1.0),
             "recstep_per_step": R, "uh_ordinates": U,
             "forcing_bank": bank,
             "parallelism": (f"one basin, element-sharded x{dist.world} by hydpy_b200.shard.partition, NCCL boundary "
@@ -703,13 +730,27 @@ def cpu_run(args: argparse.Namespace, steps: int, warmup: int, elements: int) ->
 
     cores = os.cpu_count() or 1
     win = args.window
-    land, states = synth.make_land(elements, "1h", seed=1)
-    river, discharge = synth.make_tree_river(elements, "1h", seed=2, levels=max(2, args.levels * elements // args.elements))
+    daily = args.config == 2                     # configs[2]: daily steps, runoff generation only
+    step = "1d" if daily else "1h"
+    if daily and win == 438:
+        win = 365
+    land, states = synth.make_land(elements, step, seed=1)
+    if daily:
+        from hydpy_b200.abi import RiverBundle
+
+        river = RiverBundle.empty(elements)
+        river.entry_ptr = np.arange(elements + 1, dtype=np.int64)
+        river.entry_src = np.arange(elements, dtype=np.int32)
+        river.normalise()
+        discharge = np.zeros(0)
+    else:
+        river, discharge = synth.make_tree_river(elements, step, seed=2,
+                                                 levels=max(2, args.levels * elements // args.elements))
     kind = "reference" if refdriver.available() else "port"
     zone_steps = land.n_zone * win
     times = []
     for s in range(warmup + steps):
-        forcing, doy = synth.make_forcing(win, "1h", seed=0, t0=s * win, kind=args.forcing)
+        forcing, doy = synth.make_forcing(win, step, seed=0, t0=s * win, kind=args.forcing)
         if kind == "reference":
             if s == 0:
                 els = refdriver.prepare_land(land, states, forcing, doy)   # object set-up (once) is not timed
@@ -731,7 +772,7 @@ def cpu_run(args: argparse.Namespace, steps: int, warmup: int, elements: int) ->
     total = float(np.sum(times))
     value = zone_steps * steps / total
     return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{elements} of {args.elements} elements ({land.n_zone} zones) x {win} hourly steps per step, "
+            "sample": f"{elements} of {args.elements} elements ({land.n_zone} zones) x {win} {'daily' if daily else 'hourly'} steps per step, "
                       f"{steps} steps, runoff generation on {cores} threads"
                       f" ({'unmodified reference binaries oracle/_ref' if kind == 'reference' else 'C restatement'})"
                       f" + routing", "ms_per_step": 1e3 * total / steps}
@@ -742,7 +783,8 @@ def auto_cpu_elements(args: argparse.Namespace) -> int:
         return args.cpu_elements
     cores = os.cpu_count() or 1
     # ≈3 µs per element-step and thread: aim at ≈2 s of wall time per step
-    n = int(2.0 * cores / (3e-6 * args.window))
+    # (daily steps: 1200 instead of 50 RecStep sub-steps per step, about 30 µs per element-step)
+    n = int(2.0 * cores / ((30e-6 if args.config == 2 else 3e-6) * (365 if args.config == 2 and args.window == 438 else args.window)))
     return int(max(256, min(args.elements, n // 64 * 64)))
 
 
@@ -772,9 +814,11 @@ def main() -> None:
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                     "data": "synthetic",
-                    "config": {"workload": "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, "
-                                           "hourly, discharge-only (bounded element sample on the host CPU)",
-                               "window_steps": args.window},
+                    "config": {"workload": ("configs[2]: synthetic 10^5-element hland_96 basin, daily steps, runoff generation "
+                                            "only (bounded element sample on the host CPU)" if args.config == 2 else
+                                            "configs[3]: synthetic 10^5-element hland_96 + musk_classic river tree, "
+                                            "hourly, discharge-only (bounded element sample on the host CPU)"),
+                               "window_steps": 365 if args.config == 2 and args.window == 438 else args.window},
                     "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                     "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0,
