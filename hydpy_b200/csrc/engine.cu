@@ -170,8 +170,14 @@ struct hb_engine {
   int fcur = 0;
   cudaEvent_t ev_forcing_ready[2] = {nullptr, nullptr};   // H2D copy into forcing buffer f is complete
   cudaEvent_t ev_forcing_read[2] = {nullptr, nullptr};    // the last land run that reads forcing buffer f is complete
-  double* h_sin[2] = {nullptr, nullptr};                  // pinned staging of the seasonal factor
-  size_t h_sin_cap[2] = {0, 0};
+  // pinned staging of the seasonal factor: a ring, so that the host may enqueue several windows ahead of the device (with
+  // one slot per forcing buffer it waited for the copy of two windows ago at every window — a caller whose thread is
+  // delayed now and then by the OS could not build up a queue to bridge it)
+  static const int SIN_RING = 8;
+  double* h_sin[SIN_RING] = {};
+  size_t h_sin_cap_ring[SIN_RING] = {};
+  cudaEvent_t ev_sin_copied[SIN_RING] = {};
+  unsigned sin_next = 0;
   cudaEvent_t ev_ext_ready[2] = {nullptr, nullptr};   // boundary rows of the window have arrived (NCCL, s_comm)
   cudaEvent_t ev_send_done[2] = {nullptr, nullptr};   // boundary rows of the window have left (their buffers may be reused)
   bool ext_async[2] = {false, false};                 // … and the routing of that window has to wait for them
@@ -629,10 +635,13 @@ void hb_destroy(hb_engine* h) {
   for (int i = 0; i < 2; ++i) {
     if (h->ev_forcing_ready[i]) cudaEventDestroy(h->ev_forcing_ready[i]);
     if (h->ev_forcing_read[i]) cudaEventDestroy(h->ev_forcing_read[i]);
-    if (h->h_sin[i]) cudaFreeHost(h->h_sin[i]);
   }
   for (cudaEvent_t e : {h->ev_ext_ready[0], h->ev_ext_ready[1], h->ev_send_done[0], h->ev_send_done[1]})
     if (e) cudaEventDestroy(e);
+  for (int i = 0; i < hb_engine::SIN_RING; ++i) {
+    if (h->h_sin[i]) cudaFreeHost(h->h_sin[i]);
+    if (h->ev_sin_copied[i]) cudaEventDestroy(h->ev_sin_copied[i]);
+  }
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1735,18 +1744,20 @@ static int stage_forcing(hb_engine* h, int64_t nt, int64_t n_col, const double* 
   if (n) HB_CUDA(h, cudaMemcpyAsync(h->d_forcing[f].p, forcing, n * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
   // 0.5*sin(2*pi*(doy+1)/366-1.39) with the HOST libm, evaluated exactly like the generated C of the reference
   // (ref: hydpy/models/hland/hland_model.py:1056-1058) — the seasonal factor is therefore bit-identical to the CPU path
-  if ((size_t)nt > h->h_sin_cap[f]) {
-    if (h->h_sin[f]) { HB_CUDA(h, cudaEventSynchronize(h->ev_forcing_ready[f])); HB_CUDA(h, cudaFreeHost(h->h_sin[f])); }
-    h->h_sin[f] = nullptr;
-    HB_CUDA(h, cudaHostAlloc((void**)&h->h_sin[f], (size_t)nt * sizeof(double), cudaHostAllocDefault));
-    h->h_sin_cap[f] = (size_t)nt;
-  } else if (h->h_sin[f]) {
-    HB_CUDA(h, cudaEventSynchronize(h->ev_forcing_ready[f]));   // the previous copy out of this staging slot is through
+  const int ss = (int)(h->sin_next++ % hb_engine::SIN_RING);
+  if (!h->ev_sin_copied[ss]) HB_CUDA(h, cudaEventCreateWithFlags(&h->ev_sin_copied[ss], cudaEventDisableTiming));
+  else HB_CUDA(h, cudaEventSynchronize(h->ev_sin_copied[ss]));   // the copy out of this slot, SIN_RING windows ago, is through
+  if ((size_t)nt > h->h_sin_cap_ring[ss]) {
+    if (h->h_sin[ss]) HB_CUDA(h, cudaFreeHost(h->h_sin[ss]));
+    h->h_sin[ss] = nullptr;
+    HB_CUDA(h, cudaHostAlloc((void**)&h->h_sin[ss], (size_t)nt * sizeof(double), cudaHostAllocDefault));
+    h->h_sin_cap_ring[ss] = (size_t)nt;
   }
   const double pi = 3.141592653589793;
-  for (int64_t t = 0; t < nt; ++t) h->h_sin[f][t] = 0.5 * sin((((2.0 * pi) * (double)(doy[t] + 1)) / 366.0) - 1.39);
-  if (nt) HB_CUDA(h, cudaMemcpyAsync(h->d_sinfactor[f].p, h->h_sin[f], (size_t)nt * sizeof(double), cudaMemcpyHostToDevice,
+  for (int64_t t = 0; t < nt; ++t) h->h_sin[ss][t] = 0.5 * sin((((2.0 * pi) * (double)(doy[t] + 1)) / 366.0) - 1.39);
+  if (nt) HB_CUDA(h, cudaMemcpyAsync(h->d_sinfactor[f].p, h->h_sin[ss], (size_t)nt * sizeof(double), cudaMemcpyHostToDevice,
                                      h->s_h2d));
+  HB_CUDA(h, cudaEventRecord(h->ev_sin_copied[ss], h->s_h2d));
   HB_CUDA(h, cudaEventRecord(h->ev_forcing_ready[f], h->s_h2d));
   HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_forcing_ready[f], 0));   // land kernels of the new window wait for it
   h->fcur = f;
@@ -1915,15 +1926,17 @@ static int run_land(hb_engine* h) {
     double budget = 6.0e9;
     // (cudaMemGetInfo costs up to milliseconds of host time — exposed in synchronous runs — so it is only asked when the
     // window does not fit the buffers held already)
-    if ((size_t)nt * per_step > h->d_term_a.cap || (size_t)nt * per_step > h->d_term_b.cap || n_staged > 0) {
+    // (all groups fused: the hand-over buffers are the two [chunk][E_pad] sum arrays, the term buffers do not exist)
+    const size_t cap_a = all_fused ? h->d_red_a.cap : h->d_term_a.cap, cap_b = all_fused ? h->d_red_b.cap : h->d_term_b.cap;
+    if ((size_t)nt * per_step > cap_a || (size_t)nt * per_step > cap_b || n_staged > 0) {
       size_t free_b = 0, total_b = 0;
       if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        const double held = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);   // already ours, counts as available
+        const double held = 8.0 * (double)(cap_a + cap_b);   // already ours, counts as available
         const double quarter = 0.25 * ((double)free_b + held);
         if (quarter > budget) budget = quarter < 32.0e9 ? quarter : 32.0e9;
       }
     }
-    else budget = 8.0 * (double)(h->d_term_a.cap + h->d_term_b.cap);
+    else budget = 8.0 * (double)(cap_a + cap_b);
     int64_t chunk_max = (int64_t)(budget / 8.0) / (per_step * (2 + n_staged));
     if (chunk_max < 8) chunk_max = 8;
     const int64_t want = h->land_chunk >= 0 ? h->land_chunk : (h->comm ? 128 : 0);
