@@ -35,7 +35,8 @@ using namespace hb;
 // dynamic shared memory of zone_kernel<…, ZW>: constants [14][ZW*32] double2 + term buffers [G][2][ZW][32] doubles
 #define HB_FUSE_SMEM(zw) ((size_t)(zw) * 32 * (14 * 16 + ZoneGeom<zw>::G * 2 * 8))
 // zone/snow series the fast path of hland_96 stages in its own layout (first block + the evap submodels' block)
-#define HB_S_STAGED(s) ((s) < HB_S_FIRST_ELEM || ((s) >= HB_S_FIRST_ZONE3 && (s) < HB_S_SC))
+#define HB_S_STAGED(s) ((s) < HB_S_FIRST_ELEM || ((s) >= HB_S_FIRST_ZONE2 && (s) < HB_S_FIRST_ELEM2) || \
+                       ((s) >= HB_S_FIRST_ZONE3 && (s) < HB_S_SC))
 enum { HB_K_BEGIN = -1, HB_K_ZONE = 0, HB_K_ELEMENT = 1, HB_K_GENERAL = 2, HB_K_END = 3, HB_K_OTHER = 4 };
 
 namespace {
@@ -1834,8 +1835,9 @@ static int run_land(hb_engine* h) {
   const bool use_fast = h->n_fast > 0 && h->land_path == HB_LAND_AUTO && !(any_series && h->zmax > 128);
   // elements with capillary flux: fused kernel (no series recording there)
   const bool use_coupled = !h->coupled_list.empty() && h->land_path == HB_LAND_AUTO && !any_series;
-  // sibling models on the fast path: only without series (their zone sequences have no staging buffers)
-  const bool use_fast_sib = (h->n_fast_sib[0] + h->n_fast_sib[1]) > 0 && h->land_path == HB_LAND_AUTO && !any_series;
+  // sibling models on the fast path (their zone sequences are staged like the others')
+  const bool use_fast_sib = (h->n_fast_sib[0] + h->n_fast_sib[1]) > 0 && h->land_path == HB_LAND_AUTO &&
+                            !(any_series && h->zmax > 128);
   // the general kernel takes every element the two special paths do not take in this run
   const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0) | (use_fast_sib ? 4 : 0) |
                           ((any_series && h->n_fast_classes > 0) ? 8 : 0);
@@ -2021,15 +2023,30 @@ static int run_land(hb_engine* h) {
           }
           h->timing.land_launches += 1;
         }
-        // sibling models: the same grid, instantiated for their model (threads of other models retire at once)
+        // sibling models: the same grid, instantiated for their model (threads of other models retire at once).  Their own
+        // zone sequences are staged like the others'; cells of another model's elements must read NaN afterwards
+        if (any_series)   // (also without sibling elements: the sequences then read NaN everywhere)
+          for (int s_ = HB_S_FIRST_ZONE2; s_ < HB_S_FIRST_ELEM2; ++s_)
+            if (h->series_on[s_])
+              HB_CUDA(h, cudaMemsetAsync(h->d_series_stage[s_].p, 0xFF, (size_t)v.nt * per_step * sizeof(double), st));
         if (use_fast_sib && h->n_fast_sib[0] > 0) {
-          zone_kernel<true, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
-          if (h->any_nonsoil_sib[0]) zone_kernel<false, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+          if (any_series) {
+            zone_kernel<true, true, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+            if (h->any_nonsoil_sib[0]) zone_kernel<false, true, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+          } else {
+            zone_kernel<true, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+            if (h->any_nonsoil_sib[0]) zone_kernel<false, false, HB_MODEL_HLAND_96P><<<zgrid, 128, 0, st>>>(v);
+          }
           h->timing.land_launches += 1 + (h->any_nonsoil_sib[0] ? 1 : 0);
         }
         if (use_fast_sib && h->n_fast_sib[1] > 0) {
-          zone_kernel<true, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
-          if (h->any_nonsoil_sib[1]) zone_kernel<false, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+          if (any_series) {
+            zone_kernel<true, true, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+            if (h->any_nonsoil_sib[1]) zone_kernel<false, true, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+          } else {
+            zone_kernel<true, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+            if (h->any_nonsoil_sib[1]) zone_kernel<false, false, HB_MODEL_HLAND_96C><<<zgrid, 128, 0, st>>>(v);
+          }
           h->timing.land_launches += 1 + (h->any_nonsoil_sib[1] ? 1 : 0);
         }
         if (n_slabs > 1) HB_CUDA(h, cudaEventRecord(h->ev_slab_zone[sl], st));
@@ -2070,12 +2087,14 @@ static int run_land(hb_engine* h) {
           elem_done(1);
         }
         if (use_fast_sib && h->n_fast_sib[0] > 0) {
-          element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, elem_stream(2)>>>(v);
+          if (any_series) element_kernel<true, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, elem_stream(2)>>>(v);
+          else element_kernel<false, HB_MODEL_HLAND_96P><<<egrid, 64, esmem, elem_stream(2)>>>(v);
           h->timing.land_launches += 1;
           elem_done(2);
         }
         if (use_fast_sib && h->n_fast_sib[1] > 0) {
-          element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, elem_stream(3)>>>(v);
+          if (any_series) element_kernel<true, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, elem_stream(3)>>>(v);
+          else element_kernel<false, HB_MODEL_HLAND_96C><<<egrid, 64, esmem, elem_stream(3)>>>(v);
           h->timing.land_launches += 1;
           elem_done(3);
         }

@@ -500,12 +500,16 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
       } else if (MODEL == HB_MODEL_HLAND_96P) {
         double dp, rs, ri, gr1, rg1;
         response_96p(r, kpercmax, kx0, kx1, kx2, kx3, kx4, kx5, kx6, zx1, zx2, dp, rs, ri, gr1, rg1);
+        SERZ(HB_S_DP, dp); SERZ(HB_S_RS, rs); SERZ(HB_S_RI, ri); SERZ(HB_S_GR1, gr1); SERZ(HB_S_RG1, rg1);
+        SERZ(HB_S_SUZ, zx1); SERZ(HB_S_SG1, zx2);
         HB_ZONE_STEP_END(w_a * (rs + ri + rg1), w_b * (dp - gr1))
       } else {
         // ref: hland_model.py:2833-2853 Calc_QAb1_QVs1_BW1_V1, 2927-2947 Calc_QAb2_QVs2_BW2_V1
         double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
         qab_qvs_bw(kx0, kx1, kx2, zx1, r, qab1, qvs1, T);
         qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
+        SERZ(HB_S_QAB1, qab1); SERZ(HB_S_QVS1, qvs1); SERZ(HB_S_QAB2, qab2); SERZ(HB_S_QVS2, qvs2);
+        SERZ(HB_S_BW1, zx1); SERZ(HB_S_BW2, zx2);
         HB_ZONE_STEP_END(w_a * (qab1 + qab2), w_b * qvs2)
       }
       if (ZW > 0) {
@@ -750,20 +754,32 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
       }
     }
     if (MODEL != HB_MODEL_HLAND_96) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;   // recorded only: dp rs ri gr1 rg1 | qab1 qvs1 qab2 qvs2
       if (upper) {
         if (MODEL == HB_MODEL_HLAND_96P) {
           double dp, rs, ri, gr1, rg1;
           response_96p(r_z, kpercmax, kx0, kx1, kx2, kx3, kx4, kx5, kx6, zx1, zx2, dp, rs, ri, gr1, rg1);
           ta = w_a * (rs + ri + rg1);
           tb = w_b * (dp - gr1);
+          s0 = dp; s1 = rs; s2 = ri; s3 = gr1; s4 = rg1;
         } else {
           double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
           qab_qvs_bw(kx0, kx1, kx2, zx1, r_z, qab1, qvs1, T);
           qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
           ta = w_a * (qab1 + qab2);
           tb = w_b * qvs2;
+          s0 = qab1; s1 = qvs1; s2 = qab2; s3 = qvs2;
         }
       } else { zx1 = 0.0; zx2 = 0.0; }   // ILAKE (terms set above), SEALED (ta = w_a * r)
+      if (SERIES) {
+        if (MODEL == HB_MODEL_HLAND_96P) {
+          SERZ(HB_S_DP, s0); SERZ(HB_S_RS, s1); SERZ(HB_S_RI, s2); SERZ(HB_S_GR1, s3); SERZ(HB_S_RG1, s4);
+          SERZ(HB_S_SUZ, zx1); SERZ(HB_S_SG1, zx2);
+        } else {
+          SERZ(HB_S_QAB1, s0); SERZ(HB_S_QVS1, s1); SERZ(HB_S_QAB2, s2); SERZ(HB_S_QVS2, s3);
+          SERZ(HB_S_BW1, zx1); SERZ(HB_S_BW2, zx2);
+        }
+      }
     }
     HB_ZONE_STEP_END(ta, tb)
   }
@@ -987,6 +1003,14 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       const double outrc = uh_smem ? uh_outflow_staged(d.uh, ep, e, nu, inrc, s_sc + threadIdx.x, s_uw)
                                  : rconc_outflow<true>(d.uh, d.quh, d.ke, ep, e, nu, nash_steps, inrc, s_sc + threadIdx.x, 64);
       d.qt[(d.t_out + t) * ep + e] = qfactor * outrc;
+      if (SERIES) {
+#define SERE(id, v) do { if (d.series[id]) d.series[id][(d.t_out + t) * d.n_elem + e] = (v); } while (0)
+        record_sc(d.series[HB_S_SC], d.t_out + t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
+        SERE(HB_S_GR2, gr2); SERE(HB_S_GR3, gr3); SERE(HB_S_RG2, rg2); SERE(HB_S_RG3, rg3); SERE(HB_S_SG2, sg2);
+        SERE(HB_S_SG3, sg3); SERE(HB_S_INRC, inrc); SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, outrc);
+        SERE(HB_S_QT, qfactor * outrc);
+#undef SERE
+      }
       continue;
     }
     if (MODEL == HB_MODEL_HLAND_96C) {
@@ -1014,6 +1038,13 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
       lz -= q1;
       const double rt = d.ke[KE_RELLANDAREA * ep + e] * outrc + rellower * q1;
       d.qt[(d.t_out + t) * ep + e] = qfactor * rt;
+      if (SERIES) {
+#define SERE(id, v) do { if (d.series[id]) d.series[id][(d.t_out + t) * d.n_elem + e] = (v); } while (0)
+        record_sc(d.series[HB_S_SC], d.t_out + t, d.n_uh, d.uh0[e], d.quh, ep, e, nu, nash_steps);
+        SERE(HB_S_Q1, q1); SERE(HB_S_INRC, inrc); SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, rt); SERE(HB_S_QT, qfactor * rt);
+        SERE(HB_S_LZ, lz);
+#undef SERE
+      }
       continue;
     }
     double inuz = 0.0, contriarea = 1.0, logsum = 0.0;   // logsum: sum of weight * log(sm/fc) over the soil zones

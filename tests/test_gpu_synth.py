@@ -673,6 +673,38 @@ def test_recstep_chain_with_out_of_range_power_arguments():
         assert_close(getattr(st_e, n), getattr(st, n), f"extreme response parameters: final {n}")
 
 
+@pytest.mark.parametrize("model", ["hland_96p", "hland_96c"])
+def test_sibling_series_come_from_the_fast_path(model):
+    """Requested series of hland_96p / hland_96c elements (their own zone and element sequences included) are recorded by
+    the sibling instances of the two fast-path kernels: the general kernel is not launched, every sequence equals the
+    oracle's, sequences of the other sibling model read NaN."""
+    from hydpy_b200.abi import RiverBundle
+
+    ne, nt = 1200, 48
+    land, states = synth.make_land(ne, "1h", variants=True, model=model, seed=6)
+    forcing, doy = synth.make_forcing(nt, "1h", t0=1500)
+    st = states.copy()
+    qt, ser = oracle.land_run(land, st, forcing, doy, threads=4, series=layout.SERIES)
+    with Engine(0) as eng:
+        eng.set_land(land)
+        eng.set_land_states(states)
+        eng.set_river(RiverBundle.empty(0))
+        eng.select_series(layout.SERIES)
+        eng.set_forcing(forcing, doy)
+        eng.run(land=True, river=False)
+        tm = eng.timing()
+        assert tm["n_fast"] == ne and tm["general_ms"] == 0.0
+        assert_close(eng.get_land_outflow(), qt, f"{model} with series: land outflow")
+        for name in layout.SERIES:
+            assert_close(eng.get_series(name), ser[name], f"{model}: series {name}")
+        other = layout.SERIES_96C_ONLY if model == "hland_96p" else layout.SERIES_96P_ONLY
+        assert all(np.isnan(eng.get_series(name)).all() for name in other)
+        st_e = eng.get_land_states()
+        for n in st.NAMES:
+            assert_close(getattr(st_e, n), getattr(st, n), f"{model} with series: final {n}")
+        eng.select_series([])
+
+
 def test_snow_classes_run_on_the_fast_path():
     """SClass > 1 (ref: hland_model.py:484-499, 1166-1187, 1318-1341, 1434-1448: the `for c in range(con.sclass)` loops):
     the fast path's general zone step loops over the classes, the general kernel is not launched — unless series are
