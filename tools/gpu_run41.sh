@@ -1,4 +1,4 @@
-O=gpurun_out/r03p; mkdir -p $O
+O=gpurun_out/r03y; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; python -c "
 import json; d=json.load(open('$O/bench_n1.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['cpu_baseline']['value'], d['roofline']['frac'], d['roofline']['kernel'])"
