@@ -12,15 +12,24 @@
 //                    32 consecutive elements: all loads/stores are coalesced and ragged zone counts only retire warps.
 //   element_kernel : one thread per element, persistent over the chunk: adds the zone terms in ZONE ORDER (the
 //                    reference's summation order: Calc_InUZ_V1, Calc_ContriArea_V1, Calc_LZ_V1, Calc_EL_LZ_V1,
-//                    Calc_InRC_V1), then the sequential RecStep loop of Calc_Q0_Perc_UZ_V1, the lower zone and the unit
-//                    hydrograph.  It needs ≈56 registers, so all 10^5 chains are resident at once (5.3 warps per
-//                    scheduler), which is what hides the ≈15 k-cycle dependent chain of the 50 sub-steps.
+//                    Calc_InRC_V1) — unless the zone kernel has done that (below) —, then the sequential RecStep loop of
+//                    Calc_Q0_Perc_UZ_V1, the lower zone and the unit hydrograph.  All 10^5 chains are resident at once
+//                    (5.3 warps per scheduler), which is what hides the dependent chain of the 50 sub-steps.
+//
+// Round 2 (profiles/r02n_summary.txt):
+//   * zone_kernel<…, ZW>: where all zones of 32 consecutive elements are FIELD/FOREST, the block is the group's zone warps
+//     and adds the zone terms itself, in zone order, every four steps (north_star's in-kernel zone→element reduction):
+//     16 B per element-step through HBM instead of 32 B per zone-step;
+//   * the RecStep chain in a short form (exact rewrite of percolation/outflow, base-2 power function with the step's
+//     invariants folded in: 15 instead of 26 dependent FP64 instructions per sub-step), chosen per element by its own
+//     data; warp-uniform exits for dry sub-steps;
+//   * several snow classes in the general zone step; series of the sibling models.
 //
 // The split is legal exactly when the zone equations do not read the element state of the previous step, i.e. when
 // every CFlux of the element is zero (then Calc_CF_SM_V1 yields min(0*(1-sm/fc), uz+r, fc-sm) = the value without the
 // uz term, because uz >= 0 and r >= 0; ref: hydpy/models/hland/hland_model.py:1904-1919) — the Lahn default and the
-// synthetic configs.  Elements with CFlux > 0, several snow classes, a finite SMax (snow redistribution) or requested
-// series run through land_kernel.cuh, which covers everything.
+// synthetic configs.  Elements with CFlux > 0 (land_kernel_coupled.cuh) or a finite SMax (snow redistribution) run
+// elsewhere; land_kernel.cuh covers everything.
 //
 // Numerics: same formulas and operand order as land_kernel.cuh; deliberate deviations (each <= 1 ulp per operation,
 // inside the 1e-9 parity bar, measured in tests/test_gpu_*): divisions by the step-invariant constants RfCF, SfCF,
