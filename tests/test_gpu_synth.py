@@ -593,6 +593,36 @@ def test_sixty_four_parameter_sets_in_one_run_equal_sequential_oracle_runs():
     assert np.ptp(ref_nse[:, 0]) > 1e-3            # the sets really differ
 
 
+@pytest.mark.parametrize("zones", [1, 2, 3, 5, 7, 10])
+def test_fused_zone_kernel_instances_for_small_zone_counts(zones):
+    """`zone_kernel<…, ZW>` exists for blocks of 1, 2, 3, 4, 6, 8 and 12 zone warps (the smallest that holds the basin's
+    largest zone count): every instance against the term buffers (bit for bit) and the oracle."""
+    from hydpy_b200.abi import RiverBundle
+
+    ne, nt = 700, 40
+    land, states = synth.make_land(ne, "1h", zones=zones, seed=zones)
+    forcing, doy = synth.make_forcing(nt, "1h", t0=4000)
+    out = []
+    with Engine(0) as eng:
+        for fuse in (False, True):
+            eng.set_land(land)
+            eng.set_land_states(states)
+            eng.set_river(RiverBundle.empty(0))
+            eng.set_land_fuse(fuse)
+            eng.set_forcing(forcing, doy)
+            eng.run(land=True, river=False)
+            tm = eng.timing()
+            assert tm["n_fused"] == (ne if fuse else 0)
+            out.append((eng.get_land_outflow(), eng.get_land_states()))
+    (q0, s0), (q1, s1) = out
+    assert np.array_equal(q0, q1)
+    for n in s0.NAMES:
+        assert np.array_equal(getattr(s0, n), getattr(s1, n)), n
+    st = states.copy()
+    qt, _ = oracle.land_run(land, st, forcing, doy, threads=4)
+    assert_close(q1, qt, f"{zones} zones: land outflow")
+
+
 @pytest.mark.parametrize("case", ["synthetic", "ragged"])
 def test_zone_terms_added_inside_the_zone_kernel_give_the_same_bits(case):
     """HB_OPT_LAND_FUSE: groups of 32 consecutive elements whose zones all run the branch-free step have their zone terms
