@@ -908,6 +908,8 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
+// (development builds for A/B timing, `python -m hydpy_b200.build --variant x -DHB_ELEM_NO_UHSMEM` etc.: the unit hydrograph in
+// global memory, the RecStep chain in its general form only, no early exits for dry sub-steps)
 #ifdef HB_ELEM_NO_UHSMEM
   const bool uh_smem = false;
 #else

@@ -197,7 +197,7 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // the SM's L1: CCTL.IVALL, 13 % of the kernel's stall samples), the bookkeeping of the bounded spin runs every 1024th
 // poll, and ONE acquire load of the same counter after the loop orders the reads that follow.  False: spin limit / error.
 #ifndef HB_WAVE_POLL
-#define HB_WAVE_POLL 2
+#define HB_WAVE_POLL 2   // 1: round 1's form (an ld.acquire and the full bookkeeping per poll), for A/B timing
 #endif
 __device__ __forceinline__ bool wait_progress(const int* flag, int need, const int* error) {
 #if HB_WAVE_POLL == 2
@@ -545,6 +545,8 @@ __device__ __forceinline__ bool reach_chunk(const RiverDev& d, const TaskPrep& t
     const int nticks = len + nseg - 1;
     // (≈40 warp instructions per tick for five flops: everything that does not depend on the tick stays out of the loop)
     const bool record = d.dis_series != nullptr;
+// (HB_WAVE_TICK = 2, measured and rejected: the last segment's lane stores the outflow row tick by tick instead of the
+// shuffle that collects it into lane = time step — 6.2 -> 9.0 ms for the whole network)
 #ifndef HB_WAVE_TICK
 #define HB_WAVE_TICK 1
 #endif
