@@ -558,7 +558,7 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     # Work in SURVEY's convention (add/mul/cmp/div/pow/exp = 1 op each): 130 ops per zone-step in the thread-per-zone
     # kernel, 14 R + 2 U + 32 ops per element-step in the thread-per-element kernel — counted as EXECUTED: the device
     # counters of the timed region (hb_get_timing) say how many element-steps ran the RecStep chain (6 ops per sub-step)
-    # and how many sub-steps had water in the upper zone (8 more ops, one of them the pow); skipped work does not count.
+    # and how many sub-steps evaluated the power function (8 more ops, one of them the pow); skipped work does not count.
     fp64_peak = eng.measure_fp64_peak()
     peak_ops = fp64_peak / 2.0                                             # T FP64 instructions/s (an FMA = 1 op)
     R, U, Z = int(land.recstep[0]), int(land.uh_ptr[1] - land.uh_ptr[0]), land.n_zone / land.n_elem

@@ -113,7 +113,8 @@ enum { HB_CNT_ZONE_WARPSTEPS = 0,   // warp-steps of the branch-free (FIELD/FORE
        HB_CNT_ZONE_STEPS_WET,       // … with in_ > 0 (water reaches the soil: Calc_R_SM_V1 pays for its power function)
        HB_CNT_ELEM_STEPS,           // element-steps of the element kernel (hland_96)
        HB_CNT_ELEM_STEPS_RUN,       // … that ran the RecStep chain of Calc_Q0_Perc_UZ_V1
-       HB_CNT_SUBSTEPS_POW,         // RecStep sub-steps with uz > 0 (a pow each), per element
+       HB_CNT_SUBSTEPS_POW,         // RecStep sub-steps that evaluated the power function, per element (short form: every
+                                    // sub-step its loop runs; general loop: those with uz > 0; a quadratic response: none)
        HB_CNT_ELEM_WARPSTEPS,       // warp-steps of the element kernel (32 elements x 1 step)
        HB_CNT_ELEM_WARPSTEPS_RUN,   // … in which at least one lane ran the chain (what the FP64 pipe is busy with)
        HB_CNT_COUNT };
@@ -937,7 +938,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   double sg2 = 0.0, sg3 = 0.0;
   if (MODEL == HB_MODEL_HLAND_96P) { sg2 = d.ex1[e]; sg3 = d.ex2[e]; }
   const int64_t tstride = (int64_t)d.zmax * ep;
-  unsigned n_run = 0, n_pow = 0;   // element-steps that ran the RecStep chain, sub-steps with uz > 0
+  unsigned n_run = 0, n_pow = 0;   // element-steps that ran the RecStep chain, sub-steps that evaluated the power function
   unsigned n_wrun = 0;             // (warp-uniform) steps in which some lane of the warp ran it
   const unsigned emask = __activemask();
   double nx_a = 0.0, nx_b = 0.0;    // FUSED: the sums of the next step, loaded one step ahead
@@ -1129,7 +1130,6 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
               u = dd - q;
               pos = p && (u > 0.0);
               if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
-              n_pow += p ? 1u : 0u;
               a = pos ? u + dt_inuz : dt_inuz;
             }
 #ifndef HB_ELEM_NO_EARLYOUT
@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
           const double c2 = resp ? fma(-alpha1 * HB_CLIT(HB_C_L1), beta_last * logsum, log2_dtk) : log2_dtk;
           double a = uz + dt_inuz, u = 0.0;
           bool pos = false, bad = false;
-          unsigned np_ = 0;
+          int n_eval = recstep;                     // power functions evaluated: every sub-step this loop runs
           const bool refill = dt_inuz > perc_pot;
           for (int i = 0, hi = 2; i < recstep; hi = hi == 2 ? 8 : recstep) {   // (runs of 2, 6 and the rest: see the quadratic loop)
             const int end = hi < recstep ? hi : recstep;
@@ -1159,11 +1159,11 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
               u = dd - q;
               pos = p && (u > 0.0);
               if (p) q0_sum += pos ? q : dd;      // min(q, dd): u == 0 means q == dd
-              np_ += p ? 1u : 0u;
               a = pos ? u + dt_inuz : dt_inuz;
             }
 #ifndef HB_ELEM_NO_EARLYOUT
             if (i < recstep && __all_sync(__activemask(), !pos && !refill)) {
+              n_eval = i;
               for (; i < recstep; ++i) perc_sum += dt_inuz;
               break;
             }
@@ -1171,7 +1171,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
           }
           uz = pos ? u : 0.0;
           if (bad) { redo = true; uz = uz_old; perc_sum = 0.0; q0_sum = 0.0; }   // out-of-range power: general loop
-          else n_pow += np_;
+          else n_pow += (unsigned)n_eval;
         }
       }
       if (redo) {

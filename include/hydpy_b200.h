@@ -474,7 +474,7 @@ typedef struct hb_timing {
   int64_t zone_steps_wet;      /* ... with in_ > 0                                                                      */
   int64_t elem_steps;          /* element-steps of the element kernel                                                   */
   int64_t elem_steps_run;      /* ... that ran the RecStep chain of Calc_Q0_Perc_UZ_V1 (not: uz == 0 and inuz == 0)     */
-  int64_t substeps_pow;        /* RecStep sub-steps with uz > 0, i.e. with a pow (of recstep * elem_steps_run)          */
+  int64_t substeps_pow;        /* RecStep sub-steps that evaluated the power function (of recstep * elem_steps_run)      */
   int64_t elem_warpsteps;      /* warp-steps (32 elements x 1 step) of the element kernel                               */
   int64_t elem_warpsteps_run;  /* ... in which at least one lane ran the chain                                          */
   int64_t n_fused;             /* elements whose zone terms the zone kernel added itself (HB_OPT_LAND_FUSE), last run    */
