@@ -635,7 +635,9 @@ def run_engine(args: argparse.Namespace, dist: Dist) -> dict:
     if not n_fast:
         dominant, dom_ms, dom_ops = "land_kernel (general)", general_ms_avg, zone_ops + element_ops
         dom_bytes = 40 * land.n_elem * win
-    elif element_ms_avg > zone_ms_avg:
+    elif (iso["element_ms"] > iso["zone_ms"]) if (iso["zone_ms"] > 0.0 and iso["element_ms"] > 0.0) else (element_ms_avg > zone_ms_avg):
+        # (by the whole-basin launches timed alone where they exist: the events inside the pipeline bracket one slab's
+        # kernel together with whatever shares the SMs with it)
         dominant, dom_ms, dom_ops = "element_kernel", element_ms_avg, element_ops * slab0_share
         dom_bytes = kernels["element_kernel"]["algorithmic_bytes_per_launch"] * slab0_share
     else:
