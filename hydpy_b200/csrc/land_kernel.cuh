@@ -175,10 +175,15 @@ __device__ __forceinline__ void zone_front(const double* __restrict__ kzk, int64
 }
 
 // ref: hland_model.py:2550-2619 Calc_QAb_QVs_BW_V1 (hland_96c): the reference's tail recursion (t0 := t1) as a loop.
-// `log` is libdevice's (the routine runs in the general kernel only); the iteration cap turns a non-advancing t1 — on
-// which the reference would exhaust its stack — into a NaN result instead of a hang.
-__device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, double& s0, double qz_, double& qa1,
-                                        double& qa2, TabRef T) {
+// The iteration cap turns a non-advancing t1 — on which the reference would exhaust its stack — into a NaN result
+// instead of a hang.  FAST = false (general kernel): libdevice `log`, IEEE divisions, the reference's operations one by
+// one.  FAST = true (thread-per-zone kernel, twice per zone-step): the table logarithm of fastmath.cuh and divisions as
+// multiplications by correctly rounded reciprocals (`__drcp_rn`: half the instructions of a division, <= 1 ulp from it) —
+// inside the 1e-9 parity bar like the other reciprocals of the fast path.
+#define HB_QDIV(a, b) (FAST ? (a) * __drcp_rn(b) : (a) / (b))
+template <bool FAST>
+__device__ __noinline__ void qab_qvs_bw_t(double h_, double k1_, double k2_, double& s0, double qz_, double& qa1,
+                                          double& qa2, TabRef T) {
   double t0 = 0.0;
   for (int it = 0; it < 4096; ++it) {
     double s0_ = s0, t1, dt_;
@@ -186,8 +191,9 @@ __device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, doubl
       qa1 += s0_ - h_;
       s0 = s0_ = h_;
     }
-    if ((k1_ == 0.0) && (s0_ == h_) && (qz_ > h_ / k2_)) {
-      const double qa2_ = h_ / k2_;
+    const double h_k2 = HB_QDIV(h_, k2_);
+    if ((k1_ == 0.0) && (s0_ == h_) && (qz_ > h_k2)) {
+      const double qa2_ = h_k2;
       dt_ = 1.0 - t0;
       qa2 += dt_ * qa2_;
       qa1 += dt_ * (qz_ - qa2_);
@@ -196,10 +202,13 @@ __device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, doubl
       qa2 += s0_ + qz_;
       s0 = 0.0;
       return;
-    } else if ((s0_ < h_) || (s0_ == h_ && qz_ <= h_ / k2_)) {
-      if ((s0_ == h_) || (qz_ <= h_ / k2_)) t1 = 1.0;
-      else if (isinf(k2_)) t1 = (h_ - s0_) / qz_;
-      else t1 = t0 + k2_ * log((qz_ - s0_ / k2_) / (qz_ - h_ / k2_));
+    } else if ((s0_ < h_) || (s0_ == h_ && qz_ <= h_k2)) {
+      if ((s0_ == h_) || (qz_ <= h_k2)) t1 = 1.0;
+      else if (isinf(k2_)) t1 = HB_QDIV(h_ - s0_, qz_);
+      else {
+        const double arg = HB_QDIV(qz_ - HB_QDIV(s0_, k2_), qz_ - h_k2);
+        t1 = t0 + k2_ * (FAST ? hb_log(arg, T) : log(arg));
+      }
       if (0.0 < t1 && t1 < 1.0) {
         qa2 += (t1 - t0) * qz_ - (h_ - s0_);
         s0 = h_;
@@ -210,27 +219,28 @@ __device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, doubl
       } else {
         dt_ = 1.0 - t0;
         const double k2qz = k2_ * qz_;
-        s0 = k2qz - (k2qz - s0_) * hb_exp(-dt_ / k2_, T);
+        s0 = k2qz - (k2qz - s0_) * hb_exp(HB_QDIV(-dt_, k2_), T);
         qa2 += s0_ - s0 + dt_ * qz_;
       }
       return;
     } else {
-      const double v1 = 1.0 / k1_ + 1.0 / k2_;
-      const double v2 = qz_ + h_ / k1_;
+      const double v1 = HB_QDIV(1.0, k1_) + HB_QDIV(1.0, k2_);
+      const double v2 = qz_ + HB_QDIV(h_, k1_);
       const double nom = v2 - h_ * v1;
       const double denom = v2 - s0_ * v1;
       bool one = (s0_ == h_) || (denom == 0.0);
-      if (!one) { const double q = nom / denom; one = !(0.0 < q && q <= 1.0); }
+      double q = 1.0;
+      if (!one) { q = HB_QDIV(nom, denom); one = !(0.0 < q && q <= 1.0); }
       if (one) t1 = 1.0;
       else {
-        t1 = t0 - 1.0 / v1 * log(nom / denom);
+        t1 = t0 - HB_QDIV(1.0, v1) * (FAST ? hb_log(q, T) : log(HB_QDIV(nom, denom)));
         t1 = HB_PYMIN(t1, 1.0);
       }
       dt_ = t1 - t0;
-      const double v3 = (v2 * dt_) / v1;
-      const double v4 = denom / (v1 * v1) * (1.0 - hb_exp(-dt_ * v1, T));
-      const double qa1_ = (v3 - v4 - h_ * dt_) / k1_;
-      const double qa2_ = (v3 - v4) / k2_;
+      const double v3 = HB_QDIV(v2 * dt_, v1);
+      const double v4 = HB_QDIV(denom, v1 * v1) * (1.0 - hb_exp(-dt_ * v1, T));
+      const double qa1_ = HB_QDIV(v3 - v4 - h_ * dt_, k1_);
+      const double qa2_ = HB_QDIV(v3 - v4, k2_);
       qa1 += qa1_;
       qa2 += qa2_;
       if (t1 == 1.0) s0 += dt_ * qz_ - qa1_ - qa2_;
@@ -240,6 +250,11 @@ __device__ __noinline__ void qab_qvs_bw(double h_, double k1_, double k2_, doubl
     }
   }
   s0 = qa1 = qa2 = __longlong_as_double(0x7ff8000000000000LL);
+}
+#undef HB_QDIV
+__device__ __forceinline__ void qab_qvs_bw(double h_, double k1_, double k2_, double& s0, double qz_, double& qa1,
+                                           double& qa2, TabRef T) {
+  qab_qvs_bw_t<false>(h_, k1_, k2_, s0, qz_, qa1, qa2, T);
 }
 
 // ref: hland_model.py:4109-4116 Calc_OutRC_V1; rconc_model.py:89-95 Determine_Outflow_V1 (rconc_uh), :179-197

@@ -516,8 +516,8 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
       } else {
         // ref: hland_model.py:2833-2853 Calc_QAb1_QVs1_BW1_V1, 2927-2947 Calc_QAb2_QVs2_BW2_V1
         double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
-        qab_qvs_bw(kx0, kx1, kx2, zx1, r, qab1, qvs1, T);
-        qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
+        qab_qvs_bw_t<true>(kx0, kx1, kx2, zx1, r, qab1, qvs1, T);
+        qab_qvs_bw_t<true>(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
         SERZ(HB_S_QAB1, qab1); SERZ(HB_S_QVS1, qvs1); SERZ(HB_S_QAB2, qab2); SERZ(HB_S_QVS2, qvs2);
         SERZ(HB_S_BW1, zx1); SERZ(HB_S_BW2, zx2);
         HB_ZONE_STEP_END(w_a * (qab1 + qab2), w_b * qvs2)
@@ -774,8 +774,8 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
           s0 = dp; s1 = rs; s2 = ri; s3 = gr1; s4 = rg1;
         } else {
           double qab1 = 0.0, qvs1 = 0.0, qab2 = 0.0, qvs2 = 0.0;
-          qab_qvs_bw(kx0, kx1, kx2, zx1, r_z, qab1, qvs1, T);
-          qab_qvs_bw(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
+          qab_qvs_bw_t<true>(kx0, kx1, kx2, zx1, r_z, qab1, qvs1, T);
+          qab_qvs_bw_t<true>(kx3, kx4, kx5, zx2, qvs1, qab2, qvs2, T);
           ta = w_a * (qab1 + qab2);
           tb = w_b * qvs2;
           s0 = qab1; s1 = qvs1; s2 = qab2; s3 = qvs2;
