@@ -39,6 +39,13 @@ _AET_CONTROL = ("temperaturethresholdice", "maxsoilwater", "soilmoisturelimit", 
 _PET_CONTROL = (
     "hrualtitude", "evapotranspirationfactor", "altitudefactor", "precipitationfactor", "airtemperaturefactor",
 )
+#: PET submodels of `evap_aet_hbv96` the engine serves.  `evap_ret_io` (reference evapotranspiration from an external
+#: time series, adjusted per zone; ref: hydpy/models/evap_ret_io.py:53-64, evap_model.py:4987-4993, 5420-5424) runs on
+#: the same kernels: its input series takes the place of NormalEvapotranspiration, and with AirTemperatureFactor =
+#: AltitudeFactor = PrecipitationFactor = 0 the evap_pet_hbv96 equations return  ret * 1.0 * exp(-0.0) = ret  bit for
+#: bit (for ret >= 0, which `_pet_inputs` checks: the HBV96 clipping to [0, 2 * NormalEvapotranspiration] is the only
+#: step that would treat a negative value differently).
+_PET_MODELS = ("evap_pet_hbv96", "evap_ret_io")
 
 
 class UnsupportedModelError(NotImplementedError):
@@ -117,9 +124,9 @@ def _check_land_model(element: Any) -> None:
             f"`{None if aet is None else _modelname(aet)}`"
         )
     pet = getattr(aet, "petmodel", None)
-    if pet is None or _modelname(pet) != "evap_pet_hbv96":
+    if pet is None or _modelname(pet) not in _PET_MODELS:
         raise UnsupportedModelError(
-            f"element `{element.name}`: evap_aet_hbv96 needs an `evap_pet_hbv96` PET submodel, found "
+            f"element `{element.name}`: evap_aet_hbv96 needs an `evap_pet_hbv96` or `evap_ret_io` PET submodel, found "
             f"`{None if pet is None else _modelname(pet)}`"
         )
     if getattr(aet, "snowycanopymodel", None) is not None:
@@ -130,8 +137,9 @@ def _check_land_model(element: Any) -> None:
             f"element `{element.name}`: only `rconc_uh`, `rconc_nash` (or no) runoff concentration submodel is supported, "
             f"found `{_modelname(rconc)}`"
         )
-    for seq in (model.sequences.inputs.p, model.sequences.inputs.t, pet.sequences.inputs.normalairtemperature,
-                pet.sequences.inputs.normalevapotranspiration):
+    for seq in (model.sequences.inputs.p, model.sequences.inputs.t, *_pet_input_sequences(pet)):
+        if seq is None:
+            continue
         if getattr(seq, "node2idx", None):
             continue                                  # fed by an input node: see `_input_series`
         if not seq.ramflag:
@@ -141,6 +149,15 @@ def _check_land_model(element: Any) -> None:
             )
     if len(tuple(getattr(element, "outputs", ()))):
         raise UnsupportedModelError(f"element `{element.name}`: output nodes are not supported")
+
+
+def _pet_input_sequences(pet: Any) -> tuple[Any, Any]:
+    """The input sequences behind forcing rows 2 and 3 (NormalAirTemperature, NormalEvapotranspiration) of a PET
+    submodel; `evap_ret_io` has no temperature input (row 2 stays zero) and its ReferenceEvapotranspiration is row 3."""
+    inp = pet.sequences.inputs
+    if _modelname(pet) == "evap_ret_io":
+        return None, inp.referenceevapotranspiration
+    return inp.normalairtemperature, inp.normalevapotranspiration
 
 
 def _input_series(element: Any, seq: Any, i0: int, i1: int) -> np.ndarray:
@@ -254,7 +271,8 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
             # ref: hydpy/models/hland_96c.py (control K4, Gamma)
             epar[ep["k4"], e] = con.k4.value
             epar[ep["gamma"], e] = con.gamma.value
-        epar[ep["petaltitude"], e] = pet.parameters.derived.altitude.value
+        ret_io = _modelname(pet) == "evap_ret_io"
+        epar[ep["petaltitude"], e] = 0.0 if ret_io else pet.parameters.derived.altitude.value
         zp = np.zeros((len(layout.ZPAR), nz))
         for name in _ZONE_CONTROL:
             zp[layout.ZP[name]] = _f(getattr(con, name), nz)
@@ -267,7 +285,10 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         for name in _AET_CONTROL:
             zp[layout.ZP[name]] = _f(getattr(aet.parameters.control, name), nz)
         for name in _PET_CONTROL:
-            zp[layout.ZP[name]] = _f(getattr(pet.parameters.control, name), nz)
+            if ret_io and name != "evapotranspirationfactor":
+                zp[layout.ZP[name]] = 0.0        # (see _PET_MODELS: the identity setting of the HBV96 equations)
+            else:
+                zp[layout.ZP[name]] = _f(getattr(pet.parameters.control, name), nz)
         zp[layout.ZP["hruareafraction"]] = _f(pet.parameters.derived.hruareafraction, nz)
         zp_l.append(zp)
         zt_l.append(np.array(con.zonetype.value, dtype=np.int32).reshape(nz))
@@ -335,11 +356,16 @@ def extract_land(elements: Iterable[Any], node_index: dict[Any, int], i0: int, i
         bw1_l.append(_f(sta.bw1, nz) if mname == "hland_96c" else zeros)
         bw2_l.append(_f(sta.bw2, nz) if mname == "hland_96c" else zeros)
         inp = model.sequences.inputs
-        pinp = pet.sequences.inputs
+        seq_nat, seq_net = _pet_input_sequences(pet)
         forcing[0, :, e] = _input_series(element, inp.p, i0, i1)
         forcing[1, :, e] = _input_series(element, inp.t, i0, i1)
-        forcing[2, :, e] = _input_series(element, pinp.normalairtemperature, i0, i1)
-        forcing[3, :, e] = _input_series(element, pinp.normalevapotranspiration, i0, i1)
+        if seq_nat is not None:
+            forcing[2, :, e] = _input_series(element, seq_nat, i0, i1)
+        forcing[3, :, e] = _input_series(element, seq_net, i0, i1)
+        if ret_io and np.any(forcing[3, :, e] < 0.0):
+            raise UnsupportedModelError(
+                f"element `{element.name}`: negative reference evapotranspiration in the input series of `evap_ret_io` "
+                f"(the B200 engine serves it through the evap_pet_hbv96 equations, which clip at zero)")
         this_doy = np.array(der.doy.value, dtype=np.int64)[i0:i1]
         if doy is None:
             doy = this_doy
@@ -559,6 +585,8 @@ def _io_sequences(model: Any):
             yield group, seq
 
 
+_MEAN_SOURCE = {"meanpet": "potentialevapotranspiration", "meanret": "referenceevapotranspiration"}
+
 #: the models below a land element: path from the main model ("" = the main model itself)
 _LAND_PATHS = ("", "aetmodel", "aetmodel.petmodel", "rconcmodel")
 
@@ -618,6 +646,7 @@ def requested_series(problem: Problem) -> list[str]:
                 break
     extra = dict(layout.SUBMODEL_SERIES)
     extra[("aetmodel.petmodel", "fluxes", "meanpotentialevapotranspiration")] = "potentialevapotranspiration"
+    extra[("aetmodel.petmodel", "fluxes", "meanreferenceevapotranspiration")] = "referenceevapotranspiration"
     for (path, group, seqname), name in extra.items():
         if name in wanted:
             continue
@@ -704,11 +733,10 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
             _set_state(sta.bw2, states.bw2[z0:z1])
             _set_state(sta.lz, float(states.lz[e]))
         # input sequences fed by nodes keep what they received (save_data, ref: modelutils.py:1127-1167)
-        pinp = model.aetmodel.petmodel.sequences.inputs
         col = int(land.forcing_col[e])
-        for k, seq in enumerate((model.sequences.inputs.p, model.sequences.inputs.t, pinp.normalairtemperature,
-                                 pinp.normalevapotranspiration)):
-            if getattr(seq, "node2idx", None) and seq.ramflag:
+        for k, seq in enumerate((model.sequences.inputs.p, model.sequences.inputs.t,
+                                 *_pet_input_sequences(model.aetmodel.petmodel))):
+            if seq is not None and getattr(seq, "node2idx", None) and seq.ramflag:
                 seq.series[i0:i1] = problem.forcing[k, :, col]
         u0, u1 = int(land.uh_ptr[e]), int(land.uh_ptr[e + 1])
         if u1 > u0:
@@ -767,10 +795,11 @@ def write_back(problem: Problem, *, states: LandStates, discharge: np.ndarray, n
                 seq.series[i0:i1] = 0.0
             elif kind == "input_t":
                 seq.series[i0:i1] = problem.forcing[1, :, col]
-            elif kind == "meanpet" and "potentialevapotranspiration" in series:
-                # ref: evap_model.py:5489-5498 — Σ hruareafraction[k] * potentialevapotranspiration[k], k = 0 … Z-1
+            elif kind in ("meanpet", "meanret") and _MEAN_SOURCE[kind] in series:
+                # ref: evap_model.py:5489-5498 — Σ hruareafraction[k] * potentialevapotranspiration[k], k = 0 … Z-1;
+                # evap_model.py:5451-5461 (evap_ret_io) — the same sum over referenceevapotranspiration
                 frac = land.zp("hruareafraction")[z0:z1]
-                pet = series["potentialevapotranspiration"][:, z0:z1]
+                pet = series[_MEAN_SOURCE[kind]][:, z0:z1]
                 acc = np.zeros(pet.shape[0])
                 for k in range(nz):
                     acc = acc + frac[k] * pet[:, k]

@@ -110,6 +110,7 @@ SUBMODEL_DERIVED = {
     ("aetmodel", "factors", "snowycanopy"): "zero",
     ("aetmodel.petmodel", "factors", "meanairtemperature"): "input_t",
     ("aetmodel.petmodel", "fluxes", "meanpotentialevapotranspiration"): "meanpet",
+    ("aetmodel.petmodel", "fluxes", "meanreferenceevapotranspiration"): "meanret",   # (evap_ret_io)
 }
 
 NODE_NEWSIM, NODE_EXT, NODE_OBSNEWSIM = 0, 1, 2

@@ -40,6 +40,8 @@ MODELS = (
     "rconc", "rconc_uh", "musk", "musk_classic",
     # sibling models on the same skeleton
     "hland_96p", "hland_96c", "rconc_nash", "musk_mct", "wq", "wq_trapeze_strickler",
+    # the second PET submodel behind evap_aet_hbv96 (external reference evapotranspiration)
+    "evap_ret_io",
 )
 
 STUBS = {

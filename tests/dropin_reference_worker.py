@@ -191,6 +191,61 @@ with model.add_wqmodel_v1("wq_trapeze_strickler"):
     return hp, (("2000-01-01", "2000-01-04"), ("2000-01-04", "2000-01-09"))
 
 
+def ret_io_project():
+    """Two hland_96 elements whose evap_aet_hbv96 submodel takes its potential evapotranspiration from `evap_ret_io`
+    (an external time series of reference evapotranspiration, adjusted per zone; ref: hydpy/models/evap_ret_io.py:53-64)
+    — one without capillary flux (fast path of the engine), one with (coupled kernel) — on a common outlet node."""
+    from hydpy import Element, Elements, HydPy, Node, Nodes
+
+    pub.timegrids = "2000-01-01", "2000-01-09", "1h"
+    n_out = Node("retio_out")
+    e_a, e_b = Element("retio_land_a", outlets=n_out), Element("retio_land_b", outlets=n_out)
+    rng = np.random.default_rng(23)
+    control = """
+from hydpy.models.hland_96 import *
+parameterstep("1h")
+area(20.0)
+nmbzones(5)
+sclass(1)
+zonetype(FIELD, FOREST, GLACIER, ILAKE, SEALED)
+zonearea(6.0, 5.0, 3.0, 2.0, 4.0)
+psi(1.0)
+zonez(2.0, 4.0, 11.0, 1.0, 2.0)
+pcorr(1.05); pcalt(0.08); rfcf(1.1); sfcf(1.25); tcorr(0.3); tcalt(0.6); icmax(1.5); sfdist(1.0); smax(inf)
+sred(0.0); tt(0.2); ttint(2.0); dttm(0.5); cfmax(0.6); cfvar(0.1); gmelt(1.0); gvar(0.2); cfr(0.1); whc(0.3)
+fc(180.0); beta(2.3); percmax(0.6); cflux({cflux}); resparea(True); recstep(50); alpha(1.3); k(0.002); k4(0.006)
+gamma(0.1)
+with model.add_aetmodel_v1("evap_aet_hbv96"):
+    temperaturethresholdice(0.0)
+    soilmoisturelimit(0.8)
+    excessreduction(0.5)
+    with model.add_petmodel_v1("evap_ret_io"):
+        evapotranspirationfactor(0.8, 1.2, 0.5, 1.3, 1.0)
+with model.add_rconcmodel_v1("rconc_uh"):
+    uh("triangle", tb=4.0)
+"""
+    for element, cflux in ((e_a, 0.0), (e_b, 0.1)):
+        ns: dict = {}
+        exec(control.format(cflux=cflux), ns)   # like a control file
+        element.model = ns["model"]
+    hp = HydPy("ret_io_project")
+    hp.update_devices(nodes=Nodes(n_out), elements=Elements(e_a, e_b))
+    hp.update_parameters()
+    hp.prepare_allseries()
+    nt = len(pub.timegrids.init)
+    for element in (e_a, e_b):
+        model = element.model
+        model.sequences.inputs.p.series = rng.gamma(0.4, 2.5, nt) * (rng.uniform(size=nt) < 0.4)
+        model.sequences.inputs.t.series = 1.0 + 7.0 * np.sin(np.arange(nt) / 24.0) + rng.normal(0.0, 2.0, nt)
+        ret = rng.uniform(0.0, 0.5, nt)
+        ret[rng.uniform(size=nt) < 0.2] = 0.0          # nights without any demand
+        model.aetmodel.petmodel.sequences.inputs.referenceevapotranspiration.series = ret
+        sta = model.sequences.states
+        sta.ic(0.4); sta.sp(2.0); sta.wc(0.2); sta.sm(120.0); sta.uz(3.0); sta.lz(9.0)
+        model.rconcmodel.sequences.logs.quh(0.05)
+    return hp, (("2000-01-01", "2000-01-05"), ("2000-01-05", "2000-01-09"))
+
+
 def add_input_nodes(hp):
     """Feed three of the four meteorological inputs of two Lahn sub-basins through input nodes in different deploy
     modes (ref: hydpy/core/devicetools.py `Element.inputs`, hydpy/core/modeltools.py:1533 `_connect_inputs`)."""
@@ -238,6 +293,9 @@ def main() -> None:
     if "--siblings" in sys.argv:
         with contextlib.redirect_stdout(io.StringIO()):
             hp, windows = sibling_project()
+    elif "--retio" in sys.argv:
+        with contextlib.redirect_stdout(io.StringIO()):
+            hp, windows = ret_io_project()
     else:
         with contextlib.redirect_stdout(io.StringIO()):
             hp, _, _ = testtools.prepare_full_example_2(lastdate="1996-03-01")
@@ -335,6 +393,16 @@ def main() -> None:
                     raise AssertionError(f"{which}, window {w}: {key} differs at {idx[:8]} of {np.size(a[key])}: "
                                          f"{np.ravel(a[key])[idx[:4]]} vs {np.ravel(b[key])[idx[:4]]}")
                 n += 1
+    if "--retio" in sys.argv:
+        # a negative reference evapotranspiration cannot pass through the HBV96 equations unchanged: refused, not clipped
+        series = hp.elements.retio_land_a.model.aetmodel.petmodel.sequences.inputs.referenceevapotranspiration.series
+        series[-3] = -0.1                                        # (inside the last simulation window)
+        try:
+            hydpy_b200.simulate(hp)
+        except hydpy_b200.UnsupportedModelError as exc:
+            assert "negative reference evapotranspiration" in str(exc)
+        else:
+            raise AssertionError("negative evap_ret_io input was not refused")
     print(f"DROPIN_OK compared {n} arrays over {len(windows)} windows, {len(hp.elements)} elements, {len(hp.nodes)} nodes"
           + (f"; CUDA engine in the middle, worst deviation {worst:.2e} (bar 1e-9); wall: reference hp.simulate() "
              f"{t_ref:.3f} s, hydpy_b200.simulate(hp) {t_got:.3f} s for both windows" if ENGINE else

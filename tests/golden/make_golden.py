@@ -12,6 +12,9 @@ What is produced (all under tests/golden/):
 * ``hland_96p_integration.npz``, ``hland_96c_integration.npz`` — the same for the sibling models (``--siblings``).
 * ``musk_mct_integration.npz`` — the 5 integration tests of ``hydpy/models/musk_mct.py`` (``--musk_mct``).
 * ``musk_classic_integration.npz`` — the 3 integration tests of ``hydpy/models/musk_classic.py``.
+* ``hland_96_ret_io.npz`` — two `hland_96` elements (five zones of every type; one without, one with capillary flux)
+  whose `evap_aet_hbv96` submodel reads its potential evapotranspiration from `evap_ret_io` (``--ret_io``; the project
+  is the one of tests/dropin_reference_worker.py), 192 hourly steps, every sequence of every step.
 * ``lahn_daily.npz`` — the HydPy-H-Lahn example project, 1996-01-01…1998-01-01 daily (config 1 of BASELINE.json):
   problem + all four gauge series + land outflows + final conditions + a few state series.
 * ``lahn_hourly_members.npz`` — config 2 in miniature: Lahn with ``simulationstep 1h`` (synthetic hourly
@@ -344,7 +347,33 @@ def write_template(daily: dict[str, np.ndarray], hourly: dict[str, np.ndarray]) 
     print(f"wrote {path}: {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def ret_io() -> dict[str, dict[str, np.ndarray]]:
+    """`evap_ret_io` behind `evap_aet_hbv96` (ref: hydpy/models/evap_ret_io.py:53-64): the project is built by
+    tests/dropin_reference_worker.py::ret_io_project through the reference's own API."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("dropin_reference_worker",
+                                                  os.path.join(ROOT, "tests", "dropin_reference_worker.py"))
+    worker = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(worker)
+    del pub.projectname
+    del pub.timegrids
+    pub.options.prepare_testing(usecython=True, threads=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hp, _ = worker.ret_io_project()
+    i0, i1 = pub.timegrids.simindices
+    problem = extract(hp, i0, i1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hp.simulate()
+    d = problem.to_npz_dict()
+    d.update(gather_expected(problem, hp))
+    return {"ret_io": d}
+
+
 def main() -> None:
+    if "--ret_io" in sys.argv:
+        save_scenarios(os.path.join(HERE, "hland_96_ret_io.npz"), ret_io())
+        return
     if "--musk_mct" in sys.argv:
         save_scenarios(os.path.join(HERE, "musk_mct_integration.npz"),
                        harvest_module("hydpy.models.musk_mct", capture_all=True))

@@ -30,6 +30,16 @@ def test_simulate_sibling_models_like_the_reference_does():
 
 
 @pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
+def test_simulate_with_evap_ret_io_like_the_reference_does():
+    """`evap_ret_io` (external reference evapotranspiration) as the PET submodel of `evap_aet_hbv96`, all series of the
+    main model and the submodels kept in RAM (ref: hydpy/models/evap_ret_io.py:53-64)."""
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_worker.py"), "--retio"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "DROPIN_OK" in proc.stdout
+
+
+@pytest.mark.skipif(not BUILT, reason="no reference build in this environment (run oracle/build_ref.py)")
 def test_simulate_with_input_nodes_like_the_reference_does():
     """Meteorological inputs fed through input nodes (`Element.inputs`) in the deploy modes oldsim, obs, obs_oldsim,
     obs_newsim and newsim: the same values reach the model, the input sequences keep them, the nodes end as in the

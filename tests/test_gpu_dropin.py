@@ -38,6 +38,11 @@ def test_sibling_models_through_the_engine():
 
 
 @pytest.mark.skipif(not AVAILABLE, reason="no importable reference (oracle/_ref) in this environment")
+def test_evap_ret_io_through_the_engine():
+    run_worker("--retio")
+
+
+@pytest.mark.skipif(not AVAILABLE, reason="no importable reference (oracle/_ref) in this environment")
 def test_input_nodes_through_the_engine():
     run_worker("--inputnodes")
 

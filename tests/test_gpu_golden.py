@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 HLAND = load_scenarios("hland_96_integration.npz")
 HLAND_P = load_scenarios("hland_96p_integration.npz")
 HLAND_C = load_scenarios("hland_96c_integration.npz")
+HLAND_RETIO = load_scenarios("hland_96_ret_io.npz")
 MUSK = load_scenarios("musk_classic_integration.npz")
 MUSK_MCT = load_scenarios("musk_mct_integration.npz")
 LAHN = load_scenarios("lahn_daily.npz")
@@ -69,6 +70,13 @@ def run_and_check(engine, sc, window=None):
 @pytest.mark.parametrize("name", sorted(HLAND))
 def test_hland_96_integration(engine, name):
     run_and_check(engine, HLAND[name])
+
+
+@pytest.mark.parametrize("name", sorted(HLAND_RETIO))
+def test_hland_96_with_evap_ret_io(engine, name):
+    """`evap_ret_io` behind `evap_aet_hbv96` (external reference evapotranspiration; ref: hydpy/models/evap_ret_io.py:53-64)
+    on the kernels of the evap_pet_hbv96 equations in their identity setting — exp(-0.0 * pc) must be exactly 1."""
+    run_and_check(engine, HLAND_RETIO[name])
 
 
 @pytest.mark.parametrize("name", sorted(HLAND_P))

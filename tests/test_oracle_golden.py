@@ -18,6 +18,7 @@ from tests.util import assert_close, load_scenarios
 HLAND = load_scenarios("hland_96_integration.npz")
 HLAND_P = load_scenarios("hland_96p_integration.npz")
 HLAND_C = load_scenarios("hland_96c_integration.npz")
+HLAND_RETIO = load_scenarios("hland_96_ret_io.npz")
 MUSK = load_scenarios("musk_classic_integration.npz")
 MUSK_MCT = load_scenarios("musk_mct_integration.npz")
 LAHN = load_scenarios("lahn_daily.npz")
@@ -63,6 +64,18 @@ def check(sc, res, exact=True):
 def test_hland_96_integration(name):
     sc = HLAND[name]
     assert len(sc.expected_series) == 44  # every factor/flux/state sequence + the 8 of the evap submodels
+    check(sc, run_oracle(sc))
+
+
+@pytest.mark.parametrize("name", sorted(HLAND_RETIO))
+def test_hland_96_with_evap_ret_io(name):
+    """`evap_ret_io` as the PET submodel of `evap_aet_hbv96` (ref: hydpy/models/evap_ret_io.py:53-64): extract.py maps it
+    onto the evap_pet_hbv96 equations with the identity setting (all factors but EvapotranspirationFactor zero), which
+    must reproduce the reference bit for bit — every sequence of both elements (without / with capillary flux)."""
+    sc = HLAND_RETIO[name]
+    zp = sc.problem.land.zp
+    assert not zp("airtemperaturefactor").any() and not zp("altitudefactor").any() and not zp("precipitationfactor").any()
+    assert "referenceevapotranspiration" in sc.expected_series and "ea" in sc.expected_series
     check(sc, run_oracle(sc))
 
 
