@@ -62,7 +62,7 @@ class hb_timing(C.Structure):
         ("zone_warpsteps", C.c_int64), ("zone_warpsteps_dry", C.c_int64), ("zone_steps", C.c_int64),
         ("zone_steps_wet", C.c_int64), ("elem_steps", C.c_int64), ("elem_steps_run", C.c_int64),
         ("substeps_pow", C.c_int64), ("elem_warpsteps", C.c_int64), ("elem_warpsteps_run", C.c_int64),
-        ("n_fused", C.c_int64),
+        ("n_fused", C.c_int64), ("n_spec", C.c_int64), ("spec_reruns", C.c_int64),
     ]
 
 

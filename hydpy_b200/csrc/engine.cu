@@ -218,6 +218,12 @@ struct hb_engine {
   bool any_nonsoil_warp = false;      // some warp of the zone kernel holds a fast-path zone that is not FIELD/FOREST with FC > 0
   int64_t n_fast = 0;                 // elements eligible for the fast path (HB_EI_FAST)
   int64_t n_fast_classes = 0;         // … of them with several snow classes (fast only while no series is recorded)
+  // speculative fast path for finite SMax (HB_EI_SPEC, HB_OPT_LAND_SPECULATE): the elements, the flags their zone kernel
+  // raises when a snow class exceeds its limit, and the conditions of the window's start for the repetition
+  int land_speculate = 1;
+  std::vector<int32_t> spec_list;
+  DBuf<int32_t> d_spec_list, d_spec_flag;
+  DBuf<double> d_snap_ic, d_snap_sm, d_snap_sp, d_snap_wc, d_snap_uz, d_snap_lz, d_snap_quh;
   std::vector<int32_t> coupled_list;  // elements of the fused kernel (HB_EI_COUPLED)
   std::vector<int32_t> general_list;  // elements of the general kernel in the current combination of paths
   // sibling models: hland_96p / hland_96c elements always run through the general kernel, instantiated
@@ -798,7 +804,7 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
       sfdist((size_t)cmax * ep, 0.0), uh((size_t)umax * ep, 0.0);
   bool any_snowlimit = false;
   int64_t n_fast = 0, n_fast_sib[2] = {0, 0}, n_fast_classes = 0;
-  std::vector<int32_t> coupled_list;
+  std::vector<int32_t> coupled_list, spec_list;
   std::vector<char> soilwarp_ok((size_t)ep, 0);   // fast hland_96 element, every zone FIELD/FOREST with FC > 0
   h->any_nonsoil_warp = false;
   h->any_nonsoil_sib[0] = h->any_nonsoil_sib[1] = false;
@@ -858,6 +864,13 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
       ++n_fast;
       if (nc[e] > 1) { nonsoil = true; ++n_fast_classes; }
     }
+    else if ((info & HB_EI_SNOWLIMIT) && !coupled && h->land_speculate) {
+      // finite SMax: speculative fast path (general zone step, which watches the limit; not while series are recorded)
+      info |= HB_EI_FAST | HB_EI_SPEC;
+      ++n_fast;
+      nonsoil = true;
+      spec_list.push_back((int32_t)e);
+    }
     else if (!(info & HB_EI_SNOWLIMIT) && nc[e] == 1 && zmax <= HB_COUPLED_ZMAX && nash[e] == 0) {
       info |= HB_EI_COUPLED;          // (the fused kernel convolves a unit hydrograph: rconc_nash elements stay general)
       coupled_list.push_back((int32_t)e);
@@ -896,6 +909,12 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
   h->n_fast_classes = n_fast_classes;
   h->n_fast_sib[0] = n_fast_sib[0]; h->n_fast_sib[1] = n_fast_sib[1];
   h->coupled_list = coupled_list;
+  h->spec_list = spec_list;
+  { int rc_ = upload(h, h->d_spec_list, spec_list); if (rc_) return rc_; }
+  if (!spec_list.empty()) {
+    HB_CUDA(h, h->d_spec_flag.reserve((size_t)ep));
+    HB_CUDA(h, cudaMemsetAsync(h->d_spec_flag.p, 0, (size_t)ep * sizeof(int32_t), h->stream));
+  }
   if (h->h_model != model) h->have_states = false;
   h->h_model = model;
   h->any_sibling = !siblings[0].empty() || !siblings[1].empty();
@@ -912,7 +931,8 @@ static int set_land_core(hb_engine* h, const hb_land_desc* d, const MemberMods& 
     for (int64_t e = 0; e < ne; ++e) {
       zone_cell0[e] = h->zone_ptr[e];
       snow_cell0[e] = h->snow_ptr[e];
-      if (!(einfo[e] & HB_EI_FAST) || nc[e] > 1) continue;   // (several snow classes: the general kernel records their series)
+      // (several snow classes, finite SMax: the general kernel records their series)
+      if (!(einfo[e] & HB_EI_FAST) || nc[e] > 1 || (einfo[e] & HB_EI_SPEC)) continue;
       for (int k = 0; k < nz[e]; ++k) {
         zone_slot[(size_t)h->zone_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);
         snow_slot[(size_t)h->snow_ptr[e] + k] = (int32_t)((int64_t)k * ep + e);   // fast path: one snow class
@@ -1153,6 +1173,10 @@ int hb_set_option(hb_engine* h, int option, int64_t value) {
     case HB_OPT_LAND_FUSE:
       HB_REQUIRE(h, value == 0 || value == 1, HB_EINVAL, "hb_set_option: land fuse must be 0 or 1");
       h->land_fuse = (int)value;
+      return HB_OK;
+    case HB_OPT_LAND_SPECULATE:
+      HB_REQUIRE(h, value == 0 || value == 1, HB_EINVAL, "hb_set_option: land speculate must be 0 or 1");
+      h->land_speculate = (int)value;
       return HB_OK;
     case HB_OPT_RIVER_SWEEP:
       HB_REQUIRE(h, value == HB_RIVER_PERSISTENT || value == HB_RIVER_LAUNCHES || value == HB_RIVER_GROUPED, HB_EINVAL,
@@ -1838,9 +1862,11 @@ static int run_land(hb_engine* h) {
   // sibling models on the fast path (their zone sequences are staged like the others')
   const bool use_fast_sib = (h->n_fast_sib[0] + h->n_fast_sib[1]) > 0 && h->land_path == HB_LAND_AUTO &&
                             !(any_series && h->zmax > 128);
+  // finite SMax: speculative fast path (see HB_EI_SPEC) while no series is recorded
+  const bool use_spec = use_fast && !any_series && !h->spec_list.empty();
   // the general kernel takes every element the two special paths do not take in this run
   const int general_key = (use_fast ? 1 : 0) | (use_coupled ? 2 : 0) | (use_fast_sib ? 4 : 0) |
-                          ((any_series && h->n_fast_classes > 0) ? 8 : 0);
+                          ((any_series && (h->n_fast_classes > 0 || !h->spec_list.empty())) ? 8 : 0);
   if (general_key != h->general_key) {
     h->general_list.clear();
     h->sibling_list[0].clear(); h->sibling_list[1].clear();
@@ -1851,7 +1877,8 @@ static int run_land(hb_engine* h) {
         if (!(use_fast_sib && (info & HB_EI_FAST))) h->sibling_list[m - 1].push_back((int32_t)e);
         continue;
       }
-      if ((use_fast && (info & HB_EI_FAST) && !(any_series && h->h_nc[e] > 1)) || (use_coupled && (info & HB_EI_COUPLED))) continue;
+      if ((use_fast && (info & HB_EI_FAST) && !(any_series && (h->h_nc[e] > 1 || (info & HB_EI_SPEC)))) ||
+          (use_coupled && (info & HB_EI_COUPLED))) continue;
       h->general_list.push_back((int32_t)e);
     }
     int rc = upload(h, h->d_general_list, h->general_list);
@@ -1862,6 +1889,7 @@ static int run_land(hb_engine* h) {
   }
   const int64_t n_general = (int64_t)h->general_list.size();
   h->timing.n_fast = (use_fast ? h->n_fast : 0) + (use_fast_sib ? h->n_fast_sib[0] + h->n_fast_sib[1] : 0);
+  h->timing.n_spec = use_spec ? (int64_t)h->spec_list.size() : 0;
   h->slabs_used = 1;
   if (h->n_elem == 0 || nt == 0) {
     HB_CUDA(h, cudaEventRecord(h->ev_slab_done[0], h->stream));
@@ -1891,6 +1919,24 @@ static int run_land(hb_engine* h) {
     v.sinfactor = h->d_sinfactor[h->fcur].p; v.tables = h->d_tables.p; v.chain_tables = h->d_chain_tables.p; v.qt = h->d_qt.p;
     v.n_zone = h->n_zone; v.n_snow = h->n_snow; v.n_uh = h->n_uh; v.uh0 = h->d_uh0.p;
     v.counters = h->d_counters.p;
+    v.spec_flag = h->d_spec_flag.p;
+    if (use_spec) {
+      // conditions of the window's start for the elements that will have to repeat it; flags down
+      const size_t zs_ = (size_t)h->zmax * ep, B = sizeof(double);
+      HB_CUDA(h, h->d_snap_ic.reserve(zs_)); HB_CUDA(h, h->d_snap_sm.reserve(zs_));
+      HB_CUDA(h, h->d_snap_sp.reserve(zs_ * h->cmax)); HB_CUDA(h, h->d_snap_wc.reserve(zs_ * h->cmax));
+      HB_CUDA(h, h->d_snap_uz.reserve((size_t)ep)); HB_CUDA(h, h->d_snap_lz.reserve((size_t)ep));
+      HB_CUDA(h, h->d_snap_quh.reserve((size_t)h->umax * ep));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_ic.p, h->d_ic.p, zs_ * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_sm.p, h->d_sm.p, zs_ * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_sp.p, h->d_sp.p, zs_ * h->cmax * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_wc.p, h->d_wc.p, zs_ * h->cmax * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_uz.p, h->d_uz.p, (size_t)ep * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemcpyAsync(h->d_snap_lz.p, h->d_lz.p, (size_t)ep * B, cudaMemcpyDeviceToDevice, h->stream));
+      if (h->umax > 0)
+        HB_CUDA(h, cudaMemcpyAsync(h->d_snap_quh.p, h->d_quh.p, (size_t)h->umax * ep * B, cudaMemcpyDeviceToDevice, h->stream));
+      HB_CUDA(h, cudaMemsetAsync(h->d_spec_flag.p, 0, (size_t)ep * sizeof(int32_t), h->stream));
+    }
     // [storage | ordinate][thread] staging of the runoff concentration: the rconc_nash cascade of a step, the rconc_uh
     // memory for the whole launch
     v.nash_stage = 1;
@@ -2127,8 +2173,8 @@ static int run_land(hb_engine* h) {
     h->timing.land_launches += 1;
   }
   const int64_t n_sib[2] = {(int64_t)h->sibling_list[0].size(), (int64_t)h->sibling_list[1].size()};
-  if (n_general > 0 || n_sib[0] > 0 || n_sib[1] > 0) {
-    LandDev d{};
+  LandDev d{};
+  if (n_general > 0 || n_sib[0] > 0 || n_sib[1] > 0 || use_spec) {
     d.n_elem = h->n_elem; d.e_pad = ep; d.n_zone = h->n_zone; d.n_snow = h->n_snow;
     d.zmax = h->zmax; d.cmax = h->cmax; d.umax = h->umax;
     d.n_list = n_general; d.elist = n_general == h->n_elem ? nullptr : h->d_general_list.p;
@@ -2144,6 +2190,8 @@ static int run_land(hb_engine* h) {
     d.nt = nt; d.n_col = h->n_col; d.nt_total = h->nt_total; d.t0 = h->t0; d.forcing = h->d_forcing[h->fcur].p;
     d.sinfactor = h->d_sinfactor[h->fcur].p; d.qt = h->d_qt.p;
     for (int s = 0; s < HB_S_COUNT; ++s) d.series[s] = h->series_on[s] ? h->d_series[s].p : nullptr;
+  }
+  if (n_general > 0 || n_sib[0] > 0 || n_sib[1] > 0) {
     const int block = 128;
     h->mark(HB_K_OTHER);
     if (n_general > 0) {
@@ -2173,7 +2221,7 @@ static int run_land(hb_engine* h) {
   // own stream and the land stream goes on to the next window without waiting for the others (s_join collects them for
   // the consumers of the rows); otherwise all slabs join the land stream first, which transposes everything.
   const int ns = (use_fast || use_fast_sib) ? h->slabs_used : 1;
-  const bool slabs_only = ns > 1 && !use_coupled && n_general == 0 && n_sib[0] == 0 && n_sib[1] == 0;
+  const bool slabs_only = ns > 1 && !use_coupled && n_general == 0 && n_sib[0] == 0 && n_sib[1] == 0 && !use_spec;
   if (slabs_only) {
     for (int sl = 0; sl < ns; ++sl) {
       cudaStream_t st = sl == 0 ? h->stream : h->s_slab[sl - 1];
@@ -2190,6 +2238,21 @@ static int run_land(hb_engine* h) {
     for (int sl = 1; sl < ns; ++sl) {
       HB_CUDA(h, cudaEventRecord(h->ev_slab_done[sl], h->s_slab[sl - 1]));
       HB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_slab_done[sl], 0));
+    }
+    if (use_spec) {
+      // every slab is through: the elements whose snow exceeded SMax somewhere in the window start again from the
+      // window's conditions and run it in the general kernel, which redistributes (results and states overwritten)
+      const int64_t n_spec = (int64_t)h->spec_list.size();
+      const unsigned sgrid = (unsigned)((n_spec + 127) / 128);
+      SpecSnap sn{h->d_ic.p, h->d_sm.p, h->d_sp.p, h->d_wc.p, h->d_uz.p, h->d_lz.p, h->d_quh.p,
+                  h->d_snap_ic.p, h->d_snap_sm.p, h->d_snap_sp.p, h->d_snap_wc.p, h->d_snap_uz.p, h->d_snap_lz.p, h->d_snap_quh.p};
+      h->mark(HB_K_OTHER);
+      spec_restore_kernel<<<sgrid, 128, 0, h->stream>>>(h->d_spec_list.p, n_spec, h->d_spec_flag.p, ep, h->zmax, h->d_nz.p,
+                                                        h->d_nc.p, h->d_nu.p, sn, h->d_counters.p);
+      d.n_list = n_spec; d.elist = h->d_spec_list.p; d.only_flagged = h->d_spec_flag.p;
+      land_kernel<false, HB_MODEL_HLAND_96><<<sgrid, 128, 0, h->stream>>>(d);
+      h->mark(HB_K_GENERAL);
+      h->timing.land_launches += 2;
     }
     dim3 tg((unsigned)((h->n_elem + 31) / 32), (unsigned)((nt + 31) / 32));
     transpose_qt_kernel<<<tg, 256, 0, h->stream>>>(h->d_qt.p, h->d_land_rows[h->cur].p, nt, h->n_elem, ep, 0);
@@ -2577,14 +2640,17 @@ int hb_get_timing(hb_engine* h, hb_timing* out) {
     h->timing.substeps_pow = (int64_t)c[HB_CNT_SUBSTEPS_POW];
     h->timing.elem_warpsteps = (int64_t)c[HB_CNT_ELEM_WARPSTEPS];
     h->timing.elem_warpsteps_run = (int64_t)c[HB_CNT_ELEM_WARPSTEPS_RUN];
+    h->timing.spec_reruns = (int64_t)c[HB_CNT_SPEC_RERUN];
   }
   *out = h->timing;
   // sums restart with the next run
-  const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast, n_fused = h->timing.n_fused;
+  const int64_t n_levels = h->timing.n_levels, n_fast = h->timing.n_fast, n_fused = h->timing.n_fused,
+                n_spec = h->timing.n_spec;
   h->timing = hb_timing{};
   h->timing.n_levels = n_levels;
   h->timing.n_fast = n_fast;
   h->timing.n_fused = n_fused;
+  h->timing.n_spec = n_spec;
   return HB_OK;
 }
 

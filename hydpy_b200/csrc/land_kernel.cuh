@@ -93,6 +93,9 @@ enum ke {
 #define HB_EI_COUPLED 64   // like HB_EI_FAST but with CFlux > 0 somewhere: fused kernel (land_kernel_coupled.cuh)
 #define HB_EI_FUSED 128    // HB_EI_FAST hland_96 element of a 32-element group whose zones are all FIELD/FOREST with FC > 0:
                            // the zone kernel can add the group's zone terms itself (land_kernel_v2.cuh, zone_kernel<…, ZW>)
+#define HB_EI_SPEC 1024     // HB_EI_FAST hland_96 element with HB_EI_SNOWLIMIT: the fast path runs it SPECULATIVELY — as long as no
+                           // snow class of any zone exceeds its SMax, Calc_SPL/Calc_SPG change nothing (all losses, gains and
+                           // excesses are zero); a window in which one does is repeated by the general kernel (engine.cu)
 #define HB_EI_MODEL_SHIFT 8   // bits 8..9: HB_MODEL_* of the element
 #define HB_EI_MODEL(i) (((i) >> HB_EI_MODEL_SHIFT) & 3)
 
@@ -106,6 +109,8 @@ struct LandDev {
   int32_t zmax, cmax, umax;
   int64_t n_list;          // number of elements this launch works on
   const int32_t* elist;    // [n_list] their indices (NULL: elements 0..n_list-1)
+  const int32_t* only_flagged;  // [E_pad] or NULL: work on the listed elements whose flag is set only (speculative fast
+                                // path: the elements whose snow exceeded SMax in this window, states restored beforehand)
   // structure
   const int32_t* nz;       // [E_pad]
   const int32_t* nc;       // [E_pad]
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
   const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= d.n_list) return;
   const int64_t e = d.elist ? (int64_t)d.elist[li] : li;
+  if (d.only_flagged && !d.only_flagged[e]) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nc = d.nc[e], nu = d.nu[e], recstep = d.recstep[e], einfo = d.einfo[e];
   const int64_t col = d.fcol[e];

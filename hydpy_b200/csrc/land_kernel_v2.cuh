@@ -51,7 +51,8 @@ struct LandV2Dev {
   int32_t slab_blocks;
   const int32_t* nz;       // [E_pad]
   const int32_t* nc;       // [E_pad] snow classes (fast path: class 0 in registers, further classes [c][zmax][E_pad] in place)
-  int32_t skip_classes;    // this run records series: elements with several snow classes go to the general kernel
+  int32_t skip_classes;    // this run records series: elements with several snow classes (and speculative ones) go to
+                           // the general kernel
   const int32_t* nu;       // [E_pad]
   const int32_t* recstep;  // [E_pad]
   const int32_t* einfo;    // [E_pad]  HB_EI_* incl. HB_EI_FAST / HB_EI_SOILONLY
@@ -104,6 +105,7 @@ struct LandV2Dev {
   double* ex2;             // [E_pad] hland_96p sg3
   // what the kernels actually executed (hb_get_timing): see enum below; one atomicAdd per warp and counter at kernel end
   unsigned long long* counters;
+  int32_t* spec_flag;      // [E_pad] set by the zone kernel when a snow class of a HB_EI_SPEC element exceeded its SMax
 };
 
 // slots of LandV2Dev::counters
@@ -117,6 +119,7 @@ enum { HB_CNT_ZONE_WARPSTEPS = 0,   // warp-steps of the branch-free (FIELD/FORE
                                     // sub-step its loop runs; general loop: those with uz > 0; a quadratic response: none)
        HB_CNT_ELEM_WARPSTEPS,       // warp-steps of the element kernel (32 elements x 1 step)
        HB_CNT_ELEM_WARPSTEPS_RUN,   // … in which at least one lane ran the chain (what the FP64 pipe is busy with)
+       HB_CNT_SPEC_RERUN,           // element-windows of the speculative fast path (HB_EI_SPEC) the general kernel repeated
        HB_CNT_COUNT };
 
 __device__ __forceinline__ void stage_tables(MathTables* s, const MathTables* g) {
@@ -218,7 +221,9 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
   const int einfo = d.einfo[e];
   // several snow classes (hland_96 only, never in a fused group): the general step below loops over them
   const int ncls = (ZW == 0 && MODEL == HB_MODEL_HLAND_96) ? d.nc[e] : 1;
-  if (ZW == 0 && ncls > 1 && d.skip_classes) return;
+  // finite SMax (hland_96 only, never in a fused group): the general step below watches the limit (see HB_EI_SPEC)
+  const bool spec = ZW == 0 && MODEL == HB_MODEL_HLAND_96 && (einfo & HB_EI_SPEC) != 0;
+  if (ZW == 0 && (ncls > 1 || spec) && d.skip_classes) return;
 
   const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
 #define KZ(name) kzk[(int64_t)(name) * ep]
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
   // kernel is latency-bound otherwise (ncu: 62 % issue utilisation, half of the stall cycles are fixed-latency waits).
   const unsigned amask = __activemask();                                             // (fused: all 32 lanes)
   const unsigned omask = ZW > 0 ? __ballot_sync(0xffffffffu, active) : amask;         // lanes that own a zone
-  if (ZW == 0 && __all_sync(amask, soil && fc > 0.0 && ncls == 1) != SOIL) return;
+  if (ZW == 0 && __all_sync(amask, soil && fc > 0.0 && ncls == 1 && !spec) != SOIL) return;
   // fused: offsets into the term buffers [G][2][ZW][32]
   const int zw_off = (int)(threadIdx.x >> 5) * 32 + lane;   // (a shadow lane writes its own, never read, cell)
   int tb_off = 0, gs = 0;
@@ -562,6 +567,10 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
   }
 
   // ---- general step (any zone type) ------------------------------------------------------------------------------------
+  // ref: hland_model.py:584-605 Calc_SPL_WCL_SP_WC_V1 — a loss arises where sp + wc of a snow class exceeds SMax right
+  // after the snowfall; as long as none does, that method and Calc_SPG_WCG_SP_WC_V1 (:876-969) leave every state as it is
+  const double smax_lim = spec ? KZX(KZ_SMAX) : HUGE_VAL;
+  bool exceeded = false;
   for (int t = 0; t < nt; ++t) {
     HB_ZONE_STEP_BEGIN
     // ref: hland_model.py:71-77 Calc_TC_V1, 125-135 Calc_FracRain_V1, 213-225 Calc_PC_V1
@@ -590,6 +599,7 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
       // ref: hland_model.py:484-499 Calc_SP_WC_V1
       wc += sf * (tf * fracrain);
       sp += sf * (tf * (1.0 - fracrain));
+      exceeded |= (sp + wc) - smax_lim > 0.0;
       // ref: hland_model.py:1050-1062 Calc_CFAct_V1
       const double cfa = cfmax + sinf * cfvar;
       const double cfact = HB_PYMAX(cfa, 0.0);
@@ -623,6 +633,7 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
           const int64_t ick = (int64_t)c * tstride + slot;
           const double sfc = d.sfdist[(int64_t)c * ep + e];
           double sp_c = d.sp[ick] + sfc * snow, wc_c = d.wc[ick] + sfc * rain;
+          exceeded |= (sp_c + wc_c) - smax_lim > 0.0;
           if (tc > ttm) {
             const double potmelt = cfact * (tc - ttm);
             const double melt = HB_PYMIN(potmelt, sp_c);
@@ -836,6 +847,38 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
 #undef KZX
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
   if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
+  if (exceeded) d.spec_flag[e] = 1;   // (every zone of the element that saw it stores the same value)
+}
+
+// Speculative fast path (HB_EI_SPEC): the elements of `list` whose flag is set get the conditions of the window's start
+// back, so that the general kernel can repeat the window for them (one thread per element; rare).
+struct SpecSnap {
+  double *ic, *sm, *sp, *wc, *uz, *lz, *quh;                            // live states
+  const double *s_ic, *s_sm, *s_sp, *s_wc, *s_uz, *s_lz, *s_quh;        // … at the start of the window
+};
+__global__ void __launch_bounds__(128) spec_restore_kernel(const int32_t* __restrict__ list, int64_t n,
+                                                           const int32_t* __restrict__ flag, int64_t ep, int zmax,
+                                                           const int32_t* __restrict__ nz, const int32_t* __restrict__ nc,
+                                                           const int32_t* __restrict__ nu, const SpecSnap s,
+                                                           unsigned long long* counters) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t e = list[i];
+  if (!flag[e]) return;
+  const int64_t zs = (int64_t)zmax * ep;
+  for (int k = 0; k < nz[e]; ++k) {
+    const int64_t slot = (int64_t)k * ep + e;
+    s.ic[slot] = s.s_ic[slot];
+    s.sm[slot] = s.s_sm[slot];
+    for (int c = 0; c < nc[e]; ++c) {
+      s.sp[c * zs + slot] = s.s_sp[c * zs + slot];
+      s.wc[c * zs + slot] = s.s_wc[c * zs + slot];
+    }
+  }
+  s.uz[e] = s.s_uz[e];
+  s.lz[e] = s.s_lz[e];
+  for (int j = 0; j < nu[e]; ++j) s.quh[(int64_t)j * ep + e] = s.s_quh[(int64_t)j * ep + e];
+  if (counters) atomicAdd(counters + HB_CNT_SPEC_RERUN, 1ull);
 }
 
 // staging layout [nt][zmax][E_pad]  →  ABI layout [nt_window][width] for the zones (or snow cells) of the fast-path
@@ -905,7 +948,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   const int einfo = d.einfo[e];
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
   if (((einfo & HB_EI_FUSED) != 0 && d.fused != 0) != FUSED) return;
-  if (MODEL == HB_MODEL_HLAND_96 && d.skip_classes && d.nc[e] > 1) return;
+  if (MODEL == HB_MODEL_HLAND_96 && d.skip_classes && (d.nc[e] > 1 || (einfo & HB_EI_SPEC))) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;

@@ -356,6 +356,11 @@ class Engine:
         """Zone terms added inside the thread-per-zone kernel where a 32-element group allows (default on; same results)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_FUSE, 1 if on else 0), "hb_set_option")
 
+    def set_land_speculate(self, on: bool) -> None:
+        """Finite `SMax`: fast path while no snow class exceeds its limit, windows in which one does are repeated by the
+        general kernel (default on; read by the next `set_land`; same results)."""
+        self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_SPECULATE, 1 if on else 0), "hb_set_option")
+
     def set_land_chunk(self, steps: int) -> None:
         """Time chunk of the fast runoff-generation path in steps (0 = as long as the scratch memory allows; -1 = the engine's default)."""
         self._check(self._lib.hb_set_option(self._h, layout.OPT_LAND_CHUNK, int(steps)), "hb_set_option")

@@ -6,7 +6,7 @@ truth.  Names follow the reference's parameter/sequence names (`hydpy/models/hla
 """
 from __future__ import annotations
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # zone types, `hydpy/models/hland/hland_constants.py`
 FIELD, FOREST, GLACIER, ILAKE, SEALED = 1, 2, 3, 4, 5
@@ -143,6 +143,7 @@ OPT_LAND_SLABS = 5
 OPT_LAND_CHUNK = 6
 OPT_LAND_FUSE = 7
 OPT_RIVER_PLAIN_MIN = 8
+OPT_LAND_SPECULATE = 9
 RIVER_PERSISTENT, RIVER_LAUNCHES, RIVER_GROUPED = 0, 1, 2
 LAND_AUTO, LAND_GENERAL = 0, 1
 ROW_NODE, ROW_REACH = 0, 1

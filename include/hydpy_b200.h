@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 4
+#define HB_ABI_VERSION 5
 
 /* ---- return codes ------------------------------------------------------------------------------------------ */
 #define HB_OK 0
@@ -340,6 +340,14 @@ int hb_select_series(hb_engine* h, int series, int on);
  * reaches (musk_classic, at most 32 segments, fed by such reaches only); headwater reaches always are.  The rest of the
  * network — the narrow, deep part of a river tree — runs in the persistent wavefront.  Same bits either way. */
 #define HB_OPT_RIVER_PLAIN_MIN 8
+/* HB_OPT_LAND_SPECULATE (0 | 1, default 1; read by the next hb_set_land): hland_96 elements with a finite SMax (without
+ * capillary flux) take the fast path SPECULATIVELY while no series is recorded.  As long as no snow class of any zone
+ * exceeds its limit, Calc_SPL_WCL_SP_WC_V1 / Calc_SPG_WCG_SP_WC_V1 (ref: hydpy/models/hland/hland_model.py:584-605,
+ * 876-969) change nothing: all losses, gains and excesses are zero.  The zone kernel watches the limit; an element whose
+ * snow exceeds it somewhere in a window gets the conditions of the window's start back and repeats the window in the
+ * general kernel, which redistributes (hb_timing.spec_reruns counts these element-windows).  0: such elements always run
+ * the general kernel (round 1's behaviour). */
+#define HB_OPT_LAND_SPECULATE 9
 enum hb_mct_series {
   HB_MS_REFERENCEDISCHARGE = 0, HB_MS_REFERENCEWATERDEPTH, HB_MS_WETTEDAREA, HB_MS_SURFACEWIDTH, HB_MS_CELERITY,
   HB_MS_CORRECTINGFACTOR, HB_MS_COEFFICIENT1, HB_MS_COEFFICIENT2, HB_MS_COEFFICIENT3, HB_MS_COURANTNUMBER,
@@ -478,6 +486,8 @@ typedef struct hb_timing {
   int64_t elem_warpsteps;      /* warp-steps (32 elements x 1 step) of the element kernel                               */
   int64_t elem_warpsteps_run;  /* ... in which at least one lane ran the chain                                          */
   int64_t n_fused;             /* elements whose zone terms the zone kernel added itself (HB_OPT_LAND_FUSE), last run    */
+  int64_t n_spec;              /* elements with a finite SMax on the speculative fast path (HB_OPT_LAND_SPECULATE), last run */
+  int64_t spec_reruns;         /* ... element-windows the general kernel had to repeat (snow above SMax somewhere)       */
 } hb_timing;
 /* Times and launch counts are SUMS over all runs since the previous hb_get_timing call (which resets them); after a
  * single hb_run they are that run's figures.  Waits for pending asynchronous work. */

@@ -48,6 +48,31 @@ def compare(res, ref, what, series=()):
         assert_close(res["series"][name], ref["series"][name], f"{what}: series {name}")
 
 
+def check_window_splitting(problem, engine, window, keys, states=False):
+    """Splitting the period into windows must not change a single bit (states stay on the device) — with one documented
+    exception: elements with a finite SMax on the speculative fast path (`HB_OPT_LAND_SPECULATE`) run a window in which
+    their snow exceeds the limit in the general kernel (the reference's operations) and every other window on the fast path
+    (reciprocal multiplications, <= 1 ulp per operation), so where the windows are cut decides the last bits.  Bit
+    equality is therefore demanded with the speculation off, the parity bar of the unsplit run with it on."""
+    engine.set_land_speculate(False)
+    try:
+        a = run_problem(problem, engine)
+        b = run_problem(problem, engine, window=window)
+    finally:
+        engine.set_land_speculate(True)
+    for key in keys:
+        assert np.array_equal(a[key], b[key], equal_nan=True), f"window splitting changes {key}"
+    if states:
+        for n in a["states"].NAMES:
+            assert np.array_equal(getattr(a["states"], n), getattr(b["states"], n), equal_nan=True), n
+    c = run_problem(problem, engine, window=window)
+    for key in keys:
+        assert_close(c[key], a[key], f"window splitting with speculation: {key}")
+    if states:
+        for n in a["states"].NAMES:
+            assert_close(getattr(c["states"], n), getattr(a["states"], n), f"window splitting with speculation: final {n}")
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_ragged_problem_all_series(engine, seed):
     ne, nt = 150, 60
@@ -64,10 +89,7 @@ def test_random_ragged_problem_all_series(engine, seed):
     # without series the eligible elements take the fast path: same bar against the oracle
     res1 = run_problem(problem, engine)
     compare(res1, ref, f"seed {seed} (no series)")
-    # splitting the period into windows must not change a single bit (states stay on the device)
-    res2 = run_problem(problem, engine, window=17)
-    for key in ("land_rows", "node_rows", "reach_out", "discharge"):
-        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+    check_window_splitting(problem, engine, 17, ("land_rows", "node_rows", "reach_out", "discharge"))
 
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -88,11 +110,7 @@ def test_random_ragged_problem_with_sibling_models(engine, seed):
     assert np.isnan(res["series"]["dp"][:, np.repeat(land.model, np.diff(land.zone_ptr)) != layout.MODEL_HLAND_96P]).all()
     res1 = run_problem(problem, engine)
     compare(res1, ref, f"siblings seed {seed} (no series)")
-    res2 = run_problem(problem, engine, window=13)
-    for key in ("land_rows", "node_rows", "reach_out", "discharge"):
-        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
-    for n in res1["states"].NAMES:
-        assert np.array_equal(getattr(res1["states"], n), getattr(res2["states"], n), equal_nan=True), n
+    check_window_splitting(problem, engine, 13, ("land_rows", "node_rows", "reach_out", "discharge"), states=True)
 
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -159,9 +177,7 @@ def test_nan_forcing_in_a_mixed_basin(engine):
     res1 = run_problem(problem, engine)
     compare(res1, ref, "NaN forcing (no series)")
     assert_close(res1["mct_states"], ref["mct_states"], "NaN forcing (no series): musk_mct factors")
-    res2 = run_problem(problem, engine, window=11)
-    for key in ("land_rows", "node_rows", "reach_out", "discharge", "mct_states"):
-        assert np.array_equal(res1[key], res2[key], equal_nan=True), f"window splitting changes {key}"
+    check_window_splitting(problem, engine, 11, ("land_rows", "node_rows", "reach_out", "discharge", "mct_states"))
 
 
 def test_long_reaches_more_than_32_segments(engine):
@@ -814,3 +830,98 @@ def test_results_do_not_depend_on_where_an_element_sits():
     assert np.array_equal(s0.uz[perm], s1.uz) and np.array_equal(s0.lz[perm], s1.lz)
     zone_of = np.concatenate([np.arange(land.zone_ptr[e], land.zone_ptr[e + 1]) for e in perm])
     assert np.array_equal(s0.sm[zone_of], s1.sm) and np.array_equal(s0.ic[zone_of], s1.ic)
+
+
+def test_finite_smax_runs_the_fast_path_speculatively():
+    """Finite SMax without capillary flux (ref: hland_model.py:584-605 Calc_SPL_WCL_SP_WC_V1, 876-969
+    Calc_SPG_WCG_SP_WC_V1): while no snow class exceeds its limit both methods leave every state alone, so such elements
+    take the fast path and its zone kernel watches the limit (`HB_OPT_LAND_SPECULATE`).  Elements whose snow exceeds it
+    somewhere in a window repeat that window in the general kernel from the window's initial conditions.  Two consecutive
+    windows (conditions carried on the device) against the oracle, limits of 5-40 mm, three times that and out of reach
+    side by side under snowfall: exactly the element-windows in which the oracle sees a loss are repeated; with the
+    speculation switched off the general kernel runs as in round 1; while series are recorded the elements stay with the
+    general kernel."""
+    import copy
+
+    from hydpy_b200.abi import RiverBundle
+
+    ne, nt = 900, 60
+    land, states0 = random_land(ne, seed=31, snowlimit_fraction=0.85, fast_fraction=0.0, recstep=10)
+    ZP = layout.ZP
+    land = copy.deepcopy(land)
+    land.zpar[ZP["cflux"]] = 0.0                             # (capillary flux would send the elements to other kernels)
+    factor = np.random.default_rng(3).choice([1.0, 3.0, 1000.0], size=ne)
+    nz = np.diff(land.zone_ptr)
+    land.zpar[ZP["smax"]] = land.zpar[ZP["smax"]] * np.repeat(factor, nz)
+    forcing, doy = random_forcing(2 * nt, ne, seed=5)
+    forcing[1] -= 6.0                                        # snowfall, melt and refreezing side by side
+    live = np.isfinite(land.zp("smax")) & (land.zonetype != layout.ILAKE)        # (lake zones carry no snow)
+    limited = np.array([live[land.zone_ptr[e]:land.zone_ptr[e + 1]].any() for e in range(ne)])
+    windows = [(np.ascontiguousarray(forcing[:, w * nt:(w + 1) * nt]), doy[w * nt:(w + 1) * nt]) for w in range(2)]
+    names = ("sp", "wc", "spl", "wcl", "spg", "wcg")
+
+    st_ref = states0.copy()
+    q_ref, ser_ref, expected = [], None, 0
+    touchy = np.zeros(ne, bool)
+    for f, d in windows:
+        q, ser_ref = oracle.land_run(land, st_ref, f, d, threads=4, series=names)
+        q_ref.append(q)
+        loss = (ser_ref["spl"] + ser_ref["wcl"]) > 0.0
+        expected += sum(bool(loss[:, land.zone_ptr[e]:land.zone_ptr[e + 1]].any()) for e in range(ne))
+        # a snow pack of less than 1e-9 mm in the REFERENCE's own run (the rounding residue of an interception storage at
+        # its capacity, frozen): evap_aet_hbv96's snow-cover indicator (sp > 0) turns it into a third less soil
+        # evapotranspiration of a three-class zone, so the last bit of the precipitation decides about 1e-7 of the soil
+        # moisture — the fast path's reciprocal multiplications (<= 1 ulp) may fall on the other side
+        residue = (ser_ref["sp"] > 0.0) & (ser_ref["sp"] < 1e-9)
+        touchy |= np.array([bool(residue[:, land.snow_ptr[e]:land.snow_ptr[e + 1]].any()) for e in range(ne)])
+    q_ref = np.concatenate(q_ref, axis=1)
+    assert 600 < limited.sum() < ne and 300 < expected < 2 * limited.sum() - 300     # both outcomes well represented
+    assert touchy.sum() < 0.06 * ne
+    firm = ~touchy
+    zone_firm, snow_firm = np.repeat(firm, nz), np.repeat(firm, np.diff(land.snow_ptr))
+    uh_firm = np.repeat(firm, np.diff(land.uh_ptr))
+
+    def engine_two_windows(eng, series=()):
+        eng.set_land(land)
+        eng.set_land_states(states0)
+        eng.set_river(RiverBundle.empty(0))
+        out = []
+        eng.set_forcing(*windows[0])
+        eng.run(land=True, river=False)
+        out.append(eng.get_land_outflow())
+        eng.select_series(list(series))
+        eng.set_forcing(*windows[1])
+        eng.run(land=True, river=False)
+        out.append(eng.get_land_outflow())
+        ser = {name: eng.get_series(name) for name in series}
+        eng.select_series([])
+        return np.concatenate(out, axis=1), eng.get_land_states(), eng.timing(), ser
+
+    def check(what, q, st):
+        assert_close(q[firm], q_ref[firm], f"{what}: land outflow of both windows")
+        assert_close(q[touchy], q_ref[touchy], f"{what}: land outflow of both windows (residual snow)", rtol=1e-3)
+        for n in st_ref.NAMES:
+            a, b = getattr(st, n), getattr(st_ref, n)
+            mask = {ne: firm, len(zone_firm): zone_firm, len(snow_firm): snow_firm, len(uh_firm): uh_firm}.get(len(b))
+            if mask is None or len(b) == 0:
+                continue
+            assert_close(a[mask], b[mask], f"{what}: final {n}")
+            assert_close(a[~mask], b[~mask], f"{what}: final {n} (residual snow)", rtol=1e-3, atol=1e-6)
+
+    with Engine(0) as eng:
+        q, st, tm, _ = engine_two_windows(eng)
+        assert tm["n_spec"] == limited.sum() and tm["n_fast"] == ne, tm
+        assert tm["spec_reruns"] == expected, (tm["spec_reruns"], expected)
+        check("speculative fast path", q, st)
+        # series recorded in the second window: the general kernel takes the limited elements there, with their series
+        q, st, tm, ser = engine_two_windows(eng, series=names)
+        assert tm["n_spec"] == 0
+        check("series in window 2", q, st)
+        for name in names:
+            mask = zone_firm if ser_ref[name].shape[1] == len(zone_firm) else snow_firm
+            assert_close(ser[name][:, mask], ser_ref[name][:, mask], f"series in window 2: {name}")
+    with Engine(0) as eng:
+        eng.set_land_speculate(False)
+        q, st, tm, _ = engine_two_windows(eng)
+        assert tm["n_spec"] == 0 and tm["spec_reruns"] == 0 and tm["n_fast"] == ne - limited.sum(), tm
+        check("speculation off", q, st)

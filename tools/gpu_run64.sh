@@ -1,0 +1,2 @@
+O=gpurun_out/r05e; mkdir -p $O
+timeout 600 python -m pytest tests -m gpu -x -q -k "finite_smax" > $O/pytest_spec.log 2>&1; echo "rc=$?" >> $O/pytest_spec.log; tail -30 $O/pytest_spec.log | cut -c1-400
