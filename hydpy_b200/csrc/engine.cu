@@ -1921,7 +1921,7 @@ static int run_land(hb_engine* h) {
     v.counters = h->d_counters.p;
     v.spec_flag = h->d_spec_flag.p;
     if (use_spec) {
-      // conditions of the window's start for the elements that will have to repeat it; flags down
+      // conditions of the window's start for the elements that will have to repeat it
       const size_t zs_ = (size_t)h->zmax * ep, B = sizeof(double);
       HB_CUDA(h, h->d_snap_ic.reserve(zs_)); HB_CUDA(h, h->d_snap_sm.reserve(zs_));
       HB_CUDA(h, h->d_snap_sp.reserve(zs_ * h->cmax)); HB_CUDA(h, h->d_snap_wc.reserve(zs_ * h->cmax));
@@ -1935,7 +1935,7 @@ static int run_land(hb_engine* h) {
       HB_CUDA(h, cudaMemcpyAsync(h->d_snap_lz.p, h->d_lz.p, (size_t)ep * B, cudaMemcpyDeviceToDevice, h->stream));
       if (h->umax > 0)
         HB_CUDA(h, cudaMemcpyAsync(h->d_snap_quh.p, h->d_quh.p, (size_t)h->umax * ep * B, cudaMemcpyDeviceToDevice, h->stream));
-      HB_CUDA(h, cudaMemsetAsync(h->d_spec_flag.p, 0, (size_t)ep * sizeof(int32_t), h->stream));
+      // (the flags are 0 or — left by the repetition of the previous window — 2 here)
     }
     // [storage | ordinate][thread] staging of the runoff concentration: the rconc_nash cascade of a step, the rconc_uh
     // memory for the whole launch
@@ -2249,7 +2249,7 @@ static int run_land(hb_engine* h) {
       h->mark(HB_K_OTHER);
       spec_restore_kernel<<<sgrid, 128, 0, h->stream>>>(h->d_spec_list.p, n_spec, h->d_spec_flag.p, ep, h->zmax, h->d_nz.p,
                                                         h->d_nc.p, h->d_nu.p, sn, h->d_counters.p);
-      d.n_list = n_spec; d.elist = h->d_spec_list.p; d.only_flagged = h->d_spec_flag.p;
+      d.n_list = n_spec; d.elist = h->d_spec_list.p; d.only_flagged = h->d_spec_flag.p; d.flag_out = h->d_spec_flag.p;
       land_kernel<false, HB_MODEL_HLAND_96><<<sgrid, 128, 0, h->stream>>>(d);
       h->mark(HB_K_GENERAL);
       h->timing.land_launches += 2;

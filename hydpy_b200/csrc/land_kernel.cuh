@@ -111,6 +111,8 @@ struct LandDev {
   const int32_t* elist;    // [n_list] their indices (NULL: elements 0..n_list-1)
   const int32_t* only_flagged;  // [E_pad] or NULL: work on the listed elements whose flag is set only (speculative fast
                                 // path: the elements whose snow exceeded SMax in this window, states restored beforehand)
+  int32_t* flag_out;            // [E_pad] or NULL: … and leave 2 there if the element lost snow to Calc_SPL_WCL_SP_WC_V1 in
+                                // this window (it then skips the speculation of the next window), else 0
   // structure
   const int32_t* nz;       // [E_pad]
   const int32_t* nc;       // [E_pad]
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
                beta_last = d.ke[KE_BETA_LAST * ep + e];
   const double dnc = (double)nc;
   const bool snowlimit = (einfo & HB_EI_SNOWLIMIT) != 0;
+  bool lost = false;       // some snow class exceeded its SMax in this window
   const int64_t zone0 = SERIES ? d.zone0[e] : 0, snow0 = SERIES ? d.snow0[e] : 0;
   double uz = d.uz[e], lz = d.lz[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;
@@ -405,6 +408,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
             if (!isinf(smax)) {
               const double snw = sp + wc, excess = snw - smax;
               if (excess > 0.0) {
+                lost = true;
                 const double excess_sp = excess * sp / snw, excess_wc = excess * wc / snw;
                 spl_k += excess_sp / dnc;
                 wcl_k += excess_wc / dnc;
@@ -933,6 +937,7 @@ __global__ void __launch_bounds__(128, 4) land_kernel(const LandDev d) {
     SERE(HB_S_PERC, perc_sum); SERE(HB_S_Q0, q0_sum); SERE(HB_S_Q1, q1); SERE(HB_S_INRC, inrc);
     SERE(HB_S_OUTRC, outrc); SERE(HB_S_RT, outrc); SERE(HB_S_QT, qt); SERE(HB_S_UZ, uz); SERE(HB_S_LZ, lz);
   }
+  if (d.flag_out) d.flag_out[e] = lost ? 2 : 0;
   d.uz[e] = uz;
   d.lz[e] = lz;
   if (MODEL == HB_MODEL_HLAND_96P) { d.ex1[e] = sg2; d.ex2[e] = sg3; }

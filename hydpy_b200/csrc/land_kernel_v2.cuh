@@ -105,7 +105,9 @@ struct LandV2Dev {
   double* ex2;             // [E_pad] hland_96p sg3
   // what the kernels actually executed (hb_get_timing): see enum below; one atomicAdd per warp and counter at kernel end
   unsigned long long* counters;
-  int32_t* spec_flag;      // [E_pad] set by the zone kernel when a snow class of a HB_EI_SPEC element exceeded its SMax
+  int32_t* spec_flag;      // [E_pad] HB_EI_SPEC elements: 1 = set by the zone kernel when a snow class exceeded its SMax in this
+                           // window; 2 = left by the general kernel's repetition of the PREVIOUS window when the element lost
+                           // snow there (the fast path then skips the element: it would only be repeated again); else 0
 };
 
 // slots of LandV2Dev::counters
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
   // finite SMax (hland_96 only, never in a fused group): the general step below watches the limit (see HB_EI_SPEC)
   const bool spec = ZW == 0 && MODEL == HB_MODEL_HLAND_96 && (einfo & HB_EI_SPEC) != 0;
   if (ZW == 0 && (ncls > 1 || spec) && d.skip_classes) return;
+  // (2: the element lost snow at its limit in the previous window — it goes straight to the general kernel in this one)
+  if (spec && d.spec_flag[e] == 2) return;
 
   const double* kzk = d.kz + (int64_t)k * KZ_COUNT * ep + e;
 #define KZ(name) kzk[(int64_t)(name) * ep]
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(ZoneGeom<ZW>::threads, MODEL == HB_MODEL_HLAND
 #undef KZX
   d.ic[slot] = ic; d.sm[slot] = sm; d.sp[slot] = sp; d.wc[slot] = wc;
   if (MODEL != HB_MODEL_HLAND_96) { d.zx1[slot] = zx1; d.zx2[slot] = zx2; }
-  if (exceeded) d.spec_flag[e] = 1;   // (every zone of the element that saw it stores the same value)
+  if (exceeded) d.spec_flag[e] = 1;   // (every zone of the element that saw it stores the same value; never beside a 2)
 }
 
 // Speculative fast path (HB_EI_SPEC): the elements of `list` whose flag is set get the conditions of the window's start
@@ -949,6 +953,7 @@ __global__ void __launch_bounds__(64, HB_ELEM_BLOCKS) element_kernel(const LandV
   if (!(einfo & HB_EI_FAST) || HB_EI_MODEL(einfo) != MODEL) return;
   if (((einfo & HB_EI_FUSED) != 0 && d.fused != 0) != FUSED) return;
   if (MODEL == HB_MODEL_HLAND_96 && d.skip_classes && (d.nc[e] > 1 || (einfo & HB_EI_SPEC))) return;
+  if (MODEL == HB_MODEL_HLAND_96 && !FUSED && (einfo & HB_EI_SPEC) && d.spec_flag[e] == 2) return;
   const int64_t ep = d.e_pad;
   const int nz = d.nz[e], nu = d.nu[e], recstep = d.recstep[e];
   const int nash_steps = d.nash_steps ? d.nash_steps[e] : 0;

@@ -345,7 +345,11 @@ int hb_select_series(hb_engine* h, int series, int on);
  * exceeds its limit, Calc_SPL_WCL_SP_WC_V1 / Calc_SPG_WCG_SP_WC_V1 (ref: hydpy/models/hland/hland_model.py:584-605,
  * 876-969) change nothing: all losses, gains and excesses are zero.  The zone kernel watches the limit; an element whose
  * snow exceeds it somewhere in a window gets the conditions of the window's start back and repeats the window in the
- * general kernel, which redistributes (hb_timing.spec_reruns counts these element-windows).  0: such elements always run
+ * general kernel, which redistributes (hb_timing.spec_reruns counts these element-windows); if the general kernel saw a
+ * loss, the element skips the speculation of the next window and goes straight to the general kernel there.  Which
+ * kernel computes a window thus depends on where the windows are cut: the fast path multiplies by host-folded reciprocals
+ * where the general kernel divides (<= 1 ulp per operation), so splitting a period differently can change the last bits of
+ * such an element (never more than the parity bar); with 0 every split gives the same bits.  0: such elements always run
  * the general kernel (round 1's behaviour). */
 #define HB_OPT_LAND_SPECULATE 9
 enum hb_mct_series {

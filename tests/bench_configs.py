@@ -66,7 +66,8 @@ def measure(eng: Engine, name: str, land, states, river, discharge, forcings, do
         "window_steps": nt, "reps": reps, "land_ms": land_ms, "land_ms_reps": [round(t["land_ms"], 3) for t in dev], "zone_ms": float(np.mean([t["zone_ms"] for t in dev])),
         "element_ms": float(np.mean([t["element_ms"] for t in dev])),
         "general_ms": float(np.mean([t["general_ms"] for t in dev])), "river_ms": river_ms if route else None,
-        "n_fast": int(dev[-1]["n_fast"]), "value": zs / (total * 1e-3), "unit": "zone-timesteps/s (device, synchronous windows)",
+        "n_fast": int(dev[-1]["n_fast"]), "n_spec": int(dev[-1]["n_spec"]),
+        "spec_reruns_per_window": float(np.mean([t["spec_reruns"] for t in dev])), "value": zs / (total * 1e-3), "unit": "zone-timesteps/s (device, synchronous windows)",
         "e2e_ms": float(np.median(e2e)), "e2e_value": zs / (float(np.median(e2e)) * 1e-3),
         "finite": bool(np.isfinite(rows).all()), "mean_discharge": float(rows.mean()),
     }
@@ -144,6 +145,27 @@ def main() -> None:
             worst = check_sample(eng, land, states, fs[0][:, :72], ds[0][:72])
             out = measure(eng, case, land, states, river, discharge, list(fs), list(ds), route=True, reps=args.reps,
                           note=f"configs[3] basin with {case} + rconc_nash elements (sibling instances of the fast path)")
+        elif case in ("smax_high", "smax_low", "smax_high_general", "smax_low_general"):
+            # finite SMax on every zone (ref: hland_model.py:584-605, 876-969) under a winter forcing (12 K colder: the
+            # snow packs grow by about 25 mm per window): speculative fast path with a limit the packs do not reach during
+            # the run (400 mm) and one most elements reach after a few windows (60 mm: the worst case — fast path AND a
+            # repetition in the general kernel; an element that lost snow goes straight to the general kernel in the next
+            # window), each against the general kernel alone (HB_OPT_LAND_SPECULATE = 0, round 1's way)
+            from hydpy_b200 import layout
+
+            land, states = synth.make_land(args.elements, "1h")
+            land.zpar[layout.ZP["smax"]] = 60.0 if case.startswith("smax_low") else 400.0
+            river, discharge = synth.make_tree_river(args.elements, "1h", levels=200)
+            fs, ds = zip(*[synth.make_forcing(240, "1h", t0=240 * i) for i in range(2)])
+            for f in fs:
+                f[1] -= 12.0
+            eng.set_land_speculate(not case.endswith("_general"))
+            worst = check_sample(eng, land, states, fs[0][:, :72], ds[0][:72])
+            out = measure(eng, case, land, states, river, discharge, list(fs), list(ds), route=True, reps=args.reps,
+                          note=f"configs[3] basin, winter, SMax = {land.zpar[layout.ZP['smax']][0]:.0f} mm on every zone: " +
+                               ("general kernel (speculation off)" if case.endswith("_general") else
+                                "speculative fast path (element-windows with snow above the limit repeated by the general kernel)"))
+            eng.set_land_speculate(True)
         else:
             raise SystemExit(f"unknown case {case}")
         out["oracle_sample_max_rel_deviation"] = worst
